@@ -1,0 +1,150 @@
+/*
+ * mnemo_cuda.h — C ABI of libmnemo_cuda.so, the sm_100a implementation of mnemophonix's
+ * fingerprint-and-match hot path.
+ *
+ * Plain C: pointers, sizes and int return codes only.  Return codes are the reference's
+ * (errors.h:5-29): 0 SUCCESS, -1 MEMORY_ERROR, -2 CANNOT_READ_FILE, -3 DECODING_ERROR,
+ * -4 UNSUPPORTED_WAVE_FORMAT, -5 FILE_TOO_SMALL, -6 NOT_A_WAVE_FILE, -7 NO_MATCH_FOUND;
+ * CUDA failures map to -1 (allocation) or -3 (anything else) and mnemo_last_error() holds
+ * the text.  There is no CPU fallback: every entry point fails if no sm_100 device is there.
+ *
+ * What each group replaces in the reference:
+ *   mnemo_batch_* / mnemo_index_pcm_batch   read_samples' downmix loop (wav.c:358-375),
+ *        resample (resample.c:47-62), normalize (audionormalizer.c:5-32),
+ *        build_spectral_images (spectralimages.c:126-221), apply_Haar_transform (haar.c:85-108),
+ *        build_raw_fingerprints (rawfingerprints.c:103-144), build_signatures (minhash.c:31-54),
+ *        i.e. the body of generate_fingerprint (fingerprinting.c:10-78) after the WAV header.
+ *   mnemo_index_samples                     generate_fingerprint_from_samples (fingerprinting.c:81-109)
+ *   mnemo_db_* / mnemo_search_batch         create_hash_tables / get_matches (lsh.c:55-112) and
+ *        search (search.c:110-193)
+ * The reference-named drop-in functions themselves (generate_fingerprint, create_hash_tables,
+ * search, ...) live in libmnemophonix.so (mnemophonix_b200/host/), which is thin C over this ABI.
+ */
+#ifndef MNEMO_CUDA_H
+#define MNEMO_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MNEMO_SIGNATURE_LENGTH 100
+
+typedef struct mnemo_ctx mnemo_ctx;
+typedef struct mnemo_batch mnemo_batch;
+typedef struct mnemo_db mnemo_db;
+
+/* One context per (host thread or process, device).  `stream` is a cudaStream_t to run on
+ * (NULL = the context creates its own non-blocking stream).  Computes the Hann window, FIR
+ * taps, FFT twiddles and band edges with the host's libm — the same calls the reference
+ * makes (hannwindow.c:10, resample.c:27-35, fft.c:49-51, logbins.c:44-55) — and uploads them. */
+int mnemo_create(int device, void* stream, mnemo_ctx** out);
+void mnemo_destroy(mnemo_ctx* ctx);
+const char* mnemo_last_error(const mnemo_ctx* ctx);
+/* Diagnostics: which glibc logf variant (0 baseline, 1 fma) the device code mirrors, and how
+ * many of the probe inputs matched the host's logf when the context was created. */
+int mnemo_logf_variant(const mnemo_ctx* ctx, uint32_t* probes, uint32_t* matched);
+
+/* ---- sizes (App. C of SURVEY.md; spectralimages.c:37-49) ---- */
+uint32_t mnemo_samples_5512(uint64_t n_pcm_frames); /* n/8 */
+uint32_t mnemo_frames(uint32_t n_samples_5512);     /* 0 if too small */
+uint32_t mnemo_images(uint32_t n_samples_5512);     /* 0 if too small */
+
+/* ---- indexing ---- */
+typedef struct mnemo_track {
+  const void* pcm;      /* interleaved little-endian int16, host memory (may be NULL for batch_create) */
+  uint64_t n_frames;    /* sample frames (data bytes / block align, wav.c:347) */
+  uint32_t channels;    /* >= 1 */
+  uint32_t reserved;
+} mnemo_track;
+
+/* Staged form: allocate device buffers for a set of tracks, upload PCM, run the kernels
+ * (asynchronously on the context's stream), download.  A batch can be re-uploaded and re-run. */
+int mnemo_batch_create(mnemo_ctx* ctx, const mnemo_track* tracks, uint32_t n_tracks, mnemo_batch** out);
+void mnemo_batch_destroy(mnemo_batch* b);
+int mnemo_batch_upload(mnemo_batch* b, const mnemo_track* tracks); /* H2D of every track's PCM, async */
+int mnemo_batch_run(mnemo_batch* b);                               /* kernels only, async */
+int mnemo_batch_sync(mnemo_batch* b);
+uint64_t mnemo_batch_max_signatures(const mnemo_batch* b);         /* = total spectral images */
+uint32_t mnemo_batch_kernel_launches(const mnemo_batch* b);        /* launches issued by one run */
+/* After run (+sync is implied): signatures of all tracks, compacted and concatenated in track
+ * order, into sigs_out (capacity in signatures); n_sigs[t] and status[t] per track (0 or
+ * FILE_TOO_SMALL). */
+int mnemo_batch_download(mnemo_batch* b, uint8_t* sigs_out, uint64_t cap_signatures, uint32_t* n_sigs,
+                         int32_t* status);
+/* Intermediates for stage-level parity tests.  what: 0 = 5512 Hz samples before normalisation
+ * (float[n/8]), 1 = rms (float[1]), 2 = band energies (float[n_frames*32]),
+ * 3 = per-image keep flags (u8[n_images]), 4 = dense signatures (u8[n_images*100]),
+ * 5 = raw fingerprint bits (u8[n_images*1024], only if debug taps enabled),
+ * 6 = scaled spectral images, 7 = Haar coefficients (float[n_images*4096], debug taps),
+ * 8 = float32 sequential sum of squares (float[1]).  Returns bytes written or <0. */
+int64_t mnemo_batch_read(mnemo_batch* b, int what, uint32_t track, void* dst, uint64_t dst_bytes);
+int mnemo_batch_enable_taps(mnemo_batch* b, int on);
+
+/* One-call form with host buffers: create + upload + run + download + destroy. */
+int mnemo_index_pcm_batch(mnemo_ctx* ctx, const mnemo_track* tracks, uint32_t n_tracks, uint8_t* sigs_out,
+                          uint64_t cap_signatures, uint32_t* n_sigs, int32_t* status);
+/* generate_fingerprint_from_samples (fingerprinting.c:81-109): samples already mono, 5512 Hz
+ * and normalised.  Returns 0 / FILE_TOO_SMALL / error; *n_sigs signatures written. */
+int mnemo_index_samples(mnemo_ctx* ctx, const float* samples, uint32_t n, uint8_t* sigs_out,
+                        uint64_t cap_signatures, uint32_t* n_sigs);
+
+/* ---- search ---- */
+/* Database = signatures of all entries concatenated in entry order; entry_start has
+ * n_entries+1 offsets.  `table_size` is lsh.c:61's size = total_signatures/2 over the WHOLE
+ * database (pass 0 to derive it from this shard alone); entry_base is the global index of the
+ * shard's first entry (database sharded across GPUs by contiguous entry ranges). */
+int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32_t* entry_start, uint32_t n_entries,
+                    uint32_t table_size, uint32_t entry_base, mnemo_db** out);
+void mnemo_db_destroy(mnemo_db* db);
+uint32_t mnemo_db_table_size(const mnemo_db* db);
+
+typedef struct mnemo_match {
+  int32_t entry;      /* matched entry (global index) or -7 */
+  float score;        /* sum of deep-check scores of that entry */
+  int32_t n_matches;
+} mnemo_match;
+
+/* get_matches (lsh.c:89-112) for one signature: (entry, signature) pairs in the order the
+ * reference's list is returned.  Returns the count (may exceed cap; only cap are written). */
+int64_t mnemo_db_get_matches(mnemo_db* db, const uint8_t* sig, uint32_t* pairs_out, uint64_t cap_pairs);
+
+/* search() (search.c:110-193) for a batch of queries.  query_start has n_queries+1 offsets into
+ * query_sigs.  out[q] receives the reference's return value and that entry's (score, n_matches).
+ * stats (optional, 2 values): total probed list nodes L and deep checks D. */
+int mnemo_search_batch(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
+                       uint32_t n_queries, mnemo_match* out, uint64_t* stats);
+
+/* Sharded search: per-query candidate records of THIS shard, to be merged across shards
+ * (concatenate the records of all shards, e.g. with an NCCL all-gather) and finished with
+ * mnemo_search_finish.  See DESIGN.md "search, multi-GPU". */
+typedef struct mnemo_cand {
+  uint32_t query;
+  int32_t entry;      /* global entry index */
+  float score;
+  int32_t n_matches;
+} mnemo_cand;
+typedef struct mnemo_lastgroup {
+  uint32_t has;       /* this shard saw >=1 candidate for the query signature */
+  uint32_t entry;     /* greatest (entry, sig) among this shard's candidates ... */
+  uint32_t sig;
+  uint32_t hits;      /* ... its bucket-hit count ... */
+  uint32_t score;     /* ... and its deep-check score (0 if hits < 2) */
+} mnemo_lastgroup;
+int mnemo_search_shard(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
+                       uint32_t n_queries, mnemo_cand* cands, uint64_t cap_cands, uint64_t* n_cands,
+                       mnemo_lastgroup* last /* one per query signature */, uint64_t* stats);
+int mnemo_search_finish(const mnemo_cand* cands, uint64_t n_cands, const mnemo_lastgroup* last_all_shards,
+                        uint32_t n_shards, const uint32_t* query_start, uint32_t n_queries,
+                        uint32_t n_entries_total, mnemo_match* out);
+
+/* ---- self tests of the exact-arithmetic building blocks (run on the device) ---- */
+/* Compares the device logf against host logf for every float in [lo_bits, hi_bits]; returns the
+ * number of mismatches (or <0).  Used to pin the glibc logf mirror exhaustively over [1, 256]. */
+int64_t mnemo_selftest_logf(mnemo_ctx* ctx, uint32_t lo_bits, uint32_t hi_bits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

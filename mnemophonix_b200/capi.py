@@ -1,0 +1,242 @@
+"""ctypes binding of libmnemo_cuda.so (include/mnemo_cuda.h).
+
+This is plumbing for tests, bench and the torch.distributed drivers; the product is the
+shared library.  There is no CPU fallback: loading fails loudly if the library is not built,
+and every call fails if no sm_100 GPU is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libmnemo_cuda.so")
+SIG_LEN = 100
+
+ERRORS = {0: "SUCCESS", -1: "MEMORY_ERROR", -2: "CANNOT_READ_FILE", -3: "DECODING_ERROR",
+          -4: "UNSUPPORTED_WAVE_FORMAT", -5: "FILE_TOO_SMALL", -6: "NOT_A_WAVE_FILE", -7: "NO_MATCH_FOUND"}
+
+
+class MnemoError(RuntimeError):
+    pass
+
+
+class Track(C.Structure):
+    _fields_ = [("pcm", C.c_void_p), ("n_frames", C.c_uint64), ("channels", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class Match(C.Structure):
+    _fields_ = [("entry", C.c_int32), ("score", C.c_float), ("n_matches", C.c_int32)]
+
+
+class Cand(C.Structure):
+    _fields_ = [("query", C.c_uint32), ("entry", C.c_int32), ("score", C.c_float), ("n_matches", C.c_int32)]
+
+
+class LastGroup(C.Structure):
+    _fields_ = [("has", C.c_uint32), ("entry", C.c_uint32), ("sig", C.c_uint32), ("hits", C.c_uint32),
+                ("score", C.c_uint32)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MnemoError(f"{LIB_PATH} is not built (python -m mnemophonix_b200.build); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+        L.mnemo_create.argtypes = [i32, vp, C.POINTER(vp)]
+        L.mnemo_destroy.argtypes = [vp]
+        L.mnemo_last_error.argtypes = [vp]
+        L.mnemo_last_error.restype = C.c_char_p
+        L.mnemo_logf_variant.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
+        L.mnemo_samples_5512.argtypes = [u64]
+        L.mnemo_samples_5512.restype = u32
+        L.mnemo_frames.argtypes = [u32]
+        L.mnemo_frames.restype = u32
+        L.mnemo_images.argtypes = [u32]
+        L.mnemo_images.restype = u32
+        L.mnemo_batch_create.argtypes = [vp, C.POINTER(Track), u32, C.POINTER(vp)]
+        L.mnemo_batch_destroy.argtypes = [vp]
+        L.mnemo_batch_upload.argtypes = [vp, C.POINTER(Track)]
+        L.mnemo_batch_run.argtypes = [vp]
+        L.mnemo_batch_sync.argtypes = [vp]
+        L.mnemo_batch_max_signatures.argtypes = [vp]
+        L.mnemo_batch_max_signatures.restype = u64
+        L.mnemo_batch_kernel_launches.argtypes = [vp]
+        L.mnemo_batch_kernel_launches.restype = u32
+        L.mnemo_batch_download.argtypes = [vp, vp, u64, vp, vp]
+        L.mnemo_batch_read.argtypes = [vp, i32, u32, vp, u64]
+        L.mnemo_batch_read.restype = C.c_int64
+        L.mnemo_batch_enable_taps.argtypes = [vp, i32]
+        L.mnemo_index_pcm_batch.argtypes = [vp, C.POINTER(Track), u32, vp, u64, vp, vp]
+        L.mnemo_index_samples.argtypes = [vp, vp, u32, vp, u64, C.POINTER(u32)]
+        L.mnemo_selftest_logf.argtypes = [vp, u32, u32]
+        L.mnemo_selftest_logf.restype = C.c_int64
+        if hasattr(L, "mnemo_db_create"):
+            L.mnemo_db_create.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(vp)]
+            L.mnemo_db_destroy.argtypes = [vp]
+            L.mnemo_db_table_size.argtypes = [vp]
+            L.mnemo_db_table_size.restype = u32
+            L.mnemo_db_get_matches.argtypes = [vp, vp, vp, u64]
+            L.mnemo_db_get_matches.restype = C.c_int64
+            L.mnemo_search_batch.argtypes = [vp, vp, vp, u32, vp, vp]
+            L.mnemo_search_shard.argtypes = [vp, vp, vp, u32, vp, u64, C.POINTER(u64), vp, vp]
+            L.mnemo_search_finish.argtypes = [vp, u64, vp, u32, vp, u32, u32, vp]
+        _lib = L
+    return _lib
+
+
+def _tracks(pcms) -> tuple[C.Array, list]:
+    arr = (Track * max(len(pcms), 1))()
+    keep = []
+    for i, p in enumerate(pcms):
+        if isinstance(p, np.ndarray):
+            if p.dtype != np.int16 or p.ndim != 2 or not p.flags.c_contiguous:
+                raise ValueError("pcm must be C-contiguous int16 [n_frames, channels]")
+            keep.append(p)
+            arr[i] = Track(p.ctypes.data, p.shape[0], p.shape[1], 0)
+        else:  # (ptr, n_frames, channels): e.g. a pinned torch tensor's data_ptr()
+            ptr, n, ch = p
+            arr[i] = Track(ptr, n, ch, 0)
+    return arr, keep
+
+
+class Context:
+    """One mnemo_ctx.  stream: raw cudaStream_t handle (int) or None."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.h = C.c_void_p()
+        rc = lib().mnemo_create(device, C.c_void_p(stream) if stream else None, C.byref(self.h))
+        if rc != 0:
+            raise MnemoError(f"mnemo_create(device={device}) failed: {ERRORS.get(rc, rc)} (no GPU? no CPU fallback exists)")
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib().mnemo_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise MnemoError(f"{what}: {ERRORS.get(rc, rc)}: {lib().mnemo_last_error(self.h).decode()}")
+
+    def logf_variant(self):
+        p, m = C.c_uint32(), C.c_uint32()
+        v = lib().mnemo_logf_variant(self.h, C.byref(p), C.byref(m))
+        return v, p.value, m.value
+
+    def selftest_logf(self, lo_bits: int, hi_bits: int) -> int:
+        return lib().mnemo_selftest_logf(self.h, lo_bits, hi_bits)
+
+    # -- indexing -------------------------------------------------------------------
+    def index_pcm_batch(self, pcms):
+        """Host buffers in, per-track signature arrays out (list of [n,100] u8) + status list."""
+        arr, keep = _tracks(pcms)
+        cap = sum(int(lib().mnemo_images(lib().mnemo_samples_5512(arr[i].n_frames))) for i in range(len(pcms)))
+        sigs = np.empty((max(cap, 1), SIG_LEN), np.uint8)
+        n = np.zeros(max(len(pcms), 1), np.uint32)
+        st = np.zeros(max(len(pcms), 1), np.int32)
+        rc = lib().mnemo_index_pcm_batch(self.h, arr, len(pcms), sigs.ctypes.data, cap, n.ctypes.data, st.ctypes.data)
+        self._check(rc, "mnemo_index_pcm_batch")
+        return _split(sigs, n[:len(pcms)]), st[:len(pcms)].tolist()
+
+    def index_samples(self, samples: np.ndarray):
+        s = np.ascontiguousarray(samples, np.float32)
+        cap = int(lib().mnemo_images(len(s)))
+        sigs = np.empty((max(cap, 1), SIG_LEN), np.uint8)
+        n = C.c_uint32(0)
+        rc = lib().mnemo_index_samples(self.h, s.ctypes.data, len(s), sigs.ctypes.data, cap, C.byref(n))
+        if rc not in (0, -5):
+            self._check(rc, "mnemo_index_samples")
+        return rc, sigs[:n.value].copy()
+
+    def batch(self, pcms) -> "Batch":
+        return Batch(self, pcms)
+
+
+def _split(sigs: np.ndarray, counts) -> list:
+    out, o = [], 0
+    for c in counts:
+        out.append(sigs[o:o + int(c)].copy())
+        o += int(c)
+    return out
+
+
+class Batch:
+    READ_DTYPES = {0: np.float32, 1: np.float32, 2: np.float32, 3: np.uint8, 4: np.uint8, 5: np.uint8,
+                   6: np.float32, 7: np.float32, 8: np.float32}
+
+    def __init__(self, ctx: Context, pcms):
+        self.ctx = ctx
+        self.arr, self._keep = _tracks(pcms)
+        self.n = len(pcms)
+        self.h = C.c_void_p()
+        ctx._check(lib().mnemo_batch_create(ctx.h, self.arr, self.n, C.byref(self.h)), "mnemo_batch_create")
+        self.cap = int(lib().mnemo_batch_max_signatures(self.h))
+
+    def close(self):
+        if self.h:
+            lib().mnemo_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, pcms=None):
+        if pcms is not None:
+            self.arr, self._keep = _tracks(pcms)
+        self.ctx._check(lib().mnemo_batch_upload(self.h, self.arr), "mnemo_batch_upload")
+
+    def run(self):
+        self.ctx._check(lib().mnemo_batch_run(self.h), "mnemo_batch_run")
+
+    def sync(self):
+        self.ctx._check(lib().mnemo_batch_sync(self.h), "mnemo_batch_sync")
+
+    def launches(self) -> int:
+        return int(lib().mnemo_batch_kernel_launches(self.h))
+
+    def enable_taps(self, on=True):
+        self.ctx._check(lib().mnemo_batch_enable_taps(self.h, 1 if on else 0), "mnemo_batch_enable_taps")
+
+    def download(self, out: np.ndarray | None = None, out_ptr: int | None = None):
+        n = np.zeros(max(self.n, 1), np.uint32)
+        st = np.zeros(max(self.n, 1), np.int32)
+        if out_ptr is None:
+            if out is None:
+                out = np.empty((max(self.cap, 1), SIG_LEN), np.uint8)
+            out_ptr = out.ctypes.data
+        rc = lib().mnemo_batch_download(self.h, out_ptr, self.cap, n.ctypes.data, st.ctypes.data)
+        self.ctx._check(rc, "mnemo_batch_download")
+        return out, n[:self.n], st[:self.n]
+
+    def signatures(self):
+        out, n, st = self.download()
+        return _split(out, n), st.tolist()
+
+    def read(self, what: int, track: int) -> np.ndarray:
+        d = self.arr[track]
+        n5 = int(lib().mnemo_samples_5512(d.n_frames))
+        nf = int(lib().mnemo_frames(n5))
+        ni = int(lib().mnemo_images(n5))
+        count = {0: n5, 1: 1, 2: nf * 32, 3: ni, 4: ni * 100, 5: ni * 1024, 6: ni * 4096, 7: ni * 4096, 8: 1}[what]
+        buf = np.empty(max(count, 1), self.READ_DTYPES[what])
+        got = lib().mnemo_batch_read(self.h, what, track, buf.ctypes.data, buf.nbytes)
+        if got < 0:
+            raise MnemoError(f"mnemo_batch_read({what}) failed: {got}: {lib().mnemo_last_error(self.ctx.h).decode()}")
+        return buf[:count]

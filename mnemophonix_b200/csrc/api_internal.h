@@ -1,0 +1,44 @@
+// api_internal.h — private definitions behind the opaque handles of include/mnemo_cuda.h.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+struct mnemo_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  mnemo::Tables h_tables;
+  mnemo::Tables* d_tables = nullptr;
+  uint16_t* d_perms = nullptr;
+  uint32_t logf_probes = 0, logf_matched = 0;
+  std::string err;
+};
+
+struct mnemo_batch {
+  mnemo_ctx* ctx = nullptr;
+  uint32_t n_tracks = 0;
+  bool prenormalized = false;
+  std::vector<mnemo::TrackDev> h_tracks;
+  std::vector<uint32_t> k0_tile_prefix, k1_tile_prefix;
+  std::vector<uint64_t> img_prefix, pcm_off;
+  uint64_t n_samples = 0, n_frames = 0, n_images = 0, n_chunks = 0;
+  uint32_t launches_per_run = 0;
+  // device buffers
+  uint8_t* d_pcm = nullptr;
+  mnemo::TrackDev* d_tracks = nullptr;
+  uint32_t *d_k0_prefix = nullptr, *d_k1_prefix = nullptr, *d_chunk_track = nullptr;
+  uint64_t* d_img_prefix = nullptr;
+  float* d_s5512 = nullptr;
+  double *d_chunk_true = nullptr, *d_chunk_prefix = nullptr;
+  mnemo::SumChunkRec* d_recs = nullptr;
+  float *d_sumsq = nullptr, *d_rms = nullptr, *d_bins = nullptr;
+  uint8_t *d_sig_dense = nullptr, *d_keep = nullptr, *d_sig_out = nullptr;
+  uint32_t *d_pos = nullptr, *d_block_sums = nullptr, *d_n_sigs = nullptr;
+  uint8_t* d_tap_raw = nullptr;
+  float *d_tap_img = nullptr, *d_tap_haar = nullptr;
+};
+
+int mnemo_fail(mnemo_ctx* ctx, cudaError_t e, const char* what);

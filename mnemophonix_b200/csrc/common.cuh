@@ -1,0 +1,143 @@
+// common.cuh — shared device/host declarations for libmnemo_cuda.so (sm_100a only).
+//
+// Arithmetic contract: every float stage reproduces the reference's C arithmetic exactly
+// (SURVEY.md App. A): separate IEEE mul/add roundings (no FMA contraction; the reference is
+// built for baseline x86-64), double-precision islands where C promotes to double, and
+// denormals kept.  Build flags: -fmad=false -ftz=false -prec-div=true -prec-sqrt=true.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mnemo {
+
+constexpr int kFrame = 2048;        // spectralimages.h:12
+constexpr int kHop = 64;            // spectralimages.h:18
+constexpr int kBands = 32;          // logbins.h:5
+constexpr int kImgW = 128;          // spectralimages.h:24
+constexpr int kImgStep = 8;         // spectralimages.h:30
+constexpr int kImgElems = kImgW * kBands;
+constexpr int kTopK = 200;          // rawfingerprints.h:13
+constexpr int kRawBytes = 1024;     // rawfingerprints.h:16
+constexpr int kSigLen = 100;        // minhash.h:7
+constexpr int kPermLen = 255;       // permutations.h:10
+constexpr int kTaps = 31;           // resample.c:7
+constexpr int kDecim = 8;
+constexpr int kTables = 25;         // lsh.h:9
+
+constexpr int kSumChunk = 4096;     // samples per speculative sum-of-squares chunk
+constexpr int kSumCands = 3;        // candidate binades simulated per chunk
+constexpr uint32_t kSumInvalid = 0xFFFFFFFFu;
+
+// Per-track descriptor (device copy lives in the batch).
+struct TrackDev {
+  const int16_t* pcm;     // device pointer, interleaved int16 (nullptr for pre-normalised input)
+  uint64_t n_pcm;         // sample frames
+  uint32_t channels;
+  uint32_t n5512;         // n_pcm / 8
+  uint32_t n_frames;      // 0 when the track is too small to fingerprint
+  uint32_t n_images;
+  uint32_t prenormalized; // samples are already normalised: skip rms division (from_samples path)
+  uint32_t n_chunks;      // ceil(n5512 / kSumChunk)
+  uint64_t s_off;         // float offset of this track's 5512 Hz samples
+  uint64_t frame_off;     // frame offset into bins
+  uint64_t img_off;       // image offset into per-image arrays
+  uint64_t chunk_off;     // chunk offset into the sum-of-squares scratch
+};
+
+// Host-computed tables (same libm calls as the reference), uploaded once per context.
+struct Tables {
+  float taps[kTaps];            // resample.c:27-35
+  float hann[kFrame];           // hannwindow.c:8-12
+  float2 tw64[32];              // twiddles W64^m, m<32 = table[32m]        (fft.c:49-51)
+  float2 tw_hi[2][31][32];      // stage 7..11 twiddles per (half, slot, lane)
+  uint16_t edges[kBands + 1];   // logbins.c:44-55
+  float log256;                 // logf(256.0f)                              (spectralimages.c:57)
+  int logf_variant;             // which glibc logf build the host runs (0 baseline, 1 fma)
+};
+
+struct SumChunkRec {   // one per chunk, 32 bytes
+  uint32_t e_hi;       // biased exponent of the highest candidate binade (0 = no candidates)
+  uint32_t delta[kSumCands][2];  // mantissa increment for (candidate, parity of incoming mantissa)
+  uint32_t pad;
+};
+
+// ---- launchers (defined in the k*.cu files); all asynchronous on `st` ----
+void launch_k0_resample(const TrackDev* tracks, const uint32_t* tile_prefix, uint32_t n_tracks, uint32_t n_tiles,
+                        const Tables* tab, float* s5512, cudaStream_t st);
+void launch_sumsq(const TrackDev* tracks, uint32_t n_tracks, uint64_t n_chunks_total, const uint32_t* chunk_track,
+                  const float* s5512, double* chunk_true, double* chunk_prefix, SumChunkRec* recs, float* sumsq,
+                  float* rms, cudaStream_t st, int* n_launches);
+void launch_k1_spectral(const TrackDev* tracks, const uint32_t* tile_prefix, uint32_t n_tracks, uint32_t n_tiles,
+                        const Tables* tab, const float* s5512, const float* rms, float* bins, int sm_count,
+                        cudaStream_t st);
+void launch_k2_fingerprint(const TrackDev* tracks, const uint64_t* img_prefix, uint32_t n_tracks, uint64_t n_images,
+                           const Tables* tab, const uint16_t* perms, const float* bins, uint8_t* sig_dense,
+                           uint8_t* keep, uint8_t* tap_raw, float* tap_img, float* tap_haar, int logf_variant,
+                           cudaStream_t st);
+void launch_compact(const uint8_t* sig_dense, const uint8_t* keep, uint64_t n_images, const uint64_t* img_prefix,
+                    uint32_t n_tracks, uint32_t* block_sums, uint32_t* pos, uint8_t* sig_out, uint32_t* n_sigs,
+                    cudaStream_t st, int* n_launches);
+void k1_upload_constants(const Tables& t);
+void launch_logf_range(uint32_t lo_bits, uint32_t n, int variant, float* out, cudaStream_t st);
+int k1_tile_frames();
+int k0_tile_outputs();
+
+// ---- device helpers ----
+#ifdef __CUDACC__
+// glibc 2.39 logf (sysdeps/ieee754/flt-32/e_logf.c, ARM optimized-routines algorithm): 16-entry
+// table, degree-3 polynomial in double.  Constants are the published table (identical to the
+// .rodata of this image's libm.so.6).  Valid for normal positive finite x (here x in [1, 256]).
+static __device__ __constant__ double c_logf_tab[16][2] = {
+    {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
+    {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
+    {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
+    {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
+    {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},
+    {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
+    {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
+    {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+
+template <int VARIANT>
+__device__ __forceinline__ float logf_glibc(float x) {
+  const double ln2 = 0x1.62e42fefa39efp-1;
+  const double a0 = -0x1.00ea348b88334p-2, a1 = 0x1.5575b0be00b6ap-2, a2 = -0x1.ffffef20a4123p-2;
+  uint32_t ix = __float_as_uint(x);
+  if (ix == 0x3f800000u) return 0.0f;
+  uint32_t tmp = ix - 0x3f330000u;
+  int i = (tmp >> 19) & 15;
+  int k = (int)tmp >> 23;
+  uint32_t iz = ix - (tmp & 0xff800000u);
+  double z = (double)__uint_as_float(iz);
+  double invc = c_logf_tab[i][0], logc = c_logf_tab[i][1];
+  if (VARIANT) {  // instruction order of the -mfma ifunc variant
+    double y0 = __fma_rn((double)k, ln2, logc);
+    double r = __fma_rn(z, invc, -1.0);
+    double y = __fma_rn(r, a1, a2);
+    double r2 = __dmul_rn(r, r);
+    double hi = __dadd_rn(r, y0);
+    y = __fma_rn(r2, a0, y);
+    return __double2float_rn(__fma_rn(r2, y, hi));
+  } else {
+    double r = __dadd_rn(__dmul_rn(z, invc), -1.0);
+    double y0 = __dadd_rn(logc, __dmul_rn((double)k, ln2));
+    double r2 = __dmul_rn(r, r);
+    double y = __dadd_rn(__dmul_rn(a1, r), a2);
+    y = __dadd_rn(__dmul_rn(a0, r2), y);
+    return __double2float_rn(__dadd_rn(__dmul_rn(y, r2), __dadd_rn(y0, r)));
+  }
+}
+
+// index of the last prefix[] entry <= v (prefix has n+1 ascending entries, prefix[0] == 0)
+template <typename T>
+__device__ __forceinline__ uint32_t find_segment(const T* __restrict__ prefix, uint32_t n, T v) {
+  uint32_t lo = 0, hi = n;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (prefix[mid] <= v) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+#endif
+
+}  // namespace mnemo

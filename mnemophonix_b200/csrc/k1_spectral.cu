@@ -1,0 +1,233 @@
+// k1_spectral.cu — normalised 5512 Hz samples -> Hann -> 2048-point FFT -> 32 log-band energies.
+//
+// Replaces normalize()'s second loop (audionormalizer.c:22-31), frames_to_bins
+// (spectralimages.c:80-107), fft/inplace_fft (fft.c:34-86) and calculate_bins (logbins.c:58-76).
+//
+// One warp transforms one frame entirely on-chip.  The reference's FFT is a radix-2
+// decimation-in-time butterfly network on bit-reversed input whose every multiply and add is
+// rounded separately; its results depend only on that dataflow graph, so the network is kept
+// and only its schedule is changed:
+//   * position p = 64*g + i (g = lane, i = register index): stages 1..6 (butterfly span < 64)
+//     are 32 independent 64-point sub-transforms, one per lane, fully unrolled in registers
+//     with warp-uniform twiddles read as constant-bank operands;
+//   * one transposition through padded shared memory (bank-conflict-free both ways);
+//   * stages 7..11 are 64 independent 32-point column transforms (fixed i, g = 0..31), two per
+//     lane, again in registers, with per-lane twiddles in a lane-major shared table;
+//   * the input is real, so positions 0 and L/2 of every sub-transform stay real: those
+//     butterflies skip the multiplications by an exactly-zero imaginary part (values identical,
+//     only the sign of a zero can differ, which no later operation can observe);
+//   * only FFT outputs 118..742 feed the bands (logbins.c:64-75 with the edges of
+//     logbins.c:44-55), so stage 11 computes the "a" half of 11 of its 16 butterflies per
+//     column and dead-code elimination prunes what feeds nothing.
+// The sequential per-band accumulation (logbins.c:68-73) is done by one lane per band.
+#include "common.cuh"
+
+namespace mnemo {
+
+constexpr int kK1Warps = 12;
+constexpr int kK1Threads = kK1Warps * 32;
+constexpr int kK1FramesPerWarp = 8;
+constexpr int kK1TileFrames = kK1Warps * kK1FramesPerWarp;            // 96 frames
+constexpr int kK1TileSamples = kHop * (kK1TileFrames - 1) + kFrame;   // 8128 samples
+constexpr int kScratchStride = 33;
+constexpr int kScratchFloats = 64 * kScratchStride;                   // per warp
+constexpr int kTwHiFloat2 = 2 * 31 * 32;
+constexpr size_t kK1Smem =
+    sizeof(float) * (kK1TileSamples + kFrame + kK1Warps * kScratchFloats) + sizeof(float2) * kTwHiFloat2;
+
+int k1_tile_frames() { return kK1TileFrames; }
+
+__constant__ float2 c_tw64[32];
+
+void k1_upload_constants(const Tables& t) { cudaMemcpyToSymbol(c_tw64, t.tw64, sizeof(float2) * 32); }
+
+__host__ __device__ constexpr int rev6(int v) {
+  return ((v & 1) << 5) | ((v & 2) << 3) | ((v & 4) << 1) | ((v & 8) >> 1) | ((v & 16) >> 3) | ((v & 32) >> 5);
+}
+
+// fft.c:53-62, each operation rounded on its own
+__device__ __forceinline__ void bfly(float& ar, float& ai, float& br, float& bi, const float wr, const float wi) {
+  const float m1 = __fmul_rn(wr, br), m2 = __fmul_rn(wi, bi);
+  const float m3 = __fmul_rn(wr, bi), m4 = __fmul_rn(wi, br);
+  const float tr = __fsub_rn(m1, m2), ti = __fadd_rn(m3, m4);
+  br = __fsub_rn(ar, tr);
+  bi = __fsub_rn(ai, ti);
+  ar = __fadd_rn(ar, tr);
+  ai = __fadd_rn(ai, ti);
+}
+
+// Stage S (span L = 2^S <= 64) of the 64-point sub-transform held in registers.
+template <int S>
+__device__ __forceinline__ void stage_lo(float (&re)[64], float (&im)[64]) {
+  constexpr int L = 1 << S, H = L >> 1;
+#pragma unroll
+  for (int base = 0; base < 64; base += L) {
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      const int a = base + k, b = a + H;
+      const int m = k * (64 / L);   // twiddle (l = L, k) == W64^m
+      if (k == 0) {
+        // both inputs real, w = (1, -0): tao == b exactly
+        const float x = re[a], y = re[b];
+        re[a] = __fadd_rn(x, y);
+        re[b] = __fsub_rn(x, y);
+      } else if (2 * k == H) {
+        // both inputs real: tao = (wr*b, wi*b); outputs (a + tr, 0 + ti), (a - tr, 0 - ti)
+        const float tr = __fmul_rn(c_tw64[m].x, re[b]), ti = __fmul_rn(c_tw64[m].y, re[b]);
+        const float x = re[a];
+        re[b] = __fsub_rn(x, tr);
+        im[b] = -ti;
+        re[a] = __fadd_rn(x, tr);
+        im[a] = ti;
+      } else {
+        bfly(re[a], im[a], re[b], im[b], c_tw64[m].x, c_tw64[m].y);
+      }
+    }
+  }
+}
+
+// Stages 7..11 on one column (fixed i; element index = g) and the band-power terms.
+// tw points at tw_hi[h][0][lane]; consecutive slots are 32 float2 apart.
+__device__ __forceinline__ void column_pass(float (&cr)[32], float (&ci)[32], const float2* __restrict__ tw,
+                                            float* __restrict__ pw_col) {
+  {  // stage 7: span 128, k = i
+    const float2 w = tw[0];
+#pragma unroll
+    for (int g = 0; g < 32; g += 2) bfly(cr[g], ci[g], cr[g + 1], ci[g + 1], w.x, w.y);
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {  // stage 8: span 256, k = 64*(g&1) + i
+    const float2 w = tw[32 * (1 + q)];
+#pragma unroll
+    for (int g = q; g < 32; g += 4) bfly(cr[g], ci[g], cr[g + 2], ci[g + 2], w.x, w.y);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {  // stage 9: span 512
+    const float2 w = tw[32 * (3 + q)];
+#pragma unroll
+    for (int g = q; g < 32; g += 8) bfly(cr[g], ci[g], cr[g + 4], ci[g + 4], w.x, w.y);
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {  // stage 10: span 1024
+    const float2 w = tw[32 * (7 + q)];
+#pragma unroll
+    for (int g = q; g < 32; g += 16) bfly(cr[g], ci[g], cr[g + 8], ci[g + 8], w.x, w.y);
+  }
+  // stage 11: span 2048; outputs 118..742 live in g = 1..11, "a" side only
+#pragma unroll
+  for (int g = 1; g <= 11; ++g) {
+    const float2 w = tw[32 * (15 + g)];
+    const float br = cr[g + 16], bi = ci[g + 16];
+    const float tr = __fsub_rn(__fmul_rn(w.x, br), __fmul_rn(w.y, bi));
+    const float ti = __fadd_rn(__fmul_rn(w.x, bi), __fmul_rn(w.y, br));
+    const float xr = __fadd_rn(cr[g], tr), xi = __fadd_rn(ci[g], ti);
+    // logbins.c:69-71: re/1024.0 and im/1024.0 (exact scalings, rounded to f32), squares, sum
+    const float r = __fmul_rn(xr, 0.0009765625f), q = __fmul_rn(xi, 0.0009765625f);
+    pw_col[64 * (g - 1)] = __fadd_rn(__fmul_rn(r, r), __fmul_rn(q, q));
+  }
+}
+
+__global__ void __launch_bounds__(kK1Threads, 1)
+    k1_spectral_kernel(const TrackDev* __restrict__ tracks, const uint32_t* __restrict__ tile_prefix, uint32_t n_tracks,
+                       uint32_t n_tiles, const Tables* __restrict__ tab, const float* __restrict__ s5512,
+                       const float* __restrict__ rms, float* __restrict__ bins) {
+  extern __shared__ __align__(16) float smem[];
+  float* tile = smem;                                   // kK1TileSamples
+  float* hann = tile + kK1TileSamples;                  // kFrame
+  float2* tw_hi = reinterpret_cast<float2*>(hann + kFrame);   // [2][31][32]
+  float* scratch_all = reinterpret_cast<float*>(tw_hi + kTwHiFloat2);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* sc = scratch_all + warp * kScratchFloats;
+
+  for (int i = threadIdx.x; i < kFrame; i += kK1Threads) hann[i] = tab->hann[i];
+  for (int i = threadIdx.x; i < kTwHiFloat2; i += kK1Threads) tw_hi[i] = (&tab->tw_hi[0][0][0])[i];
+  const int e_lo = (int)tab->edges[lane] - 64, e_hi = (int)tab->edges[lane + 1] - 64;
+  const float width = (float)(unsigned)(e_hi - e_lo);   // logbins.c:75
+  const int rl = (int)(__brev((unsigned)lane) >> 27);   // rev5(lane)
+
+  for (uint32_t tix = blockIdx.x; tix < n_tiles; tix += gridDim.x) {
+    const uint32_t t = find_segment<uint32_t>(tile_prefix, n_tracks, tix);
+    const TrackDev tr = tracks[t];
+    const uint32_t f0 = (tix - tile_prefix[t]) * kK1TileFrames;
+    const uint32_t nf = min((uint32_t)kK1TileFrames, tr.n_frames - f0);
+    const uint32_t ns = kHop * (nf - 1) + kFrame;
+    const float* __restrict__ src = s5512 + tr.s_off + (uint64_t)f0 * kHop;
+    __syncthreads();   // previous tile fully consumed (and tables visible on the first pass)
+    if (tr.prenormalized) {
+      for (uint32_t i = threadIdx.x; i < ns; i += kK1Threads) tile[i] = src[i];
+    } else {
+      const float r = rms[t];
+      for (uint32_t i = threadIdx.x; i < ns; i += kK1Threads) {
+        float v = __fdiv_rn(src[i], r);   // audionormalizer.c:23-30
+        if (v < -1.0f) v = -1.0f;
+        else if (v > 1.0f) v = 1.0f;
+        tile[i] = v;
+      }
+    }
+    __syncthreads();
+
+    for (uint32_t fl = warp; fl < nf; fl += kK1Warps) {
+      float re[64], im[64];
+      {  // spectralimages.c:94-98 Hann multiply, loaded straight into bit-reversed order (fft.c:35-45)
+        const float* fs = tile + fl * kHop + rl;
+        const float* hw = hann + rl;
+#pragma unroll
+        for (int r = 0; r < 64; ++r) re[rev6(r)] = __fmul_rn(fs[32 * r], hw[32 * r]);
+#pragma unroll
+        for (int i = 0; i < 64; ++i) im[i] = 0.0f;
+      }
+      stage_lo<1>(re, im);
+      stage_lo<2>(re, im);
+      stage_lo<3>(re, im);
+      stage_lo<4>(re, im);
+      stage_lo<5>(re, im);
+      stage_lo<6>(re, im);
+
+      // transposition: lane g owns positions 64g+i; afterwards lane t owns i = t and t+32, all g
+      float cr[2][32], ci[2][32];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) sc[i * kScratchStride + lane] = re[i];
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int g = 0; g < 32; ++g) cr[h][g] = sc[(lane + 32 * h) * kScratchStride + g];
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 64; ++i) sc[i * kScratchStride + lane] = im[i];
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int g = 0; g < 32; ++g) ci[h][g] = sc[(lane + 32 * h) * kScratchStride + g];
+      __syncwarp();
+
+      // columns; the scratch now receives the power terms of outputs 64..767 (index p - 64)
+      column_pass(cr[0], ci[0], tw_hi + lane, sc + lane);
+      column_pass(cr[1], ci[1], tw_hi + 31 * 32 + lane, sc + 32 + lane);
+      __syncwarp();
+
+      // logbins.c:64-75: sequential sum over the band's FFT bins, one band per lane
+      float sum = 0.0f;
+      for (int j = e_lo; j < e_hi; ++j) sum = __fadd_rn(sum, sc[j]);
+      bins[(tr.frame_off + f0 + fl) * kBands + lane] = __fdiv_rn(sum, width);
+      __syncwarp();
+    }
+  }
+}
+
+void launch_k1_spectral(const TrackDev* tracks, const uint32_t* tile_prefix, uint32_t n_tracks, uint32_t n_tiles,
+                        const Tables* tab, const float* s5512, const float* rms, float* bins, int sm_count,
+                        cudaStream_t st) {
+  if (n_tiles == 0) return;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k1_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem);
+    attr_set = true;
+  }
+  const unsigned grid = n_tiles < (uint32_t)sm_count ? n_tiles : (unsigned)sm_count;
+  k1_spectral_kernel<<<grid, kK1Threads, kK1Smem, st>>>(tracks, tile_prefix, n_tracks, n_tiles, tab, s5512, rms, bins);
+}
+
+}  // namespace mnemo
