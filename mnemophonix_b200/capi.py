@@ -240,3 +240,111 @@ class Batch:
         if got < 0:
             raise MnemoError(f"mnemo_batch_read({what}) failed: {got}: {lib().mnemo_last_error(self.ctx.h).decode()}")
         return buf[:count]
+
+
+# ---------------------------------------------------------------------------- search ----
+
+def _concat(sig_lists):
+    counts = np.array([len(s) for s in sig_lists], np.uint32)
+    start = np.zeros(len(sig_lists) + 1, np.uint32)
+    np.cumsum(counts, out=start[1:])
+    if len(sig_lists):
+        allsigs = np.ascontiguousarray(np.concatenate([np.asarray(s, np.uint8).reshape(-1, SIG_LEN) for s in sig_lists]))
+    else:
+        allsigs = np.zeros((0, SIG_LEN), np.uint8)
+    if allsigs.shape[0] == 0:
+        allsigs = np.zeros((1, SIG_LEN), np.uint8)[:0]
+    return allsigs, start
+
+
+class Db:
+    """LSH database (one shard) resident on the GPU: create_hash_tables (lsh.c:55-86)."""
+
+    def __init__(self, ctx: Context, entry_sigs, table_size: int = 0, entry_base: int = 0):
+        self.ctx = ctx
+        sigs, start = _concat(entry_sigs)
+        self.n_entries = len(entry_sigs)
+        self.entry_base = entry_base
+        self.h = C.c_void_p()
+        buf = sigs if sigs.shape[0] else np.zeros((1, SIG_LEN), np.uint8)
+        rc = lib().mnemo_db_create(ctx.h, buf.ctypes.data, start.ctypes.data, self.n_entries, table_size, entry_base,
+                                   C.byref(self.h))
+        ctx._check(rc, "mnemo_db_create")
+
+    def close(self):
+        if self.h:
+            lib().mnemo_db_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def table_size(self) -> int:
+        return int(lib().mnemo_db_table_size(self.h))
+
+    def get_matches(self, sig: np.ndarray, cap: int = 1 << 20):
+        sig = np.ascontiguousarray(sig, np.uint8)
+        out = np.empty((cap, 2), np.uint32)
+        n = lib().mnemo_db_get_matches(self.h, sig.ctypes.data, out.ctypes.data, cap)
+        if n < 0:
+            self.ctx._check(int(n), "mnemo_db_get_matches")
+        return [tuple(x) for x in out[:min(n, cap)].tolist()]
+
+    def search(self, queries):
+        """queries: list of [n,100] u8 arrays.  Returns (results list of (entry, score, n_matches), (L, D))."""
+        qs, qstart = _concat(queries)
+        nq = len(queries)
+        out = (Match * max(nq, 1))()
+        stats = (C.c_uint64 * 2)()
+        buf = qs if qs.shape[0] else np.zeros((1, SIG_LEN), np.uint8)
+        rc = lib().mnemo_search_batch(self.h, buf.ctypes.data, qstart.ctypes.data, nq, out, stats)
+        self.ctx._check(rc, "mnemo_search_batch")
+        return [(out[i].entry, out[i].score, out[i].n_matches) for i in range(nq)], (stats[0], stats[1])
+
+    def search_shard(self, queries, cap: int | None = None):
+        """Per-shard candidate records + last-group records, as numpy structured arrays."""
+        qs, qstart = _concat(queries)
+        nq = len(queries)
+        nqs = int(qstart[-1])
+        cap = cap or max(1024, nq * 64)
+        while True:
+            cands = (Cand * cap)()
+            last = (LastGroup * max(nqs, 1))()
+            n = C.c_uint64(0)
+            stats = (C.c_uint64 * 2)()
+            buf = qs if qs.shape[0] else np.zeros((1, SIG_LEN), np.uint8)
+            rc = lib().mnemo_search_shard(self.h, buf.ctypes.data, qstart.ctypes.data, nq, cands, cap, C.byref(n), last, stats)
+            if rc == -1 and n.value > cap:
+                cap = int(n.value)
+                continue
+            self.ctx._check(rc, "mnemo_search_shard")
+            break
+        c = np.frombuffer(cands, dtype=CAND_DTYPE, count=int(n.value)).copy()
+        l = np.frombuffer(last, dtype=LAST_DTYPE, count=nqs).copy()
+        return c, l, qstart, (stats[0], stats[1])
+
+
+CAND_DTYPE = np.dtype([("query", "<u4"), ("entry", "<i4"), ("score", "<f4"), ("n_matches", "<i4")])
+LAST_DTYPE = np.dtype([("has", "<u4"), ("entry", "<u4"), ("sig", "<u4"), ("hits", "<u4"), ("score", "<u4")])
+
+
+def search_finish(cands: np.ndarray, last_all: np.ndarray | None, n_shards: int, qstart: np.ndarray, n_entries_total: int):
+    """Host-only merge + exact selection (search.c:170-193).  cands: CAND_DTYPE records of all shards
+    concatenated; last_all: LAST_DTYPE [n_shards, n_query_sigs] or None."""
+    cands = np.ascontiguousarray(cands, dtype=CAND_DTYPE)
+    nq = len(qstart) - 1
+    out = (Match * max(nq, 1))()
+    qstart = np.ascontiguousarray(qstart, np.uint32)
+    lp = None
+    if last_all is not None:
+        last_all = np.ascontiguousarray(last_all, dtype=LAST_DTYPE)
+        lp = last_all.ctypes.data
+    rc = lib().mnemo_search_finish(cands.ctypes.data if len(cands) else None, len(cands), lp, n_shards,
+                                   qstart.ctypes.data, nq, n_entries_total, out)
+    if rc != 0:
+        raise MnemoError(f"mnemo_search_finish: {ERRORS.get(rc, rc)}")
+    return [(out[i].entry, out[i].score, out[i].n_matches) for i in range(nq)]

@@ -1,0 +1,434 @@
+// api_search.cu — C ABI (include/mnemo_cuda.h): LSH database handle, batched / sharded search.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/mnemo_cuda.h"
+#include "api_internal.h"
+#include "search_internal.h"
+
+using namespace mnemo;
+
+struct mnemo_db {
+  mnemo_ctx* ctx = nullptr;
+  uint64_t n_sigs = 0;
+  uint32_t n_entries = 0, size = 0, entry_base = 0;
+  std::vector<uint32_t> h_entry_start;
+  uint8_t* d_sigs = nullptr;
+  uint32_t *d_entry_start = nullptr, *d_sig_entry = nullptr, *d_start = nullptr, *d_ids = nullptr;
+};
+
+template <typename T>
+static cudaError_t dalloc(T** p, uint64_t count) {
+  *p = nullptr;
+  return cudaMalloc((void**)p, (count ? count : 1) * sizeof(T));
+}
+
+extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32_t* entry_start, uint32_t n_entries,
+                               uint32_t table_size, uint32_t entry_base, mnemo_db** out) {
+  if (!ctx || !out || !entry_start) return -3;
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  mnemo_db* db = new (std::nothrow) mnemo_db();
+  if (!db) return -1;
+  db->ctx = ctx;
+  db->n_entries = n_entries;
+  db->entry_base = entry_base;
+  db->h_entry_start.assign(entry_start, entry_start + n_entries + 1);
+  db->n_sigs = entry_start[n_entries];
+  db->size = table_size ? table_size : (uint32_t)(db->n_sigs / 2);   // lsh.c:61
+  if ((uint64_t)db->size * kTables + 1 >= (1ull << 32) || db->n_sigs * kTables >= (1ull << 32)) {
+    ctx->err = "mnemo_db_create: shard too large for 32-bit bucket offsets; use more shards";
+    delete db;
+    return -3;
+  }
+  const uint64_t n_slots = (uint64_t)db->size * kTables;
+  uint32_t *d_counts = nullptr, *d_cursor = nullptr, *d_block_sums = nullptr;
+  cudaError_t e = cudaSuccess;
+#define TRY(x)                      \
+  do {                              \
+    if (e == cudaSuccess) e = (x);  \
+  } while (0)
+  TRY(dalloc(&db->d_sigs, db->n_sigs * kSigLen + 4));
+  TRY(dalloc(&db->d_entry_start, (uint64_t)n_entries + 1));
+  TRY(dalloc(&db->d_sig_entry, db->n_sigs));
+  TRY(dalloc(&db->d_start, n_slots + 1));
+  TRY(dalloc(&db->d_ids, db->n_sigs * kTables));
+  TRY(dalloc(&d_counts, n_slots));
+  TRY(dalloc(&d_cursor, n_slots));
+  TRY(dalloc(&d_block_sums, (uint64_t)lsh_scan_blocks(n_slots) + 1));
+  cudaStream_t st = ctx->stream;
+  if (db->n_sigs) TRY(cudaMemcpyAsync(db->d_sigs, sigs, db->n_sigs * kSigLen, cudaMemcpyHostToDevice, st));
+  TRY(cudaMemcpyAsync(db->d_entry_start, entry_start, 4ull * (n_entries + 1), cudaMemcpyHostToDevice, st));
+  TRY(cudaMemsetAsync(db->d_start, 0, (n_slots + 1) * 4, st));
+  if (e == cudaSuccess && db->size && db->n_sigs) {
+    launch_lsh_build(db->d_sigs, db->n_sigs, db->d_entry_start, n_entries, db->size, d_counts, db->d_start, d_cursor,
+                     d_block_sums, db->d_ids, db->d_sig_entry, st);
+    TRY(cudaGetLastError());
+  }
+  TRY(cudaStreamSynchronize(st));
+#undef TRY
+  cudaFree(d_counts);
+  cudaFree(d_cursor);
+  cudaFree(d_block_sums);
+  if (e != cudaSuccess) {
+    int rc = mnemo_fail(ctx, e, "mnemo_db_create");
+    mnemo_db_destroy(db);
+    return rc;
+  }
+  *out = db;
+  return 0;
+}
+
+extern "C" void mnemo_db_destroy(mnemo_db* db) {
+  if (!db) return;
+  cudaSetDevice(db->ctx->device);
+  cudaStreamSynchronize(db->ctx->stream);
+  void* ptrs[] = {db->d_sigs, db->d_entry_start, db->d_sig_entry, db->d_start, db->d_ids};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete db;
+}
+
+extern "C" uint32_t mnemo_db_table_size(const mnemo_db* db) { return db ? db->size : 0; }
+
+static SearchParams base_params(const mnemo_db* db) {
+  SearchParams p;
+  memset(&p, 0, sizeof p);
+  p.db_sigs = db->d_sigs;
+  p.sig_entry = db->d_sig_entry;
+  p.start = db->d_start;
+  p.ids = db->d_ids;
+  p.size = db->size;
+  p.n_entries = db->n_entries;
+  return p;
+}
+
+static uint32_t local_entry_of(const mnemo_db* db, uint32_t g) {
+  const auto& es = db->h_entry_start;
+  return (uint32_t)(std::upper_bound(es.begin(), es.end(), g) - es.begin() - 1);
+}
+
+extern "C" int64_t mnemo_db_get_matches(mnemo_db* db, const uint8_t* sig, uint32_t* pairs_out, uint64_t cap_pairs) {
+  if (!db || !sig) return -3;
+  mnemo_ctx* ctx = db->ctx;
+  cudaSetDevice(ctx->device);
+  if (db->size == 0 || db->n_sigs == 0) return 0;
+  cudaStream_t st = ctx->stream;
+  uint8_t* d_q = nullptr;
+  uint32_t *d_out = nullptr, *d_counts = nullptr;
+  const uint32_t cap = (uint32_t)std::min<uint64_t>(db->n_sigs * kTables, 1u << 26);
+  cudaError_t e = dalloc(&d_q, 128);
+  if (e == cudaSuccess) e = dalloc(&d_out, cap);
+  if (e == cudaSuccess) e = dalloc(&d_counts, kTables);
+  std::vector<uint32_t> ids, counts(kTables);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_q, sig, kSigLen, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    SearchParams p = base_params(db);
+    p.query_sigs = d_q;
+    launch_search_gather(p, d_out, cap, d_counts, st);
+    e = cudaMemcpyAsync(counts.data(), d_counts, 4 * kTables, cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  uint64_t total = 0;
+  if (e == cudaSuccess) {
+    for (uint32_t c : counts) total += c;
+    ids.resize(std::min<uint64_t>(total, cap));
+    if (!ids.empty()) e = cudaMemcpy(ids.data(), d_out, ids.size() * 4, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d_q);
+  cudaFree(d_out);
+  cudaFree(d_counts);
+  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_db_get_matches");
+  // lsh.c:89-112 prepends while walking tables 0..24 and each chain from its head (members in
+  // descending (entry, signature) order): the returned list reads table 24 ascending, ..., table 0.
+  std::vector<uint32_t> off(kTables + 1, 0);
+  for (int k = 0; k < kTables; k++) off[k + 1] = off[k] + counts[k];
+  uint64_t w = 0;
+  for (int k = kTables - 1; k >= 0; k--) {
+    if (off[k + 1] > ids.size()) continue;
+    std::sort(ids.begin() + off[k], ids.begin() + off[k + 1]);
+    for (uint32_t i = off[k]; i < off[k + 1]; i++, w++) {
+      if (w >= cap_pairs) continue;
+      const uint32_t le = local_entry_of(db, ids[i]);
+      pairs_out[2 * w] = db->entry_base + le;
+      pairs_out[2 * w + 1] = ids[i] - db->h_entry_start[le];
+    }
+  }
+  return (int64_t)total;
+}
+
+// ------------------------------------------------------------------ search ----
+
+extern "C" int mnemo_search_shard(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
+                                  uint32_t n_queries, mnemo_cand* cands, uint64_t cap_cands, uint64_t* n_cands,
+                                  mnemo_lastgroup* last, uint64_t* stats) {
+  if (!db || !query_start || !n_cands) return -3;
+  mnemo_ctx* ctx = db->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  *n_cands = 0;
+  if (stats) stats[0] = stats[1] = 0;
+  const uint32_t n_qsigs = query_start[n_queries];
+  if (last)
+    for (uint32_t i = 0; i < n_qsigs; i++) last[i] = mnemo_lastgroup{0, 0, 0, 0, 0};
+  if (n_queries == 0 || n_qsigs == 0 || db->size == 0 || db->n_sigs == 0 || db->n_entries == 0) return 0;
+
+  // queries are processed in groups whose dense accumulators stay under ~1 GiB
+  const uint64_t per_query = (uint64_t)db->n_entries * 8;
+  const uint32_t group = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_queries, (1ull << 30) / per_query));
+  uint8_t* d_q = nullptr;
+  uint32_t *d_qstart = nullptr, *d_acc_s = nullptr, *d_acc_n = nullptr, *d_total = nullptr, *d_qbase = nullptr,
+           *d_qcnt = nullptr;
+  mnemo_lastgroup_dev* d_last = nullptr;
+  unsigned long long* d_stats = nullptr;
+  CandDev* d_cands = nullptr;
+  const uint32_t cand_cap = (uint32_t)std::min<uint64_t>((uint64_t)group * db->n_entries, 1u << 24);
+  cudaError_t e = cudaSuccess;
+#define TRY(x)                      \
+  do {                              \
+    if (e == cudaSuccess) e = (x);  \
+  } while (0)
+  TRY(dalloc(&d_q, (uint64_t)n_qsigs * kSigLen + 4));
+  TRY(dalloc(&d_qstart, (uint64_t)n_queries + 1));
+  TRY(dalloc(&d_acc_s, (uint64_t)group * db->n_entries));
+  TRY(dalloc(&d_acc_n, (uint64_t)group * db->n_entries));
+  TRY(dalloc(&d_last, n_qsigs));
+  TRY(dalloc(&d_stats, 2));
+  TRY(dalloc(&d_total, 1));
+  TRY(dalloc(&d_qbase, group));
+  TRY(dalloc(&d_qcnt, group));
+  TRY(dalloc(&d_cands, cand_cap));
+  TRY(cudaMemcpyAsync(d_q, query_sigs, (uint64_t)n_qsigs * kSigLen, cudaMemcpyHostToDevice, st));
+  TRY(cudaMemsetAsync(d_stats, 0, 16, st));
+  std::vector<CandDev> h_cands;
+  std::vector<uint32_t> h_qstart;
+  uint64_t written = 0;
+  int rc = 0;
+  for (uint32_t q0 = 0; q0 < n_queries && e == cudaSuccess && rc == 0; q0 += group) {
+    const uint32_t nq = std::min(group, n_queries - q0);
+    // group-local query_start (offsets relative to the group's first signature)
+    h_qstart.assign(query_start + q0, query_start + q0 + nq + 1);
+    const uint32_t s0 = h_qstart[0];
+    for (auto& v : h_qstart) v -= s0;
+    const uint32_t ns = h_qstart[nq];
+    TRY(cudaMemcpyAsync(d_qstart, h_qstart.data(), 4ull * (nq + 1), cudaMemcpyHostToDevice, st));
+    TRY(cudaMemsetAsync(d_acc_s, 0, (uint64_t)nq * db->n_entries * 4, st));
+    TRY(cudaMemsetAsync(d_acc_n, 0, (uint64_t)nq * db->n_entries * 4, st));
+    TRY(cudaMemsetAsync(d_total, 0, 4, st));
+    if (e != cudaSuccess) break;
+    SearchParams p = base_params(db);
+    p.query_sigs = d_q + (uint64_t)s0 * kSigLen;
+    p.query_start = d_qstart;
+    p.n_queries = nq;
+    p.acc_score = d_acc_s;
+    p.acc_n = d_acc_n;
+    p.last = d_last + s0;
+    p.stat_nodes = d_stats;
+    p.stat_deep = d_stats + 1;
+    launch_search(p, ns, st);
+    launch_search_compact(d_acc_s, d_acc_n, nq, db->n_entries, db->entry_base, d_cands, cand_cap, d_total, d_qbase,
+                          d_qcnt, st);
+    uint32_t total = 0;
+    TRY(cudaGetLastError());
+    TRY(cudaMemcpyAsync(&total, d_total, 4, cudaMemcpyDeviceToHost, st));
+    TRY(cudaStreamSynchronize(st));
+    if (e != cudaSuccess) break;
+    if (total > cand_cap) {
+      ctx->err = "mnemo_search_shard: candidate buffer overflow";
+      rc = -1;
+      break;
+    }
+    h_cands.resize(total);
+    if (total) TRY(cudaMemcpy(h_cands.data(), d_cands, sizeof(CandDev) * total, cudaMemcpyDeviceToHost));
+    // records come out grouped per query but in reservation order: sort (query, entry)
+    std::sort(h_cands.begin(), h_cands.end(), [](const CandDev& a, const CandDev& b) {
+      return a.query != b.query ? a.query < b.query : a.entry < b.entry;
+    });
+    for (const CandDev& c : h_cands) {
+      if (written < cap_cands && cands) {
+        cands[written].query = c.query + q0;
+        cands[written].entry = c.entry;
+        cands[written].score = c.score;
+        cands[written].n_matches = c.n_matches;
+      }
+      written++;
+    }
+  }
+  if (e == cudaSuccess && rc == 0 && last) {
+    std::vector<mnemo_lastgroup_dev> h_last(n_qsigs);
+    TRY(cudaMemcpy(h_last.data(), d_last, sizeof(mnemo_lastgroup_dev) * n_qsigs, cudaMemcpyDeviceToHost));
+    if (e == cudaSuccess)
+      for (uint32_t i = 0; i < n_qsigs; i++) {
+        last[i].has = h_last[i].has;
+        if (!h_last[i].has) continue;
+        const uint32_t le = local_entry_of(db, h_last[i].g);
+        last[i].entry = db->entry_base + le;
+        last[i].sig = h_last[i].g - db->h_entry_start[le];
+        last[i].hits = h_last[i].hits;
+        last[i].score = h_last[i].score;
+      }
+  }
+  if (e == cudaSuccess && rc == 0 && stats) {
+    unsigned long long h[2] = {0, 0};
+    TRY(cudaMemcpy(h, d_stats, 16, cudaMemcpyDeviceToHost));
+    stats[0] = h[0];
+    stats[1] = h[1];
+  }
+#undef TRY
+  void* ptrs[] = {d_q, d_qstart, d_acc_s, d_acc_n, d_last, d_stats, d_total, d_qbase, d_qcnt, d_cands};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_shard");
+  if (rc != 0) return rc;
+  *n_cands = written;
+  if (written > cap_cands) {
+    ctx->err = "mnemo_search_shard: cands capacity too small";
+    return -1;
+  }
+  return 0;
+}
+
+// ---- final ranking: search.c:65-107 comparator + the merge order of glibc's qsort ----
+
+namespace {
+struct Rec {
+  int32_t entry;
+  float score;
+  int32_t n;
+};
+
+// search.c:65-107, restated.  Not a strict weak order (integer abs() of a float difference).
+int cmp_entry_scores(const Rec& a, const Rec& b) {
+  const float avg_a = a.n == 0 ? 0 : a.score / (float)a.n;
+  const float avg_b = b.n == 0 ? 0 : b.score / (float)b.n;
+  const float delta = (float)abs((int)(avg_a - avg_b));
+  if (delta <= 3) {
+    if (delta <= 5 && a.n >= b.n + 5) return -1;
+    if (b.n >= a.n + 5) return 1;
+  }
+  if ((double)delta < 0.5) {
+    if (a.n > b.n) return -1;
+    if (a.n < b.n) return 1;
+  }
+  if (avg_a > avg_b) return -1;
+  if (avg_b > avg_a) return 1;
+  return 0;
+}
+
+// The reference sorts ALL n_entries records with libc qsort (search.c:170).  glibc's qsort is a
+// top-down merge sort (split n/2 | n - n/2, take the left element when cmp <= 0).  Entries
+// without matches compare equal to one another and lose to every entry with matches (whose
+// average is >= 30), so they end up after the others in index order and the merge tree over
+// the full index range can be replayed on the few non-zero records alone.
+void msort_sparse(std::vector<Rec>& v, size_t i0, size_t i1, uint32_t lo, uint32_t n, std::vector<Rec>& tmp) {
+  if (i1 - i0 <= 1 || n <= 1) return;
+  const uint32_t n1 = n / 2, mid = lo + n1;
+  size_t split = i0;
+  while (split < i1 && (uint32_t)v[split].entry < mid) split++;
+  msort_sparse(v, i0, split, lo, n1, tmp);
+  msort_sparse(v, split, i1, mid, n - n1, tmp);
+  size_t a = i0, b = split, w = 0;
+  tmp.resize(i1 - i0);
+  while (a < split && b < i1) tmp[w++] = cmp_entry_scores(v[a], v[b]) <= 0 ? v[a++] : v[b++];
+  while (a < split) tmp[w++] = v[a++];
+  while (b < i1) tmp[w++] = v[b++];
+  std::copy(tmp.begin(), tmp.begin() + w, v.begin() + i0);
+}
+
+// search.c:173-185 over the first ten records of the sorted array
+mnemo_match select_best(std::vector<Rec>& recs, uint32_t n_entries_total) {
+  std::vector<Rec> tmp;
+  msort_sparse(recs, 0, recs.size(), 0, n_entries_total, tmp);
+  mnemo_match best = {-7, 0.0f, 0};
+  float best_avg = 0;
+  for (size_t i = 0; i < recs.size() && i < 10; i++) {
+    const Rec& r = recs[i];
+    const float avg = r.n == 0 ? 0 : r.score / (float)r.n;
+    if ((r.n >= 10 || (avg >= 35 && r.n >= 5)) && avg >= 30)
+      if (avg > best_avg) {
+        best_avg = avg;
+        best.entry = r.entry;
+        best.score = r.score;
+        best.n_matches = r.n;
+      }
+  }
+  return best;
+}
+}  // namespace
+
+extern "C" int mnemo_search_finish(const mnemo_cand* cands, uint64_t n_cands, const mnemo_lastgroup* last,
+                                   uint32_t n_shards, const uint32_t* query_start, uint32_t n_queries,
+                                   uint32_t n_entries_total, mnemo_match* out) {
+  if (!out || !query_start || (n_cands && !cands)) return -3;
+  const uint32_t n_qsigs = query_start[n_queries];
+  // group candidate records per query
+  std::vector<std::vector<Rec>> per(n_queries);
+  for (uint64_t i = 0; i < n_cands; i++) {
+    if (cands[i].query >= n_queries) return -3;
+    per[cands[i].query].push_back(Rec{cands[i].entry, cands[i].score, cands[i].n_matches});
+  }
+  // The group the reference never flushes is the greatest (entry, signature) over the WHOLE
+  // database (search.c:147-165).  Every shard left out its own greatest group; all but the globally
+  // greatest one have to be scored after all.  last is laid out [shard][query signature].
+  if (last && n_shards > 1) {
+    for (uint32_t q = 0; q < n_queries; q++)
+      for (uint32_t s = query_start[q]; s < query_start[q + 1]; s++) {
+        int top = -1;
+        for (uint32_t r = 0; r < n_shards; r++) {
+          const mnemo_lastgroup& g = last[(uint64_t)r * n_qsigs + s];
+          if (!g.has) continue;
+          if (top < 0) {
+            top = (int)r;
+            continue;
+          }
+          const mnemo_lastgroup& t = last[(uint64_t)top * n_qsigs + s];
+          if (g.entry > t.entry || (g.entry == t.entry && g.sig > t.sig)) top = (int)r;
+        }
+        for (uint32_t r = 0; r < n_shards; r++) {
+          const mnemo_lastgroup& g = last[(uint64_t)r * n_qsigs + s];
+          if (!g.has || (int)r == top) continue;
+          if (g.hits >= 2 && g.score >= 30) {
+            bool found = false;
+            for (Rec& rec : per[q])
+              if (rec.entry == (int32_t)g.entry) {
+                rec.score += (float)g.score;
+                rec.n += 1;
+                found = true;
+                break;
+              }
+            if (!found) per[q].push_back(Rec{(int32_t)g.entry, (float)g.score, 1});
+          }
+        }
+      }
+  }
+  for (uint32_t q = 0; q < n_queries; q++) {
+    std::sort(per[q].begin(), per[q].end(), [](const Rec& a, const Rec& b) { return a.entry < b.entry; });
+    out[q] = select_best(per[q], n_entries_total);
+  }
+  return 0;
+}
+
+extern "C" int mnemo_search_batch(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
+                                  uint32_t n_queries, mnemo_match* out, uint64_t* stats) {
+  if (!db || !out) return -3;
+  for (uint32_t q = 0; q < n_queries; q++) out[q] = mnemo_match{-7, 0.0f, 0};
+  if (n_queries == 0) return 0;
+  uint64_t cap = std::max<uint64_t>(1024, (uint64_t)n_queries * 64), n = 0;
+  std::vector<mnemo_cand> cands;
+  int rc;
+  for (;;) {
+    cands.resize(cap);
+    rc = mnemo_search_shard(db, query_sigs, query_start, n_queries, cands.data(), cap, &n, nullptr, stats);
+    if (rc == -1 && n > cap) {   // capacity: retry once with the exact size
+      cap = n;
+      continue;
+    }
+    break;
+  }
+  if (rc != 0) return rc;
+  return mnemo_search_finish(cands.data(), n, nullptr, 1, query_start, n_queries, db->entry_base + db->n_entries, out);
+}

@@ -1,0 +1,428 @@
+// k_search.cu — LSH table build, batched bucket probing and candidate scoring.
+//
+// Replaces create_hash_tables / get_matches (lsh.c:55-112) and the per-signature body of
+// search (search.c:122-168).
+//
+// Build.  The reference keeps 25 chained hash tables of `size` = total_signatures/2 heads
+// (lsh.c:61) and inserts every signature under slot = big-endian-u32(bytes 4k..4k+3) % size
+// (lsh.c:49-52,74).  Here each table is a CSR: one histogram pass (global reductions), one
+// exclusive scan over the 25*size counters, one scatter pass.  A bucket holds exactly the
+// members of the reference's chain (collisions through the modulo included).
+//
+// Probe + score.  For one query signature the reference concatenates the 25 probed chains,
+// sorts the (entry, signature) pairs, and deep-checks every pair that occurs at least twice,
+// except the last group in sort order, which its loop never flushes (search.c:147-165).
+// One CTA per query signature:
+//   1. 25 lanes compute the probe ranges; L = total candidates;
+//   2. all threads stream the candidate ids (coalesced within a bucket) through a shared-memory
+//      bitmap with atomicOr: an id seen "again" (or colliding in the bitmap) goes to a short list;
+//      the block also keeps the greatest id = the reference's never-flushed last group;
+//   3. the short list is de-duplicated in a shared-memory hash set;
+//   4. one warp per surviving id reads that database signature once (25 lanes x 4 bytes): the exact
+//      number of shared buckets is recomputed from the signature itself (so bitmap collisions are
+//      harmless) and the 100-byte equality count is a byte-wise compare; pairs with >= 2 shared
+//      buckets and >= 30 equal bytes add (score, 1) to the query's per-entry accumulators.
+// Traffic per query signature = 100 + 25*8 + 4*L + 100*D' bytes, D' = deep checks
+// plus the few bitmap false positives.
+#include "common.cuh"
+#include "search_internal.h"
+
+namespace mnemo {
+
+// ------------------------------------------------------------------ build ----
+
+__device__ __forceinline__ uint32_t bucket_key(uint32_t word_le) { return __byte_perm(word_le, 0, 0x0123); }
+
+// one thread per (signature, table)
+__global__ void __launch_bounds__(256) lsh_count_kernel(const uint32_t* __restrict__ sig_words, uint64_t n_sigs,
+                                                        uint32_t size, uint32_t* __restrict__ counts) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_sigs * kTables) return;
+  const uint32_t slot = bucket_key(sig_words[i]) % size;   // word i = signature i/25, table i%25
+  atomicAdd(&counts[(uint64_t)(i % kTables) * size + slot], 1u);
+}
+
+__global__ void __launch_bounds__(256) lsh_scatter_kernel(const uint32_t* __restrict__ sig_words, uint64_t n_sigs,
+                                                          uint32_t size, uint32_t* __restrict__ cursor,
+                                                          uint32_t* __restrict__ ids) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_sigs * kTables) return;
+  const uint32_t slot = bucket_key(sig_words[i]) % size;
+  const uint32_t pos = atomicAdd(&cursor[(uint64_t)(i % kTables) * size + slot], 1u);
+  ids[pos] = (uint32_t)(i / kTables);
+}
+
+__global__ void __launch_bounds__(256) sig_entry_kernel(const uint32_t* __restrict__ entry_start, uint32_t n_entries,
+                                                        uint64_t n_sigs, uint32_t* __restrict__ sig_entry) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_sigs) return;
+  sig_entry[g] = find_segment<uint32_t>(entry_start, n_entries, (uint32_t)g);
+}
+
+// ---- exclusive scan of a long u32 array (3 kernels) ----
+constexpr int kScanT = 256, kScanE = 8, kScanB = kScanT * kScanE;
+
+__device__ __forceinline__ uint32_t blk_excl(uint32_t v, uint32_t* ws, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) ws[warp] = incl;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kScanT / 32; ++w) {
+    const uint32_t s = ws[w];
+    base += w < warp ? s : 0u;
+    tot += s;
+  }
+  *total = tot;
+  __syncthreads();
+  return base + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanT) scan_reduce_kernel(const uint32_t* __restrict__ in, uint64_t n,
+                                                             uint32_t* __restrict__ block_sums) {
+  __shared__ uint32_t ws[kScanT / 32];
+  const uint64_t base = (uint64_t)blockIdx.x * kScanB + (uint64_t)threadIdx.x * kScanE;
+  uint32_t c = 0;
+#pragma unroll
+  for (int k = 0; k < kScanE; ++k) c += (base + k < n) ? in[base + k] : 0u;
+  uint32_t tot;
+  blk_excl(c, ws, &tot);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kScanT) scan_sums_kernel(uint32_t* __restrict__ block_sums, uint32_t n_blocks) {
+  __shared__ uint32_t ws[kScanT / 32];
+  uint32_t carry = 0;
+  for (uint32_t b0 = 0; b0 < n_blocks; b0 += kScanT) {
+    const uint32_t i = b0 + threadIdx.x;
+    const uint32_t v = i < n_blocks ? block_sums[i] : 0u;
+    uint32_t tot;
+    const uint32_t ex = blk_excl(v, ws, &tot);
+    if (i < n_blocks) block_sums[i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) block_sums[n_blocks] = carry;
+}
+
+// out[i] = exclusive prefix; also out2 (a second copy used as the scatter cursor); out[n] = total
+__global__ void __launch_bounds__(kScanT) scan_apply_kernel(const uint32_t* __restrict__ in, uint64_t n,
+                                                            const uint32_t* __restrict__ block_sums,
+                                                            uint32_t* __restrict__ out, uint32_t* __restrict__ out2) {
+  __shared__ uint32_t ws[kScanT / 32];
+  const uint64_t base = (uint64_t)blockIdx.x * kScanB + (uint64_t)threadIdx.x * kScanE;
+  uint32_t v[kScanE], c = 0;
+#pragma unroll
+  for (int k = 0; k < kScanE; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0u;
+    c += v[k];
+  }
+  uint32_t tot;
+  uint32_t p = block_sums[blockIdx.x] + blk_excl(c, ws, &tot);
+#pragma unroll
+  for (int k = 0; k < kScanE; ++k) {
+    if (base + k < n) {
+      out[base + k] = p;
+      out2[base + k] = p;
+    }
+    p += v[k];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = block_sums[gridDim.x];
+}
+
+uint32_t lsh_scan_blocks(uint64_t n_slots) { return (uint32_t)((n_slots + kScanB - 1) / kScanB); }
+
+void launch_lsh_build(const uint8_t* sigs, uint64_t n_sigs, const uint32_t* entry_start, uint32_t n_entries,
+                      uint32_t size, uint32_t* counts, uint32_t* start, uint32_t* cursor, uint32_t* block_sums,
+                      uint32_t* ids, uint32_t* sig_entry, cudaStream_t st) {
+  const uint64_t n_words = n_sigs * kTables;
+  const uint64_t n_slots = (uint64_t)size * kTables;
+  if (n_sigs == 0 || size == 0) return;
+  const uint32_t* words = reinterpret_cast<const uint32_t*>(sigs);
+  cudaMemsetAsync(counts, 0, n_slots * sizeof(uint32_t), st);
+  lsh_count_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(words, n_sigs, size, counts);
+  const uint32_t n_blocks = (uint32_t)((n_slots + kScanB - 1) / kScanB);
+  scan_reduce_kernel<<<n_blocks, kScanT, 0, st>>>(counts, n_slots, block_sums);
+  scan_sums_kernel<<<1, kScanT, 0, st>>>(block_sums, n_blocks);
+  scan_apply_kernel<<<n_blocks, kScanT, 0, st>>>(counts, n_slots, block_sums, start, cursor);
+  lsh_scatter_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(words, n_sigs, size, cursor, ids);
+  sig_entry_kernel<<<(unsigned)((n_sigs + 255) / 256), 256, 0, st>>>(entry_start, n_entries, n_sigs, sig_entry);
+}
+
+// ------------------------------------------------------------------ probe + score ----
+
+constexpr int kSearchThreads = 256;
+constexpr uint32_t kDupCap = 4096;        // short list capacity (ids seen "again")
+constexpr uint32_t kSetCap = 8192;        // hash set slots for de-duplication (power of two, > kDupCap)
+constexpr uint32_t kBitmapMaxWords = 32768;   // 128 KB
+constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+constexpr uint32_t kPassCap = 32768;         // candidates per id-space partition
+
+size_t search_smem_bytes() { return sizeof(uint32_t) * (kBitmapMaxWords + kDupCap + kSetCap + kDupCap); }
+
+struct Probe {
+  uint32_t begin[kTables];
+  uint32_t prefix[kTables + 1];
+  uint32_t qslot[kTables];
+  uint32_t qword[kTables];
+};
+
+// Deep check of one database signature against the query, by one warp.  Returns (hits, score).
+__device__ __forceinline__ void check_pair(const uint32_t* __restrict__ db_words, uint32_t g, const Probe& pr,
+                                           uint32_t size, int lane, uint32_t* hits, uint32_t* score) {
+  uint32_t h = 0, eq = 0;
+  if (lane < kTables) {
+    const uint32_t w = __ldg(db_words + (uint64_t)g * kTables + lane);
+    h = (bucket_key(w) % size) == pr.qslot[lane];
+    eq = __popc(__vcmpeq4(w, pr.qword[lane])) >> 3;   // search.c:35-43: number of equal bytes
+  }
+  *hits = __popc(__ballot_sync(0xffffffffu, h));
+  *score = __reduce_add_sync(0xffffffffu, eq);
+}
+
+__device__ __forceinline__ int table_of(const Probe& pr, uint32_t i) {
+  int k = 0;
+#pragma unroll
+  for (int s = 16; s; s >>= 1)
+    if (k + s <= kTables - 1 && pr.prefix[k + s] <= i) k += s;
+  return k;   // largest k with prefix[k] <= i
+}
+
+__global__ void __launch_bounds__(kSearchThreads)
+    search_probe_kernel(SearchParams p) {
+  extern __shared__ __align__(16) uint32_t sm[];
+  uint32_t* bitmap = sm;
+  uint32_t* dup = bitmap + kBitmapMaxWords;
+  uint32_t* set = dup + kDupCap;
+  uint32_t* uniq = set + kSetCap;
+  __shared__ Probe pr;
+  __shared__ uint32_t s_ndup, s_nuniq, s_gmax;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t qs = blockIdx.x;   // query-signature index
+  const uint32_t* __restrict__ qwords = reinterpret_cast<const uint32_t*>(p.query_sigs) + (uint64_t)qs * kTables;
+
+  if (tid < kTables) {
+    const uint32_t w = qwords[tid];
+    const uint32_t slot = bucket_key(w) % p.size;
+    pr.qword[tid] = w;
+    pr.qslot[tid] = slot;
+    const uint32_t b = p.start[(uint64_t)tid * p.size + slot], e = p.start[(uint64_t)tid * p.size + slot + 1];
+    pr.begin[tid] = b;
+    pr.prefix[tid + 1] = e - b;
+  }
+  if (tid == 0) {
+    pr.prefix[0] = 0;
+    s_gmax = 0;
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int k = 0; k < kTables; ++k) pr.prefix[k + 1] += pr.prefix[k];
+  __syncthreads();
+  const uint32_t L = pr.prefix[kTables];
+  const uint32_t query = find_segment<uint32_t>(p.query_start, p.n_queries, qs);
+  mnemo_lastgroup_dev lg = {0, 0, 0, 0};
+  if (L == 0) {
+    if (tid == 0) p.last[qs] = lg;
+    return;
+  }
+  // Candidates are handled in n_pass partitions of the id space (one for ordinary list lengths) so
+  // that the bitmap stays sparse; each partition re-streams the ids (4 bytes each).
+  const uint32_t n_pass = (L + kPassCap - 1) / kPassCap;
+  const uint32_t per_pass = (L + n_pass - 1) / n_pass;
+  uint32_t bm_words = 1024;   // ~64 bitmap bits per candidate, 4 KB .. 128 KB
+  while (bm_words < kBitmapMaxWords && bm_words < 2 * per_pass) bm_words <<= 1;
+  const uint32_t bm_shift = 32 - (31 - __clz(bm_words * 32));
+  const uint32_t* __restrict__ dbw = reinterpret_cast<const uint32_t*>(p.db_sigs);
+  uint32_t deep = 0, gmax = 0;
+
+  for (uint32_t pass = 0; pass < n_pass; ++pass) {
+    for (uint32_t i = tid; i < bm_words; i += kSearchThreads) bitmap[i] = 0;
+    for (uint32_t i = tid; i < kSetCap; i += kSearchThreads) set[i] = kEmpty;
+    if (tid == 0) {
+      s_ndup = 0;
+      s_nuniq = 0;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < L; i += kSearchThreads) {
+      const int k = table_of(pr, i);
+      const uint32_t g = __ldg(p.ids + pr.begin[k] + (i - pr.prefix[k]));
+      if (pass == 0) gmax = max(gmax, g);
+      if (n_pass > 1 && ((g * 2246822519u) >> 7) % n_pass != pass) continue;
+      const uint32_t h = (g * 2654435761u) >> bm_shift;
+      const uint32_t bit = 1u << (h & 31u);
+      const uint32_t old = atomicOr(&bitmap[h >> 5], bit);
+      if (old & bit) {
+        const uint32_t pos = atomicAdd(&s_ndup, 1u);
+        if (pos < kDupCap) dup[pos] = g;
+      }
+    }
+    if (pass == 0) {
+      gmax = __reduce_max_sync(0xffffffffu, gmax);
+      if (lane == 0) atomicMax(&s_gmax, gmax);
+    }
+    __syncthreads();
+    gmax = s_gmax;
+    const uint32_t ndup = s_ndup;
+    if (ndup <= kDupCap) {
+      // de-duplicate the short list, then one warp per distinct id
+      for (uint32_t i = tid; i < ndup; i += kSearchThreads) {
+        const uint32_t g = dup[i];
+        uint32_t h = (g * 2246822519u) & (kSetCap - 1);
+        while (true) {
+          const uint32_t prev = atomicCAS(&set[h], kEmpty, g);
+          if (prev == kEmpty) {
+            uniq[atomicAdd(&s_nuniq, 1u)] = g;
+            break;
+          }
+          if (prev == g) break;
+          h = (h + 1) & (kSetCap - 1);
+        }
+      }
+      __syncthreads();
+      const uint32_t nuniq = s_nuniq;
+      for (uint32_t i = warp; i < nuniq; i += kSearchThreads / 32) {
+        const uint32_t g = uniq[i];
+        if (g == gmax) continue;   // search.c:147-165: the last group is never flushed
+        uint32_t hits, score;
+        check_pair(dbw, g, pr, p.size, lane, &hits, &score);
+        if (hits >= 2) {           // MIN_BUCKET_MATCH_FOR_DEEP_CHECK (search.c:11)
+          ++deep;
+          if (score >= 30 && lane == 0) {   // MIN_SCORE (search.c:16)
+            const uint64_t a = (uint64_t)query * p.n_entries + p.sig_entry[g];
+            atomicAdd(&p.acc_score[a], score);
+            atomicAdd(&p.acc_n[a], 1u);
+          }
+        }
+      }
+    } else {
+      // More repeats than the short list holds (pathological buckets): no list at all.  One warp
+      // per candidate recomputes the exact shared-bucket mask from the signature, and the pair is
+      // scored only from its lowest matching table, i.e. exactly once.
+      for (uint32_t i = warp; i < L; i += kSearchThreads / 32) {
+        const int k = table_of(pr, i);
+        const uint32_t g = __ldg(p.ids + pr.begin[k] + (i - pr.prefix[k]));
+        if (g == gmax) continue;
+        if (n_pass > 1 && ((g * 2246822519u) >> 7) % n_pass != pass) continue;
+        uint32_t h = 0, eq = 0;
+        if (lane < kTables) {
+          const uint32_t w = __ldg(dbw + (uint64_t)g * kTables + lane);
+          h = (bucket_key(w) % p.size) == pr.qslot[lane];
+          eq = __popc(__vcmpeq4(w, pr.qword[lane])) >> 3;
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, h);
+        const uint32_t score = __reduce_add_sync(0xffffffffu, eq);
+        if (__popc(mask) >= 2 && (__ffs(mask) - 1) == k) {
+          ++deep;
+          if (score >= 30 && lane == 0) {
+            const uint64_t a = (uint64_t)query * p.n_entries + p.sig_entry[g];
+            atomicAdd(&p.acc_score[a], score);
+            atomicAdd(&p.acc_n[a], 1u);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (warp == 0) {
+    uint32_t hits, score;
+    check_pair(dbw, gmax, pr, p.size, lane, &hits, &score);
+    if (lane == 0) {
+      lg.has = 1;
+      lg.g = gmax;
+      lg.hits = hits;
+      lg.score = score;
+      p.last[qs] = lg;
+    }
+  }
+  if (lane == 0) {
+    if (deep) atomicAdd(p.stat_deep, (unsigned long long)deep);
+    if (warp == 0) atomicAdd(p.stat_nodes, (unsigned long long)L);
+  }
+}
+
+// Per query: compact the non-zero per-entry accumulators into candidate records, ascending entry.
+__global__ void __launch_bounds__(256) search_compact_kernel(const uint32_t* __restrict__ acc_score,
+                                                             const uint32_t* __restrict__ acc_n, uint32_t n_entries,
+                                                             uint32_t entry_base, CandDev* __restrict__ cands,
+                                                             uint32_t cap, uint32_t* __restrict__ total,
+                                                             uint32_t* __restrict__ q_base, uint32_t* __restrict__ q_cnt) {
+  __shared__ uint32_t ws[8];
+  __shared__ uint32_t s_base;
+  const uint32_t q = blockIdx.x;
+  const uint32_t* __restrict__ rn = acc_n + (uint64_t)q * n_entries;
+  const uint32_t* __restrict__ rs = acc_score + (uint64_t)q * n_entries;
+  const uint32_t per = (n_entries + 255) / 256;
+  const uint32_t lo = min(n_entries, threadIdx.x * per), hi = min(n_entries, lo + per);
+  uint32_t c = 0;
+  for (uint32_t e = lo; e < hi; ++e) c += rn[e] != 0;
+  uint32_t tot;
+  uint32_t off = blk_excl(c, ws, &tot);
+  if (threadIdx.x == 0) {
+    s_base = tot ? atomicAdd(total, tot) : 0;
+    q_base[q] = s_base;
+    q_cnt[q] = tot;
+  }
+  __syncthreads();
+  off += s_base;
+  for (uint32_t e = lo; e < hi; ++e)
+    if (rn[e] != 0) {
+      if (off < cap) {
+        CandDev r;
+        r.query = q;
+        r.entry = (int32_t)(entry_base + e);
+        r.score = (float)rs[e];
+        r.n_matches = (int32_t)rn[e];
+        cands[off] = r;
+      }
+      ++off;
+    }
+}
+
+// get_matches for one signature: gather (global id) of every bucket member, table by table
+__global__ void __launch_bounds__(256) search_gather_kernel(SearchParams p, uint32_t* __restrict__ out, uint32_t cap,
+                                                            uint32_t* __restrict__ table_counts) {
+  __shared__ Probe pr;
+  const int tid = threadIdx.x;
+  const uint32_t* __restrict__ qwords = reinterpret_cast<const uint32_t*>(p.query_sigs);
+  if (tid < kTables) {
+    const uint32_t slot = bucket_key(qwords[tid]) % p.size;
+    const uint32_t b = p.start[(uint64_t)tid * p.size + slot], e = p.start[(uint64_t)tid * p.size + slot + 1];
+    pr.begin[tid] = b;
+    pr.prefix[tid + 1] = e - b;
+    table_counts[tid] = e - b;
+  }
+  if (tid == 0) pr.prefix[0] = 0;
+  __syncthreads();
+  if (tid == 0)
+    for (int k = 0; k < kTables; ++k) pr.prefix[k + 1] += pr.prefix[k];
+  __syncthreads();
+  const uint32_t L = pr.prefix[kTables];
+  for (uint32_t i = tid; i < L && i < cap; i += 256) {
+    int k = 0;
+    while (k < kTables - 1 && pr.prefix[k + 1] <= i) ++k;
+    out[i] = p.ids[pr.begin[k] + (i - pr.prefix[k])];
+  }
+}
+
+void launch_search(const SearchParams& p, uint32_t n_query_sigs, cudaStream_t st) {
+  if (!n_query_sigs) return;
+  cudaFuncSetAttribute(search_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes());
+  search_probe_kernel<<<n_query_sigs, kSearchThreads, search_smem_bytes(), st>>>(p);
+}
+void launch_search_compact(const uint32_t* acc_score, const uint32_t* acc_n, uint32_t n_queries, uint32_t n_entries,
+                           uint32_t entry_base, CandDev* cands, uint32_t cap, uint32_t* total, uint32_t* q_base,
+                           uint32_t* q_cnt, cudaStream_t st) {
+  if (n_queries) search_compact_kernel<<<n_queries, 256, 0, st>>>(acc_score, acc_n, n_entries, entry_base, cands, cap,
+                                                                  total, q_base, q_cnt);
+}
+void launch_search_gather(const SearchParams& p, uint32_t* out, uint32_t cap, uint32_t* table_counts, cudaStream_t st) {
+  search_gather_kernel<<<1, 256, 0, st>>>(p, out, cap, table_counts);
+}
+
+}  // namespace mnemo

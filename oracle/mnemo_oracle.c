@@ -388,6 +388,20 @@ float mo_logf_glibc(float x, int variant) {
   return (float)(y * r2 + (y0 + r));
 }
 
+/* counts floats in [lo_bits, hi_bits] where the restatement differs from this host's logf */
+uint64_t mo_logf_check(uint32_t lo_bits, uint32_t hi_bits, int variant) {
+  uint64_t bad = 0;
+  for (uint64_t b = lo_bits; b <= hi_bits; b++) {
+    uint32_t u = (uint32_t)b;
+    float x, a, c;
+    memcpy(&x, &u, 4);
+    a = logf(x);
+    c = mo_logf_glibc(x, variant);
+    bad += memcmp(&a, &c, 4) != 0;
+  }
+  return bad;
+}
+
 /* --------------------------------------------------------------------- search ---- */
 
 /* lsh.c:49-52 — big-endian u32 of bytes 4k..4k+3. */

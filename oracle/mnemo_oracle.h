@@ -67,6 +67,7 @@ int mo_fingerprint_pcm(const int16_t* pcm, uint64_t n_frames, int channels, uint
 /* glibc 2.39 logf (sysdeps/ieee754/flt-32/e_logf.c) restated for x in [2^-126, inf):
  * variant 0 = build without FMA contraction, 1 = the -mfma ifunc variant. */
 float mo_logf_glibc(float x, int variant);
+uint64_t mo_logf_check(uint32_t lo_bits, uint32_t hi_bits, int variant);
 
 /* search side: database = concatenated signatures + per-entry counts */
 typedef struct mo_db {

@@ -41,6 +41,8 @@ class Oracle:
         lib.mo_n_frames.argtypes = [C.c_uint32]
         lib.mo_n_images.argtypes = [C.c_uint32]
         lib.mo_get_matches.restype = C.c_uint32
+        lib.mo_logf_check.restype = C.c_uint64
+        lib.mo_logf_check.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
 
     # tables
     def taps(self):
@@ -105,6 +107,9 @@ class Oracle:
 
     def logf(self, x: float, variant: int) -> float:
         return self.lib.mo_logf_glibc(C.c_float(x), variant)
+
+    def logf_check(self, lo_bits: int, hi_bits: int, variant: int) -> int:
+        return int(self.lib.mo_logf_check(lo_bits, hi_bits, variant))
 
     def fingerprint_samples(self, s, taps=False):
         s = np.ascontiguousarray(s, np.float32)

@@ -1,0 +1,158 @@
+"""GPU: LSH build + batched search through the C ABI against the oracle / reference / golden results."""
+import os
+
+import numpy as np
+import pytest
+
+from mnemophonix_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def corpus(ctx):
+    pcms = [synth.synth_track(4000 + i, 20.0 + 3 * (i % 4), 1 + (i % 2)) for i in range(12)]
+    sigs, st = ctx.index_pcm_batch(pcms)
+    assert all(s == 0 for s in st)
+    clips = [np.ascontiguousarray(p[6 * 44100 + 1234: 11 * 44100 + 1234]) for p in pcms]
+    qs, st = ctx.index_pcm_batch(clips)
+    return sigs, qs
+
+
+def test_golden_search_results(ctx):
+    g = np.load(os.path.join(HERE, "golden", "search_golden.npz"))
+    n = int(g["n_tracks"][0])
+    tracks = [g[f"track{i}"] for i in range(n)]
+    db = capi.Db(ctx, tracks)
+    queries = [g[f"query{i}"] for i in range(n + 1)] + [tracks[1]]
+    res, (L, D) = db.search(queries)
+    assert [r[0] for r in res] == g["results"].tolist()
+    assert db.get_matches(g["gm0_sig"]) == [tuple(x) for x in g["gm0"].tolist()]
+    assert db.get_matches(g["gm1_sig"]) == [tuple(x) for x in g["gm1"].tolist()]
+    db.close()
+
+
+def test_scores_and_stats_equal_oracle(ctx, oracle, corpus):
+    sigs, qs = corpus
+    db = capi.Db(ctx, sigs)
+    odb = oracle.make_db(sigs)
+    assert db.table_size == sum(len(s) for s in sigs) // 2           # lsh.c:61
+    res, (L, D) = db.search(qs)
+    cands, last, qstart, _ = db.search_shard(qs)
+    Lo = Do = 0
+    for q, (query, r) in enumerate(zip(qs, res)):
+        best, sc, l, d = oracle.search(odb, query)
+        Lo += l
+        Do += d
+        assert r[0] == best == q                                     # identified track identical, and right
+        mine = cands[cands["query"] == q]
+        dense = np.zeros_like(sc)
+        dense[mine["entry"], 0] = mine["score"]
+        dense[mine["entry"], 1] = mine["n_matches"]
+        assert np.array_equal(dense, sc)                             # per-entry (score, n_matches) identical
+    assert (L, D) == (Lo, Do)                                        # probed nodes / deep checks identical
+    db.close()
+
+
+def test_self_search_reproduces_the_dropped_last_group(ctx, oracle, corpus):
+    sigs, _ = corpus
+    db = capi.Db(ctx, sigs)
+    odb = oracle.make_db(sigs)
+    res, _ = db.search([sigs[3], sigs[11]])
+    for r, e in zip(res, (3, 11)):
+        best, sc, _, _ = oracle.search(odb, sigs[e])
+        assert r == (best, float(sc[e, 0]), int(sc[e, 1]))
+        # a flush-corrected loop would count one more match per query signature whose own group is last
+        assert sc[e, 1] < len(sigs[e]) + 10 * len(sigs[e])
+    db.close()
+
+
+def test_unrelated_and_empty_queries(ctx, corpus):
+    sigs, _ = corpus
+    db = capi.Db(ctx, sigs)
+    rng = np.random.RandomState(1)
+    noise = rng.randint(0, 255, (34, 100)).astype(np.uint8)
+    res, _ = db.search([noise, np.zeros((0, 100), np.uint8), sigs[0][:5]])
+    assert res[0][0] == -7 and res[1][0] == -7
+    db.close()
+
+
+def test_tiny_databases(ctx, oracle):
+    one = [np.full((1, 100), 7, np.uint8)]
+    db = capi.Db(ctx, one)                       # total_signatures/2 == 0: the reference would divide by zero
+    assert db.table_size == 0
+    assert db.search([one[0]])[0][0][0] == -7
+    db.close()
+    rng = np.random.RandomState(2)
+    two = [rng.randint(0, 4, (3, 100)).astype(np.uint8), rng.randint(0, 4, (2, 100)).astype(np.uint8)]
+    db = capi.Db(ctx, two)
+    odb = oracle.make_db(two)
+    res, _ = db.search([two[0], two[1]])
+    assert [r[0] for r in res] == [oracle.search(odb, two[0])[0], oracle.search(odb, two[1])[0]]
+    db.close()
+
+
+def test_modulo_collisions_count_as_hits(ctx, oracle):
+    # lsh.c:74,94: buckets are key % size; signatures whose keys differ by a multiple of size collide
+    rng = np.random.RandomState(3)
+    base = rng.randint(0, 200, (40, 100)).astype(np.uint8)
+    entries = [base[:20].copy(), base[20:].copy()]
+    size = 20
+    q = base[5].copy()[None, :].repeat(12, 0)
+    # alter bytes so that keys differ from entry 0 / sig 5 yet land in the same slots: add `size` to the
+    # big-endian key of tables 0 and 1 (low byte + 20 stays < 256)
+    q[:, 3] = (q[:, 3].astype(int) % 200 + size).astype(np.uint8)
+    entries[0][5, 3] = q[0, 3] - size
+    db = capi.Db(ctx, entries)
+    odb = oracle.make_db(entries)
+    assert db.table_size == size
+    res, (L, D) = db.search([q])
+    best, sc, Lo, Do = oracle.search(odb, q)
+    assert (res[0][0], L, D) == (best, Lo, Do)
+    db.close()
+
+
+def test_sharded_search_equals_single_database(ctx, oracle, corpus):
+    """Database split into contiguous entry ranges (one shard per GPU in production): every shard uses
+    the GLOBAL table size, drops its own last group, and the merge restores all but the global one."""
+    sigs, qs = corpus
+    total = sum(len(s) for s in sigs)
+    single = capi.Db(ctx, sigs)
+    want, _ = single.search(qs + [sigs[2]])
+    single.close()
+    for cuts in ([0, 5, 12], [0, 3, 6, 9, 12], [0, 11, 12]):
+        shards = [capi.Db(ctx, sigs[a:b], table_size=total // 2, entry_base=a) for a, b in zip(cuts[:-1], cuts[1:])]
+        parts = [s.search_shard(qs + [sigs[2]]) for s in shards]
+        cands = np.concatenate([p[0] for p in parts])
+        last = np.stack([p[1] for p in parts])
+        got = capi.search_finish(cands, last, len(shards), parts[0][2], len(sigs))
+        assert got == want
+        for s in shards:
+            s.close()
+
+
+def test_long_buckets_take_the_partitioned_path(ctx, oracle):
+    """Many near-identical signatures make one bucket tens of thousands long and push the number of
+    repeated candidates past the shared-memory short list: exercises the id-space partitions and the
+    list-free fallback of the probe kernel."""
+    rng = np.random.RandomState(5)
+    proto = rng.randint(0, 250, 100).astype(np.uint8)
+    e0 = np.repeat(proto[None, :], 6000, 0)
+    e0[:, 8:] = rng.randint(0, 250, (6000, 92))          # tables 0,1 identical for all, the rest random
+    e1 = rng.randint(0, 250, (500, 100)).astype(np.uint8)
+    e1[:, :4] = proto[:4]                                 # only table 0 in common
+    q = np.repeat(proto[None, :], 3, 0)
+    q[1, 4:8] = 1
+    db = capi.Db(ctx, [e0, e1])
+    odb = oracle.make_db([e0, e1])
+    res, (L, D) = db.search([q])
+    best, sc, Lo, Do = oracle.search(odb, q)
+    assert (res[0][0], L, D) == (best, Lo, Do)
+    cands, _, _, _ = db.search_shard([q])
+    dense = np.zeros_like(sc)
+    dense[cands["entry"], 0] = cands["score"]
+    dense[cands["entry"], 1] = cands["n_matches"]
+    assert np.array_equal(dense, sc)
+    db.close()
