@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 index path (BASELINE.json config #2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--seconds S]
+
+Workload: index ONE 2-hour synthetic 44.1 kHz 16-bit STEREO track (1.27 GB of PCM, 77 500 spectral
+images) per GPU.  A "step" is one pass of the whole hot path (PCM -> signatures) over that track.
+  value   audio-hours fingerprinted per second, whole job, PCM already resident in HBM
+          (CUDA events on the launching stream, max over ranks);
+  e2e     the same through the C ABI with HOST buffers: pinned-host -> device copy of the PCM,
+          kernels, device -> host copy of the signatures, every step;
+  roofline  the dominant kernel's algorithmic bytes / its measured duration against measured HBM;
+  cpu_baseline  the unmodified reference (oracle/_ref, -O2 build) on this box's host cores on a
+          bounded sample of the same workload (N = 1, rank 0 only).
+N > 1 (torchrun, one rank per GPU): indexing shards whole tracks across GPUs with no data-path
+collective; every rank indexes its own 2-hour track (weak scaling), value = N tracks / max time.
+--impl reference: the reference's own CPU implementation timed on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "audio-hours fingerprinted/s/GPU at 1/2/4/8 B200 (% HBM roofline); search queries/s"
+UNIT = "audio-hours/s"
+BYTES_PER_AUDIO_SECOND = {1: 44100 * 2 * 1 + 100 * 5512.5 / 512, 2: 44100 * 2 * 2 + 100 * 5512.5 / 512}
+
+
+def make_track(seconds: float, channels: int, seed: int) -> np.ndarray:
+    """2 h of synthetic audio: a 10-minute synthetic take (SURVEY.md §8d generator) tiled."""
+    from mnemophonix_b200 import synth
+    take = min(seconds, 600.0)
+    base = synth.synth_track(seed, take, channels)
+    reps = int(np.ceil(seconds / take))
+    pcm = np.tile(base, (reps, 1))[: int(round(seconds * 44100))]
+    return np.ascontiguousarray(pcm)
+
+
+# ------------------------------------------------------------------------------ clocks ----
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------- reference arm ----
+def reference_throughput(seconds_sample: float, channels: int, steps: int, warmup: int):
+    """Times the unmodified reference (oracle/_ref -O2, generate_fingerprint on a WAV file) on the host
+    cores: P = cores // 2 (at most 32) concurrent processes, each with the library's own 8 threads per stage
+    (spectralimages.c:11), each fingerprinting the sample; this is the configuration that saturated the
+    survey's box."""
+    from mnemophonix_b200 import synth
+    from oracle import ref as refmod
+    if not refmod.available("O2"):
+        return None
+    cores = os.cpu_count() or 1
+    # ~1/3 of the reference's pipeline is serial, so one process per 2 cores keeps the box busy
+    procs = max(1, min(32, cores // 2))
+    pcm = make_track(seconds_sample, channels, seed=1)
+    tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    path = os.path.join(tmpdir, f"mnemo_bench_{os.getpid()}.wav")
+    synth.write_wav(path, pcm)
+    worker = (
+        "import sys, time; sys.path.insert(0, %r)\n"
+        "from oracle.ref import Ref\n"
+        "r = Ref('O2')\n"
+        "sys.stdout.write('ready\\n'); sys.stdout.flush()\n"
+        "for line in sys.stdin:\n"
+        "    t = time.perf_counter(); rc, sigs, *_ = r.fingerprint_wav(%r); dt = time.perf_counter() - t\n"
+        "    sys.stdout.write('%%d %%d %%.6f\\n' %% (rc, 0 if sigs is None else len(sigs), dt)); sys.stdout.flush()\n"
+    ) % (ROOT, path)
+    ps = [subprocess.Popen([sys.executable, "-c", worker], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
+          for _ in range(procs)]
+    try:
+        for p in ps:
+            assert p.stdout.readline().strip() == "ready"
+        times = []
+        n_sigs = None
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            for p in ps:
+                p.stdin.write("go\n")
+                p.stdin.flush()
+            for p in ps:
+                rc, n, dt = p.stdout.readline().split()
+                assert int(rc) == 0
+                n_sigs = int(n)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    finally:
+        for p in ps:
+            try:
+                p.stdin.close()
+                p.wait(timeout=5)
+            except Exception:
+                p.kill()
+        if os.path.exists(path):
+            os.remove(path)
+    ms = 1e3 * float(np.mean(times))
+    hours = procs * seconds_sample / 3600.0
+    return {"value": hours / (ms / 1e3), "ms_per_step": ms, "cores": cores, "threads": procs * 8, "procs": procs,
+            "sample": f"{procs} concurrent processes x one {seconds_sample:.0f} s {channels}-channel excerpt of the "
+                      f"workload, reference -O2 build, generate_fingerprint() on a WAV in tmpfs, tables pre-warmed",
+            "n_sigs": n_sigs}
+
+
+# ------------------------------------------------------------------------------ main ----
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seconds", type=float, default=7200.0)
+    ap.add_argument("--channels", type=int, default=2)
+    ap.add_argument("--cpu-sample-seconds", type=float, default=1200.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"index one {args.seconds / 3600:g} h synthetic 44.1 kHz 16-bit {args.channels}-channel "
+                          f"track per GPU (BASELINE.json configs[1]); PCM {args.seconds * 44100 * 2 * args.channels / 1e9:.2f} GB "
+                          "per track > 126 MB L2, so no L2 flush between steps",
+              "tracks_per_gpu": 1, "seconds_per_track": args.seconds, "channels": args.channels,
+              "parallelism": f"tracks sharded across {args.gpus} GPU(s), no data-path collective"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = reference_throughput(args.cpu_sample_seconds, args.channels, max(1, args.steps), max(0, min(args.warmup, 1)))
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
+            return
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
+                             "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+
+    import torch
+    from mnemophonix_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    stream = torch.cuda.Stream()
+    ctx = capi.Context(local_rank, stream.cuda_stream)
+    pcm = make_track(args.seconds, args.channels, seed=1 + rank)
+    pinned = torch.from_numpy(pcm).pin_memory()
+    n_frames = pcm.shape[0]
+    track = [(pinned.data_ptr(), n_frames, args.channels)]
+    batch = ctx.batch(track)
+    out_pinned = torch.empty((max(batch.cap, 1), 100), dtype=torch.uint8).pin_memory()
+    hours_per_step = args.seconds / 3600.0
+
+    # ---- device-resident: value ----
+    batch.upload()
+    batch.sync()
+    for _ in range(max(args.warmup, 3)):
+        batch.run()
+    batch.sync()
+    batch.set_timing(True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            batch.run()
+        ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_per_step = ms_total / args.steps
+    stage_ms, n_timed = batch.get_timing()
+    batch.set_timing(False)
+    launches_per_run = batch.launches()
+    value = world * hours_per_step / (ms_per_step / 1e3)
+
+    # ---- end to end through the C ABI with host buffers: e2e ----
+    for _ in range(2):
+        batch.upload()
+        batch.run()
+        batch.download(out_ptr=out_pinned.data_ptr())
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    e0.record(stream)
+    n_sigs = None
+    for _ in range(args.steps):
+        batch.upload()
+        batch.run()
+        _, n_sigs, status = batch.download(out_ptr=out_pinned.data_ptr())
+    e1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / args.steps
+    e2e_value = world * hours_per_step / (e2e_ms / 1e3)
+    h2d = int(pcm.nbytes)
+    d2h = int(batch.cap * 100 + 4)
+    assert int(status[0]) == 0 and int(n_sigs[0]) > 0
+
+    # ---- roofline of the dominant kernel ----
+    dom = max(stage_ms, key=lambda k: stage_ms[k])
+    alg_bytes = BYTES_PER_AUDIO_SECOND.get(args.channels, 44100 * 2 * args.channels + 1076.7) * args.seconds
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = alg_bytes / (stage_ms[dom] / 1e3) / 1e9 if stage_ms[dom] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": stage_ms[dom],
+                "stage_ms": stage_ms,
+                "whole_path_frac": (alg_bytes / (ms_per_step / 1e3) / 1e9) / peak,
+                "note": "the path is FP32/FP64-issue bound, not HBM bound (DESIGN.md); frac is the contract's "
+                        "algorithmic-bytes figure"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches_per_run * (args.steps * 2 + max(args.warmup, 3) + 2)),
+            "roofline": roofline, "signatures_per_track": int(n_sigs[0])}
+
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        r = reference_throughput(args.cpu_sample_seconds, args.channels, 1, 0)
+        if r is not None:
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
+                                    "sample": r["sample"], "threads": r["threads"]}
+        else:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                                    "sample": "oracle/_ref not available on this box"}
+    if rank == 0:
+        print(json.dumps(line))
+    batch.close()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -81,6 +81,11 @@ int mnemo_batch_download(mnemo_batch* b, uint8_t* sigs_out, uint64_t cap_signatu
  * 8 = float32 sequential sum of squares (float[1]).  Returns bytes written or <0. */
 int64_t mnemo_batch_read(mnemo_batch* b, int what, uint32_t track, void* dst, uint64_t dst_bytes);
 int mnemo_batch_enable_taps(mnemo_batch* b, int on);
+/* Per-stage device times (CUDA events on the context's stream), averaged over the runs since timing
+ * was switched on: [0] downmix+resample, [1] sum of squares + rms, [2] frames -> band energies,
+ * [3] image -> signature, [4] compaction.  Milliseconds. */
+int mnemo_batch_set_timing(mnemo_batch* b, int on);
+int mnemo_batch_get_timing(mnemo_batch* b, double* stage_ms_avg /* 5 */, uint32_t* n_runs);
 
 /* One-call form with host buffers: create + upload + run + download + destroy. */
 int mnemo_index_pcm_batch(mnemo_ctx* ctx, const mnemo_track* tracks, uint32_t n_tracks, uint8_t* sigs_out,
@@ -143,6 +148,11 @@ int mnemo_search_finish(const mnemo_cand* cands, uint64_t n_cands, const mnemo_l
 /* Compares the device logf against host logf for every float in [lo_bits, hi_bits]; returns the
  * number of mismatches (or <0).  Used to pin the glibc logf mirror exhaustively over [1, 256]. */
 int64_t mnemo_selftest_logf(mnemo_ctx* ctx, uint32_t lo_bits, uint32_t hi_bits);
+/* Compares the reciprocal-based exact divisions of the kernels with IEEE division on the device;
+ * returns the number of mismatches.  which 0: x / M_SQRT2 (haar.c:35-36) and 1: x / 32767.0
+ * (wav.c:373) for the n floats whose bit patterns start at lo_bits (n = 2^32 covers every float);
+ * 2: (255*v) / max (spectralimages.c:53) for n pseudo-random pairs. */
+int64_t mnemo_selftest_div(mnemo_ctx* ctx, int which, uint32_t lo_bits, uint64_t n);
 
 #ifdef __cplusplus
 }

@@ -74,10 +74,14 @@ def lib() -> C.CDLL:
         L.mnemo_batch_read.argtypes = [vp, i32, u32, vp, u64]
         L.mnemo_batch_read.restype = C.c_int64
         L.mnemo_batch_enable_taps.argtypes = [vp, i32]
+        L.mnemo_batch_set_timing.argtypes = [vp, i32]
+        L.mnemo_batch_get_timing.argtypes = [vp, vp, C.POINTER(u32)]
         L.mnemo_index_pcm_batch.argtypes = [vp, C.POINTER(Track), u32, vp, u64, vp, vp]
         L.mnemo_index_samples.argtypes = [vp, vp, u32, vp, u64, C.POINTER(u32)]
         L.mnemo_selftest_logf.argtypes = [vp, u32, u32]
         L.mnemo_selftest_logf.restype = C.c_int64
+        L.mnemo_selftest_div.argtypes = [vp, i32, u32, u64]
+        L.mnemo_selftest_div.restype = C.c_int64
         if hasattr(L, "mnemo_db_create"):
             L.mnemo_db_create.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(vp)]
             L.mnemo_db_destroy.argtypes = [vp]
@@ -139,6 +143,9 @@ class Context:
 
     def selftest_logf(self, lo_bits: int, hi_bits: int) -> int:
         return lib().mnemo_selftest_logf(self.h, lo_bits, hi_bits)
+
+    def selftest_div(self, which: int, lo_bits: int, n: int) -> int:
+        return lib().mnemo_selftest_div(self.h, which, lo_bits, n)
 
     # -- indexing -------------------------------------------------------------------
     def index_pcm_batch(self, pcms):
@@ -213,6 +220,17 @@ class Batch:
 
     def enable_taps(self, on=True):
         self.ctx._check(lib().mnemo_batch_enable_taps(self.h, 1 if on else 0), "mnemo_batch_enable_taps")
+
+    STAGES = ("k0_resample", "sumsq_rms", "k1_spectral", "k2_fingerprint", "compact")
+
+    def set_timing(self, on=True):
+        self.ctx._check(lib().mnemo_batch_set_timing(self.h, 1 if on else 0), "mnemo_batch_set_timing")
+
+    def get_timing(self) -> tuple[dict, int]:
+        ms = (C.c_double * 5)()
+        n = C.c_uint32(0)
+        self.ctx._check(lib().mnemo_batch_get_timing(self.h, ms, C.byref(n)), "mnemo_batch_get_timing")
+        return dict(zip(self.STAGES, list(ms))), n.value
 
     def download(self, out: np.ndarray | None = None, out_ptr: int | None = None):
         n = np.zeros(max(self.n, 1), np.uint32)

@@ -415,6 +415,8 @@ extern "C" void mnemo_batch_destroy(mnemo_batch* b) {
                   b->d_n_sigs,   b->d_tap_raw, b->d_tap_img,   b->d_tap_haar};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (int i = 0; i < 6; i++)
+    if (b->ev[i]) cudaEventDestroy(b->ev[i]);
   delete b;
 }
 
@@ -443,29 +445,77 @@ extern "C" int mnemo_batch_upload(mnemo_batch* b, const mnemo_track* tracks) {
   return 0;
 }
 
+static void timing_collect(mnemo_batch* b) {
+  if (!b->ev_pending) return;
+  cudaEventSynchronize(b->ev[5]);
+  for (int i = 0; i < 5; i++) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, b->ev[i], b->ev[i + 1]);
+    b->stage_ms[i] += ms;
+  }
+  b->timed_runs++;
+  b->ev_pending = false;
+}
+
+extern "C" int mnemo_batch_set_timing(mnemo_batch* b, int on) {
+  if (!b) return -3;
+  cudaSetDevice(b->ctx->device);
+  if (on && !b->ev[0])
+    for (int i = 0; i < 6; i++)
+      if (cudaEventCreate(&b->ev[i]) != cudaSuccess) return -1;
+  if (b->ev_pending) timing_collect(b);
+  b->timing = on != 0;
+  for (int i = 0; i < 5; i++) b->stage_ms[i] = 0;
+  b->timed_runs = 0;
+  return 0;
+}
+
+extern "C" int mnemo_batch_get_timing(mnemo_batch* b, double* stage_ms_avg, uint32_t* n_runs) {
+  if (!b) return -3;
+  cudaSetDevice(b->ctx->device);
+  timing_collect(b);
+  for (int i = 0; i < 5; i++) stage_ms_avg[i] = b->timed_runs ? b->stage_ms[i] / b->timed_runs : 0.0;
+  if (n_runs) *n_runs = b->timed_runs;
+  return 0;
+}
+
 extern "C" int mnemo_batch_run(mnemo_batch* b) {
   if (!b) return -3;
   mnemo_ctx* ctx = b->ctx;
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
   int launches = 0;
+  const bool tm = b->timing;
+  if (tm) {
+    timing_collect(b);   // previous run's events, if any
+    cudaEventRecord(b->ev[0], st);
+  }
   if (!b->prenormalized) {
     const uint32_t k0_tiles = b->k0_tile_prefix[b->n_tracks];
     launch_k0_resample(b->d_tracks, b->d_k0_prefix, b->n_tracks, k0_tiles, ctx->d_tables, b->d_s5512, st);
     launches += k0_tiles ? 1 : 0;
+  }
+  if (tm) cudaEventRecord(b->ev[1], st);
+  if (!b->prenormalized)
     launch_sumsq(b->d_tracks, b->n_tracks, b->n_chunks, b->d_chunk_track, b->d_s5512, b->d_chunk_true,
                  b->d_chunk_prefix, b->d_recs, b->d_sumsq, b->d_rms, st, &launches);
-  }
+  if (tm) cudaEventRecord(b->ev[2], st);
   const uint32_t k1_tiles = b->k1_tile_prefix[b->n_tracks];
   launch_k1_spectral(b->d_tracks, b->d_k1_prefix, b->n_tracks, k1_tiles, ctx->d_tables, b->d_s5512, b->d_rms, b->d_bins,
                      ctx->sm_count, st);
   launches += k1_tiles ? 1 : 0;
+  if (tm) cudaEventRecord(b->ev[3], st);
   launch_k2_fingerprint(b->d_tracks, b->d_img_prefix, b->n_tracks, b->n_images, ctx->d_tables, ctx->d_perms, b->d_bins,
                         b->d_sig_dense, b->d_keep, b->d_tap_raw, b->d_tap_img, b->d_tap_haar,
                         ctx->h_tables.logf_variant, st);
   launches += b->n_images ? 1 : 0;
+  if (tm) cudaEventRecord(b->ev[4], st);
   launch_compact(b->d_sig_dense, b->d_keep, b->n_images, b->d_img_prefix, b->n_tracks, b->d_block_sums, b->d_pos,
                  b->d_sig_out, b->d_n_sigs, st, &launches);
+  if (tm) {
+    cudaEventRecord(b->ev[5], st);
+    b->ev_pending = true;
+  }
   b->launches_per_run = (uint32_t)launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_batch_run");
@@ -621,4 +671,27 @@ extern "C" int64_t mnemo_selftest_logf(mnemo_ctx* ctx, uint32_t lo_bits, uint32_
   }
   cudaFree(d_out);
   return bad;
+}
+
+extern "C" int64_t mnemo_selftest_div(mnemo_ctx* ctx, int which, uint32_t lo_bits, uint64_t n) {
+  if (!ctx || which < 0 || which > 2) return -3;
+  cudaSetDevice(ctx->device);
+  unsigned long long* d_bad = nullptr;
+  if (cudaMalloc(&d_bad, 16) != cudaSuccess) return -1;
+  cudaMemsetAsync(d_bad, 0, 8, ctx->stream);
+  cudaMemsetAsync(d_bad + 1, 0xff, 8, ctx->stream);
+  const uint64_t kChunk = 1ull << 30;
+  for (uint64_t off = 0; off < n; off += kChunk)
+    launch_div_test(which, (uint32_t)(lo_bits + off), (n - off < kChunk) ? (n - off) : kChunk, d_bad, ctx->stream);
+  unsigned long long bad[2] = {0, 0};
+  cudaError_t e = cudaMemcpyAsync(bad, d_bad, 16, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_bad);
+  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_selftest_div");
+  if (bad[0]) {
+    char buf[96];
+    snprintf(buf, sizeof buf, "selftest_div(%d): first mismatch at input 0x%llx", which, bad[1]);
+    ctx->err = buf;
+  }
+  return (int64_t)bad[0];
 }

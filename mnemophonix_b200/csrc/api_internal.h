@@ -26,6 +26,12 @@ struct mnemo_batch {
   std::vector<uint64_t> img_prefix, pcm_off;
   uint64_t n_samples = 0, n_frames = 0, n_images = 0, n_chunks = 0;
   uint32_t launches_per_run = 0;
+  // optional per-stage timing (CUDA events on the context's stream)
+  bool timing = false;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double stage_ms[5] = {0, 0, 0, 0, 0};
+  uint32_t timed_runs = 0;
+  bool ev_pending = false;
   // device buffers
   uint8_t* d_pcm = nullptr;
   mnemo::TrackDev* d_tracks = nullptr;

@@ -78,6 +78,7 @@ void launch_compact(const uint8_t* sig_dense, const uint8_t* keep, uint64_t n_im
                     uint32_t n_tracks, uint32_t* block_sums, uint32_t* pos, uint8_t* sig_out, uint32_t* n_sigs,
                     cudaStream_t st, int* n_launches);
 void k1_upload_constants(const Tables& t);
+void launch_div_test(int which, uint32_t lo_bits, uint64_t n, unsigned long long* bad, cudaStream_t st);
 void launch_logf_range(uint32_t lo_bits, uint32_t n, int variant, float* out, cudaStream_t st);
 int k1_tile_frames();
 int k0_tile_outputs();
@@ -126,6 +127,34 @@ __device__ __forceinline__ float logf_glibc(float x) {
     return __double2float_rn(__dadd_rn(__dmul_rn(y, r2), __dadd_rn(y0, r)));
   }
 }
+
+// ---- exact division by reciprocal (Markstein) ----
+// q = RN(a / b) in double from y = RN(1 / b): q0 = RN(a*y), r0 = a - b*q0 (exact, one FMA),
+// q1 = RN(q0 + r0*y).  One more residual step gives the correctly rounded quotient whenever q1 is
+// a faithful rounding (Markstein's theorem), which it always is here.  For the two constant
+// divisors of the path (sqrt(2) in haar.c:35-36, 32767 in wav.c:373) the ONE-step form is verified
+// against IEEE division for every float dividend by mnemo_selftest_div (tests/test_gpu_index.py);
+// the per-image divisor of spectralimages.c:53 uses the two-step form.
+__device__ __forceinline__ double div_markstein1(double a, double b, double y) {
+  const double q0 = __dmul_rn(a, y);
+  const double r0 = __fma_rn(-b, q0, a);
+  return __fma_rn(r0, y, q0);
+}
+__device__ __forceinline__ double div_markstein2(double a, double b, double y) {
+  const double q1 = div_markstein1(a, b, y);
+  const double r1 = __fma_rn(-b, q1, a);
+  return __fma_rn(r1, y, q1);
+}
+// (float)((double)x / b) for the constant divisors b > 0: one-step form; a zero dividend is passed
+// through so that -0 keeps its sign (the only float for which the one-step form differs from IEEE
+// division).  mnemo_selftest_div checks all 2^32 dividends against __ddiv_rn.
+__device__ __forceinline__ float div_const_f32(float x, double b, double y) {
+  const float q = __double2float_rn(div_markstein1((double)x, b, y));
+  return x == 0.0f ? x : q;
+}
+constexpr double kSqrt2 = 1.41421356237309504880;        // M_SQRT2
+constexpr double kInvSqrt2 = 0.70710678118654746172;     // RN(1 / M_SQRT2) as a double
+constexpr double kInv32767 = 3.0518509475997192e-05;     // RN(1 / 32767.0)
 
 // index of the last prefix[] entry <= v (prefix has n+1 ascending entries, prefix[0] == 0)
 template <typename T>

@@ -22,7 +22,7 @@ int k0_tile_outputs() { return kTileOut; }
 // wav.c:364-374: int sum; (float)sum / (float)channels in f32; then / 32767.0 in f64.
 __device__ __forceinline__ float downmix_value(int sum, float chf) {
   float mean = __fdiv_rn((float)sum, chf);
-  return __double2float_rn(__ddiv_rn((double)mean, 32767.0));
+  return div_const_f32(mean, 32767.0, kInv32767);   // (float)((double)mean / 32767.0), see common.cuh
 }
 
 __global__ void __launch_bounds__(kK0Threads) k0_resample_kernel(const TrackDev* __restrict__ tracks,

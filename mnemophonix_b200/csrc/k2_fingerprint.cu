@@ -12,8 +12,9 @@
 //   4. Haar along bands: 2 threads per row, 4 levels in registers + 1 shuffle level
 //      (every step (float)((double)(a +/- b) / M_SQRT2), as haar.c:35-36)
 //   5. exact top-200 by |c| with ties to the lower index (what glibc's stable merge sort gives
-//      the reference): 8 rounds of 4-bit radix select on the magnitude bits, counters in
-//      registers, then an index-ordered rank among the elements equal to the threshold
+//      the reference): 8-bit radix select on the magnitude bits (match.any-aggregated shared
+//      histogram), survivors gathered into ever shorter shared lists, <= 32 ranked by one warp,
+//      then an index-ordered rank among the elements equal to the threshold
 //   6. each thread owns 16 consecutive coefficients = exactly one 32-bit word of the
 //      fingerprint: bits are assembled without atomics
 //   7. MinHash: one warp per permutation, 32 positions per ballot, first set bit wins
@@ -24,11 +25,51 @@ namespace mnemo {
 constexpr int kK2Threads = 256;
 constexpr int kBStride = 33;
 
+// haar.c:35-36: (float)((double)(a +/- b) / M_SQRT2); exact division by reciprocal (common.cuh)
 __device__ __forceinline__ float haar_lo(float a, float b) {
-  return __double2float_rn(__ddiv_rn((double)__fadd_rn(a, b), 1.41421356237309504880));
+  return div_const_f32(__fadd_rn(a, b), kSqrt2, kInvSqrt2);
 }
 __device__ __forceinline__ float haar_hi(float a, float b) {
-  return __double2float_rn(__ddiv_rn((double)__fsub_rn(a, b), 1.41421356237309504880));
+  return div_const_f32(__fsub_rn(a, b), kSqrt2, kInvSqrt2);
+}
+
+// Which of the 256 digit counters holds the `want`-th largest element (digits descending).
+// Called by warp 0 only; result[0] = digit, [1] = elements in higher digits, [2] = count in that digit.
+__device__ __forceinline__ void select_digit(const uint32_t* __restrict__ hist, uint32_t want, int lane,
+                                             uint32_t* __restrict__ result) {
+  uint32_t c[8], local = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    c[k] = hist[255 - (8 * lane + k)];
+    local += c[k];
+  }
+  uint32_t incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  const uint32_t cross = __ballot_sync(0xffffffffu, incl >= want);
+  if (cross && lane == __ffs(cross) - 1) {
+    uint32_t acc = incl - local;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (acc + c[k] >= want) {
+        result[0] = 255 - (8 * lane + k);
+        result[1] = acc;
+        result[2] = c[k];
+        break;
+      }
+      acc += c[k];
+    }
+  }
+}
+
+// Adds one element with digit d to the 256-bin histogram; lanes with the same digit are merged
+// into one shared-memory atomic (d == 0xFFFFFFFF marks "no element").
+__device__ __forceinline__ void hist_add(uint32_t* __restrict__ hist, uint32_t d, int lane) {
+  const uint32_t peers = __match_any_sync(0xffffffffu, d);
+  if (d != 0xFFFFFFFFu && lane == __ffs(peers) - 1) atomicAdd(&hist[d], (uint32_t)__popc(peers));
 }
 
 template <int LOGF_VARIANT>
@@ -40,7 +81,9 @@ __global__ void __launch_bounds__(kK2Threads, 4)
   __shared__ float B[kImgW * kBStride];
   __shared__ float lows[8][kBands];
   __shared__ uint32_t bits[256];
-  __shared__ uint32_t hist[8][8];
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t list_b[kImgElems];
+  __shared__ uint32_t s_sel[3], s_count[2];
   __shared__ uint32_t red[8];
   __shared__ uint32_t s_strong, s_any;
   __shared__ uint8_t s_sig[104];
@@ -52,7 +95,6 @@ __global__ void __launch_bounds__(kK2Threads, 4)
   const uint64_t j = img - img_prefix[t];
   const float* __restrict__ src = bins + (tr.frame_off + j * kImgStep) * kBands;
 
-  if (tid < 64) (&hist[0][0])[tid] = 0;
   if (tid == 0) {
     s_strong = 0;
     s_any = 0;
@@ -82,10 +124,11 @@ __global__ void __launch_bounds__(kK2Threads, 4)
     return;
   }
   const double dmx = (double)mx;
+  const double rmx = __drcp_rn(dmx);
   const float log256 = tab->log256;
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
-    float sc = __double2float_rn(__ddiv_rn(__dmul_rn(255.0, (double)v[u]), dmx));   // spectralimages.c:53
+    float sc = __double2float_rn(div_markstein2(__dmul_rn(255.0, (double)v[u]), dmx, rmx));   // spectralimages.c:53
     if (sc > 255.0f) sc = 255.0f;
     v[u] = __fdiv_rn(logf_glibc<LOGF_VARIANT>(__fadd_rn(1.0f, sc)), log256);          // spectralimages.c:57
   }
@@ -174,53 +217,106 @@ __global__ void __launch_bounds__(kK2Threads, 4)
     for (int e = 0; e < 16; ++e) tap_haar[img * kImgElems + 16 * tid + e] = c[e];
   }
 
-  // 5. exact 200th largest magnitude: radix select, 4 bits per round
+  // 5. exact 200th largest magnitude.  Round 1: 8-bit radix step on the exponent straight from the
+  // registers.  Then the survivors (elements sharing the 200th's exponent) are gathered into shared
+  // memory and refined 8 bits at a time on ever shorter lists; 32 or fewer are ranked by one warp.
   uint32_t key[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) key[e] = __float_as_uint(c[e]) & 0x7fffffffu;
-  uint32_t prefix = 0, decided = 0, want = kTopK, n_eq = 0;
-#pragma unroll 1
-  for (int it = 0; it < 8; ++it) {
-    const int shift = 28 - 4 * it;
-    uint64_t c0 = 0, c1 = 0;   // 16 byte-wide counters (<= 16 each)
+  uint32_t* list0 = reinterpret_cast<uint32_t*>(B);   // B is dead: the coefficients live in registers
+  uint32_t* list1 = list_b;
+  hist[tid] = 0;
+  if (tid == 0) s_count[0] = s_count[1] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 16; ++e) hist_add(hist, key[e] >> 23, lane);
+  __syncthreads();
+  if (warp == 0) select_digit(hist, kTopK, lane, s_sel);
+  __syncthreads();
+  uint32_t prefix = s_sel[0] << 23, want = kTopK - s_sel[1], n_eq = s_sel[2];
+  int shift = 23;            // bits [shift, 31) of the threshold are decided
+  {  // gather the survivors (warp-aggregated append)
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
-      const bool in = (key[e] & decided) == prefix;
-      const uint32_t d = (key[e] >> shift) & 15u;
-      const uint64_t inc = in ? (1ull << (8 * (d & 7u))) : 0ull;
-      c0 += (d < 8u) ? inc : 0ull;
-      c1 += (d < 8u) ? 0ull : inc;
+      const bool alive = (key[e] >> 23) == (prefix >> 23);
+      const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+      if (bal) {
+        uint32_t base = 0;
+        if (lane == __ffs(bal) - 1) base = atomicAdd(&s_count[0], (uint32_t)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+        if (alive) list0[base + __popc(bal & ((1u << lane) - 1u))] = key[e];
+      }
     }
-    // widen to 16-bit fields, two digits per word, and reduce across the warp
+  }
+  __syncthreads();
+  uint32_t thr = prefix;
+  int cur = 0;
+  while (true) {
+    uint32_t* src = cur ? list1 : list0;
+    uint32_t* dst = cur ? list0 : list1;
+    const uint32_t n = n_eq;   // == s_count[cur]
+    if (shift == 0) {          // every bit decided: the n survivors are all equal to the threshold
+      thr = prefix;
+      break;
+    }
+    if (n <= 32) {             // rank the survivors in one warp
+      if (warp == 0) {
+        const uint32_t k = lane < n ? src[lane] : 0u;
+        uint32_t gt = 0, eq = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      const uint64_t s = w < 4 ? c0 : c1;
-      const int sh = 16 * (w & 3);
-      uint32_t pair = (uint32_t)((s >> sh) & 0xffu) | ((uint32_t)((s >> (sh + 8)) & 0xffu) << 16);
-      pair = __reduce_add_sync(0xffffffffu, pair);
-      if (lane == 0) atomicAdd(&hist[it][w], pair);
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t o = __shfl_sync(0xffffffffu, k, j);
+          gt += (j < (int)n) && (o > k);
+          eq += (j < (int)n) && (o == k);
+        }
+        const uint32_t hit = __ballot_sync(0xffffffffu, lane < n && gt < want && gt + eq >= want);
+        if (lane == __ffs(hit) - 1) {
+          s_sel[0] = k;
+          s_sel[1] = gt;
+          s_sel[2] = eq;
+        }
+      }
+      __syncthreads();
+      thr = s_sel[0];
+      want -= s_sel[1];
+      n_eq = s_sel[2];
+      break;
+    }
+    // 8-bit (last round: 7-bit) radix step on the list
+    const int bits = shift >= 8 ? 8 : shift;
+    shift -= bits;
+    const uint32_t mask = (1u << bits) - 1u;
+    hist[tid] = 0;
+    if (tid == 0) s_count[cur ^ 1] = 0;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < n; i0 += kK2Threads) {
+      const uint32_t i = i0 + tid;
+      hist_add(hist, i < n ? (src[i] >> shift) & mask : 0xFFFFFFFFu, lane);
     }
     __syncthreads();
-    uint32_t above = 0;
-    int dsel = 0;
-    uint32_t cnt_sel = 0;
-    bool found = false;
-#pragma unroll
-    for (int d = 15; d >= 0; --d) {
-      const uint32_t cnt = (hist[it][d >> 1] >> (16 * (d & 1))) & 0xffffu;
-      if (!found && above + cnt >= want) {
-        found = true;
-        dsel = d;
-        cnt_sel = cnt;
+    if (warp == 0) select_digit(hist, want, lane, s_sel);
+    __syncthreads();
+    const uint32_t dsel = s_sel[0];
+    want -= s_sel[1];
+    n_eq = s_sel[2];
+    prefix |= dsel << shift;
+    for (uint32_t i0 = 0; i0 < n; i0 += kK2Threads) {
+      const uint32_t i = i0 + tid;
+      const uint32_t k = i < n ? src[i] : 0u;
+      const bool alive = i < n && ((k >> shift) & mask) == dsel;
+      const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+      if (bal) {
+        uint32_t base = 0;
+        if (lane == __ffs(bal) - 1) base = atomicAdd(&s_count[cur ^ 1], (uint32_t)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+        if (alive) dst[base + __popc(bal & ((1u << lane) - 1u))] = k;
       }
-      if (!found) above += cnt;
     }
-    prefix |= (uint32_t)dsel << shift;
-    decided |= 15u << shift;
-    want -= above;
-    n_eq = cnt_sel;
+    __syncthreads();
+    cur ^= 1;
   }
-  const uint32_t thr = prefix;   // the 200th largest magnitude; `want` of the n_eq equal elements are taken
+
+  // thr = the 200th largest magnitude; `want` of the n_eq elements equal to it are taken
 
   // rank among equal elements in index order (stable sort => lower index first)
   uint32_t eq_before = 0;
@@ -316,6 +412,44 @@ __global__ void logf_range_kernel(uint32_t lo_bits, uint32_t n, int variant, flo
   if (i >= n) return;
   const float x = __uint_as_float(lo_bits + i);
   out[i] = variant ? logf_glibc<1>(x) : logf_glibc<0>(x);
+}
+
+// ---- device self-test of the reciprocal divisions against IEEE division ----
+// which 0: x / M_SQRT2, 1: x / 32767.0 for every float x = bits lo..lo+n-1 (one-step Markstein);
+// which 2: (255*v) / max for pseudo-random float pairs 0 <= v <= max (two-step Markstein).
+__global__ void div_test_kernel(int which, uint32_t lo_bits, uint64_t n, unsigned long long* __restrict__ bad) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double got, want;
+  if (which < 2) {
+    const float x = __uint_as_float((uint32_t)(lo_bits + i));
+    if (!(fabsf(x) <= 3.0e38f)) return;   // NaN / inf never reach the division
+    const double b = which == 0 ? kSqrt2 : 32767.0, y = which == 0 ? kInvSqrt2 : kInv32767;
+    const float g = div_const_f32(x, b, y);
+    const float w = __double2float_rn(__ddiv_rn((double)x, b));
+    if (__float_as_uint(g) != __float_as_uint(w)) {
+      atomicAdd(bad, 1ull);
+      atomicMin(bad + 1, (unsigned long long)(uint32_t)(lo_bits + i));
+    }
+    return;
+  }
+  uint64_t z = (i + lo_bits) * 0x9E3779B97F4A7C15ull;
+  z ^= z >> 29; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 32;
+  uint32_t mb = 0x00800000u + (uint32_t)(z % (0x7f000000u - 0x00800000u));   // positive normal float
+  z = z * 0x94D049BB133111EBull + 1; z ^= z >> 31;
+  const float mx = __uint_as_float(mb);
+  const uint32_t vb = (uint32_t)(z % ((uint64_t)mb + 1));                      // 0 <= v <= max (bit order)
+  const double a = __dmul_rn(255.0, (double)__uint_as_float(vb)), b = (double)mx;
+  got = div_markstein2(a, b, __drcp_rn(b));
+  want = __ddiv_rn(a, b);
+  if (__double_as_longlong(got) != __double_as_longlong(want)) {
+    atomicAdd(bad, 1ull);
+    atomicMin(bad + 1, (unsigned long long)i);
+  }
+}
+
+void launch_div_test(int which, uint32_t lo_bits, uint64_t n, unsigned long long* bad, cudaStream_t st) {
+  if (n) div_test_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(which, lo_bits, n, bad);
 }
 
 void launch_logf_range(uint32_t lo_bits, uint32_t n, int variant, float* out, cudaStream_t st) {

@@ -92,10 +92,27 @@ __global__ void __launch_bounds__(128) sumsq_sim_kernel(const TrackDev* __restri
 #pragma unroll
     for (int par = 0; par < 2; ++par) acc[j][par] = __uint_as_float(((e_hi - j) << 23) | (uint32_t)par);
   if (e_hi) {
-    // s_off and chunk starts are multiples of 4 floats: 128-bit loads
+    // s_off and chunk starts are multiples of 4 floats: 128-bit loads, 8 in flight per thread
     const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
     const uint32_t n4 = cnt >> 2;
-    for (uint32_t i = 0; i < n4; ++i) {
+    uint32_t i = 0;
+    for (; i + 8 <= n4; i += 8) {
+      float4 q[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) q[u] = __ldg(p4 + i + u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float x[4] = {__fmul_rn(q[u].x, q[u].x), __fmul_rn(q[u].y, q[u].y), __fmul_rn(q[u].z, q[u].z),
+                            __fmul_rn(q[u].w, q[u].w)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int j = 0; j < kSumCands; ++j)
+#pragma unroll
+            for (int par = 0; par < 2; ++par) acc[j][par] = __fadd_rn(acc[j][par], x[k]);
+      }
+    }
+    for (; i < n4; ++i) {
       const float4 q = __ldg(p4 + i);
       const float x[4] = {__fmul_rn(q.x, q.x), __fmul_rn(q.y, q.y), __fmul_rn(q.z, q.z), __fmul_rn(q.w, q.w)};
 #pragma unroll
@@ -125,48 +142,78 @@ __global__ void __launch_bounds__(128) sumsq_sim_kernel(const TrackDev* __restri
   recs[c] = rec;
 }
 
-// D: one warp per track
+// D: one warp per track.  Within one binade the effect of a chunk is "m += delta[parity(m)]", and
+// such maps compose associatively, so 32 chunks are stitched at once with a warp scan; the first
+// chunk that would leave the binade (or whose candidates missed) is replayed sequentially from
+// shared memory and the walk resumes behind it.
+__device__ __forceinline__ void compose(uint32_t& a0, uint32_t& a1, uint32_t b0, uint32_t b1) {
+  // (a after b)(p) = b[p] + a[(p + b[p]) & 1]
+  const uint32_t n0 = b0 + ((b0 & 1u) ? a1 : a0);
+  const uint32_t n1 = b1 + ((b1 & 1u) ? a0 : a1);
+  a0 = n0;
+  a1 = n1;
+}
+
 __global__ void __launch_bounds__(32) sumsq_stitch_kernel(const TrackDev* __restrict__ tracks,
                                                           const float* __restrict__ s5512,
                                                           const SumChunkRec* __restrict__ recs,
                                                           float* __restrict__ sumsq, float* __restrict__ rms_out) {
-  __shared__ SumChunkRec srec[32];
+  __shared__ __align__(16) float sq[kSumChunk];
   const TrackDev tr = tracks[blockIdx.x];
   const int lane = threadIdx.x;
   const float* __restrict__ s = s5512 + tr.s_off;
   uint32_t S = 0;   // bits of the float accumulator (non-negative, so bit order == value order)
   for (uint32_t base = 0; base < tr.n_chunks; base += 32) {
-    if (base + lane < tr.n_chunks) srec[lane] = recs[tr.chunk_off + base + lane];
-    __syncwarp();
     const uint32_t lim = min(32u, tr.n_chunks - base);
-    for (uint32_t l = 0; l < lim; ++l) {
-      const SumChunkRec& r = srec[l];
+    SumChunkRec rec;
+    rec.e_hi = 0;
+    if ((uint32_t)lane < lim) rec = recs[tr.chunk_off + base + lane];
+    uint32_t done = 0;
+    while (done < lim) {
       const uint32_t e = S >> 23;
-      const uint32_t j = r.e_hi - e;    // candidate index (unsigned wrap = no match)
-      bool done = false;
-      if (r.e_hi && j < (uint32_t)kSumCands) {
-        const uint32_t m = (S & 0x7fffffu) | 0x800000u;
-        const uint32_t d = r.delta[j][m & 1u];
-        if (d != kSumInvalid && m + d < 0x1000000u) {
-          S += d;
-          done = true;
+      const uint32_t m = (S & 0x7fffffu) | 0x800000u;
+      const uint32_t j = rec.e_hi - e;   // candidate index (unsigned wrap = no match)
+      uint32_t d0 = kSumInvalid, d1 = kSumInvalid;
+#pragma unroll
+      for (int c = 0; c < kSumCands; ++c)
+        if (j == (uint32_t)c) {
+          d0 = rec.delta[c][0];
+          d1 = rec.delta[c][1];
         }
+      const bool mine = (uint32_t)lane >= done && (uint32_t)lane < lim;
+      const bool ok = mine && e >= 1 && e < 255 && rec.e_hi && d0 != kSumInvalid && d1 != kSumInvalid;
+      uint32_t a0 = ok ? d0 : 0u, a1 = ok ? d1 : 0u;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t b0 = __shfl_up_sync(0xffffffffu, a0, o), b1 = __shfl_up_sync(0xffffffffu, a1, o);
+        if (lane >= o) compose(a0, a1, b0, b1);
       }
-      if (!done) {   // sequential replay of this chunk (all lanes compute the same chain)
-        const uint32_t first = (base + l) * kSumChunk;
+      const uint32_t tot = (m & 1u) ? a1 : a0;   // increment through this lane's chunk
+      const uint32_t bad = __ballot_sync(0xffffffffu, mine && (!ok || m + tot >= 0x1000000u));
+      const uint32_t first_bad = bad ? (uint32_t)(__ffs(bad) - 1) : lim;
+      if (first_bad > done) S += __shfl_sync(0xffffffffu, tot, first_bad - 1);
+      done = first_bad;
+      if (done < lim) {   // sequential replay of chunk base+done
+        const uint32_t first = (base + done) * kSumChunk;
         const uint32_t cnt = min((uint32_t)kSumChunk, tr.n5512 - first);
-        float acc = __uint_as_float(S);
-        for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
-          const uint32_t i = i0 + lane;
+        for (uint32_t i = lane; i < (uint32_t)kSumChunk; i += 32) {
           const float v = i < cnt ? s[first + i] : 0.0f;
-          const float x = __fmul_rn(v, v);
-          const uint32_t nn = min(32u, cnt - i0);
-          for (uint32_t k = 0; k < nn; ++k) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, x, k));
+          sq[i] = __fmul_rn(v, v);   // past the end: + 0.0f leaves the sum unchanged
+        }
+        __syncwarp();
+        float acc = __uint_as_float(S);
+        const float4* q4 = reinterpret_cast<const float4*>(sq);
+        const uint32_t n4 = (cnt + 3) >> 2;
+#pragma unroll 4
+        for (uint32_t i = 0; i < n4; ++i) {
+          const float4 q = q4[i];
+          acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, q.x), q.y), q.z), q.w);
         }
         S = __float_as_uint(acc);
+        __syncwarp();
+        ++done;
       }
     }
-    __syncwarp();
   }
   if (lane == 0) {
     const float ss = __uint_as_float(S);

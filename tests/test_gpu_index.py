@@ -126,6 +126,14 @@ def test_device_logf_equals_host_libm_on_its_whole_domain(ctx):
     assert ctx.selftest_logf(0x3F800000, 0x43800000) == 0
 
 
+def test_reciprocal_divisions_equal_ieee_division(ctx):
+    # x / M_SQRT2 (haar.c:35-36) and x / 32767.0 (wav.c:373): every one of the 2^32 float dividends
+    assert ctx.selftest_div(0, 0, 1 << 32) == 0
+    assert ctx.selftest_div(1, 0, 1 << 32) == 0
+    # (255*v) / max (spectralimages.c:53): 2^28 pseudo-random (v, max) pairs, double results bit-equal
+    assert ctx.selftest_div(2, 12345, 1 << 28) == 0
+
+
 def test_rerun_is_deterministic(ctx):
     pcm = synth.synth_track(91, 20.0, 2)
     b = ctx.batch([pcm])
