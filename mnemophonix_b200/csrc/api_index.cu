@@ -225,6 +225,7 @@ extern "C" int mnemo_create(int device, void* stream, mnemo_ctx** out) {
   cudaMemcpy(ctx->d_tables, &ctx->h_tables, sizeof(Tables), cudaMemcpyHostToDevice);
   cudaMemcpy(ctx->d_perms, k_permutations, sizeof(k_permutations), cudaMemcpyHostToDevice);
   k1_upload_constants(ctx->h_tables);
+  k0_upload_constants(ctx->h_tables);
   e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     fprintf(stderr, "mnemo_create: %s\n", cudaGetErrorString(e));
@@ -361,6 +362,7 @@ static int batch_create_common(mnemo_ctx* ctx, const mnemo_track* tracks, uint32
   TRY(dalloc(&b->d_img_prefix, n_tracks + 1));
   TRY(dalloc(&b->d_chunk_track, b->n_chunks));
   TRY(dalloc(&b->d_s5512, b->n_samples));
+  if (!prenormalized) TRY(dalloc(&b->d_norm, b->n_samples));
   TRY(dalloc(&b->d_chunk_true, b->n_chunks));
   TRY(dalloc(&b->d_chunk_prefix, b->n_chunks));
   TRY(dalloc(&b->d_recs, b->n_chunks));
@@ -378,6 +380,7 @@ static int batch_create_common(mnemo_ctx* ctx, const mnemo_track* tracks, uint32
     mnemo_batch_destroy(b);
     return rc;
   }
+  if (prenormalized) b->d_norm = b->d_s5512;
   for (uint32_t t = 0; t < n_tracks; t++)
     b->h_tracks[t].pcm = prenormalized ? nullptr : reinterpret_cast<const int16_t*>(b->d_pcm + b->pcm_off[t]);
   cudaStream_t st = ctx->stream;
@@ -409,7 +412,8 @@ extern "C" void mnemo_batch_destroy(mnemo_batch* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
-  void* ptrs[] = {b->d_pcm,      b->d_tracks,  b->d_k0_prefix, b->d_k1_prefix,   b->d_img_prefix, b->d_chunk_track,
+  if (b->d_norm == b->d_s5512) b->d_norm = nullptr;
+  void* ptrs[] = {b->d_norm,     b->d_pcm,      b->d_tracks,  b->d_k0_prefix, b->d_k1_prefix,   b->d_img_prefix, b->d_chunk_track,
                   b->d_s5512,    b->d_chunk_true, b->d_chunk_prefix, b->d_recs,  b->d_sumsq,      b->d_rms,
                   b->d_bins,     b->d_sig_dense, b->d_keep,    b->d_pos,         b->d_block_sums, b->d_sig_out,
                   b->d_n_sigs,   b->d_tap_raw, b->d_tap_img,   b->d_tap_haar};
@@ -496,12 +500,15 @@ extern "C" int mnemo_batch_run(mnemo_batch* b) {
     launches += k0_tiles ? 1 : 0;
   }
   if (tm) cudaEventRecord(b->ev[1], st);
-  if (!b->prenormalized)
+  if (!b->prenormalized) {
     launch_sumsq(b->d_tracks, b->n_tracks, b->n_chunks, b->d_chunk_track, b->d_s5512, b->d_chunk_true,
                  b->d_chunk_prefix, b->d_recs, b->d_sumsq, b->d_rms, st, &launches);
+    launch_normalize(b->d_tracks, b->d_chunk_track, b->n_chunks, b->d_s5512, b->d_rms, b->d_norm, st);
+    launches += b->n_chunks ? 1 : 0;
+  }
   if (tm) cudaEventRecord(b->ev[2], st);
   const uint32_t k1_tiles = b->k1_tile_prefix[b->n_tracks];
-  launch_k1_spectral(b->d_tracks, b->d_k1_prefix, b->n_tracks, k1_tiles, ctx->d_tables, b->d_s5512, b->d_rms, b->d_bins,
+  launch_k1_spectral(b->d_tracks, b->d_k1_prefix, b->n_tracks, k1_tiles, ctx->d_tables, b->d_norm, b->d_bins,
                      ctx->sm_count, st);
   launches += k1_tiles ? 1 : 0;
   if (tm) cudaEventRecord(b->ev[3], st);

@@ -38,6 +38,7 @@ struct mnemo_batch {
   uint32_t *d_k0_prefix = nullptr, *d_k1_prefix = nullptr, *d_chunk_track = nullptr;
   uint64_t* d_img_prefix = nullptr;
   float* d_s5512 = nullptr;
+  float* d_norm = nullptr;   // normalised samples (aliases d_s5512 for pre-normalised input)
   double *d_chunk_true = nullptr, *d_chunk_prefix = nullptr;
   mnemo::SumChunkRec* d_recs = nullptr;
   float *d_sumsq = nullptr, *d_rms = nullptr, *d_bins = nullptr;

@@ -67,9 +67,10 @@ void launch_k0_resample(const TrackDev* tracks, const uint32_t* tile_prefix, uin
 void launch_sumsq(const TrackDev* tracks, uint32_t n_tracks, uint64_t n_chunks_total, const uint32_t* chunk_track,
                   const float* s5512, double* chunk_true, double* chunk_prefix, SumChunkRec* recs, float* sumsq,
                   float* rms, cudaStream_t st, int* n_launches);
+void launch_normalize(const TrackDev* tracks, const uint32_t* chunk_track, uint64_t n_chunks, const float* s5512,
+                      const float* rms, float* snorm, cudaStream_t st);
 void launch_k1_spectral(const TrackDev* tracks, const uint32_t* tile_prefix, uint32_t n_tracks, uint32_t n_tiles,
-                        const Tables* tab, const float* s5512, const float* rms, float* bins, int sm_count,
-                        cudaStream_t st);
+                        const Tables* tab, const float* snorm, float* bins, int sm_count, cudaStream_t st);
 void launch_k2_fingerprint(const TrackDev* tracks, const uint64_t* img_prefix, uint32_t n_tracks, uint64_t n_images,
                            const Tables* tab, const uint16_t* perms, const float* bins, uint8_t* sig_dense,
                            uint8_t* keep, uint8_t* tap_raw, float* tap_img, float* tap_haar, int logf_variant,
@@ -78,6 +79,7 @@ void launch_compact(const uint8_t* sig_dense, const uint8_t* keep, uint64_t n_im
                     uint32_t n_tracks, uint32_t* block_sums, uint32_t* pos, uint8_t* sig_out, uint32_t* n_sigs,
                     cudaStream_t st, int* n_launches);
 void k1_upload_constants(const Tables& t);
+void k0_upload_constants(const Tables& t);
 void launch_div_test(int which, uint32_t lo_bits, uint64_t n, unsigned long long* bad, cudaStream_t st);
 void launch_logf_range(uint32_t lo_bits, uint32_t n, int variant, float* out, cudaStream_t st);
 int k1_tile_frames();
@@ -98,8 +100,10 @@ static __device__ __constant__ double c_logf_tab[16][2] = {
     {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
     {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
 
+// tab: the 16 x {invc, logc} table (c_logf_tab itself, or a shared-memory copy of it: the index is
+// data dependent, and a shared-memory read is far cheaper than a divergent constant-bank load)
 template <int VARIANT>
-__device__ __forceinline__ float logf_glibc(float x) {
+__device__ __forceinline__ float logf_glibc(float x, const double* __restrict__ tab = &c_logf_tab[0][0]) {
   const double ln2 = 0x1.62e42fefa39efp-1;
   const double a0 = -0x1.00ea348b88334p-2, a1 = 0x1.5575b0be00b6ap-2, a2 = -0x1.ffffef20a4123p-2;
   uint32_t ix = __float_as_uint(x);
@@ -109,7 +113,7 @@ __device__ __forceinline__ float logf_glibc(float x) {
   int k = (int)tmp >> 23;
   uint32_t iz = ix - (tmp & 0xff800000u);
   double z = (double)__uint_as_float(iz);
-  double invc = c_logf_tab[i][0], logc = c_logf_tab[i][1];
+  double invc = tab[2 * i], logc = tab[2 * i + 1];
   if (VARIANT) {  // instruction order of the -mfma ifunc variant
     double y0 = __fma_rn((double)k, ln2, logc);
     double r = __fma_rn(z, invc, -1.0);

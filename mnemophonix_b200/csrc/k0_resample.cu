@@ -4,7 +4,10 @@
 // One CTA produces kTileOut consecutive 5512 Hz samples of one track: it stages the
 // 8*kTileOut + 23 PCM frames it needs with 128-bit loads, down-mixes them into shared memory
 // once (int sum -> f32 divide by the channel count -> f64 divide by 32767 -> f32), then every
-// thread runs the reference's sequential mul-then-add tap loop on a bank-conflict-free view.
+// thread produces 4 consecutive outputs from 55 samples held in registers, running the
+// reference's sequential mul-then-add tap loop for each (4 independent chains).
+// Shared memory is padded by one word per 32 so that both the staging stores and the
+// stride-32 register loads are bank-conflict-free.
 #include "common.cuh"
 
 namespace mnemo {
@@ -13,52 +16,46 @@ constexpr int kK0Threads = 256;
 constexpr int kK0OutPerThread = 4;
 constexpr int kTileOut = kK0Threads * kK0OutPerThread;          // 1024 outputs
 constexpr int kTileIn = kTileOut * kDecim + (kTaps - kDecim);   // 8215 input frames
-// pad one word every 32 so the stride-8 tap reads hit 32 distinct banks
+constexpr int kPerThreadIn = kK0OutPerThread * kDecim + (kTaps - kDecim);   // 55 samples
 __device__ __forceinline__ int pad32(int i) { return i + (i >> 5); }
 constexpr int kTileInPadded = kTileIn + (kTileIn >> 5) + 1;
 
 int k0_tile_outputs() { return kTileOut; }
 
-// wav.c:364-374: int sum; (float)sum / (float)channels in f32; then / 32767.0 in f64.
+__constant__ float c_taps[kTaps];
+void k0_upload_constants(const Tables& t) { cudaMemcpyToSymbol(c_taps, t.taps, sizeof(float) * kTaps); }
+
+// wav.c:364-374: int sum; (float)sum / (float)channels in f32; then / 32767.0 in f64, back to f32.
+template <int CH>
 __device__ __forceinline__ float downmix_value(int sum, float chf) {
-  float mean = __fdiv_rn((float)sum, chf);
-  return div_const_f32(mean, 32767.0, kInv32767);   // (float)((double)mean / 32767.0), see common.cuh
+  float mean;
+  if (CH == 1) mean = (float)sum;                          // x / 1.0f
+  else if (CH == 2) mean = __fmul_rn((float)sum, 0.5f);    // x / 2.0f is exact, so is x * 0.5f
+  else mean = __fdiv_rn((float)sum, chf);
+  return div_const_f32(mean, 32767.0, kInv32767);          // exact reciprocal division, common.cuh
 }
 
-__global__ void __launch_bounds__(kK0Threads) k0_resample_kernel(const TrackDev* __restrict__ tracks,
-                                                                 const uint32_t* __restrict__ tile_prefix,
-                                                                 uint32_t n_tracks, const Tables* __restrict__ tab,
-                                                                 float* __restrict__ s5512) {
-  __shared__ float mono[kTileInPadded];
-  __shared__ float taps[kTaps];
-  const uint32_t t = find_segment<uint32_t>(tile_prefix, n_tracks, blockIdx.x);
-  const TrackDev tr = tracks[t];
-  const uint32_t tile = blockIdx.x - tile_prefix[t];
-  const uint64_t out0 = (uint64_t)tile * kTileOut;      // first output of this tile
-  const uint64_t in0 = out0 * kDecim;                   // first PCM frame
-  if (threadIdx.x < kTaps) taps[threadIdx.x] = tab->taps[threadIdx.x];
-
+template <int CH>
+__device__ __forceinline__ void stage_tile(float* __restrict__ mono, const TrackDev& tr, uint64_t in0) {
   const int16_t* __restrict__ pcm = tr.pcm;
-  const uint32_t ch = tr.channels;
-  const float chf = (float)ch;
   // frames past the end of the track contribute +0: acc + 0*h == acc, which is what the
   // reference's "start + j < n_samples" loop bound (resample.c:40) amounts to.
-  if (ch == 1) {
+  if (CH == 1) {
     const int4* __restrict__ v = reinterpret_cast<const int4*>(pcm + in0);   // 16-byte aligned: in0 % 8 == 0
     for (int i = threadIdx.x; i < (kTileIn + 7) / 8; i += kK0Threads) {
       const uint64_t f = in0 + (uint64_t)i * 8;
       int4 q = make_int4(0, 0, 0, 0);
-      if (f < tr.n_pcm) q = __ldg(v + i);      // buffers carry >= 16 bytes of slack past n_pcm
+      if (f < tr.n_pcm) q = __ldg(v + i);      // buffers carry >= 64 bytes of slack past n_pcm
       const int w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int lo = (int)(int16_t)(w[k] & 0xffff), hi = w[k] >> 16;
         const int idx = i * 8 + 2 * k;
-        if (idx < kTileIn) mono[pad32(idx)] = (f + 2 * k < tr.n_pcm) ? downmix_value(lo, chf) : 0.0f;
-        if (idx + 1 < kTileIn) mono[pad32(idx + 1)] = (f + 2 * k + 1 < tr.n_pcm) ? downmix_value(hi, chf) : 0.0f;
+        if (idx < kTileIn) mono[pad32(idx)] = (f + 2 * k < tr.n_pcm) ? downmix_value<1>(lo, 1.0f) : 0.0f;
+        if (idx + 1 < kTileIn) mono[pad32(idx + 1)] = (f + 2 * k + 1 < tr.n_pcm) ? downmix_value<1>(hi, 1.0f) : 0.0f;
       }
     }
-  } else if (ch == 2) {
+  } else if (CH == 2) {
     const int4* __restrict__ v = reinterpret_cast<const int4*>(pcm + in0 * 2);
     for (int i = threadIdx.x; i < (kTileIn + 3) / 4; i += kK0Threads) {
       const uint64_t f = in0 + (uint64_t)i * 4;
@@ -69,40 +66,68 @@ __global__ void __launch_bounds__(kK0Threads) k0_resample_kernel(const TrackDev*
       for (int k = 0; k < 4; ++k) {
         const int sum = (int)(int16_t)(w[k] & 0xffff) + (w[k] >> 16);
         const int idx = i * 4 + k;
-        if (idx < kTileIn) mono[pad32(idx)] = (f + k < tr.n_pcm) ? downmix_value(sum, chf) : 0.0f;
+        if (idx < kTileIn) mono[pad32(idx)] = (f + k < tr.n_pcm) ? downmix_value<2>(sum, 2.0f) : 0.0f;
       }
     }
   } else {
+    const uint32_t ch = tr.channels;
+    const float chf = (float)ch;
     for (int i = threadIdx.x; i < kTileIn; i += kK0Threads) {
       const uint64_t f = in0 + i;
       float m = 0.0f;
       if (f < tr.n_pcm) {
         int sum = 0;
         for (uint32_t c = 0; c < ch; ++c) sum += pcm[f * ch + c];
-        m = downmix_value(sum, chf);
+        m = downmix_value<0>(sum, chf);
       }
       mono[pad32(i)] = m;
     }
   }
+}
+
+__global__ void __launch_bounds__(kK0Threads) k0_resample_kernel(const TrackDev* __restrict__ tracks,
+                                                                 const uint32_t* __restrict__ tile_prefix,
+                                                                 uint32_t n_tracks, float* __restrict__ s5512) {
+  __shared__ float mono[kTileInPadded];
+  const uint32_t t = find_segment<uint32_t>(tile_prefix, n_tracks, blockIdx.x);
+  const TrackDev tr = tracks[t];
+  const uint32_t tile = blockIdx.x - tile_prefix[t];
+  const uint64_t out0 = (uint64_t)tile * kTileOut;      // first output of this tile
+  const uint64_t in0 = out0 * kDecim;                   // first PCM frame
+  if (tr.channels == 1) stage_tile<1>(mono, tr, in0);
+  else if (tr.channels == 2) stage_tile<2>(mono, tr, in0);
+  else stage_tile<0>(mono, tr, in0);
   __syncthreads();
 
+  // outputs 4*tid .. 4*tid+3 read samples 32*tid .. 32*tid+54 (padded index 33*tid + j + (j >= 32))
+  float x[kPerThreadIn];
+  const float* base = mono + 33 * threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < kPerThreadIn; ++j) x[j] = base[j + (j >> 5)];
+  float acc[kK0OutPerThread];
+#pragma unroll
+  for (int m = 0; m < kK0OutPerThread; ++m) acc[m] = 0.0f;
+#pragma unroll
+  for (int j = 0; j < kTaps; ++j)   // resample.c:39-43: res += in[start + j] * h[j], j ascending
+#pragma unroll
+    for (int m = 0; m < kK0OutPerThread; ++m) acc[m] = __fadd_rn(acc[m], __fmul_rn(x[m * kDecim + j], c_taps[j]));
+
   float* __restrict__ out = s5512 + tr.s_off;
+  const uint64_t oi = out0 + (uint64_t)threadIdx.x * kK0OutPerThread;
+  if (oi + kK0OutPerThread <= tr.n5512) {
+    *reinterpret_cast<float4*>(out + oi) = make_float4(acc[0], acc[1], acc[2], acc[3]);   // s_off, oi multiples of 4
+  } else {
 #pragma unroll
-  for (int m = 0; m < kK0OutPerThread; ++m) {
-    const int o = threadIdx.x + m * kK0Threads;
-    const uint64_t oi = out0 + o;
-    if (oi >= tr.n5512) continue;
-    float acc = 0.0f;   // resample.c:39-43: res += in[start + j] * h[j], j ascending
-#pragma unroll
-    for (int j = 0; j < kTaps; ++j) acc = __fadd_rn(acc, __fmul_rn(mono[pad32(o * kDecim + j)], taps[j]));
-    out[oi] = acc;
+    for (int m = 0; m < kK0OutPerThread; ++m)
+      if (oi + m < tr.n5512) out[oi + m] = acc[m];
   }
 }
 
 void launch_k0_resample(const TrackDev* tracks, const uint32_t* tile_prefix, uint32_t n_tracks, uint32_t n_tiles,
                         const Tables* tab, float* s5512, cudaStream_t st) {
+  (void)tab;
   if (n_tiles == 0) return;
-  k0_resample_kernel<<<n_tiles, kK0Threads, 0, st>>>(tracks, tile_prefix, n_tracks, tab, s5512);
+  k0_resample_kernel<<<n_tiles, kK0Threads, 0, st>>>(tracks, tile_prefix, n_tracks, s5512);
 }
 
 }  // namespace mnemo

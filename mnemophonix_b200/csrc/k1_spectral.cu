@@ -20,6 +20,11 @@
 //     logbins.c:44-55), so stage 11 computes the "a" half of 11 of its 16 butterflies per
 //     column and dead-code elimination prunes what feeds nothing.
 // The sequential per-band accumulation (logbins.c:68-73) is done by one lane per band.
+//
+// Input staging: a small elementwise kernel applies the normaliser's second loop
+// (audionormalizer.c:22-31: s / rms, clipped to [-1, 1]) once per sample; the FFT kernel then pulls
+// its 96-frame tiles (8128 samples, 32.5 KB) with TMA bulk copies (cp.async.bulk + mbarrier) into a
+// double buffer, so the next tile streams in while the current one is transformed.
 #include "common.cuh"
 
 namespace mnemo {
@@ -33,7 +38,7 @@ constexpr int kScratchStride = 33;
 constexpr int kScratchFloats = 64 * kScratchStride;                   // per warp
 constexpr int kTwHiFloat2 = 2 * 31 * 32;
 constexpr size_t kK1Smem =
-    sizeof(float) * (kK1TileSamples + kFrame + kK1Warps * kScratchFloats) + sizeof(float2) * kTwHiFloat2;
+    sizeof(float) * (2 * kK1TileSamples + kFrame + kK1Warps * kScratchFloats) + sizeof(float2) * kTwHiFloat2 + 16;
 
 int k1_tile_frames() { return kK1TileFrames; }
 
@@ -127,15 +132,75 @@ __device__ __forceinline__ void column_pass(float (&cr)[32], float (&ci)[32], co
   }
 }
 
+// ---- mbarrier / TMA bulk copy (1-D) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// audionormalizer.c:22-31, one block per 4096-sample chunk of a track
+__global__ void __launch_bounds__(256) normalize_kernel(const TrackDev* __restrict__ tracks,
+                                                        const uint32_t* __restrict__ chunk_track, uint64_t n_chunks,
+                                                        const float* __restrict__ s5512, const float* __restrict__ rms,
+                                                        float* __restrict__ out) {
+  const uint64_t c = blockIdx.x;
+  if (c >= n_chunks) return;
+  const uint32_t t = chunk_track[c];
+  const TrackDev tr = tracks[t];
+  const uint32_t first = (uint32_t)(c - tr.chunk_off) * kSumChunk;
+  const uint32_t cnt = min((uint32_t)kSumChunk, tr.n5512 - first);
+  const float r = rms[t];
+  const float4* __restrict__ src = reinterpret_cast<const float4*>(s5512 + tr.s_off + first);
+  float4* __restrict__ dst = reinterpret_cast<float4*>(out + tr.s_off + first);
+  auto nrm = [r](float x) {
+    float v = __fdiv_rn(x, r);
+    if (v < -1.0f) v = -1.0f;
+    else if (v > 1.0f) v = 1.0f;
+    return v;
+  };
+  // chunks start on 16-byte boundaries and buffers are padded to 64 floats: whole float4s
+  for (uint32_t i = threadIdx.x; i < (cnt + 3) / 4; i += 256) {
+    float4 q = src[i];
+    q.x = nrm(q.x);
+    q.y = nrm(q.y);
+    q.z = nrm(q.z);
+    q.w = nrm(q.w);
+    dst[i] = q;
+  }
+}
+
 __global__ void __launch_bounds__(kK1Threads, 1)
     k1_spectral_kernel(const TrackDev* __restrict__ tracks, const uint32_t* __restrict__ tile_prefix, uint32_t n_tracks,
-                       uint32_t n_tiles, const Tables* __restrict__ tab, const float* __restrict__ s5512,
-                       const float* __restrict__ rms, float* __restrict__ bins) {
-  extern __shared__ __align__(16) float smem[];
-  float* tile = smem;                                   // kK1TileSamples
-  float* hann = tile + kK1TileSamples;                  // kFrame
+                       uint32_t n_tiles, const Tables* __restrict__ tab, const float* __restrict__ snorm,
+                       float* __restrict__ bins) {
+  extern __shared__ __align__(128) float smem[];
+  float* const tile0 = smem;                              // 2 x kK1TileSamples (TMA destinations)
+  float* hann = smem + 2 * kK1TileSamples;                // kFrame
   float2* tw_hi = reinterpret_cast<float2*>(hann + kFrame);   // [2][31][32]
   float* scratch_all = reinterpret_cast<float*>(tw_hi + kTwHiFloat2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_all + kK1Warps * kScratchFloats);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* sc = scratch_all + warp * kScratchFloats;
@@ -146,26 +211,36 @@ __global__ void __launch_bounds__(kK1Threads, 1)
   const float width = (float)(unsigned)(e_hi - e_lo);   // logbins.c:75
   const int rl = (int)(__brev((unsigned)lane) >> 27);   // rev5(lane)
 
-  for (uint32_t tix = blockIdx.x; tix < n_tiles; tix += gridDim.x) {
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // tile -> (track, first frame, frame count); issue its TMA copy into buffer `buf`
+  auto issue = [&](uint32_t tix, int buf) {
+    const uint32_t t = find_segment<uint32_t>(tile_prefix, n_tracks, tix);
+    const uint32_t f0 = (tix - tile_prefix[t]) * kK1TileFrames;
+    const uint32_t nf = min((uint32_t)kK1TileFrames, tracks[t].n_frames - f0);
+    const uint32_t bytes = (kHop * (nf - 1) + kFrame) * (uint32_t)sizeof(float);
+    mbar_expect_tx(&bars[buf], bytes);
+    tma_load_1d(tile0 + buf * kK1TileSamples, snorm + tracks[t].s_off + (uint64_t)f0 * kHop, bytes, &bars[buf]);
+  };
+  if (threadIdx.x == 0 && blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+  uint32_t phase_bits = 0;   // bit b = parity to wait for on bars[b]
+  int cur = 0;
+
+  for (uint32_t tix = blockIdx.x; tix < n_tiles; tix += gridDim.x, cur ^= 1) {
     const uint32_t t = find_segment<uint32_t>(tile_prefix, n_tracks, tix);
     const TrackDev tr = tracks[t];
     const uint32_t f0 = (tix - tile_prefix[t]) * kK1TileFrames;
     const uint32_t nf = min((uint32_t)kK1TileFrames, tr.n_frames - f0);
-    const uint32_t ns = kHop * (nf - 1) + kFrame;
-    const float* __restrict__ src = s5512 + tr.s_off + (uint64_t)f0 * kHop;
-    __syncthreads();   // previous tile fully consumed (and tables visible on the first pass)
-    if (tr.prenormalized) {
-      for (uint32_t i = threadIdx.x; i < ns; i += kK1Threads) tile[i] = src[i];
-    } else {
-      const float r = rms[t];
-      for (uint32_t i = threadIdx.x; i < ns; i += kK1Threads) {
-        float v = __fdiv_rn(src[i], r);   // audionormalizer.c:23-30
-        if (v < -1.0f) v = -1.0f;
-        else if (v > 1.0f) v = 1.0f;
-        tile[i] = v;
-      }
-    }
-    __syncthreads();
+    // the other buffer was released by the __syncthreads that ended the previous iteration
+    if (threadIdx.x == 0 && tix + gridDim.x < n_tiles) issue(tix + gridDim.x, cur ^ 1);
+    mbar_wait(&bars[cur], (phase_bits >> cur) & 1u);
+    phase_bits ^= 1u << cur;
+    const float* tile = tile0 + cur * kK1TileSamples;
 
     for (uint32_t fl = warp; fl < nf; fl += kK1Warps) {
       float re[64], im[64];
@@ -210,24 +285,31 @@ __global__ void __launch_bounds__(kK1Threads, 1)
 
       // logbins.c:64-75: sequential sum over the band's FFT bins, one band per lane
       float sum = 0.0f;
-      for (int j = e_lo; j < e_hi; ++j) sum = __fadd_rn(sum, sc[j]);
+      for (int j0 = e_lo; j0 < e_hi; j0 += 8) {
+        float tpw[8];   // loads first, then the dependent adds; "+ 0.0f" past the band end is a no-op
+#pragma unroll
+        for (int u = 0; u < 8; ++u) tpw[u] = (j0 + u < e_hi) ? sc[j0 + u] : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sum = __fadd_rn(sum, tpw[u]);
+      }
       bins[(tr.frame_off + f0 + fl) * kBands + lane] = __fdiv_rn(sum, width);
       __syncwarp();
     }
+    __syncthreads();   // every warp is done with tile_buf[cur]: it may be refilled next iteration
   }
 }
 
+void launch_normalize(const TrackDev* tracks, const uint32_t* chunk_track, uint64_t n_chunks, const float* s5512,
+                      const float* rms, float* snorm, cudaStream_t st) {
+  if (n_chunks) normalize_kernel<<<(unsigned)n_chunks, 256, 0, st>>>(tracks, chunk_track, n_chunks, s5512, rms, snorm);
+}
+
 void launch_k1_spectral(const TrackDev* tracks, const uint32_t* tile_prefix, uint32_t n_tracks, uint32_t n_tiles,
-                        const Tables* tab, const float* s5512, const float* rms, float* bins, int sm_count,
-                        cudaStream_t st) {
+                        const Tables* tab, const float* snorm, float* bins, int sm_count, cudaStream_t st) {
   if (n_tiles == 0) return;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k1_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem);
-    attr_set = true;
-  }
+  cudaFuncSetAttribute(k1_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem);
   const unsigned grid = n_tiles < (uint32_t)sm_count ? n_tiles : (unsigned)sm_count;
-  k1_spectral_kernel<<<grid, kK1Threads, kK1Smem, st>>>(tracks, tile_prefix, n_tracks, n_tiles, tab, s5512, rms, bins);
+  k1_spectral_kernel<<<grid, kK1Threads, kK1Smem, st>>>(tracks, tile_prefix, n_tracks, n_tiles, tab, snorm, bins);
 }
 
 }  // namespace mnemo

@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(kK2Threads, 4)
   __shared__ uint32_t red[8];
   __shared__ uint32_t s_strong, s_any;
   __shared__ uint8_t s_sig[104];
+  __shared__ double s_logtab[32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t img = blockIdx.x;
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(kK2Threads, 4)
     s_strong = 0;
     s_any = 0;
   }
+  if (tid < 32) s_logtab[tid] = (&c_logf_tab[0][0])[tid];
 
   // 1. load: element (time = 16*warp + u, band = lane)
   float v[16];
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(kK2Threads, 4)
   for (int u = 0; u < 16; ++u) {
     float sc = __double2float_rn(div_markstein2(__dmul_rn(255.0, (double)v[u]), dmx, rmx));   // spectralimages.c:53
     if (sc > 255.0f) sc = 255.0f;
-    v[u] = __fdiv_rn(logf_glibc<LOGF_VARIANT>(__fadd_rn(1.0f, sc)), log256);          // spectralimages.c:57
+    v[u] = __fdiv_rn(logf_glibc<LOGF_VARIANT>(__fadd_rn(1.0f, sc), s_logtab), log256);          // spectralimages.c:57
   }
   if (tap_img) {
 #pragma unroll
@@ -217,36 +219,62 @@ __global__ void __launch_bounds__(kK2Threads, 4)
     for (int e = 0; e < 16; ++e) tap_haar[img * kImgElems + 16 * tid + e] = c[e];
   }
 
-  // 5. exact 200th largest magnitude.  Round 1: 8-bit radix step on the exponent straight from the
-  // registers.  Then the survivors (elements sharing the 200th's exponent) are gathered into shared
-  // memory and refined 8 bits at a time on ever shorter lists; 32 or fewer are ranked by one warp.
+  // 5. exact 200th largest magnitude.
+  //  (a) a lower bound first: in every warp the 25th largest of the 32 per-thread maxima (bitonic
+  //      sort across lanes); the minimum of these over the 8 warps has at least 200 elements at or
+  //      above it, so the 200th largest is among the elements >= bound (typically ~10 % of them);
+  //  (b) those are gathered into shared memory (block scan, no atomics) and refined by 8-bit radix
+  //      steps on ever shorter lists; 32 or fewer survivors are ranked by one warp.
   uint32_t key[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) key[e] = __float_as_uint(c[e]) & 0x7fffffffu;
   uint32_t* list0 = reinterpret_cast<uint32_t*>(B);   // B is dead: the coefficients live in registers
   uint32_t* list1 = list_b;
-  hist[tid] = 0;
-  if (tid == 0) s_count[0] = s_count[1] = 0;
-  __syncthreads();
+  uint32_t bound;
+  {
+    uint32_t v = key[0];
 #pragma unroll
-  for (int e = 0; e < 16; ++e) hist_add(hist, key[e] >> 23, lane);
-  __syncthreads();
-  if (warp == 0) select_digit(hist, kTopK, lane, s_sel);
-  __syncthreads();
-  uint32_t prefix = s_sel[0] << 23, want = kTopK - s_sel[1], n_eq = s_sel[2];
-  int shift = 23;            // bits [shift, 31) of the threshold are decided
-  {  // gather the survivors (warp-aggregated append)
+    for (int e = 1; e < 16; ++e) v = max(v, key[e]);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const bool alive = (key[e] >> 23) == (prefix >> 23);
-      const uint32_t bal = __ballot_sync(0xffffffffu, alive);
-      if (bal) {
-        uint32_t base = 0;
-        if (lane == __ffs(bal) - 1) base = atomicAdd(&s_count[0], (uint32_t)__popc(bal));
-        base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-        if (alive) list0[base + __popc(bal & ((1u << lane) - 1u))] = key[e];
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {   // ascending bitonic sort of the 32 thread maxima
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, v, j);
+        const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
+        v = keep_min ? min(v, o) : max(v, o);
       }
+    v = __shfl_sync(0xffffffffu, v, 7);       // 8th smallest = 25th largest thread maximum of this warp
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    bound = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) bound = min(bound, red[w]);
+  }
+  uint32_t want = kTopK, n_eq, prefix = 0;
+  int shift = 31;            // bits [shift, 31) of the threshold are decided
+  {
+    uint32_t mine = 0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) mine += key[e] >= bound;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
     }
+    __syncthreads();         // everyone has read red[] (bound)
+    if (lane == 31) red[warp] = incl;
+    __syncthreads();
+    uint32_t off = incl - mine, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      off += w < warp ? red[w] : 0u;
+      tot += red[w];
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+      if (key[e] >= bound) list0[off++] = key[e];
+    n_eq = tot;
   }
   __syncthreads();
   uint32_t thr = prefix;
