@@ -1,0 +1,120 @@
+"""torch.distributed plumbing for the multi-GPU paths (one process per GPU).
+
+Index: tracks are independent units -> sharded across ranks with NO data-path collective
+(SURVEY.md §8e); per-track results are gathered on the host only to restore input order.
+Search: the database is split into contiguous entry ranges, one per rank; every rank probes its
+shard with the GLOBAL table size (lsh.c:61) and the per-query candidate records are exchanged with
+ONE all-gather (NCCL on GPU tensors; gloo on CPU tensors in the tests), after which the exact final
+ranking (search.c:170-193) runs on the host.  The records are a few hundred bytes per query: the
+exchange is latency-bound, which is why it is a single fixed-capacity collective.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import capi
+
+
+# ------------------------------------------------------------------ index sharding ----
+
+def shard_tracks(durations, world: int):
+    """Longest-first greedy assignment of tracks to ranks.  Returns a list of index lists."""
+    order = sorted(range(len(durations)), key=lambda i: -durations[i])
+    load = [0.0] * world
+    out = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        out[r].append(i)
+        load[r] += durations[i]
+    for lst in out:
+        lst.sort()
+    return out
+
+
+def entry_ranges(sig_counts, world: int):
+    """Contiguous entry ranges with roughly equal signature counts.  Returns world+1 cut points."""
+    total = int(sum(sig_counts))
+    cuts, acc, e = [0], 0, 0
+    n = len(sig_counts)
+    for r in range(1, world):
+        target = total * r / world
+        while e < n and acc + sig_counts[e] / 2 <= target:
+            acc += sig_counts[e]
+            e += 1
+        cuts.append(e)
+    cuts.append(n)
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return cuts
+
+
+def index_sharded(ctx, pcms, rank: int, world: int, group=None, gather_to: int | None = 0):
+    """Every rank indexes its share of `pcms` (all ranks pass the same list, or None for tracks they
+    do not own).  With gather_to set, that rank receives the per-track results in input order."""
+    import torch.distributed as dist
+    durations = [0 if p is None else len(p) for p in pcms]
+    if world > 1:
+        # ranks may hold only their own tracks: agree on the durations first (host-side metadata)
+        alld = [None] * world
+        dist.all_gather_object(alld, durations, group=group)
+        durations = [max(d[i] for d in alld) for i in range(len(pcms))]
+    mine = shard_tracks(durations, world)[rank]
+    sigs, status = ctx.index_pcm_batch([pcms[i] for i in mine]) if mine else ([], [])
+    local = {i: (s, st) for i, s, st in zip(mine, sigs, status)}
+    if world == 1 or gather_to is None:
+        return local
+    gathered = [None] * world if rank == gather_to else None
+    dist.gather_object(local, gathered, dst=gather_to, group=group)
+    if rank != gather_to:
+        return None
+    merged = {}
+    for part in gathered:
+        merged.update(part)
+    return [merged[i] for i in range(len(pcms))]
+
+
+# ------------------------------------------------------------------ sharded search ----
+
+def _all_gather_bytes(buf: np.ndarray, device, group):
+    """All-gather of variable-length byte buffers: counts first, then one padded all-gather."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n = torch.tensor([buf.nbytes], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    send = torch.zeros(cap, dtype=torch.uint8, device=device)
+    if buf.nbytes:
+        send[:buf.nbytes] = torch.from_numpy(np.frombuffer(buf.tobytes(), np.uint8).copy()).to(device)
+    recv = [torch.empty(cap, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(recv, send, group=group)
+    return [r[:c].cpu().numpy().tobytes() for r, c in zip(recv, counts)]
+
+
+def merge_shards(cands_local: np.ndarray, last_local: np.ndarray, qstart: np.ndarray, n_entries_total: int,
+                 device="cpu", group=None):
+    """The exchange step: all-gather every rank's candidate and last-group records, then the exact
+    final ranking on the host.  Every rank returns the same result list."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    parts_c = _all_gather_bytes(np.ascontiguousarray(cands_local, capi.CAND_DTYPE), device, group)
+    parts_l = _all_gather_bytes(np.ascontiguousarray(last_local, capi.LAST_DTYPE), device, group)
+    cands = np.concatenate([np.frombuffer(b, capi.CAND_DTYPE) for b in parts_c]) if parts_c else cands_local
+    last = np.stack([np.frombuffer(b, capi.LAST_DTYPE) for b in parts_l])
+    return capi.search_finish(cands, last, world, qstart, n_entries_total)
+
+
+def search_sharded(ctx, entry_sigs, queries, rank: int, world: int, device, group=None, db=None):
+    """entry_sigs: the WHOLE database as a list of [n,100] arrays (every rank passes the same list; only
+    its own range is uploaded).  Returns (results, db) so the shard can be reused for more batches."""
+    counts = [len(s) for s in entry_sigs]
+    cuts = entry_ranges(counts, world)
+    a, b = cuts[rank], cuts[rank + 1]
+    if db is None:
+        db = capi.Db(ctx, entry_sigs[a:b], table_size=int(sum(counts)) // 2, entry_base=a)
+    cands, last, qstart, _ = db.search_shard(queries)
+    if world == 1:
+        return capi.search_finish(cands, None, 1, qstart, len(entry_sigs)), db
+    return merge_shards(cands, last, qstart, len(entry_sigs), device=device, group=group), db

@@ -1,0 +1,120 @@
+/* fingerprinting.c — generate_fingerprint / generate_fingerprint_from_samples.
+ *
+ * Drop-in for the reference's fingerprinting.c:10-109.  The stage sequence of the reference
+ * (read + down-mix, resample, normalise, spectral images, Haar, raw fingerprints, MinHash) runs as
+ * one GPU batch through mnemo_index_pcm_batch; this file keeps the surface: error codes, ownership
+ * and the progress lines on stderr (wav.c:346,379,390; fingerprinting.c:19-27,41,58-62,74).
+ */
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "fingerprinting.h"
+#include "host_internal.h"
+
+static pthread_once_t g_once = PTHREAD_ONCE_INIT;
+static mnemo_ctx* g_ctx = NULL;
+
+static void make_context(void) {
+    const char* dev = getenv("MNEMO_DEVICE");
+    if (mnemo_create(dev ? atoi(dev) : 0, NULL, &g_ctx) != 0) g_ctx = NULL;
+}
+
+mnemo_ctx* mnemo_host_context(void) {
+    pthread_once(&g_once, make_context);
+    return g_ctx;
+}
+
+void free_signatures(struct signatures* s) {
+    if (!s) return;
+    free(s->signatures);
+    free(s);
+}
+
+static struct signatures* new_signatures(uint64_t capacity) {
+    struct signatures* s = (struct signatures*)malloc(sizeof *s);
+    if (!s) return NULL;
+    s->n_signatures = 0;
+    s->signatures = (struct signature*)malloc((capacity ? capacity : 1) * sizeof(struct signature));
+    if (!s->signatures) {
+        free(s);
+        return NULL;
+    }
+    return s;
+}
+
+int generate_fingerprint(const char* wav, struct signatures** fingerprint,
+                         char** artist, char** track_title, char** album_title) {
+    struct wav_data w;
+    int rc = wav_load(wav, &w);
+    if (rc != SUCCESS) return rc;
+    if (w.artist) fprintf(stderr, "Artist: %s\n", w.artist);
+    if (w.track_title) fprintf(stderr, "Track title: %s\n", w.track_title);
+    if (w.album_title) fprintf(stderr, "Album title: %s\n", w.album_title);
+    /* the caller takes the metadata strings (or they are dropped with the reader, as upstream) */
+    if (artist) { *artist = w.artist; w.artist = NULL; }
+    if (track_title) { *track_title = w.track_title; w.track_title = NULL; }
+    if (album_title) { *album_title = w.album_title; w.album_title = NULL; }
+
+    fprintf(stderr, "Reading 44100Hz samples...\n");
+    fprintf(stderr, "Resampling to 5512Hz...\n");
+    fprintf(stderr, "Normalizing samples...\n");
+    const uint32_t n5512 = mnemo_samples_5512(w.n_frames);
+    fprintf(stderr, "%d 5512Hz mono samples\n", (int)n5512);
+    const uint32_t n_images = mnemo_images(n5512);
+    if (n_images == 0) {   /* fingerprinting.c:42, spectralimages.c:128 */
+        wav_release(&w);
+        return FILE_TOO_SMALL;
+    }
+    mnemo_ctx* ctx = mnemo_host_context();
+    if (!ctx) {
+        fprintf(stderr, "mnemophonix: no usable B200 GPU (there is no CPU implementation)\n");
+        wav_release(&w);
+        return DECODING_ERROR;
+    }
+    struct signatures* s = new_signatures(n_images);
+    if (!s) {
+        wav_release(&w);
+        return MEMORY_ERROR;
+    }
+    fprintf(stderr, "Got %d spectral images\n", (int)n_images);
+    fprintf(stderr, "Applying Haar transform to spectral images\n");
+    fprintf(stderr, "Building raw fingerprints\n");
+    mnemo_track tr;
+    tr.pcm = w.pcm;
+    tr.n_frames = w.n_frames;
+    tr.channels = w.channels;
+    tr.reserved = 0;
+    uint32_t n = 0;
+    int32_t status = 0;
+    rc = mnemo_index_pcm_batch(ctx, &tr, 1, (uint8_t*)s->signatures, n_images, &n, &status);
+    wav_release(&w);
+    if (rc == 0) rc = status;
+    if (rc != SUCCESS) {
+        free_signatures(s);
+        return rc;
+    }
+    s->n_signatures = n;
+    fprintf(stderr, "Generated %d signatures\n", s->n_signatures);
+    *fingerprint = s;
+    return SUCCESS;
+}
+
+int generate_fingerprint_from_samples(float* samples, unsigned int size, struct signatures** fingerprint) {
+    const uint32_t n_images = mnemo_images(size);
+    if (n_images == 0) return FILE_TOO_SMALL;   /* fingerprinting.c:82, spectralimages.c:128 */
+    mnemo_ctx* ctx = mnemo_host_context();
+    if (!ctx) return DECODING_ERROR;
+    struct signatures* s = new_signatures(n_images);
+    if (!s) return MEMORY_ERROR;
+    uint32_t n = 0;
+    int rc = mnemo_index_samples(ctx, samples, size, (uint8_t*)s->signatures, n_images, &n);
+    if (rc != SUCCESS) {
+        free_signatures(s);
+        return rc;
+    }
+    s->n_signatures = n;
+    *fingerprint = s;
+    return SUCCESS;
+}

@@ -1,0 +1,144 @@
+/* main.c — the `mnemophonix index|search` command line (surface of the reference's main.c:19-136:
+ * same arguments, same stdout/stderr text, same exit status).  Everything heavy happens on the GPU. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include "fingerprinting.h"
+#include "fingerprintio.h"
+#include "lsh.h"
+#include "search.h"
+
+static long now_ms(void) {
+    struct timeval tv;
+    gettimeofday(&tv, NULL);
+    return tv.tv_sec * 1000 + tv.tv_usec / 1000;
+}
+
+static void usage(const char* me) {
+    fprintf(stderr, "\n");
+    fprintf(stderr, " ---                                                       ---\n");
+    fprintf(stderr, " \\  \\  mnemophonix - A simple audio fingerprinting system  \\  \\\n");
+    fprintf(stderr, " O  O                                                      O  O\n");
+    fprintf(stderr, "\n");
+    fprintf(stderr, "Usage:\n");
+    fprintf(stderr, "\n");
+    fprintf(stderr, "%s index <input>\n", me);
+    fprintf(stderr, "  Prints to stdout the index data generated for the given input file. Since\n");
+    fprintf(stderr, "  the index file format is a text one, you can create a database containing\n");
+    fprintf(stderr, "  multiple indexes like this:\n");
+    fprintf(stderr, "\n");
+    fprintf(stderr, "  $ %s index song1.mp3 > db\n", me);
+    fprintf(stderr, "  $ %s index song2.wav >> db\n", me);
+    fprintf(stderr, "  $ %s index movie.mp4 >> db\n", me);
+    fprintf(stderr, "\n");
+    fprintf(stderr, "%s search <input> <index>\n", me);
+    fprintf(stderr, "  Looks for the given input file in the given index file\n");
+    fprintf(stderr, "\n");
+    fprintf(stderr, "The input file format that this code can process is 44100Hz 16-bit PCM.\n");
+    fprintf(stderr, "If it is not the case, an attempt will be made to generate such a file using\n");
+    fprintf(stderr, "ffmpeg. Because ** ffmpeg rocks **, you can use this program with pretty\n");
+    fprintf(stderr, "much any audio or video file !\n");
+    fprintf(stderr, "\n");
+}
+
+/* Host input stage (ffmpeg.c:35-65 upstream): decode anything to a temporary 44.1 kHz PCM WAVE file
+ * with an external ffmpeg.  Returns a malloc'd path or NULL.  Metadata extraction is not carried over. */
+static char* decode_with_ffmpeg(const char* input) {
+    char tmpl[] = "/tmp/mnemophonixXXXXXX.wav";
+    int fd = mkstemps(tmpl, 4);
+    if (fd < 0) return NULL;
+    close(fd);
+    pid_t pid = fork();
+    if (pid < 0) return NULL;
+    if (pid == 0) {
+        if (!freopen("/dev/null", "w", stderr)) _exit(127);
+        execlp("ffmpeg", "ffmpeg", "-y", "-i", input, "-acodec", "pcm_s16le", "-ar", "44100", "-f", "wav", tmpl,
+               (char*)NULL);
+        _exit(127);
+    }
+    int status = 0;
+    if (waitpid(pid, &status, 0) < 0 || !WIFEXITED(status) || WEXITSTATUS(status) != 0) {
+        remove(tmpl);
+        return NULL;
+    }
+    return strdup(tmpl);
+}
+
+int main(int argc, char* argv[]) {
+    if (argc < 2 || (strcmp(argv[1], "index") && strcmp(argv[1], "search")) || argc < 3 ||
+        (!strcmp(argv[1], "search") && argc != 4)) {
+        usage(argv[0]);
+        return 1;
+    }
+    char* input = argv[2];
+    struct signatures* fingerprint = NULL;
+    char *artist = NULL, *track_title = NULL, *album_title = NULL;
+    int res = generate_fingerprint(input, &fingerprint, &artist, &track_title, &album_title);
+    switch (res) {
+        case SUCCESS: break;
+        case CANNOT_READ_FILE: fprintf(stderr, "Cannot read file '%s'\n", input); return 1;
+        case MEMORY_ERROR: fprintf(stderr, "Memory allocation error\n"); return 1;
+        case DECODING_ERROR: fprintf(stderr, "Cannot decode file '%s'\n", input); return 1;
+        case FILE_TOO_SMALL: fprintf(stderr, "'%s' is too small to generate a fingerprint\n", input); return 1;
+        case UNSUPPORTED_WAVE_FORMAT:
+        case NOT_A_WAVE_FILE: {
+            char* wav = decode_with_ffmpeg(input);
+            if (!wav) {
+                fprintf(stderr, "'%s' is not a wave file and we could not convert it to one with fffmpeg\n", input);
+                return 1;
+            }
+            res = generate_fingerprint(wav, &fingerprint, NULL, NULL, NULL);
+            remove(wav);
+            free(wav);
+            if (res == MEMORY_ERROR) { fprintf(stderr, "Memory allocation error\n"); return 1; }
+            if (res == FILE_TOO_SMALL) { fprintf(stderr, "'%s' is too small to generate a fingerprint\n", input); return 1; }
+            if (res != SUCCESS) { fprintf(stderr, "Cannot decode file '%s'\n", input); return 1; }
+            break;
+        }
+        default: fprintf(stderr, "Cannot decode file '%s'\n", input); return 1;
+    }
+
+    if (!strcmp(argv[1], "index")) {
+        save(stdout, fingerprint, input, artist, track_title, album_title);
+        return 0;
+    }
+
+    const char* index = argv[3];
+    struct index* db = NULL;
+    printf("Loading database %s...\n", index);
+    long t0 = now_ms();
+    res = read_index(index, &db);
+    if (res != SUCCESS) {
+        if (res == CANNOT_READ_FILE) fprintf(stderr, "Cannot read file '%s'\n", index);
+        else if (res == MEMORY_ERROR) fprintf(stderr, "Memory allocation error\n");
+        else fprintf(stderr, "Cannot decode file '%s'\n", index);
+        return 1;
+    }
+    long t1 = now_ms();
+    printf("(raw database loading took %ld ms)\n", t1 - t0);
+    struct lsh* lsh = create_hash_tables(db);
+    long t2 = now_ms();
+    printf("(lsh index building took %ld ms)\n", t2 - t1);
+    if (!lsh) {
+        fprintf(stderr, "Memory allocation error\n");
+        return 1;
+    }
+    printf("Searching...\n");
+    int best = search(fingerprint, db, lsh, 0);
+    long t3 = now_ms();
+    printf("(Search took %ld ms)\n", t3 - t2);
+    if (best < 0) {
+        printf("\nNo match found\n\n");
+        return 1;
+    }
+    printf("\nFound match: '%s'\n", db->entries[best]->filename);
+    if (db->entries[best]->artist[0]) printf("Artist: %s\n", db->entries[best]->artist);
+    if (db->entries[best]->track_title[0]) printf("Track title: %s\n", db->entries[best]->track_title);
+    if (db->entries[best]->album_title[0]) printf("Album title: %s\n", db->entries[best]->album_title);
+    printf("\n");
+    return 0;
+}

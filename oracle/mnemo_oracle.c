@@ -437,10 +437,12 @@ static void csr_free(csr_t* c) {
   }
 }
 
+static uint32_t g_size_override = 0; /* shard tests: lsh.c:61's size computed over the WHOLE database */
+
 static int csr_build(const mo_db* db, csr_t* c) {
   memset(c, 0, sizeof *c);
   c->total = db->entry_start[db->n_entries];
-  c->size = c->total / 2; /* lsh.c:61 */
+  c->size = g_size_override ? g_size_override : c->total / 2; /* lsh.c:61 */
   if (c->size == 0) return -1;
   for (int k = 0; k < MO_TABLES; k++) {
     c->start[k] = (uint32_t*)calloc((size_t)c->size + 1, sizeof(uint32_t));
@@ -547,8 +549,8 @@ uint32_t mo_get_matches(const mo_db* db, const uint8_t* sig, uint32_t* pairs_out
 
 /* search.c:110-193.  Note the group flush exists only inside the scan loop
  * (search.c:147-165): the group with the greatest (entry, sig) is never scored. */
-int mo_search(const mo_db* db, const uint8_t* qs, uint32_t nq, mo_score* scores_out, uint64_t* L_out,
-              uint64_t* D_out) {
+static int mo_search_impl(const mo_db* db, const uint8_t* qs, uint32_t nq, mo_score* scores_out, uint64_t* L_out,
+                          uint64_t* D_out, uint32_t* last_out /* nq x 5: has, entry, sig, hits, score */) {
   csr_t c;
   int rc = csr_build(db, &c);
   if (rc != 0) {
@@ -570,6 +572,22 @@ int mo_search(const mo_db* db, const uint8_t* qs, uint32_t nq, mo_score* scores_
     }
     L += n;
     qsort(cand, n, sizeof(pair_t), cmp_pair);
+    if (last_out) {
+      uint32_t* lo = last_out + 5 * (size_t)i;
+      lo[0] = n > 0;
+      lo[1] = lo[2] = lo[3] = lo[4] = 0;
+      if (n > 0) {
+        uint32_t hits = 1;
+        for (uint32_t j = n - 1; j > 0 && cmp_pair(&cand[j], &cand[j - 1]) == 0; j--) hits++;
+        const uint8_t* d = db->sigs + ((size_t)db->entry_start[cand[n - 1].entry] + cand[n - 1].sig) * MO_SIG_LEN;
+        unsigned same = 0;
+        for (int b = 0; b < MO_SIG_LEN; b++) same += d[b] == q[b];
+        lo[1] = cand[n - 1].entry;
+        lo[2] = cand[n - 1].sig;
+        lo[3] = hits;
+        lo[4] = same;
+      }
+    }
     uint32_t run = 1;
     for (uint32_t j = 1; j < n; j++) {
       if (cmp_pair(&cand[j], &cand[j - 1]) == 0) {
@@ -597,4 +615,20 @@ int mo_search(const mo_db* db, const uint8_t* qs, uint32_t nq, mo_score* scores_
   int best = mo_select(sc, db->n_entries);
   free(sc);
   return best;
+}
+
+int mo_search(const mo_db* db, const uint8_t* qs, uint32_t nq, mo_score* scores_out, uint64_t* L_out,
+              uint64_t* D_out) {
+  return mo_search_impl(db, qs, nq, scores_out, L_out, D_out, NULL);
+}
+
+/* One shard of a database split by contiguous entry ranges: `table_size` is the size of the whole
+ * database's tables (lsh.c:61).  Besides the shard-local scores (its own last group dropped, as the
+ * reference's loop would) it reports that last group so that a merge can restore it. */
+int mo_search_shard(const mo_db* shard, uint32_t table_size, const uint8_t* qs, uint32_t nq, mo_score* scores_out,
+                    uint32_t* last_out) {
+  g_size_override = table_size;
+  int rc = mo_search_impl(shard, qs, nq, scores_out, NULL, NULL, last_out);
+  g_size_override = 0;
+  return rc;
 }

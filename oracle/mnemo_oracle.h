@@ -84,6 +84,8 @@ typedef struct mo_score {
  * entry index) and stats (L = probed nodes, D = deep checks) may be NULL. */
 int mo_search(const mo_db* db, const uint8_t* query_sigs, uint32_t n_query, mo_score* scores_out,
               uint64_t* L_out, uint64_t* D_out);
+int mo_search_shard(const mo_db* shard, uint32_t table_size, const uint8_t* query_sigs, uint32_t n_query,
+                    mo_score* scores_out, uint32_t* last_out /* n_query x {has, entry, sig, hits, score} */);
 /* final ranking only (search.c:170-193) on a dense per-entry score array */
 int mo_select(const mo_score* per_entry, uint32_t n_entries);
 /* get_matches order restated (lsh.c:89-112): returns count, writes (entry,sig) pairs */

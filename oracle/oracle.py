@@ -160,6 +160,15 @@ class Oracle:
         sc = np.array([(s.score, s.n_matches) for s in scores[:db.n_entries]], dtype=np.float64).reshape(-1, 2)
         return best, sc, L.value, D.value
 
+    def search_shard(self, shard_db, table_size, qsigs):
+        """Per-entry (score, n) of one shard (local entry indices) + last-group records [nq, 5]."""
+        qsigs = np.ascontiguousarray(qsigs, np.uint8)
+        scores = (MoScore * max(shard_db.n_entries, 1))()
+        last = np.zeros((max(len(qsigs), 1), 5), np.uint32)
+        self.lib.mo_search_shard(C.byref(shard_db), C.c_uint32(table_size), _p(qsigs), C.c_uint32(len(qsigs)), scores, _p(last))
+        sc = np.array([(s.score, s.n_matches) for s in scores[:shard_db.n_entries]], dtype=np.float64).reshape(-1, 2)
+        return sc, last[:len(qsigs)]
+
     def select(self, score, n_matches):
         n = len(score)
         arr = (MoScore * max(n, 1))()

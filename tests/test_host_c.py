@@ -1,0 +1,246 @@
+"""The drop-in C library (libmnemophonix.so: reference-named entry points over the CUDA C ABI) and CLI.
+CPU part: text database I/O and WAV container handling against the reference's own functions, error codes.
+GPU part: generate_fingerprint / create_hash_tables / get_matches / search / the command line."""
+import ctypes as C
+import os
+import struct
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from mnemophonix_b200 import synth
+from oracle import ref as refmod
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "mnemophonix_b200", "libmnemophonix.so")
+CLI = os.path.join(ROOT, "mnemophonix_b200", "mnemophonix")
+
+
+@pytest.fixture(scope="module")
+def host():
+    lib = C.CDLL(LIB)
+    lib.read_index.argtypes = [C.c_char_p, C.POINTER(C.POINTER(refmod.Index))]
+    lib.free_index.argtypes = [C.POINTER(refmod.Index)]
+    lib.save.argtypes = [C.c_void_p, C.POINTER(refmod.Signatures), C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]
+    lib.generate_fingerprint.argtypes = [C.c_char_p, C.POINTER(C.POINTER(refmod.Signatures)), C.POINTER(C.c_char_p),
+                                         C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
+    lib.generate_fingerprint_from_samples.argtypes = [C.c_void_p, C.c_uint, C.POINTER(C.POINTER(refmod.Signatures))]
+    lib.free_signatures.argtypes = [C.POINTER(refmod.Signatures)]
+    lib.create_hash_tables.argtypes = [C.POINTER(refmod.Index)]
+    lib.create_hash_tables.restype = C.c_void_p
+    lib.free_hash_tables.argtypes = [C.c_void_p]
+    lib.get_matches.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.POINTER(refmod.SignatureList))]
+    lib.free_signature_list.argtypes = [C.POINTER(refmod.SignatureList)]
+    lib.search.argtypes = [C.POINTER(refmod.Signatures), C.POINTER(refmod.Index), C.c_void_p, C.c_int]
+    return lib
+
+
+def db_text(tracks, names=None):
+    out = []
+    for i, s in enumerate(tracks):
+        name = names[i] if names else f"track{i}.wav"
+        out.append(f"{name}\nartist{i}\n\nalbum {i}\n{len(s)}\n")
+        out.append("".join("".join(f"{b:02x}" for b in row) + "\n" for row in s))
+    return "".join(out)
+
+
+def save_with(lib, sigs, name, artist, title, album):
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    p = tempfile.mktemp()
+    f = libc.fopen(p.encode(), b"w")
+    sigs = np.ascontiguousarray(sigs, np.uint8)
+    s = refmod.Signatures(len(sigs), C.cast(sigs.ctypes.data, C.POINTER(C.c_uint8 * 100)))
+    lib.save.argtypes = [C.c_void_p, C.POINTER(refmod.Signatures), C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]
+    lib.save(f, C.byref(s), name, artist, title, album)
+    libc.fclose(f)
+    data = open(p, "rb").read()
+    os.remove(p)
+    return data
+
+
+def entries_of(pidx):
+    out = []
+    for i in range(pidx.contents.n_entries):
+        e = pidx.contents.entries[i].contents
+        n = e.signatures.contents.n_signatures
+        sig = np.ctypeslib.as_array(C.cast(e.signatures.contents.signatures, C.POINTER(C.c_uint8)), (n, 100)).copy() \
+            if n else np.zeros((0, 100), np.uint8)
+        out.append((e.filename, e.artist, e.track_title, e.album_title, sig))
+    return out
+
+
+def test_save_is_byte_identical_to_reference(host, ref):
+    rng = np.random.RandomState(0)
+    sigs = rng.randint(0, 256, (37, 100)).astype(np.uint8)
+    for meta in ((b"a b.wav", b"art", b"", None), (b"x", None, None, None)):
+        assert save_with(host, sigs, *meta) == save_with(ref.lib, sigs, *meta)
+    assert save_with(host, sigs[:0], b"e", None, None, None) == save_with(ref.lib, sigs[:0], b"e", None, None, None)
+
+
+def test_read_index_matches_reference(host, ref):
+    rng = np.random.RandomState(1)
+    tracks = [rng.randint(0, 256, (n, 100)).astype(np.uint8) for n in (5, 0, 17, 1)]
+    text = db_text(tracks).replace("0a", "0A", 3)          # upper-case hex is accepted (fingerprintio.c:144)
+    p = tempfile.mktemp()
+    open(p, "w").write(text)
+    try:
+        mine = C.POINTER(refmod.Index)()
+        assert host.read_index(p.encode(), C.byref(mine)) == 0
+        rc, theirs = ref.load_index(p)
+        assert rc == 0
+        a, b = entries_of(mine), entries_of(theirs)
+        assert len(a) == len(b) == 4
+        for x, y in zip(a, b):
+            assert x[:4] == y[:4] and np.array_equal(x[4], y[4])
+        host.free_index(mine)
+        ref.lib.free_index(theirs)
+    finally:
+        os.remove(p)
+
+
+@pytest.mark.parametrize("mutation,code", [
+    (lambda t: t[:-50], -3),                               # truncated last signature line
+    (lambda t: t.replace("\n", "", 1), "ours:-3"),         # count line is not a number: DECODING_ERROR by the source, but the
+                                                           # reference then frees an uninitialised pointer (fingerprintio.c:117-119)
+    (lambda t: t[:t.rfind("\n", 0, len(t) - 1) + 1] + "zz" + t[t.rfind("\n", 0, len(t) - 1) + 3:], -3),   # bad hex
+    (lambda t: t + "dangling\n", -3),                      # entry cut after its first line
+])
+def test_read_index_error_codes_match_reference(host, ref, mutation, code):
+    rng = np.random.RandomState(2)
+    text = mutation(db_text([rng.randint(0, 256, (3, 100)).astype(np.uint8)]))
+    p = tempfile.mktemp()
+    open(p, "w").write(text)
+    try:
+        mine = C.POINTER(refmod.Index)()
+        if isinstance(code, str):
+            assert host.read_index(p.encode(), C.byref(mine)) == int(code.split(":")[1])
+        else:
+            rc_ref, _ = ref.load_index(p)
+            assert host.read_index(p.encode(), C.byref(mine)) == rc_ref == code
+    finally:
+        os.remove(p)
+    assert host.read_index(b"/nonexistent/db", C.byref(mine)) == -2
+
+
+def _wav(fmt_tag=1, rate=44100, bits=16, ch=1, fmt_size=16, head=b"RIFF", form=b"WAVE", n=20000, extra=b"", cut=0):
+    pcm = synth.synth_track(3, n / 44100.0, ch)[:n]
+    data = pcm.tobytes()
+    fmt = b"fmt " + struct.pack("<IhHIIHH", fmt_size, fmt_tag, ch, rate, rate * ch * bits // 8, ch * bits // 8, bits)
+    fmt += b"\0" * (fmt_size - 16)
+    body = form + fmt + extra + b"data" + struct.pack("<I", len(data)) + data
+    blob = head + struct.pack("<I", len(body)) + body
+    return blob[:len(blob) - cut] if cut else blob
+
+
+@pytest.mark.parametrize("kwargs,code", [
+    (dict(head=b"RIFX"), -6), (dict(form=b"AVI "), -6),                       # NOT_A_WAVE_FILE
+    (dict(fmt_tag=3), -4), (dict(rate=48000), -4), (dict(bits=8), -4), (dict(fmt_size=18), -4),   # UNSUPPORTED
+    (dict(n=4000), -5),                                                       # FILE_TOO_SMALL (500 samples at 5512 Hz)
+    (dict(cut=1000), "ours:-3"),   # data chunk shorter than declared: read_samples returns DECODING_ERROR, after which the
+                                   # reference frees an uninitialised pointer (fingerprinting.c:43) and crashes
+    (dict(n=100003, extra=b"junk" + struct.pack("<I", 6) + b"abcdef"), None),   # skipped chunk, needs a GPU
+])
+def test_wav_error_codes_match_reference(host, ref, kwargs, code):
+    p = tempfile.mktemp(suffix=".wav")
+    open(p, "wb").write(_wav(**kwargs))
+    try:
+        if isinstance(code, str):
+            psig = C.POINTER(refmod.Signatures)()
+            assert host.generate_fingerprint(p.encode(), C.byref(psig), None, None, None) == int(code.split(":")[1])
+            return
+        rc_ref = ref.fingerprint_wav(p)[0]
+        if code is None:
+            assert rc_ref == 0
+            return
+        psig = C.POINTER(refmod.Signatures)()
+        rc = host.generate_fingerprint(p.encode(), C.byref(psig), None, None, None)
+        assert rc == rc_ref == code
+    finally:
+        os.remove(p)
+    psig = C.POINTER(refmod.Signatures)()
+    assert host.generate_fingerprint(b"/nonexistent.wav", C.byref(psig), None, None, None) == -2
+
+
+def test_cli_usage_and_exit_status():
+    r = subprocess.run([CLI], capture_output=True, text=True)
+    assert r.returncode == 1 and "mnemophonix - A simple audio fingerprinting system" in r.stderr
+    r = subprocess.run([CLI, "search", "x.wav"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage:" in r.stderr
+    r = subprocess.run([CLI, "index", "/nonexistent.wav"], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.strip().endswith("Cannot read file '/nonexistent.wav'")
+
+
+# ------------------------------------------------------------------------------ GPU ----
+
+@pytest.mark.gpu
+def test_generate_fingerprint_and_metadata(host, ref):
+    pcm = synth.synth_track(77, 9.0, 2)
+    p = tempfile.mktemp(suffix=".wav")
+    synth.write_wav(p, pcm, {"IART": "an artist", "INAM": "a title", "IPRD": "an album"})
+    try:
+        psig = C.POINTER(refmod.Signatures)()
+        a, t, al = C.c_char_p(), C.c_char_p(), C.c_char_p()
+        assert host.generate_fingerprint(p.encode(), C.byref(psig), C.byref(a), C.byref(t), C.byref(al)) == 0
+        rc, want, ra, rt, ral = ref.fingerprint_wav(p)
+        got = np.ctypeslib.as_array(C.cast(psig.contents.signatures, C.POINTER(C.c_uint8)),
+                                    (psig.contents.n_signatures, 100)).copy()
+        assert np.array_equal(got, want) and (a.value, t.value, al.value) == (ra, rt, ral)
+        host.free_signatures(psig)
+    finally:
+        os.remove(p)
+
+
+@pytest.mark.gpu
+def test_cli_index_and_search_round_trip(host, ref):
+    d = tempfile.mkdtemp()
+    names = []
+    db = b""
+    for i in range(3):
+        pcm = synth.synth_track(300 + i, 25.0, 1 + i % 2)
+        path = os.path.join(d, f"song{i}.wav")
+        synth.write_wav(path, pcm, {"IART": f"artist {i}", "INAM": f"title {i}"})
+        names.append(path)
+        r = subprocess.run([CLI, "index", path], capture_output=True)
+        assert r.returncode == 0 and b"Generated" in r.stderr
+        rc, sigs, a, t, al = ref.fingerprint_wav(path)
+        assert r.stdout == save_with(ref.lib, sigs, path.encode(), a, t, al)      # byte-identical entry text
+        db += r.stdout
+    dbpath = os.path.join(d, "db")
+    open(dbpath, "wb").write(db)
+    clip = os.path.join(d, "clip.wav")
+    synth.write_wav(clip, synth.synth_track(301, 25.0, 2)[7 * 44100 + 999: 12 * 44100 + 999])
+    r = subprocess.run([CLI, "search", clip, dbpath], capture_output=True, text=True)
+    assert r.returncode == 0
+    assert f"Found match: '{names[1]}'" in r.stdout and "Artist: artist 1" in r.stdout and "Track title: title 1" in r.stdout
+    for line in ("Loading database", "(raw database loading took", "(lsh index building took", "Searching...", "(Search took"):
+        assert line in r.stdout
+    noise = os.path.join(d, "noise.wav")
+    synth.write_wav(noise, (np.random.RandomState(0).standard_normal((44100 * 5, 1)) * 3000).astype(np.int16))
+    r = subprocess.run([CLI, "search", noise, dbpath], capture_output=True, text=True)
+    assert r.returncode == 1 and "No match found" in r.stdout
+
+    # the C API on the same database: create_hash_tables / get_matches / search against the reference's
+    mine = C.POINTER(refmod.Index)()
+    assert host.read_index(dbpath.encode(), C.byref(mine)) == 0
+    rc, theirs = ref.load_index(dbpath)
+    lsh_mine = host.create_hash_tables(mine)
+    lsh_ref = ref.lib.create_hash_tables(theirs)
+    assert C.cast(lsh_mine, C.POINTER(C.c_uint)).contents.value == C.cast(lsh_ref, C.POINTER(C.c_uint)).contents.value
+    rc, q, *_ = ref.fingerprint_wav(clip)
+    s = refmod.Signatures(len(q), C.cast(q.ctypes.data, C.POINTER(C.c_uint8 * 100)))
+    assert host.search(C.byref(s), mine, lsh_mine, 0) == ref.search(q, theirs, lsh_ref) == 1
+    plist = C.POINTER(refmod.SignatureList)()
+    n = host.get_matches(lsh_mine, q[2].ctypes.data, C.byref(plist))
+    got, node = [], plist
+    while node:
+        got.append((node.contents.entry_index, node.contents.signature_index))
+        node = node.contents.next
+    assert n == len(got) and got == ref.get_matches(lsh_ref, q[2])
+    host.free_signature_list(plist)
+    host.free_hash_tables(lsh_mine)
+    host.free_index(mine)
