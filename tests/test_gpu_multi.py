@@ -1,0 +1,78 @@
+"""GPU, N >= 2 (skipped on a single-GPU box): one process per GPU over NCCL.
+Index: tracks sharded with no data-path collective.  Search: database sharded by entry ranges, one
+all-gather of candidate records over NVLink, identical results to the single-GPU search."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from mnemophonix_b200 import capi, dist as mdist, synth
+    ctx = capi.Context(rank)
+    pcms = [synth.synth_track(6000 + i, 14.0 + 2 * (i % 3), 1 + i % 2) for i in range(10)]
+    indexed = mdist.index_sharded(ctx, pcms, rank, world, gather_to=None)
+    # every rank needs the whole database for the search shards: exchange on the host (test only)
+    parts = [None] * world
+    dist.all_gather_object(parts, indexed)
+    merged = {}
+    for p in parts:
+        merged.update(p)
+    sigs = [merged[i][0] for i in range(len(pcms))]
+    clips = [np.ascontiguousarray(p[5 * 44100 + 321: 10 * 44100 + 321]) for p in pcms]
+    qs, _ = ctx.index_pcm_batch(clips)
+    res, db = mdist.search_sharded(ctx, sigs, qs + [sigs[7]], rank, world, device=torch.device("cuda", rank))
+    if rank == 0:
+        out.put(([len(s) for s in sigs], res, [np.asarray(s).tobytes() for s in sigs], [np.asarray(q).tobytes() for q in qs]))
+    dist.barrier()
+    db.close()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def test_sharded_index_and_search_over_nccl(ctx, oracle):
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = min(world, 4)
+    import torch.multiprocessing as mp
+    mpc = mp.get_context("spawn")
+    out = mpc.Queue()
+    port = _free_port()
+    procs = [mpc.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    counts, res, sig_bytes, q_bytes = out.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    sigs = [np.frombuffer(b, np.uint8).reshape(-1, 100) for b in sig_bytes]
+    qs = [np.frombuffer(b, np.uint8).reshape(-1, 100) for b in q_bytes]
+    from mnemophonix_b200 import capi, synth
+    # same tracks indexed on one GPU: identical signatures
+    pcms = [synth.synth_track(6000 + i, 14.0 + 2 * (i % 3), 1 + i % 2) for i in range(10)]
+    single, _ = ctx.index_pcm_batch(pcms)
+    assert all(np.array_equal(a, b) for a, b in zip(single, sigs))
+    db = capi.Db(ctx, sigs)
+    want, _ = db.search(qs + [sigs[7]])
+    db.close()
+    assert res == want and [r[0] for r in res] == list(range(10)) + [7]
+    odb = oracle.make_db(sigs)
+    assert [oracle.search(odb, q)[0] for q in qs] == list(range(10))
