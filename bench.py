@@ -256,27 +256,52 @@ def main():
     value = world * hours_per_step / (ms_per_step / 1e3)
 
     # ---- end to end through the C ABI with host buffers: e2e ----
-    for _ in range(2):
-        batch.upload()
-        batch.run()
-        batch.download(out_ptr=out_pinned.data_ptr())
+    # A streaming indexer keeps two device-side batches in flight, so step i+1's host->device copy
+    # overlaps step i's kernels (two streams: copy engine and SMs run concurrently).  Every step still
+    # performs its own pinned-host -> device copy of the whole track, the kernels, and the device ->
+    # host copy of its signatures; all of it is inside the timed region.
+    stream2 = torch.cuda.Stream()
+    ctx2 = capi.Context(local_rank, stream2.cuda_stream)
+    batch2 = ctx2.batch(track)
+    out_pinned2 = torch.empty((max(batch2.cap, 1), 100), dtype=torch.uint8).pin_memory()
+    lanes = [(batch, out_pinned), (batch2, out_pinned2)]
+
+    def issue(i):
+        b, _ = lanes[i % 2]
+        b.upload()
+        b.run()
+
+    def collect(i):
+        b, o = lanes[i % 2]
+        return b.download(out_ptr=o.data_ptr())
+
+    def e2e_loop(steps):
+        issue(0)
+        for i in range(1, steps):
+            issue(i)
+            collect(i - 1)
+        return collect(steps - 1)
+
+    e2e_loop(3)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
-    e0.record(stream)
-    n_sigs = None
-    for _ in range(args.steps):
-        batch.upload()
-        batch.run()
-        _, n_sigs, status = batch.download(out_ptr=out_pinned.data_ptr())
-    e1.record(stream)
+    _, n_sigs, status = e2e_loop(args.steps)
     barrier()
     wall_ms = (time.perf_counter() - t_wall) * 1e3
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / args.steps
+    e2e_ms = max_over_ranks(wall_ms) / args.steps
     e2e_value = world * hours_per_step / (e2e_ms / 1e3)
     h2d = int(pcm.nbytes)
     d2h = int(batch.cap * 100 + 4)
     assert int(status[0]) == 0 and int(n_sigs[0]) > 0
+    assert torch.equal(out_pinned[: int(n_sigs[0])], out_pinned2[: int(n_sigs[0])])
+    # single-buffer latency of one isolated step (upload -> kernels -> download), for reference
+    t0 = time.perf_counter()
+    issue(0)
+    collect(0)
+    torch.cuda.synchronize()
+    e2e_single_ms = (time.perf_counter() - t0) * 1e3
+    batch2.close()
+    ctx2.close()
 
     # ---- roofline of the dominant kernel ----
     dom = max(stage_ms, key=lambda k: stage_ms[k])
@@ -304,8 +329,10 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms},
-            "gpu_launches": int(launches_per_run * (args.steps * 2 + max(args.warmup, 3) + 2)),
+                    "ms_per_step": e2e_ms, "isolated_step_ms": e2e_single_ms,
+                    "note": "two batches in flight on two streams; each step copies its PCM from pinned host "
+                            "memory and its signatures back; timed on the host clock around all K steps"},
+            "gpu_launches": int(launches_per_run * (args.steps * 2 + max(args.warmup, 3) + 4)),
             "roofline": roofline, "signatures_per_track": int(n_sigs[0])}
 
     if world == 1 and rank == 0 and not args.no_cpu_baseline:

@@ -11,11 +11,12 @@
 // samples on S is, for a given (binade, parity of the incoming m), a fixed integer increment.
 //   A  per chunk: true sum of the squares in double           -> estimate of S at chunk starts
 //   B  per track: exclusive prefix of those sums
-//   C  per chunk: simulate the chunk with real f32 adds from the bottom of each of the 3
-//      binades the estimate allows x 2 parities               -> 6 candidate increments
-//   D  per track, one warp: walk the chunks; take the increment that matches the actual
-//      (binade, parity); if the chunk crosses a binade (or the estimate missed), redo that one
-//      chunk sequentially.  Then rms = (float)((double)sqrtf(S/(float)n) * 10.0) clamped.
+//   C  per chunk (one warp): each lane simulates 128 samples with real f32 adds from the bottom of
+//      each of the 3 binades the estimate allows x 2 parities; these maps "m += delta[parity]"
+//      compose associatively, so a warp scan yields the chunk's 6 candidate increments
+//   D  per track, one warp: stitch 32 chunk maps at a time with a warp scan; a chunk that crosses a
+//      binade (or whose estimate missed) is replayed slice-wise under the actual binade(s).
+//      Then rms = (float)((double)sqrtf(S/(float)n) * 10.0) clamped.
 // The result is bit-identical to the sequential loop by construction, for any input; the
 // estimate only decides how often step D has to fall back to the sequential path.
 #include "common.cuh"
@@ -65,100 +66,170 @@ __global__ void __launch_bounds__(32) sumsq_prefix_kernel(const TrackDev* __rest
   }
 }
 
-// C: one thread per chunk, 6 independent float accumulators
-__global__ void __launch_bounds__(128) sumsq_sim_kernel(const TrackDev* __restrict__ tracks,
-                                                        const uint32_t* __restrict__ chunk_track,
-                                                        uint64_t n_chunks, const float* __restrict__ s5512,
-                                                        const double* __restrict__ chunk_prefix,
-                                                        SumChunkRec* __restrict__ recs) {
-  const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_chunks) return;
-  const TrackDev tr = tracks[chunk_track[c]];
-  const uint32_t first = (uint32_t)(c - tr.chunk_off) * kSumChunk;
-  const uint32_t cnt = min((uint32_t)kSumChunk, tr.n5512 - first);
-  const float* __restrict__ p = s5512 + tr.s_off + first;
+// ---- building blocks shared by C and D ----
+constexpr int kSubChunk = kSumChunk / 32;   // 128 samples per lane
 
-  SumChunkRec rec;
-  rec.pad = 0;
-  // The sequential float sum never exceeds the true sum by more than rounding noise, and in
-  // practice stays above a quarter of it: candidates are the estimate's binade and the two below.
-  const float est = __double2float_ru(chunk_prefix[c] * 1.000001);
-  uint32_t e_hi = __float_as_uint(est) >> 23;
-  if (!(est > 0.0f) || e_hi < 3 || e_hi > 254) e_hi = 0;
-  rec.e_hi = e_hi;
-  float acc[kSumCands][2];
-#pragma unroll
-  for (int j = 0; j < kSumCands; ++j)
-#pragma unroll
-    for (int par = 0; par < 2; ++par) acc[j][par] = __uint_as_float(((e_hi - j) << 23) | (uint32_t)par);
-  if (e_hi) {
-    // s_off and chunk starts are multiples of 4 floats: 128-bit loads, 8 in flight per thread
-    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
-    const uint32_t n4 = cnt >> 2;
-    uint32_t i = 0;
-    for (; i + 8 <= n4; i += 8) {
-      float4 q[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) q[u] = __ldg(p4 + i + u);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float x[4] = {__fmul_rn(q[u].x, q[u].x), __fmul_rn(q[u].y, q[u].y), __fmul_rn(q[u].z, q[u].z),
-                            __fmul_rn(q[u].w, q[u].w)};
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-          for (int j = 0; j < kSumCands; ++j)
-#pragma unroll
-            for (int par = 0; par < 2; ++par) acc[j][par] = __fadd_rn(acc[j][par], x[k]);
-      }
-    }
-    for (; i < n4; ++i) {
-      const float4 q = __ldg(p4 + i);
-      const float x[4] = {__fmul_rn(q.x, q.x), __fmul_rn(q.y, q.y), __fmul_rn(q.z, q.z), __fmul_rn(q.w, q.w)};
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int j = 0; j < kSumCands; ++j)
-#pragma unroll
-          for (int par = 0; par < 2; ++par) acc[j][par] = __fadd_rn(acc[j][par], x[k]);
-    }
-    for (uint32_t i = n4 * 4; i < cnt; ++i) {
-      const float x = __fmul_rn(p[i], p[i]);
-#pragma unroll
-      for (int j = 0; j < kSumCands; ++j)
-#pragma unroll
-        for (int par = 0; par < 2; ++par) acc[j][par] = __fadd_rn(acc[j][par], x);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < kSumCands; ++j)
-#pragma unroll
-    for (int par = 0; par < 2; ++par) {
-      const uint32_t start = ((e_hi - j) << 23) | (uint32_t)par;
-      const uint32_t end = __float_as_uint(acc[j][par]);
-      // valid only while the simulated accumulator never left its binade
-      rec.delta[j][par] = (e_hi && (end >> 23) == (e_hi - j)) ? end - start : kSumInvalid;
-    }
-  recs[c] = rec;
-}
-
-// D: one warp per track.  Within one binade the effect of a chunk is "m += delta[parity(m)]", and
-// such maps compose associatively, so 32 chunks are stitched at once with a warp scan; the first
-// chunk that would leave the binade (or whose candidates missed) is replayed sequentially from
-// shared memory and the walk resumes behind it.
+// (a after b)(p) = b[p] + a[(p + b[p]) & 1]: composition of two "m += delta[parity(m)]" maps
 __device__ __forceinline__ void compose(uint32_t& a0, uint32_t& a1, uint32_t b0, uint32_t b1) {
-  // (a after b)(p) = b[p] + a[(p + b[p]) & 1]
   const uint32_t n0 = b0 + ((b0 & 1u) ? a1 : a0);
   const uint32_t n1 = b1 + ((b1 & 1u) ? a0 : a1);
   a0 = n0;
   a1 = n1;
 }
 
+// Inclusive scan of the per-lane maps over the warp (lane order = sample order).
+__device__ __forceinline__ void scan_maps(uint32_t& a0, uint32_t& a1, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t b0 = __shfl_up_sync(0xffffffffu, a0, o), b1 = __shfl_up_sync(0xffffffffu, a1, o);
+    if (lane >= o) compose(a0, a1, b0, b1);
+  }
+}
+
+// One lane simulates its n (<= 128, multiple of 4 except at the track end) samples with real f32 adds
+// from the bottom of NC candidate binades x 2 parities.  d[j][par] = mantissa increment, or
+// kSumInvalid if that accumulator left its binade.
+template <int NC>
+__device__ __forceinline__ void lane_sim(const float* __restrict__ p, uint32_t n, const uint32_t (&e)[NC],
+                                         uint32_t (&d)[NC][2]) {
+  float acc[NC][2];
+#pragma unroll
+  for (int j = 0; j < NC; ++j)
+#pragma unroll
+    for (int par = 0; par < 2; ++par) acc[j][par] = __uint_as_float((e[j] << 23) | (uint32_t)par);
+  const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
+  const uint32_t n4 = n >> 2;
+  uint32_t i = 0;
+  for (; i + 8 <= n4; i += 8) {
+    float4 q[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) q[u] = __ldg(p4 + i + u);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float x[4] = {__fmul_rn(q[u].x, q[u].x), __fmul_rn(q[u].y, q[u].y), __fmul_rn(q[u].z, q[u].z),
+                          __fmul_rn(q[u].w, q[u].w)};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < NC; ++j)
+#pragma unroll
+          for (int par = 0; par < 2; ++par) acc[j][par] = __fadd_rn(acc[j][par], x[k]);
+    }
+  }
+  for (uint32_t k = i * 4; k < n; ++k) {
+    const float x = __fmul_rn(p[k], p[k]);
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+#pragma unroll
+      for (int par = 0; par < 2; ++par) acc[j][par] = __fadd_rn(acc[j][par], x);
+  }
+#pragma unroll
+  for (int j = 0; j < NC; ++j)
+#pragma unroll
+    for (int par = 0; par < 2; ++par) {
+      const uint32_t start = (e[j] << 23) | (uint32_t)par, end = __float_as_uint(acc[j][par]);
+      d[j][par] = (end >> 23) == e[j] ? end - start : kSumInvalid;
+    }
+}
+
+// C: one WARP per chunk; each lane simulates 128 samples, the 32 maps are composed by a warp scan.
+__global__ void __launch_bounds__(256) sumsq_sim_kernel(const TrackDev* __restrict__ tracks,
+                                                        const uint32_t* __restrict__ chunk_track,
+                                                        uint64_t n_chunks, const float* __restrict__ s5512,
+                                                        const double* __restrict__ chunk_prefix,
+                                                        SumChunkRec* __restrict__ recs) {
+  const uint64_t c = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= n_chunks) return;
+  const int lane = threadIdx.x & 31;
+  const TrackDev tr = tracks[chunk_track[c]];
+  const uint32_t first = (uint32_t)(c - tr.chunk_off) * kSumChunk;
+  const uint32_t cnt = min((uint32_t)kSumChunk, tr.n5512 - first);
+  const uint32_t lo = min(cnt, (uint32_t)lane * kSubChunk), n = min(cnt - lo, (uint32_t)kSubChunk);
+  // The sequential float sum never exceeds the true sum by more than rounding noise, and in
+  // practice stays above a quarter of it: candidates are the estimate's binade and the two below.
+  const float est = __double2float_ru(chunk_prefix[c] * 1.000001);
+  uint32_t e_hi = __float_as_uint(est) >> 23;
+  if (!(est > 0.0f) || e_hi < 3 || e_hi > 254) e_hi = 0;
+  SumChunkRec rec;
+  rec.pad = 0;
+  rec.e_hi = e_hi;
+  if (e_hi) {
+    const uint32_t e[kSumCands] = {e_hi, e_hi - 1, e_hi - 2};
+    uint32_t d[kSumCands][2];
+    lane_sim<kSumCands>(s5512 + tr.s_off + first + lo, n, e, d);
+#pragma unroll
+    for (int j = 0; j < kSumCands; ++j) {
+      const bool bad = __any_sync(0xffffffffu, d[j][0] == kSumInvalid || d[j][1] == kSumInvalid);
+      uint32_t a0 = d[j][0], a1 = d[j][1];
+      scan_maps(a0, a1, lane);
+      a0 = __shfl_sync(0xffffffffu, a0, 31);
+      a1 = __shfl_sync(0xffffffffu, a1, 31);
+      // valid only if the accumulator, started at the bottom of the binade, never leaves it
+      rec.delta[j][0] = (!bad && a0 < 0x800000u) ? a0 : kSumInvalid;
+      rec.delta[j][1] = (!bad && a1 + 1u < 0x800000u) ? a1 : kSumInvalid;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kSumCands; ++j) rec.delta[j][0] = rec.delta[j][1] = kSumInvalid;
+  }
+  if (lane == 0) recs[c] = rec;
+}
+
+// D: one warp per track.  32 chunk maps are stitched at once with a warp scan; the first chunk that
+// would leave the binade (or whose candidates missed) is replayed: lanes simulate their 128-sample
+// slices under the CURRENT binade, a scan accepts the slices before the crossing, the crossing slice
+// is added sequentially, and the loop continues in the new binade.
+__device__ __forceinline__ uint32_t replay_chunk(uint32_t S, const float* __restrict__ p, uint32_t cnt, int lane) {
+  const uint32_t lo = min(cnt, (uint32_t)lane * kSubChunk), n = min(cnt - lo, (uint32_t)kSubChunk);
+  const uint32_t n_slices = (cnt + kSubChunk - 1) / kSubChunk;
+  uint32_t done = 0;
+  while (done < n_slices) {
+    const uint32_t e = S >> 23;
+    uint32_t first_bad = done;   // without a usable binade: go straight to the sequential slice
+    if (e >= 1 && e < 255) {
+      const uint32_t ee[1] = {e};
+      uint32_t d[1][2];
+      lane_sim<1>(p + lo, n, ee, d);
+      const bool mine = (uint32_t)lane >= done && (uint32_t)lane < n_slices;
+      const bool ok = mine && d[0][0] != kSumInvalid && d[0][1] != kSumInvalid;
+      uint32_t a0 = ok ? d[0][0] : 0u, a1 = ok ? d[0][1] : 0u;
+      scan_maps(a0, a1, lane);
+      const uint32_t m = (S & 0x7fffffu) | 0x800000u;
+      const uint32_t tot = (m & 1u) ? a1 : a0;
+      const uint32_t bad = __ballot_sync(0xffffffffu, mine && (!ok || m + tot >= 0x1000000u));
+      first_bad = bad ? (uint32_t)(__ffs(bad) - 1) : n_slices;
+      if (first_bad > done) S += __shfl_sync(0xffffffffu, tot, first_bad - 1);
+    }
+    done = first_bad;
+    if (done < n_slices) {   // the crossing slice, sequentially (every lane computes the same chain)
+      const uint32_t s0 = done * kSubChunk, sn = min((uint32_t)kSubChunk, cnt - s0);
+      float acc = __uint_as_float(S);
+      const float4* __restrict__ q4 = reinterpret_cast<const float4*>(p + s0);
+      uint32_t i = 0;
+      for (; i + 8 <= (sn >> 2); i += 8) {
+        float4 q[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) q[u] = __ldg(q4 + i + u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          acc = __fadd_rn(acc, __fmul_rn(q[u].x, q[u].x));
+          acc = __fadd_rn(acc, __fmul_rn(q[u].y, q[u].y));
+          acc = __fadd_rn(acc, __fmul_rn(q[u].z, q[u].z));
+          acc = __fadd_rn(acc, __fmul_rn(q[u].w, q[u].w));
+        }
+      }
+      for (uint32_t k = i * 4; k < sn; ++k) acc = __fadd_rn(acc, __fmul_rn(p[s0 + k], p[s0 + k]));
+      S = __float_as_uint(acc);
+      ++done;
+    }
+  }
+  return S;
+}
+
 __global__ void __launch_bounds__(32) sumsq_stitch_kernel(const TrackDev* __restrict__ tracks,
                                                           const float* __restrict__ s5512,
                                                           const SumChunkRec* __restrict__ recs,
                                                           float* __restrict__ sumsq, float* __restrict__ rms_out) {
-  __shared__ __align__(16) float sq[kSumChunk];
   const TrackDev tr = tracks[blockIdx.x];
   const int lane = threadIdx.x;
   const float* __restrict__ s = s5512 + tr.s_off;
@@ -183,34 +254,15 @@ __global__ void __launch_bounds__(32) sumsq_stitch_kernel(const TrackDev* __rest
       const bool mine = (uint32_t)lane >= done && (uint32_t)lane < lim;
       const bool ok = mine && e >= 1 && e < 255 && rec.e_hi && d0 != kSumInvalid && d1 != kSumInvalid;
       uint32_t a0 = ok ? d0 : 0u, a1 = ok ? d1 : 0u;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t b0 = __shfl_up_sync(0xffffffffu, a0, o), b1 = __shfl_up_sync(0xffffffffu, a1, o);
-        if (lane >= o) compose(a0, a1, b0, b1);
-      }
+      scan_maps(a0, a1, lane);
       const uint32_t tot = (m & 1u) ? a1 : a0;   // increment through this lane's chunk
       const uint32_t bad = __ballot_sync(0xffffffffu, mine && (!ok || m + tot >= 0x1000000u));
       const uint32_t first_bad = bad ? (uint32_t)(__ffs(bad) - 1) : lim;
       if (first_bad > done) S += __shfl_sync(0xffffffffu, tot, first_bad - 1);
       done = first_bad;
-      if (done < lim) {   // sequential replay of chunk base+done
+      if (done < lim) {
         const uint32_t first = (base + done) * kSumChunk;
-        const uint32_t cnt = min((uint32_t)kSumChunk, tr.n5512 - first);
-        for (uint32_t i = lane; i < (uint32_t)kSumChunk; i += 32) {
-          const float v = i < cnt ? s[first + i] : 0.0f;
-          sq[i] = __fmul_rn(v, v);   // past the end: + 0.0f leaves the sum unchanged
-        }
-        __syncwarp();
-        float acc = __uint_as_float(S);
-        const float4* q4 = reinterpret_cast<const float4*>(sq);
-        const uint32_t n4 = (cnt + 3) >> 2;
-#pragma unroll 4
-        for (uint32_t i = 0; i < n4; ++i) {
-          const float4 q = q4[i];
-          acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, q.x), q.y), q.z), q.w);
-        }
-        S = __float_as_uint(acc);
-        __syncwarp();
+        S = replay_chunk(S, s + first, min((uint32_t)kSumChunk, tr.n5512 - first), lane);
         ++done;
       }
     }
@@ -233,8 +285,8 @@ void launch_sumsq(const TrackDev* tracks, uint32_t n_tracks, uint64_t n_chunks, 
   if (n_chunks) {
     sumsq_true_kernel<<<(unsigned)((n_chunks + 7) / 8), 256, 0, st>>>(tracks, chunk_track, n_chunks, s5512, chunk_true);
     sumsq_prefix_kernel<<<n_tracks, 32, 0, st>>>(tracks, chunk_true, chunk_prefix);
-    sumsq_sim_kernel<<<(unsigned)((n_chunks + 127) / 128), 128, 0, st>>>(tracks, chunk_track, n_chunks, s5512,
-                                                                          chunk_prefix, recs);
+    sumsq_sim_kernel<<<(unsigned)((n_chunks + 7) / 8), 256, 0, st>>>(tracks, chunk_track, n_chunks, s5512,
+                                                                      chunk_prefix, recs);
     *n_launches += 3;
   }
   sumsq_stitch_kernel<<<n_tracks, 32, 0, st>>>(tracks, s5512, recs, sumsq, rms);
