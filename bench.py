@@ -97,6 +97,71 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_near_gpu(index: int) -> None:
+    """Pin this process (and thus its pinned-host allocations) to the CPUs/NUMA node next to its GPU, so that
+    N ranks uploading at once do not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
+def search_section(ctx, sigs, ref_queries: int = 8):
+    """Supplementary search figures on the signatures just produced: the track's signatures are cut into
+    30-second entries (304 signatures), queries are 34-signature excerpts (a 5 s clip)."""
+    from mnemophonix_b200 import capi
+    per = 304
+    entries = [sigs[i:i + per] for i in range(0, len(sigs) - per + 1, per)]
+    rng = np.random.RandomState(3)
+    picks = rng.randint(0, len(entries), 256)
+    offs = rng.randint(0, per - 34, 256)
+    queries = [entries[e][o:o + 34] for e, o in zip(picks, offs)]
+    t0 = time.perf_counter()
+    db = capi.Db(ctx, entries)
+    t_build = time.perf_counter() - t0
+    prepared = capi.Db.prepare(queries)
+    db.search(prepared)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        res, (L, D) = db.search(prepared)
+    dt = (time.perf_counter() - t0) / reps
+    n_qsig = 34 * len(queries)
+    out = {"queries_per_s": len(queries) / dt, "db_entries": len(entries), "db_signatures": per * len(entries),
+           "lsh_build_s": t_build, "probed_nodes_per_query_signature": L / n_qsig,
+           "deep_checks_per_query_signature": D / n_qsig,
+           "algorithmic_GBps": (n_qsig * 300 + 4 * L + 100 * D + 16 * len(queries)) / dt / 1e9,
+           "self_excerpts_identified": int(sum(r[0] == e for r, e in zip(res, picks)))}
+    try:
+        from oracle import ref as refmod
+        import ctypes as C
+        if refmod.available():
+            r = refmod.Ref()
+            keep, ents = [], (C.POINTER(refmod.IndexEntry) * len(entries))()
+            for i, e in enumerate(entries):
+                e = np.ascontiguousarray(e)
+                sg = refmod.Signatures(len(e), C.cast(e.ctypes.data, C.POINTER(C.c_uint8 * 100)))
+                ie = refmod.IndexEntry(b"t", b"", b"", b"", C.pointer(sg))
+                keep.append((e, sg, ie))
+                ents[i] = C.pointer(ie)
+            idx = refmod.Index(len(entries), C.cast(ents, C.POINTER(C.POINTER(refmod.IndexEntry))))
+            lsh = r.lib.create_hash_tables(C.byref(idx))
+            t0 = time.perf_counter()
+            ref_res = [r.search(np.ascontiguousarray(queries[i]), C.pointer(idx), lsh) for i in range(ref_queries)]
+            out["reference_queries_per_s_1thread"] = ref_queries / (time.perf_counter() - t0)
+            out["identical_to_reference_on_sample"] = ref_res == [x[0] for x in res[:ref_queries]]
+    except Exception as exc:   # the checker is optional here
+        out["reference_check_error"] = repr(exc)
+    db.close()
+    return out
+
+
 # ----------------------------------------------------------------------- reference arm ----
 def reference_throughput(seconds_sample: float, channels: int, steps: int, warmup: int):
     """Times the unmodified reference (oracle/_ref -O2, generate_fingerprint on a WAV file) on the host
@@ -202,6 +267,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    bind_near_gpu(local_rank)
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -335,6 +401,8 @@ def main():
             "gpu_launches": int(launches_per_run * (args.steps * 2 + max(args.warmup, 3) + 4)),
             "roofline": roofline, "signatures_per_track": int(n_sigs[0])}
 
+    if world == 1 and rank == 0:
+        line["search"] = search_section(ctx, out_pinned[: int(n_sigs[0])].numpy().copy())
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         r = reference_throughput(args.cpu_sample_seconds, args.channels, 1, 0)
         if r is not None:

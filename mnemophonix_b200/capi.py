@@ -312,10 +312,16 @@ class Db:
             self.ctx._check(int(n), "mnemo_db_get_matches")
         return [tuple(x) for x in out[:min(n, cap)].tolist()]
 
+    @staticmethod
+    def prepare(queries):
+        """Concatenate a list of [n,100] u8 arrays once; the result can be passed to search/search_shard."""
+        return _concat(queries)
+
     def search(self, queries):
-        """queries: list of [n,100] u8 arrays.  Returns (results list of (entry, score, n_matches), (L, D))."""
-        qs, qstart = _concat(queries)
-        nq = len(queries)
+        """queries: list of [n,100] u8 arrays (or Db.prepare(list)).  Returns (results list of
+        (entry, score, n_matches), (L, D))."""
+        qs, qstart = queries if isinstance(queries, tuple) else _concat(queries)
+        nq = len(qstart) - 1
         out = (Match * max(nq, 1))()
         stats = (C.c_uint64 * 2)()
         buf = qs if qs.shape[0] else np.zeros((1, SIG_LEN), np.uint8)
@@ -325,8 +331,8 @@ class Db:
 
     def search_shard(self, queries, cap: int | None = None):
         """Per-shard candidate records + last-group records, as numpy structured arrays."""
-        qs, qstart = _concat(queries)
-        nq = len(queries)
+        qs, qstart = queries if isinstance(queries, tuple) else _concat(queries)
+        nq = len(qstart) - 1
         nqs = int(qstart[-1])
         cap = cap or max(1024, nq * 64)
         while True:

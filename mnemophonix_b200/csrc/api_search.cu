@@ -19,7 +19,27 @@ struct mnemo_db {
   std::vector<uint32_t> h_entry_start;
   uint8_t* d_sigs = nullptr;
   uint32_t *d_entry_start = nullptr, *d_sig_entry = nullptr, *d_start = nullptr, *d_ids = nullptr;
+  // scratch kept between search calls (grown on demand): cudaMalloc/cudaFree cost more than the kernels
+  struct Scratch {
+    void* p = nullptr;
+    uint64_t bytes = 0;
+  } scratch[10];
 };
+
+static cudaError_t scratch_get(mnemo_db* db, int slot, uint64_t bytes, void** out) {
+  mnemo_db::Scratch& s = db->scratch[slot];
+  if (s.bytes < bytes || !s.p) {
+    if (s.p) cudaFree(s.p);
+    s.p = nullptr;
+    s.bytes = 0;
+    const uint64_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&s.p, want);
+    if (e != cudaSuccess) return e;
+    s.bytes = want;
+  }
+  *out = s.p;
+  return cudaSuccess;
+}
 
 template <typename T>
 static cudaError_t dalloc(T** p, uint64_t count) {
@@ -90,6 +110,8 @@ extern "C" void mnemo_db_destroy(mnemo_db* db) {
   void* ptrs[] = {db->d_sigs, db->d_entry_start, db->d_sig_entry, db->d_start, db->d_ids};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (auto& sc : db->scratch)
+    if (sc.p) cudaFree(sc.p);
   delete db;
 }
 
@@ -192,16 +214,16 @@ extern "C" int mnemo_search_shard(mnemo_db* db, const uint8_t* query_sigs, const
   do {                              \
     if (e == cudaSuccess) e = (x);  \
   } while (0)
-  TRY(dalloc(&d_q, (uint64_t)n_qsigs * kSigLen + 4));
-  TRY(dalloc(&d_qstart, (uint64_t)n_queries + 1));
-  TRY(dalloc(&d_acc_s, (uint64_t)group * db->n_entries));
-  TRY(dalloc(&d_acc_n, (uint64_t)group * db->n_entries));
-  TRY(dalloc(&d_last, n_qsigs));
-  TRY(dalloc(&d_stats, 2));
-  TRY(dalloc(&d_total, 1));
-  TRY(dalloc(&d_qbase, group));
-  TRY(dalloc(&d_qcnt, group));
-  TRY(dalloc(&d_cands, cand_cap));
+  TRY(scratch_get(db, 0, (uint64_t)n_qsigs * kSigLen + 4, (void**)&d_q));
+  TRY(scratch_get(db, 1, 4ull * ((uint64_t)n_queries + 1), (void**)&d_qstart));
+  TRY(scratch_get(db, 2, 4ull * group * db->n_entries, (void**)&d_acc_s));
+  TRY(scratch_get(db, 3, 4ull * group * db->n_entries, (void**)&d_acc_n));
+  TRY(scratch_get(db, 4, sizeof(mnemo_lastgroup_dev) * (uint64_t)n_qsigs, (void**)&d_last));
+  TRY(scratch_get(db, 5, 16, (void**)&d_stats));
+  TRY(scratch_get(db, 6, 4, (void**)&d_total));
+  TRY(scratch_get(db, 7, 4ull * group, (void**)&d_qbase));
+  TRY(scratch_get(db, 8, 4ull * group, (void**)&d_qcnt));
+  TRY(scratch_get(db, 9, sizeof(CandDev) * (uint64_t)cand_cap, (void**)&d_cands));
   TRY(cudaMemcpyAsync(d_q, query_sigs, (uint64_t)n_qsigs * kSigLen, cudaMemcpyHostToDevice, st));
   TRY(cudaMemsetAsync(d_stats, 0, 16, st));
   std::vector<CandDev> h_cands;
@@ -279,9 +301,6 @@ extern "C" int mnemo_search_shard(mnemo_db* db, const uint8_t* query_sigs, const
     stats[1] = h[1];
   }
 #undef TRY
-  void* ptrs[] = {d_q, d_qstart, d_acc_s, d_acc_n, d_last, d_stats, d_total, d_qbase, d_qcnt, d_cands};
-  for (void* p : ptrs)
-    if (p) cudaFree(p);
   if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_shard");
   if (rc != 0) return rc;
   *n_cands = written;

@@ -34,7 +34,7 @@ constexpr int kK1Threads = kK1Warps * 32;
 constexpr int kK1FramesPerWarp = 8;
 constexpr int kK1TileFrames = kK1Warps * kK1FramesPerWarp;            // 96 frames
 constexpr int kK1TileSamples = kHop * (kK1TileFrames - 1) + kFrame;   // 8128 samples
-constexpr int kScratchStride = 33;
+constexpr int kScratchStride = 36;   // rows 16-byte aligned; 36 = 4 mod 32 keeps STS.32 columns and LDS.128 rows conflict-free
 constexpr int kScratchFloats = 64 * kScratchStride;                   // per warp
 constexpr int kTwHiFloat2 = 2 * 31 * 32;
 constexpr size_t kK1Smem =
@@ -259,23 +259,41 @@ __global__ void __launch_bounds__(kK1Threads, 1)
       stage_lo<5>(re, im);
       stage_lo<6>(re, im);
 
-      // transposition: lane g owns positions 64g+i; afterwards lane t owns i = t and t+32, all g
+      // transposition: lane g owns positions 64g+i; afterwards lane t owns i = t and t+32, all g.
+      // Row i of the scratch holds the 32 values of column i: scalar stores down a column, 128-bit loads
+      // along a row.
       float cr[2][32], ci[2][32];
 #pragma unroll
       for (int i = 0; i < 64; ++i) sc[i * kScratchStride + lane] = re[i];
       __syncwarp();
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
+      for (int h = 0; h < 2; ++h) {
+        const float4* row = reinterpret_cast<const float4*>(sc + (lane + 32 * h) * kScratchStride);
 #pragma unroll
-        for (int g = 0; g < 32; ++g) cr[h][g] = sc[(lane + 32 * h) * kScratchStride + g];
+        for (int c = 0; c < 8; ++c) {
+          const float4 q = row[c];
+          cr[h][4 * c] = q.x;
+          cr[h][4 * c + 1] = q.y;
+          cr[h][4 * c + 2] = q.z;
+          cr[h][4 * c + 3] = q.w;
+        }
+      }
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 64; ++i) sc[i * kScratchStride + lane] = im[i];
       __syncwarp();
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
+      for (int h = 0; h < 2; ++h) {
+        const float4* row = reinterpret_cast<const float4*>(sc + (lane + 32 * h) * kScratchStride);
 #pragma unroll
-        for (int g = 0; g < 32; ++g) ci[h][g] = sc[(lane + 32 * h) * kScratchStride + g];
+        for (int c = 0; c < 8; ++c) {
+          const float4 q = row[c];
+          ci[h][4 * c] = q.x;
+          ci[h][4 * c + 1] = q.y;
+          ci[h][4 * c + 2] = q.z;
+          ci[h][4 * c + 3] = q.w;
+        }
+      }
       __syncwarp();
 
       // columns; the scratch now receives the power terms of outputs 64..767 (index p - 64)

@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kSearchThreads)
   // that the bitmap stays sparse; each partition re-streams the ids (4 bytes each).
   const uint32_t n_pass = (L + kPassCap - 1) / kPassCap;
   const uint32_t per_pass = (L + n_pass - 1) / n_pass;
-  uint32_t bm_words = 1024;   // ~64 bitmap bits per candidate, 4 KB .. 128 KB
+  uint32_t bm_words = 64;   // ~64 bitmap bits per candidate, 256 B .. 128 KB
   while (bm_words < kBitmapMaxWords && bm_words < 2 * per_pass) bm_words <<= 1;
   const uint32_t bm_shift = 32 - (31 - __clz(bm_words * 32));
   const uint32_t* __restrict__ dbw = reinterpret_cast<const uint32_t*>(p.db_sigs);
@@ -243,7 +243,6 @@ __global__ void __launch_bounds__(kSearchThreads)
 
   for (uint32_t pass = 0; pass < n_pass; ++pass) {
     for (uint32_t i = tid; i < bm_words; i += kSearchThreads) bitmap[i] = 0;
-    for (uint32_t i = tid; i < kSetCap; i += kSearchThreads) set[i] = kEmpty;
     if (tid == 0) {
       s_ndup = 0;
       s_nuniq = 0;
@@ -270,10 +269,14 @@ __global__ void __launch_bounds__(kSearchThreads)
     gmax = s_gmax;
     const uint32_t ndup = s_ndup;
     if (ndup <= kDupCap) {
-      // de-duplicate the short list, then one warp per distinct id
+      // de-duplicate the short list (hash set sized to it), then one warp per distinct id
+      uint32_t set_cap = 64;
+      while (set_cap < 2 * ndup) set_cap <<= 1;   // <= kSetCap because ndup <= kDupCap
+      for (uint32_t i = tid; i < set_cap; i += kSearchThreads) set[i] = kEmpty;
+      __syncthreads();
       for (uint32_t i = tid; i < ndup; i += kSearchThreads) {
         const uint32_t g = dup[i];
-        uint32_t h = (g * 2246822519u) & (kSetCap - 1);
+        uint32_t h = (g * 2246822519u) & (set_cap - 1);
         while (true) {
           const uint32_t prev = atomicCAS(&set[h], kEmpty, g);
           if (prev == kEmpty) {
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(kSearchThreads)
             break;
           }
           if (prev == g) break;
-          h = (h + 1) & (kSetCap - 1);
+          h = (h + 1) & (set_cap - 1);
         }
       }
       __syncthreads();

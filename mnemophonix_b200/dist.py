@@ -114,7 +114,7 @@ def search_sharded(ctx, entry_sigs, queries, rank: int, world: int, device, grou
     a, b = cuts[rank], cuts[rank + 1]
     if db is None:
         db = capi.Db(ctx, entry_sigs[a:b], table_size=int(sum(counts)) // 2, entry_base=a)
-    cands, last, qstart, _ = db.search_shard(queries)
+    cands, last, qstart, _ = db.search_shard(queries)   # queries: list, or capi.Db.prepare(list)
     if world == 1:
         return capi.search_finish(cands, None, 1, qstart, len(entry_sigs)), db
     return merge_shards(cands, last, qstart, len(entry_sigs), device=device, group=group), db
