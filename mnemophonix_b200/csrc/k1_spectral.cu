@@ -11,6 +11,8 @@
 //     are 32 independent 64-point sub-transforms, one per lane, fully unrolled in registers
 //     with warp-uniform twiddles read as constant-bank operands;
 //   * one transposition through padded shared memory (bank-conflict-free both ways);
+//   * complex values are 64-bit register pairs and the butterflies use Blackwell's packed FMUL2/FADD2
+//     (two separately rounded f32 operations per issue slot): 6 instructions per butterfly instead of 10;
 //   * stages 7..11 are 64 independent 32-point column transforms (fixed i, g = 0..31), two per
 //     lane, again in registers, with per-lane twiddles in a lane-major shared table;
 //   * the input is real, so positions 0 and L/2 of every sub-transform stay real: those
@@ -34,8 +36,8 @@ constexpr int kK1Threads = kK1Warps * 32;
 constexpr int kK1FramesPerWarp = 8;
 constexpr int kK1TileFrames = kK1Warps * kK1FramesPerWarp;            // 96 frames
 constexpr int kK1TileSamples = kHop * (kK1TileFrames - 1) + kFrame;   // 8128 samples
-constexpr int kScratchStride = 36;   // rows 16-byte aligned; 36 = 4 mod 32 keeps STS.32 columns and LDS.128 rows conflict-free
-constexpr int kScratchFloats = 64 * kScratchStride;                   // per warp
+constexpr int kScratchStride = 68;   // floats per row (32 complex + pad); 68 = 4 mod 32: STS.64 columns and LDS.128 rows conflict-free
+constexpr int kScratchFloats = 32 * kScratchStride;                   // per warp (also holds the 704 power terms)
 constexpr int kTwHiFloat2 = 2 * 31 * 32;
 constexpr size_t kK1Smem =
     sizeof(float) * (2 * kK1TileSamples + kFrame + kK1Warps * kScratchFloats) + sizeof(float2) * kTwHiFloat2 + 16;
@@ -50,20 +52,61 @@ __host__ __device__ constexpr int rev6(int v) {
   return ((v & 1) << 5) | ((v & 2) << 3) | ((v & 4) << 1) | ((v & 8) >> 1) | ((v & 16) >> 3) | ((v & 32) >> 5);
 }
 
-// fft.c:53-62, each operation rounded on its own
-__device__ __forceinline__ void bfly(float& ar, float& ai, float& br, float& bi, const float wr, const float wi) {
-  const float m1 = __fmul_rn(wr, br), m2 = __fmul_rn(wi, bi);
-  const float m3 = __fmul_rn(wr, bi), m4 = __fmul_rn(wi, br);
-  const float tr = __fsub_rn(m1, m2), ti = __fadd_rn(m3, m4);
-  br = __fsub_rn(ar, tr);
-  bi = __fsub_rn(ai, ti);
-  ar = __fadd_rn(ar, tr);
-  ai = __fadd_rn(ai, ti);
+// ---- packed complex arithmetic (Blackwell f32x2: FMUL2 / FADD2, two IEEE-rounded f32 ops per issue) ----
+// A complex value is a 64-bit register pair (re, im).  Only mul and add/sub are ever used packed,
+// and never a packed mul feeding a packed add: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into
+// FFMA2 even with -fmad=false, which would change the rounding.  The products are therefore
+// combined by two scalar adds, exactly as the reference's "w_re*re - w_im*im" / "w_re*im + w_im*re".
+typedef uint64_t cplx;
+__device__ __forceinline__ cplx pk(float re, float im) {
+  cplx r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(re), "f"(im));
+  return r;
+}
+__device__ __forceinline__ void upk(cplx v, float& re, float& im) { asm("mov.b64 {%0, %1}, %2;" : "=f"(re), "=f"(im) : "l"(v)); }
+__device__ __forceinline__ float lo(cplx v) {
+  float a, b;
+  upk(v, a, b);
+  return a;
+}
+__device__ __forceinline__ float hi(cplx v) {
+  float a, b;
+  upk(v, a, b);
+  return b;
+}
+__device__ __forceinline__ cplx mul2(cplx a, cplx b) {
+  cplx r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ cplx add2(cplx a, cplx b) {
+  cplx r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ cplx sub2(cplx a, cplx b) {
+  cplx r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// tao = w * b with every product and sum rounded on its own (fft.c:53-54)
+__device__ __forceinline__ cplx twiddle_mul(cplx b, const float wr, const float wi) {
+  const cplx p = mul2(b, pk(wr, wr));   // (wr*br, wr*bi)
+  const cplx q = mul2(b, pk(wi, wi));   // (wi*br, wi*bi)
+  return pk(__fsub_rn(lo(p), hi(q)), __fadd_rn(hi(p), lo(q)));
+}
+
+// fft.c:53-62: 2 FMUL2 + 2 FADD + 2 FADD2
+__device__ __forceinline__ void bfly(cplx& a, cplx& b, const float wr, const float wi) {
+  const cplx t = twiddle_mul(b, wr, wi);
+  b = sub2(a, t);
+  a = add2(a, t);
 }
 
 // Stage S (span L = 2^S <= 64) of the 64-point sub-transform held in registers.
 template <int S>
-__device__ __forceinline__ void stage_lo(float (&re)[64], float (&im)[64]) {
+__device__ __forceinline__ void stage_lo(cplx (&z)[64]) {
   constexpr int L = 1 << S, H = L >> 1;
 #pragma unroll
   for (int base = 0; base < 64; base += L) {
@@ -72,20 +115,18 @@ __device__ __forceinline__ void stage_lo(float (&re)[64], float (&im)[64]) {
       const int a = base + k, b = a + H;
       const int m = k * (64 / L);   // twiddle (l = L, k) == W64^m
       if (k == 0) {
-        // both inputs real, w = (1, -0): tao == b exactly
-        const float x = re[a], y = re[b];
-        re[a] = __fadd_rn(x, y);
-        re[b] = __fsub_rn(x, y);
+        // both inputs real, w = (1, -0): tao == b exactly; the imaginary halves stay (dead) zeros
+        const float x = lo(z[a]), y = lo(z[b]);
+        z[a] = pk(__fadd_rn(x, y), 0.0f);
+        z[b] = pk(__fsub_rn(x, y), 0.0f);
       } else if (2 * k == H) {
         // both inputs real: tao = (wr*b, wi*b); outputs (a + tr, 0 + ti), (a - tr, 0 - ti)
-        const float tr = __fmul_rn(c_tw64[m].x, re[b]), ti = __fmul_rn(c_tw64[m].y, re[b]);
-        const float x = re[a];
-        re[b] = __fsub_rn(x, tr);
-        im[b] = -ti;
-        re[a] = __fadd_rn(x, tr);
-        im[a] = ti;
+        const float x = lo(z[a]), y = lo(z[b]);
+        const float tr = __fmul_rn(c_tw64[m].x, y), ti = __fmul_rn(c_tw64[m].y, y);
+        z[b] = pk(__fsub_rn(x, tr), -ti);
+        z[a] = pk(__fadd_rn(x, tr), ti);
       } else {
-        bfly(re[a], im[a], re[b], im[b], c_tw64[m].x, c_tw64[m].y);
+        bfly(z[a], z[b], c_tw64[m].x, c_tw64[m].y);
       }
     }
   }
@@ -93,42 +134,39 @@ __device__ __forceinline__ void stage_lo(float (&re)[64], float (&im)[64]) {
 
 // Stages 7..11 on one column (fixed i; element index = g) and the band-power terms.
 // tw points at tw_hi[h][0][lane]; consecutive slots are 32 float2 apart.
-__device__ __forceinline__ void column_pass(float (&cr)[32], float (&ci)[32], const float2* __restrict__ tw,
-                                            float* __restrict__ pw_col) {
+__device__ __forceinline__ void column_pass(cplx (&c)[32], const float2* __restrict__ tw, float* __restrict__ pw_col) {
   {  // stage 7: span 128, k = i
     const float2 w = tw[0];
 #pragma unroll
-    for (int g = 0; g < 32; g += 2) bfly(cr[g], ci[g], cr[g + 1], ci[g + 1], w.x, w.y);
+    for (int g = 0; g < 32; g += 2) bfly(c[g], c[g + 1], w.x, w.y);
   }
 #pragma unroll
   for (int q = 0; q < 2; ++q) {  // stage 8: span 256, k = 64*(g&1) + i
     const float2 w = tw[32 * (1 + q)];
 #pragma unroll
-    for (int g = q; g < 32; g += 4) bfly(cr[g], ci[g], cr[g + 2], ci[g + 2], w.x, w.y);
+    for (int g = q; g < 32; g += 4) bfly(c[g], c[g + 2], w.x, w.y);
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {  // stage 9: span 512
     const float2 w = tw[32 * (3 + q)];
 #pragma unroll
-    for (int g = q; g < 32; g += 8) bfly(cr[g], ci[g], cr[g + 4], ci[g + 4], w.x, w.y);
+    for (int g = q; g < 32; g += 8) bfly(c[g], c[g + 4], w.x, w.y);
   }
 #pragma unroll
   for (int q = 0; q < 8; ++q) {  // stage 10: span 1024
     const float2 w = tw[32 * (7 + q)];
 #pragma unroll
-    for (int g = q; g < 32; g += 16) bfly(cr[g], ci[g], cr[g + 8], ci[g + 8], w.x, w.y);
+    for (int g = q; g < 32; g += 16) bfly(c[g], c[g + 8], w.x, w.y);
   }
   // stage 11: span 2048; outputs 118..742 live in g = 1..11, "a" side only
 #pragma unroll
   for (int g = 1; g <= 11; ++g) {
     const float2 w = tw[32 * (15 + g)];
-    const float br = cr[g + 16], bi = ci[g + 16];
-    const float tr = __fsub_rn(__fmul_rn(w.x, br), __fmul_rn(w.y, bi));
-    const float ti = __fadd_rn(__fmul_rn(w.x, bi), __fmul_rn(w.y, br));
-    const float xr = __fadd_rn(cr[g], tr), xi = __fadd_rn(ci[g], ti);
+    const cplx x = add2(c[g], twiddle_mul(c[g + 16], w.x, w.y));
     // logbins.c:69-71: re/1024.0 and im/1024.0 (exact scalings, rounded to f32), squares, sum
-    const float r = __fmul_rn(xr, 0.0009765625f), q = __fmul_rn(xi, 0.0009765625f);
-    pw_col[64 * (g - 1)] = __fadd_rn(__fmul_rn(r, r), __fmul_rn(q, q));
+    const cplx r = mul2(x, pk(0.0009765625f, 0.0009765625f));
+    const cplx sq = mul2(r, r);
+    pw_col[64 * (g - 1)] = __fadd_rn(lo(sq), hi(sq));
   }
 }
 
@@ -243,62 +281,43 @@ __global__ void __launch_bounds__(kK1Threads, 1)
     const float* tile = tile0 + cur * kK1TileSamples;
 
     for (uint32_t fl = warp; fl < nf; fl += kK1Warps) {
-      float re[64], im[64];
+      cplx z[64];
       {  // spectralimages.c:94-98 Hann multiply, loaded straight into bit-reversed order (fft.c:35-45)
         const float* fs = tile + fl * kHop + rl;
         const float* hw = hann + rl;
 #pragma unroll
-        for (int r = 0; r < 64; ++r) re[rev6(r)] = __fmul_rn(fs[32 * r], hw[32 * r]);
-#pragma unroll
-        for (int i = 0; i < 64; ++i) im[i] = 0.0f;
+        for (int r = 0; r < 64; ++r) z[rev6(r)] = pk(__fmul_rn(fs[32 * r], hw[32 * r]), 0.0f);
       }
-      stage_lo<1>(re, im);
-      stage_lo<2>(re, im);
-      stage_lo<3>(re, im);
-      stage_lo<4>(re, im);
-      stage_lo<5>(re, im);
-      stage_lo<6>(re, im);
+      stage_lo<1>(z);
+      stage_lo<2>(z);
+      stage_lo<3>(z);
+      stage_lo<4>(z);
+      stage_lo<5>(z);
+      stage_lo<6>(z);
 
       // transposition: lane g owns positions 64g+i; afterwards lane t owns i = t and t+32, all g.
-      // Row i of the scratch holds the 32 values of column i: scalar stores down a column, 128-bit loads
-      // along a row.
-      float cr[2][32], ci[2][32];
-#pragma unroll
-      for (int i = 0; i < 64; ++i) sc[i * kScratchStride + lane] = re[i];
-      __syncwarp();
+      // Two rounds (i < 32, then i >= 32) through a 32-row scratch: row i holds the 32 complex values
+      // of column i; 64-bit stores down a column, 128-bit loads along a row, both conflict-free.
+      cplx cz[2][32];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const float4* row = reinterpret_cast<const float4*>(sc + (lane + 32 * h) * kScratchStride);
+        cplx* sc2 = reinterpret_cast<cplx*>(sc);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 q = row[c];
-          cr[h][4 * c] = q.x;
-          cr[h][4 * c + 1] = q.y;
-          cr[h][4 * c + 2] = q.z;
-          cr[h][4 * c + 3] = q.w;
+        for (int i = 0; i < 32; ++i) sc2[i * (kScratchStride / 2) + lane] = z[i + 32 * h];
+        __syncwarp();
+        const ulonglong2* row = reinterpret_cast<const ulonglong2*>(sc + lane * kScratchStride);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const ulonglong2 q = row[c];
+          cz[h][2 * c] = q.x;
+          cz[h][2 * c + 1] = q.y;
         }
+        __syncwarp();
       }
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 64; ++i) sc[i * kScratchStride + lane] = im[i];
-      __syncwarp();
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float4* row = reinterpret_cast<const float4*>(sc + (lane + 32 * h) * kScratchStride);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 q = row[c];
-          ci[h][4 * c] = q.x;
-          ci[h][4 * c + 1] = q.y;
-          ci[h][4 * c + 2] = q.z;
-          ci[h][4 * c + 3] = q.w;
-        }
-      }
-      __syncwarp();
 
       // columns; the scratch now receives the power terms of outputs 64..767 (index p - 64)
-      column_pass(cr[0], ci[0], tw_hi + lane, sc + lane);
-      column_pass(cr[1], ci[1], tw_hi + 31 * 32 + lane, sc + 32 + lane);
+      column_pass(cz[0], tw_hi + lane, sc + lane);
+      column_pass(cz[1], tw_hi + 31 * 32 + lane, sc + 32 + lane);
       __syncwarp();
 
       // logbins.c:64-75: sequential sum over the band's FFT bins, one band per lane
