@@ -139,6 +139,7 @@ static int build_tables(Tables* t, uint32_t* probes, uint32_t* matched, std::str
     }
   host_edges(t->edges);
   t->log256 = logf((float)256.0);
+  t->inv_log256 = 1.0f / t->log256;
   // Preconditions the kernels rely on.
   if (!(t->tw64[0].x == 1.0f && t->tw64[0].y == 0.0f)) {
     *err = "host libm: cosf/sinf(-0) is not (1, -0)";
@@ -689,7 +690,8 @@ extern "C" int64_t mnemo_selftest_div(mnemo_ctx* ctx, int which, uint32_t lo_bit
   cudaMemsetAsync(d_bad + 1, 0xff, 8, ctx->stream);
   const uint64_t kChunk = 1ull << 30;
   for (uint64_t off = 0; off < n; off += kChunk)
-    launch_div_test(which, (uint32_t)(lo_bits + off), (n - off < kChunk) ? (n - off) : kChunk, d_bad, ctx->stream);
+    launch_div_test(which, (uint32_t)(lo_bits + off), (n - off < kChunk) ? (n - off) : kChunk, d_bad, ctx->h_tables.log256,
+                    ctx->h_tables.inv_log256, ctx->stream);
   unsigned long long bad[2] = {0, 0};
   cudaError_t e = cudaMemcpyAsync(bad, d_bad, 16, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -52,6 +52,7 @@ struct Tables {
   float2 tw_hi[2][31][32];      // stage 7..11 twiddles per (half, slot, lane)
   uint16_t edges[kBands + 1];   // logbins.c:44-55
   float log256;                 // logf(256.0f)                              (spectralimages.c:57)
+  float inv_log256;             // RN(1 / log256) in f32, for the exact reciprocal division
   int logf_variant;             // which glibc logf build the host runs (0 baseline, 1 fma)
 };
 
@@ -80,7 +81,8 @@ void launch_compact(const uint8_t* sig_dense, const uint8_t* keep, uint64_t n_im
                     cudaStream_t st, int* n_launches);
 void k1_upload_constants(const Tables& t);
 void k0_upload_constants(const Tables& t);
-void launch_div_test(int which, uint32_t lo_bits, uint64_t n, unsigned long long* bad, cudaStream_t st);
+void launch_div_test(int which, uint32_t lo_bits, uint64_t n, unsigned long long* bad, float c, float rc,
+                     cudaStream_t st);
 void launch_logf_range(uint32_t lo_bits, uint32_t n, int variant, float* out, cudaStream_t st);
 int k1_tile_frames();
 int k0_tile_outputs();

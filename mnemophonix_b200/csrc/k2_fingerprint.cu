@@ -73,7 +73,7 @@ __device__ __forceinline__ void hist_add(uint32_t* __restrict__ hist, uint32_t d
 }
 
 template <int LOGF_VARIANT>
-__global__ void __launch_bounds__(kK2Threads, 4)
+__global__ void __launch_bounds__(kK2Threads, 5)
     k2_fingerprint_kernel(const TrackDev* __restrict__ tracks, const uint64_t* __restrict__ img_prefix,
                           uint32_t n_tracks, const Tables* __restrict__ tab, const uint16_t* __restrict__ perms,
                           const float* __restrict__ bins, uint8_t* __restrict__ sig_dense, uint8_t* __restrict__ keep,
@@ -393,27 +393,46 @@ __global__ void __launch_bounds__(kK2Threads, 4)
     return;
   }
 
-  // 7. MinHash (minhash.c:13-28)
-  for (int p = warp; p < kSigLen; p += 8) {
-    const uint16_t* __restrict__ prow = perms + p * kPermLen;
-    uint32_t res = kPermLen;
-#pragma unroll 1
-    for (int cidx = 0; cidx < 8; ++cidx) {
-      const int jj = 32 * cidx + lane;
-      bool hit = false;
-      if (jj < kPermLen) {
-        const uint32_t pos = __ldg(prow + jj);
-        hit = (bits[pos >> 5] >> (pos & 31u)) & 1u;
-      }
-      const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-      if (bal) {
-        res = 32 * cidx + __ffs(bal) - 1;
-        break;
-      }
+  // 7. MinHash (minhash.c:13-28).  Warp w handles permutations w, w+8, ...: the first 32 positions of all
+  // of them are fetched up front (independent loads), most permutations hit there; the rest continue.
+  {
+    constexpr int kPer = (kSigLen + 7) / 8;   // 13
+    uint32_t first[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int p = warp + 8 * k;
+      first[k] = p < kSigLen ? __ldg(perms + p * kPermLen + lane) : 0u;
     }
-    if (lane == 0) {
-      s_sig[p] = (uint8_t)res;
-      if (res != kPermLen) s_any = 1;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int p = warp + 8 * k;
+      if (p >= kSigLen) break;
+      const uint32_t pos = first[k];
+      uint32_t bal = __ballot_sync(0xffffffffu, (bits[pos >> 5] >> (pos & 31u)) & 1u);
+      uint32_t res = kPermLen;
+      if (bal) {
+        res = __ffs(bal) - 1;
+      } else {
+        const uint16_t* __restrict__ prow = perms + p * kPermLen;
+#pragma unroll 1
+        for (int cidx = 1; cidx < 8; ++cidx) {
+          const int jj = 32 * cidx + lane;
+          bool hit = false;
+          if (jj < kPermLen) {
+            const uint32_t q = __ldg(prow + jj);
+            hit = (bits[q >> 5] >> (q & 31u)) & 1u;
+          }
+          bal = __ballot_sync(0xffffffffu, hit);
+          if (bal) {
+            res = 32 * cidx + __ffs(bal) - 1;
+            break;
+          }
+        }
+      }
+      if (lane == 0) {
+        s_sig[p] = (uint8_t)res;
+        if (res != kPermLen) s_any = 1;
+      }
     }
   }
   __syncthreads();
@@ -445,7 +464,8 @@ __global__ void logf_range_kernel(uint32_t lo_bits, uint32_t n, int variant, flo
 // ---- device self-test of the reciprocal divisions against IEEE division ----
 // which 0: x / M_SQRT2, 1: x / 32767.0 for every float x = bits lo..lo+n-1 (one-step Markstein);
 // which 2: (255*v) / max for pseudo-random float pairs 0 <= v <= max (two-step Markstein).
-__global__ void div_test_kernel(int which, uint32_t lo_bits, uint64_t n, unsigned long long* __restrict__ bad) {
+__global__ void div_test_kernel(int which, uint32_t lo_bits, uint64_t n, unsigned long long* __restrict__ bad, float c,
+                                float rc) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double got, want;
@@ -476,8 +496,9 @@ __global__ void div_test_kernel(int which, uint32_t lo_bits, uint64_t n, unsigne
   }
 }
 
-void launch_div_test(int which, uint32_t lo_bits, uint64_t n, unsigned long long* bad, cudaStream_t st) {
-  if (n) div_test_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(which, lo_bits, n, bad);
+void launch_div_test(int which, uint32_t lo_bits, uint64_t n, unsigned long long* bad, float c, float rc,
+                     cudaStream_t st) {
+  if (n) div_test_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(which, lo_bits, n, bad, c, rc);
 }
 
 void launch_logf_range(uint32_t lo_bits, uint32_t n, int variant, float* out, cudaStream_t st) {
