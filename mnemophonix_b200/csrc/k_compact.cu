@@ -89,16 +89,14 @@ __global__ void __launch_bounds__(kScanThreads) compact_scatter_kernel(const uin
   }
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) pos[n] = block_sums[gridDim.x];
   __syncthreads();
-  // one warp per image: 25 lanes move 4 bytes each (signatures are 100 bytes, 4-byte aligned)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = warp; i < kScanBlock; i += kScanThreads / 32) {
-    if (blk0 + i >= n) break;
-    if (!skeep[i]) continue;
-    if (lane < 25) {
-      const uint32_t* s = reinterpret_cast<const uint32_t*>(sig_dense + (blk0 + i) * kSigLen);
-      uint32_t* d = reinterpret_cast<uint32_t*>(sig_out + (uint64_t)spos[i] * kSigLen);
-      d[lane] = s[lane];
-    }
+  // all threads sweep the block's 2048 x 25 words (signatures are 100 bytes, 4-byte aligned): coalesced
+  // reads, and coalesced writes too because kept signatures land next to each other
+  const uint32_t n_here = (uint32_t)min((uint64_t)kScanBlock, n - blk0);
+  const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(sig_dense + blk0 * kSigLen);
+  uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(sig_out);
+  for (uint32_t w = threadIdx.x; w < n_here * 25u; w += kScanThreads) {
+    const uint32_t i = w / 25u, k = w - i * 25u;
+    if (skeep[i]) dst[(uint64_t)spos[i] * 25u + k] = src[w];
   }
 }
 

@@ -104,6 +104,24 @@ int main(int argc, char* argv[]) {
 
     if (!strcmp(argv[1], "index")) {
         save(stdout, fingerprint, input, artist, track_title, album_title);
+        /* Extension (the reference ignores further arguments): `index a b c ...` appends one entry per
+         * input, in order, paying for the CUDA context once.  A failing input ends the run with status 1
+         * after the entries already written, so the output stays a valid database prefix. */
+        for (int i = 3; i < argc; i++) {
+            free_signatures(fingerprint);
+            free(artist);
+            free(track_title);
+            free(album_title);
+            fingerprint = NULL;
+            artist = track_title = album_title = NULL;
+            res = generate_fingerprint(argv[i], &fingerprint, &artist, &track_title, &album_title);
+            if (res != SUCCESS) {
+                fprintf(stderr, "Cannot index '%s' (error %d)\n", argv[i], res);
+                return 1;
+            }
+            fflush(stdout);
+            save(stdout, fingerprint, argv[i], artist, track_title, album_title);
+        }
         return 0;
     }
 

@@ -110,6 +110,33 @@ def test_clamped_rms_and_clipping(ctx, oracle):
         b.close()
 
 
+def test_randomized_signals_channels_and_lengths(ctx, oracle):
+    # white noise at several levels, DC offsets, full-scale square waves, int16 extremes, 1..6 channels, ragged
+    # lengths (not multiples of 8 / 64 / 4096): one ragged batch, every track compared with the oracle
+    rng = np.random.RandomState(2024)
+    pcms = []
+    for k in range(14):
+        ch = int(rng.randint(1, 7))
+        n = int(rng.randint(81431, 3 * 81431)) + int(rng.randint(0, 9))
+        kind = k % 5
+        if kind == 0:
+            x = rng.standard_normal((n, ch)) * rng.choice([30, 800, 9000, 30000])
+        elif kind == 1:
+            x = rng.standard_normal((n, ch)) * 500 + rng.choice([-20000, 15000])
+        elif kind == 2:
+            x = np.sign(np.sin(np.arange(n)[:, None] * rng.uniform(0.01, 0.3))) * 32767 * np.ones((1, ch))
+        elif kind == 3:
+            x = rng.choice([-32768, 32767, 0, 1, -1], size=(n, ch))
+        else:
+            x = synth.synth_track(900 + k, n / 44100.0 + 0.01, 1)[:n].astype(np.float64) * np.ones((1, ch)) * rng.uniform(0.2, 1.6)
+        pcms.append(np.ascontiguousarray(np.clip(np.round(x), -32768, 32767).astype(np.int16)))
+    got, st = ctx.index_pcm_batch(pcms)
+    for pcm, g, s in zip(pcms, got, st):
+        rc, sigs = oracle.fingerprint_pcm(pcm)
+        assert s == rc
+        assert bits_equal(g, sigs)
+
+
 def test_from_samples_entry_point(ctx, oracle):
     # generate_fingerprint_from_samples (fingerprinting.c:81-109): no resample, no normalisation
     rng = np.random.RandomState(9)

@@ -210,6 +210,8 @@ def test_cli_index_and_search_round_trip(host, ref):
         rc, sigs, a, t, al = ref.fingerprint_wav(path)
         assert r.stdout == save_with(ref.lib, sigs, path.encode(), a, t, al)      # byte-identical entry text
         db += r.stdout
+    r = subprocess.run([CLI, "index"] + names, capture_output=True)     # multi-file extension: same bytes, one process
+    assert r.returncode == 0 and r.stdout == db
     dbpath = os.path.join(d, "db")
     open(dbpath, "wb").write(db)
     clip = os.path.join(d, "clip.wav")
