@@ -35,7 +35,8 @@ __device__ __forceinline__ float downmix_value(int sum, float chf) {
   return div_const_f32(mean, 32767.0, kInv32767);          // exact reciprocal division, common.cuh
 }
 
-template <int CH>
+// INTERIOR: the whole tile lies inside the track, no per-frame bounds checks
+template <int CH, bool INTERIOR>
 __device__ __forceinline__ void stage_tile(float* __restrict__ mono, const TrackDev& tr, uint64_t in0) {
   const int16_t* __restrict__ pcm = tr.pcm;
   // frames past the end of the track contribute +0: acc + 0*h == acc, which is what the
@@ -45,14 +46,15 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ mono, const Track
     for (int i = threadIdx.x; i < (kTileIn + 7) / 8; i += kK0Threads) {
       const uint64_t f = in0 + (uint64_t)i * 8;
       int4 q = make_int4(0, 0, 0, 0);
-      if (f < tr.n_pcm) q = __ldg(v + i);      // buffers carry >= 64 bytes of slack past n_pcm
+      if (INTERIOR || f < tr.n_pcm) q = __ldg(v + i);      // buffers carry >= 64 bytes of slack past n_pcm
       const int w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int lo = (int)(int16_t)(w[k] & 0xffff), hi = w[k] >> 16;
         const int idx = i * 8 + 2 * k;
-        if (idx < kTileIn) mono[pad32(idx)] = (f + 2 * k < tr.n_pcm) ? downmix_value<1>(lo, 1.0f) : 0.0f;
-        if (idx + 1 < kTileIn) mono[pad32(idx + 1)] = (f + 2 * k + 1 < tr.n_pcm) ? downmix_value<1>(hi, 1.0f) : 0.0f;
+        if (idx < kTileIn) mono[pad32(idx)] = (INTERIOR || f + 2 * k < tr.n_pcm) ? downmix_value<1>(lo, 1.0f) : 0.0f;
+        if (idx + 1 < kTileIn)
+          mono[pad32(idx + 1)] = (INTERIOR || f + 2 * k + 1 < tr.n_pcm) ? downmix_value<1>(hi, 1.0f) : 0.0f;
       }
     }
   } else if (CH == 2) {
@@ -60,13 +62,13 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ mono, const Track
     for (int i = threadIdx.x; i < (kTileIn + 3) / 4; i += kK0Threads) {
       const uint64_t f = in0 + (uint64_t)i * 4;
       int4 q = make_int4(0, 0, 0, 0);
-      if (f < tr.n_pcm) q = __ldg(v + i);
+      if (INTERIOR || f < tr.n_pcm) q = __ldg(v + i);
       const int w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int sum = (int)(int16_t)(w[k] & 0xffff) + (w[k] >> 16);
         const int idx = i * 4 + k;
-        if (idx < kTileIn) mono[pad32(idx)] = (f + k < tr.n_pcm) ? downmix_value<2>(sum, 2.0f) : 0.0f;
+        if (idx < kTileIn) mono[pad32(idx)] = (INTERIOR || f + k < tr.n_pcm) ? downmix_value<2>(sum, 2.0f) : 0.0f;
       }
     }
   } else {
@@ -75,7 +77,7 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ mono, const Track
     for (int i = threadIdx.x; i < kTileIn; i += kK0Threads) {
       const uint64_t f = in0 + i;
       float m = 0.0f;
-      if (f < tr.n_pcm) {
+      if (INTERIOR || f < tr.n_pcm) {
         int sum = 0;
         for (uint32_t c = 0; c < ch; ++c) sum += pcm[f * ch + c];
         m = downmix_value<0>(sum, chf);
@@ -94,9 +96,17 @@ __global__ void __launch_bounds__(kK0Threads) k0_resample_kernel(const TrackDev*
   const uint32_t tile = blockIdx.x - tile_prefix[t];
   const uint64_t out0 = (uint64_t)tile * kTileOut;      // first output of this tile
   const uint64_t in0 = out0 * kDecim;                   // first PCM frame
-  if (tr.channels == 1) stage_tile<1>(mono, tr, in0);
-  else if (tr.channels == 2) stage_tile<2>(mono, tr, in0);
-  else stage_tile<0>(mono, tr, in0);
+  const bool interior = in0 + kTileIn + 8 <= tr.n_pcm;   // block-uniform
+  if (tr.channels == 1) {
+    if (interior) stage_tile<1, true>(mono, tr, in0);
+    else stage_tile<1, false>(mono, tr, in0);
+  } else if (tr.channels == 2) {
+    if (interior) stage_tile<2, true>(mono, tr, in0);
+    else stage_tile<2, false>(mono, tr, in0);
+  } else {
+    if (interior) stage_tile<0, true>(mono, tr, in0);
+    else stage_tile<0, false>(mono, tr, in0);
+  }
   __syncthreads();
 
   // outputs 4*tid .. 4*tid+3 read samples 32*tid .. 32*tid+54 (padded index 33*tid + j + (j >= 32))
