@@ -49,52 +49,87 @@ def make_track(seconds: float, channels: int, seed: int) -> np.ndarray:
 
 # ------------------------------------------------------------------------------ clocks ----
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons in a background thread (NVML, 5 ms period; nvidia-smi as a
+    fallback).  mark() .. stop() delimit the timed region; only samples inside it are summarised."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.samples = []          # (t, sm_mhz, reasons_mask)
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.t0 = None
+        self.thread = None
         self.proc = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        try:
+                            mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        except Exception:
+                            mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.samples.append((time.perf_counter(), mhz, mask))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception:
+            self._start_smi()
+        deadline = time.perf_counter() + 3.0          # make sure sampling is live before timing starts
+        while not self.samples and time.perf_counter() < deadline:
+            time.sleep(0.01)
+
+    def _start_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+
+            def rd():
+                bits = [0x8, 0x40, 0x20, 0x4]
+                for line in self.proc.stdout:
+                    r = [x.strip() for x in line.split(",")]
+                    try:
+                        mask = sum(b for b, v in zip(bits, r[2:6]) if v.lower().startswith("active"))
+                        self.samples.append((time.perf_counter(), float(r[0]), mask))
+                        self.max_mhz = float(r[1])
+                    except Exception:
+                        pass
+            self.thread = threading.Thread(target=rd, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def stop(self):
+        self._stop.set()
+        if self.proc:
+            self.proc.terminate()
 
-    def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 6:
-                continue
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except ValueError:
-                continue
-            for name, v in zip(names, r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+    def summary(self, t0: float, t1: float) -> dict:
+        time.sleep(0.02)
+        inside = [(m, k) for (t, m, k) in self.samples if t0 <= t <= t1]
+        if not inside:                                   # region shorter than one period: nearest samples
+            inside = [(m, k) for (t, m, k) in self.samples[-3:]]
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"], "samples": 0}
+        mask = 0
+        for _, k in inside:
+            mask |= k
+        return {"sm_mhz": float(np.median([m for m, _ in inside])), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for b, n in self.REASONS.items() if mask & b), "samples": len(inside)}
 
 
 def bind_near_gpu(index: int) -> None:
@@ -227,7 +262,7 @@ def reference_throughput(seconds_sample: float, channels: int, steps: int, warmu
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seconds", type=float, default=7200.0)
@@ -304,8 +339,9 @@ def main():
     batch.sync()
     batch.set_timing(True)
     sampler = ClockSampler(local_rank)
-    barrier()
     sampler.start()
+    barrier()
+    t_clk0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         ev0.record(stream)
@@ -313,7 +349,7 @@ def main():
             batch.run()
         ev1.record(stream)
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.summary(t_clk0, time.perf_counter())
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     ms_per_step = ms_total / args.steps
     stage_ms, n_timed = batch.get_timing()
@@ -354,6 +390,8 @@ def main():
     _, n_sigs, status = e2e_loop(args.steps)
     barrier()
     wall_ms = (time.perf_counter() - t_wall) * 1e3
+    clocks_e2e = sampler.summary(t_wall, time.perf_counter())
+    sampler.stop()
     e2e_ms = max_over_ranks(wall_ms) / args.steps
     e2e_value = world * hours_per_step / (e2e_ms / 1e3)
     h2d = int(pcm.nbytes)
@@ -393,7 +431,7 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks, "clocks_e2e": clocks_e2e,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "isolated_step_ms": e2e_single_ms,
                     "note": "two batches in flight on two streams; each step copies its PCM from pinned host "
