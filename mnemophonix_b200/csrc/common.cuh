@@ -102,10 +102,12 @@ static __device__ __constant__ double c_logf_tab[16][2] = {
     {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
     {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
 
-// tab: the 16 x {invc, logc} table (c_logf_tab itself, or a shared-memory copy of it: the index is
-// data dependent, and a shared-memory read is far cheaper than a divergent constant-bank load)
+// invc_tab / logc_tab: the table split into two 16-entry double arrays (stride 1), e.g. in shared memory:
+// the index is data dependent, and 16 doubles span exactly the 32 banks, so a 64-bit read of either
+// array is conflict-free for any index pattern.  Defaults read the constant table (stride 2).
 template <int VARIANT>
-__device__ __forceinline__ float logf_glibc(float x, const double* __restrict__ tab = &c_logf_tab[0][0]) {
+__device__ __forceinline__ float logf_glibc(float x, const double* __restrict__ invc_tab = &c_logf_tab[0][0],
+                                            const double* __restrict__ logc_tab = &c_logf_tab[0][1], int stride = 2) {
   const double ln2 = 0x1.62e42fefa39efp-1;
   const double a0 = -0x1.00ea348b88334p-2, a1 = 0x1.5575b0be00b6ap-2, a2 = -0x1.ffffef20a4123p-2;
   uint32_t ix = __float_as_uint(x);
@@ -115,7 +117,7 @@ __device__ __forceinline__ float logf_glibc(float x, const double* __restrict__ 
   int k = (int)tmp >> 23;
   uint32_t iz = ix - (tmp & 0xff800000u);
   double z = (double)__uint_as_float(iz);
-  double invc = tab[2 * i], logc = tab[2 * i + 1];
+  double invc = invc_tab[stride * i], logc = logc_tab[stride * i];
   if (VARIANT) {  // instruction order of the -mfma ifunc variant
     double y0 = __fma_rn((double)k, ln2, logc);
     double r = __fma_rn(z, invc, -1.0);

@@ -72,6 +72,17 @@ __device__ __forceinline__ void hist_add(uint32_t* __restrict__ hist, uint32_t d
   if (d != 0xFFFFFFFFu && lane == __ffs(peers) - 1) atomicAdd(&hist[d], (uint32_t)__popc(peers));
 }
 
+// spectralimages.c:52-58 for one pixel.  Deliberately NOT inlined: the kernel is ~70 KB of straight-line
+// code and 40 resident warps sit in different phases of it; sharing this body (called 16 times per
+// thread) keeps the instruction working set smaller (stall_no_instruction was 18 % of the samples).
+template <int LOGF_VARIANT>
+__device__ __noinline__ float scale_pixel(float v, double dmx, double rmx, float log256, const double* invc,
+                                          const double* logc) {
+  float sc = __double2float_rn(div_markstein2(__dmul_rn(255.0, (double)v), dmx, rmx));   // spectralimages.c:53
+  if (sc > 255.0f) sc = 255.0f;
+  return __fdiv_rn(logf_glibc<LOGF_VARIANT>(__fadd_rn(1.0f, sc), invc, logc, 1), log256);   // spectralimages.c:57
+}
+
 template <int LOGF_VARIANT>
 __global__ void __launch_bounds__(kK2Threads, 5)
     k2_fingerprint_kernel(const TrackDev* __restrict__ tracks, const uint64_t* __restrict__ img_prefix,
@@ -87,7 +98,8 @@ __global__ void __launch_bounds__(kK2Threads, 5)
   __shared__ uint32_t red[8];
   __shared__ uint32_t s_strong, s_any;
   __shared__ uint8_t s_sig[104];
-  __shared__ double s_logtab[32];
+  __shared__ __align__(128) double s_invc[16];
+  __shared__ __align__(128) double s_logc[16];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t img = blockIdx.x;
@@ -100,7 +112,10 @@ __global__ void __launch_bounds__(kK2Threads, 5)
     s_strong = 0;
     s_any = 0;
   }
-  if (tid < 32) s_logtab[tid] = (&c_logf_tab[0][0])[tid];
+  if (tid < 16) {
+    s_invc[tid] = c_logf_tab[tid][0];
+    s_logc[tid] = c_logf_tab[tid][1];
+  }
 
   // 1. load: element (time = 16*warp + u, band = lane)
   float v[16];
@@ -129,11 +144,7 @@ __global__ void __launch_bounds__(kK2Threads, 5)
   const double rmx = __drcp_rn(dmx);
   const float log256 = tab->log256;
 #pragma unroll
-  for (int u = 0; u < 16; ++u) {
-    float sc = __double2float_rn(div_markstein2(__dmul_rn(255.0, (double)v[u]), dmx, rmx));   // spectralimages.c:53
-    if (sc > 255.0f) sc = 255.0f;
-    v[u] = __fdiv_rn(logf_glibc<LOGF_VARIANT>(__fadd_rn(1.0f, sc), s_logtab), log256);          // spectralimages.c:57
-  }
+  for (int u = 0; u < 16; ++u) v[u] = scale_pixel<LOGF_VARIANT>(v[u], dmx, rmx, log256, s_invc, s_logc);
   if (tap_img) {
 #pragma unroll
     for (int u = 0; u < 16; ++u) tap_img[img * kImgElems + (16 * warp + u) * kBands + lane] = v[u];
@@ -394,7 +405,8 @@ __global__ void __launch_bounds__(kK2Threads, 5)
   }
 
   // 7. MinHash (minhash.c:13-28).  Warp w handles permutations w, w+8, ...: the first 32 positions of all
-  // of them are fetched up front (independent loads), most permutations hit there; the rest continue.
+  // of them are fetched up front (independent loads) and most permutations hit there; the ones that
+  // do not are finished by one shared (not unrolled) loop over the remaining positions.
   {
     constexpr int kPer = (kSigLen + 7) / 8;   // 13
     uint32_t first[kPer];
@@ -403,30 +415,41 @@ __global__ void __launch_bounds__(kK2Threads, 5)
       const int p = warp + 8 * k;
       first[k] = p < kSigLen ? __ldg(perms + p * kPermLen + lane) : 0u;
     }
+    uint32_t missed = 0, found = 0;
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
       const int p = warp + 8 * k;
-      if (p >= kSigLen) break;
-      const uint32_t pos = first[k];
-      uint32_t bal = __ballot_sync(0xffffffffu, (bits[pos >> 5] >> (pos & 31u)) & 1u);
-      uint32_t res = kPermLen;
-      if (bal) {
-        res = __ffs(bal) - 1;
-      } else {
-        const uint16_t* __restrict__ prow = perms + p * kPermLen;
+      if (p < kSigLen) {
+        const uint32_t pos = first[k];
+        const uint32_t bal = __ballot_sync(0xffffffffu, (bits[pos >> 5] >> (pos & 31u)) & 1u);
+        if (bal) {
+          if (lane == 0) s_sig[p] = (uint8_t)(__ffs(bal) - 1);
+          found = 1;
+        } else {
+          missed |= 1u << k;
+        }
+      }
+    }
+    if (found && lane == 0) s_any = 1;
 #pragma unroll 1
-        for (int cidx = 1; cidx < 8; ++cidx) {
-          const int jj = 32 * cidx + lane;
-          bool hit = false;
-          if (jj < kPermLen) {
-            const uint32_t q = __ldg(prow + jj);
-            hit = (bits[q >> 5] >> (q & 31u)) & 1u;
-          }
-          bal = __ballot_sync(0xffffffffu, hit);
-          if (bal) {
-            res = 32 * cidx + __ffs(bal) - 1;
-            break;
-          }
+    while (missed) {
+      const int k = __ffs(missed) - 1;
+      missed &= missed - 1;
+      const int p = warp + 8 * k;
+      const uint16_t* __restrict__ prow = perms + p * kPermLen;
+      uint32_t res = kPermLen;
+#pragma unroll 1
+      for (int cidx = 1; cidx < 8; ++cidx) {
+        const int jj = 32 * cidx + lane;
+        bool hit = false;
+        if (jj < kPermLen) {
+          const uint32_t q = __ldg(prow + jj);
+          hit = (bits[q >> 5] >> (q & 31u)) & 1u;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) {
+          res = 32 * cidx + __ffs(bal) - 1;
+          break;
         }
       }
       if (lane == 0) {
