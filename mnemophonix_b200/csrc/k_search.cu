@@ -157,11 +157,11 @@ void launch_lsh_build(const uint8_t* sigs, uint64_t n_sigs, const uint32_t* entr
 // ------------------------------------------------------------------ probe + score ----
 
 constexpr int kSearchThreads = 256;
-constexpr uint32_t kDupCap = 4096;        // short list capacity (ids seen "again")
-constexpr uint32_t kSetCap = 8192;        // hash set slots for de-duplication (power of two, > kDupCap)
-constexpr uint32_t kBitmapMaxWords = 32768;   // 128 KB
+constexpr uint32_t kDupCap = 2048;        // short list capacity (ids seen "again")
+constexpr uint32_t kSetCap = 4096;        // hash set slots for de-duplication (power of two, >= 2 * kDupCap)
+constexpr uint32_t kBitmapMaxWords = 8192;    // 32 KB: 64 KB of shared memory per CTA in all, 3 CTAs per SM
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
-constexpr uint32_t kPassCap = 32768;         // candidates per id-space partition
+constexpr uint32_t kPassCap = 8192;          // candidates per id-space partition (>= 32 bitmap bits each)
 
 size_t search_smem_bytes() { return sizeof(uint32_t) * (kBitmapMaxWords + kDupCap + kSetCap + kDupCap); }
 
@@ -193,7 +193,7 @@ __device__ __forceinline__ int table_of(const Probe& pr, uint32_t i) {
   return k;   // largest k with prefix[k] <= i
 }
 
-__global__ void __launch_bounds__(kSearchThreads)
+__global__ void __launch_bounds__(kSearchThreads, 3)
     search_probe_kernel(SearchParams p) {
   extern __shared__ __align__(16) uint32_t sm[];
   uint32_t* bitmap = sm;
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kSearchThreads)
   // that the bitmap stays sparse; each partition re-streams the ids (4 bytes each).
   const uint32_t n_pass = (L + kPassCap - 1) / kPassCap;
   const uint32_t per_pass = (L + n_pass - 1) / n_pass;
-  uint32_t bm_words = 64;   // ~64 bitmap bits per candidate, 256 B .. 128 KB
+  uint32_t bm_words = 64;   // ~64 bitmap bits per candidate, 256 B .. 32 KB
   while (bm_words < kBitmapMaxWords && bm_words < 2 * per_pass) bm_words <<= 1;
   const uint32_t bm_shift = 32 - (31 - __clz(bm_words * 32));
   const uint32_t* __restrict__ dbw = reinterpret_cast<const uint32_t*>(p.db_sigs);

@@ -212,3 +212,36 @@ def test_full_size_two_hour_stereo_properties(ctx, oracle):
     got, st = b.signatures()
     assert st == [0] and bits_equal(got[0], dense[keep.astype(bool)])
     b.close()
+
+
+def test_staged_api_reuse_and_error_paths(ctx, oracle):
+    from mnemophonix_b200 import capi
+    # empty batch
+    got, st = ctx.index_pcm_batch([])
+    assert got == [] and st == []
+    # zero-length track next to a real one
+    a = synth.synth_track(201, 3.0, 1)
+    got, st = ctx.index_pcm_batch([np.zeros((0, 2), np.int16), a])
+    assert st[0] == -5 and len(got[0]) == 0 and bits_equal(got[1], oracle.fingerprint_pcm(a)[1])
+    # a batch object is reusable: upload different audio of the same shape, run again
+    b = ctx.batch([a])
+    b.upload()
+    b.run()
+    first, _ = b.signatures()
+    a2 = synth.synth_track(202, 3.0, 1)
+    b.upload([a2])
+    b.run()
+    second, _ = b.signatures()
+    assert bits_equal(first[0], oracle.fingerprint_pcm(a)[1]) and bits_equal(second[0], oracle.fingerprint_pcm(a2)[1])
+    # shape mismatch on upload and too small an output buffer are reported, not ignored
+    with pytest.raises(capi.MnemoError):
+        b.upload([a2[:-8]])
+    out = np.empty((1, 100), np.uint8)
+    n = np.zeros(1, np.uint32)
+    stt = np.zeros(1, np.int32)
+    rc = capi.lib().mnemo_batch_download(b.h, out.ctypes.data, 1, n.ctypes.data, stt.ctypes.data)
+    assert rc == -1 and int(n[0]) == len(second[0])
+    # taps are off by default: asking for them is an error, not garbage
+    with pytest.raises(capi.MnemoError):
+        b.read(6, 0)
+    b.close()
