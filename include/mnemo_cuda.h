@@ -144,6 +144,24 @@ int mnemo_search_finish(const mnemo_cand* cands, uint64_t n_cands, const mnemo_l
                         uint32_t n_shards, const uint32_t* query_start, uint32_t n_queries,
                         uint32_t n_entries_total, mnemo_match* out);
 
+/* Peer-memory merge (one process per GPU, NVLink): instead of returning its records to the host, a shard's
+ * search epilogue writes them straight into a result buffer in the HBM of the rank that merges.  The owner
+ * creates the buffer and hands the 64-byte CUDA IPC handle to the other ranks (any host channel); they open
+ * it; every rank then calls mnemo_search_shard_push with its shard rank; after a host-side barrier the owner
+ * calls mnemo_result_finish.  In one process (several shards on one GPU) pass the owner's handle object
+ * itself to every push.  cap_cands bounds the total number of (query, entry) records of all shards. */
+typedef struct mnemo_result mnemo_result;
+int mnemo_result_create(mnemo_ctx* ctx, uint32_t cap_cands, uint32_t n_shards, uint32_t n_query_sigs,
+                        mnemo_result** out, uint8_t ipc_handle[64]);
+int mnemo_result_open(mnemo_ctx* ctx, const uint8_t ipc_handle[64], uint32_t cap_cands, uint32_t n_shards,
+                      uint32_t n_query_sigs, mnemo_result** out);
+int mnemo_result_reset(mnemo_result* r);        /* owner only; before each query batch */
+void mnemo_result_destroy(mnemo_result* r);
+int mnemo_search_shard_push(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
+                            uint32_t n_queries, mnemo_result* dst, uint32_t shard_rank, uint64_t* stats);
+int mnemo_result_finish(mnemo_result* r, const uint32_t* query_start, uint32_t n_queries,
+                        uint32_t n_entries_total, mnemo_match* out);
+
 /* ---- self tests of the exact-arithmetic building blocks (run on the device) ---- */
 /* Compares the device logf against host logf for every float in [lo_bits, hi_bits]; returns the
  * number of mismatches (or <0).  Used to pin the glibc logf mirror exhaustively over [1, 256]. */

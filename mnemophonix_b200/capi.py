@@ -92,6 +92,12 @@ def lib() -> C.CDLL:
             L.mnemo_search_batch.argtypes = [vp, vp, vp, u32, vp, vp]
             L.mnemo_search_shard.argtypes = [vp, vp, vp, u32, vp, u64, C.POINTER(u64), vp, vp]
             L.mnemo_search_finish.argtypes = [vp, u64, vp, u32, vp, u32, u32, vp]
+            L.mnemo_result_create.argtypes = [vp, u32, u32, u32, C.POINTER(vp), vp]
+            L.mnemo_result_open.argtypes = [vp, vp, u32, u32, u32, C.POINTER(vp)]
+            L.mnemo_result_reset.argtypes = [vp]
+            L.mnemo_result_destroy.argtypes = [vp]
+            L.mnemo_search_shard_push.argtypes = [vp, vp, vp, u32, vp, u32, vp]
+            L.mnemo_result_finish.argtypes = [vp, vp, u32, u32, vp]
         _lib = L
     return _lib
 
@@ -350,6 +356,57 @@ class Db:
         c = np.frombuffer(cands, dtype=CAND_DTYPE, count=int(n.value)).copy()
         l = np.frombuffer(last, dtype=LAST_DTYPE, count=nqs).copy()
         return c, l, qstart, (stats[0], stats[1])
+
+
+class Result:
+    """Result buffer of the merging rank (device memory).  Result.create() on the owner returns the object and a
+    64-byte CUDA IPC handle; other processes Result.open() it and their shards push into it over NVLink."""
+
+    def __init__(self, ctx, h, owner, cap, n_shards, n_qsigs):
+        self.ctx, self.h, self.owner, self.cap, self.n_shards, self.n_qsigs = ctx, h, owner, cap, n_shards, n_qsigs
+
+    @classmethod
+    def create(cls, ctx: Context, cap: int, n_shards: int, n_qsigs: int):
+        h = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        ctx._check(lib().mnemo_result_create(ctx.h, cap, n_shards, n_qsigs, C.byref(h), handle), "mnemo_result_create")
+        return cls(ctx, h, True, cap, n_shards, n_qsigs), bytes(handle)
+
+    @classmethod
+    def open(cls, ctx: Context, handle: bytes, cap: int, n_shards: int, n_qsigs: int):
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        ctx._check(lib().mnemo_result_open(ctx.h, buf, cap, n_shards, n_qsigs, C.byref(h)), "mnemo_result_open")
+        return cls(ctx, h, False, cap, n_shards, n_qsigs)
+
+    def reset(self):
+        self.ctx._check(lib().mnemo_result_reset(self.h), "mnemo_result_reset")
+
+    def push(self, db: "Db", queries, shard_rank: int):
+        qs, qstart = queries if isinstance(queries, tuple) else _concat(queries)
+        stats = (C.c_uint64 * 2)()
+        buf = qs if qs.shape[0] else np.zeros((1, SIG_LEN), np.uint8)
+        rc = lib().mnemo_search_shard_push(db.h, buf.ctypes.data, qstart.ctypes.data, len(qstart) - 1, self.h, shard_rank, stats)
+        db.ctx._check(rc, "mnemo_search_shard_push")
+        return stats[0], stats[1]
+
+    def finish(self, qstart: np.ndarray, n_entries_total: int):
+        qstart = np.ascontiguousarray(qstart, np.uint32)
+        nq = len(qstart) - 1
+        out = (Match * max(nq, 1))()
+        self.ctx._check(lib().mnemo_result_finish(self.h, qstart.ctypes.data, nq, n_entries_total, out), "mnemo_result_finish")
+        return [(out[i].entry, out[i].score, out[i].n_matches) for i in range(nq)]
+
+    def close(self):
+        if self.h:
+            lib().mnemo_result_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 CAND_DTYPE = np.dtype([("query", "<u4"), ("entry", "<i4"), ("score", "<f4"), ("n_matches", "<i4")])

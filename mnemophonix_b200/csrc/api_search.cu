@@ -311,6 +311,188 @@ extern "C" int mnemo_search_shard(mnemo_db* db, const uint8_t* query_sigs, const
   return 0;
 }
 
+// ------------------------------------------------------------------ peer-memory merge ----
+// The merging rank owns a result buffer in its HBM; the other ranks (one process per GPU) map it with
+// cudaIpc and their search epilogue writes candidate and last-group records straight into it over NVLink.
+
+struct mnemo_result {
+  mnemo_ctx* ctx = nullptr;
+  bool owner = false;
+  void* base = nullptr;
+  uint32_t cap = 0, n_shards = 0, n_qsigs = 0;
+  ResultHeader* hdr = nullptr;
+  CandDev* cands = nullptr;
+  LastRec* last = nullptr;
+};
+
+static uint64_t result_bytes(uint32_t cap, uint32_t n_shards, uint32_t n_qsigs) {
+  return sizeof(ResultHeader) + (uint64_t)cap * sizeof(CandDev) + (uint64_t)n_shards * n_qsigs * sizeof(LastRec);
+}
+
+static void result_carve(mnemo_result* r) {
+  r->hdr = reinterpret_cast<ResultHeader*>(r->base);
+  r->cands = reinterpret_cast<CandDev*>(r->hdr + 1);
+  r->last = reinterpret_cast<LastRec*>(r->cands + r->cap);
+}
+
+extern "C" int mnemo_result_reset(mnemo_result* r) {
+  if (!r || !r->owner) return -3;
+  cudaSetDevice(r->ctx->device);
+  cudaStream_t st = r->ctx->stream;
+  const ResultHeader h = {0u, r->cap, r->n_shards, r->n_qsigs};
+  cudaError_t e = cudaMemsetAsync(r->base, 0, result_bytes(r->cap, r->n_shards, r->n_qsigs), st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(r->hdr, &h, sizeof h, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return mnemo_fail(r->ctx, e, "mnemo_result_reset");
+  return 0;
+}
+
+extern "C" int mnemo_result_create(mnemo_ctx* ctx, uint32_t cap_cands, uint32_t n_shards, uint32_t n_qsigs,
+                                   mnemo_result** out, uint8_t ipc_handle[64]) {
+  if (!ctx || !out || n_shards == 0) return -3;
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  mnemo_result* r = new (std::nothrow) mnemo_result();
+  if (!r) return -1;
+  r->ctx = ctx;
+  r->owner = true;
+  r->cap = cap_cands;
+  r->n_shards = n_shards;
+  r->n_qsigs = n_qsigs;
+  cudaError_t e = cudaMalloc(&r->base, result_bytes(cap_cands, n_shards, n_qsigs));
+  if (e != cudaSuccess) {
+    delete r;
+    return mnemo_fail(ctx, e, "mnemo_result_create");
+  }
+  result_carve(r);
+  if (ipc_handle) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, r->base);
+    if (e != cudaSuccess) {
+      cudaFree(r->base);
+      delete r;
+      return mnemo_fail(ctx, e, "mnemo_result_create (cudaIpcGetMemHandle)");
+    }
+    memcpy(ipc_handle, &h, 64);
+  }
+  int rc = mnemo_result_reset(r);
+  if (rc != 0) {
+    cudaFree(r->base);
+    delete r;
+    return rc;
+  }
+  *out = r;
+  return 0;
+}
+
+extern "C" int mnemo_result_open(mnemo_ctx* ctx, const uint8_t ipc_handle[64], uint32_t cap_cands, uint32_t n_shards,
+                                 uint32_t n_qsigs, mnemo_result** out) {
+  if (!ctx || !out || !ipc_handle) return -3;
+  *out = nullptr;
+  cudaSetDevice(ctx->device);
+  mnemo_result* r = new (std::nothrow) mnemo_result();
+  if (!r) return -1;
+  r->ctx = ctx;
+  r->owner = false;
+  r->cap = cap_cands;
+  r->n_shards = n_shards;
+  r->n_qsigs = n_qsigs;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(&r->base, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    delete r;
+    return mnemo_fail(ctx, e, "mnemo_result_open (cudaIpcOpenMemHandle)");
+  }
+  result_carve(r);
+  *out = r;
+  return 0;
+}
+
+extern "C" void mnemo_result_destroy(mnemo_result* r) {
+  if (!r) return;
+  cudaSetDevice(r->ctx->device);
+  cudaStreamSynchronize(r->ctx->stream);
+  if (r->owner) cudaFree(r->base);
+  else cudaIpcCloseMemHandle(r->base);
+  delete r;
+}
+
+extern "C" int mnemo_search_shard_push(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
+                                       uint32_t n_queries, mnemo_result* dst, uint32_t shard_rank, uint64_t* stats) {
+  if (!db || !query_start || !dst || shard_rank >= dst->n_shards) return -3;
+  mnemo_ctx* ctx = db->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  if (stats) stats[0] = stats[1] = 0;
+  const uint32_t n_qsigs = query_start[n_queries];
+  if (n_qsigs != dst->n_qsigs) {
+    ctx->err = "mnemo_search_shard_push: result buffer was sized for a different query batch";
+    return -3;
+  }
+  if (n_queries == 0 || n_qsigs == 0 || db->size == 0 || db->n_sigs == 0 || db->n_entries == 0) return 0;
+  const uint64_t per_query = (uint64_t)db->n_entries * 8;
+  const uint32_t group = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_queries, (1ull << 30) / per_query));
+  uint8_t* d_q = nullptr;
+  uint32_t *d_qstart = nullptr, *d_acc_s = nullptr, *d_acc_n = nullptr;
+  mnemo_lastgroup_dev* d_last = nullptr;
+  unsigned long long* d_stats = nullptr;
+  cudaError_t e = cudaSuccess;
+#define TRY(x)                      \
+  do {                              \
+    if (e == cudaSuccess) e = (x);  \
+  } while (0)
+  TRY(scratch_get(db, 0, (uint64_t)n_qsigs * kSigLen + 4, (void**)&d_q));
+  TRY(scratch_get(db, 1, 4ull * ((uint64_t)n_queries + 1), (void**)&d_qstart));
+  TRY(scratch_get(db, 2, 4ull * group * db->n_entries, (void**)&d_acc_s));
+  TRY(scratch_get(db, 3, 4ull * group * db->n_entries, (void**)&d_acc_n));
+  TRY(scratch_get(db, 4, sizeof(mnemo_lastgroup_dev) * (uint64_t)n_qsigs, (void**)&d_last));
+  TRY(scratch_get(db, 5, 16, (void**)&d_stats));
+  TRY(cudaMemcpyAsync(d_q, query_sigs, (uint64_t)n_qsigs * kSigLen, cudaMemcpyHostToDevice, st));
+  TRY(cudaMemsetAsync(d_stats, 0, 16, st));
+  std::vector<uint32_t> h_qstart;
+  for (uint32_t q0 = 0; q0 < n_queries && e == cudaSuccess; q0 += group) {
+    const uint32_t nq = std::min(group, n_queries - q0);
+    h_qstart.assign(query_start + q0, query_start + q0 + nq + 1);
+    const uint32_t s0 = h_qstart[0];
+    for (auto& v : h_qstart) v -= s0;
+    const uint32_t ns = h_qstart[nq];
+    TRY(cudaMemcpyAsync(d_qstart, h_qstart.data(), 4ull * (nq + 1), cudaMemcpyHostToDevice, st));
+    TRY(cudaMemsetAsync(d_acc_s, 0, (uint64_t)nq * db->n_entries * 4, st));
+    TRY(cudaMemsetAsync(d_acc_n, 0, (uint64_t)nq * db->n_entries * 4, st));
+    if (e != cudaSuccess) break;
+    SearchParams p = base_params(db);
+    p.query_sigs = d_q + (uint64_t)s0 * kSigLen;
+    p.query_start = d_qstart;
+    p.n_queries = nq;
+    p.acc_score = d_acc_s;
+    p.acc_n = d_acc_n;
+    p.last = d_last + s0;
+    p.stat_nodes = d_stats;
+    p.stat_deep = d_stats + 1;
+    launch_search(p, ns, st);
+    launch_search_push(d_acc_s, d_acc_n, nq, db->n_entries, db->entry_base, q0, dst->hdr, dst->cands, st);
+    TRY(cudaGetLastError());
+    if (q0 + group < n_queries) TRY(cudaStreamSynchronize(st));   // h_qstart is reused by the next group
+  }
+  if (e == cudaSuccess) {
+    launch_search_last_push(d_last, n_qsigs, db->d_sig_entry, db->d_entry_start, db->entry_base,
+                            dst->last + (uint64_t)shard_rank * n_qsigs, st);
+    TRY(cudaGetLastError());
+  }
+  TRY(cudaStreamSynchronize(st));   // the records are in the merging rank's memory when this returns
+  if (e == cudaSuccess && stats) {
+    unsigned long long h[2] = {0, 0};
+    TRY(cudaMemcpy(h, d_stats, 16, cudaMemcpyDeviceToHost));
+    stats[0] = h[0];
+    stats[1] = h[1];
+  }
+#undef TRY
+  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_shard_push");
+  return 0;
+}
+
 // ---- final ranking: search.c:65-107 comparator + the merge order of glibc's qsort ----
 
 namespace {
@@ -450,4 +632,26 @@ extern "C" int mnemo_search_batch(mnemo_db* db, const uint8_t* query_sigs, const
   }
   if (rc != 0) return rc;
   return mnemo_search_finish(cands.data(), n, nullptr, 1, query_start, n_queries, db->entry_base + db->n_entries, out);
+}
+
+extern "C" int mnemo_result_finish(mnemo_result* r, const uint32_t* query_start, uint32_t n_queries,
+                                   uint32_t n_entries_total, mnemo_match* out) {
+  if (!r || !r->owner || !query_start || !out) return -3;
+  mnemo_ctx* ctx = r->ctx;
+  cudaSetDevice(ctx->device);
+  ResultHeader h;
+  cudaError_t e = cudaMemcpy(&h, r->hdr, sizeof h, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_result_finish");
+  if (h.count > r->cap) {
+    ctx->err = "mnemo_result_finish: candidate capacity exceeded";
+    return -1;
+  }
+  static_assert(sizeof(CandDev) == sizeof(mnemo_cand) && sizeof(LastRec) == sizeof(mnemo_lastgroup), "record layouts");
+  std::vector<mnemo_cand> cands(h.count ? h.count : 1);
+  std::vector<mnemo_lastgroup> last((size_t)r->n_shards * r->n_qsigs + 1);
+  if (h.count) e = cudaMemcpy(cands.data(), r->cands, sizeof(mnemo_cand) * h.count, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && r->n_qsigs)
+    e = cudaMemcpy(last.data(), r->last, sizeof(mnemo_lastgroup) * (size_t)r->n_shards * r->n_qsigs, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_result_finish");
+  return mnemo_search_finish(cands.data(), h.count, last.data(), r->n_shards, query_start, n_queries, n_entries_total, out);
 }

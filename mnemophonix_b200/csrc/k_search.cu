@@ -387,6 +387,63 @@ __global__ void __launch_bounds__(256) search_compact_kernel(const uint32_t* __r
     }
 }
 
+// ---- fused "score -> pack -> gather": the shard's records go straight into the merging rank's HBM ----
+// Same compaction as above, but the destination (record array + its counter) lives in the result buffer of
+// the rank that merges: over NVLink peer memory when that is another GPU (cudaIpc mapping), plain global
+// memory when it is this one.  Space is reserved with one system-scope atomic per query; there is no
+// separate collective and no host staging on the data path.
+__global__ void __launch_bounds__(256) search_compact_push_kernel(const uint32_t* __restrict__ acc_score,
+                                                                  const uint32_t* __restrict__ acc_n,
+                                                                  uint32_t n_entries, uint32_t entry_base,
+                                                                  uint32_t query_base, ResultHeader* __restrict__ hdr,
+                                                                  CandDev* __restrict__ cands) {
+  __shared__ uint32_t ws[8];
+  __shared__ uint32_t s_base;
+  const uint32_t q = blockIdx.x;
+  const uint32_t* __restrict__ rn = acc_n + (uint64_t)q * n_entries;
+  const uint32_t* __restrict__ rs = acc_score + (uint64_t)q * n_entries;
+  const uint32_t per = (n_entries + 255) / 256;
+  const uint32_t lo = min(n_entries, threadIdx.x * per), hi = min(n_entries, lo + per);
+  uint32_t c = 0;
+  for (uint32_t e = lo; e < hi; ++e) c += rn[e] != 0;
+  uint32_t tot;
+  uint32_t off = blk_excl(c, ws, &tot);
+  if (threadIdx.x == 0) s_base = tot ? atomicAdd_system(&hdr->count, tot) : 0;
+  __syncthreads();
+  off += s_base;
+  const uint32_t cap = hdr->cap;
+  for (uint32_t e = lo; e < hi; ++e)
+    if (rn[e] != 0) {
+      if (off < cap) {
+        CandDev r;
+        r.query = query_base + q;
+        r.entry = (int32_t)(entry_base + e);
+        r.score = (float)rs[e];
+        r.n_matches = (int32_t)rn[e];
+        cands[off] = r;
+      }
+      ++off;
+    }
+}
+
+// This shard's "last group" records (one per query signature), converted to (entry, signature) and written
+// into row `shard` of the merging rank's table.
+__global__ void __launch_bounds__(256) search_last_push_kernel(const mnemo_lastgroup_dev* __restrict__ last,
+                                                               uint32_t n_qsigs, const uint32_t* __restrict__ sig_entry,
+                                                               const uint32_t* __restrict__ entry_start,
+                                                               uint32_t entry_base, LastRec* __restrict__ dst) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_qsigs) return;
+  const mnemo_lastgroup_dev l = last[i];
+  LastRec r = {l.has, 0u, 0u, l.hits, l.score};
+  if (l.has) {
+    const uint32_t le = sig_entry[l.g];
+    r.entry = entry_base + le;
+    r.sig = l.g - entry_start[le];
+  }
+  dst[i] = r;
+}
+
 // get_matches for one signature: gather (global id) of every bucket member, table by table
 __global__ void __launch_bounds__(256) search_gather_kernel(SearchParams p, uint32_t* __restrict__ out, uint32_t cap,
                                                             uint32_t* __restrict__ table_counts) {
@@ -423,6 +480,16 @@ void launch_search_compact(const uint32_t* acc_score, const uint32_t* acc_n, uin
                            uint32_t* q_cnt, cudaStream_t st) {
   if (n_queries) search_compact_kernel<<<n_queries, 256, 0, st>>>(acc_score, acc_n, n_entries, entry_base, cands, cap,
                                                                   total, q_base, q_cnt);
+}
+void launch_search_push(const uint32_t* acc_score, const uint32_t* acc_n, uint32_t n_queries, uint32_t n_entries,
+                        uint32_t entry_base, uint32_t query_base, ResultHeader* hdr, CandDev* cands, cudaStream_t st) {
+  if (n_queries)
+    search_compact_push_kernel<<<n_queries, 256, 0, st>>>(acc_score, acc_n, n_entries, entry_base, query_base, hdr, cands);
+}
+void launch_search_last_push(const mnemo_lastgroup_dev* last, uint32_t n_qsigs, const uint32_t* sig_entry,
+                             const uint32_t* entry_start, uint32_t entry_base, LastRec* dst, cudaStream_t st) {
+  if (n_qsigs)
+    search_last_push_kernel<<<(n_qsigs + 255) / 256, 256, 0, st>>>(last, n_qsigs, sig_entry, entry_start, entry_base, dst);
 }
 void launch_search_gather(const SearchParams& p, uint32_t* out, uint32_t cap, uint32_t* table_counts, cudaStream_t st) {
   search_gather_kernel<<<1, 256, 0, st>>>(p, out, cap, table_counts);

@@ -19,6 +19,18 @@ struct CandDev {
   int32_t n_matches;
 };
 
+// Result buffer of the merging rank (device memory, possibly mapped into other processes by cudaIpc):
+// [ResultHeader][CandDev cands[cap]][LastRec last[n_shards][n_qsigs]]
+struct ResultHeader {
+  uint32_t count;   // candidate records reserved so far (may exceed cap: overflow is detected by the owner)
+  uint32_t cap;
+  uint32_t n_shards;
+  uint32_t n_qsigs;
+};
+struct LastRec {
+  uint32_t has, entry, sig, hits, score;
+};
+
 struct SearchParams {
   const uint8_t* db_sigs;        // [n_sigs][100]
   const uint32_t* sig_entry;     // [n_sigs] shard-local entry index
@@ -43,6 +55,10 @@ void launch_search(const SearchParams& p, uint32_t n_query_sigs, cudaStream_t st
 void launch_search_compact(const uint32_t* acc_score, const uint32_t* acc_n, uint32_t n_queries, uint32_t n_entries,
                            uint32_t entry_base, CandDev* cands, uint32_t cap, uint32_t* total, uint32_t* q_base,
                            uint32_t* q_cnt, cudaStream_t st);
+void launch_search_push(const uint32_t* acc_score, const uint32_t* acc_n, uint32_t n_queries, uint32_t n_entries,
+                        uint32_t entry_base, uint32_t query_base, ResultHeader* hdr, CandDev* cands, cudaStream_t st);
+void launch_search_last_push(const mnemo_lastgroup_dev* last, uint32_t n_qsigs, const uint32_t* sig_entry,
+                             const uint32_t* entry_start, uint32_t entry_base, LastRec* dst, cudaStream_t st);
 void launch_search_gather(const SearchParams& p, uint32_t* out, uint32_t cap, uint32_t* table_counts, cudaStream_t st);
 uint32_t lsh_scan_blocks(uint64_t n_slots);
 

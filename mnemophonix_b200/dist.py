@@ -118,3 +118,41 @@ def search_sharded(ctx, entry_sigs, queries, rank: int, world: int, device, grou
     if world == 1:
         return capi.search_finish(cands, None, 1, qstart, len(entry_sigs)), db
     return merge_shards(cands, last, qstart, len(entry_sigs), device=device, group=group), db
+
+
+def search_sharded_push(ctx, entry_sigs, queries, rank: int, world: int, group=None, db=None, merge_rank: int = 0,
+                        cap: int | None = None):
+    """Sharded search with the merge fused into the kernels: every rank's search epilogue writes its candidate
+    and last-group records straight into the merging rank's HBM over NVLink peer memory (CUDA IPC mapping);
+    the only inter-process traffic besides that is the 64-byte handle and two barriers.  Returns
+    (results on merge_rank / None elsewhere, db)."""
+    import torch.distributed as dist
+    counts = [len(s) for s in entry_sigs]
+    cuts = entry_ranges(counts, world)
+    a, b = cuts[rank], cuts[rank + 1]
+    if db is None:
+        db = capi.Db(ctx, entry_sigs[a:b], table_size=int(sum(counts)) // 2, entry_base=a)
+    prepared = queries if isinstance(queries, tuple) else capi.Db.prepare(queries)
+    qstart = prepared[1]
+    nq, nqs = len(qstart) - 1, int(qstart[-1])
+    cap = cap or max(4096, 64 * nq)
+    if world == 1:
+        res, _ = capi.Result.create(ctx, cap, 1, nqs)
+        res.push(db, prepared, 0)
+        out = res.finish(qstart, len(entry_sigs))
+        res.close()
+        return out, db
+    box = [None]
+    if rank == merge_rank:
+        res, handle = capi.Result.create(ctx, cap, world, nqs)
+        box[0] = handle
+    dist.broadcast_object_list(box, src=merge_rank, group=group)
+    if rank != merge_rank:
+        res = capi.Result.open(ctx, box[0], cap, world, nqs)
+    dist.barrier(group=group)              # the buffer is zeroed and mapped everywhere
+    res.push(db, prepared, rank)           # returns once this rank's records are in the merging rank's memory
+    dist.barrier(group=group)
+    out = res.finish(qstart, len(entry_sigs)) if rank == merge_rank else None
+    dist.barrier(group=group)              # nobody unmaps before the owner has read
+    res.close()
+    return out, db

@@ -39,6 +39,9 @@ def _worker(rank, world, port, out):
     clips = [np.ascontiguousarray(p[5 * 44100 + 321: 10 * 44100 + 321]) for p in pcms]
     qs, _ = ctx.index_pcm_batch(clips)
     res, db = mdist.search_sharded(ctx, sigs, qs + [sigs[7]], rank, world, device=torch.device("cuda", rank))
+    res_push, _ = mdist.search_sharded_push(ctx, sigs, qs + [sigs[7]], rank, world, db=db)   # NVLink peer-memory merge
+    if rank == 0:
+        assert res_push == res
     if rank == 0:
         out.put(([len(s) for s in sigs], res, [np.asarray(s).tobytes() for s in sigs], [np.asarray(q).tobytes() for q in qs]))
     dist.barrier()

@@ -156,3 +156,37 @@ def test_long_buckets_take_the_partitioned_path(ctx, oracle):
     dense[cands["entry"], 1] = cands["n_matches"]
     assert np.array_equal(dense, sc)
     db.close()
+
+
+def test_peer_push_merge_equals_single_database(ctx, corpus):
+    """The fused merge: every shard's kernels write their records into one result buffer (here all shards live
+    on this GPU; across GPUs the buffer is mapped by CUDA IPC, tests/test_gpu_multi.py)."""
+    sigs, qs = corpus
+    total = sum(len(s) for s in sigs)
+    single = capi.Db(ctx, sigs)
+    queries = qs + [sigs[2]]
+    want, _ = single.search(queries)
+    single.close()
+    prepared = capi.Db.prepare(queries)
+    for cuts in ([0, 12], [0, 5, 12], [0, 3, 6, 9, 12]):
+        shards = [capi.Db(ctx, sigs[a:b], table_size=total // 2, entry_base=a) for a, b in zip(cuts[:-1], cuts[1:])]
+        res, handle = capi.Result.create(ctx, 4096, len(shards), int(prepared[1][-1]))
+        assert len(handle) == 64
+        for r, sh in enumerate(shards):
+            res.push(sh, prepared, r)
+        assert res.finish(prepared[1], len(sigs)) == want
+        res.reset()                                   # reusable for the next batch
+        for r, sh in enumerate(shards):
+            res.push(sh, prepared, r)
+        assert res.finish(prepared[1], len(sigs)) == want
+        res.close()
+        for sh in shards:
+            sh.close()
+    # capacity overflow is an error, not a truncated answer
+    sh = capi.Db(ctx, sigs)
+    res, _ = capi.Result.create(ctx, 2, 1, int(prepared[1][-1]))
+    res.push(sh, prepared, 0)
+    with pytest.raises(capi.MnemoError):
+        res.finish(prepared[1], len(sigs))
+    res.close()
+    sh.close()

@@ -21,6 +21,7 @@ ap.add_argument("--sigs-per-track", type=int, default=304)
 ap.add_argument("--queries", type=int, default=10000)
 ap.add_argument("--ref-queries", type=int, default=8)
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--merge", default="both", choices=["allgather", "push", "both"])
 args = ap.parse_args()
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); lr = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr)
@@ -52,27 +53,43 @@ t0 = time.perf_counter()
 res, db = mdist.search_sharded(ctx, entry_list, query_list[:64], rank, world, dev)     # builds the shard + warm-up
 torch.cuda.synchronize()
 t_build = time.perf_counter() - t0
-times = []
-for _ in range(args.steps):
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    res, _ = mdist.search_sharded(ctx, entry_list, prepared, rank, world, dev, db=db)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    times.append(dt)
+def timed(fn):
+    ts, out = [], None
+    for _ in range(args.steps):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        ts.append(dt)
+    return float(np.mean(ts)), out
+
+times_push = None
+if args.merge in ("push", "both"):
+    mdist.search_sharded_push(ctx, entry_list, prepared, rank, world, db=db)          # warm-up (maps the buffer once)
+    times_push, res_push = timed(lambda: mdist.search_sharded_push(ctx, entry_list, prepared, rank, world, db=db)[0])
+if args.merge in ("allgather", "both"):
+    t_ag, res = timed(lambda: mdist.search_sharded(ctx, entry_list, prepared, rank, world, dev, db=db)[0])
+    times = [t_ag]
+else:
+    res, times = res_push, [times_push]
 if rank == 0:
     got = [r[0] for r in res]
     correct = int(sum(int(g == t) for g, t in zip(got, qtrack)))
     line = {"metric": "search queries/s", "config": "BASELINE configs[3]: %d query clips x %d-track DB (%d signatures), %d GPU(s)" %
             (args.queries, args.tracks, args.tracks * S, world), "n_gpus": world, "queries_per_s": args.queries / float(np.mean(times)),
             "s_per_batch": float(np.mean(times)), "shard_build_and_warmup_s": t_build, "identified_correct_track": correct,
-            "queries": args.queries}
+            "queries": args.queries, "merge": "NCCL all-gather of records" if args.merge != "push" else "peer-memory push"}
+    if times_push is not None and args.merge == "both":
+        line["peer_push_queries_per_s"] = args.queries / times_push
+        line["peer_push_s_per_batch"] = times_push
+        line["peer_push_equals_allgather"] = res_push == res
     if refmod.available() and args.ref_queries:
         r = refmod.Ref()
         # in-memory struct index for the reference (no 600 MB text file)
