@@ -234,11 +234,15 @@ __global__ void __launch_bounds__(32) sumsq_stitch_kernel(const TrackDev* __rest
   const int lane = threadIdx.x;
   const float* __restrict__ s = s5512 + tr.s_off;
   uint32_t S = 0;   // bits of the float accumulator (non-negative, so bit order == value order)
+  SumChunkRec next;
+  next.e_hi = 0;
+  if ((uint32_t)lane < tr.n_chunks) next = recs[tr.chunk_off + lane];
   for (uint32_t base = 0; base < tr.n_chunks; base += 32) {
     const uint32_t lim = min(32u, tr.n_chunks - base);
-    SumChunkRec rec;
-    rec.e_hi = 0;
-    if ((uint32_t)lane < lim) rec = recs[tr.chunk_off + base + lane];
+    SumChunkRec rec = next;   // this group's records were fetched while the previous group was stitched
+    next.e_hi = 0;
+    if (base + 32 + lane < tr.n_chunks) next = recs[tr.chunk_off + base + 32 + lane];
+    if ((uint32_t)lane >= lim) rec.e_hi = 0;
     uint32_t done = 0;
     while (done < lim) {
       const uint32_t e = S >> 23;
