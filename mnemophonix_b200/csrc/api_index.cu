@@ -218,13 +218,17 @@ extern "C" int mnemo_create(int device, void* stream, mnemo_ctx** out) {
     mnemo_destroy(ctx);
     return rc;
   }
+  // inverse of the permutation table (permutations.c:7-1808): inv[b][p] = j with perm[p][j] == b, else 255
+  std::vector<uint8_t> inv((size_t)8192 * kSigLen, 255);
+  for (int p = 0; p < kSigLen; p++)
+    for (int j = kPermLen - 1; j >= 0; j--) inv[(size_t)k_permutations[p * kPermLen + j] * kSigLen + p] = (uint8_t)j;
   if (cudaMalloc(&ctx->d_tables, sizeof(Tables)) != cudaSuccess ||
-      cudaMalloc(&ctx->d_perms, sizeof(k_permutations)) != cudaSuccess) {
+      cudaMalloc(&ctx->d_inv_perms, inv.size()) != cudaSuccess) {
     mnemo_destroy(ctx);
     return -1;
   }
   cudaMemcpy(ctx->d_tables, &ctx->h_tables, sizeof(Tables), cudaMemcpyHostToDevice);
-  cudaMemcpy(ctx->d_perms, k_permutations, sizeof(k_permutations), cudaMemcpyHostToDevice);
+  cudaMemcpy(ctx->d_inv_perms, inv.data(), inv.size(), cudaMemcpyHostToDevice);
   k1_upload_constants(ctx->h_tables);
   k0_upload_constants(ctx->h_tables);
   e = cudaDeviceSynchronize();
@@ -241,7 +245,7 @@ extern "C" void mnemo_destroy(mnemo_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
-  if (ctx->d_perms) cudaFree(ctx->d_perms);
+  if (ctx->d_inv_perms) cudaFree(ctx->d_inv_perms);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -513,7 +517,7 @@ extern "C" int mnemo_batch_run(mnemo_batch* b) {
                      ctx->sm_count, st);
   launches += k1_tiles ? 1 : 0;
   if (tm) cudaEventRecord(b->ev[3], st);
-  launch_k2_fingerprint(b->d_tracks, b->d_img_prefix, b->n_tracks, b->n_images, ctx->d_tables, ctx->d_perms, b->d_bins,
+  launch_k2_fingerprint(b->d_tracks, b->d_img_prefix, b->n_tracks, b->n_images, ctx->d_tables, ctx->d_inv_perms, b->d_bins,
                         b->d_sig_dense, b->d_keep, b->d_tap_raw, b->d_tap_img, b->d_tap_haar,
                         ctx->h_tables.logf_variant, st);
   launches += b->n_images ? 1 : 0;

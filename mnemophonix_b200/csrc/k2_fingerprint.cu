@@ -17,7 +17,8 @@
 //      then an index-ordered rank among the elements equal to the threshold
 //   6. each thread owns 16 consecutive coefficients = exactly one 32-bit word of the
 //      fingerprint: bits are assembled without atomics
-//   7. MinHash: one warp per permutation, 32 positions per ballot, first set bit wins
+//   7. MinHash inside out: each set bit contributes its position in every permutation (inverse table,
+//      25 words per bit), signature = byte-wise minimum (__vminu4)
 #include "common.cuh"
 
 namespace mnemo {
@@ -86,18 +87,18 @@ __device__ __noinline__ float scale_pixel(float v, double dmx, double rmx, float
 template <int LOGF_VARIANT>
 __global__ void __launch_bounds__(kK2Threads, 5)
     k2_fingerprint_kernel(const TrackDev* __restrict__ tracks, const uint64_t* __restrict__ img_prefix,
-                          uint32_t n_tracks, const Tables* __restrict__ tab, const uint16_t* __restrict__ perms,
+                          uint32_t n_tracks, const Tables* __restrict__ tab, const uint8_t* __restrict__ inv,
                           const float* __restrict__ bins, uint8_t* __restrict__ sig_dense, uint8_t* __restrict__ keep,
                           uint8_t* __restrict__ tap_raw, float* __restrict__ tap_img, float* __restrict__ tap_haar) {
   __shared__ float B[kImgW * kBStride];
   __shared__ float lows[8][kBands];
-  __shared__ uint32_t bits[256];
+  __shared__ uint16_t s_list[256];          // positions of the set bits (<= 200)
+  __shared__ uint32_t s_part[8][32];        // per-warp partial MinHash minima
   __shared__ uint32_t hist[256];
   __shared__ uint32_t list_b[kImgElems];
   __shared__ uint32_t s_sel[3], s_count[2];
   __shared__ uint32_t red[8];
-  __shared__ uint32_t s_strong, s_any;
-  __shared__ uint8_t s_sig[104];
+  __shared__ uint32_t s_strong;
   __shared__ __align__(128) double s_invc[16];
   __shared__ __align__(128) double s_logc[16];
 
@@ -108,10 +109,7 @@ __global__ void __launch_bounds__(kK2Threads, 5)
   const uint64_t j = img - img_prefix[t];
   const float* __restrict__ src = bins + (tr.frame_off + j * kImgStep) * kBands;
 
-  if (tid == 0) {
-    s_strong = 0;
-    s_any = 0;
-  }
+  if (tid == 0) s_strong = 0;
   if (tid < 16) {
     s_invc[tid] = c_logf_tab[tid][0];
     s_logc[tid] = c_logf_tab[tid][1];
@@ -375,6 +373,7 @@ __global__ void __launch_bounds__(kK2Threads, 5)
 #pragma unroll
     for (int w = 0; w < 8; ++w) base += w < warp ? red[w] : 0u;
     eq_before = base + incl - mine;
+    __syncthreads();   // red[] is reused below
   }
 
   // 6. tri-state bits (rawfingerprints.c:61-74); thread tid owns word tid of the 8192-bit array
@@ -393,7 +392,15 @@ __global__ void __launch_bounds__(kK2Threads, 5)
       strong += (double)fabsf(c[e]) > 1.0;
     }
   }
-  bits[tid] = word;
+  // running count of set bits (warp scan now, cross-warp after the barrier): their positions feed MinHash
+  const uint32_t nbits_mine = __popc(word);
+  uint32_t nbits_incl = nbits_mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, nbits_incl, o);
+    if (lane >= o) nbits_incl += y;
+  }
+  if (lane == 31) red[warp] = nbits_incl;
   strong = __reduce_add_sync(0xffffffffu, strong);
   if (lane == 0 && strong) atomicAdd(&s_strong, strong);
   __syncthreads();
@@ -404,75 +411,58 @@ __global__ void __launch_bounds__(kK2Threads, 5)
     return;
   }
 
-  // 7. MinHash (minhash.c:13-28).  Warp w handles permutations w, w+8, ...: the first 32 positions of all
-  // of them are fetched up front (independent loads) and most permutations hit there; the ones that
-  // do not are finished by one shared (not unrolled) loop over the remaining positions.
+  // 7. MinHash (minhash.c:13-28), turned inside out: instead of walking each of the 100 permutations until
+  // it meets a set bit, every set bit b (at most 200) contributes its position in each permutation,
+  // inv[b][p] (255 if b is not among the first 255 entries of permutation p), and the signature is the
+  // byte-wise minimum.  Row b of the inverse table is 100 bytes = 25 words: 25 lanes take 4 permutations each
+  // (__vminu4), the 8 warps split the set bits, and a last step combines the 8 partial minima.
   {
-    constexpr int kPer = (kSigLen + 7) / 8;   // 13
-    uint32_t first[kPer];
+    uint32_t off = nbits_incl - nbits_mine, n_bits = 0;
 #pragma unroll
-    for (int k = 0; k < kPer; ++k) {
-      const int p = warp + 8 * k;
-      first[k] = p < kSigLen ? __ldg(perms + p * kPermLen + lane) : 0u;
+    for (int w = 0; w < 8; ++w) {
+      off += w < warp ? red[w] : 0u;
+      n_bits += red[w];
     }
-    uint32_t missed = 0, found = 0;
+    uint32_t rest = word;
+    while (rest) {
+      s_list[off++] = (uint16_t)(32 * tid + __ffs(rest) - 1);
+      rest &= rest - 1;
+    }
+    __syncthreads();
+    uint32_t m = 0xFFFFFFFFu;
+    if (lane < 25) {
+      const uint32_t* __restrict__ inv32 = reinterpret_cast<const uint32_t*>(inv) + lane;
+      uint32_t i = warp;
+      for (; i + 24 < n_bits; i += 32) {   // 4 independent loads in flight
+        const uint32_t a0 = __ldg(inv32 + 25u * s_list[i]), a1 = __ldg(inv32 + 25u * s_list[i + 8]);
+        const uint32_t a2 = __ldg(inv32 + 25u * s_list[i + 16]), a3 = __ldg(inv32 + 25u * s_list[i + 24]);
+        m = __vminu4(m, __vminu4(__vminu4(a0, a1), __vminu4(a2, a3)));
+      }
+      for (; i < n_bits; i += 8) m = __vminu4(m, __ldg(inv32 + 25u * s_list[i]));
+    }
+    s_part[warp][lane] = m;
+    __syncthreads();
+    if (tid < 32) {
+      uint32_t r = 0xFFFFFFFFu;
 #pragma unroll
-    for (int k = 0; k < kPer; ++k) {
-      const int p = warp + 8 * k;
-      if (p < kSigLen) {
-        const uint32_t pos = first[k];
-        const uint32_t bal = __ballot_sync(0xffffffffu, (bits[pos >> 5] >> (pos & 31u)) & 1u);
-        if (bal) {
-          if (lane == 0) s_sig[p] = (uint8_t)(__ffs(bal) - 1);
-          found = 1;
-        } else {
-          missed |= 1u << k;
-        }
-      }
-    }
-    if (found && lane == 0) s_any = 1;
-#pragma unroll 1
-    while (missed) {
-      const int k = __ffs(missed) - 1;
-      missed &= missed - 1;
-      const int p = warp + 8 * k;
-      const uint16_t* __restrict__ prow = perms + p * kPermLen;
-      uint32_t res = kPermLen;
-#pragma unroll 1
-      for (int cidx = 1; cidx < 8; ++cidx) {
-        const int jj = 32 * cidx + lane;
-        bool hit = false;
-        if (jj < kPermLen) {
-          const uint32_t q = __ldg(prow + jj);
-          hit = (bits[q >> 5] >> (q & 31u)) & 1u;
-        }
-        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-        if (bal) {
-          res = 32 * cidx + __ffs(bal) - 1;
-          break;
-        }
-      }
-      if (lane == 0) {
-        s_sig[p] = (uint8_t)res;
-        if (res != kPermLen) s_any = 1;
-      }
+      for (int w = 0; w < 8; ++w) r = __vminu4(r, s_part[w][tid]);
+      if (tid < 25) reinterpret_cast<uint32_t*>(sig_dense + img * kSigLen)[tid] = r;
+      const uint32_t any = __ballot_sync(0xffffffffu, tid < 25 && r != 0xFFFFFFFFu);
+      if (tid == 0) keep[img] = any ? 1 : 0;   // minhash.c:45: dropped when all 100 values are 255
     }
   }
-  __syncthreads();
-  if (tid < 25) reinterpret_cast<uint32_t*>(sig_dense + img * kSigLen)[tid] = reinterpret_cast<uint32_t*>(s_sig)[tid];
-  if (tid == 0) keep[img] = s_any ? 1 : 0;
 }
 
 void launch_k2_fingerprint(const TrackDev* tracks, const uint64_t* img_prefix, uint32_t n_tracks, uint64_t n_images,
-                           const Tables* tab, const uint16_t* perms, const float* bins, uint8_t* sig_dense,
+                           const Tables* tab, const uint8_t* inv, const float* bins, uint8_t* sig_dense,
                            uint8_t* keep, uint8_t* tap_raw, float* tap_img, float* tap_haar, int logf_variant,
                            cudaStream_t st) {
   if (n_images == 0) return;
   if (logf_variant)
-    k2_fingerprint_kernel<1><<<(unsigned)n_images, kK2Threads, 0, st>>>(tracks, img_prefix, n_tracks, tab, perms, bins,
+    k2_fingerprint_kernel<1><<<(unsigned)n_images, kK2Threads, 0, st>>>(tracks, img_prefix, n_tracks, tab, inv, bins,
                                                                         sig_dense, keep, tap_raw, tap_img, tap_haar);
   else
-    k2_fingerprint_kernel<0><<<(unsigned)n_images, kK2Threads, 0, st>>>(tracks, img_prefix, n_tracks, tab, perms, bins,
+    k2_fingerprint_kernel<0><<<(unsigned)n_images, kK2Threads, 0, st>>>(tracks, img_prefix, n_tracks, tab, inv, bins,
                                                                         sig_dense, keep, tap_raw, tap_img, tap_haar);
 }
 
