@@ -166,10 +166,11 @@ int mnemo_result_finish(mnemo_result* r, const uint32_t* query_start, uint32_t n
 /* Compares the device logf against host logf for every float in [lo_bits, hi_bits]; returns the
  * number of mismatches (or <0).  Used to pin the glibc logf mirror exhaustively over [1, 256]. */
 int64_t mnemo_selftest_logf(mnemo_ctx* ctx, uint32_t lo_bits, uint32_t hi_bits);
-/* Compares the reciprocal-based exact divisions of the kernels with IEEE division on the device;
- * returns the number of mismatches.  which 0: x / M_SQRT2 (haar.c:35-36) and 1: x / 32767.0
- * (wav.c:373) for the n floats whose bit patterns start at lo_bits (n = 2^32 covers every float);
- * 2: (255*v) / max (spectralimages.c:53) for n pseudo-random pairs. */
+/* Compares the reciprocal-based exact divisions of the kernels with IEEE division on the device, for the n
+ * floats whose bit patterns start at lo_bits (n = 2^32 covers every float); returns the number of mismatches.
+ * which 0: x / M_SQRT2 in double (haar.c:35-36); 1: x / 32767.0 (wav.c:373) in FP32, plain and halving forms;
+ * 3: x / M_SQRT2 in FP32 on its domain (0 or |x| >= 2^-103); 4: x / logf(256.0f) (spectralimages.c:57) in FP32
+ * on its domain (0 or |x| >= 2^-106); 2: (255*v) / max (spectralimages.c:53) for n pseudo-random pairs. */
 int64_t mnemo_selftest_div(mnemo_ctx* ctx, int which, uint32_t lo_bits, uint64_t n);
 
 #ifdef __cplusplus

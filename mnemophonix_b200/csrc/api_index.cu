@@ -686,7 +686,7 @@ extern "C" int64_t mnemo_selftest_logf(mnemo_ctx* ctx, uint32_t lo_bits, uint32_
 }
 
 extern "C" int64_t mnemo_selftest_div(mnemo_ctx* ctx, int which, uint32_t lo_bits, uint64_t n) {
-  if (!ctx || which < 0 || which > 2) return -3;
+  if (!ctx || which < 0 || which > 4) return -3;
   cudaSetDevice(ctx->device);
   unsigned long long* d_bad = nullptr;
   if (cudaMalloc(&d_bad, 16) != cudaSuccess) return -1;

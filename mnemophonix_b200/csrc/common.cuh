@@ -163,7 +163,46 @@ __device__ __forceinline__ float div_const_f32(float x, double b, double y) {
 }
 constexpr double kSqrt2 = 1.41421356237309504880;        // M_SQRT2
 constexpr double kInvSqrt2 = 0.70710678118654746172;     // RN(1 / M_SQRT2) as a double
-constexpr double kInv32767 = 3.0518509475997192e-05;     // RN(1 / 32767.0)
+
+// ---- the same constant divisions without leaving FP32 ----
+// (float)((double)x / d) costs two conversions on the 16-lane XU pipe plus three FP64 instructions; the XU pipe
+// was the busiest pipe of K0 and K2.  With d split into two floats h + l and y = RN32(1 / d):
+//   q0 = RN(x * y);  r = x - q0 * (h + l) by two FMAs (the first one exact);  q1 = RN(q0 + r * y)
+// is the correctly rounded quotient, and rounding through double first never changes it.  Not taken on trust:
+// mnemo_selftest_div compares each form against the double-precision division for EVERY float dividend
+// (tools/div_f32_probe.cu is the search that found the domains):
+//   x / 32767.0       exact for all 2^32 floats (32767 is a float, l = 0)                      -> K0
+//   x / M_SQRT2       exact for x == 0 or |x| >= 2^-103 (below that the residual underflows)    -> K2, see haar_*()
+//   x / logf(256.0f)  (an f32 division in the reference) exact for x == 0 or |x| >= 2^-106      -> K2 pixel scale
+// As with div_const_f32, a -0 dividend comes back as +0 and cannot occur.
+constexpr float kInv32767f = 0x1.0002p-15f;              // RN32(1 / 32767)
+constexpr float kSqrt2Hi = 0x1.6a09e6p+0f;               // RN32(M_SQRT2)
+constexpr float kSqrt2Lo = 0x1.9fcef4p-26f;              // RN32(M_SQRT2 - kSqrt2Hi)
+constexpr float kInvSqrt2f = 0x1.6a09e6p-1f;             // RN32(1 / M_SQRT2)
+constexpr float kDivSqrt2MinAbs = 0x1p-103f;
+constexpr float kDivLog256MinAbs = 0x1p-106f;
+
+// x * SCALE / 32767.0 with SCALE a power of two folded into the constants (SCALE = 0.5: the stereo down-mix
+// (float)sum / 2.0f / 32767.0 in one go; scaling by two is exact, so every rounding happens at the same place)
+template <int HALVE>
+__device__ __forceinline__ float div32767_f32(float x) {
+  const float y = HALVE ? 0.5f * kInv32767f : kInv32767f;
+  const float h = HALVE ? 2.0f * 32767.0f : 32767.0f;
+  const float q0 = __fmul_rn(x, y);
+  const float r = __fmaf_rn(-h, q0, x);
+  return __fmaf_rn(r, y, q0);
+}
+__device__ __forceinline__ float div_sqrt2_f32(float x) {
+  const float q0 = __fmul_rn(x, kInvSqrt2f);
+  const float r = __fmaf_rn(-kSqrt2Lo, q0, __fmaf_rn(-kSqrt2Hi, q0, x));
+  return __fmaf_rn(r, kInvSqrt2f, q0);
+}
+// x / c for an f32 constant c with y = RN32(1 / c)
+__device__ __forceinline__ float div_f32_recip(float x, float c, float y) {
+  const float q0 = __fmul_rn(x, y);
+  const float r = __fmaf_rn(-c, q0, x);
+  return __fmaf_rn(r, y, q0);
+}
 
 // index of the last prefix[] entry <= v (prefix has n+1 ascending entries, prefix[0] == 0)
 template <typename T>

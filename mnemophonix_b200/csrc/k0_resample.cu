@@ -3,7 +3,7 @@
 // Replaces the downmix loop of read_samples (wav.c:358-375) and resample (resample.c:38-62).
 // One CTA produces kTileOut consecutive 5512 Hz samples of one track: it stages the
 // 8*kTileOut + 23 PCM frames it needs with 128-bit loads, down-mixes them into shared memory
-// once (int sum -> f32 divide by the channel count -> f64 divide by 32767 -> f32), then every
+// once (int sum -> f32 divide by the channel count -> divide by 32767 as the reference's f64 division rounds it), then every
 // thread produces 4 consecutive outputs from 55 samples held in registers, running the
 // reference's sequential mul-then-add tap loop for each (4 independent chains).
 // Shared memory is padded by one word per 32 so that both the staging stores and the
@@ -26,13 +26,20 @@ __constant__ float c_taps[kTaps];
 void k0_upload_constants(const Tables& t) { cudaMemcpyToSymbol(c_taps, t.taps, sizeof(float) * kTaps); }
 
 // wav.c:364-374: int sum; (float)sum / (float)channels in f32; then / 32767.0 in f64, back to f32.
+// The f64 division is done in FP32 (div32767_f32, exact for every float, common.cuh); for two channels the
+// exact halving is folded into it.
 template <int CH>
-__device__ __forceinline__ float downmix_value(int sum, float chf) {
-  float mean;
-  if (CH == 1) mean = (float)sum;                          // x / 1.0f
-  else if (CH == 2) mean = __fmul_rn((float)sum, 0.5f);    // x / 2.0f is exact, so is x * 0.5f
-  else mean = __fdiv_rn((float)sum, chf);
-  return div_const_f32(mean, 32767.0, kInv32767);          // exact reciprocal division, common.cuh
+__device__ __forceinline__ float downmix_value(float sum, float chf) {
+  if (CH == 1) return div32767_f32<0>(sum);              // x / 1.0f
+  if (CH == 2) return div32767_f32<1>(sum);              // x / 2.0f is exact
+  return div32767_f32<0>(__fdiv_rn(sum, chf));
+}
+// (float)(a.lo * b0 + a.hi * b1) for the two int16 halves of a word and byte weights b (0 or 1), without an
+// I2F: the dot product lands on the mantissa of 1.5 * 2^23 and a float subtraction removes the bias (exact,
+// |sum| <= 2^16).
+constexpr int kMagicBits = 0x4B400000;                   // 12582912.0f
+__device__ __forceinline__ float pick_sum(int w, int weights) {
+  return __fsub_rn(__int_as_float(__dp2a_lo(w, weights, kMagicBits)), 12582912.0f);
 }
 
 // INTERIOR: the whole tile lies inside the track, no per-frame bounds checks
@@ -50,7 +57,7 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ mono, const Track
       const int w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int lo = (int)(int16_t)(w[k] & 0xffff), hi = w[k] >> 16;
+        const float lo = pick_sum(w[k], 0x0001), hi = pick_sum(w[k], 0x0100);
         const int idx = i * 8 + 2 * k;
         if (idx < kTileIn) mono[pad32(idx)] = (INTERIOR || f + 2 * k < tr.n_pcm) ? downmix_value<1>(lo, 1.0f) : 0.0f;
         if (idx + 1 < kTileIn)
@@ -66,7 +73,7 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ mono, const Track
       const int w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int sum = (int)(int16_t)(w[k] & 0xffff) + (w[k] >> 16);
+        const float sum = pick_sum(w[k], 0x0101);
         const int idx = i * 4 + k;
         if (idx < kTileIn) mono[pad32(idx)] = (INTERIOR || f + k < tr.n_pcm) ? downmix_value<2>(sum, 2.0f) : 0.0f;
       }
@@ -80,7 +87,7 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ mono, const Track
       if (INTERIOR || f < tr.n_pcm) {
         int sum = 0;
         for (uint32_t c = 0; c < ch; ++c) sum += pcm[f * ch + c];
-        m = downmix_value<0>(sum, chf);
+        m = downmix_value<0>((float)sum, chf);
       }
       mono[pad32(i)] = m;
     }

@@ -26,11 +26,21 @@ namespace mnemo {
 constexpr int kK2Threads = 256;
 constexpr int kBStride = 33;
 
-// haar.c:35-36: (float)((double)(a +/- b) / M_SQRT2); exact division by reciprocal (common.cuh)
-__device__ __forceinline__ float haar_lo(float a, float b) {
+// haar.c:35-36: (float)((double)(a +/- b) / M_SQRT2).
+// Two exact forms (common.cuh): haar_*64 divides in double by reciprocal and is exact for every float;
+// haar_*  stays in FP32 (no conversions, no FP64) and is exact whenever the dividend is 0 or at least 2^-103
+// in magnitude.  Where that is guaranteed:
+//   pixels are 0 or >= logf(1 + 2^-23) / logf(256) > 2^-26, so every value of the time transform is a sum of
+//   non-negative terms (a low: 0 or >= 2^-30, a multiple of 2^-53) or a difference of two lows (0 or >= 2^-53);
+//   its outputs are 0 or >= 2^-54, i.e. multiples of 2^-77.  Band level 1 therefore divides 0 or >= 2^-77 and
+//   yields multiples of 2^-101; band level 2 divides 0 or >= 2^-101.  From band level 3 on a (wildly
+//   adversarial) chain of cancellations could go below 2^-103, so those 3.5 of 15.5 steps keep the double form.
+__device__ __forceinline__ float haar_lo(float a, float b) { return div_sqrt2_f32(__fadd_rn(a, b)); }
+__device__ __forceinline__ float haar_hi(float a, float b) { return div_sqrt2_f32(__fsub_rn(a, b)); }
+__device__ __forceinline__ float haar_lo64(float a, float b) {
   return div_const_f32(__fadd_rn(a, b), kSqrt2, kInvSqrt2);
 }
-__device__ __forceinline__ float haar_hi(float a, float b) {
+__device__ __forceinline__ float haar_hi64(float a, float b) {
   return div_const_f32(__fsub_rn(a, b), kSqrt2, kInvSqrt2);
 }
 
@@ -77,11 +87,13 @@ __device__ __forceinline__ void hist_add(uint32_t* __restrict__ hist, uint32_t d
 // code and 40 resident warps sit in different phases of it; sharing this body (called 16 times per
 // thread) keeps the instruction working set smaller (stall_no_instruction was 18 % of the samples).
 template <int LOGF_VARIANT>
-__device__ __noinline__ float scale_pixel(float v, double dmx, double rmx, float log256, const double* invc,
-                                          const double* logc) {
+__device__ __noinline__ float scale_pixel(float v, double dmx, double rmx, float log256, float inv_log256,
+                                          const double* invc, const double* logc) {
   float sc = __double2float_rn(div_markstein2(__dmul_rn(255.0, (double)v), dmx, rmx));   // spectralimages.c:53
   if (sc > 255.0f) sc = 255.0f;
-  return __fdiv_rn(logf_glibc<LOGF_VARIANT>(__fadd_rn(1.0f, sc), invc, logc, 1), log256);   // spectralimages.c:57
+  // spectralimages.c:57: an f32 division by logf(256.0f); the dividend is 0 or >= logf(1 + 2^-23) = 1.19e-7,
+  // inside the domain where the reciprocal form is exact (common.cuh, mnemo_selftest_div which = 4)
+  return div_f32_recip(logf_glibc<LOGF_VARIANT>(__fadd_rn(1.0f, sc), invc, logc, 1), log256, inv_log256);
 }
 
 template <int LOGF_VARIANT>
@@ -140,9 +152,9 @@ __global__ void __launch_bounds__(kK2Threads, 5)
   }
   const double dmx = (double)mx;
   const double rmx = __drcp_rn(dmx);
-  const float log256 = tab->log256;
+  const float log256 = tab->log256, inv_log256 = tab->inv_log256;
 #pragma unroll
-  for (int u = 0; u < 16; ++u) v[u] = scale_pixel<LOGF_VARIANT>(v[u], dmx, rmx, log256, s_invc, s_logc);
+  for (int u = 0; u < 16; ++u) v[u] = scale_pixel<LOGF_VARIANT>(v[u], dmx, rmx, log256, inv_log256, s_invc, s_logc);
   if (tap_img) {
 #pragma unroll
     for (int u = 0; u < 16; ++u) tap_img[img * kImgElems + (16 * warp + u) * kBands + lane] = v[u];
@@ -210,15 +222,15 @@ __global__ void __launch_bounds__(kK2Threads, 5)
       r[8 + 4 * half + i] = haar_hi(l1[2 * i], l1[2 * i + 1]);
     }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      l3[i] = haar_lo(l2[2 * i], l2[2 * i + 1]);
-      r[4 + 2 * half + i] = haar_hi(l2[2 * i], l2[2 * i + 1]);
+    for (int i = 0; i < 2; ++i) {   // band levels 3..5: double form (see haar_lo64)
+      l3[i] = haar_lo64(l2[2 * i], l2[2 * i + 1]);
+      r[4 + 2 * half + i] = haar_hi64(l2[2 * i], l2[2 * i + 1]);
     }
-    const float l4 = haar_lo(l3[0], l3[1]);
-    r[2 + half] = haar_hi(l3[0], l3[1]);
+    const float l4 = haar_lo64(l3[0], l3[1]);
+    r[2 + half] = haar_hi64(l3[0], l3[1]);
     const float other = __shfl_xor_sync(0xffffffffu, l4, 1);
     const float a = half ? other : l4, b = half ? l4 : other;
-    r[half] = half ? haar_hi(a, b) : haar_lo(a, b);
+    r[half] = half ? haar_hi64(a, b) : haar_lo64(a, b);
     __syncwarp();
 #pragma unroll
     for (int e = 0; e < 16; ++e) c[e] = r[16 * half + e];   // final coefficients 16*tid .. 16*tid+15
@@ -475,19 +487,40 @@ __global__ void logf_range_kernel(uint32_t lo_bits, uint32_t n, int variant, flo
 }
 
 // ---- device self-test of the reciprocal divisions against IEEE division ----
-// which 0: x / M_SQRT2, 1: x / 32767.0 for every float x = bits lo..lo+n-1 (one-step Markstein);
-// which 2: (255*v) / max for pseudo-random float pairs 0 <= v <= max (two-step Markstein).
+// For every float x = bits lo..lo+n-1:
+//   which 0: x / M_SQRT2 in double by reciprocal (one-step Markstein)        vs (float)((double)x / M_SQRT2)
+//   which 1: x / 32767.0 in FP32 (div32767_f32, also the halving form)       vs (float)((double)x / 32767.0)
+//   which 3: x / M_SQRT2 in FP32 (div_sqrt2_f32), x == 0 or |x| >= 2^-103    vs (float)((double)x / M_SQRT2)
+//   which 4: x / c in FP32 (div_f32_recip), x == 0 or |x| >= 2^-106          vs x / c in IEEE f32, c = logf(256.0f)
+// which 2: (255*v) / max for pseudo-random float pairs 0 <= v <= max (two-step Markstein, double results).
 __global__ void div_test_kernel(int which, uint32_t lo_bits, uint64_t n, unsigned long long* __restrict__ bad, float c,
                                 float rc) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double got, want;
-  if (which < 2) {
+  if (which != 2) {
     const float x = __uint_as_float((uint32_t)(lo_bits + i));
     if (!(fabsf(x) <= 3.0e38f) || __float_as_uint(x) == 0x80000000u) return;   // NaN / inf / -0 never reach the division
-    const double b = which == 0 ? kSqrt2 : 32767.0, y = which == 0 ? kInvSqrt2 : kInv32767;
-    const float g = div_const_f32(x, b, y);
-    const float w = __double2float_rn(__ddiv_rn((double)x, b));
+    float g, w;
+    if (which == 0) {
+      g = div_const_f32(x, kSqrt2, kInvSqrt2);
+      w = __double2float_rn(__ddiv_rn((double)x, kSqrt2));
+    } else if (which == 1) {
+      g = div32767_f32<0>(x);
+      w = __double2float_rn(__ddiv_rn((double)x, 32767.0));
+      // the stereo form takes the sum before halving; (float)sum * 0.5f is exact unless it underflows
+      const float g2 = div32767_f32<1>(x);
+      const float w2 = __double2float_rn(__ddiv_rn((double)__fmul_rn(x, 0.5f), 32767.0));
+      if (fabsf(x) >= 0x1p-100f && __float_as_uint(g2) != __float_as_uint(w2)) g = __uint_as_float(~__float_as_uint(w));
+    } else if (which == 3) {
+      if (x != 0.0f && fabsf(x) < kDivSqrt2MinAbs) return;
+      g = div_sqrt2_f32(x);
+      w = __double2float_rn(__ddiv_rn((double)x, kSqrt2));
+    } else {
+      if (x != 0.0f && fabsf(x) < kDivLog256MinAbs) return;
+      g = div_f32_recip(x, c, rc);
+      w = __fdiv_rn(x, c);
+    }
     if (__float_as_uint(g) != __float_as_uint(w)) {
       atomicAdd(bad, 1ull);
       atomicMin(bad + 1, (unsigned long long)(uint32_t)(lo_bits + i));

@@ -154,9 +154,14 @@ def test_device_logf_equals_host_libm_on_its_whole_domain(ctx):
 
 
 def test_reciprocal_divisions_equal_ieee_division(ctx):
-    # x / M_SQRT2 (haar.c:35-36) and x / 32767.0 (wav.c:373): every one of the 2^32 float dividends
+    # x / M_SQRT2 (haar.c:35-36) in double by reciprocal and x / 32767.0 (wav.c:373) in FP32: every one of
+    # the 2^32 float dividends
     assert ctx.selftest_div(0, 0, 1 << 32) == 0
     assert ctx.selftest_div(1, 0, 1 << 32) == 0
+    # the FP32 forms of x / M_SQRT2 and x / logf(256.0f) (spectralimages.c:57): every float of their domains
+    # (0 or |x| >= 2^-103 resp. 2^-106; k2_fingerprint.cu shows the kernels stay inside)
+    assert ctx.selftest_div(3, 0, 1 << 32) == 0
+    assert ctx.selftest_div(4, 0, 1 << 32) == 0
     # (255*v) / max (spectralimages.c:53): 2^28 pseudo-random (v, max) pairs, double results bit-equal
     assert ctx.selftest_div(2, 12345, 1 << 28) == 0
 

@@ -18,15 +18,17 @@ ctx = capi.Context(0, st.cuda_stream)
 pin = torch.from_numpy(pcm).pin_memory()
 b = ctx.batch([(pin.data_ptr(), pcm.shape[0], ch)])
 t = time.time(); b.upload(); b.sync(); print("upload s", time.time() - t, "GB/s", pcm.nbytes / 1e9 / (time.time() - t))
-for _ in range(2):
+for _ in range(3):
     b.run()
 b.sync()
-ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-ev[0].record(st)
+b.set_timing(True)
+t = time.perf_counter()
 for i in range(steps):
-    b.run(); ev[i + 1].record(st)
-torch.cuda.synchronize()
-ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    b.run()
+b.sync()
+ms = (time.perf_counter() - t) * 1e3 / steps
+stage, n = b.get_timing()
 hours = secs / 3600.0
-print("ms/run", ms, "audio-h/s", hours / (np.mean(ms) / 1e3), "launches", b.launches())
+print("ms/run (host clock, back to back)", ms, "stage ms", stage, "sum", sum(stage.values()), "audio-h/s",
+      hours / (sum(stage.values()) / 1e3), "launches", b.launches())
 out, n, stt = b.download(); print("n_sigs", n, stt)
