@@ -219,16 +219,17 @@ extern "C" int mnemo_create(int device, void* stream, mnemo_ctx** out) {
     return rc;
   }
   // inverse of the permutation table (permutations.c:7-1808): inv[b][p] = j with perm[p][j] == b, else 255
-  std::vector<uint8_t> inv((size_t)8192 * kSigLen, 255);
+  // (16-bit entries: the kernel takes minima with the two-lane 16-bit SIMD instruction)
+  std::vector<uint16_t> inv((size_t)8192 * kSigLen, 255);
   for (int p = 0; p < kSigLen; p++)
-    for (int j = kPermLen - 1; j >= 0; j--) inv[(size_t)k_permutations[p * kPermLen + j] * kSigLen + p] = (uint8_t)j;
+    for (int j = kPermLen - 1; j >= 0; j--) inv[(size_t)k_permutations[p * kPermLen + j] * kSigLen + p] = (uint16_t)j;
   if (cudaMalloc(&ctx->d_tables, sizeof(Tables)) != cudaSuccess ||
-      cudaMalloc(&ctx->d_inv_perms, inv.size()) != cudaSuccess) {
+      cudaMalloc(&ctx->d_inv_perms, inv.size() * sizeof(uint16_t)) != cudaSuccess) {
     mnemo_destroy(ctx);
     return -1;
   }
   cudaMemcpy(ctx->d_tables, &ctx->h_tables, sizeof(Tables), cudaMemcpyHostToDevice);
-  cudaMemcpy(ctx->d_inv_perms, inv.data(), inv.size(), cudaMemcpyHostToDevice);
+  cudaMemcpy(ctx->d_inv_perms, inv.data(), inv.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
   k1_upload_constants(ctx->h_tables);
   k0_upload_constants(ctx->h_tables);
   e = cudaDeviceSynchronize();

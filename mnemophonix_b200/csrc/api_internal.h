@@ -12,7 +12,7 @@ struct mnemo_ctx {
   bool own_stream = false;
   mnemo::Tables h_tables;
   mnemo::Tables* d_tables = nullptr;
-  uint8_t* d_inv_perms = nullptr;   // [8192][100]: position of bit b in permutation p (255 = not among the first 255)
+  uint16_t* d_inv_perms = nullptr;  // [8192][100]: position of bit b in permutation p (255 = not among the first 255)
   uint32_t logf_probes = 0, logf_matched = 0;
   std::string err;
 };

@@ -73,7 +73,7 @@ void launch_normalize(const TrackDev* tracks, const uint32_t* chunk_track, uint6
 void launch_k1_spectral(const TrackDev* tracks, const uint32_t* tile_prefix, uint32_t n_tracks, uint32_t n_tiles,
                         const Tables* tab, const float* snorm, float* bins, int sm_count, cudaStream_t st);
 void launch_k2_fingerprint(const TrackDev* tracks, const uint64_t* img_prefix, uint32_t n_tracks, uint64_t n_images,
-                           const Tables* tab, const uint8_t* inv_perms, const float* bins, uint8_t* sig_dense,
+                           const Tables* tab, const uint16_t* inv_perms, const float* bins, uint8_t* sig_dense,
                            uint8_t* keep, uint8_t* tap_raw, float* tap_img, float* tap_haar, int logf_variant,
                            cudaStream_t st);
 void launch_compact(const uint8_t* sig_dense, const uint8_t* keep, uint64_t n_images, const uint64_t* img_prefix,

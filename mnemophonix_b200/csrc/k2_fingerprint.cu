@@ -18,7 +18,7 @@
 //   6. each thread owns 16 consecutive coefficients = exactly one 32-bit word of the
 //      fingerprint: bits are assembled without atomics
 //   7. MinHash inside out: each set bit contributes its position in every permutation (inverse table,
-//      25 words per bit), signature = byte-wise minimum (__vminu4)
+//      100 x u16 per bit), signature = element-wise minimum (VIMNMX3.U16x2)
 #include "common.cuh"
 
 namespace mnemo {
@@ -83,12 +83,10 @@ __device__ __forceinline__ void hist_add(uint32_t* __restrict__ hist, uint32_t d
   if (d != 0xFFFFFFFFu && lane == __ffs(peers) - 1) atomicAdd(&hist[d], (uint32_t)__popc(peers));
 }
 
-// spectralimages.c:52-58 for one pixel.  Deliberately NOT inlined: the kernel is ~70 KB of straight-line
-// code and 40 resident warps sit in different phases of it; sharing this body (called 16 times per
-// thread) keeps the instruction working set smaller (stall_no_instruction was 18 % of the samples).
+// spectralimages.c:52-58 for one pixel
 template <int LOGF_VARIANT>
-__device__ __noinline__ float scale_pixel(float v, double dmx, double rmx, float log256, float inv_log256,
-                                          const double* invc, const double* logc) {
+__device__ __forceinline__ float scale_pixel(float v, double dmx, double rmx, float log256, float inv_log256,
+                                             const double* invc, const double* logc) {
   float sc = __double2float_rn(div_markstein2(__dmul_rn(255.0, (double)v), dmx, rmx));   // spectralimages.c:53
   if (sc > 255.0f) sc = 255.0f;
   // spectralimages.c:57: an f32 division by logf(256.0f); the dividend is 0 or >= logf(1 + 2^-23) = 1.19e-7,
@@ -96,16 +94,19 @@ __device__ __noinline__ float scale_pixel(float v, double dmx, double rmx, float
   return div_f32_recip(logf_glibc<LOGF_VARIANT>(__fadd_rn(1.0f, sc), invc, logc, 1), log256, inv_log256);
 }
 
+// 16-bit two-lane minimum of three (one VIMNMX3.U16x2)
+__device__ __forceinline__ uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
+
 template <int LOGF_VARIANT>
 __global__ void __launch_bounds__(kK2Threads, 5)
     k2_fingerprint_kernel(const TrackDev* __restrict__ tracks, const uint64_t* __restrict__ img_prefix,
-                          uint32_t n_tracks, const Tables* __restrict__ tab, const uint8_t* __restrict__ inv,
+                          uint32_t n_tracks, const Tables* __restrict__ tab, const uint16_t* __restrict__ inv,
                           const float* __restrict__ bins, uint8_t* __restrict__ sig_dense, uint8_t* __restrict__ keep,
                           uint8_t* __restrict__ tap_raw, float* __restrict__ tap_img, float* __restrict__ tap_haar) {
   __shared__ float B[kImgW * kBStride];
   __shared__ float lows[8][kBands];
   __shared__ uint16_t s_list[256];          // positions of the set bits (<= 200)
-  __shared__ uint32_t s_part[8][32];        // per-warp partial MinHash minima
+  __shared__ uint2 s_part[8][32];           // per-warp partial MinHash minima
   __shared__ uint32_t hist[256];
   __shared__ uint32_t list_b[kImgElems];
   __shared__ uint32_t s_sel[3], s_count[2];
@@ -153,33 +154,40 @@ __global__ void __launch_bounds__(kK2Threads, 5)
   const double dmx = (double)mx;
   const double rmx = __drcp_rn(dmx);
   const float log256 = tab->log256, inv_log256 = tab->inv_log256;
-#pragma unroll
-  for (int u = 0; u < 16; ++u) v[u] = scale_pixel<LOGF_VARIANT>(v[u], dmx, rmx, log256, inv_log256, s_invc, s_logc);
-  if (tap_img) {
-#pragma unroll
-    for (int u = 0; u < 16; ++u) tap_img[img * kImgElems + (16 * warp + u) * kBands + lane] = v[u];
-  }
-
-  // 3. Haar along time (haar.c:56-67): row = band `lane`, this thread holds t in [16*warp, 16*warp+16)
+  // 2.+3. scale, then Haar along time (haar.c:56-67): row = band `lane`, this thread holds t in [16*warp,
+  // 16*warp+16).  The pixel body (two double-precision divisions' worth of code) is instantiated kPxUnroll times
+  // inside a rolled loop: fully unrolled the kernel outgrows the 32 KB instruction cache and 40 resident warps
+  // in different phases starve on instruction fetch; as a called function the per-call register shuffling and
+  // constant reloads cost a tenth of the kernel's instructions.
   {
-    float l1[8], l2[4], l3[2];
+    constexpr int kPxUnroll = 4;
+    float l2v[4];
+#pragma unroll 1
+    for (int it = 0; it < 16 / kPxUnroll; ++it) {
+      float p[kPxUnroll];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      l1[i] = haar_lo(v[2 * i], v[2 * i + 1]);
-      B[(64 + 8 * warp + i) * kBStride + lane] = haar_hi(v[2 * i], v[2 * i + 1]);
-    }
+      for (int u = 0; u < kPxUnroll; ++u) p[u] = scale_pixel<LOGF_VARIANT>(v[u], dmx, rmx, log256, inv_log256, s_invc, s_logc);
+      if (tap_img) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      l2[i] = haar_lo(l1[2 * i], l1[2 * i + 1]);
-      B[(32 + 4 * warp + i) * kBStride + lane] = haar_hi(l1[2 * i], l1[2 * i + 1]);
-    }
+        for (int u = 0; u < kPxUnroll; ++u) tap_img[img * kImgElems + (16 * warp + kPxUnroll * it + u) * kBands + lane] = p[u];
+      }
+      const float a = haar_lo(p[0], p[1]), b = haar_lo(p[2], p[3]);
+      B[(64 + 8 * warp + 2 * it) * kBStride + lane] = haar_hi(p[0], p[1]);
+      B[(64 + 8 * warp + 2 * it + 1) * kBStride + lane] = haar_hi(p[2], p[3]);
+      B[(32 + 4 * warp + it) * kBStride + lane] = haar_hi(a, b);
+      const float l2 = haar_lo(a, b);
+      // rotate the register arrays instead of indexing them with the loop counter
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      l3[i] = haar_lo(l2[2 * i], l2[2 * i + 1]);
-      B[(16 + 2 * warp + i) * kBStride + lane] = haar_hi(l2[2 * i], l2[2 * i + 1]);
+      for (int u = 0; u + kPxUnroll < 16; ++u) v[u] = v[u + kPxUnroll];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) l2v[u] = l2v[u + 1];
+      l2v[3] = l2;
     }
-    lows[warp][lane] = haar_lo(l3[0], l3[1]);
-    B[(8 + warp) * kBStride + lane] = haar_hi(l3[0], l3[1]);
+    const float l3a = haar_lo(l2v[0], l2v[1]), l3b = haar_lo(l2v[2], l2v[3]);
+    B[(16 + 2 * warp) * kBStride + lane] = haar_hi(l2v[0], l2v[1]);
+    B[(16 + 2 * warp + 1) * kBStride + lane] = haar_hi(l2v[2], l2v[3]);
+    lows[warp][lane] = haar_lo(l3a, l3b);
+    B[(8 + warp) * kBStride + lane] = haar_hi(l3a, l3b);
   }
   __syncthreads();
   if (warp == 0) {
@@ -388,20 +396,37 @@ __global__ void __launch_bounds__(kK2Threads, 5)
     __syncthreads();   // red[] is reused below
   }
 
-  // 6. tri-state bits (rawfingerprints.c:61-74); thread tid owns word tid of the 8192-bit array
+  // 6. tri-state bits (rawfingerprints.c:61-74); thread tid owns word tid of the 8192-bit array.
+  // The reference compares (double)c with 0.001, -0.001 and 1.0.  0.001 lies strictly between two adjacent
+  // floats, 0x3A83126E < 0.001 < 0x3A83126F = 0.001f, so (double)c > 0.001 <=> c >= 0.001f, and on the
+  // magnitude bits that is an integer comparison; likewise |c| > 1.0 <=> key > 0x3F800000.  A selected
+  // element (key >= thr) sets a bit iff key >= max(thr, bits(0.001f)): positive c by a signed comparison of
+  // the float's bits, negative c by an unsigned one with the sign bit set.
+  constexpr uint32_t kEpsBits = 0x3A83126Fu, kOneBits = 0x3F800000u;
   uint32_t word = 0, strong = 0;
+  if (n_eq == want) {   // block-uniform, the usual case: every element equal to the threshold is selected
+    const uint32_t t_bit = max(thr, kEpsBits), t_strong = max(thr, kOneBits + 1u);
+    const int t_pos = (int)t_bit;
+    const uint32_t t_neg = t_bit | 0x80000000u;
 #pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    bool sel = key[e] > thr;
-    if (key[e] == thr) {
-      sel = eq_before < want;
-      ++eq_before;
+    for (int e = 0; e < 16; ++e) {
+      const uint32_t cb = __float_as_uint(c[e]);
+      if ((int)cb >= t_pos) word |= 1u << (2 * e);
+      if (cb >= t_neg) word |= 1u << (2 * e + 1);
+      if (key[e] >= t_strong) ++strong;
     }
-    if (sel) {
-      const double cd = (double)c[e];
-      if (cd > 0.001) word |= 1u << (2 * e);
-      else if (cd < -0.001) word |= 1u << (2 * e + 1);
-      strong += (double)fabsf(c[e]) > 1.0;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      bool sel = key[e] > thr;
+      if (key[e] == thr) {
+        sel = eq_before < want;
+        ++eq_before;
+      }
+      if (sel) {
+        if (key[e] >= kEpsBits) word |= 1u << (2 * e + (__float_as_uint(c[e]) >> 31));
+        strong += key[e] > kOneBits;
+      }
     }
   }
   // running count of set bits (warp scan now, cross-warp after the barrier): their positions feed MinHash
@@ -426,8 +451,9 @@ __global__ void __launch_bounds__(kK2Threads, 5)
   // 7. MinHash (minhash.c:13-28), turned inside out: instead of walking each of the 100 permutations until
   // it meets a set bit, every set bit b (at most 200) contributes its position in each permutation,
   // inv[b][p] (255 if b is not among the first 255 entries of permutation p), and the signature is the
-  // byte-wise minimum.  Row b of the inverse table is 100 bytes = 25 words: 25 lanes take 4 permutations each
-  // (__vminu4), the 8 warps split the set bits, and a last step combines the 8 partial minima.
+  // element-wise minimum.  Row b of the inverse table is 100 x u16 = 25 x 8 bytes: 25 lanes take 4 permutations
+  // each (two-lane 16-bit SIMD minima; sm_100 has no native 4 x 8-bit minimum), the 8 warps split the set
+  // bits, and a last step combines the 8 partial minima.
   {
     uint32_t off = nbits_incl - nbits_mine, n_bits = 0;
 #pragma unroll
@@ -441,23 +467,33 @@ __global__ void __launch_bounds__(kK2Threads, 5)
       rest &= rest - 1;
     }
     __syncthreads();
-    uint32_t m = 0xFFFFFFFFu;
+    uint32_t m0 = 0xFFFFFFFFu, m1 = 0xFFFFFFFFu;   // permutations 4*lane, 4*lane+1 | 4*lane+2, 4*lane+3
     if (lane < 25) {
-      const uint32_t* __restrict__ inv32 = reinterpret_cast<const uint32_t*>(inv) + lane;
+      const uint2* __restrict__ inv64 = reinterpret_cast<const uint2*>(inv) + lane;   // rows of 200 bytes = 25 x 8
       uint32_t i = warp;
       for (; i + 24 < n_bits; i += 32) {   // 4 independent loads in flight
-        const uint32_t a0 = __ldg(inv32 + 25u * s_list[i]), a1 = __ldg(inv32 + 25u * s_list[i + 8]);
-        const uint32_t a2 = __ldg(inv32 + 25u * s_list[i + 16]), a3 = __ldg(inv32 + 25u * s_list[i + 24]);
-        m = __vminu4(m, __vminu4(__vminu4(a0, a1), __vminu4(a2, a3)));
+        const uint2 a0 = __ldg(inv64 + 25u * s_list[i]), a1 = __ldg(inv64 + 25u * s_list[i + 8]);
+        const uint2 a2 = __ldg(inv64 + 25u * s_list[i + 16]), a3 = __ldg(inv64 + 25u * s_list[i + 24]);
+        m0 = min3_u16x2(min3_u16x2(m0, a0.x, a1.x), a2.x, a3.x);
+        m1 = min3_u16x2(min3_u16x2(m1, a0.y, a1.y), a2.y, a3.y);
       }
-      for (; i < n_bits; i += 8) m = __vminu4(m, __ldg(inv32 + 25u * s_list[i]));
+      for (; i < n_bits; i += 8) {
+        const uint2 a = __ldg(inv64 + 25u * s_list[i]);
+        m0 = min3_u16x2(m0, a.x, a.x);
+        m1 = min3_u16x2(m1, a.y, a.y);
+      }
     }
-    s_part[warp][lane] = m;
+    s_part[warp][lane] = make_uint2(m0, m1);
     __syncthreads();
     if (tid < 32) {
-      uint32_t r = 0xFFFFFFFFu;
+      uint32_t r0 = 0xFFFFFFFFu, r1 = 0xFFFFFFFFu;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) r = __vminu4(r, s_part[w][tid]);
+      for (int w = 0; w < 8; w += 2) {
+        const uint2 x = s_part[w][tid], y = s_part[w + 1][tid];
+        r0 = min3_u16x2(r0, x.x, y.x);
+        r1 = min3_u16x2(r1, x.y, y.y);
+      }
+      const uint32_t r = __byte_perm(r0, r1, 0x6420);   // four values <= 255 -> four bytes
       if (tid < 25) reinterpret_cast<uint32_t*>(sig_dense + img * kSigLen)[tid] = r;
       const uint32_t any = __ballot_sync(0xffffffffu, tid < 25 && r != 0xFFFFFFFFu);
       if (tid == 0) keep[img] = any ? 1 : 0;   // minhash.c:45: dropped when all 100 values are 255
@@ -466,7 +502,7 @@ __global__ void __launch_bounds__(kK2Threads, 5)
 }
 
 void launch_k2_fingerprint(const TrackDev* tracks, const uint64_t* img_prefix, uint32_t n_tracks, uint64_t n_images,
-                           const Tables* tab, const uint8_t* inv, const float* bins, uint8_t* sig_dense,
+                           const Tables* tab, const uint16_t* inv, const float* bins, uint8_t* sig_dense,
                            uint8_t* keep, uint8_t* tap_raw, float* tap_img, float* tap_haar, int logf_variant,
                            cudaStream_t st) {
   if (n_images == 0) return;

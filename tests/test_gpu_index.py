@@ -137,6 +137,35 @@ def test_randomized_signals_channels_and_lengths(ctx, oracle):
         assert bits_equal(g, sigs)
 
 
+def tie_track(seed):
+    """PCM whose 5512 Hz samples repeat every 2048 samples (= 32 frames): the 128-frame image consists of 4
+    bit-identical repeats, so Haar coefficients come in groups of exactly equal magnitude and the 200th
+    largest falls inside such a group (asserted on the oracle's coefficients in the test)."""
+    rng = np.random.RandomState(seed)
+    P = 16384
+    t = np.arange(P)
+    env = np.where((t // 2048) % 4 == 0, 1.0, 0.03)
+    base = rng.standard_normal(P) * 6000 * env + 9000 * np.sin(2 * np.pi * t * (40 + (seed - 70) * 7) / P) * env[::-1]
+    return np.tile(np.clip(np.round(base), -32768, 32767).astype(np.int16), 12)[:, None]
+
+
+@pytest.mark.parametrize("seed", [70, 71])
+def test_ties_at_rank_200_go_to_the_lower_index(ctx, oracle, seed):
+    # rawfingerprints.c:90: qsort by |c|; glibc's merge sort is stable, so among equal magnitudes the lower
+    # index is selected.  Raw fingerprints (which coefficients got a bit) and signatures must be identical.
+    pcm = tie_track(seed)
+    b = run_with_taps(ctx, pcm)
+    norm, rms = oracle.normalize(oracle.resample(oracle.downmix(pcm)))
+    rc, sigs, taps = oracle.fingerprint_samples(norm, taps=True)
+    mags = np.sort(np.abs(taps["haar"]), axis=1)[:, ::-1]
+    assert (mags[:, 199] == mags[:, 200]).sum() >= 10                      # the fixture does straddle the cut
+    assert bits_equal(b.read(7, 0).reshape(-1, 4096), taps["haar"])
+    assert bits_equal(b.read(5, 0).reshape(-1, 1024), taps["raw"])
+    got, st = b.signatures()
+    assert st == [0] and len(sigs) > 0 and bits_equal(got[0], sigs)
+    b.close()
+
+
 def test_from_samples_entry_point(ctx, oracle):
     # generate_fingerprint_from_samples (fingerprinting.c:81-109): no resample, no normalisation
     rng = np.random.RandomState(9)
