@@ -102,22 +102,34 @@ static __device__ __constant__ double c_logf_tab[16][2] = {
     {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
     {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
 
-// invc_tab / logc_tab: the table split into two 16-entry double arrays (stride 1), e.g. in shared memory:
-// the index is data dependent, and 16 doubles span exactly the 32 banks, so a 64-bit read of either
-// array is conflict-free for any index pattern.  Defaults read the constant table (stride 2).
+// Polynomial coefficients and ln2 live in the constant bank so that the FP64 instructions take them as
+// operands (as immediates they cost two UMOVs each, re-materialised for every pixel).
+static __device__ __constant__ double c_logf_poly[4] = {-0x1.00ea348b88334p-2, 0x1.5575b0be00b6ap-2,
+                                                         -0x1.ffffef20a4123p-2, 0x1.62e42fefa39efp-1};   // A0 A1 A2 Ln2
+
+// tab_saddr: shared-window address of a copy of the table split into two 16-entry double arrays,
+// invc[16] followed by logc[16] (256 bytes, 128-byte aligned).  The index is data dependent, and 16 doubles
+// span exactly the 32 banks, so a 64-bit read of either array is conflict-free for any index pattern;
+// the two reads share one address computation.  tab_saddr == 0 reads the constant table instead.
+// glibc returns +0 for x == 1 through an early exit; the general path gives the same +0 (r = 0, k = 0,
+// logc[9] = 0), so there is no branch here (the exhaustive self-test covers x = 1).
 template <int VARIANT>
-__device__ __forceinline__ float logf_glibc(float x, const double* __restrict__ invc_tab = &c_logf_tab[0][0],
-                                            const double* __restrict__ logc_tab = &c_logf_tab[0][1], int stride = 2) {
-  const double ln2 = 0x1.62e42fefa39efp-1;
-  const double a0 = -0x1.00ea348b88334p-2, a1 = 0x1.5575b0be00b6ap-2, a2 = -0x1.ffffef20a4123p-2;
-  uint32_t ix = __float_as_uint(x);
-  if (ix == 0x3f800000u) return 0.0f;
-  uint32_t tmp = ix - 0x3f330000u;
-  int i = (tmp >> 19) & 15;
-  int k = (int)tmp >> 23;
-  uint32_t iz = ix - (tmp & 0xff800000u);
-  double z = (double)__uint_as_float(iz);
-  double invc = invc_tab[stride * i], logc = logc_tab[stride * i];
+__device__ __forceinline__ float logf_glibc(float x, uint32_t tab_saddr = 0) {
+  const double a0 = c_logf_poly[0], a1 = c_logf_poly[1], a2 = c_logf_poly[2], ln2 = c_logf_poly[3];
+  const uint32_t ix = __float_as_uint(x);
+  const uint32_t tmp = ix - 0x3f330000u;
+  const int k = (int)tmp >> 23;
+  const uint32_t iz = ix - (tmp & 0xff800000u);
+  const double z = (double)__uint_as_float(iz);
+  double invc, logc;
+  if (tab_saddr) {
+    const uint32_t a = tab_saddr + ((tmp >> 16) & 0x78u);   // 8 * ((tmp >> 19) & 15)
+    asm("ld.shared.f64 %0, [%2];\n\tld.shared.f64 %1, [%2+128];" : "=d"(invc), "=d"(logc) : "r"(a));
+  } else {
+    const int i = (tmp >> 19) & 15;
+    invc = c_logf_tab[i][0];
+    logc = c_logf_tab[i][1];
+  }
   if (VARIANT) {  // instruction order of the -mfma ifunc variant
     double y0 = __fma_rn((double)k, ln2, logc);
     double r = __fma_rn(z, invc, -1.0);

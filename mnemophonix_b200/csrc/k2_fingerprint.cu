@@ -86,12 +86,12 @@ __device__ __forceinline__ void hist_add(uint32_t* __restrict__ hist, uint32_t d
 // spectralimages.c:52-58 for one pixel
 template <int LOGF_VARIANT>
 __device__ __forceinline__ float scale_pixel(float v, double dmx, double rmx, float log256, float inv_log256,
-                                             const double* invc, const double* logc) {
+                                             uint32_t logtab_saddr) {
   float sc = __double2float_rn(div_markstein2(__dmul_rn(255.0, (double)v), dmx, rmx));   // spectralimages.c:53
   if (sc > 255.0f) sc = 255.0f;
   // spectralimages.c:57: an f32 division by logf(256.0f); the dividend is 0 or >= logf(1 + 2^-23) = 1.19e-7,
   // inside the domain where the reciprocal form is exact (common.cuh, mnemo_selftest_div which = 4)
-  return div_f32_recip(logf_glibc<LOGF_VARIANT>(__fadd_rn(1.0f, sc), invc, logc, 1), log256, inv_log256);
+  return div_f32_recip(logf_glibc<LOGF_VARIANT>(__fadd_rn(1.0f, sc), logtab_saddr), log256, inv_log256);
 }
 
 // 16-bit two-lane minimum of three (one VIMNMX3.U16x2)
@@ -112,8 +112,7 @@ __global__ void __launch_bounds__(kK2Threads, 5)
   __shared__ uint32_t s_sel[3], s_count[2];
   __shared__ uint32_t red[8];
   __shared__ uint32_t s_strong;
-  __shared__ __align__(128) double s_invc[16];
-  __shared__ __align__(128) double s_logc[16];
+  __shared__ __align__(128) double s_logtab[32];   // invc[16] | logc[16]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t img = blockIdx.x;
@@ -123,10 +122,8 @@ __global__ void __launch_bounds__(kK2Threads, 5)
   const float* __restrict__ src = bins + (tr.frame_off + j * kImgStep) * kBands;
 
   if (tid == 0) s_strong = 0;
-  if (tid < 16) {
-    s_invc[tid] = c_logf_tab[tid][0];
-    s_logc[tid] = c_logf_tab[tid][1];
-  }
+  if (tid < 32) s_logtab[tid] = c_logf_tab[tid & 15][tid >> 4];
+  const uint32_t logtab_saddr = (uint32_t)__cvta_generic_to_shared(s_logtab);
 
   // 1. load: element (time = 16*warp + u, band = lane)
   float v[16];
@@ -166,7 +163,7 @@ __global__ void __launch_bounds__(kK2Threads, 5)
     for (int it = 0; it < 16 / kPxUnroll; ++it) {
       float p[kPxUnroll];
 #pragma unroll
-      for (int u = 0; u < kPxUnroll; ++u) p[u] = scale_pixel<LOGF_VARIANT>(v[u], dmx, rmx, log256, inv_log256, s_invc, s_logc);
+      for (int u = 0; u < kPxUnroll; ++u) p[u] = scale_pixel<LOGF_VARIANT>(v[u], dmx, rmx, log256, inv_log256, logtab_saddr);
       if (tap_img) {
 #pragma unroll
         for (int u = 0; u < kPxUnroll; ++u) tap_img[img * kImgElems + (16 * warp + kPxUnroll * it + u) * kBands + lane] = p[u];
@@ -516,10 +513,14 @@ void launch_k2_fingerprint(const TrackDev* tracks, const uint64_t* img_prefix, u
 
 // ---- device self-test of the logf mirror: compare against host values for a bit range ----
 __global__ void logf_range_kernel(uint32_t lo_bits, uint32_t n, int variant, float* __restrict__ out) {
+  __shared__ __align__(128) double s_logtab[32];   // same shared-memory table path as the fingerprint kernel
+  if (threadIdx.x < 32) s_logtab[threadIdx.x] = c_logf_tab[threadIdx.x & 15][threadIdx.x >> 4];
+  __syncthreads();
+  const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(s_logtab);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float x = __uint_as_float(lo_bits + i);
-  out[i] = variant ? logf_glibc<1>(x) : logf_glibc<0>(x);
+  out[i] = variant ? logf_glibc<1>(x, saddr) : logf_glibc<0>(x, saddr);
 }
 
 // ---- device self-test of the reciprocal divisions against IEEE division ----
