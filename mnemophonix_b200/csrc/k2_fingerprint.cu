@@ -37,6 +37,10 @@ constexpr int kBStride = 33;
 //   adversarial) chain of cancellations could go below 2^-103, so those 3.5 of 15.5 steps keep the double form.
 __device__ __forceinline__ float haar_lo(float a, float b) { return div_sqrt2_f32(__fadd_rn(a, b)); }
 __device__ __forceinline__ float haar_hi(float a, float b) { return div_sqrt2_f32(__fsub_rn(a, b)); }
+// both outputs of one step: lo = (a + b) / sqrt2, hi = (a - b) / sqrt2 (packed FP32 form of haar_lo / haar_hi)
+__device__ __forceinline__ void haar_pair(float a, float b, float& lo, float& hi) {
+  div_sqrt2_f32x2(__fadd_rn(a, b), __fsub_rn(a, b), lo, hi);
+}
 __device__ __forceinline__ float haar_lo64(float a, float b) {
   return div_const_f32(__fadd_rn(a, b), kSqrt2, kInvSqrt2);
 }
@@ -129,11 +133,13 @@ __global__ void __launch_bounds__(kK2Threads, 5)
 #pragma unroll
         for (int u = 0; u < kPxUnroll; ++u) tap_img[img * kImgElems + (16 * warp + kPxUnroll * it + u) * kBands + lane] = p[u];
       }
-      const float a = haar_lo(p[0], p[1]), b = haar_lo(p[2], p[3]);
-      B[(64 + 8 * warp + 2 * it) * kBStride + lane] = haar_hi(p[0], p[1]);
-      B[(64 + 8 * warp + 2 * it + 1) * kBStride + lane] = haar_hi(p[2], p[3]);
-      B[(32 + 4 * warp + it) * kBStride + lane] = haar_hi(a, b);
-      const float l2 = haar_lo(a, b);
+      float a, b, l2, h;
+      haar_pair(p[0], p[1], a, h);
+      B[(64 + 8 * warp + 2 * it) * kBStride + lane] = h;
+      haar_pair(p[2], p[3], b, h);
+      B[(64 + 8 * warp + 2 * it + 1) * kBStride + lane] = h;
+      haar_pair(a, b, l2, h);
+      B[(32 + 4 * warp + it) * kBStride + lane] = h;
       // rotate the register arrays instead of indexing them with the loop counter
 #pragma unroll
       for (int u = 0; u + kPxUnroll < 16; ++u) v[u] = v[u + kPxUnroll];
@@ -141,11 +147,14 @@ __global__ void __launch_bounds__(kK2Threads, 5)
       for (int u = 0; u < 3; ++u) l2v[u] = l2v[u + 1];
       l2v[3] = l2;
     }
-    const float l3a = haar_lo(l2v[0], l2v[1]), l3b = haar_lo(l2v[2], l2v[3]);
-    B[(16 + 2 * warp) * kBStride + lane] = haar_hi(l2v[0], l2v[1]);
-    B[(16 + 2 * warp + 1) * kBStride + lane] = haar_hi(l2v[2], l2v[3]);
-    lows[warp][lane] = haar_lo(l3a, l3b);
-    B[(8 + warp) * kBStride + lane] = haar_hi(l3a, l3b);
+    float l3a, l3b, l4, h;
+    haar_pair(l2v[0], l2v[1], l3a, h);
+    B[(16 + 2 * warp) * kBStride + lane] = h;
+    haar_pair(l2v[2], l2v[3], l3b, h);
+    B[(16 + 2 * warp + 1) * kBStride + lane] = h;
+    haar_pair(l3a, l3b, l4, h);
+    lows[warp][lane] = l4;
+    B[(8 + warp) * kBStride + lane] = h;
   }
   __syncthreads();
   if (warp == 0) {
@@ -154,16 +163,20 @@ __global__ void __launch_bounds__(kK2Threads, 5)
     for (int i = 0; i < 8; ++i) l4[i] = lows[i][lane];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      l5[i] = haar_lo(l4[2 * i], l4[2 * i + 1]);
-      B[(4 + i) * kBStride + lane] = haar_hi(l4[2 * i], l4[2 * i + 1]);
+      float h;
+      haar_pair(l4[2 * i], l4[2 * i + 1], l5[i], h);
+      B[(4 + i) * kBStride + lane] = h;
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      l6[i] = haar_lo(l5[2 * i], l5[2 * i + 1]);
-      B[(2 + i) * kBStride + lane] = haar_hi(l5[2 * i], l5[2 * i + 1]);
+      float h;
+      haar_pair(l5[2 * i], l5[2 * i + 1], l6[i], h);
+      B[(2 + i) * kBStride + lane] = h;
     }
-    B[1 * kBStride + lane] = haar_hi(l6[0], l6[1]);
-    B[0 * kBStride + lane] = haar_lo(l6[0], l6[1]);
+    float l7, h7;
+    haar_pair(l6[0], l6[1], l7, h7);
+    B[1 * kBStride + lane] = h7;
+    B[0 * kBStride + lane] = l7;
   }
   __syncthreads();
 
@@ -179,13 +192,15 @@ __global__ void __launch_bounds__(kK2Threads, 5)
     float l1[8], l2[4], l3[2];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      l1[i] = haar_lo(x[2 * i], x[2 * i + 1]);
-      r[16 + 8 * half + i] = haar_hi(x[2 * i], x[2 * i + 1]);
+      float h;
+      haar_pair(x[2 * i], x[2 * i + 1], l1[i], h);
+      r[16 + 8 * half + i] = h;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      l2[i] = haar_lo(l1[2 * i], l1[2 * i + 1]);
-      r[8 + 4 * half + i] = haar_hi(l1[2 * i], l1[2 * i + 1]);
+      float h;
+      haar_pair(l1[2 * i], l1[2 * i + 1], l2[i], h);
+      r[8 + 4 * half + i] = h;
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {   // band levels 3..5: double form (see haar_lo64)
