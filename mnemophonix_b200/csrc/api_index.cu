@@ -220,7 +220,7 @@ extern "C" int mnemo_create(int device, void* stream, mnemo_ctx** out) {
   }
   // inverse of the permutation table (permutations.c:7-1808): inv[b][p] = j with perm[p][j] == b, else 255
   // (16-bit entries: the kernel takes minima with the two-lane 16-bit SIMD instruction)
-  std::vector<uint16_t> inv((size_t)8192 * kSigLen, 255);
+  std::vector<uint16_t> inv((size_t)(8192 + 1) * kSigLen, 255);   // + one all-255 row used as padding
   for (int p = 0; p < kSigLen; p++)
     for (int j = kPermLen - 1; j >= 0; j--) inv[(size_t)k_permutations[p * kPermLen + j] * kSigLen + p] = (uint16_t)j;
   if (cudaMalloc(&ctx->d_tables, sizeof(Tables)) != cudaSuccess ||

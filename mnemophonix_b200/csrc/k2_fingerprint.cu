@@ -62,7 +62,9 @@ __device__ __forceinline__ float scale_pixel(float v, double dmx, double rmx, fl
 // 16-bit two-lane minimum of three (one VIMNMX3.U16x2)
 __device__ __forceinline__ uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
 
-template <int LOGF_VARIANT>
+// TAPS: also write the scaled image, the Haar coefficients and the raw fingerprint to global memory (stage
+// parity tests only; a separate instantiation so that the production kernel carries none of it)
+template <int LOGF_VARIANT, bool TAPS>
 __global__ void __launch_bounds__(kK2Threads, 5)
     k2_fingerprint_kernel(const TrackDev* __restrict__ tracks, const uint64_t* __restrict__ img_prefix,
                           uint32_t n_tracks, const Tables* __restrict__ tab, const uint16_t* __restrict__ inv,
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(kK2Threads, 5)
                           uint8_t* __restrict__ tap_raw, float* __restrict__ tap_img, float* __restrict__ tap_haar) {
   __shared__ float B[kImgW * kBStride];
   __shared__ float lows[8][kBands];
-  __shared__ uint16_t s_list[256];          // positions of the set bits (<= 200)
+  __shared__ __align__(16) uint32_t s_list[208];   // inverse-table rows of the set bits (<= 200), padded to 4
   __shared__ uint2 s_part[8][32];           // per-warp partial MinHash minima
   __shared__ uint32_t s_small[32];
   __shared__ uint32_t s_sel[3], s_count[2];
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(kK2Threads, 5)
     // all-zero window: 255*0/0 = NaN everywhere, the reference's sort keeps the first 200
     // (all NaN), sets no bit and flags silence (rawfingerprints.c:64-71,96).  Same for NaN/inf.
     if (tid == 0) keep[img] = 0;
-    if (tap_raw) reinterpret_cast<uint32_t*>(tap_raw + img * kRawBytes)[tid] = 0;
+    if (TAPS && tap_raw) reinterpret_cast<uint32_t*>(tap_raw + img * kRawBytes)[tid] = 0;
     return;
   }
   const double dmx = (double)mx;
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(kK2Threads, 5)
       float p[kPxUnroll];
 #pragma unroll
       for (int u = 0; u < kPxUnroll; ++u) p[u] = scale_pixel<LOGF_VARIANT>(v[u], dmx, rmx, log256, inv_log256, logtab_saddr);
-      if (tap_img) {
+      if (TAPS && tap_img) {
 #pragma unroll
         for (int u = 0; u < kPxUnroll; ++u) tap_img[img * kImgElems + (16 * warp + kPxUnroll * it + u) * kBands + lane] = p[u];
       }
@@ -216,53 +218,42 @@ __global__ void __launch_bounds__(kK2Threads, 5)
 #pragma unroll
     for (int e = 0; e < 16; ++e) c[e] = r[16 * half + e];   // final coefficients 16*tid .. 16*tid+15
   }
-  if (tap_haar) {
+  if (TAPS && tap_haar) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) tap_haar[img * kImgElems + 16 * tid + e] = c[e];
   }
 
   // 5. exact 200th largest magnitude, by bisection of the key range with the coefficients staying in registers.
-  //  (a) a lower bound first: in every warp the 25th largest of the 32 per-thread maxima (bitonic
-  //      sort across lanes); the minimum of these over the 8 warps has at least 200 elements at or
-  //      above it.  Upper end: the largest key + 1.
+  //  (a) the range is [0, largest key + 1); the first trial value is the smallest of the 8 per-warp maxima
+  //      (warps own different Haar scales, so that is a cheap guess just below the answer: typically
+  //      500-1000 keys lie above it);
   //  (b) each step counts the keys >= mid (16 compares per thread, warp reduction, 8 partial counts through
   //      shared memory, one barrier) and halves [lo, hi) keeping count(>= lo) >= 200 > count(>= hi); a warp whose
   //      largest key is below mid skips the compares.  About six steps leave 32 or fewer keys inside [lo, hi);
   //  (c) those are appended to a 32-entry list and ranked by one warp.
-  // (Earlier versions gathered the ~28 % of keys above the bound into a shared list and ran 8-bit radix passes
-  // over it with match.any-aggregated histogram atomics: 6 k warp instructions per image against 3 k here.)
+  // (Earlier versions: a bitonic sort of the thread maxima for a guaranteed lower bound, a gather of the ~28 % of
+  // keys above it into a shared list and 8-bit radix passes with match.any-aggregated histogram atomics:
+  // 6 k warp instructions per image against 2.5 k here.)
   uint32_t key[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) key[e] = __float_as_uint(c[e]) & 0x7fffffffu;
-  uint32_t lo, hi, wmax;
+  uint32_t lo = 0, hi, wmax, first;
   {
     uint32_t v = key[0];
 #pragma unroll
     for (int e = 1; e < 16; ++e) v = max(v, key[e]);
     wmax = __reduce_max_sync(0xffffffffu, v);
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1)
-#pragma unroll
-      for (int j = k >> 1; j > 0; j >>= 1) {   // ascending bitonic sort of the 32 thread maxima
-        const uint32_t o = __shfl_xor_sync(0xffffffffu, v, j);
-        const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
-        v = keep_min ? min(v, o) : max(v, o);
-      }
-    v = __shfl_sync(0xffffffffu, v, 7);       // 8th smallest = 25th largest thread maximum of this warp
-    if (lane == 0) {
-      s_cnt[0][warp] = v;
-      s_cnt[1][warp] = wmax;
-    }
+    if (lane == 0) s_cnt[1][warp] = wmax;
     if (tid == 0) s_count[0] = 0;
     __syncthreads();
-    const uint4 b0 = *reinterpret_cast<const uint4*>(&s_cnt[0][0]), b1 = *reinterpret_cast<const uint4*>(&s_cnt[0][4]);
     const uint4 m0 = *reinterpret_cast<const uint4*>(&s_cnt[1][0]), m1 = *reinterpret_cast<const uint4*>(&s_cnt[1][4]);
-    lo = min(min(min(b0.x, b0.y), min(b0.z, b0.w)), min(min(b1.x, b1.y), min(b1.z, b1.w)));
+    first = min(min(min(m0.x, m0.y), min(m0.z, m0.w)), min(min(m1.x, m1.y), min(m1.z, m1.w)));
     hi = max(max(max(m0.x, m0.y), max(m0.z, m0.w)), max(max(m1.x, m1.y), max(m1.z, m1.w))) + 1u;
   }
-  uint32_t c_lo = kImgElems, c_hi = 0;   // c_lo: any value >= 200 will do until a count replaces it
+  uint32_t c_lo = kImgElems, c_hi = 0;   // count(>= 0) = 4096
   for (int step = 0; hi - lo > 1u && c_lo - c_hi > 32u; ++step) {
-    const uint32_t mid = lo + ((hi - lo) >> 1);
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    if (step == 0 && first > lo && first < hi) mid = first;
     uint32_t cnt = 0;
     if (wmax >= mid) {                   // warp-uniform
 #pragma unroll
@@ -283,8 +274,7 @@ __global__ void __launch_bounds__(kK2Threads, 5)
     }
   }
   if (hi - lo > 1u) {
-    // (c_lo is a real count here: with c_lo still at its initial 4096 the loop cannot have ended on the
-    // second condition.)  At most 32 keys lie in [lo, hi): collect them, rank them in warp 0.
+    // at most 32 keys lie in [lo, hi): collect them, rank them in warp 0
     const uint32_t span = hi - lo;
 #pragma unroll
     for (int e = 0; e < 16; ++e)
@@ -311,18 +301,6 @@ __global__ void __launch_bounds__(kK2Threads, 5)
     lo = s_sel[0];
     c_hi = s_sel[1];
     c_lo = c_hi + s_sel[2];
-  } else if (c_lo == (uint32_t)kImgElems) {
-    // hi == lo + 1 without a single count (all thread maxima equal, e.g. a flat image): count(>= lo) is needed
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int e = 0; e < 16; ++e) cnt += key[e] >= lo;
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
-    __syncthreads();
-    if (lane == 0) s_cnt[2][warp] = cnt;
-    __syncthreads();
-    c_lo = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) c_lo += s_cnt[2][w];
   }
   // every key in [lo, lo + 1) equals lo
   const uint32_t thr = lo;
@@ -365,11 +343,18 @@ __global__ void __launch_bounds__(kK2Threads, 5)
     const int t_pos = (int)t_bit;
     const uint32_t t_neg = t_bit | 0x80000000u;
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const uint32_t cb = __float_as_uint(c[e]);
-      if ((int)cb >= t_pos) word |= 1u << (2 * e);
-      if (cb >= t_neg) word |= 1u << (2 * e + 1);
-      if (key[e] >= t_strong) ++strong;
+    for (int e = 0; e < 16; ++e) {   // three compares, each with one predicated update (spelled out: the compiler's
+                                     // version went through SEL/LOP3 chains, twice the instructions)
+      asm("{\n\t.reg .pred p, q, r;\n\t"
+          "setp.ge.s32 p, %2, %4;\n\t"
+          "setp.ge.u32 q, %2, %5;\n\t"
+          "setp.ge.u32 r, %3, %6;\n\t"
+          "@p or.b32 %0, %0, %7;\n\t"
+          "@q or.b32 %0, %0, %8;\n\t"
+          "@r add.u32 %1, %1, 1;\n\t}"
+          : "+r"(word), "+r"(strong)
+          : "r"(__float_as_uint(c[e])), "r"(key[e]), "r"(t_pos), "r"(t_neg), "r"(t_strong), "r"(1u << (2 * e)),
+            "r"(2u << (2 * e)));
     }
   } else {
 #pragma unroll
@@ -398,7 +383,7 @@ __global__ void __launch_bounds__(kK2Threads, 5)
   if (lane == 0 && strong) atomicAdd(&s_strong, strong);
   __syncthreads();
   const bool silent = s_strong < 10u;   // rawfingerprints.c:96
-  if (tap_raw) reinterpret_cast<uint32_t*>(tap_raw + img * kRawBytes)[tid] = word;
+  if (TAPS && tap_raw) reinterpret_cast<uint32_t*>(tap_raw + img * kRawBytes)[tid] = word;
   if (silent) {
     if (tid == 0) keep[img] = 0;
     return;
@@ -418,25 +403,22 @@ __global__ void __launch_bounds__(kK2Threads, 5)
       n_bits += red[w];
     }
     uint32_t rest = word;
-    while (rest) {
-      s_list[off++] = (uint16_t)(32 * tid + __ffs(rest) - 1);
+    while (rest) {   // list entry = index of the bit's row in 8-byte units (rows of the inverse table are 25 x 8 bytes)
+      s_list[off++] = 25u * (32u * tid + __ffs(rest) - 1u);
       rest &= rest - 1;
     }
+    // pad to a multiple of 4 with the all-255 row that follows the table
+    const uint32_t n_chunks = (n_bits + 3u) >> 2;
+    if (tid < 4 && n_bits + tid < 4u * n_chunks) s_list[n_bits + tid] = 25u * 8192u;
     __syncthreads();
     uint32_t m0 = 0xFFFFFFFFu, m1 = 0xFFFFFFFFu;   // permutations 4*lane, 4*lane+1 | 4*lane+2, 4*lane+3
     if (lane < 25) {
-      const uint2* __restrict__ inv64 = reinterpret_cast<const uint2*>(inv) + lane;   // rows of 200 bytes = 25 x 8
-      uint32_t i = warp;
-      for (; i + 24 < n_bits; i += 32) {   // 4 independent loads in flight
-        const uint2 a0 = __ldg(inv64 + 25u * s_list[i]), a1 = __ldg(inv64 + 25u * s_list[i + 8]);
-        const uint2 a2 = __ldg(inv64 + 25u * s_list[i + 16]), a3 = __ldg(inv64 + 25u * s_list[i + 24]);
+      const uint2* __restrict__ inv64 = reinterpret_cast<const uint2*>(inv) + lane;
+      for (uint32_t ch = warp; ch < n_chunks; ch += 8) {   // 4 bits per step: one 128-bit list read, 4 loads in flight
+        const uint4 b = *reinterpret_cast<const uint4*>(&s_list[4 * ch]);
+        const uint2 a0 = __ldg(inv64 + b.x), a1 = __ldg(inv64 + b.y), a2 = __ldg(inv64 + b.z), a3 = __ldg(inv64 + b.w);
         m0 = min3_u16x2(min3_u16x2(m0, a0.x, a1.x), a2.x, a3.x);
         m1 = min3_u16x2(min3_u16x2(m1, a0.y, a1.y), a2.y, a3.y);
-      }
-      for (; i < n_bits; i += 8) {
-        const uint2 a = __ldg(inv64 + 25u * s_list[i]);
-        m0 = min3_u16x2(m0, a.x, a.x);
-        m1 = min3_u16x2(m1, a.y, a.y);
       }
     }
     s_part[warp][lane] = make_uint2(m0, m1);
@@ -462,12 +444,18 @@ void launch_k2_fingerprint(const TrackDev* tracks, const uint64_t* img_prefix, u
                            uint8_t* keep, uint8_t* tap_raw, float* tap_img, float* tap_haar, int logf_variant,
                            cudaStream_t st) {
   if (n_images == 0) return;
-  if (logf_variant)
-    k2_fingerprint_kernel<1><<<(unsigned)n_images, kK2Threads, 0, st>>>(tracks, img_prefix, n_tracks, tab, inv, bins,
-                                                                        sig_dense, keep, tap_raw, tap_img, tap_haar);
-  else
-    k2_fingerprint_kernel<0><<<(unsigned)n_images, kK2Threads, 0, st>>>(tracks, img_prefix, n_tracks, tab, inv, bins,
-                                                                        sig_dense, keep, tap_raw, tap_img, tap_haar);
+  const bool taps = tap_raw || tap_img || tap_haar;
+#define MNEMO_K2_LAUNCH(V, T)                                                                                      \
+  k2_fingerprint_kernel<V, T><<<(unsigned)n_images, kK2Threads, 0, st>>>(tracks, img_prefix, n_tracks, tab, inv, bins, \
+                                                                         sig_dense, keep, tap_raw, tap_img, tap_haar)
+  if (logf_variant) {
+    if (taps) MNEMO_K2_LAUNCH(1, true);
+    else MNEMO_K2_LAUNCH(1, false);
+  } else {
+    if (taps) MNEMO_K2_LAUNCH(0, true);
+    else MNEMO_K2_LAUNCH(0, false);
+  }
+#undef MNEMO_K2_LAUNCH
 }
 
 // ---- device self-test of the logf mirror: compare against host values for a bit range ----
