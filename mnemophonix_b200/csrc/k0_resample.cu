@@ -50,11 +50,21 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ mono, const Track
   // reference's "start + j < n_samples" loop bound (resample.c:40) amounts to.
   if (CH == 1) {
     const int4* __restrict__ v = reinterpret_cast<const int4*>(pcm + in0);   // 16-byte aligned: in0 % 8 == 0
-    for (int i = threadIdx.x; i < (kTileIn + 7) / 8; i += kK0Threads) {
+    constexpr int kVec = (kTileIn + 7) / 8;
+    constexpr int kRounds = (kVec + kK0Threads - 1) / kK0Threads;   // 5
+    int4 q[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {   // loads first (see the two-channel case)
+      const int i = threadIdx.x + r * kK0Threads;
+      q[r] = make_int4(0, 0, 0, 0);
+      if (i < kVec && (INTERIOR || in0 + (uint64_t)i * 8 < tr.n_pcm)) q[r] = __ldg(v + i);   // buffers carry >= 64 bytes of slack past n_pcm
+    }
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      const int i = threadIdx.x + r * kK0Threads;
+      if (i >= kVec) break;
       const uint64_t f = in0 + (uint64_t)i * 8;
-      int4 q = make_int4(0, 0, 0, 0);
-      if (INTERIOR || f < tr.n_pcm) q = __ldg(v + i);      // buffers carry >= 64 bytes of slack past n_pcm
-      const int w[4] = {q.x, q.y, q.z, q.w};
+      const int w[4] = {q[r].x, q[r].y, q[r].z, q[r].w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float lo = pick_sum(w[k], 0x0001), hi = pick_sum(w[k], 0x0100);
@@ -66,11 +76,23 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ mono, const Track
     }
   } else if (CH == 2) {
     const int4* __restrict__ v = reinterpret_cast<const int4*>(pcm + in0 * 2);
-    for (int i = threadIdx.x; i < (kTileIn + 3) / 4; i += kK0Threads) {
+    constexpr int kVec = (kTileIn + 3) / 4;                       // 16-byte loads per tile
+    constexpr int kRounds = (kVec + kK0Threads - 1) / kK0Threads;   // 9
+    // all of a thread's loads are issued before the first one is used: the kernel is bound by DRAM latency
+    // (one 16-byte load in flight per thread covered only ~2/3 of the bandwidth-delay product)
+    int4 q[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      const int i = threadIdx.x + r * kK0Threads;
+      q[r] = make_int4(0, 0, 0, 0);
+      if (i < kVec && (INTERIOR || in0 + (uint64_t)i * 4 < tr.n_pcm)) q[r] = __ldg(v + i);
+    }
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+      const int i = threadIdx.x + r * kK0Threads;
+      if (i >= kVec) break;
       const uint64_t f = in0 + (uint64_t)i * 4;
-      int4 q = make_int4(0, 0, 0, 0);
-      if (INTERIOR || f < tr.n_pcm) q = __ldg(v + i);
-      const int w[4] = {q.x, q.y, q.z, q.w};
+      const int w[4] = {q[r].x, q[r].y, q[r].z, q[r].w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float sum = pick_sum(w[k], 0x0101);
