@@ -371,7 +371,10 @@ static int batch_create_common(mnemo_ctx* ctx, const mnemo_track* tracks, uint32
   if (!prenormalized) TRY(dalloc(&b->d_norm, b->n_samples));
   TRY(dalloc(&b->d_chunk_true, b->n_chunks));
   TRY(dalloc(&b->d_chunk_prefix, b->n_chunks));
+  TRY(dalloc(&b->d_chunk_prefix_end, b->n_chunks));
   TRY(dalloc(&b->d_recs, b->n_chunks));
+  TRY(dalloc(&b->d_grecs, b->n_chunks));                                  // used at the first chunk of every group of 32
+  TRY(dalloc(&b->d_slice_maps, b->n_chunks * (2ull * kSumCands * 32)));   // 768 B per chunk
   TRY(dalloc(&b->d_sumsq, n_tracks));
   TRY(dalloc(&b->d_rms, n_tracks));
   TRY(dalloc(&b->d_bins, b->n_frames * kBands));
@@ -420,7 +423,7 @@ extern "C" void mnemo_batch_destroy(mnemo_batch* b) {
   cudaStreamSynchronize(b->ctx->stream);
   if (b->d_norm == b->d_s5512) b->d_norm = nullptr;
   void* ptrs[] = {b->d_norm,     b->d_pcm,      b->d_tracks,  b->d_k0_prefix, b->d_k1_prefix,   b->d_img_prefix, b->d_chunk_track,
-                  b->d_s5512,    b->d_chunk_true, b->d_chunk_prefix, b->d_recs,  b->d_sumsq,      b->d_rms,
+                  b->d_s5512,    b->d_chunk_true, b->d_chunk_prefix, b->d_recs,  b->d_sumsq,      b->d_rms, b->d_grecs, b->d_slice_maps, b->d_chunk_prefix_end,
                   b->d_bins,     b->d_sig_dense, b->d_keep,    b->d_pos,         b->d_block_sums, b->d_sig_out,
                   b->d_n_sigs,   b->d_tap_raw, b->d_tap_img,   b->d_tap_haar};
   for (void* p : ptrs)
@@ -508,7 +511,7 @@ extern "C" int mnemo_batch_run(mnemo_batch* b) {
   if (tm) cudaEventRecord(b->ev[1], st);
   if (!b->prenormalized) {
     launch_sumsq(b->d_tracks, b->n_tracks, b->n_chunks, b->d_chunk_track, b->d_s5512, b->d_chunk_true,
-                 b->d_chunk_prefix, b->d_recs, b->d_sumsq, b->d_rms, st, &launches);
+                 b->d_chunk_prefix, b->d_chunk_prefix_end, b->d_recs, b->d_grecs, b->d_slice_maps, b->d_sumsq, b->d_rms, st, &launches);
     launch_normalize(b->d_tracks, b->d_chunk_track, b->n_chunks, b->d_s5512, b->d_rms, b->d_norm, st);
     launches += b->n_chunks ? 1 : 0;
   }

@@ -40,7 +40,10 @@ struct mnemo_batch {
   float* d_s5512 = nullptr;
   float* d_norm = nullptr;   // normalised samples (aliases d_s5512 for pre-normalised input)
   double *d_chunk_true = nullptr, *d_chunk_prefix = nullptr;
+  double* d_chunk_prefix_end = nullptr;
   mnemo::SumChunkRec* d_recs = nullptr;
+  mnemo::SumChunkRec* d_grecs = nullptr;    // composed maps per group of 32 chunks
+  uint32_t* d_slice_maps = nullptr;         // per-lane maps of every chunk (replay of binade-crossing chunks)
   float *d_sumsq = nullptr, *d_rms = nullptr, *d_bins = nullptr;
   uint8_t *d_sig_dense = nullptr, *d_keep = nullptr, *d_sig_out = nullptr;
   uint32_t *d_pos = nullptr, *d_block_sums = nullptr, *d_n_sigs = nullptr;

@@ -66,8 +66,9 @@ struct SumChunkRec {   // one per chunk, 32 bytes
 void launch_k0_resample(const TrackDev* tracks, const uint32_t* tile_prefix, uint32_t n_tracks, uint32_t n_tiles,
                         const Tables* tab, float* s5512, cudaStream_t st);
 void launch_sumsq(const TrackDev* tracks, uint32_t n_tracks, uint64_t n_chunks_total, const uint32_t* chunk_track,
-                  const float* s5512, double* chunk_true, double* chunk_prefix, SumChunkRec* recs, float* sumsq,
-                  float* rms, cudaStream_t st, int* n_launches);
+                  const float* s5512, double* chunk_true, double* chunk_prefix, double* chunk_prefix_end,
+                  SumChunkRec* recs, SumChunkRec* grecs, uint32_t* slice_maps, float* sumsq, float* rms, cudaStream_t st,
+                  int* n_launches);
 void launch_normalize(const TrackDev* tracks, const uint32_t* chunk_track, uint64_t n_chunks, const float* s5512,
                       const float* rms, float* snorm, cudaStream_t st);
 void launch_k1_spectral(const TrackDev* tracks, const uint32_t* tile_prefix, uint32_t n_tracks, uint32_t n_tiles,

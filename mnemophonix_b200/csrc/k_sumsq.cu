@@ -14,8 +14,12 @@
 //   C  per chunk (one warp): each lane simulates 128 samples with real f32 adds from the bottom of
 //      each of the 3 binades the estimate allows x 2 parities; these maps "m += delta[parity]"
 //      compose associatively, so a warp scan yields the chunk's 6 candidate increments
-//   D  per track, one warp: stitch 32 chunk maps at a time with a warp scan; a chunk that crosses a
-//      binade (or whose estimate missed) is replayed slice-wise under the actual binade(s).
+//   C' per group of 32 chunks (one warp): the 32 chunk maps composed once more, for the 3 binades the group's
+//      estimates allow -> 6 candidate increments per group
+//   D  per track, one warp: walks the groups; a group whose map exists for the accumulator's current binade
+//      and keeps it inside that binade is taken in one step.  Otherwise (about once per binade the sum climbs
+//      through) the group is stitched chunk by chunk with a warp scan, and the chunk that crosses the binade is
+//      replayed slice-wise from the per-lane maps step C kept, the crossing 128-sample slice sequentially.
 //      Then rms = (float)((double)sqrtf(S/(float)n) * 10.0) clamped.
 // The result is bit-identical to the sequential loop by construction, for any input; the
 // estimate only decides how often step D has to fall back to the sequential path.
@@ -45,24 +49,39 @@ __global__ void __launch_bounds__(256) sumsq_true_kernel(const TrackDev* __restr
   if (lane == 0) chunk_true[c] = acc;
 }
 
-// B: one warp per track, exclusive scan over the track's chunks
-__global__ void __launch_bounds__(32) sumsq_prefix_kernel(const TrackDev* __restrict__ tracks,
-                                                          const double* __restrict__ chunk_true,
-                                                          double* __restrict__ chunk_prefix) {
+// B: one CTA per track, exclusive scan over the track's chunks; also the inclusive value (prefix at the chunk's
+// end), which is what bounds the binades the accumulator can visit inside the chunk.
+constexpr int kPrefixThreads = 1024;
+__global__ void __launch_bounds__(kPrefixThreads) sumsq_prefix_kernel(const TrackDev* __restrict__ tracks,
+                                                                      const double* __restrict__ chunk_true,
+                                                                      double* __restrict__ chunk_prefix,
+                                                                      double* __restrict__ chunk_prefix_end) {
+  __shared__ double warp_tot[32];
+  __shared__ double s_carry;
   const TrackDev tr = tracks[blockIdx.x];
-  const int lane = threadIdx.x;
-  double carry = 0.0;
-  for (uint32_t base = 0; base < tr.n_chunks; base += 32) {
-    const uint32_t i = base + lane;
-    double v = i < tr.n_chunks ? chunk_true[tr.chunk_off + i] : 0.0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0.0;
+  __syncthreads();
+  for (uint32_t base = 0; base < tr.n_chunks; base += kPrefixThreads) {
+    const uint32_t i = base + threadIdx.x;
+    const double v = i < tr.n_chunks ? chunk_true[tr.chunk_off + i] : 0.0;
     double incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      double y = __shfl_up_sync(0xffffffffu, incl, o);
+      const double y = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += y;
     }
-    if (i < tr.n_chunks) chunk_prefix[tr.chunk_off + i] = carry + (incl - v);
-    carry += __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    double before = s_carry;
+    for (int w = 0; w < warp; ++w) before += warp_tot[w];   // fixed order: the estimate is deterministic
+    if (i < tr.n_chunks) {
+      chunk_prefix[tr.chunk_off + i] = before + (incl - v);
+      chunk_prefix_end[tr.chunk_off + i] = before + incl;
+    }
+    __syncthreads();
+    if (threadIdx.x == kPrefixThreads - 1) s_carry = before + incl;
+    __syncthreads();
   }
 }
 
@@ -136,8 +155,9 @@ __device__ __forceinline__ void lane_sim(const float* __restrict__ p, uint32_t n
 __global__ void __launch_bounds__(256) sumsq_sim_kernel(const TrackDev* __restrict__ tracks,
                                                         const uint32_t* __restrict__ chunk_track,
                                                         uint64_t n_chunks, const float* __restrict__ s5512,
-                                                        const double* __restrict__ chunk_prefix,
-                                                        SumChunkRec* __restrict__ recs) {
+                                                        const double* __restrict__ chunk_prefix_end,
+                                                        SumChunkRec* __restrict__ recs,
+                                                        uint32_t* __restrict__ slice_maps) {
   const uint64_t c = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= n_chunks) return;
   const int lane = threadIdx.x & 31;
@@ -146,8 +166,9 @@ __global__ void __launch_bounds__(256) sumsq_sim_kernel(const TrackDev* __restri
   const uint32_t cnt = min((uint32_t)kSumChunk, tr.n5512 - first);
   const uint32_t lo = min(cnt, (uint32_t)lane * kSubChunk), n = min(cnt - lo, (uint32_t)kSubChunk);
   // The sequential float sum never exceeds the true sum by more than rounding noise, and in
-  // practice stays above a quarter of it: candidates are the estimate's binade and the two below.
-  const float est = __double2float_ru(chunk_prefix[c] * 1.000001);
+  // practice stays above a quarter of it: candidates are the binade of the estimate at the END of the chunk
+  // (so that a chunk which lifts the sum into the next binade still has a map for it) and the two below.
+  const float est = __double2float_ru(chunk_prefix_end[c] * 1.000001);
   uint32_t e_hi = __float_as_uint(est) >> 23;
   if (!(est > 0.0f) || e_hi < 3 || e_hi > 254) e_hi = 0;
   SumChunkRec rec;
@@ -157,6 +178,13 @@ __global__ void __launch_bounds__(256) sumsq_sim_kernel(const TrackDev* __restri
     const uint32_t e[kSumCands] = {e_hi, e_hi - 1, e_hi - 2};
     uint32_t d[kSumCands][2];
     lane_sim<kSumCands>(s5512 + tr.s_off + first + lo, n, e, d);
+    // the per-lane (128-sample slice) maps are kept for the replay of chunks that cross a binade
+    uint32_t* __restrict__ sm = slice_maps + c * (2 * kSumCands * 32);
+#pragma unroll
+    for (int j = 0; j < kSumCands; ++j) {
+      sm[(2 * j) * 32 + lane] = d[j][0];
+      sm[(2 * j + 1) * 32 + lane] = d[j][1];
+    }
 #pragma unroll
     for (int j = 0; j < kSumCands; ++j) {
       const bool bad = __any_sync(0xffffffffu, d[j][0] == kSumInvalid || d[j][1] == kSumInvalid);
@@ -175,21 +203,81 @@ __global__ void __launch_bounds__(256) sumsq_sim_kernel(const TrackDev* __restri
   if (lane == 0) recs[c] = rec;
 }
 
+// C': one warp per group of 32 consecutive chunks of a track (launched one warp per chunk; only the warp of a
+// group's first chunk works).  grecs[first chunk of the group] = the composed maps for the binades
+// e_top, e_top-1, e_top-2, e_top = the highest estimate in the group.
+__global__ void __launch_bounds__(256) sumsq_group_kernel(const TrackDev* __restrict__ tracks,
+                                                          const uint32_t* __restrict__ chunk_track, uint64_t n_chunks,
+                                                          const SumChunkRec* __restrict__ recs,
+                                                          SumChunkRec* __restrict__ grecs) {
+  const uint64_t c = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= n_chunks) return;
+  const int lane = threadIdx.x & 31;
+  const TrackDev tr = tracks[chunk_track[c]];
+  const uint32_t ci = (uint32_t)(c - tr.chunk_off);
+  if (ci & 31u) return;
+  const uint32_t lim = min(32u, tr.n_chunks - ci);
+  SumChunkRec rec;
+  rec.e_hi = 0;
+  if ((uint32_t)lane < lim) rec = recs[c + lane];
+  const uint32_t e_top = __reduce_max_sync(0xffffffffu, rec.e_hi);
+  const bool all_est = !__any_sync(0xffffffffu, (uint32_t)lane < lim && rec.e_hi == 0);
+  SumChunkRec g;
+  g.pad = 0;
+  g.e_hi = (all_est && e_top >= 3) ? e_top : 0;
+#pragma unroll
+  for (int k = 0; k < kSumCands; ++k) {
+    const uint32_t j = rec.e_hi - (e_top - k);   // this chunk's candidate index for binade e_top - k
+    uint32_t d0 = kSumInvalid, d1 = kSumInvalid;
+#pragma unroll
+    for (int q = 0; q < kSumCands; ++q)
+      if (j == (uint32_t)q) {
+        d0 = rec.delta[q][0];
+        d1 = rec.delta[q][1];
+      }
+    const bool mine = (uint32_t)lane < lim;
+    const bool ok = !mine || (d0 != kSumInvalid && d1 != kSumInvalid);
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    uint32_t a0 = mine ? d0 : 0u, a1 = mine ? d1 : 0u;   // identity map past the end of the track
+    if (!all_ok) a0 = a1 = 0u;
+    scan_maps(a0, a1, lane);
+    a0 = __shfl_sync(0xffffffffu, a0, 31);
+    a1 = __shfl_sync(0xffffffffu, a1, 31);
+    // an increment of 2^23 or more cannot be applied inside one binade anyway
+    g.delta[k][0] = (all_ok && g.e_hi && a0 < 0x800000u) ? a0 : kSumInvalid;
+    g.delta[k][1] = (all_ok && g.e_hi && a1 < 0x800000u) ? a1 : kSumInvalid;
+  }
+  if (lane == 0) grecs[c] = g;
+}
+
 // D: one warp per track.  32 chunk maps are stitched at once with a warp scan; the first chunk that
 // would leave the binade (or whose candidates missed) is replayed: lanes simulate their 128-sample
 // slices under the CURRENT binade, a scan accepts the slices before the crossing, the crossing slice
 // is added sequentially, and the loop continues in the new binade.
-__device__ __forceinline__ uint32_t replay_chunk(uint32_t S, const float* __restrict__ p, uint32_t cnt, int lane) {
+// sm / e_hi: the chunk's per-lane maps from step C (candidate j = binade e_hi - j), nullptr if none.
+__device__ __forceinline__ uint32_t replay_chunk(uint32_t S, const float* __restrict__ p, uint32_t cnt, int lane,
+                                                 const uint32_t* __restrict__ sm, uint32_t e_hi) {
   const uint32_t lo = min(cnt, (uint32_t)lane * kSubChunk), n = min(cnt - lo, (uint32_t)kSubChunk);
   const uint32_t n_slices = (cnt + kSubChunk - 1) / kSubChunk;
   uint32_t done = 0;
+  bool may_sim = true;   // one fresh simulation per call at most: after it, slices without a stored map for the
+                         // current binade are simply added sequentially (a start-of-track chunk climbs through
+                         // twenty binades in its first few slices; re-simulating after each is far slower)
   while (done < n_slices) {
     const uint32_t e = S >> 23;
     uint32_t first_bad = done;   // without a usable binade: go straight to the sequential slice
-    if (e >= 1 && e < 255) {
-      const uint32_t ee[1] = {e};
+    const uint32_t j = e_hi - e;
+    const bool have_map = sm && e_hi && j < (uint32_t)kSumCands;   // warp-uniform
+    if (e >= 1 && e < 255 && (have_map || may_sim)) {
       uint32_t d[1][2];
-      lane_sim<1>(p + lo, n, ee, d);
+      if (have_map) {
+        d[0][0] = sm[(2 * j) * 32 + lane];
+        d[0][1] = sm[(2 * j + 1) * 32 + lane];
+      } else {
+        const uint32_t ee[1] = {e};
+        lane_sim<1>(p + lo, n, ee, d);
+        may_sim = false;
+      }
       const bool mine = (uint32_t)lane >= done && (uint32_t)lane < n_slices;
       const bool ok = mine && d[0][0] != kSumInvalid && d[0][1] != kSumInvalid;
       uint32_t a0 = ok ? d[0][0] : 0u, a1 = ok ? d[0][1] : 0u;
@@ -229,45 +317,71 @@ __device__ __forceinline__ uint32_t replay_chunk(uint32_t S, const float* __rest
 __global__ void __launch_bounds__(32) sumsq_stitch_kernel(const TrackDev* __restrict__ tracks,
                                                           const float* __restrict__ s5512,
                                                           const SumChunkRec* __restrict__ recs,
+                                                          const SumChunkRec* __restrict__ grecs,
+                                                          const uint32_t* __restrict__ slice_maps,
                                                           float* __restrict__ sumsq, float* __restrict__ rms_out) {
   const TrackDev tr = tracks[blockIdx.x];
   const int lane = threadIdx.x;
   const float* __restrict__ s = s5512 + tr.s_off;
   uint32_t S = 0;   // bits of the float accumulator (non-negative, so bit order == value order)
-  SumChunkRec next;
-  next.e_hi = 0;
-  if ((uint32_t)lane < tr.n_chunks) next = recs[tr.chunk_off + lane];
-  for (uint32_t base = 0; base < tr.n_chunks; base += 32) {
-    const uint32_t lim = min(32u, tr.n_chunks - base);
-    SumChunkRec rec = next;   // this group's records were fetched while the previous group was stitched
-    next.e_hi = 0;
-    if (base + 32 + lane < tr.n_chunks) next = recs[tr.chunk_off + base + 32 + lane];
-    if ((uint32_t)lane >= lim) rec.e_hi = 0;
-    uint32_t done = 0;
-    while (done < lim) {
+  const uint32_t n_groups = (tr.n_chunks + 31u) >> 5;
+  SumChunkRec gnext;
+  gnext.e_hi = 0;
+  if ((uint32_t)lane < n_groups) gnext = grecs[tr.chunk_off + 32ull * lane];
+  for (uint32_t gbase = 0; gbase < n_groups; gbase += 32) {
+    const SumChunkRec grec = gnext;   // lane l holds the record of group gbase + l; the next 32 are on their way
+    gnext.e_hi = 0;
+    if (gbase + 32 + lane < n_groups) gnext = grecs[tr.chunk_off + 32ull * (gbase + 32 + lane)];
+    const uint32_t glim = min(32u, n_groups - gbase);
+    for (uint32_t gl = 0; gl < glim; ++gl) {
+      // fast path: the whole group in one step
       const uint32_t e = S >> 23;
       const uint32_t m = (S & 0x7fffffu) | 0x800000u;
-      const uint32_t j = rec.e_hi - e;   // candidate index (unsigned wrap = no match)
-      uint32_t d0 = kSumInvalid, d1 = kSumInvalid;
+      const uint32_t ge = __shfl_sync(0xffffffffu, grec.e_hi, gl);
+      const uint32_t k = ge - e;
+      uint32_t pick = kSumInvalid;   // my lane's view of delta[k][parity of m], then broadcast from lane gl
 #pragma unroll
-      for (int c = 0; c < kSumCands; ++c)
-        if (j == (uint32_t)c) {
-          d0 = rec.delta[c][0];
-          d1 = rec.delta[c][1];
+      for (int q = 0; q < kSumCands; ++q)
+        if (k == (uint32_t)q) pick = (m & 1u) ? grec.delta[q][1] : grec.delta[q][0];
+      const uint32_t tot_g = __shfl_sync(0xffffffffu, pick, gl);
+      if (ge && e >= 1 && e < 255 && k < (uint32_t)kSumCands && tot_g != kSumInvalid && m + tot_g < 0x1000000u) {
+        S += tot_g;
+        continue;
+      }
+      // slow path: chunk by chunk
+      const uint32_t base = (gbase + gl) << 5;
+      const uint32_t lim = min(32u, tr.n_chunks - base);
+      SumChunkRec rec;
+      rec.e_hi = 0;
+      if ((uint32_t)lane < lim) rec = recs[tr.chunk_off + base + lane];
+      uint32_t done = 0;
+      while (done < lim) {
+        const uint32_t e2 = S >> 23;
+        const uint32_t m2 = (S & 0x7fffffu) | 0x800000u;
+        const uint32_t j = rec.e_hi - e2;   // candidate index (unsigned wrap = no match)
+        uint32_t d0 = kSumInvalid, d1 = kSumInvalid;
+#pragma unroll
+        for (int c = 0; c < kSumCands; ++c)
+          if (j == (uint32_t)c) {
+            d0 = rec.delta[c][0];
+            d1 = rec.delta[c][1];
+          }
+        const bool mine = (uint32_t)lane >= done && (uint32_t)lane < lim;
+        const bool ok = mine && e2 >= 1 && e2 < 255 && rec.e_hi && d0 != kSumInvalid && d1 != kSumInvalid;
+        uint32_t a0 = ok ? d0 : 0u, a1 = ok ? d1 : 0u;
+        scan_maps(a0, a1, lane);
+        const uint32_t tot = (m2 & 1u) ? a1 : a0;   // increment through this lane's chunk
+        const uint32_t bad = __ballot_sync(0xffffffffu, mine && (!ok || m2 + tot >= 0x1000000u));
+        const uint32_t first_bad = bad ? (uint32_t)(__ffs(bad) - 1) : lim;
+        if (first_bad > done) S += __shfl_sync(0xffffffffu, tot, first_bad - 1);
+        done = first_bad;
+        if (done < lim) {
+          const uint32_t first = (base + done) * kSumChunk;
+          const uint32_t e_hi_c = __shfl_sync(0xffffffffu, rec.e_hi, done);
+          S = replay_chunk(S, s + first, min((uint32_t)kSumChunk, tr.n5512 - first), lane,
+                           slice_maps + (tr.chunk_off + base + done) * (2ull * kSumCands * 32), e_hi_c);
+          ++done;
         }
-      const bool mine = (uint32_t)lane >= done && (uint32_t)lane < lim;
-      const bool ok = mine && e >= 1 && e < 255 && rec.e_hi && d0 != kSumInvalid && d1 != kSumInvalid;
-      uint32_t a0 = ok ? d0 : 0u, a1 = ok ? d1 : 0u;
-      scan_maps(a0, a1, lane);
-      const uint32_t tot = (m & 1u) ? a1 : a0;   // increment through this lane's chunk
-      const uint32_t bad = __ballot_sync(0xffffffffu, mine && (!ok || m + tot >= 0x1000000u));
-      const uint32_t first_bad = bad ? (uint32_t)(__ffs(bad) - 1) : lim;
-      if (first_bad > done) S += __shfl_sync(0xffffffffu, tot, first_bad - 1);
-      done = first_bad;
-      if (done < lim) {
-        const uint32_t first = (base + done) * kSumChunk;
-        S = replay_chunk(S, s + first, min((uint32_t)kSumChunk, tr.n5512 - first), lane);
-        ++done;
       }
     }
   }
@@ -283,17 +397,19 @@ __global__ void __launch_bounds__(32) sumsq_stitch_kernel(const TrackDev* __rest
 }
 
 void launch_sumsq(const TrackDev* tracks, uint32_t n_tracks, uint64_t n_chunks, const uint32_t* chunk_track,
-                  const float* s5512, double* chunk_true, double* chunk_prefix, SumChunkRec* recs, float* sumsq,
-                  float* rms, cudaStream_t st, int* n_launches) {
+                  const float* s5512, double* chunk_true, double* chunk_prefix, double* chunk_prefix_end,
+                  SumChunkRec* recs, SumChunkRec* grecs, uint32_t* slice_maps, float* sumsq, float* rms, cudaStream_t st,
+                  int* n_launches) {
   if (n_tracks == 0) return;
   if (n_chunks) {
-    sumsq_true_kernel<<<(unsigned)((n_chunks + 7) / 8), 256, 0, st>>>(tracks, chunk_track, n_chunks, s5512, chunk_true);
-    sumsq_prefix_kernel<<<n_tracks, 32, 0, st>>>(tracks, chunk_true, chunk_prefix);
-    sumsq_sim_kernel<<<(unsigned)((n_chunks + 7) / 8), 256, 0, st>>>(tracks, chunk_track, n_chunks, s5512,
-                                                                      chunk_prefix, recs);
-    *n_launches += 3;
+    const unsigned grid = (unsigned)((n_chunks + 7) / 8);
+    sumsq_true_kernel<<<grid, 256, 0, st>>>(tracks, chunk_track, n_chunks, s5512, chunk_true);
+    sumsq_prefix_kernel<<<n_tracks, kPrefixThreads, 0, st>>>(tracks, chunk_true, chunk_prefix, chunk_prefix_end);
+    sumsq_sim_kernel<<<grid, 256, 0, st>>>(tracks, chunk_track, n_chunks, s5512, chunk_prefix_end, recs, slice_maps);
+    sumsq_group_kernel<<<grid, 256, 0, st>>>(tracks, chunk_track, n_chunks, recs, grecs);
+    *n_launches += 4;
   }
-  sumsq_stitch_kernel<<<n_tracks, 32, 0, st>>>(tracks, s5512, recs, sumsq, rms);
+  sumsq_stitch_kernel<<<n_tracks, 32, 0, st>>>(tracks, s5512, recs, grecs, slice_maps, sumsq, rms);
   *n_launches += 1;
 }
 
