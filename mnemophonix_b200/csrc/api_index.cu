@@ -149,11 +149,16 @@ static int build_tables(Tables* t, uint32_t* probes, uint32_t* matched, std::str
     *err = "host libm: band edges fall outside FFT bins [64, 768)";
     return -3;
   }
-  for (int i = 0; i < kBands; i++)
+  for (int i = 0; i < kBands; i++) {
     if (t->edges[i + 1] <= t->edges[i]) {
       *err = "host libm: band edges are not increasing";
       return -3;
     }
+    if (t->edges[i + 1] - t->edges[i] > k1_max_band_width()) {
+      *err = "host libm: a band is wider than the spectral kernel's unrolled sum";
+      return -3;
+    }
+  }
   // Which build of glibc's logf does this host run?  glibc selects the FMA variant when the CPU
   // has FMA and AVX2 (sysdeps/x86_64/fpu/multiarch/ifunc-fma.h); confirm against the real logf.
   __builtin_cpu_init();

@@ -86,6 +86,7 @@ void launch_div_test(int which, uint32_t lo_bits, uint64_t n, unsigned long long
                      cudaStream_t st);
 void launch_logf_range(uint32_t lo_bits, uint32_t n, int variant, float* out, cudaStream_t st);
 int k1_tile_frames();
+int k1_max_band_width();
 int k0_tile_outputs();
 
 // ---- device helpers ----

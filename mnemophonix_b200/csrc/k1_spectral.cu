@@ -39,6 +39,8 @@ constexpr int kK1TileSamples = kHop * (kK1TileFrames - 1) + kFrame;   // 8128 sa
 constexpr int kScratchStride = 68;   // floats per row (32 complex + pad); 68 = 4 mod 32: STS.64 columns and LDS.128 rows conflict-free
 constexpr int kScratchFloats = 32 * kScratchStride;                   // per warp (also holds the 704 power terms)
 constexpr int kTwHiFloat2 = 2 * 31 * 32;
+constexpr int kMaxBandWidth = 44;   // >= the widest band (41 FFT bins with the reference's edges; checked at context creation)
+int k1_max_band_width() { return kMaxBandWidth; }
 constexpr size_t kK1Smem =
     sizeof(float) * (2 * kK1TileSamples + kFrame + kK1Warps * kScratchFloats) + sizeof(float2) * kTwHiFloat2 + 16;
 
@@ -321,13 +323,21 @@ __global__ void __launch_bounds__(kK1Threads, 1)
       __syncwarp();
 
       // logbins.c:64-75: sequential sum over the band's FFT bins, one band per lane
+      // Fully unrolled over the widest band (41 bins, App. B of SURVEY.md): one predicated load at an immediate
+      // offset and one add per slot; "+ 0.0f" past the band end is a no-op (the sum is never -0).
       float sum = 0.0f;
-      for (int j0 = e_lo; j0 < e_hi; j0 += 8) {
-        float tpw[8];   // loads first, then the dependent adds; "+ 0.0f" past the band end is a no-op
+      {
+        const float* __restrict__ pb = sc + e_lo;
+        const int w = e_hi - e_lo;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) tpw[u] = (j0 + u < e_hi) ? sc[j0 + u] : 0.0f;
+        for (int u0 = 0; u0 < kMaxBandWidth; u0 += 8) {
+          float tpw[8];   // loads first, then the dependent adds
 #pragma unroll
-        for (int u = 0; u < 8; ++u) sum = __fadd_rn(sum, tpw[u]);
+          for (int u = 0; u < 8; ++u) tpw[u] = (u0 + u < w) ? pb[u0 + u] : 0.0f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (u0 + u < kMaxBandWidth) sum = __fadd_rn(sum, tpw[u]);
+        }
       }
       bins[(tr.frame_off + f0 + fl) * kBands + lane] = __fdiv_rn(sum, width);
       __syncwarp();
