@@ -309,6 +309,7 @@ static int batch_create_common(mnemo_ctx* ctx, const mnemo_track* tracks, uint32
   b->k1_tile_prefix.assign(n_tracks + 1, 0);
   b->img_prefix.assign(n_tracks + 1, 0);
   b->pcm_off.assign(n_tracks + 1, 0);
+  b->group_prefix.assign(n_tracks + 1, 0);
   const uint32_t k0_out = (uint32_t)k0_tile_outputs(), k1_fr = (uint32_t)k1_tile_frames();
   uint64_t s_off = 0, frame_off = 0, chunk_off = 0;
   for (uint32_t t = 0; t < n_tracks; t++) {
@@ -336,6 +337,9 @@ static int batch_create_common(mnemo_ctx* ctx, const mnemo_track* tracks, uint32
     d.frame_off = frame_off;
     d.img_off = b->img_prefix[t];
     d.chunk_off = chunk_off;
+    d.group_off = b->group_prefix[t];
+    // images only ever touch complete groups: the last image ends at frame 8 * (n_images + 15) - 1 < n_frames
+    b->group_prefix[t + 1] = b->group_prefix[t] + (d.n_images ? d.n_images + 15 : 0);
     s_off += align_up(d.n5512, 64);
     frame_off += d.n_frames;
     chunk_off += d.n_chunks;
@@ -350,6 +354,7 @@ static int batch_create_common(mnemo_ctx* ctx, const mnemo_track* tracks, uint32
   b->n_frames = frame_off;
   b->n_images = b->img_prefix[n_tracks];
   b->n_chunks = chunk_off;
+  b->n_groups = b->group_prefix[n_tracks];
   if (b->n_images >= 0xffffffffull || b->n_frames * (uint64_t)kBands >= (1ull << 40)) {
     delete b;
     ctx->err = "batch too large";
@@ -383,6 +388,11 @@ static int batch_create_common(mnemo_ctx* ctx, const mnemo_track* tracks, uint32
   TRY(dalloc(&b->d_sumsq, n_tracks));
   TRY(dalloc(&b->d_rms, n_tracks));
   TRY(dalloc(&b->d_bins, b->n_frames * kBands));
+  TRY(dalloc(&b->d_group_prefix, n_tracks + 1));
+  TRY(dalloc(&b->d_gmax, b->n_groups));
+  TRY(dalloc(&b->d_imax, b->n_images));
+  TRY(dalloc(&b->d_slot, b->n_images * 16));
+  TRY(dalloc(&b->d_grec, b->n_groups * 16 * 256));   // room for 16 records per group; traffic follows the slots in use
   TRY(dalloc(&b->d_sig_dense, b->n_images * kSigLen));
   TRY(dalloc(&b->d_keep, b->n_images));
   TRY(dalloc(&b->d_pos, b->n_images + 1));
@@ -402,6 +412,7 @@ static int batch_create_common(mnemo_ctx* ctx, const mnemo_track* tracks, uint32
   TRY(cudaMemcpyAsync(b->d_k0_prefix, b->k0_tile_prefix.data(), 4ull * (n_tracks + 1), cudaMemcpyHostToDevice, st));
   TRY(cudaMemcpyAsync(b->d_k1_prefix, b->k1_tile_prefix.data(), 4ull * (n_tracks + 1), cudaMemcpyHostToDevice, st));
   TRY(cudaMemcpyAsync(b->d_img_prefix, b->img_prefix.data(), 8ull * (n_tracks + 1), cudaMemcpyHostToDevice, st));
+  TRY(cudaMemcpyAsync(b->d_group_prefix, b->group_prefix.data(), 4ull * (n_tracks + 1), cudaMemcpyHostToDevice, st));
   if (b->n_chunks)
     TRY(cudaMemcpyAsync(b->d_chunk_track, chunk_track.data(), 4ull * b->n_chunks, cudaMemcpyHostToDevice, st));
   // the slack after each track's PCM is read (masked) by the 128-bit loads: keep it defined
@@ -428,7 +439,7 @@ extern "C" void mnemo_batch_destroy(mnemo_batch* b) {
   cudaStreamSynchronize(b->ctx->stream);
   if (b->d_norm == b->d_s5512) b->d_norm = nullptr;
   void* ptrs[] = {b->d_norm,     b->d_pcm,      b->d_tracks,  b->d_k0_prefix, b->d_k1_prefix,   b->d_img_prefix, b->d_chunk_track,
-                  b->d_s5512,    b->d_chunk_true, b->d_chunk_prefix, b->d_recs,  b->d_sumsq,      b->d_rms, b->d_grecs, b->d_slice_maps, b->d_chunk_prefix_end,
+                  b->d_s5512,    b->d_chunk_true, b->d_chunk_prefix, b->d_recs,  b->d_sumsq,      b->d_rms, b->d_grecs, b->d_slice_maps, b->d_chunk_prefix_end, b->d_group_prefix, b->d_gmax, b->d_imax, b->d_slot, b->d_grec, b->d_tap_px,
                   b->d_bins,     b->d_sig_dense, b->d_keep,    b->d_pos,         b->d_block_sums, b->d_sig_out,
                   b->d_n_sigs,   b->d_tap_raw, b->d_tap_img,   b->d_tap_haar};
   for (void* p : ptrs)
@@ -526,9 +537,10 @@ extern "C" int mnemo_batch_run(mnemo_batch* b) {
                      ctx->sm_count, st);
   launches += k1_tiles ? 1 : 0;
   if (tm) cudaEventRecord(b->ev[3], st);
-  launch_k2_fingerprint(b->d_tracks, b->d_img_prefix, b->n_tracks, b->n_images, ctx->d_tables, ctx->d_inv_perms, b->d_bins,
-                        b->d_sig_dense, b->d_keep, b->d_tap_raw, b->d_tap_img, b->d_tap_haar,
-                        ctx->h_tables.logf_variant, st);
+  launch_group_records(b->d_tracks, b->d_group_prefix, b->n_tracks, (uint32_t)b->n_groups, ctx->d_tables, b->d_bins,
+                       b->d_gmax, b->d_imax, b->d_slot, b->d_grec, b->d_tap_px, ctx->h_tables.logf_variant, st, &launches);
+  launch_k2_fingerprint(b->d_tracks, b->d_img_prefix, b->n_tracks, b->n_images, ctx->d_inv_perms, b->d_imax, b->d_slot,
+                        b->d_grec, b->d_tap_px, b->d_sig_dense, b->d_keep, b->d_tap_raw, b->d_tap_img, b->d_tap_haar, st);
   launches += b->n_images ? 1 : 0;
   if (tm) cudaEventRecord(b->ev[4], st);
   launch_compact(b->d_sig_dense, b->d_keep, b->n_images, b->d_img_prefix, b->n_tracks, b->d_block_sums, b->d_pos,
@@ -592,11 +604,14 @@ extern "C" int mnemo_batch_enable_taps(mnemo_batch* b, int on) {
     cudaError_t e = dalloc(&b->d_tap_raw, b->n_images * kRawBytes);
     if (e == cudaSuccess) e = dalloc(&b->d_tap_img, b->n_images * kImgElems);
     if (e == cudaSuccess) e = dalloc(&b->d_tap_haar, b->n_images * kImgElems);
+    if (e == cudaSuccess) e = dalloc(&b->d_tap_px, b->n_groups * 16 * 256);
     if (e != cudaSuccess) return mnemo_fail(b->ctx, e, "mnemo_batch_enable_taps");
   } else if (!on && b->d_tap_raw) {
     cudaFree(b->d_tap_raw);
     cudaFree(b->d_tap_img);
     cudaFree(b->d_tap_haar);
+    cudaFree(b->d_tap_px);
+    b->d_tap_px = nullptr;
     b->d_tap_raw = nullptr;
     b->d_tap_img = b->d_tap_haar = nullptr;
   }

@@ -24,6 +24,8 @@ struct mnemo_batch {
   std::vector<mnemo::TrackDev> h_tracks;
   std::vector<uint32_t> k0_tile_prefix, k1_tile_prefix;
   std::vector<uint64_t> img_prefix, pcm_off;
+  std::vector<uint32_t> group_prefix;        // 8-frame groups per track (k15_groups.cu)
+  uint64_t n_groups = 0;
   uint64_t n_samples = 0, n_frames = 0, n_images = 0, n_chunks = 0;
   uint32_t launches_per_run = 0;
   // optional per-stage timing (CUDA events on the context's stream)
@@ -47,6 +49,13 @@ struct mnemo_batch {
   float *d_sumsq = nullptr, *d_rms = nullptr, *d_bins = nullptr;
   uint8_t *d_sig_dense = nullptr, *d_keep = nullptr, *d_sig_out = nullptr;
   uint32_t *d_pos = nullptr, *d_block_sums = nullptr, *d_n_sigs = nullptr;
+  // group records: what consecutive images share (k15_groups.cu)
+  uint32_t* d_group_prefix = nullptr;
+  uint32_t* d_gmax = nullptr;     // [n_groups] largest energy of the group (float bits)
+  float* d_imax = nullptr;        // [n_images] window maximum
+  uint8_t* d_slot = nullptr;      // [n_images][16] record slot of each of the image's groups
+  float* d_grec = nullptr;        // [n_groups][16][256] records (slots in use only)
+  float* d_tap_px = nullptr;      // same shape: scaled pixels (debug taps only)
   uint8_t* d_tap_raw = nullptr;
   float *d_tap_img = nullptr, *d_tap_haar = nullptr;
 };

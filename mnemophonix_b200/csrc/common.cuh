@@ -42,6 +42,7 @@ struct TrackDev {
   uint64_t frame_off;     // frame offset into bins
   uint64_t img_off;       // image offset into per-image arrays
   uint64_t chunk_off;     // chunk offset into the sum-of-squares scratch
+  uint64_t group_off;     // offset of this track's 8-frame groups (n_frames / 8 of them) into the group arrays
 };
 
 // Host-computed tables (same libm calls as the reference), uploaded once per context.
@@ -73,10 +74,13 @@ void launch_normalize(const TrackDev* tracks, const uint32_t* chunk_track, uint6
                       const float* rms, float* snorm, cudaStream_t st);
 void launch_k1_spectral(const TrackDev* tracks, const uint32_t* tile_prefix, uint32_t n_tracks, uint32_t n_tiles,
                         const Tables* tab, const float* snorm, float* bins, int sm_count, cudaStream_t st);
+void launch_group_records(const TrackDev* tracks, const uint32_t* group_prefix, uint32_t n_tracks, uint32_t n_groups,
+                          const Tables* tab, const float* bins, uint32_t* gmax, float* imax, uint8_t* slot, float* rec,
+                          float* tap_px, int logf_variant, cudaStream_t st, int* n_launches);
 void launch_k2_fingerprint(const TrackDev* tracks, const uint64_t* img_prefix, uint32_t n_tracks, uint64_t n_images,
-                           const Tables* tab, const uint16_t* inv_perms, const float* bins, uint8_t* sig_dense,
-                           uint8_t* keep, uint8_t* tap_raw, float* tap_img, float* tap_haar, int logf_variant,
-                           cudaStream_t st);
+                           const uint16_t* inv_perms, const float* imax, const uint8_t* slot, const float* rec,
+                           const float* tap_px, uint8_t* sig_dense, uint8_t* keep, uint8_t* tap_raw, float* tap_img,
+                           float* tap_haar, cudaStream_t st);
 void launch_compact(const uint8_t* sig_dense, const uint8_t* keep, uint64_t n_images, const uint64_t* img_prefix,
                     uint32_t n_tracks, uint32_t* block_sums, uint32_t* pos, uint8_t* sig_out, uint32_t* n_sigs,
                     cudaStream_t st, int* n_launches);

@@ -19,57 +19,26 @@
 //      fingerprint: bits are assembled without atomics
 //   7. MinHash inside out: each set bit contributes its position in every permutation (inverse table,
 //      100 x u16 per bit), signature = element-wise minimum (VIMNMX3.U16x2)
-#include "common.cuh"
+#include "fingerprint_math.cuh"
 
 namespace mnemo {
 
 constexpr int kK2Threads = 256;
 constexpr int kBStride = 33;
 
-// haar.c:35-36: (float)((double)(a +/- b) / M_SQRT2).
-// Two exact forms (common.cuh): haar_*64 divides in double by reciprocal and is exact for every float;
-// haar_*  stays in FP32 (no conversions, no FP64) and is exact whenever the dividend is 0 or at least 2^-103
-// in magnitude.  Where that is guaranteed:
-//   pixels are 0 or >= logf(1 + 2^-23) / logf(256) > 2^-26, so every value of the time transform is a sum of
-//   non-negative terms (a low: 0 or >= 2^-30, a multiple of 2^-53) or a difference of two lows (0 or >= 2^-53);
-//   its outputs are 0 or >= 2^-54, i.e. multiples of 2^-77.  Band level 1 therefore divides 0 or >= 2^-77 and
-//   yields multiples of 2^-101; band level 2 divides 0 or >= 2^-101.  From band level 3 on a (wildly
-//   adversarial) chain of cancellations could go below 2^-103, so those 3.5 of 15.5 steps keep the double form.
-__device__ __forceinline__ float haar_lo(float a, float b) { return div_sqrt2_f32(__fadd_rn(a, b)); }
-__device__ __forceinline__ float haar_hi(float a, float b) { return div_sqrt2_f32(__fsub_rn(a, b)); }
-// both outputs of one step: lo = (a + b) / sqrt2, hi = (a - b) / sqrt2 (packed FP32 form of haar_lo / haar_hi)
-__device__ __forceinline__ void haar_pair(float a, float b, float& lo, float& hi) {
-  div_sqrt2_f32x2(__fadd_rn(a, b), __fsub_rn(a, b), lo, hi);
-}
-__device__ __forceinline__ float haar_lo64(float a, float b) {
-  return div_const_f32(__fadd_rn(a, b), kSqrt2, kInvSqrt2);
-}
-__device__ __forceinline__ float haar_hi64(float a, float b) {
-  return div_const_f32(__fsub_rn(a, b), kSqrt2, kInvSqrt2);
-}
-
-// spectralimages.c:52-58 for one pixel
-template <int LOGF_VARIANT>
-__device__ __forceinline__ float scale_pixel(float v, double dmx, double rmx, float log256, float inv_log256,
-                                             uint32_t logtab_saddr) {
-  float sc = __double2float_rn(div_markstein2(__dmul_rn(255.0, (double)v), dmx, rmx));   // spectralimages.c:53
-  if (sc > 255.0f) sc = 255.0f;
-  // spectralimages.c:57: an f32 division by logf(256.0f); the dividend is 0 or >= logf(1 + 2^-23) = 1.19e-7,
-  // inside the domain where the reciprocal form is exact (common.cuh, mnemo_selftest_div which = 4)
-  return div_f32_recip(logf_glibc<LOGF_VARIANT>(__fadd_rn(1.0f, sc), logtab_saddr), log256, inv_log256);
-}
-
 // 16-bit two-lane minimum of three (one VIMNMX3.U16x2)
 __device__ __forceinline__ uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
 
 // TAPS: also write the scaled image, the Haar coefficients and the raw fingerprint to global memory (stage
 // parity tests only; a separate instantiation so that the production kernel carries none of it)
-template <int LOGF_VARIANT, bool TAPS>
+template <bool TAPS>
 __global__ void __launch_bounds__(kK2Threads, 5)
     k2_fingerprint_kernel(const TrackDev* __restrict__ tracks, const uint64_t* __restrict__ img_prefix,
-                          uint32_t n_tracks, const Tables* __restrict__ tab, const uint16_t* __restrict__ inv,
-                          const float* __restrict__ bins, uint8_t* __restrict__ sig_dense, uint8_t* __restrict__ keep,
-                          uint8_t* __restrict__ tap_raw, float* __restrict__ tap_img, float* __restrict__ tap_haar) {
+                          uint32_t n_tracks, const uint16_t* __restrict__ inv, const float* __restrict__ imax,
+                          const uint8_t* __restrict__ slot, const float* __restrict__ rec,
+                          const float* __restrict__ tap_px, uint8_t* __restrict__ sig_dense,
+                          uint8_t* __restrict__ keep, uint8_t* __restrict__ tap_raw, float* __restrict__ tap_img,
+                          float* __restrict__ tap_haar) {
   __shared__ float B[kImgW * kBStride];
   __shared__ float lows[8][kBands];
   __shared__ __align__(16) uint32_t s_list[208];   // inverse-table rows of the set bits (<= 200), padded to 4
@@ -79,35 +48,18 @@ __global__ void __launch_bounds__(kK2Threads, 5)
   __shared__ uint32_t red[8];
   __shared__ __align__(16) uint32_t s_cnt[4][8];   // bound / max exchange, then alternating per-step partial counts
   __shared__ uint32_t s_strong;
-  __shared__ __align__(128) double s_logtab[32];   // invc[16] | logc[16]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t img = blockIdx.x;
   const uint32_t t = find_segment<uint64_t>(img_prefix, n_tracks, img);
   const TrackDev tr = tracks[t];
   const uint64_t j = img - img_prefix[t];
-  const float* __restrict__ src = bins + (tr.frame_off + j * kImgStep) * kBands;
-
   if (tid == 0) s_strong = 0;
-  if (tid < 32) s_logtab[tid] = c_logf_tab[tid & 15][tid >> 4];
-  const uint32_t logtab_saddr = (uint32_t)__cvta_generic_to_shared(s_logtab);
 
-  // 1. load: element (time = 16*warp + u, band = lane)
-  float v[16];
-#pragma unroll
-  for (int u = 0; u < 16; ++u) v[u] = src[(16 * warp + u) * kBands + lane];
-
-  // 2. max (energies are >= +0, so unsigned bit order is value order)
-  uint32_t mb = 0;
-#pragma unroll
-  for (int u = 0; u < 16; ++u) mb = max(mb, __float_as_uint(v[u]));
-  mb = __reduce_max_sync(0xffffffffu, mb);
-  if (lane == 0) red[warp] = mb;
-  __syncthreads();
-  mb = red[0];
-#pragma unroll
-  for (int w = 1; w < 8; ++w) mb = max(mb, red[w]);
-  const float mx = __uint_as_float(mb);
+  // 1.-3. The image's maximum, its scaled pixels and the first three Haar levels along time come from the
+  // group records (k15_groups.cu): image j = frame groups j .. j+15, warp w takes groups 2w and 2w+1 (frames
+  // 16w .. 16w+15), lane = band.  A record holds, per band, {hi1[0..3]; hi2[0..1], hi3, lo3} of its 8 frames.
+  const float mx = imax[img];
   if (!(mx > 0.0f) || !(mx < __int_as_float(0x7f800000))) {
     // all-zero window: 255*0/0 = NaN everywhere, the reference's sort keeps the first 200
     // (all NaN), sets no bit and flags silence (rawfingerprints.c:64-71,96).  Same for NaN/inf.
@@ -115,46 +67,31 @@ __global__ void __launch_bounds__(kK2Threads, 5)
     if (TAPS && tap_raw) reinterpret_cast<uint32_t*>(tap_raw + img * kRawBytes)[tid] = 0;
     return;
   }
-  const double dmx = (double)mx;
-  const double rmx = __drcp_rn(dmx);
-  const float log256 = tab->log256, inv_log256 = tab->inv_log256;
-  // 2.+3. scale, then Haar along time (haar.c:56-67): row = band `lane`, this thread holds t in [16*warp,
-  // 16*warp+16).  The pixel body (two double-precision divisions' worth of code) is instantiated kPxUnroll times
-  // inside a rolled loop: fully unrolled the kernel outgrows the 32 KB instruction cache and 40 resident warps
-  // in different phases starve on instruction fetch; as a called function the per-call register shuffling and
-  // constant reloads cost a tenth of the kernel's instructions.
   {
-    constexpr int kPxUnroll = 4;
-    float l2v[4];
-#pragma unroll 1
-    for (int it = 0; it < 16 / kPxUnroll; ++it) {
-      float p[kPxUnroll];
+    float l3[2];
 #pragma unroll
-      for (int u = 0; u < kPxUnroll; ++u) p[u] = scale_pixel<LOGF_VARIANT>(v[u], dmx, rmx, log256, inv_log256, logtab_saddr);
-      if (TAPS && tap_img) {
+    for (int kk = 0; kk < 2; ++kk) {
+      const uint32_t k = 2 * warp + kk;
+      const uint32_t d = slot[img * 16 + k];
+      const uint64_t base = ((tr.group_off + j + k) * 16 + d) * 256;
+      const float4* __restrict__ r4 = reinterpret_cast<const float4*>(rec + base + 8 * lane);
+      const float4 h1 = __ldg(r4), o = __ldg(r4 + 1);
+      B[(64 + 8 * warp + 4 * kk + 0) * kBStride + lane] = h1.x;
+      B[(64 + 8 * warp + 4 * kk + 1) * kBStride + lane] = h1.y;
+      B[(64 + 8 * warp + 4 * kk + 2) * kBStride + lane] = h1.z;
+      B[(64 + 8 * warp + 4 * kk + 3) * kBStride + lane] = h1.w;
+      B[(32 + 4 * warp + 2 * kk + 0) * kBStride + lane] = o.x;
+      B[(32 + 4 * warp + 2 * kk + 1) * kBStride + lane] = o.y;
+      B[(16 + 2 * warp + kk) * kBStride + lane] = o.z;
+      l3[kk] = o.w;
+      if (TAPS && tap_img && tap_px) {
 #pragma unroll
-        for (int u = 0; u < kPxUnroll; ++u) tap_img[img * kImgElems + (16 * warp + kPxUnroll * it + u) * kBands + lane] = p[u];
+        for (int f = 0; f < 8; ++f)
+          tap_img[img * kImgElems + (16 * warp + 8 * kk + f) * kBands + lane] = tap_px[base + f * kBands + lane];
       }
-      float a, b, l2, h;
-      haar_pair(p[0], p[1], a, h);
-      B[(64 + 8 * warp + 2 * it) * kBStride + lane] = h;
-      haar_pair(p[2], p[3], b, h);
-      B[(64 + 8 * warp + 2 * it + 1) * kBStride + lane] = h;
-      haar_pair(a, b, l2, h);
-      B[(32 + 4 * warp + it) * kBStride + lane] = h;
-      // rotate the register arrays instead of indexing them with the loop counter
-#pragma unroll
-      for (int u = 0; u + kPxUnroll < 16; ++u) v[u] = v[u + kPxUnroll];
-#pragma unroll
-      for (int u = 0; u < 3; ++u) l2v[u] = l2v[u + 1];
-      l2v[3] = l2;
     }
-    float l3a, l3b, l4, h;
-    haar_pair(l2v[0], l2v[1], l3a, h);
-    B[(16 + 2 * warp) * kBStride + lane] = h;
-    haar_pair(l2v[2], l2v[3], l3b, h);
-    B[(16 + 2 * warp + 1) * kBStride + lane] = h;
-    haar_pair(l3a, l3b, l4, h);
+    float l4, h;
+    haar_pair(l3[0], l3[1], l4, h);   // level 4: the first step that crosses a group boundary
     lows[warp][lane] = l4;
     B[(8 + warp) * kBStride + lane] = h;
   }
@@ -440,22 +377,17 @@ __global__ void __launch_bounds__(kK2Threads, 5)
 }
 
 void launch_k2_fingerprint(const TrackDev* tracks, const uint64_t* img_prefix, uint32_t n_tracks, uint64_t n_images,
-                           const Tables* tab, const uint16_t* inv, const float* bins, uint8_t* sig_dense,
-                           uint8_t* keep, uint8_t* tap_raw, float* tap_img, float* tap_haar, int logf_variant,
-                           cudaStream_t st) {
+                           const uint16_t* inv, const float* imax, const uint8_t* slot, const float* rec,
+                           const float* tap_px, uint8_t* sig_dense, uint8_t* keep, uint8_t* tap_raw, float* tap_img,
+                           float* tap_haar, cudaStream_t st) {
   if (n_images == 0) return;
-  const bool taps = tap_raw || tap_img || tap_haar;
-#define MNEMO_K2_LAUNCH(V, T)                                                                                      \
-  k2_fingerprint_kernel<V, T><<<(unsigned)n_images, kK2Threads, 0, st>>>(tracks, img_prefix, n_tracks, tab, inv, bins, \
-                                                                         sig_dense, keep, tap_raw, tap_img, tap_haar)
-  if (logf_variant) {
-    if (taps) MNEMO_K2_LAUNCH(1, true);
-    else MNEMO_K2_LAUNCH(1, false);
-  } else {
-    if (taps) MNEMO_K2_LAUNCH(0, true);
-    else MNEMO_K2_LAUNCH(0, false);
-  }
-#undef MNEMO_K2_LAUNCH
+  // the kernel itself no longer evaluates logf (the group records carry the scaled pixels' transforms)
+  if (tap_raw || tap_img || tap_haar)
+    k2_fingerprint_kernel<true><<<(unsigned)n_images, kK2Threads, 0, st>>>(
+        tracks, img_prefix, n_tracks, inv, imax, slot, rec, tap_px, sig_dense, keep, tap_raw, tap_img, tap_haar);
+  else
+    k2_fingerprint_kernel<false><<<(unsigned)n_images, kK2Threads, 0, st>>>(
+        tracks, img_prefix, n_tracks, inv, imax, slot, rec, tap_px, sig_dense, keep, tap_raw, tap_img, tap_haar);
 }
 
 // ---- device self-test of the logf mirror: compare against host values for a bit range ----
