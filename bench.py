@@ -147,16 +147,21 @@ def bind_near_gpu(index: int) -> None:
         pass
 
 
-def search_section(ctx, sigs, ref_queries: int = 8):
-    """Supplementary search figures on the signatures just produced: the track's signatures are cut into
-    30-second entries (304 signatures), queries are 34-signature excerpts (a 5 s clip)."""
-    from mnemophonix_b200 import capi
-    per = 304
-    entries = [sigs[i:i + per] for i in range(0, len(sigs) - per + 1, per)]
-    rng = np.random.RandomState(3)
-    picks = rng.randint(0, len(entries), 256)
-    offs = rng.randint(0, per - 34, 256)
-    queries = [entries[e][o:o + 34] for e, o in zip(picks, offs)]
+def search_section(ctx, ref_queries: int = 8, n_tracks: int = 96, seconds: float = 30.0):
+    """Supplementary search figures (BASELINE.json configs[0] scaled out): n_tracks DISTINCT 30-second synthetic
+    tracks are indexed on the GPU into one database; queries are 5-second PCM excerpts of every track at four
+    offsets that are not hop-aligned (re-fingerprinted on the GPU, as `mnemophonix search` would)."""
+    from mnemophonix_b200 import capi, synth
+    pcms = [synth.synth_track(5000 + i, seconds, 1) for i in range(n_tracks)]
+    entries, st = ctx.index_pcm_batch(pcms)
+    clips, picks = [], []
+    for i, p in enumerate(pcms):
+        for k in range(4):
+            off = int((3.0 + 5.5 * k) * 44100) + 1234 + 97 * k
+            clips.append(np.ascontiguousarray(p[off: off + 5 * 44100]))
+            picks.append(i)
+    queries, st = ctx.index_pcm_batch(clips)
+    per = int(np.mean([len(e) for e in entries]))
     t0 = time.perf_counter()
     db = capi.Db(ctx, entries)
     t_build = time.perf_counter() - t0
@@ -167,12 +172,13 @@ def search_section(ctx, sigs, ref_queries: int = 8):
     for _ in range(reps):
         res, (L, D) = db.search(prepared)
     dt = (time.perf_counter() - t0) / reps
-    n_qsig = 34 * len(queries)
-    out = {"queries_per_s": len(queries) / dt, "db_entries": len(entries), "db_signatures": per * len(entries),
+    n_qsig = int(sum(len(q) for q in queries))
+    out = {"queries_per_s": len(queries) / dt, "queries": len(queries), "db_entries": len(entries),
+           "db_signatures": int(sum(len(e) for e in entries)),
            "lsh_build_s": t_build, "probed_nodes_per_query_signature": L / n_qsig,
            "deep_checks_per_query_signature": D / n_qsig,
            "algorithmic_GBps": (n_qsig * 300 + 4 * L + 100 * D + 16 * len(queries)) / dt / 1e9,
-           "self_excerpts_identified": int(sum(r[0] == e for r, e in zip(res, picks)))}
+           "excerpts_identified": int(sum(r[0] == e for r, e in zip(res, picks)))}
     try:
         from oracle import ref as refmod
         import ctypes as C
@@ -427,7 +433,19 @@ def main():
                 "stage_ms": stage_ms,
                 "whole_path_frac": (alg_bytes / (ms_per_step / 1e3) / 1e9) / peak,
                 "note": "the path is FP32/FP64-issue bound, not HBM bound (DESIGN.md); frac is the contract's "
-                        "algorithmic-bytes figure"}
+                        "algorithmic-bytes figure; stage k2_fingerprint = group records + fingerprint kernel"}
+    # The roofline that actually binds the dominant kernel (k1_spectral): the FP32 pipe.  The bit-exact radix-2
+    # butterfly network costs 2865 FP32-pipe cycles per frame and SM sub-partition (ncu: 1871 FMA-pipe
+    # instructions, 994 of them packed FMUL2/FADD2 at two cycles each; tools/fp32x2_probe.cu measures those
+    # issue costs), so the kernel cannot run faster than frames * 2865 / (SMs * 4 * SM clock).
+    sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+    n5512 = int(args.seconds * 44100) // 8
+    n_frames_track = 1 + (n5512 - 2048) // 64 if n5512 >= 2048 else 0
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    fp32_floor_ms = n_frames_track * 2865.0 / (sm_count * 4 * sm_mhz * 1e6) * 1e3
+    roofline["fp32_pipe"] = {"kernel": "k1_spectral", "pipe_cycles_per_frame": 2865, "frames": n_frames_track,
+                             "sm_mhz": sm_mhz, "floor_ms": fp32_floor_ms, "kernel_ms": stage_ms.get("k1_spectral"),
+                             "frac": (fp32_floor_ms / stage_ms["k1_spectral"]) if stage_ms.get("k1_spectral") else None}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -440,7 +458,7 @@ def main():
             "roofline": roofline, "signatures_per_track": int(n_sigs[0])}
 
     if world == 1 and rank == 0:
-        line["search"] = search_section(ctx, out_pinned[: int(n_sigs[0])].numpy().copy())
+        line["search"] = search_section(ctx)
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         r = reference_throughput(args.cpu_sample_seconds, args.channels, 1, 0)
         if r is not None:

@@ -185,14 +185,13 @@ extern "C" int64_t mnemo_db_get_matches(mnemo_db* db, const uint8_t* sig, uint32
 
 // ------------------------------------------------------------------ search ----
 
-extern "C" int mnemo_search_shard(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
-                                  uint32_t n_queries, mnemo_cand* cands, uint64_t cap_cands, uint64_t* n_cands,
-                                  mnemo_lastgroup* last, uint64_t* stats) {
-  if (!db || !query_start || !n_cands) return -3;
+// Records of all queries, in (query, entry) order, appended to `out` (no capacity limit).
+static int search_shard_impl(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start, uint32_t n_queries,
+                             std::vector<mnemo_cand>& out, mnemo_lastgroup* last, uint64_t* stats) {
+  if (!db || !query_start) return -3;
   mnemo_ctx* ctx = db->ctx;
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
-  *n_cands = 0;
   if (stats) stats[0] = stats[1] = 0;
   const uint32_t n_qsigs = query_start[n_queries];
   if (last)
@@ -228,7 +227,6 @@ extern "C" int mnemo_search_shard(mnemo_db* db, const uint8_t* query_sigs, const
   TRY(cudaMemsetAsync(d_stats, 0, 16, st));
   std::vector<CandDev> h_cands;
   std::vector<uint32_t> h_qstart;
-  uint64_t written = 0;
   int rc = 0;
   for (uint32_t q0 = 0; q0 < n_queries && e == cudaSuccess && rc == 0; q0 += group) {
     const uint32_t nq = std::min(group, n_queries - q0);
@@ -270,15 +268,7 @@ extern "C" int mnemo_search_shard(mnemo_db* db, const uint8_t* query_sigs, const
     std::sort(h_cands.begin(), h_cands.end(), [](const CandDev& a, const CandDev& b) {
       return a.query != b.query ? a.query < b.query : a.entry < b.entry;
     });
-    for (const CandDev& c : h_cands) {
-      if (written < cap_cands && cands) {
-        cands[written].query = c.query + q0;
-        cands[written].entry = c.entry;
-        cands[written].score = c.score;
-        cands[written].n_matches = c.n_matches;
-      }
-      written++;
-    }
+    for (const CandDev& c : h_cands) out.push_back(mnemo_cand{c.query + q0, c.entry, c.score, c.n_matches});
   }
   if (e == cudaSuccess && rc == 0 && last) {
     std::vector<mnemo_lastgroup_dev> h_last(n_qsigs);
@@ -302,12 +292,23 @@ extern "C" int mnemo_search_shard(mnemo_db* db, const uint8_t* query_sigs, const
   }
 #undef TRY
   if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_shard");
+  return rc;
+}
+
+extern "C" int mnemo_search_shard(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
+                                  uint32_t n_queries, mnemo_cand* cands, uint64_t cap_cands, uint64_t* n_cands,
+                                  mnemo_lastgroup* last, uint64_t* stats) {
+  if (!db || !query_start || !n_cands) return -3;
+  *n_cands = 0;
+  std::vector<mnemo_cand> v;
+  const int rc = search_shard_impl(db, query_sigs, query_start, n_queries, v, last, stats);
   if (rc != 0) return rc;
-  *n_cands = written;
-  if (written > cap_cands) {
-    ctx->err = "mnemo_search_shard: cands capacity too small";
+  *n_cands = v.size();
+  if (v.size() > cap_cands) {
+    db->ctx->err = "mnemo_search_shard: cands capacity too small";
     return -1;
   }
+  if (cands && !v.empty()) memcpy(cands, v.data(), v.size() * sizeof(mnemo_cand));
   return 0;
 }
 
@@ -618,19 +619,10 @@ extern "C" int mnemo_search_batch(mnemo_db* db, const uint8_t* query_sigs, const
   if (!db || !out) return -3;
   for (uint32_t q = 0; q < n_queries; q++) out[q] = mnemo_match{-7, 0.0f, 0};
   if (n_queries == 0) return 0;
-  uint64_t cap = std::max<uint64_t>(1024, (uint64_t)n_queries * 64), n = 0;
   std::vector<mnemo_cand> cands;
-  int rc;
-  for (;;) {
-    cands.resize(cap);
-    rc = mnemo_search_shard(db, query_sigs, query_start, n_queries, cands.data(), cap, &n, nullptr, stats);
-    if (rc == -1 && n > cap) {   // capacity: retry once with the exact size
-      cap = n;
-      continue;
-    }
-    break;
-  }
+  const int rc = search_shard_impl(db, query_sigs, query_start, n_queries, cands, nullptr, stats);
   if (rc != 0) return rc;
+  const uint64_t n = cands.size();
   return mnemo_search_finish(cands.data(), n, nullptr, 1, query_start, n_queries, db->entry_base + db->n_entries, out);
 }
 
