@@ -47,8 +47,13 @@ constexpr size_t kK1Smem =
 int k1_tile_frames() { return kK1TileFrames; }
 
 __constant__ float2 c_tw64[32];
+__constant__ float c_one;   // 1.0f at run time (see twiddle_mul)
 
-void k1_upload_constants(const Tables& t) { cudaMemcpyToSymbol(c_tw64, t.tw64, sizeof(float2) * 32); }
+void k1_upload_constants(const Tables& t) {
+  const float one = 1.0f;
+  cudaMemcpyToSymbol(c_tw64, t.tw64, sizeof(float2) * 32);
+  cudaMemcpyToSymbol(c_one, &one, sizeof(float));
+}
 
 __host__ __device__ constexpr int rev6(int v) {
   return ((v & 1) << 5) | ((v & 2) << 3) | ((v & 4) << 1) | ((v & 8) >> 1) | ((v & 16) >> 3) | ((v & 32) >> 5);
@@ -93,13 +98,23 @@ __device__ __forceinline__ cplx sub2(cplx a, cplx b) {
 }
 
 // tao = w * b with every product and sum rounded on its own (fft.c:53-54)
+// (wr*br - wi*bi, wr*bi + wi*br) with all four products and both sums rounded on their own (fft.c:53-54), and no
+// scalar FP32 instruction.  The second product is taken on the swapped operand with the sign folded into the
+// twiddle, q' = (bi * -wi, br * wi) — half-swap and per-half negation are free operand modifiers of the packed
+// instructions — and the sum is an FMA by one, fma(p, 1, q') = RN(p + q').  The 1 must be a RUN-TIME value
+// (c_one, set by the host): a packed add of a packed product, or an FMA by a literal 1, is contracted by ptxas
+// into an FFMA2 that rounds the product away, -fmad=false or not.  (Scalar FP32 instructions between packed ones
+// cost up to two cycles each, tools/fp32x2_probe.cu; with them this kernel ran at 2.16 ms instead of 1.9.)
 __device__ __forceinline__ cplx twiddle_mul(cplx b, const float wr, const float wi) {
-  const cplx p = mul2(b, pk(wr, wr));   // (wr*br, wr*bi)
-  const cplx q = mul2(b, pk(wi, wi));   // (wi*br, wi*bi)
-  return pk(__fsub_rn(lo(p), hi(q)), __fadd_rn(hi(p), lo(q)));
+  const cplx p = mul2(b, pk(wr, wr));
+  const cplx qs = mul2(pk(hi(b), lo(b)), pk(-wi, wi));
+  const float one = c_one;
+  cplx t;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t) : "l"(p), "l"(pk(one, one)), "l"(qs));
+  return t;
 }
 
-// fft.c:53-62: 2 FMUL2 + 2 FADD + 2 FADD2
+// fft.c:53-62: 2 FMUL2 + 1 FFMA2 + 2 FADD2
 __device__ __forceinline__ void bfly(cplx& a, cplx& b, const float wr, const float wi) {
   const cplx t = twiddle_mul(b, wr, wi);
   b = sub2(a, t);
