@@ -9,9 +9,23 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "fingerprinting.h"
 #include "host_internal.h"
+
+/* MNEMO_TRACE=1: wall-clock stage times on stderr (diagnostics only) */
+static double now_ms(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
+}
+static int trace_on(void) {
+    static int on = -1;
+    if (on < 0) on = getenv("MNEMO_TRACE") != NULL;
+    return on;
+}
+#define TRACE(what, t0) do { if (trace_on()) fprintf(stderr, "[mnemo] %-28s %8.1f ms\n", what, now_ms() - (t0)); } while (0)
 
 static pthread_once_t g_once = PTHREAD_ONCE_INIT;
 static mnemo_ctx* g_ctx = NULL;
@@ -24,6 +38,20 @@ static void make_context(void) {
 mnemo_ctx* mnemo_host_context(void) {
     pthread_once(&g_once, make_context);
     return g_ctx;
+}
+
+/* Creating the CUDA context takes a second or more in a fresh process; it does not depend on the input, so it is
+ * started on a helper thread while the caller parses and reads the WAV file. */
+static void* warm_context(void* arg) {
+    (void)arg;
+    mnemo_host_context();
+    return NULL;
+}
+void mnemo_host_context_prefetch(void) {
+    static int started = 0;
+    if (__sync_lock_test_and_set(&started, 1)) return;
+    pthread_t th;
+    if (pthread_create(&th, NULL, warm_context, NULL) == 0) pthread_detach(th);
 }
 
 void free_signatures(struct signatures* s) {
@@ -47,7 +75,10 @@ static struct signatures* new_signatures(uint64_t capacity) {
 int generate_fingerprint(const char* wav, struct signatures** fingerprint,
                          char** artist, char** track_title, char** album_title) {
     struct wav_data w;
+    double t0 = now_ms();
+    mnemo_host_context_prefetch();
     int rc = wav_load(wav, &w);
+    TRACE("wav_load", t0);
     if (rc != SUCCESS) return rc;
     if (w.artist) fprintf(stderr, "Artist: %s\n", w.artist);
     if (w.track_title) fprintf(stderr, "Track title: %s\n", w.track_title);
@@ -67,7 +98,9 @@ int generate_fingerprint(const char* wav, struct signatures** fingerprint,
         wav_release(&w);
         return FILE_TOO_SMALL;
     }
+    t0 = now_ms();
     mnemo_ctx* ctx = mnemo_host_context();
+    TRACE("context", t0);
     if (!ctx) {
         fprintf(stderr, "mnemophonix: no usable B200 GPU (there is no CPU implementation)\n");
         wav_release(&w);
@@ -88,8 +121,12 @@ int generate_fingerprint(const char* wav, struct signatures** fingerprint,
     tr.reserved = 0;
     uint32_t n = 0;
     int32_t status = 0;
+    t0 = now_ms();
     rc = mnemo_index_pcm_batch(ctx, &tr, 1, (uint8_t*)s->signatures, n_images, &n, &status);
+    TRACE("mnemo_index_pcm_batch", t0);
+    t0 = now_ms();
     wav_release(&w);
+    TRACE("wav_release", t0);
     if (rc == 0) rc = status;
     if (rc != SUCCESS) {
         free_signatures(s);

@@ -7,6 +7,8 @@
 /* Process-wide GPU context, created on first use (device = $MNEMO_DEVICE, default 0).
  * Returns NULL if no B200 is available: there is no CPU path. */
 mnemo_ctx* mnemo_host_context(void);
+/* Starts creating it on a helper thread (returns at once); mnemo_host_context() then waits for it. */
+void mnemo_host_context_prefetch(void);
 
 /* One parsed WAVE file: PCM frames in memory plus LIST/INFO metadata (malloc'd, may be NULL). */
 struct wav_data {
