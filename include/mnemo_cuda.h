@@ -64,6 +64,14 @@ typedef struct mnemo_track {
 int mnemo_batch_create(mnemo_ctx* ctx, const mnemo_track* tracks, uint32_t n_tracks, mnemo_batch** out);
 void mnemo_batch_destroy(mnemo_batch* b);
 int mnemo_batch_upload(mnemo_batch* b, const mnemo_track* tracks); /* H2D of every track's PCM, async */
+/* Streaming ingest (replaces read_samples' per-block fread loop, wav.c:345-394, for files that are read in
+ * pieces): bytes [byte_offset, byte_offset + bytes) of one track's interleaved int16 data, asynchronous on the
+ * context's stream when `src` is pinned (mnemo_host_alloc).  The caller reads the next piece of the file into a
+ * second staging buffer meanwhile and calls mnemo_batch_sync before reusing a buffer. */
+int mnemo_batch_upload_part(mnemo_batch* b, uint32_t track, uint64_t byte_offset, const void* src, uint64_t bytes);
+/* Pinned host memory for callers that do not link the CUDA runtime themselves. */
+int mnemo_host_alloc(mnemo_ctx* ctx, void** p, uint64_t bytes);
+void mnemo_host_free(mnemo_ctx* ctx, void* p);
 int mnemo_batch_run(mnemo_batch* b);                               /* kernels only, async */
 int mnemo_batch_sync(mnemo_batch* b);
 uint64_t mnemo_batch_max_signatures(const mnemo_batch* b);         /* = total spectral images */

@@ -508,6 +508,39 @@ extern "C" int mnemo_batch_get_timing(mnemo_batch* b, double* stage_ms_avg, uint
   return 0;
 }
 
+extern "C" int mnemo_batch_upload_part(mnemo_batch* b, uint32_t track, uint64_t byte_offset, const void* src,
+                                       uint64_t bytes) {
+  if (!b || track >= b->n_tracks || (!src && bytes) || b->prenormalized) return -3;
+  cudaSetDevice(b->ctx->device);
+  const uint64_t total = b->h_tracks[track].n_pcm * b->h_tracks[track].channels * 2ull;
+  if (byte_offset > total || bytes > total - byte_offset) {
+    b->ctx->err = "mnemo_batch_upload_part: range outside the track";
+    return -3;
+  }
+  if (!bytes || !b->h_tracks[track].n_frames) return 0;
+  cudaError_t e = cudaMemcpyAsync(b->d_pcm + b->pcm_off[track] + byte_offset, src, bytes, cudaMemcpyHostToDevice,
+                                  b->ctx->stream);
+  if (e != cudaSuccess) return mnemo_fail(b->ctx, e, "mnemo_batch_upload_part");
+  return 0;
+}
+
+extern "C" int mnemo_host_alloc(mnemo_ctx* ctx, void** p, uint64_t bytes) {
+  if (!ctx || !p) return -3;
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    *p = nullptr;
+    return mnemo_fail(ctx, e, "mnemo_host_alloc");
+  }
+  return 0;
+}
+
+extern "C" void mnemo_host_free(mnemo_ctx* ctx, void* p) {
+  if (!ctx || !p) return;
+  cudaSetDevice(ctx->device);
+  cudaFreeHost(p);
+}
+
 extern "C" int mnemo_batch_run(mnemo_batch* b) {
   if (!b) return -3;
   mnemo_ctx* ctx = b->ctx;

@@ -72,13 +72,67 @@ static struct signatures* new_signatures(uint64_t capacity) {
     return s;
 }
 
+/* Pinned staging for the streaming ingest: two buffers per process, reused for every file. */
+#define STAGE_BYTES (32u << 20)
+static void* g_stage[2] = {NULL, NULL};
+static pthread_mutex_t g_stage_lock = PTHREAD_MUTEX_INITIALIZER;   /* one file at a time through the staging pair */
+
+/* The data chunk goes to the GPU in 32 MB pieces: while piece k is on its way (asynchronous copy from a pinned
+ * buffer), piece k+1 is read from the file into the other buffer.  This replaces read_samples' loop of one fread
+ * per sample block (wav.c:358-375), and the one big malloc + fread + pageable copy of the whole-file path. */
+static int ingest_streaming(mnemo_ctx* ctx, FILE* f, const struct wav_data* w, struct signatures* s, uint32_t n_images,
+                            uint32_t* n_out) {
+    mnemo_track tr;
+    tr.pcm = NULL;
+    tr.n_frames = w->n_frames;
+    tr.channels = w->channels;
+    tr.reserved = 0;
+    mnemo_batch* b = NULL;
+    double tc = now_ms();
+    int rc = mnemo_batch_create(ctx, &tr, 1, &b);
+    TRACE("batch create (device buffers)", tc);
+    if (rc != 0) return rc;
+    pthread_mutex_lock(&g_stage_lock);
+    for (int i = 0; i < 2 && rc == 0; i++)
+        if (!g_stage[i]) rc = mnemo_host_alloc(ctx, &g_stage[i], STAGE_BYTES);
+    const uint64_t total = w->n_frames * (uint64_t)w->channels * 2u;
+    uint64_t off = 0;
+    int cur = 0;
+    double t0 = now_ms();
+    while (rc == 0 && off < total) {
+        const size_t want = (size_t)((total - off < STAGE_BYTES) ? (total - off) : STAGE_BYTES);
+        if (fread(g_stage[cur], 1, want, f) != want) {   /* truncated data chunk (read_samples: DECODING_ERROR) */
+            rc = DECODING_ERROR;
+            break;
+        }
+        rc = mnemo_batch_sync(b);                        /* the copy that used the other buffer is done */
+        if (rc == 0) rc = mnemo_batch_upload_part(b, 0, off, g_stage[cur], want);
+        off += want;
+        cur ^= 1;
+    }
+    if (rc == 0) rc = mnemo_batch_sync(b);
+    pthread_mutex_unlock(&g_stage_lock);
+    TRACE("read + upload (streamed)", t0);
+    t0 = now_ms();
+    int32_t status = 0;
+    if (rc == 0) rc = mnemo_batch_run(b);
+    if (rc == 0) rc = mnemo_batch_download(b, (uint8_t*)s->signatures, n_images, n_out, &status);
+    TRACE("kernels + download", t0);
+    t0 = now_ms();
+    mnemo_batch_destroy(b);
+    TRACE("batch destroy", t0);
+    if (rc == 0) rc = status;
+    return rc;
+}
+
 int generate_fingerprint(const char* wav, struct signatures** fingerprint,
                          char** artist, char** track_title, char** album_title) {
     struct wav_data w;
+    FILE* f = NULL;
+    unsigned int align = 0;
     double t0 = now_ms();
     mnemo_host_context_prefetch();
-    int rc = wav_load(wav, &w);
-    TRACE("wav_load", t0);
+    int rc = wav_open(wav, &w, &f, &align);
     if (rc != SUCCESS) return rc;
     if (w.artist) fprintf(stderr, "Artist: %s\n", w.artist);
     if (w.track_title) fprintf(stderr, "Track title: %s\n", w.track_title);
@@ -92,42 +146,67 @@ int generate_fingerprint(const char* wav, struct signatures** fingerprint,
     fprintf(stderr, "Resampling to 5512Hz...\n");
     fprintf(stderr, "Normalizing samples...\n");
     const uint32_t n5512 = mnemo_samples_5512(w.n_frames);
-    fprintf(stderr, "%d 5512Hz mono samples\n", (int)n5512);
     const uint32_t n_images = mnemo_images(n5512);
+    const int streamed = (align == 2u * w.channels) && n_images != 0;
+    if (!streamed) {
+        /* padded sample blocks, or a file too small to fingerprint: the whole-file reader (it also reports a
+         * truncated data chunk before the size check, as read_samples does) */
+        fclose(f);
+        f = NULL;
+        char *a2 = w.artist, *t2 = w.track_title, *l2 = w.album_title;
+        w.artist = w.track_title = w.album_title = NULL;
+        wav_release(&w);
+        rc = wav_load(wav, &w);
+        /* metadata was already handed out (or kept) above: drop the second copy */
+        free(w.artist); free(w.track_title); free(w.album_title);
+        w.artist = a2; w.track_title = t2; w.album_title = l2;
+        if (rc != SUCCESS) {
+            wav_release(&w);
+            return rc;
+        }
+    }
+    TRACE("wav header / load", t0);
+    fprintf(stderr, "%d 5512Hz mono samples\n", (int)n5512);
     if (n_images == 0) {   /* fingerprinting.c:42, spectralimages.c:128 */
+        if (f) fclose(f);
         wav_release(&w);
         return FILE_TOO_SMALL;
     }
     t0 = now_ms();
     mnemo_ctx* ctx = mnemo_host_context();
-    TRACE("context", t0);
+    TRACE("context (wait)", t0);
     if (!ctx) {
         fprintf(stderr, "mnemophonix: no usable B200 GPU (there is no CPU implementation)\n");
+        if (f) fclose(f);
         wav_release(&w);
         return DECODING_ERROR;
     }
     struct signatures* s = new_signatures(n_images);
     if (!s) {
+        if (f) fclose(f);
         wav_release(&w);
         return MEMORY_ERROR;
     }
     fprintf(stderr, "Got %d spectral images\n", (int)n_images);
     fprintf(stderr, "Applying Haar transform to spectral images\n");
     fprintf(stderr, "Building raw fingerprints\n");
-    mnemo_track tr;
-    tr.pcm = w.pcm;
-    tr.n_frames = w.n_frames;
-    tr.channels = w.channels;
-    tr.reserved = 0;
     uint32_t n = 0;
-    int32_t status = 0;
-    t0 = now_ms();
-    rc = mnemo_index_pcm_batch(ctx, &tr, 1, (uint8_t*)s->signatures, n_images, &n, &status);
-    TRACE("mnemo_index_pcm_batch", t0);
-    t0 = now_ms();
+    if (streamed) {
+        rc = ingest_streaming(ctx, f, &w, s, n_images, &n);
+        fclose(f);
+    } else {
+        mnemo_track tr;
+        tr.pcm = w.pcm;
+        tr.n_frames = w.n_frames;
+        tr.channels = w.channels;
+        tr.reserved = 0;
+        int32_t status = 0;
+        t0 = now_ms();
+        rc = mnemo_index_pcm_batch(ctx, &tr, 1, (uint8_t*)s->signatures, n_images, &n, &status);
+        TRACE("mnemo_index_pcm_batch", t0);
+        if (rc == 0) rc = status;
+    }
     wav_release(&w);
-    TRACE("wav_release", t0);
-    if (rc == 0) rc = status;
     if (rc != SUCCESS) {
         free_signatures(s);
         return rc;

@@ -21,5 +21,9 @@ struct wav_data {
 };
 int wav_load(const char* path, struct wav_data* out);
 void wav_release(struct wav_data* w);
+/* Same parsing and error codes as wav_load, but the data chunk is left in the file: *f_out is positioned at its
+ * first byte, *block_align is the file's frame stride; out->pcm stays NULL.  The caller closes the file. */
+#include <stdio.h>
+int wav_open(const char* path, struct wav_data* out, FILE** f_out, unsigned int* block_align);
 
 #endif

@@ -80,7 +80,7 @@ static int parse_info(FILE* f, uint32_t file_size, uint32_t after_data, struct w
     return SUCCESS;
 }
 
-int wav_load(const char* path, struct wav_data* w) {
+int wav_open(const char* path, struct wav_data* w, FILE** f_out, unsigned int* block_align) {
     memset(w, 0, sizeof *w);
     FILE* f = fopen(path, "rb");
     if (!f) return CANNOT_READ_FILE;
@@ -129,6 +129,21 @@ int wav_load(const char* path, struct wav_data* w) {
         rc = DECODING_ERROR;
         goto fail;
     }
+    *f_out = f;
+    *block_align = align;
+    return SUCCESS;
+fail:
+    fclose(f);
+    wav_release(w);
+    return rc;
+}
+
+int wav_load(const char* path, struct wav_data* w) {
+    FILE* f = NULL;
+    unsigned int align = 0;
+    int rc = wav_open(path, w, &f, &align);
+    if (rc != SUCCESS) return rc;
+    const unsigned int channels = w->channels;
     {
         const size_t bytes = (size_t)w->n_frames * align;
         uint8_t* raw = (uint8_t*)malloc(bytes ? bytes : 1);

@@ -16,6 +16,17 @@ for it in range(3):
     if it == 0: print(r.stderr.decode()[-900:])
     dt = time.perf_counter() - t
     print("ours: rc %d, %.3f s wall, %d bytes of text, %.1f audio-h/s" % (r.returncode, dt, len(r.stdout), secs / 3600 / dt))
+# several files in one process: the context is created once
+paths = [path] + ["/dev/shm/mnemo_cli_2h_%d.wav" % i for i in range(1, 4)]
+for q in paths[1:]:
+    os.link(path, q) if not os.path.exists(q) else None
+t = time.perf_counter()
+r = subprocess.run([cli, "index"] + paths, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=dict(os.environ, MNEMO_TRACE="1"))
+dt = time.perf_counter() - t
+print("ours, 4 files in one process: rc %d, %.3f s wall, %.1f audio-h/s" % (r.returncode, dt, 4 * secs / 3600 / dt))
+print(r.stderr.decode()[-700:])
+for q in paths[1:]:
+    os.remove(q)
 if "--ref" in sys.argv:
     from oracle import ref as refmod
     if refmod.available("O2"):
