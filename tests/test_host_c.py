@@ -196,6 +196,29 @@ def test_generate_fingerprint_and_metadata(host, ref):
 
 
 @pytest.mark.gpu
+def test_streamed_ingest_of_a_multi_piece_file(host, ref):
+    # 250 s of stereo = 44 MB: two 32 MB pieces through the pinned staging pair (host/fingerprinting.c)
+    pcm = synth.synth_track(78, 250.0, 2)
+    p = tempfile.mktemp(suffix=".wav")
+    synth.write_wav(p, pcm)
+    try:
+        psig = C.POINTER(refmod.Signatures)()
+        assert host.generate_fingerprint(p.encode(), C.byref(psig), None, None, None) == 0
+        rc, want, *_ = ref.fingerprint_wav(p)
+        got = np.ctypeslib.as_array(C.cast(psig.contents.signatures, C.POINTER(C.c_uint8)),
+                                    (psig.contents.n_signatures, 100)).copy()
+        assert rc == 0 and np.array_equal(got, want)
+        host.free_signatures(psig)
+        # the same file cut short inside its second piece: read_samples' DECODING_ERROR (wav.c:381-386)
+        with open(p, "r+b") as f:
+            f.truncate(os.path.getsize(p) - 5_000_001)
+        psig = C.POINTER(refmod.Signatures)()
+        assert host.generate_fingerprint(p.encode(), C.byref(psig), None, None, None) == -3
+    finally:
+        os.remove(p)
+
+
+@pytest.mark.gpu
 def test_cli_index_and_search_round_trip(host, ref):
     d = tempfile.mkdtemp()
     names = []
