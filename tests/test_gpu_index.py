@@ -166,6 +166,36 @@ def test_ties_at_rank_200_go_to_the_lower_index(ctx, oracle, seed):
     b.close()
 
 
+@pytest.mark.parametrize("direction", ["crescendo", "decrescendo", "steps"])
+def test_window_maximum_changes_every_image(ctx, oracle, direction):
+    # Group records (k15_groups.cu) are shared by the images of a frame group that have the same window maximum.
+    # A steadily rising (falling) level gives every image its own maximum: all 16 slots of a group are in use;
+    # level steps give runs of equal maxima in between.  Images, Haar coefficients and signatures must not notice.
+    n = 44100 * 14
+    t = np.arange(n) / 44100.0
+    rng = np.random.RandomState(5)
+    if direction == "crescendo":
+        env = 0.02 + 0.9 * (t / t[-1]) ** 2
+    elif direction == "decrescendo":
+        env = 0.02 + 0.9 * (1 - t / t[-1]) ** 2
+    else:
+        env = 0.05 + 0.25 * np.floor(t / 1.3) % 4
+    x = env * (np.sin(2 * np.pi * (500 + 300 * np.sin(2 * np.pi * 0.7 * t)) * t) + 0.2 * rng.standard_normal(n))
+    pcm = np.clip(np.round(x * 20000), -32768, 32767).astype(np.int16)[:, None]
+    b = run_with_taps(ctx, pcm)
+    norm, rms = oracle.normalize(oracle.resample(oracle.downmix(pcm)))
+    rc, sigs, taps = oracle.fingerprint_samples(norm, taps=True)
+    assert rc == 0 and len(taps["images"]) > 100
+    assert bits_equal(b.read(6, 0).reshape(-1, 4096), taps["images"])
+    assert bits_equal(b.read(7, 0).reshape(-1, 4096), taps["haar"])
+    assert bits_equal(b.read(5, 0).reshape(-1, 1024), taps["raw"])
+    got, st = b.signatures()
+    assert st == [0] and bits_equal(got[0], sigs)
+    b.close()
+    got2, st2 = ctx.index_pcm_batch([pcm])          # the production instantiation (no taps)
+    assert bits_equal(got2[0], sigs)
+
+
 def test_from_samples_entry_point(ctx, oracle):
     # generate_fingerprint_from_samples (fingerprinting.c:81-109): no resample, no normalisation
     rng = np.random.RandomState(9)
