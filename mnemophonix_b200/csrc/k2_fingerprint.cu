@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(kK2Threads, 5)
   __shared__ uint32_t s_small[32];
   __shared__ uint32_t s_sel[3], s_count[2];
   __shared__ uint32_t red[8];
-  __shared__ __align__(16) uint32_t s_cnt[4][8];   // bound / max exchange, then alternating per-step partial counts
+  __shared__ __align__(16) uint32_t s_cnt[4][8];   // per-warp maxima exchange
+  __shared__ uint32_t s_tot[3][2];                 // rotating block totals of the selection steps
   __shared__ uint32_t s_strong;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -164,9 +165,10 @@ __global__ void __launch_bounds__(kK2Threads, 5)
   //  (a) the range is [0, largest key + 1); the first trial value is the smallest of the 8 per-warp maxima
   //      (warps own different Haar scales, so that is a cheap guess just below the answer: typically
   //      500-1000 keys lie above it);
-  //  (b) each step counts the keys >= mid (16 compares per thread, warp reduction, 8 partial counts through
-  //      shared memory, one barrier) and halves [lo, hi) keeping count(>= lo) >= 200 > count(>= hi); a warp whose
-  //      largest key is below mid skips the compares.  About six steps leave 32 or fewer keys inside [lo, hi);
+  //  (b) each step counts the keys >= three trial values (48 compares per thread, warp reductions, shared
+  //      atomics, one barrier) and keeps the quarter of [lo, hi) with count(>= lo) >= 200 > count(>= hi); a warp
+  //      whose largest key is below the lowest trial value skips the compares.  About three steps leave 32 or
+  //      fewer keys inside [lo, hi);
   //  (c) those are appended to a 32-entry list and ranked by one warp.
   // (Earlier versions: a bitonic sort of the thread maxima for a guaranteed lower bound, a gather of the ~28 % of
   // keys above it into a shared list and 8-bit radix passes with match.any-aggregated histogram atomics:
@@ -181,33 +183,72 @@ __global__ void __launch_bounds__(kK2Threads, 5)
     for (int e = 1; e < 16; ++e) v = max(v, key[e]);
     wmax = __reduce_max_sync(0xffffffffu, v);
     if (lane == 0) s_cnt[1][warp] = wmax;
-    if (tid == 0) s_count[0] = 0;
+    if (tid == 0) {
+      s_count[0] = 0;
+      s_tot[0][0] = s_tot[0][1] = 0;
+    }
     __syncthreads();
     const uint4 m0 = *reinterpret_cast<const uint4*>(&s_cnt[1][0]), m1 = *reinterpret_cast<const uint4*>(&s_cnt[1][4]);
     first = min(min(min(m0.x, m0.y), min(m0.z, m0.w)), min(min(m1.x, m1.y), min(m1.z, m1.w)));
     hi = max(max(max(m0.x, m0.y), max(m0.z, m0.w)), max(max(m1.x, m1.y), max(m1.z, m1.w))) + 1u;
   }
   uint32_t c_lo = kImgElems, c_hi = 0;   // count(>= 0) = 4096
+  // Four-way steps: three trial values per step (counts c1 >= c2 >= c3), one barrier per step, ~3 steps per
+  // image instead of ~6.3 two-way steps.  Warp totals go through shared atomics into one of three rotating slots
+  // (the slot of the next step is cleared before this step's barrier); c1 and c2 travel packed in one word
+  // (a warp holds 512 keys, the block 4096: 16 bits each are enough).
+  uint32_t slot_cur = 0;
   for (int step = 0; hi - lo > 1u && c_lo - c_hi > 32u; ++step) {
-    uint32_t mid = lo + ((hi - lo) >> 1);
-    if (step == 0 && first > lo && first < hi) mid = first;
-    uint32_t cnt = 0;
-    if (wmax >= mid) {                   // warp-uniform
-#pragma unroll
-      for (int e = 0; e < 16; ++e) cnt += key[e] >= mid;
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
-    }
-    uint32_t* slot = s_cnt[2 + (step & 1)];   // two alternating slots: one barrier per step
-    if (lane == 0) slot[warp] = cnt;
-    __syncthreads();
-    const uint4 p0 = *reinterpret_cast<const uint4*>(slot), p1 = *reinterpret_cast<const uint4*>(slot + 4);
-    const uint32_t total = (p0.x + p0.y) + (p0.z + p0.w) + (p1.x + p1.y) + (p1.z + p1.w);
-    if (total >= (uint32_t)kTopK) {
-      lo = mid;
-      c_lo = total;
+    uint32_t p1, p2, p3;
+    if (step == 0 && first > lo && first < hi) {
+      const uint32_t r = hi - first;
+      p1 = first;
+      p2 = first + r / 3u;
+      p3 = first + (2u * r) / 3u;
     } else {
-      hi = mid;
-      c_hi = total;
+      const uint32_t q = (hi - lo) >> 2;
+      p1 = q ? lo + q : lo + ((hi - lo) >> 1);
+      p2 = q ? lo + 2u * q : p1;
+      p3 = q ? lo + 3u * q : p1;
+    }
+    if (wmax >= p1) {                    // warp-uniform; otherwise this warp contributes nothing to any count
+      uint32_t n1 = 0, n2 = 0, n3 = 0;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        n1 += key[e] >= p1;
+        n2 += key[e] >= p2;
+        n3 += key[e] >= p3;
+      }
+      uint32_t w0 = n1 | (n2 << 16), w1 = n3;
+      asm("redux.sync.add.u32 %0, %0, 0xffffffff;" : "+r"(w0));
+      asm("redux.sync.add.u32 %0, %0, 0xffffffff;" : "+r"(w1));
+      if (lane == 0) {
+        atomicAdd(&s_tot[slot_cur][0], w0);
+        atomicAdd(&s_tot[slot_cur][1], w1);
+      }
+    }
+    const uint32_t slot_next = slot_cur == 2 ? 0 : slot_cur + 1;
+    if (tid == 0) s_tot[slot_next][0] = s_tot[slot_next][1] = 0;
+    __syncthreads();
+    const uint32_t t0 = s_tot[slot_cur][0], c3 = s_tot[slot_cur][1];
+    const uint32_t c1 = t0 & 0xffffu, c2 = t0 >> 16;
+    slot_cur = slot_next;
+    if (c3 >= (uint32_t)kTopK) {
+      lo = p3;
+      c_lo = c3;
+    } else if (c2 >= (uint32_t)kTopK) {
+      lo = p2;
+      c_lo = c2;
+      hi = p3;
+      c_hi = c3;
+    } else if (c1 >= (uint32_t)kTopK) {
+      lo = p1;
+      c_lo = c1;
+      hi = p2;
+      c_hi = c2;
+    } else {
+      hi = p1;
+      c_hi = c1;
     }
   }
   if (hi - lo > 1u) {
@@ -350,10 +391,12 @@ __global__ void __launch_bounds__(kK2Threads, 5)
     __syncthreads();
     uint32_t m0 = 0xFFFFFFFFu, m1 = 0xFFFFFFFFu;   // permutations 4*lane, 4*lane+1 | 4*lane+2, 4*lane+3
     if (lane < 25) {
-      const uint2* __restrict__ inv64 = reinterpret_cast<const uint2*>(inv) + lane;
+      const uint2* __restrict__ inv64 = reinterpret_cast<const uint2*>(inv);
+      const uint32_t ul = (uint32_t)lane;   // 32-bit index arithmetic: one IMAD.WIDE per address
       for (uint32_t ch = warp; ch < n_chunks; ch += 8) {   // 4 bits per step: one 128-bit list read, 4 loads in flight
         const uint4 b = *reinterpret_cast<const uint4*>(&s_list[4 * ch]);
-        const uint2 a0 = __ldg(inv64 + b.x), a1 = __ldg(inv64 + b.y), a2 = __ldg(inv64 + b.z), a3 = __ldg(inv64 + b.w);
+        const uint2 a0 = __ldg(inv64 + (b.x + ul)), a1 = __ldg(inv64 + (b.y + ul)), a2 = __ldg(inv64 + (b.z + ul)),
+                    a3 = __ldg(inv64 + (b.w + ul));
         m0 = min3_u16x2(min3_u16x2(m0, a0.x, a1.x), a2.x, a3.x);
         m1 = min3_u16x2(min3_u16x2(m1, a0.y, a1.y), a2.y, a3.y);
       }
