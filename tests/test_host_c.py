@@ -269,3 +269,69 @@ def test_cli_index_and_search_round_trip(host, ref):
     host.free_signature_list(plist)
     host.free_hash_tables(lsh_mine)
     host.free_index(mine)
+
+
+@pytest.mark.gpu
+def test_concurrent_callers_share_one_context(host, oracle):
+    """SURVEY.md §8(b) threading row: the reference's API is re-entrant after warm-up (search / LSH are read-only
+    on shared index + lsh), so the drop-in must accept calls from any thread at once.  Eight threads index
+    different WAV files and search one shared database simultaneously (ctypes releases the GIL during the calls);
+    every result must equal the serial one."""
+    import threading
+    d = tempfile.mkdtemp()
+    paths, want = [], []
+    for i in range(8):
+        pcm = synth.synth_track(900 + i, 12.0 + 2.5 * i, 1 + i % 2)
+        p = os.path.join(d, f"t{i}.wav")
+        synth.write_wav(p, pcm)
+        paths.append(p)
+        rc, s = oracle.fingerprint_pcm(pcm)
+        assert rc == 0
+        want.append(s)
+    dbpath = os.path.join(d, "db")
+    open(dbpath, "w").write(db_text(want, paths))
+    idx = C.POINTER(refmod.Index)()
+    assert host.read_index(dbpath.encode(), C.byref(idx)) == 0
+    lsh = host.create_hash_tables(idx)
+    assert lsh
+    queries = []
+    for i in range(8):
+        clip = synth.synth_track(900 + i, 12.0 + 2.5 * i, 1 + i % 2)[3 * 44100 + 321: 8 * 44100 + 321]
+        rc, q = oracle.fingerprint_pcm(clip)
+        assert rc == 0 and len(q)
+        queries.append(np.ascontiguousarray(q))
+    odb = oracle.make_db(want)
+    best = [oracle.search(odb, q)[0] for q in queries]
+    n_nodes = [len(oracle.get_matches(odb, q[0])) for q in queries]
+    assert best == list(range(8))          # every excerpt identifies its own track (serial, CPU oracle)
+    errors = []
+
+    def worker(i):
+        try:
+            for rep in range(3):
+                psig = C.POINTER(refmod.Signatures)()
+                rc = host.generate_fingerprint(paths[i].encode(), C.byref(psig), None, None, None)
+                assert rc == 0, rc
+                got = np.ctypeslib.as_array(C.cast(psig.contents.signatures, C.POINTER(C.c_uint8)),
+                                            (psig.contents.n_signatures, 100)).copy()
+                host.free_signatures(psig)
+                assert np.array_equal(got, want[i]), f"thread {i}: signatures differ"
+                q = queries[(i + rep) % 8]
+                s = refmod.Signatures(len(q), C.cast(q.ctypes.data, C.POINTER(C.c_uint8 * 100)))
+                assert host.search(C.byref(s), idx, lsh, 0) == best[(i + rep) % 8]
+                plist = C.POINTER(refmod.SignatureList)()
+                n = host.get_matches(lsh, q[0].ctypes.data, C.byref(plist))
+                assert n == n_nodes[(i + rep) % 8]
+                host.free_signature_list(plist)
+        except BaseException as e:   # noqa: BLE001 - collected and re-raised on the main thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    host.free_hash_tables(lsh)
+    host.free_index(idx)
+    if errors:
+        raise errors[0]
