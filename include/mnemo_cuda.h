@@ -181,6 +181,12 @@ int64_t mnemo_selftest_logf(mnemo_ctx* ctx, uint32_t lo_bits, uint32_t hi_bits);
  * on its domain (0 or |x| >= 2^-106); 2: (255*v) / max (spectralimages.c:53) for n pseudo-random pairs. */
 int64_t mnemo_selftest_div(mnemo_ctx* ctx, int which, uint32_t lo_bits, uint64_t n);
 
+/* The ranking kernel (search.c:65-107,170-193 on the GPU) on caller-supplied per-entry rows score[q][e], n_matches[q][e]
+ * (n_queries x n_entries, host memory); out[q] as mnemo_search_batch.  entry_base shifts the rows to tree positions
+ * entry_base .. entry_base + n_entries - 1 (the entries below have no matches). */
+int mnemo_selftest_select(mnemo_ctx* ctx, const uint32_t* score, const uint32_t* n_matches, uint32_t n_queries,
+                          uint32_t n_entries, uint32_t entry_base, mnemo_match* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,7 @@ def lib() -> C.CDLL:
         L.mnemo_selftest_logf.restype = C.c_int64
         L.mnemo_selftest_div.argtypes = [vp, i32, u32, u64]
         L.mnemo_selftest_div.restype = C.c_int64
+        L.mnemo_selftest_select.argtypes = [vp, vp, vp, u32, u32, u32, vp]
         if hasattr(L, "mnemo_db_create"):
             L.mnemo_db_create.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(vp)]
             L.mnemo_db_destroy.argtypes = [vp]
@@ -152,6 +153,16 @@ class Context:
 
     def selftest_div(self, which: int, lo_bits: int, n: int) -> int:
         return lib().mnemo_selftest_div(self.h, which, lo_bits, n)
+
+    def selftest_select(self, score: np.ndarray, n_matches: np.ndarray, entry_base: int = 0):
+        """The GPU ranking kernel on dense per-entry rows [n_queries, n_entries] (u32): list of (entry, score, n)."""
+        score = np.ascontiguousarray(score, np.uint32)
+        n_matches = np.ascontiguousarray(n_matches, np.uint32)
+        nq, ne = score.shape
+        out = (Match * max(nq, 1))()
+        self._check(lib().mnemo_selftest_select(self.h, score.ctypes.data, n_matches.ctypes.data, nq, ne, entry_base, out),
+                    "mnemo_selftest_select")
+        return [(out[i].entry, out[i].score, out[i].n_matches) for i in range(nq)]
 
     # -- indexing -------------------------------------------------------------------
     def index_pcm_batch(self, pcms):

@@ -23,7 +23,7 @@ struct mnemo_db {
   struct Scratch {
     void* p = nullptr;
     uint64_t bytes = 0;
-  } scratch[10];
+  } scratch[16];
 };
 
 static cudaError_t scratch_get(mnemo_db* db, int slot, uint64_t bytes, void** out) {
@@ -614,16 +614,131 @@ extern "C" int mnemo_search_finish(const mnemo_cand* cands, uint64_t n_cands, co
   return 0;
 }
 
+// Dense path used by mnemo_search_batch: probe kernel -> per-(query, entry) accumulators -> exact ranking on the GPU
+// (k_select.cu).  Only 12 bytes per query come back to the host, however many entries a query touches.
+static int search_batch_select(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start, uint32_t n_queries,
+                               mnemo_match* out, uint64_t* stats) {
+  mnemo_ctx* ctx = db->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  if (stats) stats[0] = stats[1] = 0;
+  const uint32_t n_qsigs = query_start[n_queries];
+  if (n_qsigs == 0 || db->size == 0 || db->n_sigs == 0 || db->n_entries == 0) return 0;
+  const uint64_t per_query = (uint64_t)db->n_entries * 8;
+  const uint32_t group = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_queries, (1ull << 30) / per_query));
+  const uint32_t n_total = db->entry_base + db->n_entries;   // entries below entry_base have no matches here
+  const uint32_t depth = select_depth(n_total);
+  const uint32_t grid = select_grid(group, ctx->sm_count);
+  uint8_t* d_q = nullptr;
+  uint32_t *d_qstart = nullptr, *d_acc_s = nullptr, *d_acc_n = nullptr, *d_leaf = nullptr;
+  mnemo_lastgroup_dev* d_last = nullptr;
+  unsigned long long* d_stats = nullptr;
+  SelRec* d_sel = nullptr;
+  uint8_t* d_cnt = nullptr;
+  mnemo_match_dev* d_out = nullptr;
+  cudaError_t e = cudaSuccess;
+#define TRY(x)                      \
+  do {                              \
+    if (e == cudaSuccess) e = (x);  \
+  } while (0)
+  TRY(scratch_get(db, 0, (uint64_t)n_qsigs * kSigLen + 4, (void**)&d_q));
+  TRY(scratch_get(db, 1, 4ull * ((uint64_t)n_queries + 1), (void**)&d_qstart));
+  TRY(scratch_get(db, 2, 4ull * group * db->n_entries, (void**)&d_acc_s));
+  TRY(scratch_get(db, 3, 4ull * group * db->n_entries, (void**)&d_acc_n));
+  TRY(scratch_get(db, 4, sizeof(mnemo_lastgroup_dev) * (uint64_t)n_qsigs, (void**)&d_last));
+  TRY(scratch_get(db, 5, 16, (void**)&d_stats));
+  TRY(scratch_get(db, 10, 4ull * ((1ull << depth) + 1), (void**)&d_leaf));
+  TRY(scratch_get(db, 11, sizeof(SelRec) * (uint64_t)grid * n_total, (void**)&d_sel));
+  TRY(scratch_get(db, 12, (uint64_t)grid << depth, (void**)&d_cnt));
+  TRY(scratch_get(db, 13, sizeof(mnemo_match_dev) * (uint64_t)n_queries, (void**)&d_out));
+  TRY(cudaMemcpyAsync(d_q, query_sigs, (uint64_t)n_qsigs * kSigLen, cudaMemcpyHostToDevice, st));
+  TRY(cudaMemsetAsync(d_stats, 0, 16, st));
+  if (e == cudaSuccess) launch_select_bounds(n_total, depth, d_leaf, st);
+  std::vector<uint32_t> h_qstart;
+  for (uint32_t q0 = 0; q0 < n_queries && e == cudaSuccess; q0 += group) {
+    const uint32_t nq = std::min(group, n_queries - q0);
+    h_qstart.assign(query_start + q0, query_start + q0 + nq + 1);
+    const uint32_t s0 = h_qstart[0];
+    for (auto& v : h_qstart) v -= s0;
+    const uint32_t ns = h_qstart[nq];
+    TRY(cudaMemcpyAsync(d_qstart, h_qstart.data(), 4ull * (nq + 1), cudaMemcpyHostToDevice, st));
+    TRY(cudaMemsetAsync(d_acc_s, 0, (uint64_t)nq * db->n_entries * 4, st));
+    TRY(cudaMemsetAsync(d_acc_n, 0, (uint64_t)nq * db->n_entries * 4, st));
+    if (e != cudaSuccess) break;
+    SearchParams p = base_params(db);
+    p.query_sigs = d_q + (uint64_t)s0 * kSigLen;
+    p.query_start = d_qstart;
+    p.n_queries = nq;
+    p.acc_score = d_acc_s;
+    p.acc_n = d_acc_n;
+    p.last = d_last + s0;
+    p.stat_nodes = d_stats;
+    p.stat_deep = d_stats + 1;
+    launch_search(p, ns, st);
+    launch_search_select(d_acc_s, d_acc_n, nq, db->n_entries, db->entry_base, n_total, 0, depth, d_leaf, d_sel, d_cnt,
+                         select_grid(nq, ctx->sm_count), d_out + q0, nullptr, nullptr, st);
+    TRY(cudaGetLastError());
+    if (q0 + group < n_queries) TRY(cudaStreamSynchronize(st));   // h_qstart is reused by the next group
+  }
+  static_assert(sizeof(mnemo_match_dev) == sizeof(mnemo_match), "match layouts");
+  TRY(cudaMemcpyAsync(out, d_out, sizeof(mnemo_match) * (uint64_t)n_queries, cudaMemcpyDeviceToHost, st));
+  TRY(cudaStreamSynchronize(st));
+  if (e == cudaSuccess && stats) {
+    unsigned long long h[2] = {0, 0};
+    TRY(cudaMemcpy(h, d_stats, 16, cudaMemcpyDeviceToHost));
+    stats[0] = h[0];
+    stats[1] = h[1];
+  }
+#undef TRY
+  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_batch");
+  return 0;
+}
+
 extern "C" int mnemo_search_batch(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
                                   uint32_t n_queries, mnemo_match* out, uint64_t* stats) {
-  if (!db || !out) return -3;
+  if (!db || !out || !query_start) return -3;
   for (uint32_t q = 0; q < n_queries; q++) out[q] = mnemo_match{-7, 0.0f, 0};
   if (n_queries == 0) return 0;
-  std::vector<mnemo_cand> cands;
-  const int rc = search_shard_impl(db, query_sigs, query_start, n_queries, cands, nullptr, stats);
-  if (rc != 0) return rc;
-  const uint64_t n = cands.size();
-  return mnemo_search_finish(cands.data(), n, nullptr, 1, query_start, n_queries, db->entry_base + db->n_entries, out);
+  return search_batch_select(db, query_sigs, query_start, n_queries, out, stats);
+}
+
+// Self-test of the ranking kernel on caller-supplied per-entry (score, n_matches) rows [n_queries][n_entries]
+// (tests: adversarial averages for the non-transitive comparator, against the qsort-based restatement).
+extern "C" int mnemo_selftest_select(mnemo_ctx* ctx, const uint32_t* score, const uint32_t* n_matches, uint32_t n_queries,
+                                     uint32_t n_entries, uint32_t entry_base, mnemo_match* out) {
+  if (!ctx || !out || (n_queries && n_entries && (!score || !n_matches))) return -3;
+  for (uint32_t q = 0; q < n_queries; q++) out[q] = mnemo_match{-7, 0.0f, 0};
+  if (n_queries == 0 || n_entries == 0) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const uint32_t n_total = entry_base + n_entries, depth = select_depth(n_total);
+  const uint32_t grid = select_grid(n_queries, ctx->sm_count);
+  const uint64_t cells = (uint64_t)n_queries * n_entries;
+  uint32_t *d_s = nullptr, *d_n = nullptr, *d_leaf = nullptr;
+  SelRec* d_sel = nullptr;
+  uint8_t* d_cnt = nullptr;
+  mnemo_match_dev* d_out = nullptr;
+  cudaError_t e = dalloc(&d_s, cells);
+  if (e == cudaSuccess) e = dalloc(&d_n, cells);
+  if (e == cudaSuccess) e = dalloc(&d_leaf, (1ull << depth) + 1);
+  if (e == cudaSuccess) e = dalloc(&d_sel, (uint64_t)grid * n_total);
+  if (e == cudaSuccess) e = dalloc(&d_cnt, (uint64_t)grid << depth);
+  if (e == cudaSuccess) e = dalloc(&d_out, (uint64_t)n_queries);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_s, score, cells * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, n_matches, cells * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    launch_select_bounds(n_total, depth, d_leaf, st);
+    launch_search_select(d_s, d_n, n_queries, n_entries, entry_base, n_total, 0, depth, d_leaf, d_sel, d_cnt, grid, d_out,
+                         nullptr, nullptr, st);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(mnemo_match) * (uint64_t)n_queries, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  void* ptrs[] = {d_s, d_n, d_leaf, d_sel, d_cnt, d_out};
+  for (void* q : ptrs)
+    if (q) cudaFree(q);
+  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_selftest_select");
+  return 0;
 }
 
 extern "C" int mnemo_result_finish(mnemo_result* r, const uint32_t* query_start, uint32_t n_queries,
@@ -635,7 +750,9 @@ extern "C" int mnemo_result_finish(mnemo_result* r, const uint32_t* query_start,
   cudaError_t e = cudaMemcpy(&h, r->hdr, sizeof h, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_result_finish");
   if (h.count > r->cap) {
-    ctx->err = "mnemo_result_finish: candidate capacity exceeded";
+    char buf[128];
+    snprintf(buf, sizeof buf, "mnemo_result_finish: candidate capacity exceeded (%u records, capacity %u)", h.count, r->cap);
+    ctx->err = buf;
     return -1;
   }
   static_assert(sizeof(CandDev) == sizeof(mnemo_cand) && sizeof(LastRec) == sizeof(mnemo_lastgroup), "record layouts");

@@ -31,6 +31,38 @@ struct LastRec {
   uint32_t has, entry, sig, hits, score;
 };
 
+// ---- final ranking (k_select.cu) ----
+constexpr int kSelTop = 10;   // search.c:175: only the first ten records of the sorted array are looked at
+struct SelRec {
+  int32_t entry;   // global entry index
+  float score;     // sum of deep-check scores (exact below 2^24)
+  int32_t n;       // n_matches (> 0: entries without matches are never stored)
+  float avg;       // score / (float)n, search.c:66-67
+};
+struct mnemo_match_dev {
+  int32_t entry;
+  float score;
+  int32_t n_matches;
+};
+// compare_entry_scores (search.c:65-107) on precomputed averages.  Not a strict weak order: abs() is the integer
+// one, applied to the truncated difference.
+__host__ __device__ inline int cmp_entry_avg(float avg_a, int32_t n_a, float avg_b, int32_t n_b) {
+  int di = (int)(avg_a - avg_b);
+  if (di < 0) di = -di;
+  const float delta = (float)di;
+  if (delta <= 3) {
+    if (delta <= 5 && n_a >= n_b + 5) return -1;
+    if (n_b >= n_a + 5) return 1;
+  }
+  if ((double)delta < 0.5) {
+    if (n_a > n_b) return -1;
+    if (n_a < n_b) return 1;
+  }
+  if (avg_a > avg_b) return -1;
+  if (avg_b > avg_a) return 1;
+  return 0;
+}
+
 struct SearchParams {
   const uint8_t* db_sigs;        // [n_sigs][100]
   const uint32_t* sig_entry;     // [n_sigs] shard-local entry index
@@ -61,5 +93,15 @@ void launch_search_last_push(const mnemo_lastgroup_dev* last, uint32_t n_qsigs, 
                              const uint32_t* entry_start, uint32_t entry_base, LastRec* dst, cudaStream_t st);
 void launch_search_gather(const SearchParams& p, uint32_t* out, uint32_t cap, uint32_t* table_counts, cudaStream_t st);
 uint32_t lsh_scan_blocks(uint64_t n_slots);
+uint32_t select_depth(uint32_t n_total);
+uint32_t select_grid(uint32_t n_queries, int sm_count);
+void launch_select_bounds(uint32_t n_total, uint32_t depth, uint32_t* leaf_lo, cudaStream_t st);
+// Tree over positions [0, n_total); accumulator column of position p is p - first_local (columns outside
+// [0, n_local) are entries without matches); reported entry = entry_offset + p.  out != nullptr: the selected match
+// per query; out_lists != nullptr: the root's list (kSelTop records per query) and its length instead.
+void launch_search_select(const uint32_t* acc_score, const uint32_t* acc_n, uint32_t n_queries, uint32_t n_local,
+                          uint32_t first_local, uint32_t n_total, uint32_t entry_offset, uint32_t depth,
+                          const uint32_t* leaf_lo, SelRec* scratch, uint8_t* cnt_scratch, uint32_t grid,
+                          mnemo_match_dev* out, SelRec* out_lists, uint32_t* out_counts, cudaStream_t st);
 
 }  // namespace mnemo

@@ -156,3 +156,69 @@ def search_sharded_push(ctx, entry_sigs, queries, rank: int, world: int, group=N
     dist.barrier(group=group)              # nobody unmaps before the owner has read
     res.close()
     return out, db
+
+
+class ShardedSearcher:
+    """A database shard per rank plus ONE result buffer kept mapped on every rank (peer memory over NVLink),
+    reused for every query batch of the same size: what a resident search service does.  Per batch the ranks
+    meet at two barriers (buffer cleared / records written); there is no other inter-process traffic.
+
+        s = ShardedSearcher(ctx, my_entry_sigs, table_size, entry_base, n_entries_total, rank, world)
+        results = s.search(prepared_queries)        # list on merge_rank, None elsewhere
+    """
+
+    def __init__(self, ctx, shard_sigs, table_size: int, entry_base: int, n_entries_total: int, rank: int,
+                 world: int, group=None, merge_rank: int = 0):
+        self.ctx, self.rank, self.world, self.group, self.merge_rank = ctx, rank, world, group, merge_rank
+        self.n_entries_total = n_entries_total
+        self.db = capi.Db(ctx, shard_sigs, table_size=table_size, entry_base=entry_base)
+        self.res, self.res_key = None, None
+
+    def _barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
+
+    def _result(self, cap: int, nqs: int):
+        if self.res_key == (cap, nqs):
+            return self.res
+        self._drop_result()
+        if self.world == 1:
+            self.res, _ = capi.Result.create(self.ctx, cap, 1, nqs)
+        else:
+            import torch.distributed as dist
+            box = [None]
+            if self.rank == self.merge_rank:
+                self.res, box[0] = capi.Result.create(self.ctx, cap, self.world, nqs)
+            dist.broadcast_object_list(box, src=self.merge_rank, group=self.group)
+            if self.rank != self.merge_rank:
+                self.res = capi.Result.open(self.ctx, box[0], cap, self.world, nqs)
+        self.res_key = (cap, nqs)
+        return self.res
+
+    def search(self, queries, cap: int | None = None):
+        prepared = queries if isinstance(queries, tuple) else capi.Db.prepare(queries)
+        qstart = prepared[1]
+        nq, nqs = len(qstart) - 1, int(qstart[-1])
+        res = self._result(cap or max(4096, 64 * nq), nqs)
+        if self.rank == self.merge_rank:
+            res.reset()
+        self._barrier()                       # the buffer is cleared (and mapped everywhere)
+        res.push(self.db, prepared, self.rank)
+        self._barrier()                       # every shard's records are in the merging rank's memory
+        return res.finish(qstart, self.n_entries_total) if self.rank == self.merge_rank else None
+
+    def close(self):
+        self._drop_result()
+        self.db.close()
+
+    def _drop_result(self):
+        if self.res is None:
+            return
+        self._barrier()                       # nobody unmaps before the owner has read
+        if self.rank != self.merge_rank:
+            self.res.close()
+        self._barrier()                       # the owner frees once every peer mapping is gone
+        if self.rank == self.merge_rank:
+            self.res.close()
+        self.res, self.res_key = None, None

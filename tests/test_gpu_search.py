@@ -190,3 +190,69 @@ def test_peer_push_merge_equals_single_database(ctx, corpus):
         res.finish(prepared[1], len(sigs))
     res.close()
     sh.close()
+
+
+# ------------------------------------------------------------------ final ranking on the GPU (k_select.cu) ----
+
+def _select_cases(rng, n_cases, sizes, max_m, avgs=None):
+    """Dense (score, n) rows with adversarial averages for search.c:65-107 (differences around 0.5, 3 and 5,
+    match counts around the +5 rule and the 5/10 thresholds)."""
+    rows = []
+    for _ in range(n_cases):
+        E = int(rng.choice(sizes))
+        m = rng.randint(0, min(E, max_m) + 1)
+        idx = np.sort(rng.choice(E, m, replace=False))
+        n = rng.randint(1, 30, m)
+        if avgs is None:
+            avg = rng.choice([30, 31, 33, 34, 35, 36, 37, 38, 40, 44, 50], m) + rng.choice([0, 0.25, 0.5, 0.75], m)
+        else:
+            avg = rng.uniform(*avgs, m)
+        s = np.zeros(E, np.uint32)
+        c = np.zeros(E, np.uint32)
+        s[idx] = np.maximum(np.round(avg * n), 30 * n).astype(np.uint32)
+        c[idx] = n
+        rows.append((s, c))
+    return rows
+
+
+@pytest.mark.gpu
+def test_gpu_ranking_equals_libc_qsort_on_dense_rows(ctx, oracle):
+    """The truncated merge tree of k_select.cu against the oracle's qsort over the dense per-entry array, exactly as
+    the reference sorts it (search.c:170): sparse, dense, more than ten candidates, sizes around powers of two."""
+    rng = np.random.RandomState(11)
+    cases = _select_cases(rng, 1500, [1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 16, 17, 31, 33, 37, 100, 257, 1000, 1023, 1025, 4099], 25)
+    cases += _select_cases(rng, 300, [300, 301, 511, 640], 40, avgs=(30, 42))
+    cases += _select_cases(rng, 200, [64, 100, 999, 2048, 2500], 2500, avgs=(30, 45))        # most entries matched
+    by_size = {}
+    for s, c in cases:
+        by_size.setdefault(len(s), []).append((s, c))
+    for E, group in by_size.items():
+        S = np.stack([g[0] for g in group])
+        N = np.stack([g[1] for g in group])
+        got = ctx.selftest_select(S, N)
+        for k, (s, c) in enumerate(group):
+            want = oracle.select(s.astype(np.float32), c.astype(np.int32))
+            assert got[k][0] == want, (E, k, got[k], want)
+            if want >= 0:
+                assert got[k][1] == float(s[want]) and got[k][2] == int(c[want])
+
+
+@pytest.mark.gpu
+def test_gpu_ranking_comparator_cycle_and_entry_base(ctx, oracle):
+    # SURVEY.md §4(d): A=(40,5), B=(37,10), C=(34,15) form a cycle under search.c:65-107
+    for perm in ([0, 1, 2], [2, 0, 1], [1, 2, 0]):
+        avg = np.array([40, 37, 34])[perm]
+        n = np.array([5, 10, 15])[perm]
+        s = np.zeros(50, np.uint32)
+        c = np.zeros(50, np.uint32)
+        s[[3, 17, 40]] = avg * n
+        c[[3, 17, 40]] = n
+        want = oracle.select(s.astype(np.float32), c.astype(np.int32))
+        assert ctx.selftest_select(s[None], c[None])[0][0] == want
+        # the same rows as the upper part of a larger index range (a shard searched on its own: the entries below
+        # entry_base have no matches but still shape the merge tree)
+        for base in (1, 7, 50, 333):
+            full_s = np.concatenate([np.zeros(base, np.uint32), s])
+            full_c = np.concatenate([np.zeros(base, np.uint32), c])
+            want = oracle.select(full_s.astype(np.float32), full_c.astype(np.int32))
+            assert ctx.selftest_select(s[None], c[None], entry_base=base)[0][0] == want

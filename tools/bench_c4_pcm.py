@@ -1,0 +1,227 @@
+"""BASELINE config #4 from PCM: index M synthetic 30-second tracks, then search M five-second excerpts against
+the resulting database, sharded across the GPUs of one box (contiguous entry ranges, records pushed into the
+merging rank's HBM over NVLink, exact ranking there).
+
+    python tools/bench_c4_pcm.py [--tracks 10000] [--seconds 30]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_c4_pcm.py
+
+Unlike tools/bench_search_c4.py (signature-level random database: almost no bucket collisions, ~100 probed nodes per
+query signature) the signatures here come from audio, so bucket occupancy is what a real database has (thousands of
+probed nodes per query signature at this size).  10 k x 30 s of PCM (26 GB) cannot be synthesised by
+the numpy generator in bench time, so the same recipe (repeating chirp + 3 voices of tone bursts + noise, SURVEY.md
+§8d) is evaluated with torch on the GPU; the PCM then takes the normal route: device -> pinned host -> C ABI
+(mnemo_batch_upload) -> kernels.  Rank 0 runs the unmodified reference (oracle/_ref; measurement tool, the reference
+is the checker) on a sample of queries against the same database and compares the answers.
+"""
+import argparse, ctypes as C, json, math, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from mnemophonix_b200 import capi, dist as mdist
+
+RATE = 44100
+ap = argparse.ArgumentParser()
+ap.add_argument("--tracks", type=int, default=10000)
+ap.add_argument("--seconds", type=float, default=30.0)
+ap.add_argument("--chunk", type=int, default=50)          # tracks synthesised + indexed per step
+ap.add_argument("--ref-queries", type=int, default=8)
+ap.add_argument("--steps", type=int, default=3)
+args = ap.parse_args()
+rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); lr = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(lr)
+dev = torch.device("cuda", lr)
+dist = None
+if world > 1:
+    import torch.distributed as dist
+    sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
+    dist.init_process_group("nccl", device_id=dev)
+    dist.all_reduce(torch.zeros(1, device=dev)); torch.cuda.synchronize()
+    sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+
+
+def synth_gpu(track_ids, seconds):
+    """int16 [B, n] on the GPU; track t is a function of t alone (its own generator seed)."""
+    n = int(round(seconds * RATE))
+    B = len(track_ids)
+    idx = torch.arange(n, device=dev, dtype=torch.float64)
+    t = idx / RATE
+    K = int(math.ceil(seconds / 0.08)) + 1
+    par = torch.empty((B, 3), dtype=torch.float64)
+    seg = torch.empty((B, 3, K, 3), dtype=torch.float64)     # duration, frequency, gain
+    noise = torch.empty((B, n), device=dev, dtype=torch.float32)
+    for i, tid in enumerate(track_ids):
+        g = torch.Generator().manual_seed(1000 + int(tid))
+        u = torch.rand(3, generator=g, dtype=torch.float64)
+        par[i] = torch.stack([2.0 + 3.0 * u[0], 250.0 + 150.0 * u[1], 1500.0 + 700.0 * u[2]])
+        v = torch.rand((3, K, 3), generator=g, dtype=torch.float64)
+        seg[i, :, :, 0] = 0.08 + 0.52 * v[:, :, 0]
+        seg[i, :, :, 1] = 300.0 + 1700.0 * v[:, :, 1]
+        seg[i, :, :, 2] = 0.3 * v[:, :, 2]
+        gg = torch.Generator(device=dev).manual_seed(77000 + int(tid))
+        noise[i] = torch.randn(n, generator=gg, device=dev, dtype=torch.float32)
+    par = par.to(dev); seg = seg.to(dev)
+    period, f0, f1 = par[:, 0:1], par[:, 1:2], par[:, 2:3]
+    tau = torch.remainder(t.unsqueeze(0), period)
+    x = 0.35 * torch.sin(2.0 * math.pi * (f0 * tau + 0.5 * (f1 - f0) / period * tau * tau))
+    del tau
+    ramp = int(0.010 * RATE)
+    for vce in range(3):
+        dur = seg[:, vce, :, 0]
+        start = torch.cumsum(dur, dim=1) - dur                                    # [B, K] seconds
+        s0 = torch.floor(start * RATE)                                            # start sample
+        ln = torch.floor(dur * RATE)
+        which = torch.searchsorted(s0.contiguous(), idx.unsqueeze(0).expand(B, n).contiguous(), right=True) - 1
+        which.clamp_(0, K - 1)
+        k = idx.unsqueeze(0) - torch.gather(s0, 1, which)
+        lnw = torch.gather(ln, 1, which)
+        inside = k < lnw
+        env = torch.clamp(torch.minimum(k, lnw - 1 - k) / ramp, max=1.0)
+        fr = torch.gather(seg[:, vce, :, 1], 1, which)
+        gn = torch.gather(seg[:, vce, :, 2], 1, which)
+        x += torch.where(inside, gn * env * torch.sin(2.0 * math.pi * fr * k / RATE), torch.zeros((), device=dev, dtype=torch.float64))
+        del which, k, lnw, inside, env, fr, gn
+    x += 0.05 * noise.double()
+    x.clamp_(-1.0, 1.0)
+    return torch.round(x * 20000.0).to(torch.int16)
+
+
+# ---- this rank's contiguous range of tracks: synthesise, index, cut the query excerpts ----
+per = (args.tracks + world - 1) // world
+a, b = min(args.tracks, rank * per), min(args.tracks, (rank + 1) * per)
+stream = torch.cuda.Stream()
+ctx = capi.Context(lr, stream.cuda_stream)
+n_frames = int(round(args.seconds * RATE))
+q_off = int(10.0 * RATE) + 1234 if args.seconds < 70 else int(60.0 * RATE) + 1234
+q_len = 5 * RATE
+my_sigs, my_queries = [], []
+t_synth = t_index = 0.0
+for c0 in range(a, b, args.chunk):
+    ids = list(range(c0, min(b, c0 + args.chunk)))
+    t0 = time.perf_counter()
+    pcm = synth_gpu(ids, args.seconds)
+    host = torch.empty(pcm.shape, dtype=torch.int16).pin_memory()
+    host.copy_(pcm); torch.cuda.synchronize()
+    t_synth += time.perf_counter() - t0
+    t0 = time.perf_counter()
+    arr = host.numpy()
+    tracks = [arr[i].reshape(-1, 1) for i in range(len(ids))]
+    sigs, status = ctx.index_pcm_batch(tracks)
+    clips = [np.ascontiguousarray(arr[i, q_off:q_off + q_len]).reshape(-1, 1) for i in range(len(ids))]
+    qs, qstatus = ctx.index_pcm_batch(clips)
+    assert not any(status) and not any(qstatus)
+    my_sigs += sigs; my_queries += qs
+    t_index += time.perf_counter() - t0
+    del pcm, host
+
+counts = torch.zeros(args.tracks, dtype=torch.int64, device=dev)
+counts[a:b] = torch.tensor([len(s) for s in my_sigs], dtype=torch.int64)
+if dist is not None:
+    dist.all_reduce(counts)
+total_sigs = int(counts.sum())
+
+# queries: every rank needs all of them (replicated to all shards): all-gather the signatures
+qcnt = torch.zeros(args.tracks, dtype=torch.int64, device=dev)
+qcnt[a:b] = torch.tensor([len(q) for q in my_queries], dtype=torch.int64)
+if dist is not None:
+    dist.all_reduce(qcnt)
+qcnt = qcnt.cpu().numpy()
+qmax = int(qcnt.max())
+mine = torch.zeros((per, qmax, 100), dtype=torch.uint8)
+for i, q in enumerate(my_queries):
+    mine[i, :len(q)] = torch.from_numpy(np.ascontiguousarray(q))
+if dist is not None:
+    allq = [torch.empty((per, qmax, 100), dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(allq, mine.to(dev))
+    allq = torch.cat(allq)[:args.tracks].cpu().numpy()
+else:
+    allq = mine.numpy()
+queries = [allq[i, :qcnt[i]] for i in range(args.tracks)]
+prepared = capi.Db.prepare(queries)
+n_qsig = int(prepared[1][-1])
+
+t0 = time.perf_counter()
+searcher = mdist.ShardedSearcher(ctx, my_sigs, total_sigs // 2, a, args.tracks, rank, world)
+torch.cuda.synchronize()
+t_build = time.perf_counter() - t0
+
+
+def timed(fn, steps):
+    ts, out = [], None
+    for _ in range(steps):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        ts.append(dt)
+    return float(np.mean(ts)), out
+
+
+cap = min(4096 * args.tracks, 1 << 26)
+if world == 1:
+    # one shard: probe + exact ranking on the GPU (mnemo_search_batch), 12 bytes per query come back
+    searcher.db.search(prepared)
+    dt, res = timed(lambda: searcher.db.search(prepared)[0], args.steps)
+else:
+    searcher.search(prepared, cap=cap)                    # warm-up (allocates and maps the result buffer)
+    dt, res = timed(lambda: searcher.search(prepared, cap=cap), args.steps)
+L = D = 0
+if world == 1:
+    L, D = searcher.db.search(prepared)[1]
+
+breakdown = None
+if rank == 0:
+    got = [r[0] for r in res]
+    line = {"metric": "search queries/s",
+            "config": "BASELINE configs[3] from PCM: %d five-second excerpts x %d-track database (%g s tracks, %d signatures from "
+                      "GPU-synthesised audio), %d GPU(s), peer-memory merge" % (args.tracks, args.tracks, args.seconds, total_sigs, world),
+            "n_gpus": world, "queries": args.tracks, "query_signatures": n_qsig, "queries_per_s": args.tracks / dt,
+            "s_per_batch": dt, "identified_own_track": int(sum(int(g == i) for i, g in enumerate(got))),
+            "no_match": int(sum(int(g < 0) for g in got)), "lsh_build_s_per_shard": t_build,
+            "index_s_this_rank": t_index, "synth_s_this_rank": t_synth}
+    if world == 1:
+        line.update({"breakdown": breakdown, "probed_nodes_per_query_signature": L / n_qsig, "deep_checks_per_query_signature": D / n_qsig,
+                     "algorithmic_GBps": (n_qsig * 300 + 4 * L + 100 * D + 16 * args.tracks) / dt / 1e9})
+    print(json.dumps(line)); sys.stdout.flush()
+
+# ---- reference on a sample (rank 0 needs the whole database for that) ----
+if args.ref_queries:
+    smax = int(counts.max())
+    mine_s = torch.zeros((per, smax, 100), dtype=torch.uint8)
+    for i, s in enumerate(my_sigs):
+        mine_s[i, :len(s)] = torch.from_numpy(np.ascontiguousarray(s))
+    if dist is not None:
+        alls = [torch.empty((per, smax, 100), dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(alls, mine_s.to(dev))
+        alls = torch.cat(alls)[:args.tracks].cpu().numpy()
+    else:
+        alls = mine_s.numpy()
+    if rank == 0:
+        from oracle import ref as refmod
+        if refmod.available():
+            cn = counts.cpu().numpy()
+            r = refmod.Ref()
+            ents = (C.POINTER(refmod.IndexEntry) * args.tracks)()
+            keep = []
+            for i in range(args.tracks):
+                e = np.ascontiguousarray(alls[i, :cn[i]])
+                sg = refmod.Signatures(int(cn[i]), C.cast(e.ctypes.data, C.POINTER(C.c_uint8 * 100)))
+                ie = refmod.IndexEntry(b"t", b"", b"", b"", C.pointer(sg))
+                keep.append((e, sg, ie)); ents[i] = C.pointer(ie)
+            idx = refmod.Index(args.tracks, C.cast(ents, C.POINTER(C.POINTER(refmod.IndexEntry))))
+            t0 = time.perf_counter(); lsh = r.lib.create_hash_tables(C.byref(idx)); t_lsh = time.perf_counter() - t0
+            pick = np.linspace(0, args.tracks - 1, args.ref_queries).astype(int)
+            t0 = time.perf_counter()
+            ref_res = [r.search(np.ascontiguousarray(queries[i]), C.pointer(idx), lsh) for i in pick]
+            t_ref = (time.perf_counter() - t0) / len(pick)
+            print(json.dumps({"ref_create_hash_tables_s": t_lsh, "ref_search_s_per_query": t_ref, "ref_sample": len(pick),
+                              "identical_results_on_sample": ref_res == [got[i] for i in pick]}))
+searcher.close(); ctx.close()
+if dist is not None:
+    dist.destroy_process_group()
