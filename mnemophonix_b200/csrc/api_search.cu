@@ -67,6 +67,9 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
   }
   const uint64_t n_slots = (uint64_t)db->size * kTables;
   uint32_t *d_counts = nullptr, *d_cursor = nullptr, *d_block_sums = nullptr;
+  uint32_t *d_keys_in = nullptr, *d_vals_in = nullptr, *d_keys_out = nullptr;
+  void* d_temp = nullptr;
+  const size_t temp_bytes = (db->size && db->n_sigs) ? lsh_sort_temp_bytes(db->n_sigs, db->size) : 0;
   cudaError_t e = cudaSuccess;
 #define TRY(x)                      \
   do {                              \
@@ -80,13 +83,17 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
   TRY(dalloc(&d_counts, n_slots));
   TRY(dalloc(&d_cursor, n_slots));
   TRY(dalloc(&d_block_sums, (uint64_t)lsh_scan_blocks(n_slots) + 1));
+  TRY(dalloc(&d_keys_in, db->n_sigs * kTables));
+  TRY(dalloc(&d_vals_in, db->n_sigs * kTables));
+  TRY(dalloc(&d_keys_out, db->n_sigs * kTables));
+  TRY(cudaMalloc(&d_temp, temp_bytes ? temp_bytes : 1));
   cudaStream_t st = ctx->stream;
   if (db->n_sigs) TRY(cudaMemcpyAsync(db->d_sigs, sigs, db->n_sigs * kSigLen, cudaMemcpyHostToDevice, st));
   TRY(cudaMemcpyAsync(db->d_entry_start, entry_start, 4ull * (n_entries + 1), cudaMemcpyHostToDevice, st));
   TRY(cudaMemsetAsync(db->d_start, 0, (n_slots + 1) * 4, st));
   if (e == cudaSuccess && db->size && db->n_sigs) {
-    launch_lsh_build(db->d_sigs, db->n_sigs, db->d_entry_start, n_entries, db->size, d_counts, db->d_start, d_cursor,
-                     d_block_sums, db->d_ids, db->d_sig_entry, st);
+    TRY(launch_lsh_build(db->d_sigs, db->n_sigs, db->d_entry_start, n_entries, db->size, d_counts, db->d_start, d_cursor,
+                         d_block_sums, d_keys_in, d_vals_in, d_keys_out, d_temp, temp_bytes, db->d_ids, db->d_sig_entry, st));
     TRY(cudaGetLastError());
   }
   TRY(cudaStreamSynchronize(st));
@@ -94,6 +101,10 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
   cudaFree(d_counts);
   cudaFree(d_cursor);
   cudaFree(d_block_sums);
+  cudaFree(d_keys_in);
+  cudaFree(d_vals_in);
+  cudaFree(d_keys_out);
+  cudaFree(d_temp);
   if (e != cudaSuccess) {
     int rc = mnemo_fail(ctx, e, "mnemo_db_create");
     mnemo_db_destroy(db);
@@ -126,6 +137,7 @@ static SearchParams base_params(const mnemo_db* db) {
   p.ids = db->d_ids;
   p.size = db->size;
   p.n_entries = db->n_entries;
+  p.n_sigs = (uint32_t)db->n_sigs;
   return p;
 }
 

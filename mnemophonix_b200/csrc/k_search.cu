@@ -6,8 +6,10 @@
 // Build.  The reference keeps 25 chained hash tables of `size` = total_signatures/2 heads
 // (lsh.c:61) and inserts every signature under slot = big-endian-u32(bytes 4k..4k+3) % size
 // (lsh.c:49-52,74).  Here each table is a CSR: one histogram pass (global reductions), one
-// exclusive scan over the 25*size counters, one scatter pass.  A bucket holds exactly the
-// members of the reference's chain (collisions through the modulo included).
+// exclusive scan over the 25*size counters, and a STABLE radix sort of the 25*n (bucket, id) pairs
+// (cub::DeviceRadixSort on the build path only), so that every bucket lists its members in ascending
+// id order.  A bucket holds exactly the members of the reference's chain (collisions through the
+// modulo included); the sorted order is what lets the probe kernel walk id ranges (below).
 //
 // Probe + score.  For one query signature the reference concatenates the 25 probed chains,
 // sorts the (entry, signature) pairs, and deep-checks every pair that occurs at least twice,
@@ -24,6 +26,8 @@
 //      buckets and >= 30 equal bytes add (score, 1) to the query's per-entry accumulators.
 // Traffic per query signature = 100 + 25*8 + 4*L + 100*D' bytes, D' = deep checks
 // plus the few bitmap false positives.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
 #include "search_internal.h"
 
@@ -42,14 +46,16 @@ __global__ void __launch_bounds__(256) lsh_count_kernel(const uint32_t* __restri
   atomicAdd(&counts[(uint64_t)(i % kTables) * size + slot], 1u);
 }
 
-__global__ void __launch_bounds__(256) lsh_scatter_kernel(const uint32_t* __restrict__ sig_words, uint64_t n_sigs,
-                                                          uint32_t size, uint32_t* __restrict__ cursor,
-                                                          uint32_t* __restrict__ ids) {
+// sort input: key = global bucket index (table * size + slot), value = signature id; word order is id-major, so
+// equal keys arrive in ascending id order and a stable sort keeps them so
+__global__ void __launch_bounds__(256) lsh_pairs_kernel(const uint32_t* __restrict__ sig_words, uint64_t n_sigs,
+                                                        uint32_t size, uint32_t* __restrict__ keys,
+                                                        uint32_t* __restrict__ vals) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_sigs * kTables) return;
   const uint32_t slot = bucket_key(sig_words[i]) % size;
-  const uint32_t pos = atomicAdd(&cursor[(uint64_t)(i % kTables) * size + slot], 1u);
-  ids[pos] = (uint32_t)(i / kTables);
+  keys[i] = (uint32_t)(i % kTables) * size + slot;
+  vals[i] = (uint32_t)(i / kTables);
 }
 
 __global__ void __launch_bounds__(256) sig_entry_kernel(const uint32_t* __restrict__ entry_start, uint32_t n_entries,
@@ -137,21 +143,39 @@ __global__ void __launch_bounds__(kScanT) scan_apply_kernel(const uint32_t* __re
 
 uint32_t lsh_scan_blocks(uint64_t n_slots) { return (uint32_t)((n_slots + kScanB - 1) / kScanB); }
 
-void launch_lsh_build(const uint8_t* sigs, uint64_t n_sigs, const uint32_t* entry_start, uint32_t n_entries,
-                      uint32_t size, uint32_t* counts, uint32_t* start, uint32_t* cursor, uint32_t* block_sums,
-                      uint32_t* ids, uint32_t* sig_entry, cudaStream_t st) {
+static int key_bits(uint64_t n_slots) {
+  int b = 1;
+  while (b < 32 && (1ull << b) < n_slots) ++b;
+  return b;
+}
+
+size_t lsh_sort_temp_bytes(uint64_t n_sigs, uint32_t size) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int64_t)(n_sigs * kTables), 0, key_bits((uint64_t)size * kTables));
+  return bytes;
+}
+
+// keys_in / vals_in / keys_out: 25*n_sigs u32 each; temp: lsh_sort_temp_bytes()
+cudaError_t launch_lsh_build(const uint8_t* sigs, uint64_t n_sigs, const uint32_t* entry_start, uint32_t n_entries,
+                             uint32_t size, uint32_t* counts, uint32_t* start, uint32_t* scan_copy, uint32_t* block_sums,
+                             uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, void* temp, size_t temp_bytes,
+                             uint32_t* ids, uint32_t* sig_entry, cudaStream_t st) {
   const uint64_t n_words = n_sigs * kTables;
   const uint64_t n_slots = (uint64_t)size * kTables;
-  if (n_sigs == 0 || size == 0) return;
+  if (n_sigs == 0 || size == 0) return cudaSuccess;
   const uint32_t* words = reinterpret_cast<const uint32_t*>(sigs);
   cudaMemsetAsync(counts, 0, n_slots * sizeof(uint32_t), st);
   lsh_count_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(words, n_sigs, size, counts);
   const uint32_t n_blocks = (uint32_t)((n_slots + kScanB - 1) / kScanB);
   scan_reduce_kernel<<<n_blocks, kScanT, 0, st>>>(counts, n_slots, block_sums);
   scan_sums_kernel<<<1, kScanT, 0, st>>>(block_sums, n_blocks);
-  scan_apply_kernel<<<n_blocks, kScanT, 0, st>>>(counts, n_slots, block_sums, start, cursor);
-  lsh_scatter_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(words, n_sigs, size, cursor, ids);
+  scan_apply_kernel<<<n_blocks, kScanT, 0, st>>>(counts, n_slots, block_sums, start, scan_copy);
+  lsh_pairs_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(words, n_sigs, size, keys_in, vals_in);
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const uint32_t*)keys_in, keys_out,
+                                                  (const uint32_t*)vals_in, ids, (int64_t)n_words, 0, key_bits(n_slots), st);
   sig_entry_kernel<<<(unsigned)((n_sigs + 255) / 256), 256, 0, st>>>(entry_start, n_entries, n_sigs, sig_entry);
+  return e;
 }
 
 // ------------------------------------------------------------------ probe + score ----
@@ -162,6 +186,8 @@ constexpr uint32_t kSetCap = 4096;        // hash set slots for de-duplication (
 constexpr uint32_t kBitmapMaxWords = 8192;    // 32 KB: 64 KB of shared memory per CTA in all, 3 CTAs per SM
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kPassCap = 8192;          // candidates per id-space partition (>= 32 bitmap bits each)
+constexpr uint32_t kRangeBits = kBitmapMaxWords * 32;   // ids per pass in range mode: one bitmap bit per id, exact
+constexpr uint32_t kMaxRangePasses = 32;                // range mode serves shards of up to 8.4 M signatures
 
 size_t search_smem_bytes() { return sizeof(uint32_t) * (kBitmapMaxWords + kDupCap + kSetCap + kDupCap); }
 
@@ -185,14 +211,25 @@ __device__ __forceinline__ void check_pair(const uint32_t* __restrict__ db_words
   *score = __reduce_add_sync(0xffffffffu, eq);
 }
 
-__device__ __forceinline__ int table_of(const Probe& pr, uint32_t i) {
+__device__ __forceinline__ int table_of(const uint32_t* prefix, uint32_t i) {
   int k = 0;
 #pragma unroll
   for (int s = 16; s; s >>= 1)
-    if (k + s <= kTables - 1 && pr.prefix[k + s] <= i) k += s;
+    if (k + s <= kTables - 1 && prefix[k + s] <= i) k += s;
   return k;   // largest k with prefix[k] <= i
 }
 
+// id-space partition of the hashed multi-pass mode (multiply-shift: no integer division per candidate)
+__device__ __forceinline__ uint32_t hash_part(uint32_t g, uint32_t n_pass) { return __umulhi(g * 2246822519u, n_pass); }
+
+// Candidate de-duplication has two modes, chosen per query signature:
+//   hashed (L <= kPassCap, the usual case for small databases): one pass, bitmap indexed by a hash of the id with
+//     >= 32 bits per candidate; a collision only costs one extra deep check (hits are recomputed exactly);
+//   id ranges (long candidate lists): buckets are sorted by id, so the candidates with ids in
+//     [pass * kRangeBits, (pass + 1) * kRangeBits) are one contiguous piece of each of the 25 lists, found by binary
+//     search; each pass streams just those through a bitmap with one bit per id (exact, no false repeats).  Every
+//     candidate id is read once however long the lists are, and passes without candidates cost nothing.
+//   (Shards beyond kMaxRangePasses * kRangeBits signatures fall back to hashed partitions that re-stream the lists.)
 __global__ void __launch_bounds__(kSearchThreads, 3)
     search_probe_kernel(SearchParams p) {
   extern __shared__ __align__(16) uint32_t sm[];
@@ -201,6 +238,8 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
   uint32_t* set = dup + kDupCap;
   uint32_t* uniq = set + kSetCap;
   __shared__ Probe pr;
+  __shared__ uint32_t seg_begin[kTables], seg_prefix[kTables + 1];   // this pass's piece of each list
+  __shared__ uint32_t s_bound[kTables][kMaxRangePasses + 1];
   __shared__ uint32_t s_ndup, s_nuniq, s_gmax;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -231,37 +270,95 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
     if (tid == 0) p.last[qs] = lg;
     return;
   }
-  // Candidates are handled in n_pass partitions of the id space (one for ordinary list lengths) so
-  // that the bitmap stays sparse; each partition re-streams the ids (4 bytes each).
-  const uint32_t n_pass = (L + kPassCap - 1) / kPassCap;
+  const uint32_t range_passes = (p.n_sigs + kRangeBits - 1) / kRangeBits;
+  const bool range_mode = L > kPassCap && range_passes <= kMaxRangePasses;   // block-uniform
+  const uint32_t n_pass = range_mode ? range_passes : (L + kPassCap - 1) / kPassCap;
   const uint32_t per_pass = (L + n_pass - 1) / n_pass;
-  uint32_t bm_words = 64;   // ~64 bitmap bits per candidate, 256 B .. 32 KB
+  uint32_t bm_words = 64;   // hashed mode: ~64 bitmap bits per candidate, 256 B .. 32 KB
   while (bm_words < kBitmapMaxWords && bm_words < 2 * per_pass) bm_words <<= 1;
+  if (range_mode) bm_words = kBitmapMaxWords;
   const uint32_t bm_shift = 32 - (31 - __clz(bm_words * 32));
   const uint32_t* __restrict__ dbw = reinterpret_cast<const uint32_t*>(p.db_sigs);
   uint32_t deep = 0, gmax = 0;
 
+  if (range_mode) {
+    // the greatest candidate id is the greatest last element of the sorted lists
+    if (warp == 0) {
+      uint32_t v = 0;
+      if (lane < kTables) {
+        const uint32_t len = pr.prefix[lane + 1] - pr.prefix[lane];
+        if (len) v = __ldg(p.ids + pr.begin[lane] + len - 1);
+      }
+      v = __reduce_max_sync(0xffffffffu, v);
+      if (lane == 0) s_gmax = v;
+    }
+    // where each id range starts in each list
+    for (uint32_t t = tid; t < kTables * (range_passes + 1); t += kSearchThreads) {
+      const uint32_t k = t / (range_passes + 1), j = t - k * (range_passes + 1);
+      const uint32_t len = pr.prefix[k + 1] - pr.prefix[k];
+      const uint32_t* __restrict__ lst = p.ids + pr.begin[k];
+      const uint32_t target = j * kRangeBits;
+      uint32_t lo = 0, hi = len;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(lst + mid) < target) lo = mid + 1;
+        else hi = mid;
+      }
+      s_bound[k][j] = lo;
+    }
+    __syncthreads();
+  }
+
   for (uint32_t pass = 0; pass < n_pass; ++pass) {
-    for (uint32_t i = tid; i < bm_words; i += kSearchThreads) bitmap[i] = 0;
+    if (tid < kTables) {
+      if (range_mode) {
+        const uint32_t b = s_bound[tid][pass], e = s_bound[tid][pass + 1];
+        seg_begin[tid] = pr.begin[tid] + b;
+        seg_prefix[tid + 1] = e - b;
+      } else {
+        seg_begin[tid] = pr.begin[tid];
+        seg_prefix[tid + 1] = pr.prefix[tid + 1] - pr.prefix[tid];
+      }
+    }
     if (tid == 0) {
+      seg_prefix[0] = 0;
       s_ndup = 0;
       s_nuniq = 0;
     }
     __syncthreads();
-    for (uint32_t i = tid; i < L; i += kSearchThreads) {
-      const int k = table_of(pr, i);
-      const uint32_t g = __ldg(p.ids + pr.begin[k] + (i - pr.prefix[k]));
-      if (pass == 0) gmax = max(gmax, g);
-      if (n_pass > 1 && ((g * 2246822519u) >> 7) % n_pass != pass) continue;
-      const uint32_t h = (g * 2654435761u) >> bm_shift;
-      const uint32_t bit = 1u << (h & 31u);
-      const uint32_t old = atomicOr(&bitmap[h >> 5], bit);
-      if (old & bit) {
-        const uint32_t pos = atomicAdd(&s_ndup, 1u);
-        if (pos < kDupCap) dup[pos] = g;
+    if (tid == 0)
+      for (int k = 0; k < kTables; ++k) seg_prefix[k + 1] += seg_prefix[k];
+    __syncthreads();
+    const uint32_t Lp = seg_prefix[kTables];
+    if (range_mode && Lp < 2) {   // nothing can repeat in this id range
+      __syncthreads();            // (everyone has read Lp before the next pass rewrites the segments)
+      continue;
+    }
+    for (uint32_t i = tid; i < bm_words / 4; i += kSearchThreads) reinterpret_cast<uint4*>(bitmap)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    {
+      const uint32_t id_base = pass * kRangeBits;
+      uint32_t k = 0;
+      for (uint32_t i = tid; i < Lp; i += kSearchThreads) {
+        while (i >= seg_prefix[k + 1]) ++k;   // i only grows: amortised O(25) per thread
+        const uint32_t g = __ldg(p.ids + seg_begin[k] + (i - seg_prefix[k]));
+        uint32_t h;
+        if (range_mode) {
+          h = g - id_base;
+        } else {
+          if (pass == 0) gmax = max(gmax, g);
+          if (n_pass > 1 && hash_part(g, n_pass) != pass) continue;
+          h = (g * 2654435761u) >> bm_shift;
+        }
+        const uint32_t bit = 1u << (h & 31u);
+        const uint32_t old = atomicOr(&bitmap[h >> 5], bit);
+        if (old & bit) {
+          const uint32_t pos = atomicAdd(&s_ndup, 1u);
+          if (pos < kDupCap) dup[pos] = g;
+        }
       }
     }
-    if (pass == 0) {
+    if (!range_mode && pass == 0) {
       gmax = __reduce_max_sync(0xffffffffu, gmax);
       if (lane == 0) atomicMax(&s_gmax, gmax);
     }
@@ -307,11 +404,11 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
       // More repeats than the short list holds (pathological buckets): no list at all.  One warp
       // per candidate recomputes the exact shared-bucket mask from the signature, and the pair is
       // scored only from its lowest matching table, i.e. exactly once.
-      for (uint32_t i = warp; i < L; i += kSearchThreads / 32) {
-        const int k = table_of(pr, i);
-        const uint32_t g = __ldg(p.ids + pr.begin[k] + (i - pr.prefix[k]));
+      for (uint32_t i = warp; i < Lp; i += kSearchThreads / 32) {
+        const int k = table_of(seg_prefix, i);
+        const uint32_t g = __ldg(p.ids + seg_begin[k] + (i - seg_prefix[k]));
         if (g == gmax) continue;
-        if (n_pass > 1 && ((g * 2246822519u) >> 7) % n_pass != pass) continue;
+        if (!range_mode && n_pass > 1 && hash_part(g, n_pass) != pass) continue;
         uint32_t h = 0, eq = 0;
         if (lane < kTables) {
           const uint32_t w = __ldg(dbw + (uint64_t)g * kTables + lane);

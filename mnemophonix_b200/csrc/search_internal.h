@@ -70,6 +70,7 @@ struct SearchParams {
   const uint32_t* ids;           // [25*n_sigs]
   uint32_t size;                 // lsh.c:61 (global)
   uint32_t n_entries;            // entries in this shard
+  uint32_t n_sigs;               // signatures in this shard
   const uint8_t* query_sigs;     // [n_query_sigs][100]
   const uint32_t* query_start;   // [n_queries + 1]
   uint32_t n_queries;
@@ -80,9 +81,11 @@ struct SearchParams {
   unsigned long long* stat_deep;
 };
 
-void launch_lsh_build(const uint8_t* sigs, uint64_t n_sigs, const uint32_t* entry_start, uint32_t n_entries,
-                      uint32_t size, uint32_t* counts, uint32_t* start, uint32_t* cursor, uint32_t* block_sums,
-                      uint32_t* ids, uint32_t* sig_entry, cudaStream_t st);
+size_t lsh_sort_temp_bytes(uint64_t n_sigs, uint32_t size);
+cudaError_t launch_lsh_build(const uint8_t* sigs, uint64_t n_sigs, const uint32_t* entry_start, uint32_t n_entries,
+                             uint32_t size, uint32_t* counts, uint32_t* start, uint32_t* scan_copy, uint32_t* block_sums,
+                             uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, void* temp, size_t temp_bytes,
+                             uint32_t* ids, uint32_t* sig_entry, cudaStream_t st);
 void launch_search(const SearchParams& p, uint32_t n_query_sigs, cudaStream_t st);
 void launch_search_compact(const uint32_t* acc_score, const uint32_t* acc_n, uint32_t n_queries, uint32_t n_entries,
                            uint32_t entry_base, CandDev* cands, uint32_t cap, uint32_t* total, uint32_t* q_base,

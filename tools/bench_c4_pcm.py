@@ -26,6 +26,7 @@ ap.add_argument("--seconds", type=float, default=30.0)
 ap.add_argument("--chunk", type=int, default=50)          # tracks synthesised + indexed per step
 ap.add_argument("--ref-queries", type=int, default=8)
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--queries", type=int, default=0)         # 0 = one excerpt per track; else only the first N (profiling)
 args = ap.parse_args()
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); lr = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr)
@@ -135,7 +136,8 @@ if dist is not None:
     allq = torch.cat(allq)[:args.tracks].cpu().numpy()
 else:
     allq = mine.numpy()
-queries = [allq[i, :qcnt[i]] for i in range(args.tracks)]
+n_q = args.queries or args.tracks
+queries = [allq[i, :qcnt[i]] for i in range(n_q)]
 prepared = capi.Db.prepare(queries)
 n_qsig = int(prepared[1][-1])
 
@@ -181,13 +183,13 @@ if rank == 0:
     line = {"metric": "search queries/s",
             "config": "BASELINE configs[3] from PCM: %d five-second excerpts x %d-track database (%g s tracks, %d signatures from "
                       "GPU-synthesised audio), %d GPU(s), peer-memory merge" % (args.tracks, args.tracks, args.seconds, total_sigs, world),
-            "n_gpus": world, "queries": args.tracks, "query_signatures": n_qsig, "queries_per_s": args.tracks / dt,
+            "n_gpus": world, "queries": n_q, "query_signatures": n_qsig, "queries_per_s": n_q / dt,
             "s_per_batch": dt, "identified_own_track": int(sum(int(g == i) for i, g in enumerate(got))),
             "no_match": int(sum(int(g < 0) for g in got)), "lsh_build_s_per_shard": t_build,
             "index_s_this_rank": t_index, "synth_s_this_rank": t_synth}
     if world == 1:
         line.update({"breakdown": breakdown, "probed_nodes_per_query_signature": L / n_qsig, "deep_checks_per_query_signature": D / n_qsig,
-                     "algorithmic_GBps": (n_qsig * 300 + 4 * L + 100 * D + 16 * args.tracks) / dt / 1e9})
+                     "algorithmic_GBps": (n_qsig * 300 + 4 * L + 100 * D + 16 * n_q) / dt / 1e9})
     print(json.dumps(line)); sys.stdout.flush()
 
 # ---- reference on a sample (rank 0 needs the whole database for that) ----
@@ -216,7 +218,7 @@ if args.ref_queries:
                 keep.append((e, sg, ie)); ents[i] = C.pointer(ie)
             idx = refmod.Index(args.tracks, C.cast(ents, C.POINTER(C.POINTER(refmod.IndexEntry))))
             t0 = time.perf_counter(); lsh = r.lib.create_hash_tables(C.byref(idx)); t_lsh = time.perf_counter() - t0
-            pick = np.linspace(0, args.tracks - 1, args.ref_queries).astype(int)
+            pick = np.linspace(0, n_q - 1, args.ref_queries).astype(int)
             t0 = time.perf_counter()
             ref_res = [r.search(np.ascontiguousarray(queries[i]), C.pointer(idx), lsh) for i in pick]
             t_ref = (time.perf_counter() - t0) / len(pick)
