@@ -136,6 +136,7 @@ static SearchParams base_params(const mnemo_db* db) {
   p.start = db->d_start;
   p.ids = db->d_ids;
   p.size = db->size;
+  p.size_magic = db->size ? 0xFFFFFFFFFFFFFFFFull / db->size + 1 : 0;
   p.n_entries = db->n_entries;
   p.n_sigs = (uint32_t)db->n_sigs;
   return p;

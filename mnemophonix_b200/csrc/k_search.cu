@@ -37,6 +37,13 @@ namespace mnemo {
 
 __device__ __forceinline__ uint32_t bucket_key(uint32_t word_le) { return __byte_perm(word_le, 0, 0x0123); }
 
+// x % d for 32-bit x and d without a division (Lemire's fastmod; exact for every 32-bit pair):
+// magic = 0xFFFFFFFFFFFFFFFF / d + 1, x % d = hi64((magic * x mod 2^64) * d).  `size` is fixed per database, so the
+// host computes the magic once; the probe kernel takes 25 remainders per deep-checked signature.
+__device__ __forceinline__ uint32_t fastmod(uint32_t x, uint64_t magic, uint32_t d) {
+  return (uint32_t)__umul64hi(magic * (uint64_t)x, (uint64_t)d);
+}
+
 // one thread per (signature, table)
 __global__ void __launch_bounds__(256) lsh_count_kernel(const uint32_t* __restrict__ sig_words, uint64_t n_sigs,
                                                         uint32_t size, uint32_t* __restrict__ counts) {
@@ -200,11 +207,11 @@ struct Probe {
 
 // Deep check of one database signature against the query, by one warp.  Returns (hits, score).
 __device__ __forceinline__ void check_pair(const uint32_t* __restrict__ db_words, uint32_t g, const Probe& pr,
-                                           uint32_t size, int lane, uint32_t* hits, uint32_t* score) {
+                                           uint32_t size, uint64_t magic, int lane, uint32_t* hits, uint32_t* score) {
   uint32_t h = 0, eq = 0;
   if (lane < kTables) {
     const uint32_t w = __ldg(db_words + (uint64_t)g * kTables + lane);
-    h = (bucket_key(w) % size) == pr.qslot[lane];
+    h = fastmod(bucket_key(w), magic, size) == pr.qslot[lane];
     eq = __popc(__vcmpeq4(w, pr.qword[lane])) >> 3;   // search.c:35-43: number of equal bytes
   }
   *hits = __popc(__ballot_sync(0xffffffffu, h));
@@ -248,7 +255,7 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
 
   if (tid < kTables) {
     const uint32_t w = qwords[tid];
-    const uint32_t slot = bucket_key(w) % p.size;
+    const uint32_t slot = fastmod(bucket_key(w), p.size_magic, p.size);
     pr.qword[tid] = w;
     pr.qslot[tid] = slot;
     const uint32_t b = p.start[(uint64_t)tid * p.size + slot], e = p.start[(uint64_t)tid * p.size + slot + 1];
@@ -279,7 +286,7 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
   if (range_mode) bm_words = kBitmapMaxWords;
   const uint32_t bm_shift = 32 - (31 - __clz(bm_words * 32));
   const uint32_t* __restrict__ dbw = reinterpret_cast<const uint32_t*>(p.db_sigs);
-  uint32_t deep = 0, gmax = 0;
+  uint32_t deep = 0, deep_t = 0, gmax = 0;   // deep checks counted per warp (fallback path) / per thread
 
   if (range_mode) {
     // the greatest candidate id is the greatest last element of the sorted lists
@@ -338,16 +345,25 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
     __syncthreads();
     {
       const uint32_t id_base = pass * kRangeBits;
-      uint32_t k = 0;
-      for (uint32_t i = tid; i < Lp; i += kSearchThreads) {
-        while (i >= seg_prefix[k + 1]) ++k;   // i only grows: amortised O(25) per thread
-        const uint32_t g = __ldg(p.ids + seg_begin[k] + (i - seg_prefix[k]));
+      // flat index over the pass's candidates; the thread's position in the segment table only moves forward, and
+      // four loads are in flight before the first id is used
+      uint32_t k = 0, seg_end = seg_prefix[1];
+      const uint32_t* src = p.ids + seg_begin[0];   // src + i addresses candidate i while i < seg_end
+      auto locate = [&](uint32_t i) -> const uint32_t* {
+        while (i >= seg_end) {
+          ++k;
+          seg_end = seg_prefix[k + 1];
+          src = p.ids + seg_begin[k] - seg_prefix[k];
+        }
+        return src + i;
+      };
+      auto visit = [&](uint32_t g) {
         uint32_t h;
         if (range_mode) {
           h = g - id_base;
         } else {
           if (pass == 0) gmax = max(gmax, g);
-          if (n_pass > 1 && hash_part(g, n_pass) != pass) continue;
+          if (n_pass > 1 && hash_part(g, n_pass) != pass) return;
           h = (g * 2654435761u) >> bm_shift;
         }
         const uint32_t bit = 1u << (h & 31u);
@@ -356,7 +372,20 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
           const uint32_t pos = atomicAdd(&s_ndup, 1u);
           if (pos < kDupCap) dup[pos] = g;
         }
+      };
+      uint32_t i = tid;
+      for (; i + 3 * kSearchThreads < Lp; i += 4 * kSearchThreads) {
+        const uint32_t* a0 = locate(i);
+        const uint32_t* a1 = locate(i + kSearchThreads);
+        const uint32_t* a2 = locate(i + 2 * kSearchThreads);
+        const uint32_t* a3 = locate(i + 3 * kSearchThreads);
+        const uint32_t g0 = __ldg(a0), g1 = __ldg(a1), g2 = __ldg(a2), g3 = __ldg(a3);
+        visit(g0);
+        visit(g1);
+        visit(g2);
+        visit(g3);
       }
+      for (; i < Lp; i += kSearchThreads) visit(__ldg(locate(i)));
     }
     if (!range_mode && pass == 0) {
       gmax = __reduce_max_sync(0xffffffffu, gmax);
@@ -386,14 +415,26 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
       }
       __syncthreads();
       const uint32_t nuniq = s_nuniq;
-      for (uint32_t i = warp; i < nuniq; i += kSearchThreads / 32) {
+      // One THREAD per distinct id: its 25 words are loaded back to back (25 loads in flight per thread, 256
+      // signatures per CTA at once; a warp-per-signature loop kept 8 in flight and waited on each), the query's
+      // words and slots are shared-memory broadcasts.  The 4 sectors of a 100-byte row are fetched once and then hit
+      // in L1 for the row's other words.
+      for (uint32_t i = tid; i < nuniq; i += kSearchThreads) {
         const uint32_t g = uniq[i];
         if (g == gmax) continue;   // search.c:147-165: the last group is never flushed
-        uint32_t hits, score;
-        check_pair(dbw, g, pr, p.size, lane, &hits, &score);
+        const uint32_t* __restrict__ row = dbw + (uint64_t)g * kTables;
+        uint32_t w[kTables];
+#pragma unroll
+        for (int k = 0; k < kTables; ++k) w[k] = __ldg(row + k);
+        uint32_t hits = 0, score = 0;
+#pragma unroll
+        for (int k = 0; k < kTables; ++k) {
+          hits += fastmod(bucket_key(w[k]), p.size_magic, p.size) == pr.qslot[k];
+          score += __popc(__vcmpeq4(w[k], pr.qword[k])) >> 3;   // search.c:35-43: number of equal bytes
+        }
         if (hits >= 2) {           // MIN_BUCKET_MATCH_FOR_DEEP_CHECK (search.c:11)
-          ++deep;
-          if (score >= 30 && lane == 0) {   // MIN_SCORE (search.c:16)
+          ++deep_t;
+          if (score >= 30) {       // MIN_SCORE (search.c:16)
             const uint64_t a = (uint64_t)query * p.n_entries + p.sig_entry[g];
             atomicAdd(&p.acc_score[a], score);
             atomicAdd(&p.acc_n[a], 1u);
@@ -412,7 +453,7 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
         uint32_t h = 0, eq = 0;
         if (lane < kTables) {
           const uint32_t w = __ldg(dbw + (uint64_t)g * kTables + lane);
-          h = (bucket_key(w) % p.size) == pr.qslot[lane];
+          h = fastmod(bucket_key(w), p.size_magic, p.size) == pr.qslot[lane];
           eq = __popc(__vcmpeq4(w, pr.qword[lane])) >> 3;
         }
         const uint32_t mask = __ballot_sync(0xffffffffu, h);
@@ -431,7 +472,7 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
   }
   if (warp == 0) {
     uint32_t hits, score;
-    check_pair(dbw, gmax, pr, p.size, lane, &hits, &score);
+    check_pair(dbw, gmax, pr, p.size, p.size_magic, lane, &hits, &score);
     if (lane == 0) {
       lg.has = 1;
       lg.g = gmax;
@@ -440,6 +481,7 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
       p.last[qs] = lg;
     }
   }
+  deep += __reduce_add_sync(0xffffffffu, deep_t);
   if (lane == 0) {
     if (deep) atomicAdd(p.stat_deep, (unsigned long long)deep);
     if (warp == 0) atomicAdd(p.stat_nodes, (unsigned long long)L);

@@ -69,6 +69,7 @@ struct SearchParams {
   const uint32_t* start;         // [25*size + 1] CSR offsets into ids
   const uint32_t* ids;           // [25*n_sigs]
   uint32_t size;                 // lsh.c:61 (global)
+  uint64_t size_magic;           // 0xFFFFFFFFFFFFFFFF / size + 1 (fastmod, k_search.cu)
   uint32_t n_entries;            // entries in this shard
   uint32_t n_sigs;               // signatures in this shard
   const uint8_t* query_sigs;     // [n_query_sigs][100]
