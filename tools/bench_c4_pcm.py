@@ -26,6 +26,8 @@ ap.add_argument("--seconds", type=float, default=30.0)
 ap.add_argument("--chunk", type=int, default=50)          # tracks synthesised + indexed per step
 ap.add_argument("--ref-queries", type=int, default=8)
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--cache", default="")                    # single GPU: keep / reuse the corpus signatures in this .npz
+ap.add_argument("--l-hist", type=int, default=0)          # sample this many query signatures: distribution of L
 ap.add_argument("--queries", type=int, default=0)         # 0 = one excerpt per track; else only the first N (profiling)
 args = ap.parse_args()
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); lr = int(os.environ.get("LOCAL_RANK", 0))
@@ -96,7 +98,13 @@ q_off = int(10.0 * RATE) + 1234 if args.seconds < 70 else int(60.0 * RATE) + 123
 q_len = 5 * RATE
 my_sigs, my_queries = [], []
 t_synth = t_index = 0.0
-for c0 in range(a, b, args.chunk):
+cached = bool(args.cache) and world == 1 and os.path.exists(args.cache)
+if cached:
+    z = np.load(args.cache)
+    zs, zst, zq, zqst = z["sigs"], z["start"], z["qsigs"], z["qstart"]     # (an NpzFile re-reads the array on every access)
+    my_sigs = [zs[zst[i]:zst[i + 1]] for i in range(len(zst) - 1)]
+    my_queries = [zq[zqst[i]:zqst[i + 1]] for i in range(len(zqst) - 1)]
+for c0 in ([] if cached else range(a, b, args.chunk)):
     ids = list(range(c0, min(b, c0 + args.chunk)))
     t0 = time.perf_counter()
     pcm = synth_gpu(ids, args.seconds)
@@ -114,6 +122,9 @@ for c0 in range(a, b, args.chunk):
     t_index += time.perf_counter() - t0
     del pcm, host
 
+if args.cache and world == 1 and not cached:
+    np.savez(args.cache, sigs=np.concatenate(my_sigs), start=np.cumsum([0] + [len(x) for x in my_sigs]),
+             qsigs=np.concatenate(my_queries), qstart=np.cumsum([0] + [len(x) for x in my_queries]))
 counts = torch.zeros(args.tracks, dtype=torch.int64, device=dev)
 counts[a:b] = torch.tensor([len(s) for s in my_sigs], dtype=torch.int64)
 if dist is not None:
@@ -178,6 +189,24 @@ if world == 1:
     L, D = searcher.db.search(prepared)[1]
 
 breakdown = None
+l_hist = None
+if args.l_hist and world == 1:
+    rs = np.random.RandomState(5)
+    pick_q = rs.randint(0, n_qsig, args.l_hist)
+    one = np.empty((1, 2), np.uint32)
+    Ls = np.array([capi.lib().mnemo_db_get_matches(searcher.db.h, np.ascontiguousarray(prepared[0][i]).ctypes.data,
+                                                   one.ctypes.data, 1) for i in pick_q], dtype=np.int64)
+    # time the heaviest and the lightest sampled signatures as single-signature queries
+    order = np.argsort(Ls)
+    def t_one(ix):
+        q = [prepared[0][pick_q[ix]][None, :]]
+        searcher.db.search(q); torch.cuda.synchronize(); t0 = time.perf_counter(); searcher.db.search(q); torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3
+    l_hist = {"n": int(len(Ls)), "mean": float(Ls.mean()), "p50": float(np.percentile(Ls, 50)), "p90": float(np.percentile(Ls, 90)),
+              "p99": float(np.percentile(Ls, 99)), "max": int(Ls.max()), "share_of_nodes_in_top_1pct": float(np.sort(Ls)[-max(1, len(Ls) // 100):].sum() / Ls.sum()),
+              "ms_single_sig_query_lightest": t_one(order[0]), "ms_single_sig_query_median": t_one(order[len(order) // 2]),
+              "ms_single_sig_query_p99": t_one(order[int(len(order) * 0.99)]), "ms_single_sig_query_heaviest": t_one(order[-1]),
+              "L_lightest": int(Ls[order[0]]), "L_median": int(Ls[order[len(order) // 2]]), "L_p99": int(Ls[order[int(len(order) * 0.99)]])}
 if rank == 0:
     got = [r[0] for r in res]
     line = {"metric": "search queries/s",
@@ -188,7 +217,7 @@ if rank == 0:
             "no_match": int(sum(int(g < 0) for g in got)), "lsh_build_s_per_shard": t_build,
             "index_s_this_rank": t_index, "synth_s_this_rank": t_synth}
     if world == 1:
-        line.update({"breakdown": breakdown, "probed_nodes_per_query_signature": L / n_qsig, "deep_checks_per_query_signature": D / n_qsig,
+        line.update({"L_distribution": l_hist, "probed_nodes_per_query_signature": L / n_qsig, "deep_checks_per_query_signature": D / n_qsig,
                      "algorithmic_GBps": (n_qsig * 300 + 4 * L + 100 * D + 16 * n_q) / dt / 1e9})
     print(json.dumps(line)); sys.stdout.flush()
 
