@@ -152,6 +152,31 @@ int mnemo_search_finish(const mnemo_cand* cands, uint64_t n_cands, const mnemo_l
                         uint32_t n_shards, const uint32_t* query_start, uint32_t n_queries,
                         uint32_t n_entries_total, mnemo_match* out);
 
+/* Sharded search ranked on the GPUs (search.c:170-193 needs only the first ten records of glibc's merge sort over all
+ * entries; every node of that merge tree can be ranked where its entries live).  The database is sharded on node
+ * boundaries of the tree: mnemo_tree_cuts fills cuts[n_shards + 1] (entry ranges of the shards) and node_lo[n_nodes + 1]
+ * (entry ranges of the n_nodes = 2^ceil(log2 n_shards) nodes, contiguous groups of which make up the shards) and
+ * returns n_nodes.  Per query batch: mnemo_search_dense_begin probes this shard (accumulators stay on the device) and
+ * reports has[s] = the shard holds a candidate for query signature s; after the ranks have exchanged those flags,
+ * mnemo_search_dense_lists takes has_higher[s] = some shard with greater entry indices has a candidate (the globally
+ * greatest (entry, signature) group, which search.c:147-165 never scores, then lives there and this shard's own greatest
+ * group is scored after all), ranks each of the shard's nodes (node_bounds[n_nodes + 1], global entry indices) and
+ * returns lists_out[node][query][10] + counts_out[node][query].  mnemo_select_merge (host) merges the lists of all
+ * n_nodes nodes, in node order, through the top levels of the tree and applies the thresholds. */
+typedef struct mnemo_sel_rec {
+  int32_t entry;      /* global entry index */
+  float score;
+  int32_t n_matches;
+  float avg;          /* score / n_matches (search.c:66-67) */
+} mnemo_sel_rec;
+uint32_t mnemo_tree_cuts(uint32_t n_entries_total, uint32_t n_shards, uint32_t* cuts, uint32_t* node_lo, uint32_t node_cap);
+int mnemo_search_dense_begin(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start, uint32_t n_queries,
+                             uint8_t* has_out /* one per query signature */, uint64_t* stats);
+int mnemo_search_dense_lists(mnemo_db* db, const uint8_t* has_higher, const uint32_t* node_bounds, uint32_t n_nodes,
+                             mnemo_sel_rec* lists_out, uint32_t* counts_out);
+int mnemo_select_merge(const mnemo_sel_rec* lists, const uint32_t* counts, uint32_t n_nodes, uint32_t n_queries,
+                       mnemo_match* out);
+
 /* Peer-memory merge (one process per GPU, NVLink): instead of returning its records to the host, a shard's
  * search epilogue writes them straight into a result buffer in the HBM of the rank that merges.  The owner
  * creates the buffer and hands the 64-byte CUDA IPC handle to the other ranks (any host channel); they open

@@ -83,6 +83,11 @@ def lib() -> C.CDLL:
         L.mnemo_selftest_div.argtypes = [vp, i32, u32, u64]
         L.mnemo_selftest_div.restype = C.c_int64
         L.mnemo_selftest_select.argtypes = [vp, vp, vp, u32, u32, u32, vp]
+        L.mnemo_tree_cuts.argtypes = [u32, u32, vp, vp, u32]
+        L.mnemo_tree_cuts.restype = u32
+        L.mnemo_search_dense_begin.argtypes = [vp, vp, vp, u32, vp, vp]
+        L.mnemo_search_dense_lists.argtypes = [vp, vp, vp, u32, vp, vp]
+        L.mnemo_select_merge.argtypes = [vp, vp, u32, u32, vp]
         if hasattr(L, "mnemo_db_create"):
             L.mnemo_db_create.argtypes = [vp, vp, vp, u32, u32, u32, C.POINTER(vp)]
             L.mnemo_db_destroy.argtypes = [vp]
@@ -346,6 +351,31 @@ class Db:
         self.ctx._check(rc, "mnemo_search_batch")
         return [(out[i].entry, out[i].score, out[i].n_matches) for i in range(nq)], (stats[0], stats[1])
 
+    # -- sharded search ranked on the GPUs (DESIGN.md "search, multi-GPU") --
+    def dense_begin(self, queries):
+        """Probe this shard; the accumulators stay on the device.  Returns (has[n_query_sigs] u8, (L, D))."""
+        qs, qstart = queries if isinstance(queries, tuple) else _concat(queries)
+        nq, nqs = len(qstart) - 1, int(qstart[-1])
+        has = np.zeros(max(nqs, 1), np.uint8)
+        stats = (C.c_uint64 * 2)()
+        buf = qs if qs.shape[0] else np.zeros((1, SIG_LEN), np.uint8)
+        rc = lib().mnemo_search_dense_begin(self.h, buf.ctypes.data, qstart.ctypes.data, nq, has.ctypes.data, stats)
+        self.ctx._check(rc, "mnemo_search_dense_begin")
+        self._dense_nq = nq
+        return has[:nqs], (stats[0], stats[1])
+
+    def dense_lists(self, has_higher, node_bounds):
+        """Fix-up + ranking of this shard's nodes.  Returns (lists [n_nodes, nq, 10] SEL_DTYPE, counts [n_nodes, nq])."""
+        node_bounds = np.ascontiguousarray(node_bounds, np.uint32)
+        n_nodes, nq = len(node_bounds) - 1, self._dense_nq
+        lists = np.zeros((n_nodes, max(nq, 1), 10), SEL_DTYPE)
+        counts = np.zeros((n_nodes, max(nq, 1)), np.uint32)
+        hh = None if has_higher is None else np.ascontiguousarray(has_higher, np.uint8)
+        rc = lib().mnemo_search_dense_lists(self.h, None if hh is None else hh.ctypes.data, node_bounds.ctypes.data, n_nodes,
+                                            lists.ctypes.data, counts.ctypes.data)
+        self.ctx._check(rc, "mnemo_search_dense_lists")
+        return lists[:, :nq], counts[:, :nq]
+
     def search_shard(self, queries, cap: int | None = None):
         """Per-shard candidate records + last-group records, as numpy structured arrays."""
         qs, qstart = queries if isinstance(queries, tuple) else _concat(queries)
@@ -418,6 +448,33 @@ class Result:
             self.close()
         except Exception:
             pass
+
+
+SEL_DTYPE = np.dtype([("entry", "<i4"), ("score", "<f4"), ("n_matches", "<i4"), ("avg", "<f4")])
+
+
+def tree_cuts(n_entries_total: int, n_shards: int):
+    """Entry ranges of shards that sit on node boundaries of the ranking tree: (cuts[n_shards+1], node_lo[n_nodes+1])."""
+    n_nodes = 1
+    while n_nodes < n_shards:
+        n_nodes *= 2
+    cuts = np.zeros(n_shards + 1, np.uint32)
+    node_lo = np.zeros(n_nodes + 1, np.uint32)
+    got = lib().mnemo_tree_cuts(n_entries_total, n_shards, cuts.ctypes.data, node_lo.ctypes.data, n_nodes + 1)
+    assert got == n_nodes
+    return cuts, node_lo
+
+
+def select_merge(lists: np.ndarray, counts: np.ndarray):
+    """lists [n_nodes, nq, 10] SEL_DTYPE of ALL nodes in node order, counts [n_nodes, nq] -> [(entry, score, n)] per query."""
+    lists = np.ascontiguousarray(lists, SEL_DTYPE)
+    counts = np.ascontiguousarray(counts, np.uint32)
+    n_nodes, nq = counts.shape
+    out = (Match * max(nq, 1))()
+    rc = lib().mnemo_select_merge(lists.ctypes.data, counts.ctypes.data, n_nodes, nq, out)
+    if rc != 0:
+        raise MnemoError(f"mnemo_select_merge: {ERRORS.get(rc, rc)}")
+    return [(out[i].entry, out[i].score, out[i].n_matches) for i in range(nq)]
 
 
 CAND_DTYPE = np.dtype([("query", "<u4"), ("entry", "<i4"), ("score", "<f4"), ("n_matches", "<i4")])

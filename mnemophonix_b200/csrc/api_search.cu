@@ -24,6 +24,7 @@ struct mnemo_db {
     void* p = nullptr;
     uint64_t bytes = 0;
   } scratch[16];
+  uint32_t dense_nq = 0, dense_nqs = 0;   // query batch held on the device between mnemo_search_dense_begin / _lists
 };
 
 static cudaError_t scratch_get(mnemo_db* db, int slot, uint64_t bytes, void** out) {
@@ -713,6 +714,219 @@ extern "C" int mnemo_search_batch(mnemo_db* db, const uint8_t* query_sigs, const
   for (uint32_t q = 0; q < n_queries; q++) out[q] = mnemo_match{-7, 0.0f, 0};
   if (n_queries == 0) return 0;
   return search_batch_select(db, query_sigs, query_start, n_queries, out, stats);
+}
+
+// ------------------------------------------------------------------ sharded search, ranked on the GPUs ----
+// The database is sharded on node boundaries of the ranking tree (mnemo_tree_cuts), so every shard can rank its own
+// subtrees exactly (k_select.cu) and hand over kSelTop records per query and node instead of one record per matched
+// entry.  Protocol per query batch (mnemophonix_b200/dist.py drives it):
+//   1. every rank: mnemo_search_dense_begin  -> probe kernel into dense accumulators kept on the device;
+//                                               has[s] = this shard holds a candidate for query signature s
+//   2. all-gather of the has flags (n_query_signatures bytes per rank: the path's small exchange step)
+//   3. every rank: mnemo_search_dense_lists  -> last-group fix-up where a higher shard holds candidates, ranking of each
+//                                               owned node, lists + counts to the host
+//   4. all-gather of the lists, mnemo_select_merge on the merging rank (top levels of the tree + thresholds).
+
+extern "C" uint32_t mnemo_tree_cuts(uint32_t n_entries_total, uint32_t n_shards, uint32_t* cuts, uint32_t* node_lo,
+                                    uint32_t node_cap) {
+  if (n_shards == 0) return 0;
+  uint32_t depth = 0;
+  while ((1u << depth) < n_shards) ++depth;
+  const uint32_t n_nodes = 1u << depth;
+  std::vector<uint32_t> lo(n_nodes + 1);
+  for (uint32_t i = 0; i < n_nodes; i++) {   // msort's split: n -> n/2 | n - n/2
+    uint32_t l = 0, n = n_entries_total;
+    for (int b = (int)depth - 1; b >= 0; --b) {
+      const uint32_t n1 = n / 2;
+      if ((i >> b) & 1u) {
+        l += n1;
+        n -= n1;
+      } else {
+        n = n1;
+      }
+    }
+    lo[i] = l;
+  }
+  lo[n_nodes] = n_entries_total;
+  if (node_lo)
+    for (uint32_t i = 0; i <= n_nodes && i < node_cap; i++) node_lo[i] = lo[i];
+  if (cuts)
+    for (uint32_t r = 0; r <= n_shards; r++) cuts[r] = lo[(uint64_t)r * n_nodes / n_shards];   // contiguous node groups
+  return n_nodes;
+}
+
+extern "C" int mnemo_search_dense_begin(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
+                                        uint32_t n_queries, uint8_t* has_out, uint64_t* stats) {
+  if (!db || !query_start || !has_out) return -3;
+  mnemo_ctx* ctx = db->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  if (stats) stats[0] = stats[1] = 0;
+  const uint32_t n_qsigs = query_start[n_queries];
+  db->dense_nq = n_queries;
+  db->dense_nqs = n_qsigs;
+  memset(has_out, 0, n_qsigs);
+  if (n_queries == 0 || n_qsigs == 0 || db->size == 0 || db->n_sigs == 0 || db->n_entries == 0) return 0;
+  const uint64_t cells = (uint64_t)n_queries * db->n_entries;
+  if (cells * 8 > (8ull << 30)) {
+    ctx->err = "mnemo_search_dense_begin: query batch x shard entries exceeds 8 GiB of accumulators; send smaller batches";
+    return -1;
+  }
+  uint8_t *d_q = nullptr, *d_has = nullptr;
+  uint32_t *d_qstart = nullptr, *d_acc_s = nullptr, *d_acc_n = nullptr;
+  mnemo_lastgroup_dev* d_last = nullptr;
+  unsigned long long* d_stats = nullptr;
+  cudaError_t e = cudaSuccess;
+#define TRY(x)                      \
+  do {                              \
+    if (e == cudaSuccess) e = (x);  \
+  } while (0)
+  TRY(scratch_get(db, 0, (uint64_t)n_qsigs * kSigLen + 4, (void**)&d_q));
+  TRY(scratch_get(db, 1, 4ull * ((uint64_t)n_queries + 1), (void**)&d_qstart));
+  TRY(scratch_get(db, 2, 4ull * cells, (void**)&d_acc_s));
+  TRY(scratch_get(db, 3, 4ull * cells, (void**)&d_acc_n));
+  TRY(scratch_get(db, 4, sizeof(mnemo_lastgroup_dev) * (uint64_t)n_qsigs, (void**)&d_last));
+  TRY(scratch_get(db, 5, 16, (void**)&d_stats));
+  TRY(scratch_get(db, 14, n_qsigs, (void**)&d_has));
+  TRY(cudaMemcpyAsync(d_q, query_sigs, (uint64_t)n_qsigs * kSigLen, cudaMemcpyHostToDevice, st));
+  TRY(cudaMemcpyAsync(d_qstart, query_start, 4ull * (n_queries + 1), cudaMemcpyHostToDevice, st));
+  TRY(cudaMemsetAsync(d_stats, 0, 16, st));
+  TRY(cudaMemsetAsync(d_acc_s, 0, cells * 4, st));
+  TRY(cudaMemsetAsync(d_acc_n, 0, cells * 4, st));
+  if (e == cudaSuccess) {
+    SearchParams p = base_params(db);
+    p.query_sigs = d_q;
+    p.query_start = d_qstart;
+    p.n_queries = n_queries;
+    p.acc_score = d_acc_s;
+    p.acc_n = d_acc_n;
+    p.last = d_last;
+    p.stat_nodes = d_stats;
+    p.stat_deep = d_stats + 1;
+    launch_search(p, n_qsigs, st);
+    launch_search_has(d_last, n_qsigs, d_has, st);
+    TRY(cudaGetLastError());
+  }
+  TRY(cudaMemcpyAsync(has_out, d_has, n_qsigs, cudaMemcpyDeviceToHost, st));
+  TRY(cudaStreamSynchronize(st));
+  if (e == cudaSuccess && stats) {
+    unsigned long long h[2] = {0, 0};
+    TRY(cudaMemcpy(h, d_stats, 16, cudaMemcpyDeviceToHost));
+    stats[0] = h[0];
+    stats[1] = h[1];
+  }
+#undef TRY
+  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_dense_begin");
+  return 0;
+}
+
+extern "C" int mnemo_search_dense_lists(mnemo_db* db, const uint8_t* has_higher, const uint32_t* node_bounds,
+                                        uint32_t n_nodes, mnemo_sel_rec* lists_out, uint32_t* counts_out) {
+  if (!db || !node_bounds || !lists_out || !counts_out) return -3;
+  mnemo_ctx* ctx = db->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const uint32_t n_queries = db->dense_nq, n_qsigs = db->dense_nqs;
+  for (uint64_t i = 0; i < (uint64_t)n_nodes * n_queries; i++) counts_out[i] = 0;
+  if (n_queries == 0 || n_nodes == 0) return 0;
+  if (node_bounds[0] != db->entry_base || node_bounds[n_nodes] != db->entry_base + db->n_entries) {
+    ctx->err = "mnemo_search_dense_lists: the nodes do not tile this shard's entry range";
+    return -3;
+  }
+  if (n_qsigs == 0 || db->size == 0 || db->n_sigs == 0 || db->n_entries == 0) return 0;
+  uint8_t *d_hh = nullptr, *d_cnt = nullptr;
+  uint32_t *d_leaf = nullptr, *d_counts = nullptr;
+  SelRec *d_sel = nullptr, *d_lists = nullptr;
+  uint32_t max_n = 0;
+  for (uint32_t i = 0; i < n_nodes; i++) max_n = std::max(max_n, node_bounds[i + 1] - node_bounds[i]);
+  const uint32_t max_depth = select_depth(max_n ? max_n : 1);
+  const uint32_t grid = select_grid(n_queries, ctx->sm_count);
+  cudaError_t e = cudaSuccess;
+#define TRY(x)                      \
+  do {                              \
+    if (e == cudaSuccess) e = (x);  \
+  } while (0)
+  TRY(scratch_get(db, 15, n_qsigs, (void**)&d_hh));
+  TRY(scratch_get(db, 10, 4ull * ((1ull << max_depth) + 1), (void**)&d_leaf));
+  TRY(scratch_get(db, 11, sizeof(SelRec) * (uint64_t)grid * (max_n ? max_n : 1), (void**)&d_sel));
+  TRY(scratch_get(db, 12, (uint64_t)grid << max_depth, (void**)&d_cnt));
+  TRY(scratch_get(db, 13, (sizeof(SelRec) * kSelTop + 4) * (uint64_t)n_queries, (void**)&d_lists));
+  d_counts = reinterpret_cast<uint32_t*>(d_lists + (uint64_t)n_queries * kSelTop);
+  uint32_t* d_qstart = (uint32_t*)db->scratch[1].p;
+  uint32_t* d_acc_s = (uint32_t*)db->scratch[2].p;
+  uint32_t* d_acc_n = (uint32_t*)db->scratch[3].p;
+  mnemo_lastgroup_dev* d_last = (mnemo_lastgroup_dev*)db->scratch[4].p;
+  if (has_higher) {
+    TRY(cudaMemcpyAsync(d_hh, has_higher, n_qsigs, cudaMemcpyHostToDevice, st));
+    if (e == cudaSuccess)
+      launch_search_fixup(d_last, d_hh, n_qsigs, d_qstart, n_queries, db->d_sig_entry, db->n_entries, d_acc_s, d_acc_n, st);
+  }
+  static_assert(sizeof(SelRec) == sizeof(mnemo_sel_rec), "record layouts");
+  for (uint32_t i = 0; i < n_nodes && e == cudaSuccess; i++) {
+    const uint32_t lo = node_bounds[i], n = node_bounds[i + 1] - lo;
+    if (n == 0) continue;
+    const uint32_t depth = select_depth(n);
+    launch_select_bounds(n, depth, d_leaf, st);
+    // tree over the node's own entries: position p <-> accumulator column (lo - entry_base) + p, global entry lo + p
+    launch_search_select(d_acc_s + (lo - db->entry_base), d_acc_n + (lo - db->entry_base), n_queries, db->n_entries, 0, n, lo,
+                         depth, d_leaf, d_sel, d_cnt, grid, nullptr, d_lists, d_counts, st);
+    TRY(cudaGetLastError());
+    TRY(cudaMemcpyAsync(lists_out + (uint64_t)i * n_queries * kSelTop, d_lists, sizeof(SelRec) * (uint64_t)n_queries * kSelTop,
+                        cudaMemcpyDeviceToHost, st));
+    TRY(cudaMemcpyAsync(counts_out + (uint64_t)i * n_queries, d_counts, 4ull * n_queries, cudaMemcpyDeviceToHost, st));
+    TRY(cudaStreamSynchronize(st));   // d_lists / d_leaf are reused by the next node
+  }
+#undef TRY
+  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_dense_lists");
+  return 0;
+}
+
+// Top levels of the ranking tree on the host: lists[node][query][kSelTop] of the 2^depth nodes (in node order) are
+// merged pairwise exactly as glibc's merge sort would merge the nodes' sorted ranges, truncated to the first ten;
+// then search.c:173-185.
+extern "C" int mnemo_select_merge(const mnemo_sel_rec* lists, const uint32_t* counts, uint32_t n_nodes, uint32_t n_queries,
+                                  mnemo_match* out) {
+  if (!out || (n_queries && n_nodes && (!lists || !counts))) return -3;
+  if (n_nodes & (n_nodes - 1)) return -3;
+  std::vector<mnemo_sel_rec> cur, nxt;
+  std::vector<uint32_t> ccnt, ncnt;
+  for (uint32_t q = 0; q < n_queries; q++) {
+    out[q] = mnemo_match{-7, 0.0f, 0};
+    if (n_nodes == 0) continue;
+    cur.assign((size_t)n_nodes * kSelTop, mnemo_sel_rec{0, 0.0f, 0, 0.0f});
+    ccnt.assign(n_nodes, 0);
+    for (uint32_t i = 0; i < n_nodes; i++) {
+      ccnt[i] = std::min<uint32_t>(counts[(uint64_t)i * n_queries + q], kSelTop);
+      for (uint32_t k = 0; k < ccnt[i]; k++) cur[(size_t)i * kSelTop + k] = lists[((uint64_t)i * n_queries + q) * kSelTop + k];
+    }
+    for (uint32_t m = n_nodes; m > 1; m >>= 1) {
+      nxt.assign((size_t)(m / 2) * kSelTop, mnemo_sel_rec{0, 0.0f, 0, 0.0f});
+      ncnt.assign(m / 2, 0);
+      for (uint32_t i = 0; i < m / 2; i++) {
+        const mnemo_sel_rec* A = &cur[(size_t)(2 * i) * kSelTop];
+        const mnemo_sel_rec* B = &cur[(size_t)(2 * i + 1) * kSelTop];
+        const uint32_t ca = ccnt[2 * i], cb = ccnt[2 * i + 1];
+        uint32_t ia = 0, ib = 0, w = 0;
+        mnemo_sel_rec* O = &nxt[(size_t)i * kSelTop];
+        while (w < (uint32_t)kSelTop && ia < ca && ib < cb)
+          O[w++] = cmp_entry_avg(A[ia].avg, A[ia].n_matches, B[ib].avg, B[ib].n_matches) <= 0 ? A[ia++] : B[ib++];
+        while (w < (uint32_t)kSelTop && ia < ca) O[w++] = A[ia++];
+        while (w < (uint32_t)kSelTop && ib < cb) O[w++] = B[ib++];
+        ncnt[i] = w;
+      }
+      cur.swap(nxt);
+      ccnt.swap(ncnt);
+    }
+    float best_avg = 0.0f;
+    for (uint32_t k = 0; k < ccnt[0]; k++) {
+      const mnemo_sel_rec& r = cur[k];
+      if ((r.n_matches >= 10 || (r.avg >= 35.0f && r.n_matches >= 5)) && r.avg >= 30.0f && r.avg > best_avg) {
+        best_avg = r.avg;
+        out[q] = mnemo_match{r.entry, r.score, r.n_matches};
+      }
+    }
+  }
+  return 0;
 }
 
 // Self-test of the ranking kernel on caller-supplied per-entry (score, n_matches) rows [n_queries][n_entries]

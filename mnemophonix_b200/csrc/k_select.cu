@@ -142,6 +142,43 @@ __global__ void __launch_bounds__(kSelThreads)
   }
 }
 
+// Sharded search: a shard's own last group (search.c:147-165 drops the greatest (entry, signature) candidate of a query
+// signature) has to be scored after all whenever a HIGHER shard holds a candidate for that query signature, because
+// then the globally greatest candidate lives there.  One thread per query signature.
+__global__ void __launch_bounds__(256) search_fixup_kernel(const mnemo_lastgroup_dev* __restrict__ last,
+                                                           const uint8_t* __restrict__ has_higher, uint32_t n_qsigs,
+                                                           const uint32_t* __restrict__ query_start, uint32_t n_queries,
+                                                           const uint32_t* __restrict__ sig_entry, uint32_t n_entries,
+                                                           uint32_t* __restrict__ acc_score, uint32_t* __restrict__ acc_n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_qsigs) return;
+  const mnemo_lastgroup_dev l = last[i];
+  if (!l.has || !has_higher[i]) return;
+  if (l.hits >= 2 && l.score >= 30) {   // search.c:11,16
+    const uint32_t q = find_segment<uint32_t>(query_start, n_queries, i);
+    const uint64_t a = (uint64_t)q * n_entries + sig_entry[l.g];
+    atomicAdd(&acc_score[a], l.score);
+    atomicAdd(&acc_n[a], 1u);
+  }
+}
+
+__global__ void __launch_bounds__(256) search_has_kernel(const mnemo_lastgroup_dev* __restrict__ last, uint32_t n_qsigs,
+                                                         uint8_t* __restrict__ has) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_qsigs) has[i] = last[i].has ? 1 : 0;
+}
+
+void launch_search_fixup(const mnemo_lastgroup_dev* last, const uint8_t* has_higher, uint32_t n_qsigs,
+                         const uint32_t* query_start, uint32_t n_queries, const uint32_t* sig_entry, uint32_t n_entries,
+                         uint32_t* acc_score, uint32_t* acc_n, cudaStream_t st) {
+  if (n_qsigs)
+    search_fixup_kernel<<<(n_qsigs + 255) / 256, 256, 0, st>>>(last, has_higher, n_qsigs, query_start, n_queries, sig_entry,
+                                                               n_entries, acc_score, acc_n);
+}
+void launch_search_has(const mnemo_lastgroup_dev* last, uint32_t n_qsigs, uint8_t* has, cudaStream_t st) {
+  if (n_qsigs) search_has_kernel<<<(n_qsigs + 255) / 256, 256, 0, st>>>(last, n_qsigs, has);
+}
+
 uint32_t select_depth(uint32_t n_total) {   // depth at which every node holds one or two entries
   uint32_t d = 0;
   while (((uint64_t)2 << d) < n_total) ++d;   // 2^(d+1) >= n_total

@@ -97,6 +97,10 @@ void launch_search_last_push(const mnemo_lastgroup_dev* last, uint32_t n_qsigs, 
                              const uint32_t* entry_start, uint32_t entry_base, LastRec* dst, cudaStream_t st);
 void launch_search_gather(const SearchParams& p, uint32_t* out, uint32_t cap, uint32_t* table_counts, cudaStream_t st);
 uint32_t lsh_scan_blocks(uint64_t n_slots);
+void launch_search_fixup(const mnemo_lastgroup_dev* last, const uint8_t* has_higher, uint32_t n_qsigs,
+                         const uint32_t* query_start, uint32_t n_queries, const uint32_t* sig_entry, uint32_t n_entries,
+                         uint32_t* acc_score, uint32_t* acc_n, cudaStream_t st);
+void launch_search_has(const mnemo_lastgroup_dev* last, uint32_t n_qsigs, uint8_t* has, cudaStream_t st);
 uint32_t select_depth(uint32_t n_total);
 uint32_t select_grid(uint32_t n_queries, int sm_count);
 void launch_select_bounds(uint32_t n_total, uint32_t depth, uint32_t* leaf_lo, cudaStream_t st);

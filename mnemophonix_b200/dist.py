@@ -222,3 +222,60 @@ class ShardedSearcher:
         if self.rank == self.merge_rank:
             self.res.close()
         self.res, self.res_key = None, None
+
+
+class RankedShardedSearcher:
+    """Sharded search with the ranking done where the entries live (k_select.cu): shards sit on node boundaries of
+    the reference's merge-sort tree, each rank ranks its own nodes on its GPU and contributes ten records per query
+    and node.  Two small all-gathers per batch (NCCL on GPU tensors; gloo on CPU tensors in tests): one byte per
+    query signature ("this shard holds a candidate"), then the lists.  Every rank returns the results.
+
+        cuts, node_lo = capi.tree_cuts(n_entries_total, world)       # rank r owns entries cuts[r] .. cuts[r+1]-1
+        s = RankedShardedSearcher(ctx, sigs_of_my_entries, table_size, n_entries_total, rank, world, device)
+        results = s.search(prepared_queries)
+    """
+
+    def __init__(self, ctx, shard_sigs, table_size: int, n_entries_total: int, rank: int, world: int, device="cpu",
+                 group=None):
+        self.ctx, self.rank, self.world, self.device, self.group = ctx, rank, world, device, group
+        self.cuts, self.node_lo = capi.tree_cuts(n_entries_total, world)
+        n_nodes = len(self.node_lo) - 1
+        self.node_range = (rank * n_nodes // world, (rank + 1) * n_nodes // world)     # my nodes
+        a, b = int(self.cuts[rank]), int(self.cuts[rank + 1])
+        assert len(shard_sigs) == b - a, "shard does not match capi.tree_cuts"
+        self.db = capi.Db(ctx, shard_sigs, table_size=table_size, entry_base=a)
+
+    def _all_gather(self, arr: np.ndarray):
+        """Equal-shaped numpy arrays from every rank, in rank order."""
+        if self.world == 1:
+            return [arr]
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).to(self.device)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t, group=self.group)
+        return [o.cpu().numpy().view(arr.dtype).reshape(arr.shape) for o in out]
+
+    def search(self, queries):
+        prepared = queries if isinstance(queries, tuple) else capi.Db.prepare(queries)
+        has, _ = self.db.dense_begin(prepared)
+        all_has = self._all_gather(has)                                   # the exchange step: 1 byte per query signature
+        higher = np.zeros_like(has)
+        for r in range(self.rank + 1, self.world):
+            higher |= all_has[r]
+        n0, n1 = self.node_range
+        lists, counts = self.db.dense_lists(higher, self.node_lo[n0:n1 + 1])
+        # ranks may own different numbers of nodes (world not a power of two): pad to the largest for the all-gather
+        n_nodes = len(self.node_lo) - 1
+        per = max((r + 1) * n_nodes // self.world - r * n_nodes // self.world for r in range(self.world))
+        nq = counts.shape[1]
+        pl = np.zeros((per, nq, 10), capi.SEL_DTYPE)
+        pc = np.zeros((per, nq), np.uint32)
+        pl[:n1 - n0], pc[:n1 - n0] = lists, counts
+        gl, gc = self._all_gather(pl), self._all_gather(pc)
+        all_l = np.concatenate([gl[r][:(r + 1) * n_nodes // self.world - r * n_nodes // self.world] for r in range(self.world)])
+        all_c = np.concatenate([gc[r][:(r + 1) * n_nodes // self.world - r * n_nodes // self.world] for r in range(self.world)])
+        return capi.select_merge(all_l, all_c)
+
+    def close(self):
+        self.db.close()

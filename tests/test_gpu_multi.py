@@ -42,6 +42,14 @@ def _worker(rank, world, port, out):
     res_push, _ = mdist.search_sharded_push(ctx, sigs, qs + [sigs[7]], rank, world, db=db)   # NVLink peer-memory merge
     if rank == 0:
         assert res_push == res
+    # ranked on the GPUs: shards on node boundaries of the ranking tree, two small all-gathers (dist.RankedShardedSearcher)
+    cuts, _ = capi.tree_cuts(len(sigs), world)
+    total = sum(len(x) for x in sigs)
+    ranked = mdist.RankedShardedSearcher(ctx, sigs[int(cuts[rank]):int(cuts[rank + 1])], total // 2, len(sigs), rank, world,
+                                         device=torch.device("cuda", rank))
+    res_ranked = ranked.search(qs + [sigs[7]])
+    ranked.close()
+    assert res_ranked == [tuple(r) for r in res] or res_ranked == res, (res_ranked, res)
     if rank == 0:
         out.put(([len(s) for s in sigs], res, [np.asarray(s).tobytes() for s in sigs], [np.asarray(q).tobytes() for q in qs]))
     dist.barrier()

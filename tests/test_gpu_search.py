@@ -256,3 +256,38 @@ def test_gpu_ranking_comparator_cycle_and_entry_base(ctx, oracle):
             full_c = np.concatenate([np.zeros(base, np.uint32), c])
             want = oracle.select(full_s.astype(np.float32), full_c.astype(np.int32))
             assert ctx.selftest_select(s[None], c[None], entry_base=base)[0][0] == want
+
+
+@pytest.mark.gpu
+def test_ranked_shards_equal_single_database(ctx, oracle, corpus):
+    """Sharded search ranked on the GPU (dist.RankedShardedSearcher's protocol, all shards in this process): shards on
+    node boundaries of the ranking tree, one `has` byte per query signature exchanged, the last group of every shard
+    but the highest one with candidates scored after all, ten records per query and node merged on the host."""
+    sigs, qs = corpus
+    queries = qs + [sigs[2]]
+    total = sum(len(s) for s in sigs)
+    single = capi.Db(ctx, sigs)
+    want, _ = single.search(queries)
+    single.close()
+    odb = oracle.make_db(sigs)
+    assert [w[0] for w in want] == [oracle.search(odb, q)[0] for q in queries]
+    prepared = capi.Db.prepare(queries)
+    for world in (1, 2, 3, 4, 8):
+        cuts, node_lo = capi.tree_cuts(len(sigs), world)
+        n_nodes = len(node_lo) - 1
+        shards = [capi.Db(ctx, sigs[int(cuts[r]):int(cuts[r + 1])], table_size=total // 2, entry_base=int(cuts[r]))
+                  for r in range(world)]
+        has = [s.dense_begin(prepared)[0] for s in shards]
+        lists, counts = [], []
+        for r, s in enumerate(shards):
+            higher = np.zeros_like(has[r])
+            for o in range(r + 1, world):
+                higher |= has[o]
+            n0, n1 = r * n_nodes // world, (r + 1) * n_nodes // world
+            l, c = s.dense_lists(higher, node_lo[n0:n1 + 1])
+            lists.append(l)
+            counts.append(c)
+        got = capi.select_merge(np.concatenate(lists), np.concatenate(counts))
+        assert got == want, world
+        for s in shards:
+            s.close()

@@ -77,3 +77,75 @@ def test_last_group_merge_across_shards():
     assert res[0][0] == -7
     last[0, 0]["hits"] = 1                             # a single bucket hit is never deep-checked
     assert capi.search_finish(cands, last, 2, qstart, 8)[0][0] == -7
+
+
+# ---- ranking tree: ten records per node are enough, and shards on node boundaries can be merged (host parts) ----
+
+def _cmp(a, b):
+    """search.c:65-107 on (avg float32, n)."""
+    d = abs(int(np.float32(a[0]) - np.float32(b[0])))
+    if d <= 3:
+        if a[1] >= b[1] + 5:
+            return -1
+        if b[1] >= a[1] + 5:
+            return 1
+    if d < 0.5:
+        if a[1] > b[1]:
+            return -1
+        if a[1] < b[1]:
+            return 1
+    if a[0] > b[0]:
+        return -1
+    if b[0] > a[0]:
+        return 1
+    return 0
+
+
+def _node_list(s, c, lo, n, top=10):
+    """First `top` matched records of glibc's merge sort over positions lo .. lo+n-1 (split n/2 | n - n/2, left head
+    taken when cmp <= 0), computed from the children's first `top` only."""
+    if n <= 0:
+        return []
+    if n == 1:
+        return [(np.float32(s[lo]) / np.float32(c[lo]), int(c[lo]), lo, float(s[lo]))] if c[lo] else []
+    n1 = n // 2
+    A, B = _node_list(s, c, lo, n1, top), _node_list(s, c, lo + n1, n - n1, top)
+    out, ia, ib = [], 0, 0
+    while len(out) < top and ia < len(A) and ib < len(B):
+        if _cmp(A[ia], B[ib]) <= 0:
+            out.append(A[ia]); ia += 1
+        else:
+            out.append(B[ib]); ib += 1
+    while len(out) < top and ia < len(A):
+        out.append(A[ia]); ia += 1
+    while len(out) < top and ib < len(B):
+        out.append(B[ib]); ib += 1
+    return out
+
+
+def test_node_lists_of_tree_aligned_shards_merge_to_the_reference_selection(oracle):
+    rng = np.random.RandomState(21)
+    for trial in range(400):
+        E = int(rng.choice([1, 2, 3, 5, 8, 9, 16, 31, 100, 257, 1000]))
+        m = rng.randint(0, E + 1) if trial % 3 else rng.randint(0, min(E, 12) + 1)
+        idx = np.sort(rng.choice(E, m, replace=False))
+        n = rng.randint(1, 30, m)
+        avg = rng.choice([30, 31, 33, 34, 35, 36, 37, 38, 40, 44, 50], m) + rng.choice([0, 0.25, 0.5, 0.75], m)
+        s = np.zeros(E, np.float32)
+        c = np.zeros(E, np.int32)
+        s[idx] = np.maximum(np.round(avg * n), 30 * n)
+        c[idx] = n
+        want = oracle.select(s, c)
+        for shards in (1, 2, 3, 4, 8):
+            cuts, node_lo = capi.tree_cuts(E, shards)
+            n_nodes = len(node_lo) - 1
+            assert cuts[0] == 0 and cuts[-1] == E and all(int(x) in set(node_lo.tolist()) for x in cuts)
+            lists = np.zeros((n_nodes, 1, 10), capi.SEL_DTYPE)
+            counts = np.zeros((n_nodes, 1), np.uint32)
+            for i in range(n_nodes):
+                lst = _node_list(s, c, int(node_lo[i]), int(node_lo[i + 1] - node_lo[i]))
+                counts[i, 0] = len(lst)
+                for k, (a, nn, e, sc) in enumerate(lst):
+                    lists[i, 0, k] = (e, sc, nn, a)
+            got = capi.select_merge(lists, counts)[0]
+            assert got[0] == want, (trial, E, shards, got, want)
