@@ -89,8 +89,9 @@ def synth_gpu(track_ids, seconds):
 
 
 # ---- this rank's contiguous range of tracks: synthesise, index, cut the query excerpts ----
-per = (args.tracks + world - 1) // world
-a, b = min(args.tracks, rank * per), min(args.tracks, (rank + 1) * per)
+cuts, _node_lo = capi.tree_cuts(args.tracks, world)      # shards on node boundaries of the ranking tree
+a, b = int(cuts[rank]), int(cuts[rank + 1])
+per = int(max(cuts[1:] - cuts[:-1]))
 stream = torch.cuda.Stream()
 ctx = capi.Context(lr, stream.cuda_stream)
 n_frames = int(round(args.seconds * RATE))
@@ -144,7 +145,7 @@ for i, q in enumerate(my_queries):
 if dist is not None:
     allq = [torch.empty((per, qmax, 100), dtype=torch.uint8, device=dev) for _ in range(world)]
     dist.all_gather(allq, mine.to(dev))
-    allq = torch.cat(allq)[:args.tracks].cpu().numpy()
+    allq = torch.cat([allq[r][:int(cuts[r + 1] - cuts[r])] for r in range(world)]).cpu().numpy()
 else:
     allq = mine.numpy()
 n_q = args.queries or args.tracks
@@ -153,7 +154,7 @@ prepared = capi.Db.prepare(queries)
 n_qsig = int(prepared[1][-1])
 
 t0 = time.perf_counter()
-searcher = mdist.ShardedSearcher(ctx, my_sigs, total_sigs // 2, a, args.tracks, rank, world)
+searcher = mdist.RankedShardedSearcher(ctx, my_sigs, total_sigs // 2, args.tracks, rank, world, device=dev)
 torch.cuda.synchronize()
 t_build = time.perf_counter() - t0
 
@@ -176,14 +177,14 @@ def timed(fn, steps):
     return float(np.mean(ts)), out
 
 
-cap = min(4096 * args.tracks, 1 << 26)
 if world == 1:
     # one shard: probe + exact ranking on the GPU (mnemo_search_batch), 12 bytes per query come back
     searcher.db.search(prepared)
     dt, res = timed(lambda: searcher.db.search(prepared)[0], args.steps)
 else:
-    searcher.search(prepared, cap=cap)                    # warm-up (allocates and maps the result buffer)
-    dt, res = timed(lambda: searcher.search(prepared, cap=cap), args.steps)
+    # shards ranked on their GPUs, two small all-gathers, host merge of ten records per query and node
+    searcher.search(prepared)
+    dt, res = timed(lambda: searcher.search(prepared), args.steps)
 L = D = 0
 if world == 1:
     L, D = searcher.db.search(prepared)[1]
@@ -211,7 +212,7 @@ if rank == 0:
     got = [r[0] for r in res]
     line = {"metric": "search queries/s",
             "config": "BASELINE configs[3] from PCM: %d five-second excerpts x %d-track database (%g s tracks, %d signatures from "
-                      "GPU-synthesised audio), %d GPU(s), peer-memory merge" % (args.tracks, args.tracks, args.seconds, total_sigs, world),
+                      "GPU-synthesised audio), %d GPU(s), shards ranked on their GPUs" % (args.tracks, args.tracks, args.seconds, total_sigs, world),
             "n_gpus": world, "queries": n_q, "query_signatures": n_qsig, "queries_per_s": n_q / dt,
             "s_per_batch": dt, "identified_own_track": int(sum(int(g == i) for i, g in enumerate(got))),
             "no_match": int(sum(int(g < 0) for g in got)), "lsh_build_s_per_shard": t_build,
@@ -230,7 +231,7 @@ if args.ref_queries:
     if dist is not None:
         alls = [torch.empty((per, smax, 100), dtype=torch.uint8, device=dev) for _ in range(world)]
         dist.all_gather(alls, mine_s.to(dev))
-        alls = torch.cat(alls)[:args.tracks].cpu().numpy()
+        alls = torch.cat([alls[r][:int(cuts[r + 1] - cuts[r])] for r in range(world)]).cpu().numpy()
     else:
         alls = mine_s.numpy()
     if rank == 0:
