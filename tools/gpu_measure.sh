@@ -11,3 +11,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:"k0_resample|sumsq|normalize|k1_spectral|group_|k2_fingerprint|compact" -c 16 \
     -o gpurun_out/${tag}_prof_index python tools/gpu_time_index.py 7200 2 1 > gpurun_out/${tag}_ncu_full.log 2>&1
 tail -2 gpurun_out/${tag}_ncu_full.log
+# search kernels in the config #4 regime (10 k tracks from PCM, 600 queries so that the ncu replays stay short)
+ncu --set full --clock-control none --import-source on -k regex:"search_probe|search_select" -c 2 -f \
+    -o gpurun_out/${tag}_prof_search python tools/bench_c4_pcm.py --queries 600 --ref-queries 0 --steps 1 > gpurun_out/${tag}_ncu_search.log 2>&1
+tail -1 gpurun_out/${tag}_ncu_search.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
