@@ -17,7 +17,7 @@ import argparse, ctypes as C, json, math, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from mnemophonix_b200 import capi, dist as mdist
+from mnemophonix_b200 import capi, dist as mdist, synth
 
 RATE = 44100
 ap = argparse.ArgumentParser()
@@ -43,49 +43,7 @@ if world > 1:
 
 
 def synth_gpu(track_ids, seconds):
-    """int16 [B, n] on the GPU; track t is a function of t alone (its own generator seed)."""
-    n = int(round(seconds * RATE))
-    B = len(track_ids)
-    idx = torch.arange(n, device=dev, dtype=torch.float64)
-    t = idx / RATE
-    K = int(math.ceil(seconds / 0.08)) + 1
-    par = torch.empty((B, 3), dtype=torch.float64)
-    seg = torch.empty((B, 3, K, 3), dtype=torch.float64)     # duration, frequency, gain
-    noise = torch.empty((B, n), device=dev, dtype=torch.float32)
-    for i, tid in enumerate(track_ids):
-        g = torch.Generator().manual_seed(1000 + int(tid))
-        u = torch.rand(3, generator=g, dtype=torch.float64)
-        par[i] = torch.stack([2.0 + 3.0 * u[0], 250.0 + 150.0 * u[1], 1500.0 + 700.0 * u[2]])
-        v = torch.rand((3, K, 3), generator=g, dtype=torch.float64)
-        seg[i, :, :, 0] = 0.08 + 0.52 * v[:, :, 0]
-        seg[i, :, :, 1] = 300.0 + 1700.0 * v[:, :, 1]
-        seg[i, :, :, 2] = 0.3 * v[:, :, 2]
-        gg = torch.Generator(device=dev).manual_seed(77000 + int(tid))
-        noise[i] = torch.randn(n, generator=gg, device=dev, dtype=torch.float32)
-    par = par.to(dev); seg = seg.to(dev)
-    period, f0, f1 = par[:, 0:1], par[:, 1:2], par[:, 2:3]
-    tau = torch.remainder(t.unsqueeze(0), period)
-    x = 0.35 * torch.sin(2.0 * math.pi * (f0 * tau + 0.5 * (f1 - f0) / period * tau * tau))
-    del tau
-    ramp = int(0.010 * RATE)
-    for vce in range(3):
-        dur = seg[:, vce, :, 0]
-        start = torch.cumsum(dur, dim=1) - dur                                    # [B, K] seconds
-        s0 = torch.floor(start * RATE)                                            # start sample
-        ln = torch.floor(dur * RATE)
-        which = torch.searchsorted(s0.contiguous(), idx.unsqueeze(0).expand(B, n).contiguous(), right=True) - 1
-        which.clamp_(0, K - 1)
-        k = idx.unsqueeze(0) - torch.gather(s0, 1, which)
-        lnw = torch.gather(ln, 1, which)
-        inside = k < lnw
-        env = torch.clamp(torch.minimum(k, lnw - 1 - k) / ramp, max=1.0)
-        fr = torch.gather(seg[:, vce, :, 1], 1, which)
-        gn = torch.gather(seg[:, vce, :, 2], 1, which)
-        x += torch.where(inside, gn * env * torch.sin(2.0 * math.pi * fr * k / RATE), torch.zeros((), device=dev, dtype=torch.float64))
-        del which, k, lnw, inside, env, fr, gn
-    x += 0.05 * noise.double()
-    x.clamp_(-1.0, 1.0)
-    return torch.round(x * 20000.0).to(torch.int16)
+    return synth.synth_tracks_torch(track_ids, seconds, dev)
 
 
 # ---- this rank's contiguous range of tracks: synthesise, index, cut the query excerpts ----
