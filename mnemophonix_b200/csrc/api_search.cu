@@ -138,6 +138,18 @@ static SearchParams base_params(const mnemo_db* db) {
   p.ids = db->d_ids;
   p.size = db->size;
   p.size_magic = db->size ? 0xFFFFFFFFFFFFFFFFull / db->size + 1 : 0;
+  if (db->size) {   // size = 2^shift * odd; inverse of the odd part modulo 2^32 by Newton's iteration
+    uint32_t odd = db->size, shift = 0;
+    while ((odd & 1u) == 0) {
+      odd >>= 1;
+      ++shift;
+    }
+    uint32_t inv = odd;                                   // correct to 3 bits
+    for (int i = 0; i < 5; i++) inv *= 2u - odd * inv;    // 6, 12, 24, 48 bits
+    p.div_inv = inv;
+    p.div_shift = shift;
+    p.div_thr = 0xFFFFFFFFu / db->size;
+  }
   p.n_entries = db->n_entries;
   p.n_sigs = (uint32_t)db->n_sigs;
   return p;

@@ -70,6 +70,7 @@ struct SearchParams {
   const uint32_t* ids;           // [25*n_sigs]
   uint32_t size;                 // lsh.c:61 (global)
   uint64_t size_magic;           // 0xFFFFFFFFFFFFFFFF / size + 1 (fastmod, k_search.cu)
+  uint32_t div_inv, div_shift, div_thr;   // divisibility by size (same_slot, k_search.cu)
   uint32_t n_entries;            // entries in this shard
   uint32_t n_sigs;               // signatures in this shard
   const uint8_t* query_sigs;     // [n_query_sigs][100]
