@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
   __shared__ Probe pr;
   __shared__ uint32_t seg_begin[kTables], seg_prefix[kTables + 1];   // this pass's piece of each list
   __shared__ uint32_t s_bound[kTables][kMaxRangePasses + 1];
+  __shared__ uint32_t s_pref[kMaxRangePasses][kTables + 1];   // range mode: prefix of the piece lengths of every pass
   __shared__ uint32_t s_ndup, s_nuniq, s_gmax;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -321,10 +322,159 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
       }
       s_bound[k][j] = lo;
     }
+    for (uint32_t i = tid; i < kBitmapMaxWords / 4; i += kSearchThreads) reinterpret_cast<uint4*>(bitmap)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
+    for (uint32_t j = tid; j < range_passes; j += kSearchThreads) {
+      uint32_t c = 0;
+      for (int k = 0; k < kTables; ++k) {
+        s_pref[j][k] = c;
+        c += s_bound[k][j + 1] - s_bound[k][j];
+      }
+      s_pref[j][kTables] = c;
+    }
+    if (tid == 0) {
+      s_ndup = 0;
+      s_nuniq = 0;
+    }
+    __syncthreads();
+
+    // ---- id ranges: the CTA's latency chain is what bounds this kernel at long lists, so a pass is two barriers:
+    // stream (mark + collect repeats) | clear the bitmap for the next pass.  Everything a pass needs was computed
+    // above for all passes at once; repeats are scored together every few passes (flush).
+    const uint32_t g_last = s_gmax;
+    uint32_t listed = 0;   // block-uniform: entries waiting in dup[]
+    auto flush = [&]() {
+      if (listed == 0) return;
+      const uint32_t ndup = listed;
+      uint32_t set_cap = 64;
+      while (set_cap < 2 * ndup) set_cap <<= 1;   // <= kSetCap because ndup <= kDupCap
+      for (uint32_t i = tid; i < set_cap; i += kSearchThreads) set[i] = kEmpty;
+      __syncthreads();
+      for (uint32_t i = tid; i < ndup; i += kSearchThreads) {
+        const uint32_t g = dup[i];
+        uint32_t h = (g * 2246822519u) & (set_cap - 1);
+        while (true) {
+          const uint32_t prev = atomicCAS(&set[h], kEmpty, g);
+          if (prev == kEmpty) {
+            uniq[atomicAdd(&s_nuniq, 1u)] = g;
+            break;
+          }
+          if (prev == g) break;
+          h = (h + 1) & (set_cap - 1);
+        }
+      }
+      __syncthreads();
+      const uint32_t nuniq = s_nuniq;
+      for (uint32_t i = tid; i < nuniq; i += kSearchThreads) {   // one thread per distinct id (see the hashed path)
+        const uint32_t g = uniq[i];
+        if (g == g_last) continue;   // search.c:147-165: the last group is never flushed
+        const uint32_t* __restrict__ row = dbw + (uint64_t)g * kTables;
+        uint32_t w[kTables];
+#pragma unroll
+        for (int k = 0; k < kTables; ++k) w[k] = __ldg(row + k);
+        uint32_t hits = 0, score = 0;
+#pragma unroll
+        for (int k = 0; k < kTables; ++k) {
+          hits += same_slot(bucket_key(w[k]), pr.qslot[k], p.div_inv, p.div_shift, p.div_thr);
+          score += __popc(__vcmpeq4(w[k], pr.qword[k])) >> 3;
+        }
+        if (hits >= 2) {
+          ++deep_t;
+          if (score >= 30) {
+            const uint64_t a = (uint64_t)query * p.n_entries + p.sig_entry[g];
+            atomicAdd(&p.acc_score[a], score);
+            atomicAdd(&p.acc_n[a], 1u);
+          }
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        s_ndup = 0;
+        s_nuniq = 0;
+      }
+      listed = 0;
+      __syncthreads();
+    };
+    for (uint32_t pass = 0; pass < n_pass; ++pass) {
+      const uint32_t* __restrict__ pref = s_pref[pass];
+      const uint32_t Lp = pref[kTables];
+      if (Lp < 2) continue;   // nothing can repeat in this id range; no barrier: the tables are read-only by now
+      if (listed && listed + Lp / 4 > kDupCap) flush();
+      const uint32_t id_base = pass * kRangeBits;
+      {
+        uint32_t k = 0, seg_end = pref[1];
+        const uint32_t* src = p.ids + pr.begin[0] + s_bound[0][pass];   // src + i addresses candidate i while i < seg_end
+        auto locate = [&](uint32_t i) -> const uint32_t* {
+          while (i >= seg_end) {
+            ++k;
+            seg_end = pref[k + 1];
+            src = p.ids + pr.begin[k] + s_bound[k][pass] - pref[k];
+          }
+          return src + i;
+        };
+        auto visit = [&](uint32_t g) {
+          const uint32_t h = g - id_base;
+          const uint32_t bit = 1u << (h & 31u);
+          if (atomicOr(&bitmap[h >> 5], bit) & bit) {
+            const uint32_t pos = atomicAdd(&s_ndup, 1u);
+            if (pos < kDupCap) dup[pos] = g;
+          }
+        };
+        uint32_t i = tid;
+        for (; i + 3 * kSearchThreads < Lp; i += 4 * kSearchThreads) {
+          const uint32_t* a0 = locate(i);
+          const uint32_t* a1 = locate(i + kSearchThreads);
+          const uint32_t* a2 = locate(i + 2 * kSearchThreads);
+          const uint32_t* a3 = locate(i + 3 * kSearchThreads);
+          const uint32_t g0 = __ldg(a0), g1 = __ldg(a1), g2 = __ldg(a2), g3 = __ldg(a3);
+          visit(g0);
+          visit(g1);
+          visit(g2);
+          visit(g3);
+        }
+        for (; i < Lp; i += kSearchThreads) visit(__ldg(locate(i)));
+      }
+      __syncthreads();   // every mark is in, s_ndup is final
+      const uint32_t ndup = s_ndup;
+      for (uint32_t i = tid; i < kBitmapMaxWords / 4; i += kSearchThreads) reinterpret_cast<uint4*>(bitmap)[i] = make_uint4(0, 0, 0, 0);
+      if (ndup <= kDupCap) {
+        listed = ndup;   // scored at the next flush
+      } else {
+        // more repeats than the list holds: this pass's entries are dropped from it and the pass is scored list-free
+        // (one warp per candidate; the pair is scored only from its lowest matching list, i.e. exactly once)
+        __syncthreads();             // everyone has read s_ndup
+        if (tid == 0) s_ndup = listed;
+        for (int k = 0; k < kTables; ++k) {
+          const uint32_t b = s_bound[k][pass], n = s_bound[k][pass + 1] - b;
+          const uint32_t* __restrict__ lst = p.ids + pr.begin[k] + b;
+          for (uint32_t j = warp; j < n; j += kSearchThreads / 32) {
+            const uint32_t g = __ldg(lst + j);
+            if (g == g_last) continue;
+            uint32_t h = 0, eq = 0;
+            if (lane < kTables) {
+              const uint32_t w = __ldg(dbw + (uint64_t)g * kTables + lane);
+              h = same_slot(bucket_key(w), pr.qslot[lane], p.div_inv, p.div_shift, p.div_thr);
+              eq = __popc(__vcmpeq4(w, pr.qword[lane])) >> 3;
+            }
+            const uint32_t mask = __ballot_sync(0xffffffffu, h);
+            const uint32_t score = __reduce_add_sync(0xffffffffu, eq);
+            if (__popc(mask) >= 2 && (__ffs(mask) - 1) == k) {
+              ++deep;
+              if (score >= 30 && lane == 0) {
+                const uint64_t a = (uint64_t)query * p.n_entries + p.sig_entry[g];
+                atomicAdd(&p.acc_score[a], score);
+                atomicAdd(&p.acc_n[a], 1u);
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();   // bitmap clean, and nobody still reads s_ndup when the next pass appends
+    }
+    flush();
   }
 
-  for (uint32_t pass = 0; pass < n_pass; ++pass) {
+  for (uint32_t pass = 0; !range_mode && pass < n_pass; ++pass) {
     if (tid < kTables) {
       if (range_mode) {
         const uint32_t b = s_bound[tid][pass], e = s_bound[tid][pass + 1];
@@ -478,6 +628,7 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
     }
     __syncthreads();
   }
+  gmax = s_gmax;
   if (warp == 0) {
     uint32_t hits, score;
     check_pair(dbw, gmax, pr, p.size, p.size_magic, lane, &hits, &score);
