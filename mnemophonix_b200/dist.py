@@ -236,14 +236,17 @@ class RankedShardedSearcher:
     """
 
     def __init__(self, ctx, shard_sigs, table_size: int, n_entries_total: int, rank: int, world: int, device="cpu",
-                 group=None):
+                 group=None, db_factory=None):
+        """db_factory(shard_sigs, table_size, entry_base) -> object with dense_begin / dense_lists / close; default:
+        capi.Db on ctx (the CPU tests pass a stand-in so that the plumbing runs without a GPU)."""
         self.ctx, self.rank, self.world, self.device, self.group = ctx, rank, world, device, group
         self.cuts, self.node_lo = capi.tree_cuts(n_entries_total, world)
         n_nodes = len(self.node_lo) - 1
         self.node_range = (rank * n_nodes // world, (rank + 1) * n_nodes // world)     # my nodes
         a, b = int(self.cuts[rank]), int(self.cuts[rank + 1])
         assert len(shard_sigs) == b - a, "shard does not match capi.tree_cuts"
-        self.db = capi.Db(ctx, shard_sigs, table_size=table_size, entry_base=a)
+        self.db = db_factory(shard_sigs, table_size, a) if db_factory else \
+            capi.Db(ctx, shard_sigs, table_size=table_size, entry_base=a)
 
     def _all_gather(self, arr: np.ndarray):
         """Equal-shaped numpy arrays from every rank, in rank order."""

@@ -76,6 +76,105 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+class _OracleShard:
+    """Stand-in for capi.Db in the ranked protocol: probe + scoring by the oracle on this rank's shard, the per-node
+    lists by the Python replay of the ranking tree (tests/ranking_ref.py)."""
+
+    def __init__(self, oracle, sigs, table_size, entry_base):
+        self.o, self.sigs, self.table_size, self.base = oracle, sigs, table_size, entry_base
+        self.db = oracle.make_db(sigs) if len(sigs) else None
+
+    def dense_begin(self, prepared):
+        qs, qstart = prepared
+        self.qstart = qstart
+        nq = len(qstart) - 1
+        n = len(self.sigs)
+        self.acc = np.zeros((nq, max(n, 1), 2), np.float64)
+        self.last = np.zeros((int(qstart[-1]), 5), np.uint32)
+        for q in range(nq):
+            if self.db is None:
+                continue
+            sc, last = self.o.search_shard(self.db, self.table_size, qs[qstart[q]:qstart[q + 1]])
+            self.acc[q, :n] = sc
+            self.last[qstart[q]:qstart[q + 1]] = last
+        return self.last[:, 0].astype(np.uint8), (0, 0)
+
+    def dense_lists(self, has_higher, node_bounds):
+        from ranking_ref import node_list
+        from mnemophonix_b200 import capi
+        nq = len(self.qstart) - 1
+        acc = self.acc.copy()
+        for q in range(nq):
+            for s in range(int(self.qstart[q]), int(self.qstart[q + 1])):
+                has, e, _, hits, score = (int(x) for x in self.last[s])
+                if has and has_higher[s] and hits >= 2 and score >= 30:      # this shard's own last group, scored after all
+                    acc[q, e, 0] += score
+                    acc[q, e, 1] += 1
+        n_nodes = len(node_bounds) - 1
+        lists = np.zeros((n_nodes, nq, 10), capi.SEL_DTYPE)
+        counts = np.zeros((n_nodes, nq), np.uint32)
+        for i in range(n_nodes):
+            lo, n = int(node_bounds[i]) - self.base, int(node_bounds[i + 1] - node_bounds[i])
+            for q in range(nq):
+                s = acc[q, :, 0].astype(np.float32)
+                c = acc[q, :, 1].astype(np.int32)
+                lst = node_list(s, c, lo, n)
+                counts[i, q] = len(lst)
+                for k, (avg, nn, e, sc) in enumerate(lst):
+                    lists[i, q, k] = (self.base + e, sc, nn, avg)
+        return lists, counts
+
+    def close(self):
+        pass
+
+
+def _ranked_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mnemophonix_b200 import capi, dist as mdist
+    from oracle.oracle import Oracle
+    o = Oracle()
+    entries, queries = _make_corpus()
+    total = sum(len(s) for s in entries)
+    cuts, _ = capi.tree_cuts(len(entries), world)
+    mine = entries[int(cuts[rank]):int(cuts[rank + 1])]
+    s = mdist.RankedShardedSearcher(None, mine, total // 2, len(entries), rank, world, device="cpu",
+                                    db_factory=lambda sigs, ts, base: _OracleShard(o, sigs, ts, base))
+    res = s.search(capi.Db.prepare(queries))
+    s.close()
+    if rank == 0:
+        out.put(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ranked_shards_over_gloo_equal_single_database(world):
+    """dist.RankedShardedSearcher over gloo (two all-gathers, last-group fix-up, host merge of the node lists), the GPU
+    work of each rank stood in for by the oracle: 2 ranks (one node each) and 3 ranks (rank 2 owns two nodes)."""
+    from oracle.oracle import Oracle
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ranked_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = out.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    o = Oracle()
+    entries, queries = _make_corpus()
+    db = o.make_db(entries)
+    want = []
+    for q in queries:
+        best, sc, _, _ = o.search(db, q)
+        want.append((best, float(sc[best, 0]) if best >= 0 else 0.0, int(sc[best, 1]) if best >= 0 else 0))
+    assert res == want
+
+
 def test_two_rank_search_merge_equals_single_database():
     from oracle.oracle import Oracle
     ctx = mp.get_context("spawn")

@@ -2,9 +2,15 @@
 reference's non-transitive comparator, search.c:65-107,170-193) against the oracle, which calls libc
 qsort on the dense per-entry array exactly as the reference does.  No GPU needed: mnemo_search_finish
 is pure host code."""
+import os
+import sys
+
 import numpy as np
 
 from mnemophonix_b200 import capi
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from ranking_ref import node_list as _node_list  # noqa: E402
 
 
 def _finish_one(idx, score, n, n_entries):
@@ -80,48 +86,6 @@ def test_last_group_merge_across_shards():
 
 
 # ---- ranking tree: ten records per node are enough, and shards on node boundaries can be merged (host parts) ----
-
-def _cmp(a, b):
-    """search.c:65-107 on (avg float32, n)."""
-    d = abs(int(np.float32(a[0]) - np.float32(b[0])))
-    if d <= 3:
-        if a[1] >= b[1] + 5:
-            return -1
-        if b[1] >= a[1] + 5:
-            return 1
-    if d < 0.5:
-        if a[1] > b[1]:
-            return -1
-        if a[1] < b[1]:
-            return 1
-    if a[0] > b[0]:
-        return -1
-    if b[0] > a[0]:
-        return 1
-    return 0
-
-
-def _node_list(s, c, lo, n, top=10):
-    """First `top` matched records of glibc's merge sort over positions lo .. lo+n-1 (split n/2 | n - n/2, left head
-    taken when cmp <= 0), computed from the children's first `top` only."""
-    if n <= 0:
-        return []
-    if n == 1:
-        return [(np.float32(s[lo]) / np.float32(c[lo]), int(c[lo]), lo, float(s[lo]))] if c[lo] else []
-    n1 = n // 2
-    A, B = _node_list(s, c, lo, n1, top), _node_list(s, c, lo + n1, n - n1, top)
-    out, ia, ib = [], 0, 0
-    while len(out) < top and ia < len(A) and ib < len(B):
-        if _cmp(A[ia], B[ib]) <= 0:
-            out.append(A[ia]); ia += 1
-        else:
-            out.append(B[ib]); ib += 1
-    while len(out) < top and ia < len(A):
-        out.append(A[ia]); ia += 1
-    while len(out) < top and ib < len(B):
-        out.append(B[ib]); ib += 1
-    return out
-
 
 def test_node_lists_of_tree_aligned_shards_merge_to_the_reference_selection(oracle):
     rng = np.random.RandomState(21)
