@@ -68,18 +68,13 @@ static char* decode_with_ffmpeg(const char* input) {
     return strdup(tmpl);
 }
 
-int main(int argc, char* argv[]) {
-    if (argc < 2 || (strcmp(argv[1], "index") && strcmp(argv[1], "search")) || argc < 3 ||
-        (!strcmp(argv[1], "search") && argc != 4)) {
-        usage(argv[0]);
-        return 1;
-    }
-    char* input = argv[2];
-    struct signatures* fingerprint = NULL;
-    char *artist = NULL, *track_title = NULL, *album_title = NULL;
-    int res = generate_fingerprint(input, &fingerprint, &artist, &track_title, &album_title);
+/* generate_fingerprint with the reference's error texts and its ffmpeg fallback (main.c:57-84 upstream).
+ * Returns 0 on success, 1 after printing the message. */
+static int fingerprint_input(const char* input, struct signatures** fingerprint, char** artist, char** track_title,
+                             char** album_title) {
+    int res = generate_fingerprint(input, fingerprint, artist, track_title, album_title);
     switch (res) {
-        case SUCCESS: break;
+        case SUCCESS: return 0;
         case CANNOT_READ_FILE: fprintf(stderr, "Cannot read file '%s'\n", input); return 1;
         case MEMORY_ERROR: fprintf(stderr, "Memory allocation error\n"); return 1;
         case DECODING_ERROR: fprintf(stderr, "Cannot decode file '%s'\n", input); return 1;
@@ -91,16 +86,43 @@ int main(int argc, char* argv[]) {
                 fprintf(stderr, "'%s' is not a wave file and we could not convert it to one with fffmpeg\n", input);
                 return 1;
             }
-            res = generate_fingerprint(wav, &fingerprint, NULL, NULL, NULL);
+            res = generate_fingerprint(wav, fingerprint, NULL, NULL, NULL);
             remove(wav);
             free(wav);
             if (res == MEMORY_ERROR) { fprintf(stderr, "Memory allocation error\n"); return 1; }
             if (res == FILE_TOO_SMALL) { fprintf(stderr, "'%s' is too small to generate a fingerprint\n", input); return 1; }
             if (res != SUCCESS) { fprintf(stderr, "Cannot decode file '%s'\n", input); return 1; }
-            break;
+            return 0;
         }
         default: fprintf(stderr, "Cannot decode file '%s'\n", input); return 1;
     }
+}
+
+static int report(const struct index* db, int best) {
+    if (best < 0) {
+        printf("\nNo match found\n\n");
+        return 1;
+    }
+    printf("\nFound match: '%s'\n", db->entries[best]->filename);
+    if (db->entries[best]->artist[0]) printf("Artist: %s\n", db->entries[best]->artist);
+    if (db->entries[best]->track_title[0]) printf("Track title: %s\n", db->entries[best]->track_title);
+    if (db->entries[best]->album_title[0]) printf("Album title: %s\n", db->entries[best]->album_title);
+    printf("\n");
+    return 0;
+}
+
+int main(int argc, char* argv[]) {
+    /* `search` takes <input> <index> as upstream; with more arguments (an extension) every argument but the last
+     * is an input and the last one the index: the database is loaded and its tables are built once. */
+    if (argc < 2 || (strcmp(argv[1], "index") && strcmp(argv[1], "search")) || argc < 3 ||
+        (!strcmp(argv[1], "search") && argc < 4)) {
+        usage(argv[0]);
+        return 1;
+    }
+    char* input = argv[2];
+    struct signatures* fingerprint = NULL;
+    char *artist = NULL, *track_title = NULL, *album_title = NULL;
+    if (fingerprint_input(input, &fingerprint, &artist, &track_title, &album_title)) return 1;
 
     if (!strcmp(argv[1], "index")) {
         save(stdout, fingerprint, input, artist, track_title, album_title);
@@ -114,7 +136,7 @@ int main(int argc, char* argv[]) {
             free(album_title);
             fingerprint = NULL;
             artist = track_title = album_title = NULL;
-            res = generate_fingerprint(argv[i], &fingerprint, &artist, &track_title, &album_title);
+            int res = generate_fingerprint(argv[i], &fingerprint, &artist, &track_title, &album_title);
             if (res != SUCCESS) {
                 fprintf(stderr, "Cannot index '%s' (error %d)\n", argv[i], res);
                 return 1;
@@ -125,11 +147,11 @@ int main(int argc, char* argv[]) {
         return 0;
     }
 
-    const char* index = argv[3];
+    const char* index = argv[argc - 1];
     struct index* db = NULL;
     printf("Loading database %s...\n", index);
     long t0 = now_ms();
-    res = read_index(index, &db);
+    int res = read_index(index, &db);
     if (res != SUCCESS) {
         if (res == CANNOT_READ_FILE) fprintf(stderr, "Cannot read file '%s'\n", index);
         else if (res == MEMORY_ERROR) fprintf(stderr, "Memory allocation error\n");
@@ -149,14 +171,21 @@ int main(int argc, char* argv[]) {
     int best = search(fingerprint, db, lsh, 0);
     long t3 = now_ms();
     printf("(Search took %ld ms)\n", t3 - t2);
-    if (best < 0) {
-        printf("\nNo match found\n\n");
-        return 1;
+    int status = report(db, best);
+    /* further inputs (extension): same block per input, headed by its name; exit status 1 if any input failed or
+     * found nothing */
+    for (int i = 3; i < argc - 1; i++) {
+        free_signatures(fingerprint);
+        fingerprint = NULL;
+        printf("Searching '%s'...\n", argv[i]);
+        if (fingerprint_input(argv[i], &fingerprint, NULL, NULL, NULL)) {
+            status = 1;
+            continue;
+        }
+        long t4 = now_ms();
+        best = search(fingerprint, db, lsh, 0);
+        printf("(Search took %ld ms)\n", now_ms() - t4);
+        status |= report(db, best);
     }
-    printf("\nFound match: '%s'\n", db->entries[best]->filename);
-    if (db->entries[best]->artist[0]) printf("Artist: %s\n", db->entries[best]->artist);
-    if (db->entries[best]->track_title[0]) printf("Track title: %s\n", db->entries[best]->track_title);
-    if (db->entries[best]->album_title[0]) printf("Album title: %s\n", db->entries[best]->album_title);
-    printf("\n");
-    return 0;
+    return status;
 }

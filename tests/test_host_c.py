@@ -248,6 +248,15 @@ def test_cli_index_and_search_round_trip(host, ref):
     synth.write_wav(noise, (np.random.RandomState(0).standard_normal((44100 * 5, 1)) * 3000).astype(np.int16))
     r = subprocess.run([CLI, "search", noise, dbpath], capture_output=True, text=True)
     assert r.returncode == 1 and "No match found" in r.stdout
+    # several inputs per invocation (extension): one database load, one block per input, status 1 if any found nothing
+    clip2 = os.path.join(d, "clip2.wav")
+    synth.write_wav(clip2, synth.synth_track(302, 25.0, 1)[9 * 44100 + 5: 14 * 44100 + 5])
+    r = subprocess.run([CLI, "search", clip, noise, clip2, dbpath], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.count("Loading database") == 1
+    blocks = r.stdout.split("Searching")
+    assert f"Found match: '{names[1]}'" in blocks[1] and "No match found" in blocks[2] and f"Found match: '{names[2]}'" in blocks[3]
+    r = subprocess.run([CLI, "search", clip, clip2, dbpath], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.count("Found match") == 2
 
     # the C API on the same database: create_hash_tables / get_matches / search against the reference's
     mine = C.POINTER(refmod.Index)()
