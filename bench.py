@@ -276,14 +276,14 @@ def search_c4_section(ctx, device, n_tracks: int = 10000, seconds: float = 30.0,
 
 
 # ----------------------------------------------------------------------- reference arm ----
-def reference_throughput(seconds_sample: float, channels: int, steps: int, warmup: int):
+def reference_throughput(seconds_sample: float, channels: int, steps: int, warmup: int, variant: str = "O2"):
     """Times the unmodified reference (oracle/_ref -O2, generate_fingerprint on a WAV file) on the host
     cores: P = cores // 2 (at most 32) concurrent processes, each with the library's own 8 threads per stage
     (spectralimages.c:11), each fingerprinting the sample; this is the configuration that saturated the
     survey's box."""
     from mnemophonix_b200 import synth
     from oracle import ref as refmod
-    if not refmod.available("O2"):
+    if not refmod.available(variant):
         return None
     cores = os.cpu_count() or 1
     # ~1/3 of the reference's pipeline is serial (SURVEY.md §3.1), so one process per 2 cores keeps the box busy
@@ -295,12 +295,12 @@ def reference_throughput(seconds_sample: float, channels: int, steps: int, warmu
     worker = (
         "import sys, time; sys.path.insert(0, %r)\n"
         "from oracle.ref import Ref\n"
-        "r = Ref('O2')\n"
+        "r = Ref(%r)\n"
         "sys.stdout.write('ready\\n'); sys.stdout.flush()\n"
         "for line in sys.stdin:\n"
         "    t = time.perf_counter(); rc, sigs, *_ = r.fingerprint_wav(%r); dt = time.perf_counter() - t\n"
         "    sys.stdout.write('%%d %%d %%.6f\\n' %% (rc, 0 if sigs is None else len(sigs), dt)); sys.stdout.flush()\n"
-    ) % (ROOT, path)
+    ) % (ROOT, variant, path)
     ps = [subprocess.Popen([sys.executable, "-c", worker], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
           for _ in range(procs)]
     try:
@@ -332,7 +332,7 @@ def reference_throughput(seconds_sample: float, channels: int, steps: int, warmu
     hours = procs * seconds_sample / 3600.0
     return {"value": hours / (ms / 1e3), "ms_per_step": ms, "cores": cores, "threads": procs * 8, "procs": procs,
             "sample": f"{procs} concurrent processes x one {seconds_sample:.0f} s {channels}-channel excerpt of the "
-                      f"workload, reference -O2 build, generate_fingerprint() on a WAV in tmpfs, tables pre-warmed",
+                      f"workload, reference -{variant} build, generate_fingerprint() on a WAV in tmpfs, tables pre-warmed",
             "n_sigs": n_sigs}
 
 
@@ -556,6 +556,10 @@ def main():
         if r is not None:
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
                                     "sample": r["sample"], "threads": r["threads"]}
+            # also the build exactly as the reference's Makefile ships it (no -O flag), on half the sample
+            r0 = reference_throughput(args.cpu_sample_seconds / 2, args.channels, 1, 0, variant="O0")
+            if r0 is not None:
+                line["cpu_baseline"]["value_as_shipped_O0"] = r0["value"]
         else:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                                     "sample": "oracle/_ref not available on this box"}
