@@ -297,6 +297,46 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
   const uint32_t* __restrict__ dbw = reinterpret_cast<const uint32_t*>(p.db_sigs);
   uint32_t deep = 0, deep_t = 0, gmax = 0;   // deep checks counted per warp (fallback path) / per thread
 
+  // Deep checks of the distinct repeated ids lst[0 .. n): warps take groups of 32.  Lane k (< 25) loads word k of each
+  // of the group's 32 signatures — 32 coalesced 100-byte loads in flight per warp — then one warp reduction per
+  // signature yields its shared-bucket count and its equal-byte count together, and lane r scores signature r.
+  // (One thread per signature with 25 loads of its own cost 32 L1 sectors per load instruction and made the L1 the
+  // bound of the kernel: 84 of 150 ms per batch at config #4; one warp per signature kept a single row in flight.)
+  auto check_list = [&](const uint32_t* lst, uint32_t n, uint32_t g_skip) {
+    const uint32_t my_slot = lane < kTables ? pr.qslot[lane] : 0u, my_word = lane < kTables ? pr.qword[lane] : 0u;
+    for (uint32_t base = (uint32_t)warp * 32u; base < n; base += kSearchThreads) {
+      const uint32_t cnt = min(32u, n - base);
+      uint32_t w[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const uint32_t g = lst[base + ((uint32_t)r < cnt ? r : 0)];   // shared-memory broadcast
+        w[r] = lane < kTables ? __ldg(dbw + (uint64_t)g * kTables + lane) : 0u;
+      }
+      uint32_t mine = 0;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        uint32_t v = 0;
+        if (lane < kTables) {
+          const uint32_t h = same_slot(bucket_key(w[r]), my_slot, p.div_inv, p.div_shift, p.div_thr);
+          v = (__popc(__vcmpeq4(w[r], my_word)) >> 3) | (h << 16);   // search.c:35-43 equal bytes | bucket hit
+        }
+        v = __reduce_add_sync(0xffffffffu, v);
+        if (lane == r) mine = v;
+      }
+      if ((uint32_t)lane < cnt) {
+        const uint32_t g = lst[base + lane], hits = mine >> 16, score = mine & 0xFFFFu;
+        if (g != g_skip && hits >= 2) {   // search.c:147-165 (last group never flushed), MIN_BUCKET_MATCH_FOR_DEEP_CHECK
+          ++deep_t;
+          if (score >= 30) {              // MIN_SCORE (search.c:16)
+            const uint64_t a = (uint64_t)query * p.n_entries + p.sig_entry[g];
+            atomicAdd(&p.acc_score[a], score);
+            atomicAdd(&p.acc_n[a], 1u);
+          }
+        }
+      }
+    }
+  };
+
   if (range_mode) {
     // the greatest candidate id is the greatest last element of the sorted lists
     if (warp == 0) {
@@ -365,28 +405,7 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
       }
       __syncthreads();
       const uint32_t nuniq = s_nuniq;
-      for (uint32_t i = tid; i < nuniq; i += kSearchThreads) {   // one thread per distinct id (see the hashed path)
-        const uint32_t g = uniq[i];
-        if (g == g_last) continue;   // search.c:147-165: the last group is never flushed
-        const uint32_t* __restrict__ row = dbw + (uint64_t)g * kTables;
-        uint32_t w[kTables];
-#pragma unroll
-        for (int k = 0; k < kTables; ++k) w[k] = __ldg(row + k);
-        uint32_t hits = 0, score = 0;
-#pragma unroll
-        for (int k = 0; k < kTables; ++k) {
-          hits += same_slot(bucket_key(w[k]), pr.qslot[k], p.div_inv, p.div_shift, p.div_thr);
-          score += __popc(__vcmpeq4(w[k], pr.qword[k])) >> 3;
-        }
-        if (hits >= 2) {
-          ++deep_t;
-          if (score >= 30) {
-            const uint64_t a = (uint64_t)query * p.n_entries + p.sig_entry[g];
-            atomicAdd(&p.acc_score[a], score);
-            atomicAdd(&p.acc_n[a], 1u);
-          }
-        }
-      }
+      check_list(uniq, nuniq, g_last);
       __syncthreads();
       if (tid == 0) {
         s_ndup = 0;
@@ -573,32 +592,7 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
       }
       __syncthreads();
       const uint32_t nuniq = s_nuniq;
-      // One THREAD per distinct id: its 25 words are loaded back to back (25 loads in flight per thread, 256
-      // signatures per CTA at once; a warp-per-signature loop kept 8 in flight and waited on each), the query's
-      // words and slots are shared-memory broadcasts.  The 4 sectors of a 100-byte row are fetched once and then hit
-      // in L1 for the row's other words.
-      for (uint32_t i = tid; i < nuniq; i += kSearchThreads) {
-        const uint32_t g = uniq[i];
-        if (g == gmax) continue;   // search.c:147-165: the last group is never flushed
-        const uint32_t* __restrict__ row = dbw + (uint64_t)g * kTables;
-        uint32_t w[kTables];
-#pragma unroll
-        for (int k = 0; k < kTables; ++k) w[k] = __ldg(row + k);
-        uint32_t hits = 0, score = 0;
-#pragma unroll
-        for (int k = 0; k < kTables; ++k) {
-          hits += same_slot(bucket_key(w[k]), pr.qslot[k], p.div_inv, p.div_shift, p.div_thr);
-          score += __popc(__vcmpeq4(w[k], pr.qword[k])) >> 3;   // search.c:35-43: number of equal bytes
-        }
-        if (hits >= 2) {           // MIN_BUCKET_MATCH_FOR_DEEP_CHECK (search.c:11)
-          ++deep_t;
-          if (score >= 30) {       // MIN_SCORE (search.c:16)
-            const uint64_t a = (uint64_t)query * p.n_entries + p.sig_entry[g];
-            atomicAdd(&p.acc_score[a], score);
-            atomicAdd(&p.acc_n[a], 1u);
-          }
-        }
-      }
+      check_list(uniq, nuniq, gmax);
     } else {
       // More repeats than the short list holds (pathological buckets): no list at all.  One warp
       // per candidate recomputes the exact shared-bucket mask from the signature, and the pair is
