@@ -6,9 +6,8 @@
 // Build.  The reference keeps 25 chained hash tables of `size` = total_signatures/2 heads
 // (lsh.c:61) and inserts every signature under slot = big-endian-u32(bytes 4k..4k+3) % size
 // (lsh.c:49-52,74).  Here each table is a CSR: one histogram pass (global reductions), one
-// exclusive scan over the 25*size counters, and a STABLE radix sort of the 25*n (bucket, id) pairs
-// (cub::DeviceRadixSort on the build path only), so that every bucket lists its members in ascending
-// id order.  A bucket holds exactly the members of the reference's chain (collisions through the
+// exclusive scan over the 25*size counters, and a STABLE least-significant-digit radix sort of the 25*n
+// (bucket, id) pairs (8-bit digits, below), so that every bucket lists its members in ascending id order.  A bucket holds exactly the members of the reference's chain (collisions through the
 // modulo included); the sorted order is what lets the probe kernel walk id ranges (below).
 //
 // Probe + score.  For one query signature the reference concatenates the 25 probed chains,
@@ -26,8 +25,6 @@
 //      buckets and >= 30 equal bytes add (score, 1) to the query's per-entry accumulators.
 // Traffic per query signature = 100 + 25*8 + 4*L + 100*D' bytes, D' = deep checks
 // plus the few bitmap false positives.
-#include <cub/device/device_radix_sort.cuh>
-
 #include "common.cuh"
 #include "search_internal.h"
 
@@ -164,14 +161,99 @@ static int key_bits(uint64_t n_slots) {
   return b;
 }
 
-size_t lsh_sort_temp_bytes(uint64_t n_sigs, uint32_t size) {
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, (int64_t)(n_sigs * kTables), 0, key_bits((uint64_t)size * kTables));
-  return bytes;
+// ---- stable LSD radix sort of (key, value) pairs, 8 bits per pass ----
+// Pass = histogram per tile (digit-major, tile-minor in global memory) -> exclusive scan of that table -> scatter.
+// Stability inside a tile: a warp owns 256 consecutive elements and ranks them 32 at a time, in order, with
+// match.any (lanes holding the same digit) and a per-warp counter per digit in shared memory; the warps' counters are
+// then prefixed in warp order.  Equal keys therefore keep their input order: ids ascending inside every bucket.
+constexpr int kSortThreads = 256, kSortItems = 8, kSortTile = kSortThreads * kSortItems;
+
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, int shift,
+                                                                  uint32_t n_tiles, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t base = (uint64_t)blockIdx.x * kSortTile;
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    const uint64_t i = base + (uint64_t)j * kSortThreads + threadIdx.x;
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(uint64_t)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
 }
 
-// keys_in / vals_in / keys_out: 25*n_sigs u32 each; temp: lsh_sort_temp_bytes()
+__global__ void __launch_bounds__(kSortThreads)
+    radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t n, int shift,
+                         uint32_t n_tiles, const uint32_t* __restrict__ hist_scanned, uint32_t* __restrict__ keys_out,
+                         uint32_t* __restrict__ vals_out) {
+  __shared__ uint32_t cnt[kSortThreads / 32][256];
+  __shared__ uint32_t goff[256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int w = 0; w < kSortThreads / 32; ++w) cnt[w][tid] = 0;
+  goff[tid] = hist_scanned[(uint64_t)tid * n_tiles + blockIdx.x];
+  __syncthreads();
+  const uint64_t wbase = (uint64_t)blockIdx.x * kSortTile + (uint64_t)warp * (32 * kSortItems);
+  uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    const uint64_t i = wbase + (uint64_t)j * 32 + lane;
+    key[j] = i < n ? keys_in[i] : 0u;
+    val[j] = i < n ? vals_in[i] : 0u;
+  }
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {   // in input order
+    const bool valid = wbase + (uint64_t)j * 32 + lane < n;
+    const uint32_t d = (key[j] >> shift) & 255u;
+    const uint32_t act = __ballot_sync(0xffffffffu, valid);
+    uint32_t r = 0;
+    if (valid) {
+      const uint32_t peers = __match_any_sync(act, d);
+      const int leader = __ffs(peers) - 1;
+      uint32_t c = 0;
+      if (lane == leader) {
+        c = cnt[warp][d];
+        cnt[warp][d] = c + (uint32_t)__popc(peers);
+      }
+      c = __shfl_sync(peers, c, leader);
+      r = c + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    }
+    rank[j] = r;
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    uint32_t run = 0;   // digit tid: exclusive prefix of the warps' counts, in warp order
+#pragma unroll
+    for (int w = 0; w < kSortThreads / 32; ++w) {
+      const uint32_t t = cnt[w][tid];
+      cnt[w][tid] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    if (wbase + (uint64_t)j * 32 + lane < n) {
+      const uint32_t d = (key[j] >> shift) & 255u;
+      const uint32_t dst = goff[d] + cnt[warp][d] + rank[j];
+      keys_out[dst] = key[j];
+      vals_out[dst] = val[j];
+    }
+  }
+}
+
+static uint32_t sort_tiles(uint64_t n) { return (uint32_t)((n + kSortTile - 1) / kSortTile); }
+
+// scratch of the sort: the digit table [256 * tiles + 1] and the block sums of its scan
+size_t lsh_sort_temp_bytes(uint64_t n_sigs, uint32_t size) {
+  (void)size;
+  const uint64_t h = 256ull * sort_tiles(n_sigs * kTables);
+  return sizeof(uint32_t) * (h + 1 + lsh_scan_blocks(h) + 1);
+}
+
+// keys_in / vals_in / keys_out: 25*n_sigs u32 each (the sort's two buffers); temp: lsh_sort_temp_bytes()
 cudaError_t launch_lsh_build(const uint8_t* sigs, uint64_t n_sigs, const uint32_t* entry_start, uint32_t n_entries,
                              uint32_t size, uint32_t* counts, uint32_t* start, uint32_t* scan_copy, uint32_t* block_sums,
                              uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, void* temp, size_t temp_bytes,
@@ -187,8 +269,28 @@ cudaError_t launch_lsh_build(const uint8_t* sigs, uint64_t n_sigs, const uint32_
   scan_sums_kernel<<<1, kScanT, 0, st>>>(block_sums, n_blocks);
   scan_apply_kernel<<<n_blocks, kScanT, 0, st>>>(counts, n_slots, block_sums, start, scan_copy);
   lsh_pairs_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(words, n_sigs, size, keys_in, vals_in);
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const uint32_t*)keys_in, keys_out,
-                                                  (const uint32_t*)vals_in, ids, (int64_t)n_words, 0, key_bits(n_slots), st);
+  // stable sort by bucket: A = (keys_in, vals_in), B = (keys_out, ids); passes alternate A -> B -> A ...
+  cudaError_t e = cudaSuccess;
+  {
+    (void)temp_bytes;
+    const uint32_t n_tiles = sort_tiles(n_words);
+    const uint64_t h = 256ull * n_tiles;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(temp);
+    uint32_t* hsums = hist + h + 1;
+    const uint32_t h_blocks = lsh_scan_blocks(h);
+    const int bits = key_bits(n_slots);
+    uint32_t *ka = keys_in, *va = vals_in, *kb = keys_out, *vb = ids;
+    for (int shift = 0; shift < bits; shift += 8) {
+      radix_hist_kernel<<<n_tiles, kSortThreads, 0, st>>>(ka, n_words, shift, n_tiles, hist);
+      scan_reduce_kernel<<<h_blocks, kScanT, 0, st>>>(hist, h, hsums);
+      scan_sums_kernel<<<1, kScanT, 0, st>>>(hsums, h_blocks);
+      scan_apply_kernel<<<h_blocks, kScanT, 0, st>>>(hist, h, hsums, hist, hist);   // in place (each block reads its part first)
+      radix_scatter_kernel<<<n_tiles, kSortThreads, 0, st>>>(ka, va, n_words, shift, n_tiles, hist, kb, vb);
+      uint32_t* t = ka; ka = kb; kb = t;
+      t = va; va = vb; vb = t;
+    }
+    if (va != ids) e = cudaMemcpyAsync(ids, va, n_words * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
+  }
   sig_entry_kernel<<<(unsigned)((n_sigs + 255) / 256), 256, 0, st>>>(entry_start, n_entries, n_sigs, sig_entry);
   return e;
 }
