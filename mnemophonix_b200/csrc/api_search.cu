@@ -24,6 +24,7 @@ struct mnemo_db {
     void* p = nullptr;
     uint64_t bytes = 0;
   } scratch[16];
+  uint32_t range_ids = 1u << 18;   // ids per pass of the probe's id-range mode; MNEMO_RANGE_IDS shrinks it (tests)
   uint32_t dense_nq = 0, dense_nqs = 0;   // query batch held on the device between mnemo_search_dense_begin / _lists
 };
 
@@ -61,6 +62,10 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
   db->h_entry_start.assign(entry_start, entry_start + n_entries + 1);
   db->n_sigs = entry_start[n_entries];
   db->size = table_size ? table_size : (uint32_t)(db->n_sigs / 2);   // lsh.c:61
+  if (const char* env = getenv("MNEMO_RANGE_IDS")) {   // test hook: many small id ranges on a small database
+    const long v = atol(env);
+    if (v > 0) db->range_ids = (uint32_t)std::min<long>(1L << 18, (v + 127) / 128 * 128);
+  }
   if ((uint64_t)db->size * kTables + 1 >= (1ull << 32) || db->n_sigs * kTables >= (1ull << 32)) {
     ctx->err = "mnemo_db_create: shard too large for 32-bit bucket offsets; use more shards";
     delete db;
@@ -152,6 +157,7 @@ static SearchParams base_params(const mnemo_db* db) {
   }
   p.n_entries = db->n_entries;
   p.n_sigs = (uint32_t)db->n_sigs;
+  p.range_ids = db->range_ids;
   return p;
 }
 

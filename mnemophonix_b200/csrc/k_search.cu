@@ -336,9 +336,6 @@ __device__ __forceinline__ int table_of(const uint32_t* prefix, uint32_t i) {
   return k;   // largest k with prefix[k] <= i
 }
 
-// id-space partition of the hashed multi-pass mode (multiply-shift: no integer division per candidate)
-__device__ __forceinline__ uint32_t hash_part(uint32_t g, uint32_t n_pass) { return __umulhi(g * 2246822519u, n_pass); }
-
 // Candidate de-duplication has two modes, chosen per query signature:
 //   hashed (L <= kPassCap, the usual case for small databases): one pass, bitmap indexed by a hash of the id with
 //     >= 32 bits per candidate; a collision only costs one extra deep check (hits are recomputed exactly);
@@ -346,7 +343,7 @@ __device__ __forceinline__ uint32_t hash_part(uint32_t g, uint32_t n_pass) { ret
 //     [pass * kRangeBits, (pass + 1) * kRangeBits) are one contiguous piece of each of the 25 lists, found by binary
 //     search; each pass streams just those through a bitmap with one bit per id (exact, no false repeats).  Every
 //     candidate id is read once however long the lists are, and passes without candidates cost nothing.
-//   (Shards beyond kMaxRangePasses * kRangeBits signatures fall back to hashed partitions that re-stream the lists.)
+//   Shards of any size: the ranges are walked kMaxRangePasses at a time.
 __global__ void __launch_bounds__(kSearchThreads, 3)
     search_probe_kernel(SearchParams p) {
   extern __shared__ __align__(16) uint32_t sm[];
@@ -355,7 +352,6 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
   uint32_t* set = dup + kDupCap;
   uint32_t* uniq = set + kSetCap;
   __shared__ Probe pr;
-  __shared__ uint32_t seg_begin[kTables], seg_prefix[kTables + 1];   // this pass's piece of each list
   __shared__ uint32_t s_bound[kTables][kMaxRangePasses + 1];
   __shared__ uint32_t s_pref[kMaxRangePasses][kTables + 1];   // range mode: prefix of the piece lengths of every pass
   __shared__ uint32_t s_ndup, s_nuniq, s_gmax;
@@ -388,13 +384,11 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
     if (tid == 0) p.last[qs] = lg;
     return;
   }
-  const uint32_t range_passes = (p.n_sigs + kRangeBits - 1) / kRangeBits;
-  const bool range_mode = L > kPassCap && range_passes <= kMaxRangePasses;   // block-uniform
-  const uint32_t n_pass = range_mode ? range_passes : (L + kPassCap - 1) / kPassCap;
-  const uint32_t per_pass = (L + n_pass - 1) / n_pass;
+  const uint32_t range_ids = p.range_ids;   // ids per pass in range mode (kRangeBits unless a test shrinks it)
+  const uint32_t range_passes = (p.n_sigs + range_ids - 1) / range_ids;
+  const bool range_mode = L > kPassCap;     // block-uniform
   uint32_t bm_words = 64;   // hashed mode: ~64 bitmap bits per candidate, 256 B .. 32 KB
-  while (bm_words < kBitmapMaxWords && bm_words < 2 * per_pass) bm_words <<= 1;
-  if (range_mode) bm_words = kBitmapMaxWords;
+  while (bm_words < kBitmapMaxWords && bm_words < 2 * L) bm_words <<= 1;
   const uint32_t bm_shift = 32 - (31 - __clz(bm_words * 32));
   const uint32_t* __restrict__ dbw = reinterpret_cast<const uint32_t*>(p.db_sigs);
   uint32_t deep = 0, deep_t = 0, gmax = 0;   // deep checks counted per warp (fallback path) / per thread
@@ -450,12 +444,21 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
       v = __reduce_max_sync(0xffffffffu, v);
       if (lane == 0) s_gmax = v;
     }
+    for (uint32_t i = tid; i < kBitmapMaxWords / 4; i += kSearchThreads) reinterpret_cast<uint4*>(bitmap)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+      s_ndup = 0;
+      s_nuniq = 0;
+    }
+    uint32_t listed = 0;   // block-uniform: entries waiting in dup[]
+    // the id ranges are walked kMaxRangePasses at a time (the per-pass tables live in shared memory)
+    for (uint32_t c0 = 0; c0 < range_passes; c0 += kMaxRangePasses) {
+    const uint32_t n_pass = min(kMaxRangePasses, range_passes - c0);
     // where each id range starts in each list
-    for (uint32_t t = tid; t < kTables * (range_passes + 1); t += kSearchThreads) {
-      const uint32_t k = t / (range_passes + 1), j = t - k * (range_passes + 1);
+    for (uint32_t t = tid; t < kTables * (n_pass + 1); t += kSearchThreads) {
+      const uint32_t k = t / (n_pass + 1), j = t - k * (n_pass + 1);
       const uint32_t len = pr.prefix[k + 1] - pr.prefix[k];
       const uint32_t* __restrict__ lst = p.ids + pr.begin[k];
-      const uint32_t target = j * kRangeBits;
+      const uint32_t target = (c0 + j) * range_ids;   // <= n_sigs + range_ids: no overflow
       uint32_t lo = 0, hi = len;
       while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
@@ -464,9 +467,8 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
       }
       s_bound[k][j] = lo;
     }
-    for (uint32_t i = tid; i < kBitmapMaxWords / 4; i += kSearchThreads) reinterpret_cast<uint4*>(bitmap)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    for (uint32_t j = tid; j < range_passes; j += kSearchThreads) {
+    for (uint32_t j = tid; j < n_pass; j += kSearchThreads) {
       uint32_t c = 0;
       for (int k = 0; k < kTables; ++k) {
         s_pref[j][k] = c;
@@ -474,17 +476,12 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
       }
       s_pref[j][kTables] = c;
     }
-    if (tid == 0) {
-      s_ndup = 0;
-      s_nuniq = 0;
-    }
     __syncthreads();
 
     // ---- id ranges: the CTA's latency chain is what bounds this kernel at long lists, so a pass is two barriers:
     // stream (mark + collect repeats) | clear the bitmap for the next pass.  Everything a pass needs was computed
     // above for all passes at once; repeats are scored together every few passes (flush).
     const uint32_t g_last = s_gmax;
-    uint32_t listed = 0;   // block-uniform: entries waiting in dup[]
     auto flush = [&]() {
       if (listed == 0) return;
       const uint32_t ndup = listed;
@@ -521,7 +518,7 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
       const uint32_t Lp = pref[kTables];
       if (Lp < 2) continue;   // nothing can repeat in this id range; no barrier: the tables are read-only by now
       if (listed && listed + Lp / 4 > kDupCap) flush();
-      const uint32_t id_base = pass * kRangeBits;
+      const uint32_t id_base = (c0 + pass) * range_ids;
       {
         uint32_t k = 0, seg_end = pref[1];
         const uint32_t* src = p.ids + pr.begin[0] + s_bound[0][pass];   // src + i addresses candidate i while i < seg_end
@@ -592,40 +589,29 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
       }
       __syncthreads();   // bitmap clean, and nobody still reads s_ndup when the next pass appends
     }
-    flush();
+    if (c0 + kMaxRangePasses < range_passes) {
+      flush();
+      __syncthreads();   // the per-pass tables are rewritten for the next group of ranges
+    } else {
+      flush();
+    }
+    }
   }
 
-  for (uint32_t pass = 0; !range_mode && pass < n_pass; ++pass) {
-    if (tid < kTables) {
-      if (range_mode) {
-        const uint32_t b = s_bound[tid][pass], e = s_bound[tid][pass + 1];
-        seg_begin[tid] = pr.begin[tid] + b;
-        seg_prefix[tid + 1] = e - b;
-      } else {
-        seg_begin[tid] = pr.begin[tid];
-        seg_prefix[tid + 1] = pr.prefix[tid + 1] - pr.prefix[tid];
-      }
-    }
+  // ---- hashed mode: every pass streams the whole lists (pr.begin / pr.prefix) and keeps its hash partition ----
+  for (uint32_t pass = 0; !range_mode && pass < 1; ++pass) {   // hashed mode is one pass (L <= kPassCap)
     if (tid == 0) {
-      seg_prefix[0] = 0;
       s_ndup = 0;
       s_nuniq = 0;
     }
-    __syncthreads();
-    if (tid == 0)
-      for (int k = 0; k < kTables; ++k) seg_prefix[k + 1] += seg_prefix[k];
-    __syncthreads();
-    const uint32_t Lp = seg_prefix[kTables];
-    if (range_mode && Lp < 2) {   // nothing can repeat in this id range
-      __syncthreads();            // (everyone has read Lp before the next pass rewrites the segments)
-      continue;
-    }
+    const uint32_t Lp = L;
     for (uint32_t i = tid; i < bm_words / 4; i += kSearchThreads) reinterpret_cast<uint4*>(bitmap)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
+    const uint32_t* const seg_prefix = pr.prefix;
+    const uint32_t* const seg_begin = pr.begin;
     {
-      const uint32_t id_base = pass * kRangeBits;
-      // flat index over the pass's candidates; the thread's position in the segment table only moves forward, and
-      // four loads are in flight before the first id is used
+      // flat index over the candidates; the thread's position in the list table only moves forward, and four loads
+      // are in flight before the first id is used
       uint32_t k = 0, seg_end = seg_prefix[1];
       const uint32_t* src = p.ids + seg_begin[0];   // src + i addresses candidate i while i < seg_end
       auto locate = [&](uint32_t i) -> const uint32_t* {
@@ -637,14 +623,8 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
         return src + i;
       };
       auto visit = [&](uint32_t g) {
-        uint32_t h;
-        if (range_mode) {
-          h = g - id_base;
-        } else {
-          if (pass == 0) gmax = max(gmax, g);
-          if (n_pass > 1 && hash_part(g, n_pass) != pass) return;
-          h = (g * 2654435761u) >> bm_shift;
-        }
+        gmax = max(gmax, g);
+        const uint32_t h = (g * 2654435761u) >> bm_shift;
         const uint32_t bit = 1u << (h & 31u);
         const uint32_t old = atomicOr(&bitmap[h >> 5], bit);
         if (old & bit) {
@@ -666,7 +646,7 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
       }
       for (; i < Lp; i += kSearchThreads) visit(__ldg(locate(i)));
     }
-    if (!range_mode && pass == 0) {
+    if (pass == 0) {
       gmax = __reduce_max_sync(0xffffffffu, gmax);
       if (lane == 0) atomicMax(&s_gmax, gmax);
     }
@@ -703,7 +683,6 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
         const int k = table_of(seg_prefix, i);
         const uint32_t g = __ldg(p.ids + seg_begin[k] + (i - seg_prefix[k]));
         if (g == gmax) continue;
-        if (!range_mode && n_pass > 1 && hash_part(g, n_pass) != pass) continue;
         uint32_t h = 0, eq = 0;
         if (lane < kTables) {
           const uint32_t w = __ldg(dbw + (uint64_t)g * kTables + lane);

@@ -73,6 +73,7 @@ struct SearchParams {
   uint32_t div_inv, div_shift, div_thr;   // divisibility by size (same_slot, k_search.cu)
   uint32_t n_entries;            // entries in this shard
   uint32_t n_sigs;               // signatures in this shard
+  uint32_t range_ids;            // ids per pass of the probe's id-range mode (multiple of 128, <= 2^18)
   const uint8_t* query_sigs;     // [n_query_sigs][100]
   const uint32_t* query_start;   // [n_queries + 1]
   uint32_t n_queries;

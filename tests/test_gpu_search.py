@@ -133,10 +133,16 @@ def test_sharded_search_equals_single_database(ctx, oracle, corpus):
             s.close()
 
 
-def test_long_buckets_take_the_partitioned_path(ctx, oracle):
-    """Many near-identical signatures make one bucket tens of thousands long and push the number of
-    repeated candidates past the shared-memory short list: exercises the id-space partitions and the
-    list-free fallback of the probe kernel."""
+@pytest.mark.parametrize("range_ids", [0, 1024, 128])
+def test_long_buckets_take_the_partitioned_path(ctx, oracle, range_ids, monkeypatch):
+    """Many near-identical signatures make one bucket thousands long and push the number of repeated candidates
+    past the shared-memory short list: exercises the id-range mode of the probe kernel, with its list-free fallback
+    (default range size: one pass with 6000 repeats), and with small ranges (test hook MNEMO_RANGE_IDS) the repeats
+    collected over many passes and the walk over more than kMaxRangePasses ranges (128 ids per range: 51 ranges)."""
+    if range_ids:
+        monkeypatch.setenv("MNEMO_RANGE_IDS", str(range_ids))
+    else:
+        monkeypatch.delenv("MNEMO_RANGE_IDS", raising=False)
     rng = np.random.RandomState(5)
     proto = rng.randint(0, 250, 100).astype(np.uint8)
     e0 = np.repeat(proto[None, :], 6000, 0)
