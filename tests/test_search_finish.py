@@ -113,3 +113,27 @@ def test_node_lists_of_tree_aligned_shards_merge_to_the_reference_selection(orac
                     lists[i, 0, k] = (e, sc, nn, a)
             got = capi.select_merge(lists, counts)[0]
             assert got[0] == want, (trial, E, shards, got, want)
+
+
+def test_tree_cuts_are_node_boundaries_of_the_merge_tree():
+    """mnemo_tree_cuts: 2^ceil(log2 shards) nodes whose sizes come from msort's n/2 | n - n/2 split, contiguous groups of
+    nodes per shard, every shard at least one node, everything covered, for awkward sizes too."""
+    rng = np.random.RandomState(3)
+    for trial in range(300):
+        E = int(rng.choice([0, 1, 2, 3, 5, 7, 8, 9, 100, 1000, 10000, 12345, 1 << 20, rng.randint(1, 1 << 24)]))
+        shards = int(rng.choice([1, 2, 3, 4, 5, 6, 7, 8, 16]))
+        cuts, node_lo = capi.tree_cuts(E, shards)
+        n_nodes = len(node_lo) - 1
+        assert n_nodes >= shards and n_nodes & (n_nodes - 1) == 0 and n_nodes < 2 * max(shards, 1) + 1
+        assert node_lo[0] == 0 and node_lo[-1] == E and np.all(np.diff(node_lo.astype(np.int64)) >= 0)
+        sizes = np.diff(node_lo.astype(np.int64))
+        assert sizes.max() - sizes.min() <= 1                      # floor / ceil of E / n_nodes
+        # the split rule itself: every internal node's left child has floor(n / 2) entries
+        lo, m = node_lo.astype(np.int64), n_nodes
+        while m > 1:
+            for i in range(0, n_nodes, m):
+                n = lo[i + m] - lo[i]
+                assert lo[i + m // 2] - lo[i] == n // 2
+            m //= 2
+        assert cuts[0] == 0 and cuts[-1] == E and len(cuts) == shards + 1
+        assert all(int(c) in set(node_lo.tolist()) for c in cuts) and np.all(np.diff(cuts.astype(np.int64)) >= 0)
