@@ -103,6 +103,52 @@ def test_read_index_matches_reference(host, ref):
         os.remove(p)
 
 
+def test_large_index_takes_the_threaded_parser_and_matches_reference(host, ref):
+    """A database big enough for the multi-threaded fast path of read_index (mapped file, entries located by one walk
+    over the headers, signature blocks decoded in parallel): same entries as the reference's parser; a corrupt byte
+    deep inside, a short line and a truncated file are rejected with the reference's code by the sequential parser."""
+    import binascii
+    rng = np.random.RandomState(7)
+    tracks = [rng.randint(0, 256, (int(n), 100)).astype(np.uint8) for n in rng.randint(0, 700, 700)]
+    assert sum(len(t) for t in tracks) > 200000
+    parts = []
+    for i, t in enumerate(tracks):
+        hexed = binascii.hexlify(t.tobytes()).decode()
+        parts.append(f"dir/track {i}.wav\nartist {i % 7}\n\nalbum {i % 3}\n{len(t)}\n")
+        parts.append("".join(hexed[200 * k:200 * k + 200] + "\n" for k in range(len(t))))
+    text = "".join(parts)
+    p = tempfile.mktemp()
+    try:
+        open(p, "w").write(text)
+        mine = C.POINTER(refmod.Index)()
+        assert host.read_index(p.encode(), C.byref(mine)) == 0
+        assert mine.contents.n_entries == len(tracks)
+        got = entries_of(mine)
+        for i in (0, 1, 2, 99, 350, 698, 699):                      # spot-check against the reference structures below
+            assert got[i][0] == f"dir/track {i}.wav".encode() and np.array_equal(got[i][4], tracks[i])
+        assert all(np.array_equal(g[4], t) for g, t in zip(got, tracks))
+        rc, theirs = ref.load_index(p)
+        assert rc == 0
+        want = entries_of(theirs)
+        assert all(x[:4] == y[:4] and np.array_equal(x[4], y[4]) for x, y in zip(got, want)) and len(got) == len(want)
+        host.free_index(mine)
+        ref.lib.free_index(theirs)
+        mid = len(text) // 2
+        line_start = text.rfind("\n", 0, mid) + 1
+        while len(text[line_start:text.find("\n", line_start)]) != 200:   # find a signature line near the middle
+            line_start = text.find("\n", line_start) + 1
+        for bad in (text[:line_start + 10] + "g" + text[line_start + 11:],          # not a hex digit
+                    text[:line_start + 10] + text[line_start + 11:],                # one character short
+                    text[:mid]):                                                   # cut in the middle
+            open(p, "w").write(bad)
+            mine = C.POINTER(refmod.Index)()
+            assert host.read_index(p.encode(), C.byref(mine)) == -3
+            assert ref.load_index(p)[0] == -3
+    finally:
+        if os.path.exists(p):
+            os.remove(p)
+
+
 @pytest.mark.parametrize("mutation,code", [
     (lambda t: t[:-50], -3),                               # truncated last signature line
     (lambda t: t.replace("\n", "", 1), "ours:-3"),         # count line is not a number: DECODING_ERROR by the source, but the
