@@ -203,78 +203,6 @@ def search_section(ctx, ref_queries: int = 8, n_tracks: int = 96, seconds: float
     return out
 
 
-def search_c4_section(ctx, device, n_tracks: int = 10000, seconds: float = 30.0, chunk: int = 50, ref_queries: int = 4):
-    """BASELINE.json configs[3] on this GPU: n_tracks synthetic 30-second tracks (synthesised with torch on the GPU:
-    mnemophonix_b200.synth.synth_tracks_torch) indexed through the C ABI from pinned host buffers, then one 5-second
-    excerpt per track (starting at 10 s + 1234 samples, not hop-aligned) re-fingerprinted and searched against the
-    resulting database: LSH build, probe, scoring and the exact final ranking all on the GPU; the reference answers a
-    sample of the same queries against the same database."""
-    import torch
-    from mnemophonix_b200 import capi, synth
-    q_off, q_len = int(10.0 * 44100) + 1234, 5 * 44100
-    entries, queries = [], []
-    t_index = 0.0
-    for c0 in range(0, n_tracks, chunk):
-        ids = list(range(c0, min(n_tracks, c0 + chunk)))
-        pcm = synth.synth_tracks_torch(ids, seconds, device)
-        host = torch.empty(pcm.shape, dtype=torch.int16).pin_memory()
-        host.copy_(pcm)
-        torch.cuda.synchronize()
-        arr = host.numpy()
-        t0 = time.perf_counter()
-        sigs, st = ctx.index_pcm_batch([arr[i].reshape(-1, 1) for i in range(len(ids))])
-        qs, qst = ctx.index_pcm_batch([np.ascontiguousarray(arr[i, q_off:q_off + q_len]).reshape(-1, 1) for i in range(len(ids))])
-        t_index += time.perf_counter() - t0
-        assert not any(st) and not any(qst)
-        entries += sigs
-        queries += qs
-        del pcm, host
-    t0 = time.perf_counter()
-    db = capi.Db(ctx, entries)
-    t_build = time.perf_counter() - t0
-    prepared = capi.Db.prepare(queries)
-    db.search(prepared)
-    reps = 3
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        res, (L, D) = db.search(prepared)
-    dt = (time.perf_counter() - t0) / reps
-    n_qsig = int(prepared[1][-1])
-    out = {"workload": f"{n_tracks} five-second excerpts x {n_tracks}-track database ({seconds:g} s tracks from GPU-synthesised "
-                       "PCM), one GPU, host buffers in, answers out",
-           "queries_per_s": n_tracks / dt, "s_per_batch": dt, "db_signatures": int(sum(len(e) for e in entries)),
-           "query_signatures": n_qsig, "lsh_build_s": t_build, "index_s": t_index,
-           "probed_nodes_per_query_signature": L / n_qsig, "deep_checks_per_query_signature": D / n_qsig,
-           "algorithmic_GBps": (n_qsig * 300 + 4 * L + 100 * D + 16 * n_tracks) / dt / 1e9,
-           "excerpts_identified": int(sum(int(r[0] == i) for i, r in enumerate(res)))}
-    try:
-        from oracle import ref as refmod
-        import ctypes as C
-        if refmod.available() and ref_queries:
-            r = refmod.Ref()
-            keep, ents = [], (C.POINTER(refmod.IndexEntry) * len(entries))()
-            for i, e in enumerate(entries):
-                e = np.ascontiguousarray(e)
-                sg = refmod.Signatures(len(e), C.cast(e.ctypes.data, C.POINTER(C.c_uint8 * 100)))
-                ie = refmod.IndexEntry(b"t", b"", b"", b"", C.pointer(sg))
-                keep.append((e, sg, ie))
-                ents[i] = C.pointer(ie)
-            idx = refmod.Index(len(entries), C.cast(ents, C.POINTER(C.POINTER(refmod.IndexEntry))))
-            t0 = time.perf_counter()
-            lsh = r.lib.create_hash_tables(C.byref(idx))
-            out["reference_lsh_build_s"] = time.perf_counter() - t0
-            pick = np.linspace(0, n_tracks - 1, ref_queries).astype(int)
-            t0 = time.perf_counter()
-            ref_res = [r.search(np.ascontiguousarray(queries[i]), C.pointer(idx), lsh) for i in pick]
-            out["reference_queries_per_s_1thread"] = len(pick) / (time.perf_counter() - t0)
-            out["identical_to_reference_on_sample"] = ref_res == [res[i][0] for i in pick]
-    except Exception as exc:   # the checker is optional here
-        out["reference_check_error"] = repr(exc)
-    db.close()
-    return out
-
-
 # ----------------------------------------------------------------------- reference arm ----
 def reference_throughput(seconds_sample: float, channels: int, steps: int, warmup: int, variant: str = "O2"):
     """Times the unmodified reference (oracle/_ref -O2, generate_fingerprint on a WAV file) on the host
@@ -348,7 +276,9 @@ def main():
     ap.add_argument("--cpu-sample-seconds", type=float, default=1200.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--search-c4-tracks", type=int, default=10000,
-                    help="database size of the configs[3] search section (N=1 only; 0 = skip)")
+                    help="database size of the configs[3] search section, sharded over the N GPUs (0 = skip)")
+    ap.add_argument("--search-c4-ref-queries", type=int, default=64,
+                    help="queries of the configs[3] section also answered by the reference / oracle on rank 0")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -358,7 +288,10 @@ def main():
                           f"track per GPU (BASELINE.json configs[1]); PCM {args.seconds * 44100 * 2 * args.channels / 1e9:.2f} GB "
                           "per track > 126 MB L2, so no L2 flush between steps",
               "tracks_per_gpu": 1, "seconds_per_track": args.seconds, "channels": args.channels,
-              "parallelism": f"tracks sharded across {args.gpus} GPU(s), no data-path collective"}
+              "parallelism": f"tracks sharded across {args.gpus} GPU(s), no data-path collective",
+              "reference_arm_sample": f"--impl reference times {args.cpu_sample_seconds:.0f} s excerpts of this track (cores // 2 "
+                                      "concurrent processes x the library's 8 threads), not the whole 2 h file: audio-hours/s "
+                                      "does not depend on the length"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -546,11 +479,17 @@ def main():
 
     if world == 1 and rank == 0:
         line["search"] = search_section(ctx)
-        if args.search_c4_tracks > 0:
-            try:
-                line["search_c4"] = search_c4_section(ctx, torch.device("cuda", local_rank), args.search_c4_tracks)
-            except Exception as exc:   # a supplementary section must never cost the bench line
-                line["search_c4"] = {"error": repr(exc)}
+    if args.search_c4_tracks > 0:
+        # BASELINE.json configs[3] at every N: the database sharded over the N ranks, NCCL all-gathers + GPU merge,
+        # every answer compared with the single-GPU search, a sample with the reference and the oracle's dense rows
+        from mnemophonix_b200 import workloads
+        try:
+            c4 = workloads.c4_search(ctx, stream, torch.device("cuda", local_rank), rank, world, dist,
+                                     n_tracks=args.search_c4_tracks, ref_queries=args.search_c4_ref_queries)
+        except Exception as exc:   # a supplementary section must never cost the bench line
+            c4 = {"error": repr(exc)}
+        if rank == 0:
+            line["search_c4"] = c4
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         r = reference_throughput(args.cpu_sample_seconds, args.channels, 1, 0)
         if r is not None:

@@ -129,9 +129,14 @@ int64_t mnemo_db_get_matches(mnemo_db* db, const uint8_t* sig, uint32_t* pairs_o
 int mnemo_search_batch(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
                        uint32_t n_queries, mnemo_match* out, uint64_t* stats);
 
-/* Sharded search: per-query candidate records of THIS shard, to be merged across shards
- * (concatenate the records of all shards, e.g. with an NCCL all-gather) and finished with
- * mnemo_search_finish.  See DESIGN.md "search, multi-GPU". */
+/* The dense rows search.c:55-59 accumulates, for parity checks: score_out / n_matches_out are [n_queries][n_entries of this
+ * shard] (host), before any cross-shard fix-up. */
+int mnemo_search_scores(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start, uint32_t n_queries,
+                        uint32_t* score_out, uint32_t* n_matches_out);
+
+/* Record form of a sharded search (arbitrary entry ranges; diagnostic — the production protocol is the ranked one
+ * below): per-query candidate records of THIS shard, to be concatenated over the shards and finished on the host with
+ * mnemo_search_finish. */
 typedef struct mnemo_cand {
   uint32_t query;
   int32_t entry;      /* global entry index */
@@ -152,17 +157,27 @@ int mnemo_search_finish(const mnemo_cand* cands, uint64_t n_cands, const mnemo_l
                         uint32_t n_shards, const uint32_t* query_start, uint32_t n_queries,
                         uint32_t n_entries_total, mnemo_match* out);
 
-/* Sharded search ranked on the GPUs (search.c:170-193 needs only the first ten records of glibc's merge sort over all
- * entries; every node of that merge tree can be ranked where its entries live).  The database is sharded on node
- * boundaries of the tree: mnemo_tree_cuts fills cuts[n_shards + 1] (entry ranges of the shards) and node_lo[n_nodes + 1]
- * (entry ranges of the n_nodes = 2^ceil(log2 n_shards) nodes, contiguous groups of which make up the shards) and
- * returns n_nodes.  Per query batch: mnemo_search_dense_begin probes this shard (accumulators stay on the device) and
- * reports has[s] = the shard holds a candidate for query signature s; after the ranks have exchanged those flags,
- * mnemo_search_dense_lists takes has_higher[s] = some shard with greater entry indices has a candidate (the globally
- * greatest (entry, signature) group, which search.c:147-165 never scores, then lives there and this shard's own greatest
- * group is scored after all), ranks each of the shard's nodes (node_bounds[n_nodes + 1], global entry indices) and
- * returns lists_out[node][query][10] + counts_out[node][query].  mnemo_select_merge (host) merges the lists of all
- * n_nodes nodes, in node order, through the top levels of the tree and applies the thresholds. */
+/* Sharded search ranked on the GPUs: THE multi-GPU protocol (search.c:170-193 needs only the first ten records of
+ * glibc's merge sort over all entries; every node of that merge tree can be ranked where its entries live).  The database
+ * is sharded on node boundaries of the tree: mnemo_tree_cuts fills cuts[n_shards + 1] (entry ranges of the shards) and
+ * node_lo[n_nodes + 1] (entry ranges of the n_nodes = 2^ceil(log2 n_shards) nodes; shard r owns nodes
+ * r * n_nodes / n_shards .. (r + 1) * n_nodes / n_shards - 1) and returns n_nodes.
+ *
+ * Device-resident form (everything asynchronous on the context's stream; the two all-gathers between the calls are the
+ * caller's, e.g. NCCL on the same stream).  Per tile of at most mnemo_db_tile_queries() queries:
+ *   mnemo_search_dense_begin_dev   probes this shard (host query signatures in, accumulators stay on the device) and
+ *                                  writes d_has_out[s] = the shard holds a candidate for query signature s;
+ *   -- all-gather of the flags: d_has_all[n_shards][n_query_signatures] --
+ *   mnemo_search_dense_lists_dev   where a higher shard holds candidates the globally greatest (entry, signature)
+ *                                  group, which search.c:147-165 never scores, lives there, so this shard's own
+ *                                  greatest group is scored after all; then every owned node is ranked:
+ *                                  d_lists_out[node][query][10] + d_counts_out[node][query] (device memory; a shard's
+ *                                  block of mnemo_shard_record_bytes() is lists followed by counts);
+ *   -- all-gather of the blocks --
+ *   mnemo_select_merge_dev         merges the lists of all nodes through the top levels of the tree on the GPU, applies
+ *                                  the thresholds, returns 12 bytes per query to the host (synchronises).
+ * Host-pointer forms of the same steps: mnemo_search_dense_begin / _lists (has_higher[s] = some shard with greater
+ * entry indices has a candidate) and mnemo_select_merge (lists of ALL nodes in node order). */
 typedef struct mnemo_sel_rec {
   int32_t entry;      /* global entry index */
   float score;
@@ -170,30 +185,25 @@ typedef struct mnemo_sel_rec {
   float avg;          /* score / n_matches (search.c:66-67) */
 } mnemo_sel_rec;
 uint32_t mnemo_tree_cuts(uint32_t n_entries_total, uint32_t n_shards, uint32_t* cuts, uint32_t* node_lo, uint32_t node_cap);
+uint32_t mnemo_db_tile_queries(const mnemo_db* db);   /* queries whose dense accumulators fit the budget (1 GiB) */
+int mnemo_search_dense_begin_dev(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start, uint32_t n_queries,
+                                 uint8_t* d_has_out /* device, one per query signature */);
+int mnemo_search_dense_lists_dev(mnemo_db* db, const uint8_t* d_has_all /* device */, uint32_t n_shards, uint32_t shard,
+                                 const uint32_t* node_bounds /* host */, uint32_t n_nodes, mnemo_sel_rec* d_lists_out,
+                                 uint32_t* d_counts_out);
+uint64_t mnemo_shard_record_bytes(uint32_t nodes_per_shard, uint32_t n_queries);
+int mnemo_select_merge_dev(mnemo_ctx* ctx, const void* d_gathered /* device: n_shards blocks */, uint32_t n_shards,
+                           uint32_t n_nodes, uint32_t nodes_per_shard, uint32_t n_queries, mnemo_match* out /* host */);
+int mnemo_search_dense_stats(mnemo_db* db, uint64_t* stats /* L, D of the last probe */);
+/* Diagnostics for parity tests: the accumulator row (score sum, n_matches per entry of this shard, search.c:55-59) of
+ * one query of the batch held since mnemo_search_dense_begin*, after the fix-up when _lists has run. */
+int mnemo_search_dense_read(mnemo_db* db, uint32_t query, uint32_t* score_out, uint32_t* n_matches_out);
 int mnemo_search_dense_begin(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start, uint32_t n_queries,
                              uint8_t* has_out /* one per query signature */, uint64_t* stats);
 int mnemo_search_dense_lists(mnemo_db* db, const uint8_t* has_higher, const uint32_t* node_bounds, uint32_t n_nodes,
                              mnemo_sel_rec* lists_out, uint32_t* counts_out);
 int mnemo_select_merge(const mnemo_sel_rec* lists, const uint32_t* counts, uint32_t n_nodes, uint32_t n_queries,
                        mnemo_match* out);
-
-/* Peer-memory merge (one process per GPU, NVLink): instead of returning its records to the host, a shard's
- * search epilogue writes them straight into a result buffer in the HBM of the rank that merges.  The owner
- * creates the buffer and hands the 64-byte CUDA IPC handle to the other ranks (any host channel); they open
- * it; every rank then calls mnemo_search_shard_push with its shard rank; after a host-side barrier the owner
- * calls mnemo_result_finish.  In one process (several shards on one GPU) pass the owner's handle object
- * itself to every push.  cap_cands bounds the total number of (query, entry) records of all shards. */
-typedef struct mnemo_result mnemo_result;
-int mnemo_result_create(mnemo_ctx* ctx, uint32_t cap_cands, uint32_t n_shards, uint32_t n_query_sigs,
-                        mnemo_result** out, uint8_t ipc_handle[64]);
-int mnemo_result_open(mnemo_ctx* ctx, const uint8_t ipc_handle[64], uint32_t cap_cands, uint32_t n_shards,
-                      uint32_t n_query_sigs, mnemo_result** out);
-int mnemo_result_reset(mnemo_result* r);        /* owner only; before each query batch */
-void mnemo_result_destroy(mnemo_result* r);
-int mnemo_search_shard_push(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
-                            uint32_t n_queries, mnemo_result* dst, uint32_t shard_rank, uint64_t* stats);
-int mnemo_result_finish(mnemo_result* r, const uint32_t* query_start, uint32_t n_queries,
-                        uint32_t n_entries_total, mnemo_match* out);
 
 /* ---- self tests of the exact-arithmetic building blocks (run on the device) ---- */
 /* Compares the device logf against host logf for every float in [lo_bits, hi_bits]; returns the

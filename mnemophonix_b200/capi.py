@@ -98,12 +98,16 @@ def lib() -> C.CDLL:
             L.mnemo_search_batch.argtypes = [vp, vp, vp, u32, vp, vp]
             L.mnemo_search_shard.argtypes = [vp, vp, vp, u32, vp, u64, C.POINTER(u64), vp, vp]
             L.mnemo_search_finish.argtypes = [vp, u64, vp, u32, vp, u32, u32, vp]
-            L.mnemo_result_create.argtypes = [vp, u32, u32, u32, C.POINTER(vp), vp]
-            L.mnemo_result_open.argtypes = [vp, vp, u32, u32, u32, C.POINTER(vp)]
-            L.mnemo_result_reset.argtypes = [vp]
-            L.mnemo_result_destroy.argtypes = [vp]
-            L.mnemo_search_shard_push.argtypes = [vp, vp, vp, u32, vp, u32, vp]
-            L.mnemo_result_finish.argtypes = [vp, vp, u32, u32, vp]
+            L.mnemo_search_scores.argtypes = [vp, vp, vp, u32, vp, vp]
+            L.mnemo_db_tile_queries.argtypes = [vp]
+            L.mnemo_db_tile_queries.restype = u32
+            L.mnemo_search_dense_begin_dev.argtypes = [vp, vp, vp, u32, vp]
+            L.mnemo_search_dense_lists_dev.argtypes = [vp, vp, u32, u32, vp, u32, vp, vp]
+            L.mnemo_shard_record_bytes.argtypes = [u32, u32]
+            L.mnemo_shard_record_bytes.restype = u64
+            L.mnemo_select_merge_dev.argtypes = [vp, vp, u32, u32, u32, u32, vp]
+            L.mnemo_search_dense_stats.argtypes = [vp, vp]
+            L.mnemo_search_dense_read.argtypes = [vp, u32, vp, vp]
         _lib = L
     return _lib
 
@@ -351,7 +355,49 @@ class Db:
         self.ctx._check(rc, "mnemo_search_batch")
         return [(out[i].entry, out[i].score, out[i].n_matches) for i in range(nq)], (stats[0], stats[1])
 
+    def scores(self, queries):
+        """Dense per-entry rows of search.c:55-59 for a (small) batch: (score[nq, n_entries], n_matches[nq, n_entries]) u32."""
+        qs, qstart = queries if isinstance(queries, tuple) else _concat(queries)
+        nq = len(qstart) - 1
+        sc = np.zeros((max(nq, 1), max(self.n_entries, 1)), np.uint32)
+        nm = np.zeros_like(sc)
+        buf = qs if qs.shape[0] else np.zeros((1, SIG_LEN), np.uint8)
+        rc = lib().mnemo_search_scores(self.h, buf.ctypes.data, qstart.ctypes.data, nq, sc.ctypes.data, nm.ctypes.data)
+        self.ctx._check(rc, "mnemo_search_scores")
+        return sc[:nq, :self.n_entries], nm[:nq, :self.n_entries]
+
+    @property
+    def tile_queries(self) -> int:
+        return int(lib().mnemo_db_tile_queries(self.h))
+
     # -- sharded search ranked on the GPUs (DESIGN.md "search, multi-GPU") --
+    def dense_begin_dev(self, queries, d_has_ptr: int):
+        """Device-resident form: probe this shard, has flags into device memory at d_has_ptr (async on the context's stream)."""
+        qs, qstart = queries if isinstance(queries, tuple) else _concat(queries)
+        nq = len(qstart) - 1
+        buf = qs if qs.shape[0] else np.zeros((1, SIG_LEN), np.uint8)
+        rc = lib().mnemo_search_dense_begin_dev(self.h, buf.ctypes.data, qstart.ctypes.data, nq, C.c_void_p(d_has_ptr))
+        self.ctx._check(rc, "mnemo_search_dense_begin_dev")
+        self._dense_nq = nq
+
+    def dense_lists_dev(self, d_has_all_ptr: int, n_shards: int, shard: int, node_bounds, d_lists_ptr: int, d_counts_ptr: int):
+        node_bounds = np.ascontiguousarray(node_bounds, np.uint32)
+        rc = lib().mnemo_search_dense_lists_dev(self.h, C.c_void_p(d_has_all_ptr), n_shards, shard, node_bounds.ctypes.data,
+                                                len(node_bounds) - 1, C.c_void_p(d_lists_ptr), C.c_void_p(d_counts_ptr))
+        self.ctx._check(rc, "mnemo_search_dense_lists_dev")
+
+    def dense_stats(self):
+        stats = (C.c_uint64 * 2)()
+        self.ctx._check(lib().mnemo_search_dense_stats(self.h, stats), "mnemo_search_dense_stats")
+        return int(stats[0]), int(stats[1])
+
+    def dense_read(self, query: int):
+        """Accumulator row of one query of the held batch: (score[n_entries], n_matches[n_entries]) u32, this shard's entries."""
+        sc = np.zeros(max(self.n_entries, 1), np.uint32)
+        nm = np.zeros_like(sc)
+        self.ctx._check(lib().mnemo_search_dense_read(self.h, query, sc.ctypes.data, nm.ctypes.data), "mnemo_search_dense_read")
+        return sc[:self.n_entries], nm[:self.n_entries]
+
     def dense_begin(self, queries):
         """Probe this shard; the accumulators stay on the device.  Returns (has[n_query_sigs] u8, (L, D))."""
         qs, qstart = queries if isinstance(queries, tuple) else _concat(queries)
@@ -399,57 +445,6 @@ class Db:
         return c, l, qstart, (stats[0], stats[1])
 
 
-class Result:
-    """Result buffer of the merging rank (device memory).  Result.create() on the owner returns the object and a
-    64-byte CUDA IPC handle; other processes Result.open() it and their shards push into it over NVLink."""
-
-    def __init__(self, ctx, h, owner, cap, n_shards, n_qsigs):
-        self.ctx, self.h, self.owner, self.cap, self.n_shards, self.n_qsigs = ctx, h, owner, cap, n_shards, n_qsigs
-
-    @classmethod
-    def create(cls, ctx: Context, cap: int, n_shards: int, n_qsigs: int):
-        h = C.c_void_p()
-        handle = (C.c_uint8 * 64)()
-        ctx._check(lib().mnemo_result_create(ctx.h, cap, n_shards, n_qsigs, C.byref(h), handle), "mnemo_result_create")
-        return cls(ctx, h, True, cap, n_shards, n_qsigs), bytes(handle)
-
-    @classmethod
-    def open(cls, ctx: Context, handle: bytes, cap: int, n_shards: int, n_qsigs: int):
-        h = C.c_void_p()
-        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
-        ctx._check(lib().mnemo_result_open(ctx.h, buf, cap, n_shards, n_qsigs, C.byref(h)), "mnemo_result_open")
-        return cls(ctx, h, False, cap, n_shards, n_qsigs)
-
-    def reset(self):
-        self.ctx._check(lib().mnemo_result_reset(self.h), "mnemo_result_reset")
-
-    def push(self, db: "Db", queries, shard_rank: int):
-        qs, qstart = queries if isinstance(queries, tuple) else _concat(queries)
-        stats = (C.c_uint64 * 2)()
-        buf = qs if qs.shape[0] else np.zeros((1, SIG_LEN), np.uint8)
-        rc = lib().mnemo_search_shard_push(db.h, buf.ctypes.data, qstart.ctypes.data, len(qstart) - 1, self.h, shard_rank, stats)
-        db.ctx._check(rc, "mnemo_search_shard_push")
-        return stats[0], stats[1]
-
-    def finish(self, qstart: np.ndarray, n_entries_total: int):
-        qstart = np.ascontiguousarray(qstart, np.uint32)
-        nq = len(qstart) - 1
-        out = (Match * max(nq, 1))()
-        self.ctx._check(lib().mnemo_result_finish(self.h, qstart.ctypes.data, nq, n_entries_total, out), "mnemo_result_finish")
-        return [(out[i].entry, out[i].score, out[i].n_matches) for i in range(nq)]
-
-    def close(self):
-        if self.h:
-            lib().mnemo_result_destroy(self.h)
-            self.h = C.c_void_p()
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
-
-
 SEL_DTYPE = np.dtype([("entry", "<i4"), ("score", "<f4"), ("n_matches", "<i4"), ("avg", "<f4")])
 
 
@@ -463,6 +458,18 @@ def tree_cuts(n_entries_total: int, n_shards: int):
     got = lib().mnemo_tree_cuts(n_entries_total, n_shards, cuts.ctypes.data, node_lo.ctypes.data, n_nodes + 1)
     assert got == n_nodes
     return cuts, node_lo
+
+
+def shard_record_bytes(nodes_per_shard: int, n_queries: int) -> int:
+    return int(lib().mnemo_shard_record_bytes(nodes_per_shard, n_queries))
+
+
+def select_merge_dev(ctx: Context, d_gathered_ptr: int, n_shards: int, n_nodes: int, nodes_per_shard: int, n_queries: int):
+    """Top levels of the ranking tree on the GPU over the all-gathered shard blocks (device memory)."""
+    out = (Match * max(n_queries, 1))()
+    rc = lib().mnemo_select_merge_dev(ctx.h, C.c_void_p(d_gathered_ptr), n_shards, n_nodes, nodes_per_shard, n_queries, out)
+    ctx._check(rc, "mnemo_select_merge_dev")
+    return [(out[i].entry, out[i].score, out[i].n_matches) for i in range(n_queries)]
 
 
 def select_merge(lists: np.ndarray, counts: np.ndarray):

@@ -1,4 +1,8 @@
 // api_search.cu — C ABI (include/mnemo_cuda.h): LSH database handle, batched / sharded search.
+//
+// One probe driver (probe_batch / probe_tile) serves every entry point: the query signatures go to the device once,
+// the queries are processed in tiles whose dense per-(query, entry) accumulators fit a fixed budget, and each tile is
+// handed to the entry point's own epilogue (exact ranking on the GPU, candidate records, or the ranked-shard lists).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -23,9 +27,15 @@ struct mnemo_db {
   struct Scratch {
     void* p = nullptr;
     uint64_t bytes = 0;
-  } scratch[16];
-  uint32_t range_ids = 1u << 18;   // ids per pass of the probe's id-range mode; MNEMO_RANGE_IDS shrinks it (tests)
+  } scratch[20];
+  uint32_t range_ids = 1u << 18;      // ids per pass of the probe's id-range mode; MNEMO_RANGE_IDS shrinks it (tests)
+  uint64_t acc_budget = 1ull << 30;   // bytes of dense accumulators per query tile; MNEMO_ACC_BYTES shrinks it (tests)
   uint32_t dense_nq = 0, dense_nqs = 0;   // query batch held on the device between mnemo_search_dense_begin / _lists
+};
+
+enum {   // scratch slots
+  kScrQ = 0, kScrQstart, kScrAccS, kScrAccN, kScrLast, kScrStats, kScrTotal, kScrQbase, kScrQcnt, kScrCands, kScrLeaf,
+  kScrSel, kScrSelCnt, kScrOut, kScrHas, kScrHasAll, kScrLists
 };
 
 static cudaError_t scratch_get(mnemo_db* db, int slot, uint64_t bytes, void** out) {
@@ -49,6 +59,11 @@ static cudaError_t dalloc(T** p, uint64_t count) {
   return cudaMalloc((void**)p, (count ? count : 1) * sizeof(T));
 }
 
+#define TRY(x)                      \
+  do {                              \
+    if (e == cudaSuccess) e = (x);  \
+  } while (0)
+
 extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32_t* entry_start, uint32_t n_entries,
                                uint32_t table_size, uint32_t entry_base, mnemo_db** out) {
   if (!ctx || !out || !entry_start) return -3;
@@ -66,6 +81,10 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
     const long v = atol(env);
     if (v > 0) db->range_ids = (uint32_t)std::min<long>(1L << 18, (v + 127) / 128 * 128);
   }
+  if (const char* env = getenv("MNEMO_ACC_BYTES")) {   // test hook: several query tiles on a small batch
+    const long long v = atoll(env);
+    if (v > 0) db->acc_budget = (uint64_t)v;
+  }
   if ((uint64_t)db->size * kTables + 1 >= (1ull << 32) || db->n_sigs * kTables >= (1ull << 32)) {
     ctx->err = "mnemo_db_create: shard too large for 32-bit bucket offsets; use more shards";
     delete db;
@@ -77,10 +96,6 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
   void* d_temp = nullptr;
   const size_t temp_bytes = (db->size && db->n_sigs) ? lsh_sort_temp_bytes(db->n_sigs, db->size) : 0;
   cudaError_t e = cudaSuccess;
-#define TRY(x)                      \
-  do {                              \
-    if (e == cudaSuccess) e = (x);  \
-  } while (0)
   TRY(dalloc(&db->d_sigs, db->n_sigs * kSigLen + 4));
   TRY(dalloc(&db->d_entry_start, (uint64_t)n_entries + 1));
   TRY(dalloc(&db->d_sig_entry, db->n_sigs));
@@ -103,7 +118,6 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
     TRY(cudaGetLastError());
   }
   TRY(cudaStreamSynchronize(st));
-#undef TRY
   cudaFree(d_counts);
   cudaFree(d_cursor);
   cudaFree(d_block_sums);
@@ -133,6 +147,12 @@ extern "C" void mnemo_db_destroy(mnemo_db* db) {
 }
 
 extern "C" uint32_t mnemo_db_table_size(const mnemo_db* db) { return db ? db->size : 0; }
+
+extern "C" uint32_t mnemo_db_tile_queries(const mnemo_db* db) {
+  if (!db) return 0;
+  const uint64_t per_query = (uint64_t)std::max<uint32_t>(db->n_entries, 1) * 8;
+  return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(0xFFFFFFFFu, db->acc_budget / per_query));
+}
 
 static SearchParams base_params(const mnemo_db* db) {
   SearchParams p;
@@ -174,24 +194,26 @@ extern "C" int64_t mnemo_db_get_matches(mnemo_db* db, const uint8_t* sig, uint32
   cudaStream_t st = ctx->stream;
   uint8_t* d_q = nullptr;
   uint32_t *d_out = nullptr, *d_counts = nullptr;
-  const uint32_t cap = (uint32_t)std::min<uint64_t>(db->n_sigs * kTables, 1u << 26);
-  cudaError_t e = dalloc(&d_q, 128);
-  if (e == cudaSuccess) e = dalloc(&d_out, cap);
-  if (e == cudaSuccess) e = dalloc(&d_counts, kTables);
   std::vector<uint32_t> ids, counts(kTables);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_q, sig, kSigLen, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) {
-    SearchParams p = base_params(db);
-    p.query_sigs = d_q;
-    launch_search_gather(p, d_out, cap, d_counts, st);
-    e = cudaMemcpyAsync(counts.data(), d_counts, 4 * kTables, cudaMemcpyDeviceToHost, st);
-  }
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  SearchParams p = base_params(db);
+  cudaError_t e = dalloc(&d_q, 128);
+  TRY(dalloc(&d_counts, kTables));
+  TRY(cudaMemcpyAsync(d_q, sig, kSigLen, cudaMemcpyHostToDevice, st));
+  p.query_sigs = d_q;
+  // first the list lengths alone, then a gather buffer of exactly that size: nothing is truncated however long
+  // the chains are
+  if (e == cudaSuccess) launch_search_gather(p, nullptr, 0, d_counts, st);
+  TRY(cudaMemcpyAsync(counts.data(), d_counts, 4 * kTables, cudaMemcpyDeviceToHost, st));
+  TRY(cudaStreamSynchronize(st));
   uint64_t total = 0;
-  if (e == cudaSuccess) {
+  if (e == cudaSuccess)
     for (uint32_t c : counts) total += c;
-    ids.resize(std::min<uint64_t>(total, cap));
-    if (!ids.empty()) e = cudaMemcpy(ids.data(), d_out, ids.size() * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && total) {
+    TRY(dalloc(&d_out, total));
+    if (e == cudaSuccess) launch_search_gather(p, d_out, (uint32_t)total, d_counts, st);
+    ids.resize(total);
+    TRY(cudaMemcpyAsync(ids.data(), d_out, total * 4, cudaMemcpyDeviceToHost, st));
+    TRY(cudaStreamSynchronize(st));
   }
   cudaFree(d_q);
   cudaFree(d_out);
@@ -203,7 +225,6 @@ extern "C" int64_t mnemo_db_get_matches(mnemo_db* db, const uint8_t* sig, uint32
   for (int k = 0; k < kTables; k++) off[k + 1] = off[k] + counts[k];
   uint64_t w = 0;
   for (int k = kTables - 1; k >= 0; k--) {
-    if (off[k + 1] > ids.size()) continue;
     std::sort(ids.begin() + off[k], ids.begin() + off[k + 1]);
     for (uint32_t i = off[k]; i < off[k + 1]; i++, w++) {
       if (w >= cap_pairs) continue;
@@ -215,96 +236,199 @@ extern "C" int64_t mnemo_db_get_matches(mnemo_db* db, const uint8_t* sig, uint32
   return (int64_t)total;
 }
 
-// ------------------------------------------------------------------ search ----
+// ------------------------------------------------------------------ the probe driver ----
 
-// Records of all queries, in (query, entry) order, appended to `out` (no capacity limit).
-static int search_shard_impl(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start, uint32_t n_queries,
-                             std::vector<mnemo_cand>& out, mnemo_lastgroup* last, uint64_t* stats) {
-  if (!db || !query_start) return -3;
+struct ProbeBatch {
+  uint8_t* d_q = nullptr;
+  uint32_t *d_qstart = nullptr, *d_acc_s = nullptr, *d_acc_n = nullptr;
+  mnemo_lastgroup_dev* d_last = nullptr;
+  unsigned long long* d_stats = nullptr;
+  uint32_t n_queries = 0, n_qsigs = 0, tile = 0;
+  std::vector<uint32_t> h_qstart;
+};
+
+static bool db_is_empty(const mnemo_db* db) { return db->size == 0 || db->n_sigs == 0 || db->n_entries == 0; }
+
+// Query signatures to the device, scratch for one tile of `tile` queries (0 = as many as the budget allows).
+static cudaError_t probe_batch(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start, uint32_t n_queries,
+                               uint32_t tile, ProbeBatch& b) {
+  cudaStream_t st = db->ctx->stream;
+  b.n_queries = n_queries;
+  b.n_qsigs = query_start[n_queries];
+  b.tile = std::max<uint32_t>(1, std::min(n_queries, tile ? tile : mnemo_db_tile_queries(db)));
+  const uint64_t cells = (uint64_t)b.tile * db->n_entries;
+  cudaError_t e = cudaSuccess;
+  TRY(scratch_get(db, kScrQ, (uint64_t)b.n_qsigs * kSigLen + 4, (void**)&b.d_q));
+  TRY(scratch_get(db, kScrQstart, 4ull * ((uint64_t)b.tile + 1), (void**)&b.d_qstart));
+  TRY(scratch_get(db, kScrAccS, 4ull * cells, (void**)&b.d_acc_s));
+  TRY(scratch_get(db, kScrAccN, 4ull * cells, (void**)&b.d_acc_n));
+  TRY(scratch_get(db, kScrLast, sizeof(mnemo_lastgroup_dev) * (uint64_t)b.n_qsigs, (void**)&b.d_last));
+  TRY(scratch_get(db, kScrStats, 32, (void**)&b.d_stats));
+  TRY(cudaMemcpyAsync(b.d_q, query_sigs, (uint64_t)b.n_qsigs * kSigLen, cudaMemcpyHostToDevice, st));
+  TRY(cudaMemsetAsync(b.d_stats, 0, 32, st));
+  return e;
+}
+
+// Probe + score queries [q0, q0 + nq) into the (zeroed) accumulators [nq][n_entries]; last-group records of the
+// tile's query signatures land in d_last at their batch-wide index.
+static cudaError_t probe_tile(mnemo_db* db, ProbeBatch& b, const uint32_t* query_start, uint32_t q0, uint32_t nq) {
+  cudaStream_t st = db->ctx->stream;
+  cudaError_t e = cudaSuccess;
+  // tile-local query_start (offsets relative to the tile's first signature); a pageable source is staged by the
+  // driver before cudaMemcpyAsync returns, so the vector can be rewritten for the next tile
+  b.h_qstart.assign(query_start + q0, query_start + q0 + nq + 1);
+  const uint32_t s0 = b.h_qstart[0];
+  for (auto& v : b.h_qstart) v -= s0;
+  const uint32_t ns = b.h_qstart[nq];
+  TRY(cudaMemcpyAsync(b.d_qstart, b.h_qstart.data(), 4ull * (nq + 1), cudaMemcpyHostToDevice, st));
+  TRY(cudaMemsetAsync(b.d_acc_s, 0, (uint64_t)nq * db->n_entries * 4, st));
+  TRY(cudaMemsetAsync(b.d_acc_n, 0, (uint64_t)nq * db->n_entries * 4, st));
+  if (e != cudaSuccess) return e;
+  SearchParams p = base_params(db);
+  p.query_sigs = b.d_q + (uint64_t)s0 * kSigLen;
+  p.query_start = b.d_qstart;
+  p.n_queries = nq;
+  p.acc_score = b.d_acc_s;
+  p.acc_n = b.d_acc_n;
+  p.last = b.d_last + s0;
+  p.stat_nodes = b.d_stats;
+  p.stat_deep = b.d_stats + 1;
+  launch_search(p, ns, st);
+  return cudaGetLastError();
+}
+
+static cudaError_t read_stats(const unsigned long long* d_stats, uint64_t* stats, cudaStream_t st) {
+  if (!stats) return cudaSuccess;
+  unsigned long long h[2] = {0, 0};
+  cudaError_t e = cudaMemcpyAsync(h, d_stats, 16, cudaMemcpyDeviceToHost, st);
+  TRY(cudaStreamSynchronize(st));
+  stats[0] = h[0];
+  stats[1] = h[1];
+  return e;
+}
+
+// ------------------------------------------------------------------ search: one database on one GPU ----
+
+// probe kernel -> per-(query, entry) accumulators -> exact ranking on the GPU (k_select.cu).  Only 12 bytes per query
+// come back to the host, however many entries a query touches.
+extern "C" int mnemo_search_batch(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
+                                  uint32_t n_queries, mnemo_match* out, uint64_t* stats) {
+  if (!db || !out || !query_start) return -3;
+  for (uint32_t q = 0; q < n_queries; q++) out[q] = mnemo_match{-7, 0.0f, 0};
+  if (stats) stats[0] = stats[1] = 0;
+  if (n_queries == 0 || query_start[n_queries] == 0 || db_is_empty(db)) return 0;
   mnemo_ctx* ctx = db->ctx;
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
+  ProbeBatch b;
+  cudaError_t e = probe_batch(db, query_sigs, query_start, n_queries, 0, b);
+  const uint32_t n_total = db->entry_base + db->n_entries;   // entries below entry_base have no matches here
+  const uint32_t depth = select_depth(n_total);
+  const uint32_t grid = select_grid(b.tile, ctx->sm_count);
+  uint32_t* d_leaf = nullptr;
+  SelRec* d_sel = nullptr;
+  uint8_t* d_cnt = nullptr;
+  mnemo_match_dev* d_out = nullptr;
+  TRY(scratch_get(db, kScrLeaf, 4ull * ((1ull << depth) + 1), (void**)&d_leaf));
+  TRY(scratch_get(db, kScrSel, sizeof(SelRec) * (uint64_t)grid * n_total, (void**)&d_sel));
+  TRY(scratch_get(db, kScrSelCnt, (uint64_t)grid << depth, (void**)&d_cnt));
+  TRY(scratch_get(db, kScrOut, sizeof(mnemo_match_dev) * (uint64_t)n_queries, (void**)&d_out));
+  if (e == cudaSuccess) launch_select_bounds(n_total, depth, d_leaf, st);
+  for (uint32_t q0 = 0; q0 < n_queries && e == cudaSuccess; q0 += b.tile) {
+    const uint32_t nq = std::min(b.tile, n_queries - q0);
+    TRY(probe_tile(db, b, query_start, q0, nq));
+    if (e != cudaSuccess) break;
+    launch_search_select(b.d_acc_s, b.d_acc_n, nq, db->n_entries, db->entry_base, n_total, 0, depth, d_leaf, d_sel, d_cnt,
+                         select_grid(nq, ctx->sm_count), d_out + q0, nullptr, nullptr, st);
+    TRY(cudaGetLastError());
+  }
+  static_assert(sizeof(mnemo_match_dev) == sizeof(mnemo_match), "match layouts");
+  TRY(cudaMemcpyAsync(out, d_out, sizeof(mnemo_match) * (uint64_t)n_queries, cudaMemcpyDeviceToHost, st));
+  TRY(cudaStreamSynchronize(st));
+  TRY(read_stats(b.d_stats, stats, st));
+  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_batch");
+  return 0;
+}
+
+// Diagnostic form: the dense per-entry rows search.c:55-59 accumulates (score sum, n_matches), [n_queries][n_entries]
+// in this shard's entry order.  What the parity tests and bench.py compare with the reference's scores[] array.
+extern "C" int mnemo_search_scores(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start, uint32_t n_queries,
+                                   uint32_t* score_out, uint32_t* n_matches_out) {
+  if (!db || !query_start || !score_out || !n_matches_out) return -3;
+  const uint64_t row = db->n_entries;
+  memset(score_out, 0, 4ull * n_queries * row);
+  memset(n_matches_out, 0, 4ull * n_queries * row);
+  if (n_queries == 0 || query_start[n_queries] == 0 || db_is_empty(db)) return 0;
+  mnemo_ctx* ctx = db->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  ProbeBatch b;
+  cudaError_t e = probe_batch(db, query_sigs, query_start, n_queries, 0, b);
+  for (uint32_t q0 = 0; q0 < n_queries && e == cudaSuccess; q0 += b.tile) {
+    const uint32_t nq = std::min(b.tile, n_queries - q0);
+    TRY(probe_tile(db, b, query_start, q0, nq));
+    TRY(cudaMemcpyAsync(score_out + (uint64_t)q0 * row, b.d_acc_s, 4ull * nq * row, cudaMemcpyDeviceToHost, st));
+    TRY(cudaMemcpyAsync(n_matches_out + (uint64_t)q0 * row, b.d_acc_n, 4ull * nq * row, cudaMemcpyDeviceToHost, st));
+    TRY(cudaStreamSynchronize(st));
+  }
+  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_scores");
+  return 0;
+}
+
+// ------------------------------------------------------------------ record form (arbitrary shard cuts) ----
+
+extern "C" int mnemo_search_shard(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
+                                  uint32_t n_queries, mnemo_cand* cands, uint64_t cap_cands, uint64_t* n_cands,
+                                  mnemo_lastgroup* last, uint64_t* stats) {
+  if (!db || !query_start || !n_cands) return -3;
+  *n_cands = 0;
   if (stats) stats[0] = stats[1] = 0;
   const uint32_t n_qsigs = query_start[n_queries];
   if (last)
     for (uint32_t i = 0; i < n_qsigs; i++) last[i] = mnemo_lastgroup{0, 0, 0, 0, 0};
-  if (n_queries == 0 || n_qsigs == 0 || db->size == 0 || db->n_sigs == 0 || db->n_entries == 0) return 0;
-
-  // queries are processed in groups whose dense accumulators stay under ~1 GiB
-  const uint64_t per_query = (uint64_t)db->n_entries * 8;
-  const uint32_t group = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_queries, (1ull << 30) / per_query));
-  uint8_t* d_q = nullptr;
-  uint32_t *d_qstart = nullptr, *d_acc_s = nullptr, *d_acc_n = nullptr, *d_total = nullptr, *d_qbase = nullptr,
-           *d_qcnt = nullptr;
-  mnemo_lastgroup_dev* d_last = nullptr;
-  unsigned long long* d_stats = nullptr;
+  if (n_queries == 0 || n_qsigs == 0 || db_is_empty(db)) return 0;
+  mnemo_ctx* ctx = db->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  ProbeBatch b;
+  cudaError_t e = probe_batch(db, query_sigs, query_start, n_queries, 0, b);
+  uint32_t *d_total = nullptr, *d_qbase = nullptr, *d_qcnt = nullptr;
   CandDev* d_cands = nullptr;
-  const uint32_t cand_cap = (uint32_t)std::min<uint64_t>((uint64_t)group * db->n_entries, 1u << 24);
-  cudaError_t e = cudaSuccess;
-#define TRY(x)                      \
-  do {                              \
-    if (e == cudaSuccess) e = (x);  \
-  } while (0)
-  TRY(scratch_get(db, 0, (uint64_t)n_qsigs * kSigLen + 4, (void**)&d_q));
-  TRY(scratch_get(db, 1, 4ull * ((uint64_t)n_queries + 1), (void**)&d_qstart));
-  TRY(scratch_get(db, 2, 4ull * group * db->n_entries, (void**)&d_acc_s));
-  TRY(scratch_get(db, 3, 4ull * group * db->n_entries, (void**)&d_acc_n));
-  TRY(scratch_get(db, 4, sizeof(mnemo_lastgroup_dev) * (uint64_t)n_qsigs, (void**)&d_last));
-  TRY(scratch_get(db, 5, 16, (void**)&d_stats));
-  TRY(scratch_get(db, 6, 4, (void**)&d_total));
-  TRY(scratch_get(db, 7, 4ull * group, (void**)&d_qbase));
-  TRY(scratch_get(db, 8, 4ull * group, (void**)&d_qcnt));
-  TRY(scratch_get(db, 9, sizeof(CandDev) * (uint64_t)cand_cap, (void**)&d_cands));
-  TRY(cudaMemcpyAsync(d_q, query_sigs, (uint64_t)n_qsigs * kSigLen, cudaMemcpyHostToDevice, st));
-  TRY(cudaMemsetAsync(d_stats, 0, 16, st));
+  uint64_t cand_cap = std::min<uint64_t>((uint64_t)b.tile * db->n_entries, 1u << 22);
+  TRY(scratch_get(db, kScrTotal, 4, (void**)&d_total));
+  TRY(scratch_get(db, kScrQbase, 4ull * b.tile, (void**)&d_qbase));
+  TRY(scratch_get(db, kScrQcnt, 4ull * b.tile, (void**)&d_qcnt));
+  TRY(scratch_get(db, kScrCands, sizeof(CandDev) * cand_cap, (void**)&d_cands));
   std::vector<CandDev> h_cands;
-  std::vector<uint32_t> h_qstart;
-  int rc = 0;
-  for (uint32_t q0 = 0; q0 < n_queries && e == cudaSuccess && rc == 0; q0 += group) {
-    const uint32_t nq = std::min(group, n_queries - q0);
-    // group-local query_start (offsets relative to the group's first signature)
-    h_qstart.assign(query_start + q0, query_start + q0 + nq + 1);
-    const uint32_t s0 = h_qstart[0];
-    for (auto& v : h_qstart) v -= s0;
-    const uint32_t ns = h_qstart[nq];
-    TRY(cudaMemcpyAsync(d_qstart, h_qstart.data(), 4ull * (nq + 1), cudaMemcpyHostToDevice, st));
-    TRY(cudaMemsetAsync(d_acc_s, 0, (uint64_t)nq * db->n_entries * 4, st));
-    TRY(cudaMemsetAsync(d_acc_n, 0, (uint64_t)nq * db->n_entries * 4, st));
-    TRY(cudaMemsetAsync(d_total, 0, 4, st));
-    if (e != cudaSuccess) break;
-    SearchParams p = base_params(db);
-    p.query_sigs = d_q + (uint64_t)s0 * kSigLen;
-    p.query_start = d_qstart;
-    p.n_queries = nq;
-    p.acc_score = d_acc_s;
-    p.acc_n = d_acc_n;
-    p.last = d_last + s0;
-    p.stat_nodes = d_stats;
-    p.stat_deep = d_stats + 1;
-    launch_search(p, ns, st);
-    launch_search_compact(d_acc_s, d_acc_n, nq, db->n_entries, db->entry_base, d_cands, cand_cap, d_total, d_qbase,
-                          d_qcnt, st);
+  std::vector<mnemo_cand> all;
+  for (uint32_t q0 = 0; q0 < n_queries && e == cudaSuccess; q0 += b.tile) {
+    const uint32_t nq = std::min(b.tile, n_queries - q0);
+    TRY(probe_tile(db, b, query_start, q0, nq));
     uint32_t total = 0;
-    TRY(cudaGetLastError());
-    TRY(cudaMemcpyAsync(&total, d_total, 4, cudaMemcpyDeviceToHost, st));
-    TRY(cudaStreamSynchronize(st));
-    if (e != cudaSuccess) break;
-    if (total > cand_cap) {
-      ctx->err = "mnemo_search_shard: candidate buffer overflow";
-      rc = -1;
-      break;
+    for (int attempt = 0; attempt < 2 && e == cudaSuccess; attempt++) {
+      TRY(cudaMemsetAsync(d_total, 0, 4, st));
+      if (e == cudaSuccess)
+        launch_search_compact(b.d_acc_s, b.d_acc_n, nq, db->n_entries, db->entry_base, d_cands, (uint32_t)cand_cap, d_total,
+                              d_qbase, d_qcnt, st);
+      TRY(cudaGetLastError());
+      TRY(cudaMemcpyAsync(&total, d_total, 4, cudaMemcpyDeviceToHost, st));
+      TRY(cudaStreamSynchronize(st));
+      if (e != cudaSuccess || total <= cand_cap) break;
+      cand_cap = total;   // more records than the buffer held: compact again into one that fits (the accumulators are intact)
+      TRY(scratch_get(db, kScrCands, sizeof(CandDev) * cand_cap, (void**)&d_cands));
     }
+    if (e != cudaSuccess) break;
     h_cands.resize(total);
     if (total) TRY(cudaMemcpy(h_cands.data(), d_cands, sizeof(CandDev) * total, cudaMemcpyDeviceToHost));
     // records come out grouped per query but in reservation order: sort (query, entry)
-    std::sort(h_cands.begin(), h_cands.end(), [](const CandDev& a, const CandDev& b) {
-      return a.query != b.query ? a.query < b.query : a.entry < b.entry;
+    std::sort(h_cands.begin(), h_cands.end(), [](const CandDev& x, const CandDev& y) {
+      return x.query != y.query ? x.query < y.query : x.entry < y.entry;
     });
-    for (const CandDev& c : h_cands) out.push_back(mnemo_cand{c.query + q0, c.entry, c.score, c.n_matches});
+    for (const CandDev& c : h_cands) all.push_back(mnemo_cand{c.query + q0, c.entry, c.score, c.n_matches});
   }
-  if (e == cudaSuccess && rc == 0 && last) {
+  if (e == cudaSuccess && last) {
     std::vector<mnemo_lastgroup_dev> h_last(n_qsigs);
-    TRY(cudaMemcpy(h_last.data(), d_last, sizeof(mnemo_lastgroup_dev) * n_qsigs, cudaMemcpyDeviceToHost));
+    TRY(cudaMemcpy(h_last.data(), b.d_last, sizeof(mnemo_lastgroup_dev) * n_qsigs, cudaMemcpyDeviceToHost));
     if (e == cudaSuccess)
       for (uint32_t i = 0; i < n_qsigs; i++) {
         last[i].has = h_last[i].has;
@@ -316,217 +440,18 @@ static int search_shard_impl(mnemo_db* db, const uint8_t* query_sigs, const uint
         last[i].score = h_last[i].score;
       }
   }
-  if (e == cudaSuccess && rc == 0 && stats) {
-    unsigned long long h[2] = {0, 0};
-    TRY(cudaMemcpy(h, d_stats, 16, cudaMemcpyDeviceToHost));
-    stats[0] = h[0];
-    stats[1] = h[1];
-  }
-#undef TRY
+  TRY(read_stats(b.d_stats, stats, st));
   if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_shard");
-  return rc;
-}
-
-extern "C" int mnemo_search_shard(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
-                                  uint32_t n_queries, mnemo_cand* cands, uint64_t cap_cands, uint64_t* n_cands,
-                                  mnemo_lastgroup* last, uint64_t* stats) {
-  if (!db || !query_start || !n_cands) return -3;
-  *n_cands = 0;
-  std::vector<mnemo_cand> v;
-  const int rc = search_shard_impl(db, query_sigs, query_start, n_queries, v, last, stats);
-  if (rc != 0) return rc;
-  *n_cands = v.size();
-  if (v.size() > cap_cands) {
-    db->ctx->err = "mnemo_search_shard: cands capacity too small";
+  *n_cands = all.size();
+  if (all.size() > cap_cands) {
+    ctx->err = "mnemo_search_shard: cands capacity too small (n_cands holds the number needed)";
     return -1;
   }
-  if (cands && !v.empty()) memcpy(cands, v.data(), v.size() * sizeof(mnemo_cand));
+  if (cands && !all.empty()) memcpy(cands, all.data(), all.size() * sizeof(mnemo_cand));
   return 0;
 }
 
-// ------------------------------------------------------------------ peer-memory merge ----
-// The merging rank owns a result buffer in its HBM; the other ranks (one process per GPU) map it with
-// cudaIpc and their search epilogue writes candidate and last-group records straight into it over NVLink.
-
-struct mnemo_result {
-  mnemo_ctx* ctx = nullptr;
-  bool owner = false;
-  void* base = nullptr;
-  uint32_t cap = 0, n_shards = 0, n_qsigs = 0;
-  ResultHeader* hdr = nullptr;
-  CandDev* cands = nullptr;
-  LastRec* last = nullptr;
-};
-
-static uint64_t result_bytes(uint32_t cap, uint32_t n_shards, uint32_t n_qsigs) {
-  return sizeof(ResultHeader) + (uint64_t)cap * sizeof(CandDev) + (uint64_t)n_shards * n_qsigs * sizeof(LastRec);
-}
-
-static void result_carve(mnemo_result* r) {
-  r->hdr = reinterpret_cast<ResultHeader*>(r->base);
-  r->cands = reinterpret_cast<CandDev*>(r->hdr + 1);
-  r->last = reinterpret_cast<LastRec*>(r->cands + r->cap);
-}
-
-extern "C" int mnemo_result_reset(mnemo_result* r) {
-  if (!r || !r->owner) return -3;
-  cudaSetDevice(r->ctx->device);
-  cudaStream_t st = r->ctx->stream;
-  const ResultHeader h = {0u, r->cap, r->n_shards, r->n_qsigs};
-  cudaError_t e = cudaMemsetAsync(r->base, 0, result_bytes(r->cap, r->n_shards, r->n_qsigs), st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(r->hdr, &h, sizeof h, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) return mnemo_fail(r->ctx, e, "mnemo_result_reset");
-  return 0;
-}
-
-extern "C" int mnemo_result_create(mnemo_ctx* ctx, uint32_t cap_cands, uint32_t n_shards, uint32_t n_qsigs,
-                                   mnemo_result** out, uint8_t ipc_handle[64]) {
-  if (!ctx || !out || n_shards == 0) return -3;
-  *out = nullptr;
-  cudaSetDevice(ctx->device);
-  mnemo_result* r = new (std::nothrow) mnemo_result();
-  if (!r) return -1;
-  r->ctx = ctx;
-  r->owner = true;
-  r->cap = cap_cands;
-  r->n_shards = n_shards;
-  r->n_qsigs = n_qsigs;
-  cudaError_t e = cudaMalloc(&r->base, result_bytes(cap_cands, n_shards, n_qsigs));
-  if (e != cudaSuccess) {
-    delete r;
-    return mnemo_fail(ctx, e, "mnemo_result_create");
-  }
-  result_carve(r);
-  if (ipc_handle) {
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-    cudaIpcMemHandle_t h;
-    e = cudaIpcGetMemHandle(&h, r->base);
-    if (e != cudaSuccess) {
-      cudaFree(r->base);
-      delete r;
-      return mnemo_fail(ctx, e, "mnemo_result_create (cudaIpcGetMemHandle)");
-    }
-    memcpy(ipc_handle, &h, 64);
-  }
-  int rc = mnemo_result_reset(r);
-  if (rc != 0) {
-    cudaFree(r->base);
-    delete r;
-    return rc;
-  }
-  *out = r;
-  return 0;
-}
-
-extern "C" int mnemo_result_open(mnemo_ctx* ctx, const uint8_t ipc_handle[64], uint32_t cap_cands, uint32_t n_shards,
-                                 uint32_t n_qsigs, mnemo_result** out) {
-  if (!ctx || !out || !ipc_handle) return -3;
-  *out = nullptr;
-  cudaSetDevice(ctx->device);
-  mnemo_result* r = new (std::nothrow) mnemo_result();
-  if (!r) return -1;
-  r->ctx = ctx;
-  r->owner = false;
-  r->cap = cap_cands;
-  r->n_shards = n_shards;
-  r->n_qsigs = n_qsigs;
-  cudaIpcMemHandle_t h;
-  memcpy(&h, ipc_handle, 64);
-  cudaError_t e = cudaIpcOpenMemHandle(&r->base, h, cudaIpcMemLazyEnablePeerAccess);
-  if (e != cudaSuccess) {
-    delete r;
-    return mnemo_fail(ctx, e, "mnemo_result_open (cudaIpcOpenMemHandle)");
-  }
-  result_carve(r);
-  *out = r;
-  return 0;
-}
-
-extern "C" void mnemo_result_destroy(mnemo_result* r) {
-  if (!r) return;
-  cudaSetDevice(r->ctx->device);
-  cudaStreamSynchronize(r->ctx->stream);
-  if (r->owner) cudaFree(r->base);
-  else cudaIpcCloseMemHandle(r->base);
-  delete r;
-}
-
-extern "C" int mnemo_search_shard_push(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
-                                       uint32_t n_queries, mnemo_result* dst, uint32_t shard_rank, uint64_t* stats) {
-  if (!db || !query_start || !dst || shard_rank >= dst->n_shards) return -3;
-  mnemo_ctx* ctx = db->ctx;
-  cudaSetDevice(ctx->device);
-  cudaStream_t st = ctx->stream;
-  if (stats) stats[0] = stats[1] = 0;
-  const uint32_t n_qsigs = query_start[n_queries];
-  if (n_qsigs != dst->n_qsigs) {
-    ctx->err = "mnemo_search_shard_push: result buffer was sized for a different query batch";
-    return -3;
-  }
-  if (n_queries == 0 || n_qsigs == 0 || db->size == 0 || db->n_sigs == 0 || db->n_entries == 0) return 0;
-  const uint64_t per_query = (uint64_t)db->n_entries * 8;
-  const uint32_t group = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_queries, (1ull << 30) / per_query));
-  uint8_t* d_q = nullptr;
-  uint32_t *d_qstart = nullptr, *d_acc_s = nullptr, *d_acc_n = nullptr;
-  mnemo_lastgroup_dev* d_last = nullptr;
-  unsigned long long* d_stats = nullptr;
-  cudaError_t e = cudaSuccess;
-#define TRY(x)                      \
-  do {                              \
-    if (e == cudaSuccess) e = (x);  \
-  } while (0)
-  TRY(scratch_get(db, 0, (uint64_t)n_qsigs * kSigLen + 4, (void**)&d_q));
-  TRY(scratch_get(db, 1, 4ull * ((uint64_t)n_queries + 1), (void**)&d_qstart));
-  TRY(scratch_get(db, 2, 4ull * group * db->n_entries, (void**)&d_acc_s));
-  TRY(scratch_get(db, 3, 4ull * group * db->n_entries, (void**)&d_acc_n));
-  TRY(scratch_get(db, 4, sizeof(mnemo_lastgroup_dev) * (uint64_t)n_qsigs, (void**)&d_last));
-  TRY(scratch_get(db, 5, 16, (void**)&d_stats));
-  TRY(cudaMemcpyAsync(d_q, query_sigs, (uint64_t)n_qsigs * kSigLen, cudaMemcpyHostToDevice, st));
-  TRY(cudaMemsetAsync(d_stats, 0, 16, st));
-  std::vector<uint32_t> h_qstart;
-  for (uint32_t q0 = 0; q0 < n_queries && e == cudaSuccess; q0 += group) {
-    const uint32_t nq = std::min(group, n_queries - q0);
-    h_qstart.assign(query_start + q0, query_start + q0 + nq + 1);
-    const uint32_t s0 = h_qstart[0];
-    for (auto& v : h_qstart) v -= s0;
-    const uint32_t ns = h_qstart[nq];
-    TRY(cudaMemcpyAsync(d_qstart, h_qstart.data(), 4ull * (nq + 1), cudaMemcpyHostToDevice, st));
-    TRY(cudaMemsetAsync(d_acc_s, 0, (uint64_t)nq * db->n_entries * 4, st));
-    TRY(cudaMemsetAsync(d_acc_n, 0, (uint64_t)nq * db->n_entries * 4, st));
-    if (e != cudaSuccess) break;
-    SearchParams p = base_params(db);
-    p.query_sigs = d_q + (uint64_t)s0 * kSigLen;
-    p.query_start = d_qstart;
-    p.n_queries = nq;
-    p.acc_score = d_acc_s;
-    p.acc_n = d_acc_n;
-    p.last = d_last + s0;
-    p.stat_nodes = d_stats;
-    p.stat_deep = d_stats + 1;
-    launch_search(p, ns, st);
-    launch_search_push(d_acc_s, d_acc_n, nq, db->n_entries, db->entry_base, q0, dst->hdr, dst->cands, st);
-    TRY(cudaGetLastError());
-    if (q0 + group < n_queries) TRY(cudaStreamSynchronize(st));   // h_qstart is reused by the next group
-  }
-  if (e == cudaSuccess) {
-    launch_search_last_push(d_last, n_qsigs, db->d_sig_entry, db->d_entry_start, db->entry_base,
-                            dst->last + (uint64_t)shard_rank * n_qsigs, st);
-    TRY(cudaGetLastError());
-  }
-  TRY(cudaStreamSynchronize(st));   // the records are in the merging rank's memory when this returns
-  if (e == cudaSuccess && stats) {
-    unsigned long long h[2] = {0, 0};
-    TRY(cudaMemcpy(h, d_stats, 16, cudaMemcpyDeviceToHost));
-    stats[0] = h[0];
-    stats[1] = h[1];
-  }
-#undef TRY
-  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_shard_push");
-  return 0;
-}
-
-// ---- final ranking: search.c:65-107 comparator + the merge order of glibc's qsort ----
+// ---- final ranking on the host: search.c:65-107 comparator + the merge order of glibc's qsort ----
 
 namespace {
 struct Rec {
@@ -535,22 +460,11 @@ struct Rec {
   int32_t n;
 };
 
-// search.c:65-107, restated.  Not a strict weak order (integer abs() of a float difference).
+// search.c:65-107, restated (cmp_entry_avg, search_internal.h).  Not a strict weak order.
 int cmp_entry_scores(const Rec& a, const Rec& b) {
   const float avg_a = a.n == 0 ? 0 : a.score / (float)a.n;
   const float avg_b = b.n == 0 ? 0 : b.score / (float)b.n;
-  const float delta = (float)abs((int)(avg_a - avg_b));
-  if (delta <= 3) {
-    if (delta <= 5 && a.n >= b.n + 5) return -1;
-    if (b.n >= a.n + 5) return 1;
-  }
-  if ((double)delta < 0.5) {
-    if (a.n > b.n) return -1;
-    if (a.n < b.n) return 1;
-  }
-  if (avg_a > avg_b) return -1;
-  if (avg_b > avg_a) return 1;
-  return 0;
+  return cmp_entry_avg(avg_a, a.n, avg_b, b.n);
 }
 
 // The reference sorts ALL n_entries records with libc qsort (search.c:170).  glibc's qsort is a
@@ -646,104 +560,20 @@ extern "C" int mnemo_search_finish(const mnemo_cand* cands, uint64_t n_cands, co
   return 0;
 }
 
-// Dense path used by mnemo_search_batch: probe kernel -> per-(query, entry) accumulators -> exact ranking on the GPU
-// (k_select.cu).  Only 12 bytes per query come back to the host, however many entries a query touches.
-static int search_batch_select(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start, uint32_t n_queries,
-                               mnemo_match* out, uint64_t* stats) {
-  mnemo_ctx* ctx = db->ctx;
-  cudaSetDevice(ctx->device);
-  cudaStream_t st = ctx->stream;
-  if (stats) stats[0] = stats[1] = 0;
-  const uint32_t n_qsigs = query_start[n_queries];
-  if (n_qsigs == 0 || db->size == 0 || db->n_sigs == 0 || db->n_entries == 0) return 0;
-  const uint64_t per_query = (uint64_t)db->n_entries * 8;
-  const uint32_t group = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(n_queries, (1ull << 30) / per_query));
-  const uint32_t n_total = db->entry_base + db->n_entries;   // entries below entry_base have no matches here
-  const uint32_t depth = select_depth(n_total);
-  const uint32_t grid = select_grid(group, ctx->sm_count);
-  uint8_t* d_q = nullptr;
-  uint32_t *d_qstart = nullptr, *d_acc_s = nullptr, *d_acc_n = nullptr, *d_leaf = nullptr;
-  mnemo_lastgroup_dev* d_last = nullptr;
-  unsigned long long* d_stats = nullptr;
-  SelRec* d_sel = nullptr;
-  uint8_t* d_cnt = nullptr;
-  mnemo_match_dev* d_out = nullptr;
-  cudaError_t e = cudaSuccess;
-#define TRY(x)                      \
-  do {                              \
-    if (e == cudaSuccess) e = (x);  \
-  } while (0)
-  TRY(scratch_get(db, 0, (uint64_t)n_qsigs * kSigLen + 4, (void**)&d_q));
-  TRY(scratch_get(db, 1, 4ull * ((uint64_t)n_queries + 1), (void**)&d_qstart));
-  TRY(scratch_get(db, 2, 4ull * group * db->n_entries, (void**)&d_acc_s));
-  TRY(scratch_get(db, 3, 4ull * group * db->n_entries, (void**)&d_acc_n));
-  TRY(scratch_get(db, 4, sizeof(mnemo_lastgroup_dev) * (uint64_t)n_qsigs, (void**)&d_last));
-  TRY(scratch_get(db, 5, 16, (void**)&d_stats));
-  TRY(scratch_get(db, 10, 4ull * ((1ull << depth) + 1), (void**)&d_leaf));
-  TRY(scratch_get(db, 11, sizeof(SelRec) * (uint64_t)grid * n_total, (void**)&d_sel));
-  TRY(scratch_get(db, 12, (uint64_t)grid << depth, (void**)&d_cnt));
-  TRY(scratch_get(db, 13, sizeof(mnemo_match_dev) * (uint64_t)n_queries, (void**)&d_out));
-  TRY(cudaMemcpyAsync(d_q, query_sigs, (uint64_t)n_qsigs * kSigLen, cudaMemcpyHostToDevice, st));
-  TRY(cudaMemsetAsync(d_stats, 0, 16, st));
-  if (e == cudaSuccess) launch_select_bounds(n_total, depth, d_leaf, st);
-  std::vector<uint32_t> h_qstart;
-  for (uint32_t q0 = 0; q0 < n_queries && e == cudaSuccess; q0 += group) {
-    const uint32_t nq = std::min(group, n_queries - q0);
-    h_qstart.assign(query_start + q0, query_start + q0 + nq + 1);
-    const uint32_t s0 = h_qstart[0];
-    for (auto& v : h_qstart) v -= s0;
-    const uint32_t ns = h_qstart[nq];
-    TRY(cudaMemcpyAsync(d_qstart, h_qstart.data(), 4ull * (nq + 1), cudaMemcpyHostToDevice, st));
-    TRY(cudaMemsetAsync(d_acc_s, 0, (uint64_t)nq * db->n_entries * 4, st));
-    TRY(cudaMemsetAsync(d_acc_n, 0, (uint64_t)nq * db->n_entries * 4, st));
-    if (e != cudaSuccess) break;
-    SearchParams p = base_params(db);
-    p.query_sigs = d_q + (uint64_t)s0 * kSigLen;
-    p.query_start = d_qstart;
-    p.n_queries = nq;
-    p.acc_score = d_acc_s;
-    p.acc_n = d_acc_n;
-    p.last = d_last + s0;
-    p.stat_nodes = d_stats;
-    p.stat_deep = d_stats + 1;
-    launch_search(p, ns, st);
-    launch_search_select(d_acc_s, d_acc_n, nq, db->n_entries, db->entry_base, n_total, 0, depth, d_leaf, d_sel, d_cnt,
-                         select_grid(nq, ctx->sm_count), d_out + q0, nullptr, nullptr, st);
-    TRY(cudaGetLastError());
-    if (q0 + group < n_queries) TRY(cudaStreamSynchronize(st));   // h_qstart is reused by the next group
-  }
-  static_assert(sizeof(mnemo_match_dev) == sizeof(mnemo_match), "match layouts");
-  TRY(cudaMemcpyAsync(out, d_out, sizeof(mnemo_match) * (uint64_t)n_queries, cudaMemcpyDeviceToHost, st));
-  TRY(cudaStreamSynchronize(st));
-  if (e == cudaSuccess && stats) {
-    unsigned long long h[2] = {0, 0};
-    TRY(cudaMemcpy(h, d_stats, 16, cudaMemcpyDeviceToHost));
-    stats[0] = h[0];
-    stats[1] = h[1];
-  }
-#undef TRY
-  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_batch");
-  return 0;
-}
-
-extern "C" int mnemo_search_batch(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
-                                  uint32_t n_queries, mnemo_match* out, uint64_t* stats) {
-  if (!db || !out || !query_start) return -3;
-  for (uint32_t q = 0; q < n_queries; q++) out[q] = mnemo_match{-7, 0.0f, 0};
-  if (n_queries == 0) return 0;
-  return search_batch_select(db, query_sigs, query_start, n_queries, out, stats);
-}
-
 // ------------------------------------------------------------------ sharded search, ranked on the GPUs ----
 // The database is sharded on node boundaries of the ranking tree (mnemo_tree_cuts), so every shard can rank its own
 // subtrees exactly (k_select.cu) and hand over kSelTop records per query and node instead of one record per matched
-// entry.  Protocol per query batch (mnemophonix_b200/dist.py drives it):
-//   1. every rank: mnemo_search_dense_begin  -> probe kernel into dense accumulators kept on the device;
-//                                               has[s] = this shard holds a candidate for query signature s
+// entry.  Protocol per query tile (mnemophonix_b200/dist.py drives it; everything stays on the device and on the
+// context's stream, the collectives are the caller's):
+//   1. every rank: mnemo_search_dense_begin_dev  -> probe kernel into dense accumulators kept on the device;
+//                                                   has[s] = this shard holds a candidate for query signature s
 //   2. all-gather of the has flags (n_query_signatures bytes per rank: the path's small exchange step)
-//   3. every rank: mnemo_search_dense_lists  -> last-group fix-up where a higher shard holds candidates, ranking of each
-//                                               owned node, lists + counts to the host
-//   4. all-gather of the lists, mnemo_select_merge on the merging rank (top levels of the tree + thresholds).
+//   3. every rank: mnemo_search_dense_lists_dev  -> last-group fix-up where a higher shard holds candidates, ranking of
+//                                                   each owned node: [per][nq][10] records + [per][nq] counts
+//   4. all-gather of those, mnemo_select_merge_dev on every rank (top levels of the tree + thresholds), 12 bytes
+//      per query to the host.
+// The host-pointer forms (mnemo_search_dense_begin / _lists, mnemo_select_merge) wrap the same kernels for tests and
+// for callers without a device-side collective.
 
 extern "C" uint32_t mnemo_tree_cuts(uint32_t n_entries_total, uint32_t n_shards, uint32_t* cuts, uint32_t* node_lo,
                                     uint32_t node_cap) {
@@ -773,69 +603,166 @@ extern "C" uint32_t mnemo_tree_cuts(uint32_t n_entries_total, uint32_t n_shards,
   return n_nodes;
 }
 
-extern "C" int mnemo_search_dense_begin(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
-                                        uint32_t n_queries, uint8_t* has_out, uint64_t* stats) {
-  if (!db || !query_start || !has_out) return -3;
+extern "C" int mnemo_search_dense_begin_dev(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
+                                            uint32_t n_queries, uint8_t* d_has_out) {
+  if (!db || !query_start || !d_has_out) return -3;
   mnemo_ctx* ctx = db->ctx;
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
-  if (stats) stats[0] = stats[1] = 0;
   const uint32_t n_qsigs = query_start[n_queries];
   db->dense_nq = n_queries;
   db->dense_nqs = n_qsigs;
-  memset(has_out, 0, n_qsigs);
-  if (n_queries == 0 || n_qsigs == 0 || db->size == 0 || db->n_sigs == 0 || db->n_entries == 0) return 0;
-  const uint64_t cells = (uint64_t)n_queries * db->n_entries;
-  if (cells * 8 > (8ull << 30)) {
-    ctx->err = "mnemo_search_dense_begin: query batch x shard entries exceeds 8 GiB of accumulators; send smaller batches";
+  if (n_queries == 0 || n_qsigs == 0) return 0;
+  cudaError_t e = cudaMemsetAsync(d_has_out, 0, n_qsigs, st);
+  if (db_is_empty(db)) {
+    if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_dense_begin");
+    return 0;
+  }
+  if (n_queries > mnemo_db_tile_queries(db)) {
+    ctx->err = "mnemo_search_dense_begin: query batch x shard entries exceeds the accumulator budget; send tiles of "
+               "mnemo_db_tile_queries() queries";
     return -1;
   }
-  uint8_t *d_q = nullptr, *d_has = nullptr;
-  uint32_t *d_qstart = nullptr, *d_acc_s = nullptr, *d_acc_n = nullptr;
-  mnemo_lastgroup_dev* d_last = nullptr;
-  unsigned long long* d_stats = nullptr;
-  cudaError_t e = cudaSuccess;
-#define TRY(x)                      \
-  do {                              \
-    if (e == cudaSuccess) e = (x);  \
-  } while (0)
-  TRY(scratch_get(db, 0, (uint64_t)n_qsigs * kSigLen + 4, (void**)&d_q));
-  TRY(scratch_get(db, 1, 4ull * ((uint64_t)n_queries + 1), (void**)&d_qstart));
-  TRY(scratch_get(db, 2, 4ull * cells, (void**)&d_acc_s));
-  TRY(scratch_get(db, 3, 4ull * cells, (void**)&d_acc_n));
-  TRY(scratch_get(db, 4, sizeof(mnemo_lastgroup_dev) * (uint64_t)n_qsigs, (void**)&d_last));
-  TRY(scratch_get(db, 5, 16, (void**)&d_stats));
-  TRY(scratch_get(db, 14, n_qsigs, (void**)&d_has));
-  TRY(cudaMemcpyAsync(d_q, query_sigs, (uint64_t)n_qsigs * kSigLen, cudaMemcpyHostToDevice, st));
-  TRY(cudaMemcpyAsync(d_qstart, query_start, 4ull * (n_queries + 1), cudaMemcpyHostToDevice, st));
-  TRY(cudaMemsetAsync(d_stats, 0, 16, st));
-  TRY(cudaMemsetAsync(d_acc_s, 0, cells * 4, st));
-  TRY(cudaMemsetAsync(d_acc_n, 0, cells * 4, st));
-  if (e == cudaSuccess) {
-    SearchParams p = base_params(db);
-    p.query_sigs = d_q;
-    p.query_start = d_qstart;
-    p.n_queries = n_queries;
-    p.acc_score = d_acc_s;
-    p.acc_n = d_acc_n;
-    p.last = d_last;
-    p.stat_nodes = d_stats;
-    p.stat_deep = d_stats + 1;
-    launch_search(p, n_qsigs, st);
-    launch_search_has(d_last, n_qsigs, d_has, st);
-    TRY(cudaGetLastError());
-  }
-  TRY(cudaMemcpyAsync(has_out, d_has, n_qsigs, cudaMemcpyDeviceToHost, st));
-  TRY(cudaStreamSynchronize(st));
-  if (e == cudaSuccess && stats) {
-    unsigned long long h[2] = {0, 0};
-    TRY(cudaMemcpy(h, d_stats, 16, cudaMemcpyDeviceToHost));
-    stats[0] = h[0];
-    stats[1] = h[1];
-  }
-#undef TRY
+  ProbeBatch b;
+  TRY(probe_batch(db, query_sigs, query_start, n_queries, n_queries, b));
+  TRY(probe_tile(db, b, query_start, 0, n_queries));
+  if (e == cudaSuccess) launch_search_has(b.d_last, n_qsigs, d_has_out, st);
+  TRY(cudaGetLastError());
   if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_dense_begin");
   return 0;
+}
+
+extern "C" int mnemo_search_dense_lists_dev(mnemo_db* db, const uint8_t* d_has_all, uint32_t n_shards, uint32_t shard,
+                                            const uint32_t* node_bounds, uint32_t n_nodes, mnemo_sel_rec* d_lists_out,
+                                            uint32_t* d_counts_out) {
+  if (!db || !node_bounds || !d_lists_out || !d_counts_out || n_shards == 0 || shard >= n_shards || (n_shards > 1 && !d_has_all))
+    return -3;
+  mnemo_ctx* ctx = db->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const uint32_t n_queries = db->dense_nq, n_qsigs = db->dense_nqs;
+  if (n_queries == 0 || n_nodes == 0) return 0;
+  if (node_bounds[0] != db->entry_base || node_bounds[n_nodes] != db->entry_base + db->n_entries) {
+    ctx->err = "mnemo_search_dense_lists: the nodes do not tile this shard's entry range";
+    return -3;
+  }
+  cudaError_t e = cudaMemsetAsync(d_counts_out, 0, 4ull * n_nodes * n_queries, st);
+  if (n_qsigs == 0 || db_is_empty(db)) {
+    if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_dense_lists");
+    return 0;
+  }
+  uint8_t* d_cnt = nullptr;
+  uint32_t* d_leaf = nullptr;
+  SelRec* d_sel = nullptr;
+  uint32_t max_n = 0;
+  for (uint32_t i = 0; i < n_nodes; i++) max_n = std::max(max_n, node_bounds[i + 1] - node_bounds[i]);
+  const uint32_t max_depth = select_depth(max_n ? max_n : 1);
+  const uint32_t grid = select_grid(n_queries, ctx->sm_count);
+  // one leaf table per node: the nodes are ranked back to back on the stream without a host round trip
+  const uint64_t leaf_stride = (1ull << max_depth) + 1;
+  TRY(scratch_get(db, kScrLeaf, 4ull * leaf_stride * n_nodes, (void**)&d_leaf));
+  TRY(scratch_get(db, kScrSel, sizeof(SelRec) * (uint64_t)grid * (max_n ? max_n : 1), (void**)&d_sel));
+  TRY(scratch_get(db, kScrSelCnt, (uint64_t)grid << max_depth, (void**)&d_cnt));
+  uint32_t* d_qstart = (uint32_t*)db->scratch[kScrQstart].p;
+  uint32_t* d_acc_s = (uint32_t*)db->scratch[kScrAccS].p;
+  uint32_t* d_acc_n = (uint32_t*)db->scratch[kScrAccN].p;
+  mnemo_lastgroup_dev* d_last = (mnemo_lastgroup_dev*)db->scratch[kScrLast].p;
+  if (e == cudaSuccess && shard + 1 < n_shards)
+    launch_search_fixup(d_last, d_has_all, n_shards, shard, n_qsigs, d_qstart, n_queries, db->d_sig_entry, db->n_entries,
+                        d_acc_s, d_acc_n, st);
+  static_assert(sizeof(SelRec) == sizeof(mnemo_sel_rec), "record layouts");
+  for (uint32_t i = 0; i < n_nodes && e == cudaSuccess; i++) {
+    const uint32_t lo = node_bounds[i], n = node_bounds[i + 1] - lo;
+    if (n == 0) continue;
+    const uint32_t depth = select_depth(n);
+    uint32_t* leaf = d_leaf + leaf_stride * i;
+    launch_select_bounds(n, depth, leaf, st);
+    // tree over the node's own entries: position p <-> accumulator column (lo - entry_base) + p, global entry lo + p
+    launch_search_select(d_acc_s + (lo - db->entry_base), d_acc_n + (lo - db->entry_base), n_queries, db->n_entries, 0, n, lo,
+                         depth, leaf, d_sel, d_cnt, grid, nullptr,
+                         reinterpret_cast<SelRec*>(d_lists_out) + (uint64_t)i * n_queries * kSelTop,
+                         d_counts_out + (uint64_t)i * n_queries, st);
+    TRY(cudaGetLastError());
+  }
+  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_dense_lists");
+  return 0;
+}
+
+extern "C" uint64_t mnemo_shard_record_bytes(uint32_t nodes_per_shard, uint32_t n_queries) {
+  return (uint64_t)nodes_per_shard * n_queries * (sizeof(SelRec) * kSelTop + 4);
+}
+
+extern "C" int mnemo_select_merge_dev(mnemo_ctx* ctx, const void* d_gathered, uint32_t n_shards, uint32_t n_nodes,
+                                      uint32_t nodes_per_shard, uint32_t n_queries, mnemo_match* out) {
+  if (!ctx || !out || (n_queries && n_nodes && !d_gathered)) return -3;
+  if ((n_nodes & (n_nodes - 1)) || n_nodes > (uint32_t)kMergeMaxNodes || n_shards == 0 || n_shards > n_nodes) return -3;
+  for (uint32_t q = 0; q < n_queries; q++) out[q] = mnemo_match{-7, 0.0f, 0};
+  if (n_queries == 0 || n_nodes == 0) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  mnemo_match_dev* d_out = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d_out, sizeof(mnemo_match_dev) * (uint64_t)n_queries);
+  if (e == cudaSuccess) launch_select_merge(d_gathered, n_shards, n_nodes, nodes_per_shard, n_queries, d_out, st);
+  TRY(cudaGetLastError());
+  TRY(cudaMemcpyAsync(out, d_out, sizeof(mnemo_match) * (uint64_t)n_queries, cudaMemcpyDeviceToHost, st));
+  TRY(cudaStreamSynchronize(st));
+  if (d_out) cudaFree(d_out);
+  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_select_merge_dev");
+  return 0;
+}
+
+extern "C" int mnemo_search_dense_stats(mnemo_db* db, uint64_t* stats) {
+  if (!db || !stats) return -3;
+  stats[0] = stats[1] = 0;
+  if (!db->scratch[kScrStats].p) return 0;
+  cudaSetDevice(db->ctx->device);
+  cudaError_t e = read_stats((const unsigned long long*)db->scratch[kScrStats].p, stats, db->ctx->stream);
+  if (e != cudaSuccess) return mnemo_fail(db->ctx, e, "mnemo_search_dense_stats");
+  return 0;
+}
+
+// Accumulator row of one query of the batch held since mnemo_search_dense_begin (after the fix-up when _lists ran).
+extern "C" int mnemo_search_dense_read(mnemo_db* db, uint32_t query, uint32_t* score_out, uint32_t* n_matches_out) {
+  if (!db || !score_out || !n_matches_out || query >= db->dense_nq) return -3;
+  if (db->n_entries == 0) return 0;
+  memset(score_out, 0, 4ull * db->n_entries);
+  memset(n_matches_out, 0, 4ull * db->n_entries);
+  if (db->dense_nqs == 0 || db_is_empty(db)) return 0;
+  cudaSetDevice(db->ctx->device);
+  cudaStream_t st = db->ctx->stream;
+  const uint32_t* d_acc_s = (const uint32_t*)db->scratch[kScrAccS].p;
+  const uint32_t* d_acc_n = (const uint32_t*)db->scratch[kScrAccN].p;
+  cudaError_t e = cudaMemcpyAsync(score_out, d_acc_s + (uint64_t)query * db->n_entries, 4ull * db->n_entries,
+                                  cudaMemcpyDeviceToHost, st);
+  TRY(cudaMemcpyAsync(n_matches_out, d_acc_n + (uint64_t)query * db->n_entries, 4ull * db->n_entries, cudaMemcpyDeviceToHost, st));
+  TRY(cudaStreamSynchronize(st));
+  if (e != cudaSuccess) return mnemo_fail(db->ctx, e, "mnemo_search_dense_read");
+  return 0;
+}
+
+// ---- host-pointer forms of the same protocol ----
+
+extern "C" int mnemo_search_dense_begin(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
+                                        uint32_t n_queries, uint8_t* has_out, uint64_t* stats) {
+  if (!db || !query_start || !has_out) return -3;
+  if (stats) stats[0] = stats[1] = 0;
+  const uint32_t n_qsigs = query_start[n_queries];
+  memset(has_out, 0, n_qsigs);
+  db->dense_nq = n_queries;
+  db->dense_nqs = n_qsigs;
+  if (n_queries == 0 || n_qsigs == 0) return 0;
+  mnemo_ctx* ctx = db->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  uint8_t* d_has = nullptr;
+  cudaError_t e = scratch_get(db, kScrHas, n_qsigs, (void**)&d_has);
+  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_dense_begin");
+  const int rc = mnemo_search_dense_begin_dev(db, query_sigs, query_start, n_queries, d_has);
+  if (rc != 0) return rc;
+  TRY(cudaMemcpyAsync(has_out, d_has, n_qsigs, cudaMemcpyDeviceToHost, st));
+  TRY(cudaStreamSynchronize(st));
+  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_dense_begin");
+  return stats && !db_is_empty(db) ? mnemo_search_dense_stats(db, stats) : 0;
 }
 
 extern "C" int mnemo_search_dense_lists(mnemo_db* db, const uint8_t* has_higher, const uint32_t* node_bounds,
@@ -847,54 +774,24 @@ extern "C" int mnemo_search_dense_lists(mnemo_db* db, const uint8_t* has_higher,
   const uint32_t n_queries = db->dense_nq, n_qsigs = db->dense_nqs;
   for (uint64_t i = 0; i < (uint64_t)n_nodes * n_queries; i++) counts_out[i] = 0;
   if (n_queries == 0 || n_nodes == 0) return 0;
-  if (node_bounds[0] != db->entry_base || node_bounds[n_nodes] != db->entry_base + db->n_entries) {
-    ctx->err = "mnemo_search_dense_lists: the nodes do not tile this shard's entry range";
-    return -3;
+  uint8_t* d_hh = nullptr;
+  SelRec* d_lists = nullptr;
+  const uint64_t list_bytes = sizeof(SelRec) * kSelTop * (uint64_t)n_nodes * n_queries, cnt_bytes = 4ull * n_nodes * n_queries;
+  cudaError_t e = scratch_get(db, kScrLists, list_bytes + cnt_bytes, (void**)&d_lists);
+  uint32_t* d_counts = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(d_lists) + list_bytes);
+  // has_higher as the flags of one virtual higher shard: [this shard's row (unused)][the higher shards' OR]
+  if (has_higher && n_qsigs) {
+    TRY(scratch_get(db, kScrHasAll, 2ull * n_qsigs, (void**)&d_hh));
+    TRY(cudaMemsetAsync(d_hh, 0, n_qsigs, st));
+    TRY(cudaMemcpyAsync(d_hh + n_qsigs, has_higher, n_qsigs, cudaMemcpyHostToDevice, st));
   }
-  if (n_qsigs == 0 || db->size == 0 || db->n_sigs == 0 || db->n_entries == 0) return 0;
-  uint8_t *d_hh = nullptr, *d_cnt = nullptr;
-  uint32_t *d_leaf = nullptr, *d_counts = nullptr;
-  SelRec *d_sel = nullptr, *d_lists = nullptr;
-  uint32_t max_n = 0;
-  for (uint32_t i = 0; i < n_nodes; i++) max_n = std::max(max_n, node_bounds[i + 1] - node_bounds[i]);
-  const uint32_t max_depth = select_depth(max_n ? max_n : 1);
-  const uint32_t grid = select_grid(n_queries, ctx->sm_count);
-  cudaError_t e = cudaSuccess;
-#define TRY(x)                      \
-  do {                              \
-    if (e == cudaSuccess) e = (x);  \
-  } while (0)
-  TRY(scratch_get(db, 15, n_qsigs, (void**)&d_hh));
-  TRY(scratch_get(db, 10, 4ull * ((1ull << max_depth) + 1), (void**)&d_leaf));
-  TRY(scratch_get(db, 11, sizeof(SelRec) * (uint64_t)grid * (max_n ? max_n : 1), (void**)&d_sel));
-  TRY(scratch_get(db, 12, (uint64_t)grid << max_depth, (void**)&d_cnt));
-  TRY(scratch_get(db, 13, (sizeof(SelRec) * kSelTop + 4) * (uint64_t)n_queries, (void**)&d_lists));
-  d_counts = reinterpret_cast<uint32_t*>(d_lists + (uint64_t)n_queries * kSelTop);
-  uint32_t* d_qstart = (uint32_t*)db->scratch[1].p;
-  uint32_t* d_acc_s = (uint32_t*)db->scratch[2].p;
-  uint32_t* d_acc_n = (uint32_t*)db->scratch[3].p;
-  mnemo_lastgroup_dev* d_last = (mnemo_lastgroup_dev*)db->scratch[4].p;
-  if (has_higher) {
-    TRY(cudaMemcpyAsync(d_hh, has_higher, n_qsigs, cudaMemcpyHostToDevice, st));
-    if (e == cudaSuccess)
-      launch_search_fixup(d_last, d_hh, n_qsigs, d_qstart, n_queries, db->d_sig_entry, db->n_entries, d_acc_s, d_acc_n, st);
-  }
-  static_assert(sizeof(SelRec) == sizeof(mnemo_sel_rec), "record layouts");
-  for (uint32_t i = 0; i < n_nodes && e == cudaSuccess; i++) {
-    const uint32_t lo = node_bounds[i], n = node_bounds[i + 1] - lo;
-    if (n == 0) continue;
-    const uint32_t depth = select_depth(n);
-    launch_select_bounds(n, depth, d_leaf, st);
-    // tree over the node's own entries: position p <-> accumulator column (lo - entry_base) + p, global entry lo + p
-    launch_search_select(d_acc_s + (lo - db->entry_base), d_acc_n + (lo - db->entry_base), n_queries, db->n_entries, 0, n, lo,
-                         depth, d_leaf, d_sel, d_cnt, grid, nullptr, d_lists, d_counts, st);
-    TRY(cudaGetLastError());
-    TRY(cudaMemcpyAsync(lists_out + (uint64_t)i * n_queries * kSelTop, d_lists, sizeof(SelRec) * (uint64_t)n_queries * kSelTop,
-                        cudaMemcpyDeviceToHost, st));
-    TRY(cudaMemcpyAsync(counts_out + (uint64_t)i * n_queries, d_counts, 4ull * n_queries, cudaMemcpyDeviceToHost, st));
-    TRY(cudaStreamSynchronize(st));   // d_lists / d_leaf are reused by the next node
-  }
-#undef TRY
+  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_dense_lists");
+  const int rc = mnemo_search_dense_lists_dev(db, d_hh, d_hh ? 2 : 1, 0, node_bounds, n_nodes,
+                                              reinterpret_cast<mnemo_sel_rec*>(d_lists), d_counts);
+  if (rc != 0) return rc;
+  TRY(cudaMemcpyAsync(lists_out, d_lists, list_bytes, cudaMemcpyDeviceToHost, st));
+  TRY(cudaMemcpyAsync(counts_out, d_counts, cnt_bytes, cudaMemcpyDeviceToHost, st));
+  TRY(cudaStreamSynchronize(st));
   if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_dense_lists");
   return 0;
 }
@@ -964,48 +861,24 @@ extern "C" int mnemo_selftest_select(mnemo_ctx* ctx, const uint32_t* score, cons
   uint8_t* d_cnt = nullptr;
   mnemo_match_dev* d_out = nullptr;
   cudaError_t e = dalloc(&d_s, cells);
-  if (e == cudaSuccess) e = dalloc(&d_n, cells);
-  if (e == cudaSuccess) e = dalloc(&d_leaf, (1ull << depth) + 1);
-  if (e == cudaSuccess) e = dalloc(&d_sel, (uint64_t)grid * n_total);
-  if (e == cudaSuccess) e = dalloc(&d_cnt, (uint64_t)grid << depth);
-  if (e == cudaSuccess) e = dalloc(&d_out, (uint64_t)n_queries);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_s, score, cells * 4, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, n_matches, cells * 4, cudaMemcpyHostToDevice, st);
+  TRY(dalloc(&d_n, cells));
+  TRY(dalloc(&d_leaf, (1ull << depth) + 1));
+  TRY(dalloc(&d_sel, (uint64_t)grid * n_total));
+  TRY(dalloc(&d_cnt, (uint64_t)grid << depth));
+  TRY(dalloc(&d_out, (uint64_t)n_queries));
+  TRY(cudaMemcpyAsync(d_s, score, cells * 4, cudaMemcpyHostToDevice, st));
+  TRY(cudaMemcpyAsync(d_n, n_matches, cells * 4, cudaMemcpyHostToDevice, st));
   if (e == cudaSuccess) {
     launch_select_bounds(n_total, depth, d_leaf, st);
     launch_search_select(d_s, d_n, n_queries, n_entries, entry_base, n_total, 0, depth, d_leaf, d_sel, d_cnt, grid, d_out,
                          nullptr, nullptr, st);
     e = cudaGetLastError();
   }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(mnemo_match) * (uint64_t)n_queries, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  TRY(cudaMemcpyAsync(out, d_out, sizeof(mnemo_match) * (uint64_t)n_queries, cudaMemcpyDeviceToHost, st));
+  TRY(cudaStreamSynchronize(st));
   void* ptrs[] = {d_s, d_n, d_leaf, d_sel, d_cnt, d_out};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_selftest_select");
   return 0;
-}
-
-extern "C" int mnemo_result_finish(mnemo_result* r, const uint32_t* query_start, uint32_t n_queries,
-                                   uint32_t n_entries_total, mnemo_match* out) {
-  if (!r || !r->owner || !query_start || !out) return -3;
-  mnemo_ctx* ctx = r->ctx;
-  cudaSetDevice(ctx->device);
-  ResultHeader h;
-  cudaError_t e = cudaMemcpy(&h, r->hdr, sizeof h, cudaMemcpyDeviceToHost);
-  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_result_finish");
-  if (h.count > r->cap) {
-    char buf[128];
-    snprintf(buf, sizeof buf, "mnemo_result_finish: candidate capacity exceeded (%u records, capacity %u)", h.count, r->cap);
-    ctx->err = buf;
-    return -1;
-  }
-  static_assert(sizeof(CandDev) == sizeof(mnemo_cand) && sizeof(LastRec) == sizeof(mnemo_lastgroup), "record layouts");
-  std::vector<mnemo_cand> cands(h.count ? h.count : 1);
-  std::vector<mnemo_lastgroup> last((size_t)r->n_shards * r->n_qsigs + 1);
-  if (h.count) e = cudaMemcpy(cands.data(), r->cands, sizeof(mnemo_cand) * h.count, cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess && r->n_qsigs)
-    e = cudaMemcpy(last.data(), r->last, sizeof(mnemo_lastgroup) * (size_t)r->n_shards * r->n_qsigs, cudaMemcpyDeviceToHost);
-  if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_result_finish");
-  return mnemo_search_finish(cands.data(), h.count, last.data(), r->n_shards, query_start, n_queries, n_entries_total, out);
 }

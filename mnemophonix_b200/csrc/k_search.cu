@@ -315,6 +315,12 @@ struct Probe {
   uint32_t qword[kTables];
 };
 
+// bytes in which two words differ (search.c:35-43 counts the equal ones)
+__device__ __forceinline__ uint32_t differing_bytes(uint32_t a, uint32_t b) {
+  const uint32_t x = a ^ b;
+  return __popc((((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u);
+}
+
 // Deep check of one database signature against the query, by one warp.  Returns (hits, score).
 __device__ __forceinline__ void check_pair(const uint32_t* __restrict__ db_words, uint32_t g, const Probe& pr,
                                            uint32_t size, uint64_t magic, int lane, uint32_t* hits, uint32_t* score) {
@@ -398,36 +404,46 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
   // signature yields its shared-bucket count and its equal-byte count together, and lane r scores signature r.
   // (One thread per signature with 25 loads of its own cost 32 L1 sectors per load instruction and made the L1 the
   // bound of the kernel: 84 of 150 ms per batch at config #4; one warp per signature kept a single row in flight.)
+  // Two equal words are two shared buckets (same key, same slot), so the reduction counts differing bytes and EQUAL
+  // words; only a signature with fewer than two equal words can still share two buckets through key % size
+  // collisions (lsh.c:74), and only for those the slots are recomputed from the signature (same_slot).
   auto check_list = [&](const uint32_t* lst, uint32_t n, uint32_t g_skip) {
     const uint32_t my_slot = lane < kTables ? pr.qslot[lane] : 0u, my_word = lane < kTables ? pr.qword[lane] : 0u;
     for (uint32_t base = (uint32_t)warp * 32u; base < n; base += kSearchThreads) {
       const uint32_t cnt = min(32u, n - base);
+      const uint32_t my_g = lst[base + ((uint32_t)lane < cnt ? lane : 0)];
       uint32_t w[32];
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
-        const uint32_t g = lst[base + ((uint32_t)r < cnt ? r : 0)];   // shared-memory broadcast
-        w[r] = lane < kTables ? __ldg(dbw + (uint64_t)g * kTables + lane) : 0u;
+        const uint32_t g = __shfl_sync(0xffffffffu, my_g, r);
+        w[r] = lane < kTables ? __ldg(dbw + (uint64_t)g * kTables + lane) : 0u;   // lanes >= 25 hold "equal" words
       }
       uint32_t mine = 0;
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
-        uint32_t v = 0;
-        if (lane < kTables) {
-          const uint32_t h = same_slot(bucket_key(w[r]), my_slot, p.div_inv, p.div_shift, p.div_thr);
-          v = (__popc(__vcmpeq4(w[r], my_word)) >> 3) | (h << 16);   // search.c:35-43 equal bytes | bucket hit
-        }
+        uint32_t v = differing_bytes(w[r], my_word) | (w[r] == my_word ? 0x10000u : 0u);
         v = __reduce_add_sync(0xffffffffu, v);
         if (lane == r) mine = v;
       }
-      if ((uint32_t)lane < cnt) {
-        const uint32_t g = lst[base + lane], hits = mine >> 16, score = mine & 0xFFFFu;
-        if (g != g_skip && hits >= 2) {   // search.c:147-165 (last group never flushed), MIN_BUCKET_MATCH_FOR_DEEP_CHECK
-          ++deep_t;
-          if (score >= 30) {              // MIN_SCORE (search.c:16)
-            const uint64_t a = (uint64_t)query * p.n_entries + p.sig_entry[g];
-            atomicAdd(&p.acc_score[a], score);
-            atomicAdd(&p.acc_n[a], 1u);
-          }
+      const uint32_t score = 100u - (mine & 0xFFFFu);   // search.c:35-43
+      uint32_t hits = (mine >> 16) - (32u - kTables);
+      uint32_t slow = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && hits < 2u);
+      while (slow) {
+        const int r = __ffs(slow) - 1;
+        slow &= slow - 1u;
+        const uint32_t g = __shfl_sync(0xffffffffu, my_g, r);
+        uint32_t h = 0;
+        if (lane < kTables)
+          h = same_slot(bucket_key(__ldg(dbw + (uint64_t)g * kTables + lane)), my_slot, p.div_inv, p.div_shift, p.div_thr);
+        const uint32_t exact = __popc(__ballot_sync(0xffffffffu, h));
+        if (lane == r) hits = exact;
+      }
+      if ((uint32_t)lane < cnt && my_g != g_skip && hits >= 2u) {   // search.c:147-165 (last group never flushed), MIN_BUCKET_MATCH_FOR_DEEP_CHECK
+        ++deep_t;
+        if (score >= 30u) {                                         // MIN_SCORE (search.c:16)
+          const uint64_t a = (uint64_t)query * p.n_entries + p.sig_entry[my_g];
+          atomicAdd(&p.acc_score[a], score);
+          atomicAdd(&p.acc_n[a], 1u);
         }
       }
     }
@@ -760,63 +776,6 @@ __global__ void __launch_bounds__(256) search_compact_kernel(const uint32_t* __r
     }
 }
 
-// ---- fused "score -> pack -> gather": the shard's records go straight into the merging rank's HBM ----
-// Same compaction as above, but the destination (record array + its counter) lives in the result buffer of
-// the rank that merges: over NVLink peer memory when that is another GPU (cudaIpc mapping), plain global
-// memory when it is this one.  Space is reserved with one system-scope atomic per query; there is no
-// separate collective and no host staging on the data path.
-__global__ void __launch_bounds__(256) search_compact_push_kernel(const uint32_t* __restrict__ acc_score,
-                                                                  const uint32_t* __restrict__ acc_n,
-                                                                  uint32_t n_entries, uint32_t entry_base,
-                                                                  uint32_t query_base, ResultHeader* __restrict__ hdr,
-                                                                  CandDev* __restrict__ cands) {
-  __shared__ uint32_t ws[8];
-  __shared__ uint32_t s_base;
-  const uint32_t q = blockIdx.x;
-  const uint32_t* __restrict__ rn = acc_n + (uint64_t)q * n_entries;
-  const uint32_t* __restrict__ rs = acc_score + (uint64_t)q * n_entries;
-  const uint32_t per = (n_entries + 255) / 256;
-  const uint32_t lo = min(n_entries, threadIdx.x * per), hi = min(n_entries, lo + per);
-  uint32_t c = 0;
-  for (uint32_t e = lo; e < hi; ++e) c += rn[e] != 0;
-  uint32_t tot;
-  uint32_t off = blk_excl(c, ws, &tot);
-  if (threadIdx.x == 0) s_base = tot ? atomicAdd_system(&hdr->count, tot) : 0;
-  __syncthreads();
-  off += s_base;
-  const uint32_t cap = hdr->cap;
-  for (uint32_t e = lo; e < hi; ++e)
-    if (rn[e] != 0) {
-      if (off < cap) {
-        CandDev r;
-        r.query = query_base + q;
-        r.entry = (int32_t)(entry_base + e);
-        r.score = (float)rs[e];
-        r.n_matches = (int32_t)rn[e];
-        cands[off] = r;
-      }
-      ++off;
-    }
-}
-
-// This shard's "last group" records (one per query signature), converted to (entry, signature) and written
-// into row `shard` of the merging rank's table.
-__global__ void __launch_bounds__(256) search_last_push_kernel(const mnemo_lastgroup_dev* __restrict__ last,
-                                                               uint32_t n_qsigs, const uint32_t* __restrict__ sig_entry,
-                                                               const uint32_t* __restrict__ entry_start,
-                                                               uint32_t entry_base, LastRec* __restrict__ dst) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_qsigs) return;
-  const mnemo_lastgroup_dev l = last[i];
-  LastRec r = {l.has, 0u, 0u, l.hits, l.score};
-  if (l.has) {
-    const uint32_t le = sig_entry[l.g];
-    r.entry = entry_base + le;
-    r.sig = l.g - entry_start[le];
-  }
-  dst[i] = r;
-}
-
 // get_matches for one signature: gather (global id) of every bucket member, table by table
 __global__ void __launch_bounds__(256) search_gather_kernel(SearchParams p, uint32_t* __restrict__ out, uint32_t cap,
                                                             uint32_t* __restrict__ table_counts) {
@@ -845,7 +804,13 @@ __global__ void __launch_bounds__(256) search_gather_kernel(SearchParams p, uint
 
 void launch_search(const SearchParams& p, uint32_t n_query_sigs, cudaStream_t st) {
   if (!n_query_sigs) return;
-  cudaFuncSetAttribute(search_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes());
+  static unsigned long long configured = 0;   // the attribute is per function and device: set once per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((configured >> (dev & 63)) & 1ull)) {
+    cudaFuncSetAttribute(search_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes());
+    configured |= 1ull << (dev & 63);
+  }
   search_probe_kernel<<<n_query_sigs, kSearchThreads, search_smem_bytes(), st>>>(p);
 }
 void launch_search_compact(const uint32_t* acc_score, const uint32_t* acc_n, uint32_t n_queries, uint32_t n_entries,
@@ -853,16 +818,6 @@ void launch_search_compact(const uint32_t* acc_score, const uint32_t* acc_n, uin
                            uint32_t* q_cnt, cudaStream_t st) {
   if (n_queries) search_compact_kernel<<<n_queries, 256, 0, st>>>(acc_score, acc_n, n_entries, entry_base, cands, cap,
                                                                   total, q_base, q_cnt);
-}
-void launch_search_push(const uint32_t* acc_score, const uint32_t* acc_n, uint32_t n_queries, uint32_t n_entries,
-                        uint32_t entry_base, uint32_t query_base, ResultHeader* hdr, CandDev* cands, cudaStream_t st) {
-  if (n_queries)
-    search_compact_push_kernel<<<n_queries, 256, 0, st>>>(acc_score, acc_n, n_entries, entry_base, query_base, hdr, cands);
-}
-void launch_search_last_push(const mnemo_lastgroup_dev* last, uint32_t n_qsigs, const uint32_t* sig_entry,
-                             const uint32_t* entry_start, uint32_t entry_base, LastRec* dst, cudaStream_t st) {
-  if (n_qsigs)
-    search_last_push_kernel<<<(n_qsigs + 255) / 256, 256, 0, st>>>(last, n_qsigs, sig_entry, entry_start, entry_base, dst);
 }
 void launch_search_gather(const SearchParams& p, uint32_t* out, uint32_t cap, uint32_t* table_counts, cudaStream_t st) {
   search_gather_kernel<<<1, 256, 0, st>>>(p, out, cap, table_counts);

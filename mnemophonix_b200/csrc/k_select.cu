@@ -144,22 +144,86 @@ __global__ void __launch_bounds__(kSelThreads)
 
 // Sharded search: a shard's own last group (search.c:147-165 drops the greatest (entry, signature) candidate of a query
 // signature) has to be scored after all whenever a HIGHER shard holds a candidate for that query signature, because
-// then the globally greatest candidate lives there.  One thread per query signature.
+// then the globally greatest candidate lives there.  has_all[r][s] are the all-gathered flags of the n_shards shards.
+// One thread per query signature.
 __global__ void __launch_bounds__(256) search_fixup_kernel(const mnemo_lastgroup_dev* __restrict__ last,
-                                                           const uint8_t* __restrict__ has_higher, uint32_t n_qsigs,
+                                                           const uint8_t* __restrict__ has_all, uint32_t n_shards,
+                                                           uint32_t shard, uint32_t n_qsigs,
                                                            const uint32_t* __restrict__ query_start, uint32_t n_queries,
                                                            const uint32_t* __restrict__ sig_entry, uint32_t n_entries,
                                                            uint32_t* __restrict__ acc_score, uint32_t* __restrict__ acc_n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_qsigs) return;
   const mnemo_lastgroup_dev l = last[i];
-  if (!l.has || !has_higher[i]) return;
-  if (l.hits >= 2 && l.score >= 30) {   // search.c:11,16
-    const uint32_t q = find_segment<uint32_t>(query_start, n_queries, i);
-    const uint64_t a = (uint64_t)q * n_entries + sig_entry[l.g];
-    atomicAdd(&acc_score[a], l.score);
-    atomicAdd(&acc_n[a], 1u);
+  if (!l.has || l.hits < 2 || l.score < 30) return;   // search.c:11,16
+  uint32_t higher = 0;
+  for (uint32_t r = shard + 1; r < n_shards; ++r) higher |= has_all[(uint64_t)r * n_qsigs + i];
+  if (!higher) return;
+  const uint32_t q = find_segment<uint32_t>(query_start, n_queries, i);
+  const uint64_t a = (uint64_t)q * n_entries + sig_entry[l.g];
+  atomicAdd(&acc_score[a], l.score);
+  atomicAdd(&acc_n[a], 1u);
+}
+
+// Top levels of the ranking tree, one thread per query: the lists of the n_nodes nodes (every shard's block of the
+// all-gathered buffer holds [nodes_per_shard][n_queries][kSelTop] records followed by [nodes_per_shard][n_queries]
+// counts; shard r owns nodes r * n_nodes / n_shards .. (r + 1) * n_nodes / n_shards - 1) are merged pairwise exactly as
+// glibc's merge sort merges the nodes' sorted ranges, truncated to the first ten, then search.c:173-185.
+__global__ void __launch_bounds__(128) select_merge_kernel(const uint8_t* __restrict__ gathered, uint32_t n_shards,
+                                                           uint32_t n_nodes, uint32_t nodes_per_shard, uint32_t n_queries,
+                                                           mnemo_match_dev* __restrict__ out) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_queries) return;
+  const uint64_t shard_bytes = (uint64_t)nodes_per_shard * n_queries * (sizeof(SelRec) * kSelTop + 4);
+  const uint64_t lists_bytes = (uint64_t)nodes_per_shard * n_queries * sizeof(SelRec) * kSelTop;
+  SelRec cur[kMergeMaxNodes / 2][kSelTop];   // level buffers: the leaves are read from the gathered buffer directly
+  uint32_t ccnt[kMergeMaxNodes / 2];
+  auto leaf = [&](uint32_t node, const SelRec** lst) -> uint32_t {
+    uint32_t r = 0;
+    while (r + 1 < n_shards && (uint64_t)(r + 1) * n_nodes / n_shards <= node) ++r;
+    const uint32_t slot = node - (uint32_t)((uint64_t)r * n_nodes / n_shards);
+    const uint8_t* blk = gathered + (uint64_t)r * shard_bytes;
+    *lst = reinterpret_cast<const SelRec*>(blk) + ((uint64_t)slot * n_queries + q) * kSelTop;
+    const uint32_t c = reinterpret_cast<const uint32_t*>(blk + lists_bytes)[(uint64_t)slot * n_queries + q];
+    return c < (uint32_t)kSelTop ? c : (uint32_t)kSelTop;
+  };
+  auto merge = [&](const SelRec* A, uint32_t ca, const SelRec* B, uint32_t cb, SelRec* O) -> uint32_t {
+    SelRec tmp[kSelTop];
+    uint32_t ia = 0, ib = 0, w = 0;
+    while (w < (uint32_t)kSelTop && ia < ca && ib < cb)
+      tmp[w++] = cmp_entry_avg(A[ia].avg, A[ia].n, B[ib].avg, B[ib].n) <= 0 ? A[ia++] : B[ib++];
+    while (w < (uint32_t)kSelTop && ia < ca) tmp[w++] = A[ia++];
+    while (w < (uint32_t)kSelTop && ib < cb) tmp[w++] = B[ib++];
+    for (uint32_t k = 0; k < w; ++k) O[k] = tmp[k];   // O may alias A
+    return w;
+  };
+  uint32_t root_cnt;
+  const SelRec* root;
+  if (n_nodes == 1) {
+    root_cnt = leaf(0, &root);
+  } else {
+    for (uint32_t i = 0; i < n_nodes / 2; ++i) {
+      const SelRec *A, *B;
+      const uint32_t ca = leaf(2 * i, &A), cb = leaf(2 * i + 1, &B);
+      ccnt[i] = merge(A, ca, B, cb, cur[i]);
+    }
+    for (uint32_t m = n_nodes / 2; m > 1; m >>= 1)
+      for (uint32_t i = 0; i < m / 2; ++i) ccnt[i] = merge(cur[2 * i], ccnt[2 * i], cur[2 * i + 1], ccnt[2 * i + 1], cur[i]);
+    root = cur[0];
+    root_cnt = ccnt[0];
   }
+  mnemo_match_dev best = {-7, 0.0f, 0};
+  float best_avg = 0.0f;
+  for (uint32_t k = 0; k < root_cnt; ++k) {
+    const SelRec r = root[k];
+    if ((r.n >= 10 || (r.avg >= 35.0f && r.n >= 5)) && r.avg >= 30.0f && r.avg > best_avg) {
+      best_avg = r.avg;
+      best.entry = r.entry;
+      best.score = r.score;
+      best.n_matches = r.n;
+    }
+  }
+  out[q] = best;
 }
 
 __global__ void __launch_bounds__(256) search_has_kernel(const mnemo_lastgroup_dev* __restrict__ last, uint32_t n_qsigs,
@@ -168,12 +232,18 @@ __global__ void __launch_bounds__(256) search_has_kernel(const mnemo_lastgroup_d
   if (i < n_qsigs) has[i] = last[i].has ? 1 : 0;
 }
 
-void launch_search_fixup(const mnemo_lastgroup_dev* last, const uint8_t* has_higher, uint32_t n_qsigs,
-                         const uint32_t* query_start, uint32_t n_queries, const uint32_t* sig_entry, uint32_t n_entries,
-                         uint32_t* acc_score, uint32_t* acc_n, cudaStream_t st) {
+void launch_search_fixup(const mnemo_lastgroup_dev* last, const uint8_t* has_all, uint32_t n_shards, uint32_t shard,
+                         uint32_t n_qsigs, const uint32_t* query_start, uint32_t n_queries, const uint32_t* sig_entry,
+                         uint32_t n_entries, uint32_t* acc_score, uint32_t* acc_n, cudaStream_t st) {
   if (n_qsigs)
-    search_fixup_kernel<<<(n_qsigs + 255) / 256, 256, 0, st>>>(last, has_higher, n_qsigs, query_start, n_queries, sig_entry,
-                                                               n_entries, acc_score, acc_n);
+    search_fixup_kernel<<<(n_qsigs + 255) / 256, 256, 0, st>>>(last, has_all, n_shards, shard, n_qsigs, query_start, n_queries,
+                                                               sig_entry, n_entries, acc_score, acc_n);
+}
+void launch_select_merge(const void* gathered, uint32_t n_shards, uint32_t n_nodes, uint32_t nodes_per_shard,
+                         uint32_t n_queries, mnemo_match_dev* out, cudaStream_t st) {
+  if (n_queries)
+    select_merge_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(reinterpret_cast<const uint8_t*>(gathered), n_shards, n_nodes,
+                                                                 nodes_per_shard, n_queries, out);
 }
 void launch_search_has(const mnemo_lastgroup_dev* last, uint32_t n_qsigs, uint8_t* has, cudaStream_t st) {
   if (n_qsigs) search_has_kernel<<<(n_qsigs + 255) / 256, 256, 0, st>>>(last, n_qsigs, has);

@@ -19,18 +19,6 @@ struct CandDev {
   int32_t n_matches;
 };
 
-// Result buffer of the merging rank (device memory, possibly mapped into other processes by cudaIpc):
-// [ResultHeader][CandDev cands[cap]][LastRec last[n_shards][n_qsigs]]
-struct ResultHeader {
-  uint32_t count;   // candidate records reserved so far (may exceed cap: overflow is detected by the owner)
-  uint32_t cap;
-  uint32_t n_shards;
-  uint32_t n_qsigs;
-};
-struct LastRec {
-  uint32_t has, entry, sig, hits, score;
-};
-
 // ---- final ranking (k_select.cu) ----
 constexpr int kSelTop = 10;   // search.c:175: only the first ten records of the sorted array are looked at
 struct SelRec {
@@ -93,15 +81,14 @@ void launch_search(const SearchParams& p, uint32_t n_query_sigs, cudaStream_t st
 void launch_search_compact(const uint32_t* acc_score, const uint32_t* acc_n, uint32_t n_queries, uint32_t n_entries,
                            uint32_t entry_base, CandDev* cands, uint32_t cap, uint32_t* total, uint32_t* q_base,
                            uint32_t* q_cnt, cudaStream_t st);
-void launch_search_push(const uint32_t* acc_score, const uint32_t* acc_n, uint32_t n_queries, uint32_t n_entries,
-                        uint32_t entry_base, uint32_t query_base, ResultHeader* hdr, CandDev* cands, cudaStream_t st);
-void launch_search_last_push(const mnemo_lastgroup_dev* last, uint32_t n_qsigs, const uint32_t* sig_entry,
-                             const uint32_t* entry_start, uint32_t entry_base, LastRec* dst, cudaStream_t st);
 void launch_search_gather(const SearchParams& p, uint32_t* out, uint32_t cap, uint32_t* table_counts, cudaStream_t st);
 uint32_t lsh_scan_blocks(uint64_t n_slots);
-void launch_search_fixup(const mnemo_lastgroup_dev* last, const uint8_t* has_higher, uint32_t n_qsigs,
-                         const uint32_t* query_start, uint32_t n_queries, const uint32_t* sig_entry, uint32_t n_entries,
-                         uint32_t* acc_score, uint32_t* acc_n, cudaStream_t st);
+void launch_search_fixup(const mnemo_lastgroup_dev* last, const uint8_t* has_all, uint32_t n_shards, uint32_t shard,
+                         uint32_t n_qsigs, const uint32_t* query_start, uint32_t n_queries, const uint32_t* sig_entry,
+                         uint32_t n_entries, uint32_t* acc_score, uint32_t* acc_n, cudaStream_t st);
+constexpr int kMergeMaxNodes = 16;   // shards per database in the ranked-shard protocol (one box: <= 8 GPUs)
+void launch_select_merge(const void* gathered, uint32_t n_shards, uint32_t n_nodes, uint32_t nodes_per_shard,
+                         uint32_t n_queries, mnemo_match_dev* out, cudaStream_t st);
 void launch_search_has(const mnemo_lastgroup_dev* last, uint32_t n_qsigs, uint8_t* has, cudaStream_t st);
 uint32_t select_depth(uint32_t n_total);
 uint32_t select_grid(uint32_t n_queries, int sm_count);

@@ -2,11 +2,12 @@
 
 Index: tracks are independent units -> sharded across ranks with NO data-path collective
 (SURVEY.md §8e); per-track results are gathered on the host only to restore input order.
-Search: the database is split into contiguous entry ranges, one per rank; every rank probes its
-shard with the GLOBAL table size (lsh.c:61) and the per-query candidate records are exchanged with
-ONE all-gather (NCCL on GPU tensors; gloo on CPU tensors in the tests), after which the exact final
-ranking (search.c:170-193) runs on the host.  The records are a few hundred bytes per query: the
-exchange is latency-bound, which is why it is a single fixed-capacity collective.
+Search: RankedShardedSearcher — the database is split on node boundaries of the reference's ranking
+tree, one contiguous entry range per rank; every rank probes its shard with the GLOBAL table size
+(lsh.c:61), ranks its own nodes on its GPU, and two small all-gathers per query tile (NCCL on device
+tensors, no host bounce) carry one byte per query signature and ten records per query and node; the
+top levels of the tree are merged on the GPU.  search_sharded / merge_shards are the older record form
+(arbitrary cuts, host merge), kept as a diagnostic.
 """
 from __future__ import annotations
 
@@ -120,165 +121,153 @@ def search_sharded(ctx, entry_sigs, queries, rank: int, world: int, device, grou
     return merge_shards(cands, last, qstart, len(entry_sigs), device=device, group=group), db
 
 
-def search_sharded_push(ctx, entry_sigs, queries, rank: int, world: int, group=None, db=None, merge_rank: int = 0,
-                        cap: int | None = None):
-    """Sharded search with the merge fused into the kernels: every rank's search epilogue writes its candidate
-    and last-group records straight into the merging rank's HBM over NVLink peer memory (CUDA IPC mapping);
-    the only inter-process traffic besides that is the 64-byte handle and two barriers.  Returns
-    (results on merge_rank / None elsewhere, db)."""
-    import torch.distributed as dist
-    counts = [len(s) for s in entry_sigs]
-    cuts = entry_ranges(counts, world)
-    a, b = cuts[rank], cuts[rank + 1]
-    if db is None:
-        db = capi.Db(ctx, entry_sigs[a:b], table_size=int(sum(counts)) // 2, entry_base=a)
-    prepared = queries if isinstance(queries, tuple) else capi.Db.prepare(queries)
-    qstart = prepared[1]
-    nq, nqs = len(qstart) - 1, int(qstart[-1])
-    cap = cap or max(4096, 64 * nq)
-    if world == 1:
-        res, _ = capi.Result.create(ctx, cap, 1, nqs)
-        res.push(db, prepared, 0)
-        out = res.finish(qstart, len(entry_sigs))
-        res.close()
-        return out, db
-    box = [None]
-    if rank == merge_rank:
-        res, handle = capi.Result.create(ctx, cap, world, nqs)
-        box[0] = handle
-    dist.broadcast_object_list(box, src=merge_rank, group=group)
-    if rank != merge_rank:
-        res = capi.Result.open(ctx, box[0], cap, world, nqs)
-    dist.barrier(group=group)              # the buffer is zeroed and mapped everywhere
-    res.push(db, prepared, rank)           # returns once this rank's records are in the merging rank's memory
-    dist.barrier(group=group)
-    out = res.finish(qstart, len(entry_sigs)) if rank == merge_rank else None
-    dist.barrier(group=group)              # nobody unmaps before the owner has read
-    res.close()
-    return out, db
-
-
-class ShardedSearcher:
-    """A database shard per rank plus ONE result buffer kept mapped on every rank (peer memory over NVLink),
-    reused for every query batch of the same size: what a resident search service does.  Per batch the ranks
-    meet at two barriers (buffer cleared / records written); there is no other inter-process traffic.
-
-        s = ShardedSearcher(ctx, my_entry_sigs, table_size, entry_base, n_entries_total, rank, world)
-        results = s.search(prepared_queries)        # list on merge_rank, None elsewhere
-    """
-
-    def __init__(self, ctx, shard_sigs, table_size: int, entry_base: int, n_entries_total: int, rank: int,
-                 world: int, group=None, merge_rank: int = 0):
-        self.ctx, self.rank, self.world, self.group, self.merge_rank = ctx, rank, world, group, merge_rank
-        self.n_entries_total = n_entries_total
-        self.db = capi.Db(ctx, shard_sigs, table_size=table_size, entry_base=entry_base)
-        self.res, self.res_key = None, None
-
-    def _barrier(self):
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.barrier(group=self.group)
-
-    def _result(self, cap: int, nqs: int):
-        if self.res_key == (cap, nqs):
-            return self.res
-        self._drop_result()
-        if self.world == 1:
-            self.res, _ = capi.Result.create(self.ctx, cap, 1, nqs)
-        else:
-            import torch.distributed as dist
-            box = [None]
-            if self.rank == self.merge_rank:
-                self.res, box[0] = capi.Result.create(self.ctx, cap, self.world, nqs)
-            dist.broadcast_object_list(box, src=self.merge_rank, group=self.group)
-            if self.rank != self.merge_rank:
-                self.res = capi.Result.open(self.ctx, box[0], cap, self.world, nqs)
-        self.res_key = (cap, nqs)
-        return self.res
-
-    def search(self, queries, cap: int | None = None):
-        prepared = queries if isinstance(queries, tuple) else capi.Db.prepare(queries)
-        qstart = prepared[1]
-        nq, nqs = len(qstart) - 1, int(qstart[-1])
-        res = self._result(cap or max(4096, 64 * nq), nqs)
-        if self.rank == self.merge_rank:
-            res.reset()
-        self._barrier()                       # the buffer is cleared (and mapped everywhere)
-        res.push(self.db, prepared, self.rank)
-        self._barrier()                       # every shard's records are in the merging rank's memory
-        return res.finish(qstart, self.n_entries_total) if self.rank == self.merge_rank else None
-
-    def close(self):
-        self._drop_result()
-        self.db.close()
-
-    def _drop_result(self):
-        if self.res is None:
-            return
-        self._barrier()                       # nobody unmaps before the owner has read
-        if self.rank != self.merge_rank:
-            self.res.close()
-        self._barrier()                       # the owner frees once every peer mapping is gone
-        if self.rank == self.merge_rank:
-            self.res.close()
-        self.res, self.res_key = None, None
-
-
 class RankedShardedSearcher:
     """Sharded search with the ranking done where the entries live (k_select.cu): shards sit on node boundaries of
     the reference's merge-sort tree, each rank ranks its own nodes on its GPU and contributes ten records per query
-    and node.  Two small all-gathers per batch (NCCL on GPU tensors; gloo on CPU tensors in tests): one byte per
-    query signature ("this shard holds a candidate"), then the lists.  Every rank returns the results.
+    and node.  Two small all-gathers per query tile, on device tensors and on the context's stream (NCCL; gloo on
+    CPU tensors in the tests, where a stand-in replaces the GPU probe): one byte per query signature ("this shard
+    holds a candidate"), then the lists; the top levels of the tree are merged on every rank's GPU and 12 bytes per
+    query come back to the host.  Every rank returns the results.
 
         cuts, node_lo = capi.tree_cuts(n_entries_total, world)       # rank r owns entries cuts[r] .. cuts[r+1]-1
-        s = RankedShardedSearcher(ctx, sigs_of_my_entries, table_size, n_entries_total, rank, world, device)
+        s = RankedShardedSearcher(ctx, sigs_of_my_entries, table_size, n_entries_total, rank, world, device,
+                                  stream=torch_stream_the_context_runs_on)
         results = s.search(prepared_queries)
     """
 
+    PHASES = ("probe", "has_gather", "fixup_rank", "list_gather", "merge")
+
     def __init__(self, ctx, shard_sigs, table_size: int, n_entries_total: int, rank: int, world: int, device="cpu",
-                 group=None, db_factory=None):
-        """db_factory(shard_sigs, table_size, entry_base) -> object with dense_begin / dense_lists / close; default:
-        capi.Db on ctx (the CPU tests pass a stand-in so that the plumbing runs without a GPU)."""
-        self.ctx, self.rank, self.world, self.device, self.group = ctx, rank, world, device, group
+                 group=None, db_factory=None, stream=None, tile_queries: int | None = None):
+        """db_factory(shard_sigs, table_size, entry_base) -> object with dense_begin / dense_lists / close (host
+        arrays): the CPU tests pass an oracle-backed stand-in so that the collectives run without a GPU.  stream: the
+        torch.cuda.Stream whose handle the context was created with (None: the device is synchronised around the
+        collectives instead)."""
+        import os
+        self.ctx, self.rank, self.world, self.device, self.group, self.stream = ctx, rank, world, device, group, stream
         self.cuts, self.node_lo = capi.tree_cuts(n_entries_total, world)
-        n_nodes = len(self.node_lo) - 1
-        self.node_range = (rank * n_nodes // world, (rank + 1) * n_nodes // world)     # my nodes
+        self.n_nodes = len(self.node_lo) - 1
+        own = [(r + 1) * self.n_nodes // world - r * self.n_nodes // world for r in range(world)]
+        self.per = max(own)                                                                 # nodes per shard block
+        self.node_range = (rank * self.n_nodes // world, (rank + 1) * self.n_nodes // world)     # my nodes
         a, b = int(self.cuts[rank]), int(self.cuts[rank + 1])
         assert len(shard_sigs) == b - a, "shard does not match capi.tree_cuts"
+        self.on_gpu = db_factory is None
         self.db = db_factory(shard_sigs, table_size, a) if db_factory else \
             capi.Db(ctx, shard_sigs, table_size=table_size, entry_base=a)
+        # every rank must cut the batch into the same tiles: sized for the largest shard
+        budget = int(os.environ.get("MNEMO_ACC_BYTES", 1 << 30))
+        widest = max(int(self.cuts[r + 1] - self.cuts[r]) for r in range(world))
+        self.tile = tile_queries or max(1, budget // (8 * max(widest, 1)))
+        self.phase_ms = dict.fromkeys(self.PHASES, 0.0)
+        self.profile = False
+        self.message_bytes = 0          # bytes this rank contributed to the collectives of the last search()
 
-    def _all_gather(self, arr: np.ndarray):
-        """Equal-shaped numpy arrays from every rank, in rank order."""
-        if self.world == 1:
-            return [arr]
+    # -- collectives on flat uint8 tensors --
+    def _gather(self, t):
         import torch
         import torch.distributed as dist
-        t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).to(self.device)
-        out = [torch.empty_like(t) for _ in range(self.world)]
-        dist.all_gather(out, t, group=self.group)
-        return [o.cpu().numpy().view(arr.dtype).reshape(arr.shape) for o in out]
+        out = torch.empty(self.world * t.numel(), dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=self.group)
+        self.message_bytes += t.numel()
+        return out
 
     def search(self, queries):
-        prepared = queries if isinstance(queries, tuple) else capi.Db.prepare(queries)
-        has, _ = self.db.dense_begin(prepared)
-        all_has = self._all_gather(has)                                   # the exchange step: 1 byte per query signature
-        higher = np.zeros_like(has)
+        qs, qstart = queries if isinstance(queries, tuple) else capi.Db.prepare(queries)
+        nq = len(qstart) - 1
+        self.message_bytes = 0
+        if self.profile:
+            self.phase_ms = dict.fromkeys(self.PHASES, 0.0)
+        out = []
+        for q0 in range(0, max(nq, 1), self.tile):
+            q1 = min(nq, q0 + self.tile)
+            s0, s1 = int(qstart[q0]), int(qstart[q1])
+            sub = (qs[s0:s1], np.ascontiguousarray(qstart[q0:q1 + 1] - qstart[q0]).astype(np.uint32))
+            out += self._tile_gpu(sub) if self.on_gpu else self._tile_host(sub)
+        return out
+
+    # -- one tile, device-resident (production) --
+    def _tile_gpu(self, sub):
+        import contextlib
+        import torch
+        qs, qstart = sub
+        nq, nqs = len(qstart) - 1, int(qstart[-1])
+        if nq == 0:
+            return []
+        n0, n1 = self.node_range
+        dev = self.device
+        marks = []
+
+        def mark():
+            if self.profile:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(self.stream if self.stream is not None else torch.cuda.current_stream())
+                marks.append(ev)
+
+        def fence():       # without a shared stream the collectives are ordered by device synchronisation
+            if self.stream is None:
+                torch.cuda.synchronize()
+
+        scope = torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
+        with scope:
+            mark()
+            has = torch.empty(max(nqs, 1), dtype=torch.uint8, device=dev)
+            self.db.dense_begin_dev(sub, has.data_ptr())
+            fence()
+            mark()
+            all_has = self._gather(has) if self.world > 1 else has
+            fence()
+            mark()
+            block = torch.zeros(capi.shard_record_bytes(self.per, nq), dtype=torch.uint8, device=dev)
+            lists_ptr = block.data_ptr()
+            counts_ptr = lists_ptr + self.per * nq * 10 * capi.SEL_DTYPE.itemsize
+            self.db.dense_lists_dev(all_has.data_ptr(), self.world, self.rank, self.node_lo[n0:n1 + 1], lists_ptr, counts_ptr)
+            fence()
+            mark()
+            gathered = self._gather(block) if self.world > 1 else block
+            fence()
+            mark()
+            res = capi.select_merge_dev(self.ctx, gathered.data_ptr(), self.world, self.n_nodes, self.per, nq)   # synchronises
+            mark()
+        if self.profile:
+            torch.cuda.synchronize()
+            for name, e0, e1 in zip(self.PHASES, marks[:-1], marks[1:]):
+                self.phase_ms[name] += e0.elapsed_time(e1)
+        return res
+
+    # -- one tile through the host-pointer forms (tests: gloo on CPU tensors, stand-in probe) --
+    def _tile_host(self, sub):
+        import torch
+        qs, qstart = sub
+        nq, nqs = len(qstart) - 1, int(qstart[-1])
+        if nq == 0:
+            return []
+        has, _ = self.db.dense_begin(sub)
+        has = np.ascontiguousarray(has, np.uint8)
+        if self.world > 1:
+            all_has = self._gather(torch.from_numpy(has.copy())).numpy().reshape(self.world, -1)
+        else:
+            all_has = has[None, :]
+        higher = np.zeros(nqs, np.uint8)
         for r in range(self.rank + 1, self.world):
-            higher |= all_has[r]
+            higher |= all_has[r][:nqs]
         n0, n1 = self.node_range
         lists, counts = self.db.dense_lists(higher, self.node_lo[n0:n1 + 1])
-        # ranks may own different numbers of nodes (world not a power of two): pad to the largest for the all-gather
-        n_nodes = len(self.node_lo) - 1
-        per = max((r + 1) * n_nodes // self.world - r * n_nodes // self.world for r in range(self.world))
-        nq = counts.shape[1]
-        pl = np.zeros((per, nq, 10), capi.SEL_DTYPE)
-        pc = np.zeros((per, nq), np.uint32)
+        pl = np.zeros((self.per, nq, 10), capi.SEL_DTYPE)
+        pc = np.zeros((self.per, nq), np.uint32)
         pl[:n1 - n0], pc[:n1 - n0] = lists, counts
-        gl, gc = self._all_gather(pl), self._all_gather(pc)
-        all_l = np.concatenate([gl[r][:(r + 1) * n_nodes // self.world - r * n_nodes // self.world] for r in range(self.world)])
-        all_c = np.concatenate([gc[r][:(r + 1) * n_nodes // self.world - r * n_nodes // self.world] for r in range(self.world)])
-        return capi.select_merge(all_l, all_c)
+        block = np.concatenate([pl.view(np.uint8).reshape(-1), pc.view(np.uint8).reshape(-1)])
+        if self.world > 1:
+            gathered = self._gather(torch.from_numpy(block)).numpy().reshape(self.world, -1)
+        else:
+            gathered = block[None, :]
+        lb = pl.nbytes
+        all_l, all_c = [], []
+        for r in range(self.world):
+            own = (r + 1) * self.n_nodes // self.world - r * self.n_nodes // self.world
+            all_l.append(gathered[r][:lb].view(capi.SEL_DTYPE).reshape(self.per, nq, 10)[:own])
+            all_c.append(gathered[r][lb:].view(np.uint32).reshape(self.per, nq)[:own])
+        return capi.select_merge(np.concatenate(all_l), np.concatenate(all_c))
 
     def close(self):
         self.db.close()

@@ -128,7 +128,7 @@ class _OracleShard:
         pass
 
 
-def _ranked_worker(rank, world, port, out):
+def _ranked_worker(rank, world, port, out, tile=None):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -141,8 +141,9 @@ def _ranked_worker(rank, world, port, out):
     cuts, _ = capi.tree_cuts(len(entries), world)
     mine = entries[int(cuts[rank]):int(cuts[rank + 1])]
     s = mdist.RankedShardedSearcher(None, mine, total // 2, len(entries), rank, world, device="cpu",
-                                    db_factory=lambda sigs, ts, base: _OracleShard(o, sigs, ts, base))
+                                    db_factory=lambda sigs, ts, base: _OracleShard(o, sigs, ts, base), tile_queries=tile)
     res = s.search(capi.Db.prepare(queries))
+    assert s.message_bytes > 0
     s.close()
     if rank == 0:
         out.put(res)
@@ -150,15 +151,16 @@ def _ranked_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_ranked_shards_over_gloo_equal_single_database(world):
-    """dist.RankedShardedSearcher over gloo (two all-gathers, last-group fix-up, host merge of the node lists), the GPU
-    work of each rank stood in for by the oracle: 2 ranks (one node each) and 3 ranks (rank 2 owns two nodes)."""
+@pytest.mark.parametrize("world,tile", [(2, None), (3, None), (2, 2)])
+def test_ranked_shards_over_gloo_equal_single_database(world, tile):
+    """dist.RankedShardedSearcher over gloo (two all-gathers per query tile, last-group fix-up, merge of the node lists),
+    the GPU work of each rank stood in for by the oracle: 2 ranks (one node each), 3 ranks (rank 2 owns two nodes), and
+    2 ranks with the five queries cut into tiles of two."""
     from oracle.oracle import Oracle
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_ranked_worker, args=(r, world, port, out)) for r in range(world)]
+    procs = [ctx.Process(target=_ranked_worker, args=(r, world, port, out, tile)) for r in range(world)]
     for p in procs:
         p.start()
     res = out.get(timeout=180)

@@ -38,17 +38,19 @@ def _worker(rank, world, port, out):
     sigs = [merged[i][0] for i in range(len(pcms))]
     clips = [np.ascontiguousarray(p[5 * 44100 + 321: 10 * 44100 + 321]) for p in pcms]
     qs, _ = ctx.index_pcm_batch(clips)
-    res, db = mdist.search_sharded(ctx, sigs, qs + [sigs[7]], rank, world, device=torch.device("cuda", rank))
-    res_push, _ = mdist.search_sharded_push(ctx, sigs, qs + [sigs[7]], rank, world, db=db)   # NVLink peer-memory merge
-    if rank == 0:
-        assert res_push == res
-    # ranked on the GPUs: shards on node boundaries of the ranking tree, two small all-gathers (dist.RankedShardedSearcher)
+    res, db = mdist.search_sharded(ctx, sigs, qs + [sigs[7]], rank, world, device=torch.device("cuda", rank))   # record form
+    # the production protocol: shards on node boundaries of the ranking tree, ranked on their GPUs, two small
+    # all-gathers on device tensors over NCCL, merged on the GPU (dist.RankedShardedSearcher); queries in tiles of 4
     cuts, _ = capi.tree_cuts(len(sigs), world)
     total = sum(len(x) for x in sigs)
-    ranked = mdist.RankedShardedSearcher(ctx, sigs[int(cuts[rank]):int(cuts[rank + 1])], total // 2, len(sigs), rank, world,
-                                         device=torch.device("cuda", rank))
+    stream = torch.cuda.Stream()
+    ctx_s = capi.Context(rank, stream.cuda_stream)
+    ranked = mdist.RankedShardedSearcher(ctx_s, sigs[int(cuts[rank]):int(cuts[rank + 1])], total // 2, len(sigs), rank, world,
+                                         device=torch.device("cuda", rank), stream=stream, tile_queries=4)
     res_ranked = ranked.search(qs + [sigs[7]])
+    assert ranked.message_bytes > 0
     ranked.close()
+    ctx_s.close()
     assert res_ranked == [tuple(r) for r in res] or res_ranked == res, (res_ranked, res)
     if rank == 0:
         out.put(([len(s) for s in sigs], res, [np.asarray(s).tobytes() for s in sigs], [np.asarray(q).tobytes() for q in qs]))

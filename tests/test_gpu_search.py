@@ -164,38 +164,41 @@ def test_long_buckets_take_the_partitioned_path(ctx, oracle, range_ids, monkeypa
     db.close()
 
 
-def test_peer_push_merge_equals_single_database(ctx, corpus):
-    """The fused merge: every shard's kernels write their records into one result buffer (here all shards live
-    on this GPU; across GPUs the buffer is mapped by CUDA IPC, tests/test_gpu_multi.py)."""
+def test_dense_rows_equal_oracle_and_query_tiles(ctx, oracle, corpus, monkeypatch):
+    """mnemo_search_scores: the dense (score, n_matches) rows of search.c:55-59 equal the oracle's for every query;
+    with the accumulator budget shrunk to a few rows (MNEMO_ACC_BYTES) the batch is processed in several query tiles
+    and nothing changes."""
     sigs, qs = corpus
-    total = sum(len(s) for s in sigs)
-    single = capi.Db(ctx, sigs)
-    queries = qs + [sigs[2]]
-    want, _ = single.search(queries)
-    single.close()
-    prepared = capi.Db.prepare(queries)
-    for cuts in ([0, 12], [0, 5, 12], [0, 3, 6, 9, 12]):
-        shards = [capi.Db(ctx, sigs[a:b], table_size=total // 2, entry_base=a) for a, b in zip(cuts[:-1], cuts[1:])]
-        res, handle = capi.Result.create(ctx, 4096, len(shards), int(prepared[1][-1]))
-        assert len(handle) == 64
-        for r, sh in enumerate(shards):
-            res.push(sh, prepared, r)
-        assert res.finish(prepared[1], len(sigs)) == want
-        res.reset()                                   # reusable for the next batch
-        for r, sh in enumerate(shards):
-            res.push(sh, prepared, r)
-        assert res.finish(prepared[1], len(sigs)) == want
-        res.close()
-        for sh in shards:
-            sh.close()
-    # capacity overflow is an error, not a truncated answer
-    sh = capi.Db(ctx, sigs)
-    res, _ = capi.Result.create(ctx, 2, 1, int(prepared[1][-1]))
-    res.push(sh, prepared, 0)
-    with pytest.raises(capi.MnemoError):
-        res.finish(prepared[1], len(sigs))
-    res.close()
-    sh.close()
+    odb = oracle.make_db(sigs)
+    want_rows = [oracle.search(odb, q)[1] for q in qs]
+    for budget in (None, 8 * len(sigs) * 3):          # default: one tile; then tiles of three queries
+        if budget:
+            monkeypatch.setenv("MNEMO_ACC_BYTES", str(budget))
+        else:
+            monkeypatch.delenv("MNEMO_ACC_BYTES", raising=False)
+        db = capi.Db(ctx, sigs)
+        assert db.tile_queries == (3 if budget else (1 << 30) // (8 * len(sigs)))
+        sc, nm = db.scores(qs)
+        for q, rows in enumerate(want_rows):
+            assert np.array_equal(sc[q], rows[:, 0].astype(np.uint32)) and np.array_equal(nm[q], rows[:, 1].astype(np.uint32))
+        res, _ = db.search(qs)
+        assert [r[0] for r in res] == list(range(len(qs)))
+        cands, _, _, _ = db.search_shard(qs)
+        assert sorted(set(cands["query"].tolist())) == list(range(len(qs)))
+        db.close()
+
+
+def test_get_matches_returns_every_member_of_long_chains(ctx, oracle):
+    """A chain far longer than any fixed gather buffer comes back whole (lsh.c:89-112 never truncates)."""
+    rng = np.random.RandomState(9)
+    e0 = rng.randint(0, 250, (3000, 100)).astype(np.uint8)
+    e0[:, :8] = 7                                        # tables 0 and 1 shared by all 3000
+    db = capi.Db(ctx, [e0])
+    got = db.get_matches(e0[5], cap=1 << 16)
+    want = oracle.get_matches(oracle.make_db([e0]), e0[5])
+    assert len(got) >= 6000 and got == want
+    assert len(db.get_matches(e0[5], cap=16)) == 16      # a small caller buffer is filled, never overrun
+    db.close()
 
 
 # ------------------------------------------------------------------ final ranking on the GPU (k_select.cu) ----
@@ -297,3 +300,59 @@ def test_ranked_shards_equal_single_database(ctx, oracle, corpus):
         assert got == want, world
         for s in shards:
             s.close()
+
+
+@pytest.mark.gpu
+def test_device_resident_ranked_protocol_equals_single_database(ctx, corpus, monkeypatch):
+    """The production form of the sharded search (mnemo_search_dense_begin_dev / _lists_dev / mnemo_select_merge_dev):
+    flags, node lists and the merged answer never leave the device; here all shards live in this process and the two
+    all-gathers are torch.cat.  Also through dist.RankedShardedSearcher with the queries cut into tiles."""
+    import torch
+    from mnemophonix_b200 import dist as mdist
+    sigs, qs = corpus
+    queries = qs + [sigs[2]]
+    total = sum(len(s) for s in sigs)
+    single = capi.Db(ctx, sigs)
+    want, _ = single.search(queries)
+    dense_want = single.scores(queries)
+    single.close()
+    prepared = capi.Db.prepare(queries)
+    nq, nqs = len(queries), int(prepared[1][-1])
+    dev = torch.device("cuda", 0)
+    for world in (1, 2, 3, 5, 8, 16):
+        cuts, node_lo = capi.tree_cuts(len(sigs), world)
+        n_nodes = len(node_lo) - 1
+        per = max((r + 1) * n_nodes // world - r * n_nodes // world for r in range(world))
+        shards = [capi.Db(ctx, sigs[int(cuts[r]):int(cuts[r + 1])], table_size=total // 2, entry_base=int(cuts[r]))
+                  for r in range(world)]
+        has = [torch.zeros(nqs, dtype=torch.uint8, device=dev) for _ in range(world)]
+        for r, s in enumerate(shards):
+            s.dense_begin_dev(prepared, has[r].data_ptr())
+        torch.cuda.synchronize()
+        all_has = torch.cat(has)
+        blocks = []
+        for r, s in enumerate(shards):
+            blk = torch.zeros(capi.shard_record_bytes(per, nq), dtype=torch.uint8, device=dev)
+            n0, n1 = r * n_nodes // world, (r + 1) * n_nodes // world
+            s.dense_lists_dev(all_has.data_ptr(), world, r, node_lo[n0:n1 + 1], blk.data_ptr(),
+                              blk.data_ptr() + per * nq * 10 * capi.SEL_DTYPE.itemsize)
+            blocks.append(blk)
+        torch.cuda.synchronize()
+        got = capi.select_merge_dev(ctx, torch.cat(blocks).data_ptr(), world, n_nodes, per, nq)
+        assert got == want, world
+        # the accumulators after the fix-up, shard by shard, are the single database's dense rows
+        for q in (0, 5, nq - 1):
+            row_s = np.concatenate([s.dense_read(q)[0] for s in shards])
+            row_n = np.concatenate([s.dense_read(q)[1] for s in shards])
+            assert np.array_equal(row_s, dense_want[0][q]) and np.array_equal(row_n, dense_want[1][q]), (world, q)
+        for s in shards:
+            s.close()
+    # the searcher class on one rank (no collective), queries in tiles of four
+    stream = torch.cuda.Stream()
+    ctx2 = capi.Context(0, stream.cuda_stream)
+    one = mdist.RankedShardedSearcher(ctx2, sigs, total // 2, len(sigs), 0, 1, device=dev, stream=stream, tile_queries=4)
+    one.profile = True
+    assert one.search(prepared) == want
+    assert set(one.phase_ms) == set(one.PHASES) and one.phase_ms["probe"] > 0
+    one.close()
+    ctx2.close()
