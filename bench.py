@@ -203,6 +203,50 @@ def search_section(ctx, ref_queries: int = 8, n_tracks: int = 96, seconds: float
     return out
 
 
+def c4_checker(entries, queries, pick, got, single_score, single_n, sharded_rows, threads):
+    """Checker leg of the configs[3] section (rank 0): the sampled queries answered by the unmodified reference
+    (oracle/_ref, host threads: its search() is read-only on the index) and their dense per-entry (score, n_matches)
+    rows by the oracle (search.c:55-59), against the GPU's answers and rows."""
+    import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import ref as refmod
+    from oracle.oracle import Oracle
+    out = {}
+    o = Oracle()
+    odb = o.make_db(entries)
+    with ThreadPoolExecutor(threads) as ex:
+        t0 = time.perf_counter()
+        orc = list(ex.map(lambda i: o.search(odb, queries[i]), pick))
+        out["oracle_s_per_query_1thread"] = (time.perf_counter() - t0) * threads / len(pick)
+    o_rows = np.stack([r[1] for r in orc]).astype(np.int64)           # [sample, n_entries, 2]
+    out["dense_rows_single_gpu_equal_oracle"] = bool(np.array_equal(single_score.astype(np.int64), o_rows[:, :, 0])
+                                                     and np.array_equal(single_n.astype(np.int64), o_rows[:, :, 1]))
+    out["dense_rows_sharded_equal_oracle"] = bool(np.array_equal(np.asarray(sharded_rows).astype(np.int64), o_rows))
+    out["oracle_answers_equal"] = [r[0] for r in orc] == [got[i] for i in pick]
+    if refmod.available():
+        r = refmod.Ref()
+        keep, ents = [], (C.POINTER(refmod.IndexEntry) * len(entries))()
+        for i, e in enumerate(entries):
+            e = np.ascontiguousarray(e)
+            sg = refmod.Signatures(len(e), C.cast(e.ctypes.data, C.POINTER(C.c_uint8 * 100)))
+            ie = refmod.IndexEntry(b"t", b"", b"", b"", C.pointer(sg))
+            keep.append((e, sg, ie))
+            ents[i] = C.pointer(ie)
+        idx = refmod.Index(len(entries), C.cast(ents, C.POINTER(C.POINTER(refmod.IndexEntry))))
+        t0 = time.perf_counter()
+        lsh = r.lib.create_hash_tables(C.byref(idx))
+        out["reference_lsh_build_s"] = time.perf_counter() - t0
+        with ThreadPoolExecutor(threads) as ex:
+            t0 = time.perf_counter()
+            ref_res = list(ex.map(lambda i: r.search(np.ascontiguousarray(queries[i]), C.pointer(idx), lsh), pick))
+            wall = time.perf_counter() - t0
+        out["reference_queries_per_s_1thread"] = len(pick) / (wall * threads)
+        out["reference_sample"] = int(len(pick))
+        out["reference_host_threads"] = threads
+        out["identical_to_reference_on_sample"] = ref_res == [got[i] for i in pick]
+    return out
+
+
 # ----------------------------------------------------------------------- reference arm ----
 def reference_throughput(seconds_sample: float, channels: int, steps: int, warmup: int, variant: str = "O2"):
     """Times the unmodified reference (oracle/_ref -O2, generate_fingerprint on a WAV file) on the host
@@ -485,7 +529,7 @@ def main():
         from mnemophonix_b200 import workloads
         try:
             c4 = workloads.c4_search(ctx, stream, torch.device("cuda", local_rank), rank, world, dist,
-                                     n_tracks=args.search_c4_tracks, ref_queries=args.search_c4_ref_queries)
+                                     n_tracks=args.search_c4_tracks, ref_queries=args.search_c4_ref_queries, checker=c4_checker)
         except Exception as exc:   # a supplementary section must never cost the bench line
             c4 = {"error": repr(exc)}
         if rank == 0:

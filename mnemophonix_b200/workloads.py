@@ -3,16 +3,14 @@
 c4_search: BASELINE.json configs[3] — search N five-second excerpts against an N-track database sharded across the
 ranks of one box (one process per GPU), with the parity checks SURVEY.md §8d asks for:
   * every answer of the sharded search equals the single-GPU answer (the whole database gathered onto rank 0);
-  * a sample of >= 64 queries answered by the unmodified reference (oracle/_ref) on the same database: same entry;
-  * the dense per-entry (score, n_matches) rows of those queries — the single-GPU rows and the sharded rows after the
-    cross-shard last-group fix-up — equal the oracle's search.c:55-59 rows.
+  * a sample of >= 64 queries is handed to the caller's checker together with the dense per-entry (score, n_matches)
+    rows of those queries — the single-GPU rows and the sharded rows after the cross-shard last-group fix-up — so that
+    bench.py can compare answers with the unmodified reference and rows with the oracle's search.c:55-59 rows.
 """
 from __future__ import annotations
 
-import ctypes as C
 import os
 import time
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -43,21 +41,11 @@ def _pad_gather(dist, lists, per, dev, torch):
     return allc.cpu().numpy(), alld.cpu().numpy()
 
 
-def _ref_index(refmod, entries):
-    keep, ents = [], (C.POINTER(refmod.IndexEntry) * len(entries))()
-    for i, e in enumerate(entries):
-        e = np.ascontiguousarray(e)
-        sg = refmod.Signatures(len(e), C.cast(e.ctypes.data, C.POINTER(C.c_uint8 * 100)))
-        ie = refmod.IndexEntry(b"t", b"", b"", b"", C.pointer(sg))
-        keep.append((e, sg, ie))
-        ents[i] = C.pointer(ie)
-    idx = refmod.Index(len(entries), C.cast(ents, C.POINTER(C.POINTER(refmod.IndexEntry))))
-    return idx, (keep, ents)
-
-
 def c4_search(ctx, stream, dev, rank: int, world: int, dist, n_tracks: int = 10000, seconds: float = 30.0, chunk: int = 50,
-              steps: int = 3, ref_queries: int = 64, n_queries: int = 0, host_threads: int = 0):
-    """Returns the result dict on rank 0 (None elsewhere).  dist: torch.distributed (initialised, NCCL) or None."""
+              steps: int = 3, ref_queries: int = 64, n_queries: int = 0, host_threads: int = 0, checker=None):
+    """Returns the result dict on rank 0 (None elsewhere).  dist: torch.distributed (initialised, NCCL) or None.
+    checker(entries, queries, pick, got, single_score_rows, single_n_rows, sharded_rows, threads) -> dict: the caller's
+    comparison with the reference / oracle on the sampled queries (bench.py:c4_checker; this package never touches them)."""
     import torch
     cuts, _ = capi.tree_cuts(n_tracks, world)        # shards on node boundaries of the ranking tree
     a, b = int(cuts[rank]), int(cuts[rank + 1])
@@ -176,37 +164,10 @@ def c4_search(ctx, stream, dev, rank: int, world: int, dist, n_tracks: int = 100
         out["single_gpu_queries_per_s"] = n_q / (time.perf_counter() - t0)
         out["answers_equal_single_gpu"] = int(sum(int(tuple(x) == tuple(y)) for x, y in zip(res, want)))
         out["identical_to_single_gpu"] = out["answers_equal_single_gpu"] == n_q
-        if sample is not None:
+        if sample is not None and checker is not None:
             s_sc, s_nm = single.scores(sample)
             try:
-                from oracle import ref as refmod
-                from oracle.oracle import Oracle
-                threads = host_threads or min(32, os.cpu_count() or 1)
-                o = Oracle()
-                odb = o.make_db(entries)
-                with ThreadPoolExecutor(threads) as ex:
-                    t0 = time.perf_counter()
-                    orc = list(ex.map(lambda i: o.search(odb, queries[i]), pick))
-                    out["oracle_s_per_query_1thread"] = (time.perf_counter() - t0) * threads / len(pick)
-                o_rows = np.stack([r[1] for r in orc]).astype(np.int64)           # [sample, n_entries, 2]
-                out["dense_rows_single_gpu_equal_oracle"] = bool(
-                    np.array_equal(s_sc.astype(np.int64), o_rows[:, :, 0]) and np.array_equal(s_nm.astype(np.int64), o_rows[:, :, 1]))
-                out["dense_rows_sharded_equal_oracle"] = bool(np.array_equal(sharded_rows.astype(np.int64), o_rows))
-                out["oracle_answers_equal"] = [r[0] for r in orc] == [got[i] for i in pick]
-                if refmod.available():
-                    r = refmod.Ref()
-                    idx, keep = _ref_index(refmod, entries)
-                    t0 = time.perf_counter()
-                    lsh = r.lib.create_hash_tables(C.byref(idx))
-                    out["reference_lsh_build_s"] = time.perf_counter() - t0
-                    with ThreadPoolExecutor(threads) as ex:
-                        t0 = time.perf_counter()
-                        ref_res = list(ex.map(lambda i: r.search(np.ascontiguousarray(queries[i]), C.pointer(idx), lsh), pick))
-                        wall = time.perf_counter() - t0
-                    out["reference_queries_per_s_1thread"] = len(pick) / (wall * threads)
-                    out["reference_sample"] = int(len(pick))
-                    out["reference_host_threads"] = threads
-                    out["identical_to_reference_on_sample"] = ref_res == [got[i] for i in pick]
+                out.update(checker(entries, queries, pick, got, s_sc, s_nm, sharded_rows, host_threads or min(32, os.cpu_count() or 1)))
             except Exception as exc:   # the checker is optional here
                 out["reference_check_error"] = repr(exc)
         single.close()

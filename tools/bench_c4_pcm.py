@@ -16,6 +16,7 @@ import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mnemophonix_b200 import capi, workloads
+import bench     # the reference / oracle checker leg lives in bench.py
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--tracks", type=int, default=10000)
@@ -37,7 +38,7 @@ if world > 1:
 stream = torch.cuda.Stream()
 ctx = capi.Context(lr, stream.cuda_stream)
 out = workloads.c4_search(ctx, stream, dev, rank, world, dist, n_tracks=args.tracks, seconds=args.seconds, steps=args.steps,
-                          ref_queries=args.ref_queries, n_queries=args.queries)
+                          ref_queries=args.ref_queries, n_queries=args.queries, checker=bench.c4_checker)
 if rank == 0:
     print(json.dumps(out)); sys.stdout.flush()
 ctx.close()
