@@ -129,6 +129,13 @@ int64_t mnemo_db_get_matches(mnemo_db* db, const uint8_t* sig, uint32_t* pairs_o
 int mnemo_search_batch(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
                        uint32_t n_queries, mnemo_match* out, uint64_t* stats);
 
+/* mnemo_search_batch plus, per query, the matched records among the first ten of the reference's sorted scores[] array
+ * (search.c:170-175), in that order: lists_out[q][10], counts_out[q] (the entries that follow them in the reference's
+ * array are the unmatched entries in index order).  What search(..., verbose) prints (search.c:178). */
+struct mnemo_sel_rec;
+int mnemo_search_batch_top(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start, uint32_t n_queries,
+                           mnemo_match* out, struct mnemo_sel_rec* lists_out, uint32_t* counts_out);
+
 /* The dense rows search.c:55-59 accumulates, for parity checks: score_out / n_matches_out are [n_queries][n_entries of this
  * shard] (host), before any cross-shard fix-up. */
 int mnemo_search_scores(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start, uint32_t n_queries,

@@ -310,11 +310,14 @@ static cudaError_t read_stats(const unsigned long long* d_stats, uint64_t* stats
 // ------------------------------------------------------------------ search: one database on one GPU ----
 
 // probe kernel -> per-(query, entry) accumulators -> exact ranking on the GPU (k_select.cu).  Only 12 bytes per query
-// come back to the host, however many entries a query touches.
-extern "C" int mnemo_search_batch(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
-                                  uint32_t n_queries, mnemo_match* out, uint64_t* stats) {
-  if (!db || !out || !query_start) return -3;
-  for (uint32_t q = 0; q < n_queries; q++) out[q] = mnemo_match{-7, 0.0f, 0};
+// come back to the host, however many entries a query touches; with lists_out the first ten records of the sorted
+// array (search.c:175: what `verbose` prints) come back as well, 164 bytes per query.
+static int search_batch_impl(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start, uint32_t n_queries,
+                             mnemo_match* out, mnemo_sel_rec* lists_out, uint32_t* counts_out, uint64_t* stats) {
+  for (uint32_t q = 0; q < n_queries; q++) {
+    out[q] = mnemo_match{-7, 0.0f, 0};
+    if (counts_out) counts_out[q] = 0;
+  }
   if (stats) stats[0] = stats[1] = 0;
   if (n_queries == 0 || query_start[n_queries] == 0 || db_is_empty(db)) return 0;
   mnemo_ctx* ctx = db->ctx;
@@ -329,25 +332,62 @@ extern "C" int mnemo_search_batch(mnemo_db* db, const uint8_t* query_sigs, const
   SelRec* d_sel = nullptr;
   uint8_t* d_cnt = nullptr;
   mnemo_match_dev* d_out = nullptr;
+  SelRec* d_lists = nullptr;
+  uint32_t* d_counts = nullptr;
+  const uint64_t list_bytes = sizeof(SelRec) * kSelTop * (uint64_t)n_queries;
   TRY(scratch_get(db, kScrLeaf, 4ull * ((1ull << depth) + 1), (void**)&d_leaf));
   TRY(scratch_get(db, kScrSel, sizeof(SelRec) * (uint64_t)grid * n_total, (void**)&d_sel));
   TRY(scratch_get(db, kScrSelCnt, (uint64_t)grid << depth, (void**)&d_cnt));
   TRY(scratch_get(db, kScrOut, sizeof(mnemo_match_dev) * (uint64_t)n_queries, (void**)&d_out));
+  if (lists_out) {
+    TRY(scratch_get(db, kScrLists, list_bytes + 4ull * n_queries, (void**)&d_lists));
+    d_counts = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(d_lists) + list_bytes);
+  }
   if (e == cudaSuccess) launch_select_bounds(n_total, depth, d_leaf, st);
   for (uint32_t q0 = 0; q0 < n_queries && e == cudaSuccess; q0 += b.tile) {
     const uint32_t nq = std::min(b.tile, n_queries - q0);
     TRY(probe_tile(db, b, query_start, q0, nq));
     if (e != cudaSuccess) break;
     launch_search_select(b.d_acc_s, b.d_acc_n, nq, db->n_entries, db->entry_base, n_total, 0, depth, d_leaf, d_sel, d_cnt,
-                         select_grid(nq, ctx->sm_count), d_out + q0, nullptr, nullptr, st);
+                         select_grid(nq, ctx->sm_count), lists_out ? nullptr : d_out + q0,
+                         lists_out ? d_lists + (uint64_t)q0 * kSelTop : nullptr, lists_out ? d_counts + q0 : nullptr, st);
     TRY(cudaGetLastError());
   }
   static_assert(sizeof(mnemo_match_dev) == sizeof(mnemo_match), "match layouts");
-  TRY(cudaMemcpyAsync(out, d_out, sizeof(mnemo_match) * (uint64_t)n_queries, cudaMemcpyDeviceToHost, st));
+  static_assert(sizeof(SelRec) == sizeof(mnemo_sel_rec), "record layouts");
+  if (lists_out) {
+    TRY(cudaMemcpyAsync(lists_out, d_lists, list_bytes, cudaMemcpyDeviceToHost, st));
+    TRY(cudaMemcpyAsync(counts_out, d_counts, 4ull * n_queries, cudaMemcpyDeviceToHost, st));
+  } else {
+    TRY(cudaMemcpyAsync(out, d_out, sizeof(mnemo_match) * (uint64_t)n_queries, cudaMemcpyDeviceToHost, st));
+  }
   TRY(cudaStreamSynchronize(st));
   TRY(read_stats(b.d_stats, stats, st));
   if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_search_batch");
+  if (lists_out)   // search.c:173-185 over the list
+    for (uint32_t q = 0; q < n_queries; q++) {
+      float best_avg = 0.0f;
+      for (uint32_t k = 0; k < counts_out[q] && k < (uint32_t)kSelTop; k++) {
+        const mnemo_sel_rec& r = lists_out[(uint64_t)q * kSelTop + k];
+        if ((r.n_matches >= 10 || (r.avg >= 35.0f && r.n_matches >= 5)) && r.avg >= 30.0f && r.avg > best_avg) {
+          best_avg = r.avg;
+          out[q] = mnemo_match{r.entry, r.score, r.n_matches};
+        }
+      }
+    }
   return 0;
+}
+
+extern "C" int mnemo_search_batch(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start,
+                                  uint32_t n_queries, mnemo_match* out, uint64_t* stats) {
+  if (!db || !out || !query_start) return -3;
+  return search_batch_impl(db, query_sigs, query_start, n_queries, out, nullptr, nullptr, stats);
+}
+
+extern "C" int mnemo_search_batch_top(mnemo_db* db, const uint8_t* query_sigs, const uint32_t* query_start, uint32_t n_queries,
+                                      mnemo_match* out, mnemo_sel_rec* lists_out, uint32_t* counts_out) {
+  if (!db || !out || !query_start || !lists_out || !counts_out) return -3;
+  return search_batch_impl(db, query_sigs, query_start, n_queries, out, lists_out, counts_out, nullptr);
 }
 
 // Diagnostic form: the dense per-entry rows search.c:55-59 accumulates (score sum, n_matches), [n_queries][n_entries]

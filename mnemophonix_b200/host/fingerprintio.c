@@ -61,14 +61,13 @@ static void free_entry(struct index_entry* e) {
 }
 
 static int8_t g_nibble[256];
-static int g_nibble_ready = 0;
+static pthread_once_t g_nibble_once = PTHREAD_ONCE_INIT;   /* read_index is re-entrant like the reference's */
 
 static void init_nibbles(void) {
     memset(g_nibble, -1, sizeof g_nibble);
     for (int c = '0'; c <= '9'; c++) g_nibble[c] = (int8_t)(c - '0');
     for (int c = 'a'; c <= 'f'; c++) g_nibble[c] = (int8_t)(c - 'a' + 10);
     for (int c = 'A'; c <= 'F'; c++) g_nibble[c] = (int8_t)(c - 'A' + 10);
-    g_nibble_ready = 1;
 }
 
 static int read_one_entry(FILE* f, struct index_entry** out) {
@@ -76,7 +75,8 @@ static int read_one_entry(FILE* f, struct index_entry** out) {
     size_t len;
     int rc = next_line(f, buf, NULL);
     if (rc == CANNOT_READ_FILE) return CANNOT_READ_FILE;   /* clean end of the database */
-    if (rc != SUCCESS) return rc;
+    /* fingerprintio.c:78-80 upstream checks only for the end of the file here: an over-long or unterminated first line
+     * is kept as it was read (buf is untouched on DECODING_ERROR) and parsing goes on with what follows */
     struct index_entry* e = (struct index_entry*)calloc(1, sizeof *e);
     if (!e) return MEMORY_ERROR;
     char** fields[4] = {&e->filename, &e->artist, &e->track_title, &e->album_title};
@@ -314,7 +314,7 @@ static int read_index_fast(const char* filename, struct index** index) {
 }
 
 int read_index(const char* filename, struct index** index) {
-    if (!g_nibble_ready) init_nibbles();
+    pthread_once(&g_nibble_once, init_nibbles);
     if (read_index_fast(filename, index)) return SUCCESS;
     FILE* f = fopen(filename, "r");
     if (!f) return CANNOT_READ_FILE;

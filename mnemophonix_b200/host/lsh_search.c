@@ -116,16 +116,40 @@ int get_matches(struct lsh* tables, uint8_t* hash, struct signature_list** list)
     return (int)n;
 }
 
+/* Text of the last CUDA-side failure behind this library (empty when there was none): search() and
+ * create_hash_tables() keep the reference's return conventions, this tells a GPU fault from a miss. */
+const char* mnemo_host_last_error(void) {
+    mnemo_ctx* ctx = mnemo_host_context();
+    return ctx ? mnemo_last_error(ctx) : "no sm_100 GPU available (there is no CPU path)";
+}
+
 int search(struct signatures* sample, struct index* database, struct lsh* lsh, int verbose) {
     struct lsh_private* p = (struct lsh_private*)lsh;
     if (!p || !sample || !database) return MEMORY_ERROR;
     uint32_t qstart[2] = {0, sample->n_signatures};
     mnemo_match m = {NO_MATCH_FOUND, 0.0f, 0};
+    mnemo_sel_rec top[10];
+    uint32_t n_top = 0;
     pthread_mutex_lock(&p->lock);
-    int rc = mnemo_search_batch(p->db, (const uint8_t*)sample->signatures, qstart, 1, &m, NULL);
+    int rc = verbose ? mnemo_search_batch_top(p->db, (const uint8_t*)sample->signatures, qstart, 1, &m, top, &n_top)
+                     : mnemo_search_batch(p->db, (const uint8_t*)sample->signatures, qstart, 1, &m, NULL);
     pthread_mutex_unlock(&p->lock);
     if (rc != 0) return MEMORY_ERROR;
     if (verbose) {
+        /* search.c:175-178: the first ten records of the sorted scores[] array.  Matched entries come first, in the
+         * order of the reference's merge sort (n_top of them, from the GPU); the entries without matches follow in
+         * index order (they compare equal, and glibc's merge sort is stable). */
+        unsigned int printed = 0;
+        for (; printed < n_top && printed < 10; printed++)
+            printf("average_score = %f, n_matches = %d (%s)\n", top[printed].avg, top[printed].n_matches,
+                   database->entries[top[printed].entry]->filename);
+        for (unsigned int e = 0; e < database->n_entries && printed < 10; e++) {
+            int matched = 0;
+            for (unsigned int k = 0; k < n_top; k++) matched |= top[k].entry == (int32_t)e;
+            if (matched) continue;
+            printf("average_score = %f, n_matches = %d (%s)\n", 0.0f, 0, database->entries[e]->filename);
+            printed++;
+        }
         if (m.entry >= 0)
             printf("\n*** match = %f %s ***\n", m.n_matches ? m.score / (float)m.n_matches : 0.0f,
                    database->entries[m.entry]->filename);

@@ -45,26 +45,59 @@ static void usage(const char* me) {
     fprintf(stderr, "\n");
 }
 
-/* Host input stage (ffmpeg.c:35-65 upstream): decode anything to a temporary 44.1 kHz PCM WAVE file
- * with an external ffmpeg.  Returns a malloc'd path or NULL.  Metadata extraction is not carried over. */
-static char* decode_with_ffmpeg(const char* input) {
+/* ffmpeg.c:9-32 upstream: artist= / title= / album= lines of an ffmetadata file (first occurrence wins). */
+static void parse_metadata(const char* path, char** artist, char** track_title, char** album_title) {
+    FILE* f = fopen(path, "r");
+    if (!f) return;
+    char line[1024];
+    while (fgets(line, sizeof line, f)) {
+        size_t len = strlen(line);
+        if (len > 0 && line[len - 1] == '\n') line[len - 1] = '\0';
+        if (artist && !*artist && !strncmp(line, "artist=", 7)) *artist = strdup(line + 7);
+        if (track_title && !*track_title && !strncmp(line, "title=", 6)) *track_title = strdup(line + 6);
+        if (album_title && !*album_title && !strncmp(line, "album=", 6)) *album_title = strdup(line + 6);
+    }
+    fclose(f);
+}
+
+/* Host input stage (ffmpeg.c:35-65 upstream): decode anything to a temporary 44.1 kHz PCM WAVE file with an external
+ * ffmpeg, which also writes the stream's tags to an ffmetadata file (the reference's second output); artist, title
+ * and album come from there.  Returns a malloc'd path or NULL. */
+static char* decode_with_ffmpeg(const char* input, char** artist, char** track_title, char** album_title) {
     char tmpl[] = "/tmp/mnemophonixXXXXXX.wav";
+    char meta[] = "/tmp/mnemophonixXXXXXX.meta";
+    if (artist) *artist = NULL;
+    if (track_title) *track_title = NULL;
+    if (album_title) *album_title = NULL;
     int fd = mkstemps(tmpl, 4);
     if (fd < 0) return NULL;
     close(fd);
+    fd = mkstemps(meta, 5);
+    if (fd < 0) {
+        remove(tmpl);
+        return NULL;
+    }
+    close(fd);
     pid_t pid = fork();
-    if (pid < 0) return NULL;
+    if (pid < 0) {
+        remove(tmpl);
+        remove(meta);
+        return NULL;
+    }
     if (pid == 0) {
         if (!freopen("/dev/null", "w", stderr)) _exit(127);
-        execlp("ffmpeg", "ffmpeg", "-y", "-i", input, "-acodec", "pcm_s16le", "-ar", "44100", "-f", "wav", tmpl,
-               (char*)NULL);
+        execlp("ffmpeg", "ffmpeg", "-y", "-i", input, "-acodec", "pcm_s16le", "-ar", "44100", "-f", "wav", tmpl, "-f",
+               "ffmetadata", meta, (char*)NULL);
         _exit(127);
     }
     int status = 0;
     if (waitpid(pid, &status, 0) < 0 || !WIFEXITED(status) || WEXITSTATUS(status) != 0) {
         remove(tmpl);
+        remove(meta);
         return NULL;
     }
+    parse_metadata(meta, artist, track_title, album_title);
+    remove(meta);
     return strdup(tmpl);
 }
 
@@ -81,7 +114,7 @@ static int fingerprint_input(const char* input, struct signatures** fingerprint,
         case FILE_TOO_SMALL: fprintf(stderr, "'%s' is too small to generate a fingerprint\n", input); return 1;
         case UNSUPPORTED_WAVE_FORMAT:
         case NOT_A_WAVE_FILE: {
-            char* wav = decode_with_ffmpeg(input);
+            char* wav = decode_with_ffmpeg(input, artist, track_title, album_title);
             if (!wav) {
                 fprintf(stderr, "'%s' is not a wave file and we could not convert it to one with fffmpeg\n", input);
                 return 1;
@@ -98,7 +131,14 @@ static int fingerprint_input(const char* input, struct signatures** fingerprint,
     }
 }
 
+const char* mnemo_host_last_error(void);
+
 static int report(const struct index* db, int best) {
+    if (best < 0 && best != NO_MATCH_FOUND) {
+        /* not a miss: the search itself failed (the reference can only run out of memory here) */
+        fprintf(stderr, "Search failed (error %d): %s\n", best, mnemo_host_last_error());
+        return 2;
+    }
     if (best < 0) {
         printf("\nNo match found\n\n");
         return 1;
@@ -136,11 +176,7 @@ int main(int argc, char* argv[]) {
             free(album_title);
             fingerprint = NULL;
             artist = track_title = album_title = NULL;
-            int res = generate_fingerprint(argv[i], &fingerprint, &artist, &track_title, &album_title);
-            if (res != SUCCESS) {
-                fprintf(stderr, "Cannot index '%s' (error %d)\n", argv[i], res);
-                return 1;
-            }
+            if (fingerprint_input(argv[i], &fingerprint, &artist, &track_title, &album_title)) return 1;
             fflush(stdout);
             save(stdout, fingerprint, argv[i], artist, track_title, album_title);
         }
@@ -164,7 +200,7 @@ int main(int argc, char* argv[]) {
     long t2 = now_ms();
     printf("(lsh index building took %ld ms)\n", t2 - t1);
     if (!lsh) {
-        fprintf(stderr, "Memory allocation error\n");
+        fprintf(stderr, "Memory allocation error (%s)\n", mnemo_host_last_error());
         return 1;
     }
     printf("Searching...\n");

@@ -149,6 +149,33 @@ def test_large_index_takes_the_threaded_parser_and_matches_reference(host, ref):
             os.remove(p)
 
 
+def test_over_long_first_line_is_kept_like_the_reference(host, ref):
+    """fingerprintio.c:78-80 only checks the first line of an entry for the end of the file: a file name longer than
+    the 1024-byte line buffer is not an error, the entry simply starts with the first 1023 characters and the rest of
+    the line is read as the artist.  Same entries, or the same error, as the reference."""
+    rng = np.random.RandomState(4)
+    sig = rng.randint(0, 256, (2, 100)).astype(np.uint8)
+    hexed = "".join("".join(f"{b:02x}" for b in row) + "\n" for row in sig)
+    for name_len in (1500, 1023):
+        # what follows the first 1023 characters is the artist line; title, album and count complete a valid entry
+        # (anything else sends the reference into its uninitialised free, fingerprintio.c:117-119)
+        text = "n" * name_len + "\ntitle\nalbum\n2\n" + hexed
+        p = tempfile.mktemp()
+        open(p, "w").write(text)
+        try:
+            mine = C.POINTER(refmod.Index)()
+            rc_mine = host.read_index(p.encode(), C.byref(mine))
+            rc_ref, theirs = ref.load_index(p)
+            assert rc_mine == rc_ref == 0, name_len
+            a, b = entries_of(mine), entries_of(theirs)
+            assert len(a) == len(b) == 1 and all(x[:4] == y[:4] and np.array_equal(x[4], y[4]) for x, y in zip(a, b))
+            assert len(a[0][0]) == 1023 and a[0][1] == b"n" * (name_len - 1023)
+            host.free_index(mine)
+            ref.lib.free_index(theirs)
+        finally:
+            os.remove(p)
+
+
 @pytest.mark.parametrize("mutation,code", [
     (lambda t: t[:-50], -3),                               # truncated last signature line
     (lambda t: t.replace("\n", "", 1), "ours:-3"),         # count line is not a number: DECODING_ERROR by the source, but the
@@ -324,6 +351,62 @@ def test_cli_index_and_search_round_trip(host, ref):
     host.free_signature_list(plist)
     host.free_hash_tables(lsh_mine)
     host.free_index(mine)
+
+
+_VERBOSE_SCRIPT = """
+import sys, ctypes as C
+sys.path.insert(0, %r)
+import numpy as np
+from oracle import ref as refmod
+which, dbpath, qpath = sys.argv[1:4]
+q = np.load(qpath)
+r = refmod.Ref()
+if which == "ref":
+    lib = r.lib
+    rc, idx = r.load_index(dbpath)
+else:
+    lib = C.CDLL(%r)
+    idx = C.POINTER(refmod.Index)()
+    lib.read_index.argtypes = [C.c_char_p, C.POINTER(C.POINTER(refmod.Index))]
+    assert lib.read_index(dbpath.encode(), C.byref(idx)) == 0
+lib.create_hash_tables.argtypes = [C.POINTER(refmod.Index)]
+lib.create_hash_tables.restype = C.c_void_p
+lib.search.argtypes = [C.POINTER(refmod.Signatures), C.POINTER(refmod.Index), C.c_void_p, C.c_int]
+lsh = lib.create_hash_tables(idx)
+for k in range(len(q)):
+    qq = np.ascontiguousarray(q[k])
+    s = refmod.Signatures(len(qq), C.cast(qq.ctypes.data, C.POINTER(C.c_uint8 * 100)))
+    best = lib.search(C.byref(s), idx, lsh, 1)
+    C.CDLL(None).fflush(None)
+    print("RETURNED", best, flush=True)
+"""
+
+
+@pytest.mark.gpu
+def test_verbose_search_prints_the_reference_lines(oracle):
+    """search(..., verbose) (search.c:175-188): the ten `average_score = ...` lines of the sorted scores[] array (matched
+    entries in the merge sort's order, then unmatched entries in index order), the match line and the rule — the
+    whole stdout of the reference, byte for byte, for a 14-entry database (more than ten entries, so the window
+    truncates), a matching clip, a clip matching nothing and a query shorter than the thresholds."""
+    d = tempfile.mkdtemp()
+    pcms = [synth.synth_track(700 + i, 14.0 + (i % 3), 1) for i in range(14)]
+    sigs = [oracle.fingerprint_pcm(p)[1] for p in pcms]
+    dbpath = os.path.join(d, "db")
+    open(dbpath, "w").write(db_text(sigs))
+    qs = [oracle.fingerprint_pcm(pcms[11][3 * 44100 + 77: 8 * 44100 + 77])[1],
+          np.random.RandomState(3).randint(0, 255, (34, 100)).astype(np.uint8),
+          oracle.fingerprint_pcm(pcms[2][5 * 44100: 8 * 44100 + 4000])[1][:3]]
+    width = max(len(q) for q in qs)
+    qpath = os.path.join(d, "q.npy")
+    np.save(qpath, np.stack([np.concatenate([q, np.repeat(q[-1:], width - len(q), 0)]) for q in qs]))
+    outs = {}
+    for which in ("ref", "ours"):
+        r = subprocess.run([os.sys.executable, "-c", _VERBOSE_SCRIPT % (ROOT, LIB), which, dbpath, qpath], capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[which] = r.stdout
+    assert "average_score = " in outs["ref"] and "*** match = " in outs["ref"] and "RETURNED 11" in outs["ref"]
+    assert outs["ours"] == outs["ref"]
 
 
 @pytest.mark.gpu
