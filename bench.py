@@ -47,6 +47,85 @@ def make_track(seconds: float, channels: int, seed: int) -> np.ndarray:
     return np.ascontiguousarray(pcm)
 
 
+def make_worst_content_track(seconds: float, channels: int, seed: int) -> np.ndarray:
+    """Content that defeats the sharing of group records (k15_groups.cu): a frequency-modulated tone under a level that
+    rises steadily for 14 s and drops back (the signal of tests/test_gpu_index.py::test_window_maximum_changes_every_image,
+    as a saw-tooth) gives nearly every spectral image its own window maximum, so an 8-frame group needs up to all 16
+    record slots instead of the ~5 a steady-level take needs (the slots in use are reported)."""
+    n = int(round(min(seconds, 630.0) * 44100))          # 45 saw-teeth, then tiled
+    t = np.arange(n, dtype=np.float64) / 44100.0
+    rng = np.random.RandomState(seed)
+    env = 0.02 + 0.9 * ((t % 14.0) / 14.0) ** 2
+    x = env * (np.sin(2 * np.pi * (500 + 300 * np.sin(2 * np.pi * 0.7 * t)) * t) + 0.2 * rng.standard_normal(n))
+    mono = np.clip(np.round(x * 20000), -32768, 32767).astype(np.int16)
+    take = np.stack([mono] + [np.round(mono * 0.8).astype(np.int16)] * (channels - 1), axis=1) if channels > 1 else mono[:, None]
+    reps = int(np.ceil(seconds * 44100 / n))
+    return np.ascontiguousarray(np.tile(take, (reps, 1))[: int(round(seconds * 44100))])
+
+
+def dropin_section(pcm: np.ndarray, seconds: float, device: int, reps: int = 3):
+    """End to end through the DROP-IN library: generate_fingerprint(path) of libmnemophonix.so (the reference's own entry
+    point, fingerprinting.h:26) on a WAV file in tmpfs, in a warm process: header parse, threaded pread of the data
+    chunk into a ring of pinned buffers, host -> device copies, kernels, signatures back."""
+    import ctypes as C
+    from mnemophonix_b200 import synth
+    tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    path = os.path.join(tmpdir, f"mnemo_dropin_{os.getpid()}.wav")
+    synth.write_wav(path, pcm)
+    os.environ["MNEMO_DEVICE"] = str(device)
+    lib = C.CDLL(os.path.join(ROOT, "mnemophonix_b200", "libmnemophonix.so"))
+
+    class Signatures(C.Structure):
+        _fields_ = [("n_signatures", C.c_uint), ("signatures", C.c_void_p)]
+    lib.generate_fingerprint.argtypes = [C.c_char_p, C.POINTER(C.POINTER(Signatures)), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.free_signatures.argtypes = [C.POINTER(Signatures)]
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(2)
+    times, n_sigs = [], 0
+    try:
+        os.dup2(devnull, 2)                      # the reference's progress lines go to stderr on every call
+        for it in range(reps + 1):               # first call: CUDA context of the library + pinned ring
+            p = C.POINTER(Signatures)()
+            t0 = time.perf_counter()
+            rc = lib.generate_fingerprint(path.encode(), C.byref(p), None, None, None)
+            dt = time.perf_counter() - t0
+            assert rc == 0, rc
+            n_sigs = int(p.contents.n_signatures)
+            lib.free_signatures(p)
+            if it:
+                times.append(dt)
+    finally:
+        os.dup2(saved, 2)
+        os.close(saved)
+        os.close(devnull)
+        if os.path.exists(path):
+            os.remove(path)
+    dt = float(np.median(times))
+    return {"value": (seconds / 3600.0) / dt, "unit": UNIT, "ms_per_call": dt * 1e3, "file_bytes": int(pcm.nbytes),
+            "read_plus_upload_GBps_lower_bound": pcm.nbytes / dt / 1e9, "signatures": n_sigs,
+            "note": "generate_fingerprint(path) through libmnemophonix.so on a WAV in tmpfs, warm process, median of "
+                    f"{reps} calls; includes WAV parsing, device buffer allocation, kernels and the signatures coming back"}
+
+
+def live_section(ctx, seconds: float = 5.0, reps: int = 200):
+    """The live path (generate_fingerprint_from_samples, fingerprinting.c:81-109: what the ears loop calls once a second):
+    latency of one call on a query-sized window of normalised 5512 Hz samples (34 spectral images for 5 s)."""
+    rng = np.random.RandomState(3)
+    n = int(seconds * 5512.5)
+    t = np.arange(n) / 5512.5
+    s = 0.35 * np.sin(2 * np.pi * (600 + 350 * np.sin(2 * np.pi * 0.6 * t)) * t) + 0.2 * np.sin(2 * np.pi * 1310 * t) * (t % 0.7 < 0.3)
+    s = np.clip(s + 0.04 * rng.standard_normal(n), -1, 1).astype(np.float32)
+    for _ in range(5):
+        rc, sigs = ctx.index_samples(s)
+    lat = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        rc, sigs = ctx.index_samples(s)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    return {"samples": n, "signatures": int(len(sigs)), "p50_ms": float(np.percentile(lat, 50)),
+            "p99_ms": float(np.percentile(lat, 99)), "cuda_graph": bool(ctx.live_graph), "calls": reps}
+
+
 # ------------------------------------------------------------------------------ clocks ----
 class ClockSampler:
     """Samples SM clock and throttle reasons in a background thread (NVML, 5 ms period; nvidia-smi as a
@@ -132,19 +211,50 @@ class ClockSampler:
                 "reasons": sorted(n for b, n in self.REASONS.items() if mask & b), "samples": len(inside)}
 
 
-def bind_near_gpu(index: int) -> None:
-    """Pin this process (and thus its pinned-host allocations) to the CPUs/NUMA node next to its GPU, so that
-    N ranks uploading at once do not cross sockets."""
+def _cpulist(text: str) -> list:
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus += list(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_near_gpu(index: int) -> dict:
+    """Pin this process (and thus the first-touch placement of its pinned-host allocations) to the CPUs of the NUMA
+    node its GPU hangs off, so that N ranks uploading at once do not cross sockets.  The node comes from the PCI
+    device's sysfs entry (numa_node), falling back to NVML's CPU affinity; on a single-node box (or when the platform
+    reports nothing: -1) there is nothing to place.  Returns what was found, for the bench line."""
+    info = {"numa_nodes": 0, "gpu_numa_node": None, "bound_cpus": None}
     try:
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        info["numa_nodes"] = len(nodes)
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(index)
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
-        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]                       # 0000:1b:00.0
+        cpus = None
+        try:
+            node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+            info["gpu_numa_node"] = node
+            if node >= 0 and len(nodes) > 1:
+                cpus = _cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+        except Exception:
+            pass
+        if cpus is None and len(nodes) > 1:
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+            if len(cpus) >= (os.cpu_count() or 0):
+                cpus = None                           # "every CPU": uninformative
         if cpus:
             os.sched_setaffinity(0, cpus)
-    except Exception:
-        pass
+            info["bound_cpus"] = f"{cpus[0]}-{cpus[-1]} ({len(cpus)})"
+    except Exception as exc:
+        info["error"] = repr(exc)
+    return info
 
 
 def search_section(ctx, ref_queries: int = 8, n_tracks: int = 96, seconds: float = 30.0):
@@ -359,7 +469,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
-    bind_near_gpu(local_rank)
+    placement = bind_near_gpu(local_rank)
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -425,6 +535,7 @@ def main():
     stage_ms, n_timed = batch.get_timing()
     batch.set_timing(False)
     launches_per_run = batch.launches()
+    slots_in_use = batch.record_slots_in_use(0)
     value = world * hours_per_step / (ms_per_step / 1e3)
 
     # ---- end to end through the C ABI with host buffers: e2e ----
@@ -468,6 +579,15 @@ def main():
     d2h = int(batch.cap * 100 + 4)
     assert int(status[0]) == 0 and int(n_sigs[0]) > 0
     assert torch.equal(out_pinned[: int(n_sigs[0])], out_pinned2[: int(n_sigs[0])])
+    # copy-only ceiling of this run: every rank re-sends its pinned PCM to its GPU, nothing else, all ranks at once
+    batch.sync()
+    barrier()
+    t_c = time.perf_counter()
+    for _ in range(max(4, args.steps // 2)):
+        batch.upload()
+    batch.sync()
+    copy_s = max_over_ranks(time.perf_counter() - t_c) / max(4, args.steps // 2)
+    barrier()
     # single-buffer latency of one isolated step (upload -> kernels -> download), for reference
     t0 = time.perf_counter()
     issue(0)
@@ -516,12 +636,55 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks, "clocks_e2e": clocks_e2e,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "isolated_step_ms": e2e_single_ms,
+                    "h2d_GBps_aggregate": world * h2d / (e2e_ms / 1e3) / 1e9,
+                    "h2d_ceiling_GBps_aggregate": world * h2d / copy_s / 1e9,
+                    "frac_of_h2d_ceiling": copy_s / (e2e_ms / 1e3),
+                    "host_placement": placement,
                     "note": "two batches in flight on two streams; each step copies its PCM from pinned host "
-                            "memory and its signatures back; timed on the host clock around all K steps"},
+                            "memory and its signatures back; timed on the host clock around all K steps; "
+                            "h2d_ceiling = the same ranks sending the same pinned buffers with no kernels, same run"},
             "gpu_launches": int(launches_per_run * (args.steps * 2 + max(args.warmup, 3) + 4)),
-            "roofline": roofline, "signatures_per_track": int(n_sigs[0])}
+            "roofline": roofline, "signatures_per_track": int(n_sigs[0]), "group_record_slots_in_use": slots_in_use}
 
     if world == 1 and rank == 0:
+        # worst-case content for the group records: the same pass on a saw-tooth crescendo track
+        try:
+            wpcm = make_worst_content_track(args.seconds, args.channels, seed=1)
+            wpin = torch.from_numpy(wpcm).pin_memory()
+            batch.upload([(wpin.data_ptr(), n_frames, args.channels)])
+            batch.sync()
+            for _ in range(3):
+                batch.run()
+            batch.sync()
+            batch.set_timing(True)
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                w0.record(stream)
+                for _ in range(args.steps):
+                    batch.run()
+                w1.record(stream)
+            torch.cuda.synchronize()
+            wms = w0.elapsed_time(w1) / args.steps
+            wstage, _ = batch.get_timing()
+            batch.set_timing(False)
+            _, wn, wst = batch.download(out_ptr=out_pinned.data_ptr())
+            line["value_worst_content"] = {"value": hours_per_step / (wms / 1e3), "unit": UNIT, "ms_per_step": wms,
+                                           "stage_ms": wstage, "slowdown_vs_value": wms / ms_per_step,
+                                           "group_record_slots_in_use": batch.record_slots_in_use(0),
+                                           "signatures": int(wn[0]),
+                                           "content": "frequency-modulated tone + noise under a 14 s saw-tooth crescendo: nearly "
+                                                      "every image has its own window maximum"}
+            del wpin
+        except Exception as exc:
+            line["value_worst_content"] = {"error": repr(exc)}
+        try:
+            line["e2e_dropin"] = dropin_section(pcm, args.seconds, local_rank)
+        except Exception as exc:
+            line["e2e_dropin"] = {"error": repr(exc)}
+        try:
+            line["live_latency"] = live_section(ctx)
+        except Exception as exc:
+            line["live_latency"] = {"error": repr(exc)}
         line["search"] = search_section(ctx)
     if args.search_c4_tracks > 0:
         # BASELINE.json configs[3] at every N: the database sharded over the N ranks, NCCL all-gathers + GPU merge,

@@ -69,6 +69,11 @@ int mnemo_batch_upload(mnemo_batch* b, const mnemo_track* tracks); /* H2D of eve
  * context's stream when `src` is pinned (mnemo_host_alloc).  The caller reads the next piece of the file into a
  * second staging buffer meanwhile and calls mnemo_batch_sync before reusing a buffer. */
 int mnemo_batch_upload_part(mnemo_batch* b, uint32_t track, uint64_t byte_offset, const void* src, uint64_t bytes);
+/* The same with a ticket: mnemo_batch_upload_wait(ticket) returns once THAT piece (and every earlier one) has left its
+ * staging buffer, so a ring of pinned buffers can be refilled by reader threads while later pieces are still in flight. */
+int mnemo_batch_upload_part_ticket(mnemo_batch* b, uint32_t track, uint64_t byte_offset, const void* src, uint64_t bytes,
+                                   uint64_t* ticket);
+int mnemo_batch_upload_wait(mnemo_batch* b, uint64_t ticket);
 /* Pinned host memory for callers that do not link the CUDA runtime themselves. */
 int mnemo_host_alloc(mnemo_ctx* ctx, void** p, uint64_t bytes);
 void mnemo_host_free(mnemo_ctx* ctx, void* p);
@@ -86,7 +91,9 @@ int mnemo_batch_download(mnemo_batch* b, uint8_t* sigs_out, uint64_t cap_signatu
  * 3 = per-image keep flags (u8[n_images]), 4 = dense signatures (u8[n_images*100]),
  * 5 = raw fingerprint bits (u8[n_images*1024], only if debug taps enabled),
  * 6 = scaled spectral images, 7 = Haar coefficients (float[n_images*4096], debug taps),
- * 8 = float32 sequential sum of squares (float[1]).  Returns bytes written or <0. */
+ * 8 = float32 sequential sum of squares (float[1]), 9 = record slot of each of an image's 16 frame groups
+ * (u8[n_images*16], k15_groups.cu: how many distinct window maxima the images around a group have).
+ * Returns bytes written or <0. */
 int64_t mnemo_batch_read(mnemo_batch* b, int what, uint32_t track, void* dst, uint64_t dst_bytes);
 int mnemo_batch_enable_taps(mnemo_batch* b, int on);
 /* Per-stage device times (CUDA events on the context's stream), averaged over the runs since timing
@@ -102,6 +109,8 @@ int mnemo_index_pcm_batch(mnemo_ctx* ctx, const mnemo_track* tracks, uint32_t n_
  * and normalised.  Returns 0 / FILE_TOO_SMALL / error; *n_sigs signatures written. */
 int mnemo_index_samples(mnemo_ctx* ctx, const float* samples, uint32_t n, uint8_t* sigs_out,
                         uint64_t cap_signatures, uint32_t* n_sigs);
+/* 1 if the live path of the last mnemo_index_samples length runs as one captured CUDA graph, 0 if call by call. */
+int mnemo_index_samples_graph(const mnemo_ctx* ctx);
 
 /* ---- search ---- */
 /* Database = signatures of all entries concatenated in entry order; entry_start has

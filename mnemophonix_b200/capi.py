@@ -78,6 +78,7 @@ def lib() -> C.CDLL:
         L.mnemo_batch_get_timing.argtypes = [vp, vp, C.POINTER(u32)]
         L.mnemo_index_pcm_batch.argtypes = [vp, C.POINTER(Track), u32, vp, u64, vp, vp]
         L.mnemo_index_samples.argtypes = [vp, vp, u32, vp, u64, C.POINTER(u32)]
+        L.mnemo_index_samples_graph.argtypes = [vp]
         L.mnemo_selftest_logf.argtypes = [vp, u32, u32]
         L.mnemo_selftest_logf.restype = C.c_int64
         L.mnemo_selftest_div.argtypes = [vp, i32, u32, u64]
@@ -195,6 +196,11 @@ class Context:
             self._check(rc, "mnemo_index_samples")
         return rc, sigs[:n.value].copy()
 
+    @property
+    def live_graph(self) -> bool:
+        """True if the last index_samples length runs as one captured CUDA graph."""
+        return bool(lib().mnemo_index_samples_graph(self.h))
+
     def batch(self, pcms) -> "Batch":
         return Batch(self, pcms)
 
@@ -209,7 +215,7 @@ def _split(sigs: np.ndarray, counts) -> list:
 
 class Batch:
     READ_DTYPES = {0: np.float32, 1: np.float32, 2: np.float32, 3: np.uint8, 4: np.uint8, 5: np.uint8,
-                   6: np.float32, 7: np.float32, 8: np.float32}
+                   6: np.float32, 7: np.float32, 8: np.float32, 9: np.uint8}
 
     def __init__(self, ctx: Context, pcms):
         self.ctx = ctx
@@ -273,12 +279,24 @@ class Batch:
         out, n, st = self.download()
         return _split(out, n), st.tolist()
 
+    def record_slots_in_use(self, track: int = 0) -> float:
+        """Mean number of group-record slots in use per 8-frame group (1 .. 16): distinct window maxima among the images
+        that contain the group (k15_groups.cu).  Image j reads slot[j][p] of group j + p."""
+        slot = self.read(9, track).reshape(-1, 16).astype(np.int64)
+        ni = slot.shape[0]
+        if ni == 0:
+            return 0.0
+        used = np.zeros(ni + 15, np.int64)
+        for p in range(16):
+            np.maximum(used[p:p + ni], slot[:, p] + 1, out=used[p:p + ni])
+        return float(used.mean())
+
     def read(self, what: int, track: int) -> np.ndarray:
         d = self.arr[track]
         n5 = int(lib().mnemo_samples_5512(d.n_frames))
         nf = int(lib().mnemo_frames(n5))
         ni = int(lib().mnemo_images(n5))
-        count = {0: n5, 1: 1, 2: nf * 32, 3: ni, 4: ni * 100, 5: ni * 1024, 6: ni * 4096, 7: ni * 4096, 8: 1}[what]
+        count = {0: n5, 1: 1, 2: nf * 32, 3: ni, 4: ni * 100, 5: ni * 1024, 6: ni * 4096, 7: ni * 4096, 8: 1, 9: ni * 16}[what]
         buf = np.empty(max(count, 1), self.READ_DTYPES[what])
         got = lib().mnemo_batch_read(self.h, what, track, buf.ctypes.data, buf.nbytes)
         if got < 0:

@@ -247,9 +247,20 @@ extern "C" int mnemo_create(int device, void* stream, mnemo_ctx** out) {
   return 0;
 }
 
+static void live_release(mnemo_ctx* ctx) {
+  mnemo_ctx::Live& lv = ctx->live;
+  if (lv.exec) cudaGraphExecDestroy(lv.exec);
+  if (lv.batch) mnemo_batch_destroy(lv.batch);
+  if (lv.pin_in) cudaFreeHost(lv.pin_in);
+  if (lv.pin_out) cudaFreeHost(lv.pin_out);
+  lv = mnemo_ctx::Live();
+}
+
 extern "C" void mnemo_destroy(mnemo_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  live_release(ctx);
+  if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_inv_perms) cudaFree(ctx->d_inv_perms);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -294,8 +305,20 @@ static cudaError_t dalloc(T** p, uint64_t count) {
   return cudaMalloc((void**)p, (count ? count : 1) * sizeof(T));
 }
 
+// hands out 256-byte aligned pieces of one allocation (base == nullptr: only adds up the sizes)
+struct Carver {
+  uint8_t* base;
+  uint64_t off;
+  template <typename T>
+  void take(T** p, uint64_t count) {
+    const uint64_t bytes = align_up((count ? count : 1) * sizeof(T), 256);
+    if (base) *p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+  }
+};
+
 static int batch_create_common(mnemo_ctx* ctx, const mnemo_track* tracks, uint32_t n_tracks, bool prenormalized,
-                               mnemo_batch** out) {
+                               mnemo_batch** out, bool share_arena = true) {
   if (!ctx || !out || (n_tracks && !tracks)) return -3;
   *out = nullptr;
   cudaSetDevice(ctx->device);
@@ -371,34 +394,62 @@ static int batch_create_common(mnemo_ctx* ctx, const mnemo_track* tracks, uint32
   do {                              \
     if (e == cudaSuccess) e = (x);  \
   } while (0)
-  TRY(dalloc(&b->d_pcm, b->pcm_off[n_tracks]));
-  TRY(dalloc(&b->d_tracks, n_tracks));
-  TRY(dalloc(&b->d_k0_prefix, n_tracks + 1));
-  TRY(dalloc(&b->d_k1_prefix, n_tracks + 1));
-  TRY(dalloc(&b->d_img_prefix, n_tracks + 1));
-  TRY(dalloc(&b->d_chunk_track, b->n_chunks));
-  TRY(dalloc(&b->d_s5512, b->n_samples));
-  if (!prenormalized) TRY(dalloc(&b->d_norm, b->n_samples));
-  TRY(dalloc(&b->d_chunk_true, b->n_chunks));
-  TRY(dalloc(&b->d_chunk_prefix, b->n_chunks));
-  TRY(dalloc(&b->d_chunk_prefix_end, b->n_chunks));
-  TRY(dalloc(&b->d_recs, b->n_chunks));
-  TRY(dalloc(&b->d_grecs, b->n_chunks));                                  // used at the first chunk of every group of 32
-  TRY(dalloc(&b->d_slice_maps, b->n_chunks * (2ull * kSumCands * 32)));   // 768 B per chunk
-  TRY(dalloc(&b->d_sumsq, n_tracks));
-  TRY(dalloc(&b->d_rms, n_tracks));
-  TRY(dalloc(&b->d_bins, b->n_frames * kBands));
-  TRY(dalloc(&b->d_group_prefix, n_tracks + 1));
-  TRY(dalloc(&b->d_gmax, b->n_groups));
-  TRY(dalloc(&b->d_imax, b->n_images));
-  TRY(dalloc(&b->d_slot, b->n_images * 16));
-  TRY(dalloc(&b->d_grec, b->n_groups * 16 * 256));   // room for 16 records per group; traffic follows the slots in use
-  TRY(dalloc(&b->d_sig_dense, b->n_images * kSigLen));
-  TRY(dalloc(&b->d_keep, b->n_images));
-  TRY(dalloc(&b->d_pos, b->n_images + 1));
-  TRY(dalloc(&b->d_block_sums, (uint64_t)n_scan_blocks + 1));
-  TRY(dalloc(&b->d_sig_out, b->n_images * kSigLen));
-  TRY(dalloc(&b->d_n_sigs, n_tracks));
+  // every buffer of the batch comes out of one arena: first pass sizes it, second pass hands out the pieces
+  auto layout = [&](Carver& c) {
+    c.take(&b->d_pcm, b->pcm_off[n_tracks]);
+    c.take(&b->d_tracks, n_tracks);
+    c.take(&b->d_k0_prefix, n_tracks + 1);
+    c.take(&b->d_k1_prefix, n_tracks + 1);
+    c.take(&b->d_img_prefix, n_tracks + 1);
+    c.take(&b->d_chunk_track, b->n_chunks);
+    c.take(&b->d_s5512, b->n_samples);
+    if (!prenormalized) c.take(&b->d_norm, b->n_samples);
+    c.take(&b->d_chunk_true, b->n_chunks);
+    c.take(&b->d_chunk_prefix, b->n_chunks);
+    c.take(&b->d_chunk_prefix_end, b->n_chunks);
+    c.take(&b->d_recs, b->n_chunks);
+    c.take(&b->d_grecs, b->n_chunks);                                  // used at the first chunk of every group of 32
+    c.take(&b->d_slice_maps, b->n_chunks * (2ull * kSumCands * 32));   // 768 B per chunk
+    c.take(&b->d_sumsq, n_tracks);
+    c.take(&b->d_rms, n_tracks);
+    c.take(&b->d_bins, b->n_frames * kBands);
+    c.take(&b->d_group_prefix, n_tracks + 1);
+    c.take(&b->d_gmax, b->n_groups);
+    c.take(&b->d_imax, b->n_images);
+    c.take(&b->d_slot, b->n_images * 16);
+    c.take(&b->d_grec, b->n_groups * 16 * 256);   // room for 16 records per group; traffic follows the slots in use
+    c.take(&b->d_sig_dense, b->n_images * kSigLen);
+    c.take(&b->d_keep, b->n_images);
+    c.take(&b->d_pos, b->n_images + 1);
+    c.take(&b->d_block_sums, (uint64_t)n_scan_blocks + 1);
+    c.take(&b->d_sig_out, b->n_images * kSigLen);
+    c.take(&b->d_n_sigs, n_tracks);
+  };
+  Carver sizing{nullptr, 0};
+  layout(sizing);
+  const uint64_t arena_bytes = sizing.off;
+  if (share_arena) {
+    std::lock_guard<std::mutex> lock(ctx->arena_mu);
+    if (!ctx->arena_busy) {
+      if (ctx->arena_bytes < arena_bytes) {
+        if (ctx->arena) cudaFree(ctx->arena);
+        ctx->arena = nullptr;
+        ctx->arena_bytes = 0;
+        e = cudaMalloc((void**)&ctx->arena, arena_bytes);
+        if (e == cudaSuccess) ctx->arena_bytes = arena_bytes;
+      }
+      if (e == cudaSuccess) {
+        ctx->arena_busy = true;
+        b->arena = ctx->arena;
+        b->arena_of_ctx = true;
+      }
+    }
+  }
+  if (e == cudaSuccess && !b->arena) e = cudaMalloc((void**)&b->arena, arena_bytes);
+  if (e == cudaSuccess) {
+    Carver carve{b->arena, 0};
+    layout(carve);
+  }
   if (e != cudaSuccess) {
     int rc = mnemo_fail(ctx, e, "mnemo_batch_create");
     mnemo_batch_destroy(b);
@@ -437,15 +488,19 @@ extern "C" void mnemo_batch_destroy(mnemo_batch* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
-  if (b->d_norm == b->d_s5512) b->d_norm = nullptr;
-  void* ptrs[] = {b->d_norm,     b->d_pcm,      b->d_tracks,  b->d_k0_prefix, b->d_k1_prefix,   b->d_img_prefix, b->d_chunk_track,
-                  b->d_s5512,    b->d_chunk_true, b->d_chunk_prefix, b->d_recs,  b->d_sumsq,      b->d_rms, b->d_grecs, b->d_slice_maps, b->d_chunk_prefix_end, b->d_group_prefix, b->d_gmax, b->d_imax, b->d_slot, b->d_grec, b->d_tap_px,
-                  b->d_bins,     b->d_sig_dense, b->d_keep,    b->d_pos,         b->d_block_sums, b->d_sig_out,
-                  b->d_n_sigs,   b->d_tap_raw, b->d_tap_img,   b->d_tap_haar};
+  if (b->arena_of_ctx) {
+    std::lock_guard<std::mutex> lock(b->ctx->arena_mu);
+    b->ctx->arena_busy = false;   // stays allocated for the next batch
+  } else if (b->arena) {
+    cudaFree(b->arena);
+  }
+  void* ptrs[] = {b->d_tap_px, b->d_tap_raw, b->d_tap_img, b->d_tap_haar};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int i = 0; i < 6; i++)
     if (b->ev[i]) cudaEventDestroy(b->ev[i]);
+  for (cudaEvent_t ev : b->up_ev)
+    if (ev) cudaEventDestroy(ev);
   delete b;
 }
 
@@ -521,6 +576,29 @@ extern "C" int mnemo_batch_upload_part(mnemo_batch* b, uint32_t track, uint64_t 
   cudaError_t e = cudaMemcpyAsync(b->d_pcm + b->pcm_off[track] + byte_offset, src, bytes, cudaMemcpyHostToDevice,
                                   b->ctx->stream);
   if (e != cudaSuccess) return mnemo_fail(b->ctx, e, "mnemo_batch_upload_part");
+  return 0;
+}
+
+extern "C" int mnemo_batch_upload_part_ticket(mnemo_batch* b, uint32_t track, uint64_t byte_offset, const void* src,
+                                              uint64_t bytes, uint64_t* ticket) {
+  if (!ticket) return -3;
+  const int rc = mnemo_batch_upload_part(b, track, byte_offset, src, bytes);
+  if (rc != 0) return rc;
+  cudaEvent_t& ev = b->up_ev[b->up_seq % mnemo_batch::kUploadEvents];
+  cudaError_t e = cudaSuccess;
+  if (!ev) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventRecord(ev, b->ctx->stream);
+  if (e != cudaSuccess) return mnemo_fail(b->ctx, e, "mnemo_batch_upload_part_ticket");
+  *ticket = b->up_seq++;
+  return 0;
+}
+
+extern "C" int mnemo_batch_upload_wait(mnemo_batch* b, uint64_t ticket) {
+  if (!b || ticket >= b->up_seq) return -3;
+  // a reused event stands for a LATER copy on the same stream: waiting for it covers this ticket as well
+  cudaSetDevice(b->ctx->device);
+  cudaError_t e = cudaEventSynchronize(b->up_ev[ticket % mnemo_batch::kUploadEvents]);
+  if (e != cudaSuccess) return mnemo_fail(b->ctx, e, "mnemo_batch_upload_wait");
   return 0;
 }
 
@@ -667,6 +745,7 @@ extern "C" int64_t mnemo_batch_read(mnemo_batch* b, int what, uint32_t track, vo
     case 6: src = b->d_tap_img ? b->d_tap_img + d.img_off * kImgElems : nullptr; bytes = 4ull * d.n_images * kImgElems; break;
     case 7: src = b->d_tap_haar ? b->d_tap_haar + d.img_off * kImgElems : nullptr; bytes = 4ull * d.n_images * kImgElems; break;
     case 8: src = b->d_sumsq + track; bytes = 4; break;
+    case 9: src = b->d_slot + d.img_off * 16; bytes = (uint64_t)d.n_images * 16; break;
     default: return -3;
   }
   if (!src && bytes) return -3;
@@ -689,27 +768,91 @@ extern "C" int mnemo_index_pcm_batch(mnemo_ctx* ctx, const mnemo_track* tracks, 
   return rc;
 }
 
+// generate_fingerprint_from_samples (fingerprinting.c:81-109).  Its caller is a live loop that fingerprints a window of
+// the same length again and again (ears/main.m:62-93), so the batch of the last length stays alive in the context
+// together with pinned in/out buffers and ONE captured CUDA graph holding the copy in, the ~15 kernels and the copy
+// out: a call is a memcpy into pinned memory, one graph launch, one synchronisation.
 extern "C" int mnemo_index_samples(mnemo_ctx* ctx, const float* samples, uint32_t n, uint8_t* sigs_out, uint64_t cap,
                                    uint32_t* n_sigs) {
   if (n_sigs) *n_sigs = 0;
+  if (!ctx || !samples) return -3;
   if (n < (uint32_t)kFrame || mnemo_frames(n) == 0) return -5;   // fingerprinting.c:82, spectralimages.c:128
-  mnemo_track tr;
-  tr.pcm = samples;
-  tr.n_frames = n;
-  tr.channels = 1;
-  tr.reserved = 0;
-  mnemo_batch* b = nullptr;
-  int rc = batch_create_common(ctx, &tr, 1, true, &b);
-  if (rc != 0) return rc;
-  rc = mnemo_batch_upload(b, &tr);
-  if (rc == 0) rc = mnemo_batch_run(b);
-  int32_t status = 0;
+  std::lock_guard<std::mutex> lock(ctx->live_mu);
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  mnemo_ctx::Live& lv = ctx->live;
+  cudaError_t e = cudaSuccess;
+  if (lv.n != n || !lv.batch) {
+    live_release(ctx);
+    mnemo_track tr;
+    tr.pcm = nullptr;
+    tr.n_frames = n;
+    tr.channels = 1;
+    tr.reserved = 0;
+    int rc = batch_create_common(ctx, &tr, 1, true, &lv.batch, /*share_arena=*/false);
+    if (rc != 0) return rc;
+    mnemo_batch* b = lv.batch;
+    const uint64_t out_bytes = b->n_images * kSigLen + 16;
+    e = cudaHostAlloc((void**)&lv.pin_in, (uint64_t)n * sizeof(float), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&lv.pin_out, out_bytes, cudaHostAllocDefault);
+    cudaGraph_t graph = nullptr;
+    if (e == cudaSuccess) e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+      tr.pcm = lv.pin_in;
+      rc = mnemo_batch_upload(b, &tr);
+      if (rc == 0) rc = mnemo_batch_run(b);
+      cudaError_t e2 = cudaMemcpyAsync(lv.pin_out, b->d_sig_out, b->n_images * kSigLen, cudaMemcpyDeviceToHost, st);
+      if (e2 == cudaSuccess)
+        e2 = cudaMemcpyAsync(lv.pin_out + b->n_images * kSigLen, b->d_n_sigs, 4, cudaMemcpyDeviceToHost, st);
+      e = cudaStreamEndCapture(st, &graph);
+      if (e == cudaSuccess && (rc != 0 || e2 != cudaSuccess)) e = e2 != cudaSuccess ? e2 : cudaErrorUnknown;
+    }
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&lv.exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (!lv.pin_in || !lv.pin_out) {
+      live_release(ctx);
+      return mnemo_fail(ctx, e, "mnemo_index_samples (pinned buffers)");
+    }
+    if (e != cudaSuccess) {   // not capturable here: the same operations are issued one by one on every call
+      cudaGetLastError();
+      lv.exec = nullptr;
+      e = cudaSuccess;
+    }
+    lv.n = n;
+  }
+  mnemo_batch* b = lv.batch;
+  memcpy(lv.pin_in, samples, (uint64_t)n * sizeof(float));
+  if (lv.exec) {
+    e = cudaGraphLaunch(lv.exec, st);
+  } else {
+    mnemo_track tr;
+    tr.pcm = lv.pin_in;
+    tr.n_frames = n;
+    tr.channels = 1;
+    tr.reserved = 0;
+    int rc = mnemo_batch_upload(b, &tr);
+    if (rc == 0) rc = mnemo_batch_run(b);
+    if (rc != 0) return rc;
+    e = cudaMemcpyAsync(lv.pin_out, b->d_sig_out, b->n_images * kSigLen, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(lv.pin_out + b->n_images * kSigLen, b->d_n_sigs, 4, cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    live_release(ctx);
+    return mnemo_fail(ctx, e, "mnemo_index_samples");
+  }
   uint32_t cnt = 0;
-  if (rc == 0) rc = mnemo_batch_download(b, sigs_out, cap, &cnt, &status);
-  mnemo_batch_destroy(b);
-  if (rc == 0 && n_sigs) *n_sigs = cnt;
-  return rc == 0 ? status : rc;
+  memcpy(&cnt, lv.pin_out + b->n_images * kSigLen, 4);
+  if (cnt > cap) {
+    ctx->err = "mnemo_index_samples: output capacity too small";
+    return -1;
+  }
+  if (cnt && sigs_out) memcpy(sigs_out, lv.pin_out, (uint64_t)cnt * kSigLen);
+  if (n_sigs) *n_sigs = cnt;
+  return 0;
 }
+
+extern "C" int mnemo_index_samples_graph(const mnemo_ctx* ctx) { return ctx && ctx->live.exec ? 1 : 0; }
 
 // ------------------------------------------------------------------ self tests ----
 

@@ -1,5 +1,6 @@
 // api_internal.h — private definitions behind the opaque handles of include/mnemo_cuda.h.
 #pragma once
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -15,6 +16,23 @@ struct mnemo_ctx {
   uint16_t* d_inv_perms = nullptr;  // [8192][100]: position of bit b in permutation p (255 = not among the first 255)
   uint32_t logf_probes = 0, logf_matched = 0;
   std::string err;
+  // Live path (mnemo_index_samples, the ears loop's once-a-second call): the batch of the last sample count is kept,
+  // with pinned in/out buffers and the whole call (copy in, kernels, copy out) captured as one CUDA graph.
+  struct Live {
+    struct mnemo_batch* batch = nullptr;
+    uint32_t n = 0;
+    float* pin_in = nullptr;
+    uint8_t* pin_out = nullptr;     // signatures, then the count
+    cudaGraphExec_t exec = nullptr;
+  } live;
+  std::mutex live_mu;
+  // Device arena handed from batch to batch: a batch takes all its buffers from ONE allocation, and the context
+  // keeps the last one for the next batch (a process that indexes file after file pays cudaMalloc / cudaFree —
+  // milliseconds for gigabytes — once, not per file).  A second batch alive at the same time gets its own.
+  uint8_t* arena = nullptr;
+  uint64_t arena_bytes = 0;
+  bool arena_busy = false;
+  std::mutex arena_mu;
 };
 
 struct mnemo_batch {
@@ -34,7 +52,13 @@ struct mnemo_batch {
   double stage_ms[5] = {0, 0, 0, 0, 0};
   uint32_t timed_runs = 0;
   bool ev_pending = false;
-  // device buffers
+  // tickets of mnemo_batch_upload_part_ticket: an event per asynchronous piece, reused round-robin
+  static constexpr int kUploadEvents = 64;
+  cudaEvent_t up_ev[kUploadEvents] = {};
+  uint64_t up_seq = 0;
+  // device buffers: carved out of `arena` (one allocation; the context's when arena_of_ctx)
+  uint8_t* arena = nullptr;
+  bool arena_of_ctx = false;
   uint8_t* d_pcm = nullptr;
   mnemo::TrackDev* d_tracks = nullptr;
   uint32_t *d_k0_prefix = nullptr, *d_k1_prefix = nullptr, *d_chunk_track = nullptr;

@@ -9,7 +9,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/types.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "fingerprinting.h"
 #include "host_internal.h"
@@ -26,6 +28,16 @@ static int trace_on(void) {
     return on;
 }
 #define TRACE(what, t0) do { if (trace_on()) fprintf(stderr, "[mnemo] %-28s %8.1f ms\n", what, now_ms() - (t0)); } while (0)
+
+/* MNEMO_READERS=n caps the reader threads of the streaming ingest (default: up to 8) */
+static int const_env_readers(void) {
+    static int n = -1;
+    if (n < 0) {
+        const char* e = getenv("MNEMO_READERS");
+        n = e ? atoi(e) : 0;
+    }
+    return n;
+}
 
 static pthread_once_t g_once = PTHREAD_ONCE_INIT;
 static mnemo_ctx* g_ctx = NULL;
@@ -72,14 +84,60 @@ static struct signatures* new_signatures(uint64_t capacity) {
     return s;
 }
 
-/* Pinned staging for the streaming ingest: two buffers per process, reused for every file. */
-#define STAGE_BYTES (32u << 20)
-static void* g_stage[2] = {NULL, NULL};
-static pthread_mutex_t g_stage_lock = PTHREAD_MUTEX_INITIALIZER;   /* one file at a time through the staging pair */
+/* Pinned staging for the streaming ingest: a ring of buffers per process, reused for every file. */
+#define PIECE_BYTES (4u << 20)
+#define RING 32                      /* 128 MB of pinned memory */
+#define MAX_READERS 16
+static void* g_ring[RING];
+static pthread_mutex_t g_stage_lock = PTHREAD_MUTEX_INITIALIZER;   /* one file at a time through the ring */
 
-/* The data chunk goes to the GPU in 32 MB pieces: while piece k is on its way (asynchronous copy from a pinned
- * buffer), piece k+1 is read from the file into the other buffer.  This replaces read_samples' loop of one fread
- * per sample block (wav.c:358-375), and the one big malloc + fread + pageable copy of the whole-file path. */
+struct ingest {
+    int fd;
+    off_t data_off;
+    uint64_t total;
+    uint32_t n_pieces;
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    uint32_t next_piece;    /* next piece a reader may claim */
+    uint32_t free_upto;     /* pieces below this index have a free ring slot (= pieces uploaded + RING) */
+    uint8_t* state;         /* per piece: 0 pending, 1 in its ring slot, 2 could not be read */
+    int stop;
+};
+
+static void* ingest_reader(void* arg) {
+    struct ingest* g = (struct ingest*)arg;
+    for (;;) {
+        pthread_mutex_lock(&g->mu);
+        const uint32_t i = g->next_piece;
+        if (i >= g->n_pieces || g->stop) {
+            pthread_mutex_unlock(&g->mu);
+            return NULL;
+        }
+        g->next_piece = i + 1;
+        while (i >= g->free_upto && !g->stop) pthread_cond_wait(&g->cv, &g->mu);
+        const int stop = g->stop;
+        pthread_mutex_unlock(&g->mu);
+        if (stop) return NULL;
+        const uint64_t off = (uint64_t)i * PIECE_BYTES;
+        const size_t want = (size_t)((g->total - off < PIECE_BYTES) ? (g->total - off) : PIECE_BYTES);
+        char* dst = (char*)g_ring[i % RING];
+        size_t got = 0;
+        while (got < want) {
+            const ssize_t r = pread(g->fd, dst + got, want - got, g->data_off + (off_t)(off + got));
+            if (r <= 0) break;   /* truncated data chunk or I/O error */
+            got += (size_t)r;
+        }
+        pthread_mutex_lock(&g->mu);
+        g->state[i] = got == want ? 1 : 2;
+        pthread_cond_broadcast(&g->cv);
+        pthread_mutex_unlock(&g->mu);
+    }
+}
+
+/* The data chunk goes to the GPU in 8 MB pieces through a ring of pinned buffers: up to eight reader threads pread
+ * the pieces (the page cache delivers ~6 GB/s per thread, PCIe takes 55), the calling thread hands each piece to an
+ * asynchronous copy as soon as it is complete and releases a ring slot once its copy has left it.  This replaces
+ * read_samples' loop of one fread per sample block (wav.c:358-375). */
 static int ingest_streaming(mnemo_ctx* ctx, FILE* f, const struct wav_data* w, struct signatures* s, uint32_t n_images,
                             uint32_t* n_out) {
     mnemo_track tr;
@@ -92,26 +150,72 @@ static int ingest_streaming(mnemo_ctx* ctx, FILE* f, const struct wav_data* w, s
     int rc = mnemo_batch_create(ctx, &tr, 1, &b);
     TRACE("batch create (device buffers)", tc);
     if (rc != 0) return rc;
+    struct ingest g;
+    memset(&g, 0, sizeof g);
+    g.fd = fileno(f);
+    g.data_off = ftello(f);
+    g.total = w->n_frames * (uint64_t)w->channels * 2u;
+    g.n_pieces = (uint32_t)((g.total + PIECE_BYTES - 1) / PIECE_BYTES);
+    g.free_upto = RING;
+    g.state = (uint8_t*)calloc(g.n_pieces ? g.n_pieces : 1, 1);
+    uint64_t* ticket = (uint64_t*)malloc((g.n_pieces ? g.n_pieces : 1) * sizeof(uint64_t));
+    if (!g.state || !ticket || g.data_off < 0) {
+        free(g.state);
+        free(ticket);
+        mnemo_batch_destroy(b);
+        return g.data_off < 0 ? CANNOT_READ_FILE : MEMORY_ERROR;
+    }
+    pthread_mutex_init(&g.mu, NULL);
+    pthread_cond_init(&g.cv, NULL);
     pthread_mutex_lock(&g_stage_lock);
-    for (int i = 0; i < 2 && rc == 0; i++)
-        if (!g_stage[i]) rc = mnemo_host_alloc(ctx, &g_stage[i], STAGE_BYTES);
-    const uint64_t total = w->n_frames * (uint64_t)w->channels * 2u;
-    uint64_t off = 0;
-    int cur = 0;
+    tc = now_ms();
+    for (int i = 0; i < RING && rc == 0; i++)
+        if (!g_ring[i]) rc = mnemo_host_alloc(ctx, &g_ring[i], PIECE_BYTES);
+    TRACE("pinned ring", tc);
     double t0 = now_ms();
-    while (rc == 0 && off < total) {
-        const size_t want = (size_t)((total - off < STAGE_BYTES) ? (total - off) : STAGE_BYTES);
-        if (fread(g_stage[cur], 1, want, f) != want) {   /* truncated data chunk (read_samples: DECODING_ERROR) */
+    pthread_t th[MAX_READERS];
+    int n_readers = 0;
+    if (rc == 0) {
+        long cores = sysconf(_SC_NPROCESSORS_ONLN);
+        int want = (int)(g.n_pieces < MAX_READERS ? g.n_pieces : MAX_READERS);
+        if (cores > 0 && want > cores) want = (int)cores;
+        if (const_env_readers() > 0 && want > const_env_readers()) want = const_env_readers();
+        for (; n_readers < want; n_readers++)
+            if (pthread_create(&th[n_readers], NULL, ingest_reader, &g) != 0) break;
+        if (n_readers == 0 && g.n_pieces) rc = MEMORY_ERROR;
+    }
+    for (uint32_t i = 0; rc == 0 && i < g.n_pieces; i++) {
+        pthread_mutex_lock(&g.mu);
+        while (g.state[i] == 0) pthread_cond_wait(&g.cv, &g.mu);
+        const int st = g.state[i];
+        pthread_mutex_unlock(&g.mu);
+        if (st != 1) {   /* read_samples: DECODING_ERROR on a short data chunk (wav.c:381-386) */
             rc = DECODING_ERROR;
             break;
         }
-        rc = mnemo_batch_sync(b);                        /* the copy that used the other buffer is done */
-        if (rc == 0) rc = mnemo_batch_upload_part(b, 0, off, g_stage[cur], want);
-        off += want;
-        cur ^= 1;
+        const uint64_t off = (uint64_t)i * PIECE_BYTES;
+        const uint64_t want = (g.total - off < PIECE_BYTES) ? (g.total - off) : PIECE_BYTES;
+        rc = mnemo_batch_upload_part_ticket(b, 0, off, g_ring[i % RING], want, &ticket[i]);
+        if (rc == 0 && i >= RING / 2) {   /* half of the ring in flight, half being refilled */
+            rc = mnemo_batch_upload_wait(b, ticket[i - RING / 2]);
+            pthread_mutex_lock(&g.mu);
+            g.free_upto = i - RING / 2 + 1 + RING;
+            pthread_cond_broadcast(&g.cv);
+            pthread_mutex_unlock(&g.mu);
+        }
     }
+    pthread_mutex_lock(&g.mu);
+    g.stop = 1;
+    pthread_cond_broadcast(&g.cv);
+    pthread_mutex_unlock(&g.mu);
+    for (int i = 0; i < n_readers; i++) pthread_join(th[i], NULL);
     if (rc == 0) rc = mnemo_batch_sync(b);
+    else mnemo_batch_sync(b);   /* nothing may still read the ring when the next file takes it */
     pthread_mutex_unlock(&g_stage_lock);
+    pthread_cond_destroy(&g.cv);
+    pthread_mutex_destroy(&g.mu);
+    free(g.state);
+    free(ticket);
     TRACE("read + upload (streamed)", t0);
     t0 = now_ms();
     int32_t status = 0;

@@ -3,7 +3,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <signal.h>
+#include <sys/socket.h>
 #include <sys/time.h>
+#include <sys/un.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
@@ -133,27 +136,121 @@ static int fingerprint_input(const char* input, struct signatures** fingerprint,
 
 const char* mnemo_host_last_error(void);
 
-static int report(const struct index* db, int best) {
+static int report_to(FILE* out, const struct index* db, int best) {
     if (best < 0 && best != NO_MATCH_FOUND) {
         /* not a miss: the search itself failed (the reference can only run out of memory here) */
         fprintf(stderr, "Search failed (error %d): %s\n", best, mnemo_host_last_error());
+        if (out != stdout) fprintf(out, "\nSearch failed (error %d)\n\n", best);
         return 2;
     }
     if (best < 0) {
-        printf("\nNo match found\n\n");
+        fprintf(out, "\nNo match found\n\n");
         return 1;
     }
-    printf("\nFound match: '%s'\n", db->entries[best]->filename);
-    if (db->entries[best]->artist[0]) printf("Artist: %s\n", db->entries[best]->artist);
-    if (db->entries[best]->track_title[0]) printf("Track title: %s\n", db->entries[best]->track_title);
-    if (db->entries[best]->album_title[0]) printf("Album title: %s\n", db->entries[best]->album_title);
-    printf("\n");
+    fprintf(out, "\nFound match: '%s'\n", db->entries[best]->filename);
+    if (db->entries[best]->artist[0]) fprintf(out, "Artist: %s\n", db->entries[best]->artist);
+    if (db->entries[best]->track_title[0]) fprintf(out, "Track title: %s\n", db->entries[best]->track_title);
+    if (db->entries[best]->album_title[0]) fprintf(out, "Album title: %s\n", db->entries[best]->album_title);
+    fprintf(out, "\n");
+    return 0;
+}
+
+static int report(const struct index* db, int best) { return report_to(stdout, db, best); }
+
+/* Extension: `mnemophonix serve <index> [socket]` — what the reference's live companion does (ears/main.m:132-139:
+ * read_index and create_hash_tables once, then search again and again), as a resident process: the database and its
+ * hash tables stay on the GPU and every request pays for one fingerprint and one search only.  Requests are input
+ * paths, one per line, on stdin (answers on stdout) or, with a socket path, from clients of a UNIX stream socket
+ * (answers on the connection); each answer is the block `search` prints, headed by `Searching '<path>'...`. */
+/* Returns 1 if the stream asked the server to end (`shutdown`), 0 at its end or on `quit`. */
+static int serve_stream(FILE* in, FILE* out, struct index* db, struct lsh* lsh) {
+    char line[4096];
+    while (fgets(line, sizeof line, in)) {
+        size_t len = strlen(line);
+        while (len && (line[len - 1] == '\n' || line[len - 1] == '\r')) line[--len] = '\0';
+        if (!len) continue;
+        if (!strcmp(line, "quit")) break;
+        if (!strcmp(line, "shutdown")) return 1;
+        struct signatures* fp = NULL;
+        fprintf(out, "Searching '%s'...\n", line);
+        if (fingerprint_input(line, &fp, NULL, NULL, NULL)) {
+            fprintf(out, "\nCannot fingerprint '%s'\n\n", line);
+            fflush(out);
+            continue;
+        }
+        long t0 = now_ms();
+        int best = search(fp, db, lsh, 0);
+        fprintf(out, "(Search took %ld ms)\n", now_ms() - t0);
+        report_to(out, db, best);
+        fflush(out);
+        free_signatures(fp);
+    }
+    return 0;
+}
+
+static int serve(const char* index, const char* sock_path) {
+    struct index* db = NULL;
+    printf("Loading database %s...\n", index);
+    long t0 = now_ms();
+    int res = read_index(index, &db);
+    if (res != SUCCESS) {
+        if (res == CANNOT_READ_FILE) fprintf(stderr, "Cannot read file '%s'\n", index);
+        else if (res == MEMORY_ERROR) fprintf(stderr, "Memory allocation error\n");
+        else fprintf(stderr, "Cannot decode file '%s'\n", index);
+        return 1;
+    }
+    long t1 = now_ms();
+    printf("(raw database loading took %ld ms)\n", t1 - t0);
+    struct lsh* lsh = create_hash_tables(db);
+    printf("(lsh index building took %ld ms)\n", now_ms() - t1);
+    if (!lsh) {
+        fprintf(stderr, "Memory allocation error (%s)\n", mnemo_host_last_error());
+        return 1;
+    }
+    if (!sock_path) {
+        printf("Ready\n");
+        fflush(stdout);
+        serve_stream(stdin, stdout, db, lsh);
+    } else {
+        struct sockaddr_un addr;
+        memset(&addr, 0, sizeof addr);
+        addr.sun_family = AF_UNIX;
+        if (strlen(sock_path) >= sizeof addr.sun_path) {
+            fprintf(stderr, "Socket path too long\n");
+            return 1;
+        }
+        strcpy(addr.sun_path, sock_path);
+        unlink(sock_path);
+        int srv = socket(AF_UNIX, SOCK_STREAM, 0);
+        if (srv < 0 || bind(srv, (struct sockaddr*)&addr, sizeof addr) != 0 || listen(srv, 16) != 0) {
+            fprintf(stderr, "Cannot listen on '%s'\n", sock_path);
+            return 1;
+        }
+        signal(SIGPIPE, SIG_IGN);
+        printf("Ready on %s\n", sock_path);
+        fflush(stdout);
+        for (;;) {   /* one client at a time: the GPU is the shared resource anyway; the line `shutdown` ends the server */
+            int c = accept(srv, NULL, NULL);
+            if (c < 0) break;
+            FILE* in = fdopen(c, "r");
+            FILE* out = fdopen(dup(c), "w");
+            const int stop = (in && out) ? serve_stream(in, out, db, lsh) : 0;
+            if (in) fclose(in);
+            if (out) fclose(out);
+            if (stop) break;
+        }
+        close(srv);
+        unlink(sock_path);
+    }
+    free_hash_tables(lsh);
+    free_index(db);
     return 0;
 }
 
 int main(int argc, char* argv[]) {
     /* `search` takes <input> <index> as upstream; with more arguments (an extension) every argument but the last
      * is an input and the last one the index: the database is loaded and its tables are built once. */
+    if (argc >= 3 && !strcmp(argv[1], "serve")) return serve(argv[2], argc > 3 ? argv[3] : NULL);
     if (argc < 2 || (strcmp(argv[1], "index") && strcmp(argv[1], "search")) || argc < 3 ||
         (!strcmp(argv[1], "search") && argc < 4)) {
         usage(argv[0]);

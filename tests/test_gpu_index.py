@@ -196,6 +196,21 @@ def test_window_maximum_changes_every_image(ctx, oracle, direction):
     assert bits_equal(got2[0], sigs)
 
 
+def test_live_path_reuses_its_graph_and_follows_length_changes(ctx, oracle):
+    """mnemo_index_samples keeps the batch of the last length with one captured CUDA graph (the ears loop calls it once a
+    second with a window of constant length): repeated calls, new content, and a change of length all equal the oracle."""
+    rng = np.random.RandomState(12)
+    for n in (27562, 27562, 27562, 55125, 10176, 27562):
+        s = np.clip(rng.standard_normal(n) * 0.3, -1, 1).astype(np.float32)
+        rc, got = ctx.index_samples(s)
+        rc_o, sigs = oracle.fingerprint_samples(s)
+        assert rc == rc_o == 0 and bits_equal(got, sigs)
+        assert ctx.live_graph
+    assert ctx.index_samples(np.zeros(10175, np.float32))[0] == -5      # FILE_TOO_SMALL leaves the cached batch alone
+    rc, got = ctx.index_samples(s)
+    assert rc == 0 and bits_equal(got, sigs)
+
+
 def test_from_samples_entry_point(ctx, oracle):
     # generate_fingerprint_from_samples (fingerprinting.c:81-109): no resample, no normalisation
     rng = np.random.RandomState(9)

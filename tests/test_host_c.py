@@ -353,6 +353,77 @@ def test_cli_index_and_search_round_trip(host, ref):
     host.free_index(mine)
 
 
+@pytest.mark.gpu
+def test_resident_search_server(oracle):
+    """`mnemophonix serve <index> [socket]` (extension; the ears loop of the reference as a process: database and hash
+    tables built once and kept on the GPU, one fingerprint + search per request): requests on stdin, and from two
+    consecutive clients of a UNIX socket; every answer block equals what `mnemophonix search` prints for that input."""
+    import socket
+    import time
+    d = tempfile.mkdtemp()
+    names, entries = [], []
+    for i in range(4):
+        pcm = synth.synth_track(820 + i, 16.0, 1 + i % 2)
+        path = os.path.join(d, f"s{i}.wav")
+        synth.write_wav(path, pcm, {"IART": f"artist {i}"})
+        names.append(path)
+        entries.append(oracle.fingerprint_pcm(pcm)[1])
+    dbpath = os.path.join(d, "db")
+    open(dbpath, "w").write(db_text(entries, names))
+    clips = []
+    for i in (2, 0):
+        c = os.path.join(d, f"clip{i}.wav")
+        synth.write_wav(c, synth.synth_track(820 + i, 16.0, 1 + i % 2)[4 * 44100 + 55: 9 * 44100 + 55])
+        clips.append(c)
+    noise = os.path.join(d, "noise.wav")
+    synth.write_wav(noise, (np.random.RandomState(1).standard_normal((44100 * 5, 1)) * 3000).astype(np.int16))
+
+    def block_of(path):       # what the one-shot CLI prints after its timing lines
+        r = subprocess.run([CLI, "search", path, dbpath], capture_output=True, text=True)
+        return r.stdout[r.stdout.index("(Search took"):].split("\n", 1)[1]
+
+    want = {p: block_of(p) for p in clips + [noise]}
+    assert f"Found match: '{names[2]}'" in want[clips[0]] and "No match found" in want[noise]
+    r = subprocess.run([CLI, "serve", dbpath], input="\n".join([clips[0], noise, "/nonexistent.wav", clips[1]]) + "\n",
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.count("Loading database") == 1 and "Ready" in r.stdout
+    parts = r.stdout.split("Searching '")[1:]
+    assert [p.split("'...")[0] for p in parts] == [clips[0], noise, "/nonexistent.wav", clips[1]]
+    for p, path in zip(parts, [clips[0], noise, None, clips[1]]):
+        if path is None:
+            assert "Cannot fingerprint" in p
+        else:
+            assert p.split("\n", 2)[2] == want[path], (p, want[path])
+    sock = os.path.join(d, "mnemo.sock")
+    srv = subprocess.Popen([CLI, "serve", dbpath, sock], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    try:
+        for _ in range(600):
+            if os.path.exists(sock):
+                break
+            time.sleep(0.1)
+        for path in (clips[1], noise):                      # two clients, one after the other
+            c = socket.socket(socket.AF_UNIX)
+            c.connect(sock)
+            c.sendall((path + "\nquit\n").encode())
+            data = b""
+            while True:
+                chunk = c.recv(65536)
+                if not chunk:
+                    break
+                data += chunk
+            c.close()
+            text = data.decode()
+            assert text.startswith(f"Searching '{path}'...") and text.split("\n", 2)[2] == want[path]
+        c = socket.socket(socket.AF_UNIX)
+        c.connect(sock)
+        c.sendall(b"shutdown\n")
+        c.close()
+        assert srv.wait(timeout=60) == 0
+    finally:
+        if srv.poll() is None:
+            srv.kill()
+
+
 _VERBOSE_SCRIPT = """
 import sys, ctypes as C
 sys.path.insert(0, %r)
