@@ -100,7 +100,7 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
   TRY(dalloc(&db->d_entry_start, (uint64_t)n_entries + 1));
   TRY(dalloc(&db->d_sig_entry, db->n_sigs));
   TRY(dalloc(&db->d_start, n_slots + 1));
-  TRY(dalloc(&db->d_ids, db->n_sigs * kTables));
+  TRY(dalloc(&db->d_ids, db->n_sigs * kTables + 4));   // + 4: the probe kernel stages whole 16-byte units
   TRY(dalloc(&d_counts, n_slots));
   TRY(dalloc(&d_cursor, n_slots));
   TRY(dalloc(&d_block_sums, (uint64_t)lsh_scan_blocks(n_slots) + 1));

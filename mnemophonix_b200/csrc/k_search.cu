@@ -304,7 +304,8 @@ constexpr uint32_t kBitmapMaxWords = 8192;    // 32 KB: 64 KB of shared memory p
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kPassCap = 8192;          // candidates per id-space partition (>= 32 bitmap bits each)
 constexpr uint32_t kRangeBits = kBitmapMaxWords * 32;   // ids per pass in range mode: one bitmap bit per id, exact
-constexpr uint32_t kMaxRangePasses = 32;                // range mode serves shards of up to 8.4 M signatures
+constexpr uint32_t kMaxRangePasses = 16;                // id ranges whose tables are held at a time (4.2 M signatures)
+constexpr uint32_t kStageCap = kSetCap + kDupCap;       // ids of one id range staged in shared memory (the flush's set + uniq areas)
 
 size_t search_smem_bytes() { return sizeof(uint32_t) * (kBitmapMaxWords + kDupCap + kSetCap + kDupCap); }
 
@@ -360,6 +361,7 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
   __shared__ Probe pr;
   __shared__ uint32_t s_bound[kTables][kMaxRangePasses + 1];
   __shared__ uint32_t s_pref[kMaxRangePasses][kTables + 1];   // range mode: prefix of the piece lengths of every pass
+  __shared__ uint32_t s_so[kMaxRangePasses][kTables + 1];     // the same for the pieces padded to 16-byte units (stage offsets)
   __shared__ uint32_t s_ndup, s_nuniq, s_gmax;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -485,12 +487,17 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
     }
     __syncthreads();
     for (uint32_t j = tid; j < n_pass; j += kSearchThreads) {
-      uint32_t c = 0;
+      uint32_t c = 0, cs = 0;
       for (int k = 0; k < kTables; ++k) {
         s_pref[j][k] = c;
-        c += s_bound[k][j + 1] - s_bound[k][j];
+        s_so[j][k] = cs;
+        const uint32_t n = s_bound[k][j + 1] - s_bound[k][j];
+        c += n;
+        // staged form: the piece's source is aligned down to 16 bytes, its length rounded up to whole 16-byte units
+        if (n) cs += ((((pr.begin[k] + s_bound[k][j]) & 3u) + n + 3u) >> 2) << 2;
       }
       s_pref[j][kTables] = c;
+      s_so[j][kTables] = cs;
     }
     __syncthreads();
 
@@ -535,7 +542,58 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
       if (Lp < 2) continue;   // nothing can repeat in this id range; no barrier: the tables are read-only by now
       if (listed && listed + Lp / 4 > kDupCap) flush();
       const uint32_t id_base = (c0 + pass) * range_ids;
-      {
+      auto visit = [&](uint32_t g) {
+        const uint32_t h = g - id_base;
+        const uint32_t bit = 1u << (h & 31u);
+        if (atomicOr(&bitmap[h >> 5], bit) & bit) {
+          const uint32_t pos = atomicAdd(&s_ndup, 1u);
+          if (pos < kDupCap) dup[pos] = g;
+        }
+      };
+      const uint32_t staged = s_so[pass][kTables];
+      if (staged <= kStageCap) {
+        // The ids of this range go to shared memory first: every warp copies the pieces of its lists with 16-byte
+        // asynchronous copies (all of the range in flight at once, no registers held).  A piece starts at any word,
+        // so its source is aligned down — up to 3 ids of the neighbouring bucket in front, up to 3 behind — and
+        // those strangers are blanked once the copy has landed.  The marking loop then reads a flat array: no
+        // candidate -> (list, offset) walk, no global load in the loop.
+        uint32_t* const stage = set;   // set + uniq are idle between flushes
+        const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+        for (int k = warp; k < kTables; k += kSearchThreads / 32) {
+          const uint32_t b = s_bound[k][pass], n = s_bound[k][pass + 1] - b;
+          if (!n) continue;
+          const uint32_t first = pr.begin[k] + b, units = ((first & 3u) + n + 3u) >> 2;
+          const uint32_t dst = stage_s + (s_so[pass][k] << 2);
+          const uint32_t* src = p.ids + (first & ~3u);
+          for (uint32_t u = lane; u < units; u += 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (u << 4)), "l"(src + (u << 2)) : "memory");
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        for (int k = warp; k < kTables; k += kSearchThreads / 32) {
+          const uint32_t b = s_bound[k][pass], n = s_bound[k][pass + 1] - b;
+          if (!n) continue;
+          const uint32_t lead = (pr.begin[k] + b) & 3u, words = ((lead + n + 3u) >> 2) << 2;
+          uint32_t* dst = stage + s_so[pass][k];
+          if ((uint32_t)lane < lead) dst[lane] = kEmpty;
+          if ((uint32_t)lane < words - lead - n) dst[lead + n + lane] = kEmpty;
+        }
+        __syncthreads();   // the whole range is staged
+        uint32_t i = tid;
+        for (; i + 3 * kSearchThreads < staged; i += 4 * kSearchThreads) {
+          const uint32_t g0 = stage[i], g1 = stage[i + kSearchThreads], g2 = stage[i + 2 * kSearchThreads],
+                         g3 = stage[i + 3 * kSearchThreads];
+          if (g0 != kEmpty) visit(g0);
+          if (g1 != kEmpty) visit(g1);
+          if (g2 != kEmpty) visit(g2);
+          if (g3 != kEmpty) visit(g3);
+        }
+        for (; i < staged; i += kSearchThreads) {
+          const uint32_t g = stage[i];
+          if (g != kEmpty) visit(g);
+        }
+      } else {
+        // a crowded range (more ids than the stage holds): straight from global memory through the flat index
         uint32_t k = 0, seg_end = pref[1];
         const uint32_t* src = p.ids + pr.begin[0] + s_bound[0][pass];   // src + i addresses candidate i while i < seg_end
         auto locate = [&](uint32_t i) -> const uint32_t* {
@@ -545,14 +603,6 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
             src = p.ids + pr.begin[k] + s_bound[k][pass] - pref[k];
           }
           return src + i;
-        };
-        auto visit = [&](uint32_t g) {
-          const uint32_t h = g - id_base;
-          const uint32_t bit = 1u << (h & 31u);
-          if (atomicOr(&bitmap[h >> 5], bit) & bit) {
-            const uint32_t pos = atomicAdd(&s_ndup, 1u);
-            if (pos < kDupCap) dup[pos] = g;
-          }
         };
         uint32_t i = tid;
         for (; i + 3 * kSearchThreads < Lp; i += 4 * kSearchThreads) {
