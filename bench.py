@@ -612,7 +612,10 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the "
+                                  "committed ncu --set full capture of this workload (not re-measured in this run)",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": stage_ms[dom],
                 "stage_ms": stage_ms,
                 "whole_path_frac": (alg_bytes / (ms_per_step / 1e3) / 1e9) / peak,
@@ -643,7 +646,10 @@ def main():
                     "note": "two batches in flight on two streams; each step copies its PCM from pinned host "
                             "memory and its signatures back; timed on the host clock around all K steps; "
                             "h2d_ceiling = the same ranks sending the same pinned buffers with no kernels, same run"},
-            "gpu_launches": int(launches_per_run * (args.steps * 2 + max(args.warmup, 3) + 4)),
+            # kernels of the timed regions and their warm-ups: `value` (warm-up + K runs) and `e2e` (3 + K + 1 steps), each run
+            # launching launches_per_run kernels (counted by the library); the supplementary sections are not included
+            "gpu_launches": int(launches_per_run * (max(args.warmup, 3) + args.steps + 3 + args.steps + 1)),
+            "gpu_launches_per_step": int(launches_per_run),
             "roofline": roofline, "signatures_per_track": int(n_sigs[0]), "group_record_slots_in_use": slots_in_use}
 
     if world == 1 and rank == 0:
@@ -677,6 +683,45 @@ def main():
             del wpin
         except Exception as exc:
             line["value_worst_content"] = {"error": repr(exc)}
+        # the tolerance mode of K1 (never the default): same pass, same track, and how far its signatures are from the exact ones
+        try:
+            fstream = torch.cuda.Stream()
+            fctx = capi.Context(local_rank, fstream.cuda_stream, fast_spectra=True)
+            fbatch = fctx.batch(track)
+            fbatch.upload()
+            fbatch.sync()
+            for _ in range(3):
+                fbatch.run()
+            fbatch.sync()
+            fbatch.set_timing(True)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(fstream):
+                f0.record(fstream)
+                for _ in range(args.steps):
+                    fbatch.run()
+                f1.record(fstream)
+            torch.cuda.synchronize()
+            fms = f0.elapsed_time(f1) / args.steps
+            fstage, _ = fbatch.get_timing()
+            fbatch.set_timing(False)
+            fsig, fn, _ = fbatch.download()
+            batch.upload(track)
+            batch.run()
+            esig, en, _ = batch.download()
+            same = float((fsig[: int(fn[0])] == esig[: int(en[0])]).all(axis=1).mean()) if int(fn[0]) == int(en[0]) else None
+            line["fast_spectra"] = {"value": hours_per_step / (fms / 1e3), "unit": UNIT, "ms_per_step": fms, "stage_ms": fstage,
+                                    "speedup_vs_value": ms_per_step / fms, "signatures": [int(en[0]), int(fn[0])],
+                                    "signatures_identical_to_exact_fraction": same,
+                                    "k1_frac_of_hbm": (alg_bytes / (fstage["k1_spectral"] / 1e3) / 1e9) / peak,
+                                    "whole_path_frac_of_hbm": (alg_bytes / (fms / 1e3) / 1e9) / peak,
+                                    "note": "tolerance mode of the frame -> band-energy kernel (mnemo_create_ex, "
+                                            "MNEMO_FAST_SPECTRA): real-input 1024-point four-step FFT with FMA; images within "
+                                            "1e-4, raw bits >= 99.9 %, same identified tracks (profiles/r02_fast_gates.json); "
+                                            "NOT the default: value / e2e / roofline above are the bit-exact mode"}
+            fbatch.close()
+            fctx.close()
+        except Exception as exc:
+            line["fast_spectra"] = {"error": repr(exc)}
         try:
             line["e2e_dropin"] = dropin_section(pcm, args.seconds, local_rank)
         except Exception as exc:

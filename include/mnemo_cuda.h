@@ -40,6 +40,14 @@ typedef struct mnemo_db mnemo_db;
  * taps, FFT twiddles and band edges with the host's libm — the same calls the reference
  * makes (hannwindow.c:10, resample.c:27-35, fft.c:49-51, logbins.c:44-55) — and uploads them. */
 int mnemo_create(int device, void* stream, mnemo_ctx** out);
+/* The same with flags.  MNEMO_FAST_SPECTRA selects the TOLERANCE mode of the frame -> band-energy kernel: a real-input
+ * 1024-point four-step FFT with fused multiply-adds and double-precision twiddles instead of the bit-exact replay of
+ * fft.c:34-86.  Band energies then agree with the reference to ~1e-6 relative (spectral images within BASELINE.json's
+ * 1e-4), raw fingerprints on >= 99.9 % of their bits, and signatures wherever the top-200 set agrees — not bit for
+ * bit.  Never the default; mnemo_create honours the environment variable MNEMO_FAST_SPECTRA=1. */
+#define MNEMO_FAST_SPECTRA 1u
+int mnemo_create_ex(int device, void* stream, uint32_t flags, mnemo_ctx** out);
+int mnemo_spectra_mode(const mnemo_ctx* ctx); /* 0 exact, 1 tolerance mode */
 void mnemo_destroy(mnemo_ctx* ctx);
 const char* mnemo_last_error(const mnemo_ctx* ctx);
 /* Diagnostics: which glibc logf variant (0 baseline, 1 fma) the device code mirrors, and how

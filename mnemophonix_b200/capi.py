@@ -51,6 +51,8 @@ def lib() -> C.CDLL:
         L = C.CDLL(LIB_PATH)
         vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
         L.mnemo_create.argtypes = [i32, vp, C.POINTER(vp)]
+        L.mnemo_create_ex.argtypes = [i32, vp, u32, C.POINTER(vp)]
+        L.mnemo_spectra_mode.argtypes = [vp]
         L.mnemo_destroy.argtypes = [vp]
         L.mnemo_last_error.argtypes = [vp]
         L.mnemo_last_error.restype = C.c_char_p
@@ -131,9 +133,13 @@ def _tracks(pcms) -> tuple[C.Array, list]:
 class Context:
     """One mnemo_ctx.  stream: raw cudaStream_t handle (int) or None."""
 
-    def __init__(self, device: int = 0, stream: int | None = None):
+    def __init__(self, device: int = 0, stream: int | None = None, fast_spectra: bool = False):
+        """fast_spectra: the tolerance mode of the frame -> band-energy kernel (MNEMO_FAST_SPECTRA in mnemo_cuda.h)."""
         self.h = C.c_void_p()
-        rc = lib().mnemo_create(device, C.c_void_p(stream) if stream else None, C.byref(self.h))
+        if fast_spectra:
+            rc = lib().mnemo_create_ex(device, C.c_void_p(stream) if stream else None, 1, C.byref(self.h))
+        else:
+            rc = lib().mnemo_create(device, C.c_void_p(stream) if stream else None, C.byref(self.h))
         if rc != 0:
             raise MnemoError(f"mnemo_create(device={device}) failed: {ERRORS.get(rc, rc)} (no GPU? no CPU fallback exists)")
         self.device = device

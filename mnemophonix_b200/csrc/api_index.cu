@@ -181,7 +181,7 @@ static int build_tables(Tables* t, uint32_t* probes, uint32_t* matched, std::str
 
 // ------------------------------------------------------------------ context ----
 
-extern "C" int mnemo_create(int device, void* stream, mnemo_ctx** out) {
+extern "C" int mnemo_create_ex(int device, void* stream, uint32_t flags, mnemo_ctx** out) {
   if (!out) return -3;
   *out = nullptr;
   mnemo_ctx* ctx = new (std::nothrow) mnemo_ctx();
@@ -237,6 +237,18 @@ extern "C" int mnemo_create(int device, void* stream, mnemo_ctx** out) {
   cudaMemcpy(ctx->d_inv_perms, inv.data(), inv.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
   k1_upload_constants(ctx->h_tables);
   k0_upload_constants(ctx->h_tables);
+  ctx->fast_spectra = (flags & MNEMO_FAST_SPECTRA) != 0;
+  if (ctx->fast_spectra) {   // tolerance mode of K1: its twiddle tables
+    std::vector<float2> tw(k1_fast_table_float2());
+    float2 w32[16];
+    k1_fast_tables(tw.data(), w32);
+    if (cudaMalloc(&ctx->d_tw_fast, tw.size() * sizeof(float2)) != cudaSuccess) {
+      mnemo_destroy(ctx);
+      return -1;
+    }
+    cudaMemcpy(ctx->d_tw_fast, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice);
+    k1_fast_upload_constants(w32);
+  }
   e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     fprintf(stderr, "mnemo_create: %s\n", cudaGetErrorString(e));
@@ -246,6 +258,14 @@ extern "C" int mnemo_create(int device, void* stream, mnemo_ctx** out) {
   *out = ctx;
   return 0;
 }
+
+extern "C" int mnemo_create(int device, void* stream, mnemo_ctx** out) {
+  // MNEMO_FAST_SPECTRA=1 opts a whole process (e.g. the CLI) into the tolerance mode; the default is the exact replay
+  const char* env = getenv("MNEMO_FAST_SPECTRA");
+  return mnemo_create_ex(device, stream, (env && atoi(env) > 0) ? MNEMO_FAST_SPECTRA : 0u, out);
+}
+
+extern "C" int mnemo_spectra_mode(const mnemo_ctx* ctx) { return ctx && ctx->fast_spectra ? 1 : 0; }
 
 static void live_release(mnemo_ctx* ctx) {
   mnemo_ctx::Live& lv = ctx->live;
@@ -261,6 +281,7 @@ extern "C" void mnemo_destroy(mnemo_ctx* ctx) {
   cudaSetDevice(ctx->device);
   live_release(ctx);
   if (ctx->arena) cudaFree(ctx->arena);
+  if (ctx->d_tw_fast) cudaFree(ctx->d_tw_fast);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_inv_perms) cudaFree(ctx->d_inv_perms);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -644,8 +665,12 @@ extern "C" int mnemo_batch_run(mnemo_batch* b) {
   }
   if (tm) cudaEventRecord(b->ev[2], st);
   const uint32_t k1_tiles = b->k1_tile_prefix[b->n_tracks];
-  launch_k1_spectral(b->d_tracks, b->d_k1_prefix, b->n_tracks, k1_tiles, ctx->d_tables, b->d_norm, b->d_bins,
-                     ctx->sm_count, st);
+  if (ctx->fast_spectra)
+    launch_k1_fast(b->d_tracks, b->d_k1_prefix, b->n_tracks, k1_tiles, ctx->d_tables, ctx->d_tw_fast, b->d_norm, b->d_bins,
+                   ctx->sm_count, st);
+  else
+    launch_k1_spectral(b->d_tracks, b->d_k1_prefix, b->n_tracks, k1_tiles, ctx->d_tables, b->d_norm, b->d_bins,
+                       ctx->sm_count, st);
   launches += k1_tiles ? 1 : 0;
   if (tm) cudaEventRecord(b->ev[3], st);
   launch_group_records(b->d_tracks, b->d_group_prefix, b->n_tracks, (uint32_t)b->n_groups, ctx->d_tables, b->d_bins,

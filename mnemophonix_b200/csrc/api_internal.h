@@ -15,6 +15,8 @@ struct mnemo_ctx {
   mnemo::Tables* d_tables = nullptr;
   uint16_t* d_inv_perms = nullptr;  // [8192][100]: position of bit b in permutation p (255 = not among the first 255)
   uint32_t logf_probes = 0, logf_matched = 0;
+  bool fast_spectra = false;        // tolerance mode of K1 (mnemo_create_ex, MNEMO_FAST_SPECTRA)
+  float2* d_tw_fast = nullptr;      // its twiddle tables
   std::string err;
   // Live path (mnemo_index_samples, the ears loop's once-a-second call): the batch of the last sample count is kept,
   // with pinned in/out buffers and the whole call (copy in, kernels, copy out) captured as one CUDA graph.

@@ -85,6 +85,12 @@ void launch_compact(const uint8_t* sig_dense, const uint8_t* keep, uint64_t n_im
                     uint32_t n_tracks, uint32_t* block_sums, uint32_t* pos, uint8_t* sig_out, uint32_t* n_sigs,
                     cudaStream_t st, int* n_launches);
 void k1_upload_constants(const Tables& t);
+// tolerance mode of K1 (k1_spectral.cu, "fast K1"): twiddle tables from double precision, kernel launch
+size_t k1_fast_table_float2();
+void k1_fast_tables(float2* tw, float2 w32[16]);
+void k1_fast_upload_constants(const float2 w32[16]);
+void launch_k1_fast(const TrackDev* tracks, const uint32_t* tile_prefix, uint32_t n_tracks, uint32_t n_tiles, const Tables* tab,
+                    const float2* tw_fast, const float* snorm, float* bins, int sm_count, cudaStream_t st);
 void k0_upload_constants(const Tables& t);
 void launch_div_test(int which, uint32_t lo_bits, uint64_t n, unsigned long long* bad, float c, float rc,
                      cudaStream_t st);

@@ -27,6 +27,8 @@
 // (audionormalizer.c:22-31: s / rms, clipped to [-1, 1]) once per sample; the FFT kernel then pulls
 // its 96-frame tiles (8128 samples, 32.5 KB) with TMA bulk copies (cp.async.bulk + mbarrier) into a
 // double buffer, so the next tile streams in while the current one is transformed.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace mnemo {
@@ -359,6 +361,218 @@ __global__ void __launch_bounds__(kK1Threads, 1)
     }
     __syncthreads();   // every warp is done with tile_buf[cur]: it may be refilled next iteration
   }
+}
+
+// =====================================================================================================================
+// Tolerance mode ("fast K1", selected per context: mnemo_create_ex(..., MNEMO_FAST_SPECTRA), never the default).
+//
+// BASELINE.json allows 1e-4 relative error on the spectral images; the kernel above spends its time replaying the
+// reference's radix-2 network rounding for rounding.  This one computes the same band energies the cheap way:
+//   * the frame is real, so its 2048-point spectrum comes from ONE 1024-point complex transform of
+//     z[n] = x[2n] + i x[2n+1] and an untangling step, X[k] = ((Z[k] + conj Z[1024-k]) - i W2048^k (Z[k] - conj Z[1024-k])) / 2,
+//     evaluated only for the 625 bins 118..742 that feed the bands (logbins.c:64-75);
+//   * the 1024-point transform is a 32 x 32 four-step: 32-point transform per lane in registers (decimation in
+//     frequency, twiddles as constant-bank operands), twiddle by W1024^(b*c), one transposition through shared
+//     memory, second 32-point transform per lane; complex products are 1 FMUL2 + 1 FFMA2 (fused, unlike above);
+//   * twiddles come from double-precision cos/sin rounded to float (more accurate than the reference's cosf/sinf of
+//     a float angle);
+//   * band sums are four-way parallel partial sums instead of the reference's sequential order.
+// About 750 packed FP32 instructions per lane and frame against 1870 FMA-pipe instructions of the exact replay.
+// The results differ from the reference's in the last bits of the band energies (measured gates: bench.py
+// "fast_spectra" and tools/fast_gates.py); everything downstream (group records, K2) is unchanged.
+
+constexpr int kF1Warps = 12;
+constexpr int kF1Threads = kF1Warps * 32;
+constexpr int kF1TileFrames = kK1TileFrames;                     // same tiling as the exact kernel (launch code shared)
+constexpr int kF1TStride = 33;                                   // float2 per row of the transposition scratch
+constexpr int kF1ScratchF2 = 32 * kF1TStride;                    // per warp
+constexpr int kF1FirstD = 3, kF1LastD = 23;                      // k = c + 32 d covers 118..742 for d = 3..23
+constexpr int kF1NumD = kF1LastD - kF1FirstD + 1;
+constexpr size_t kF1Smem = sizeof(float) * (2 * kK1TileSamples + kFrame) + sizeof(float2) * (1024 + kF1NumD * 32) +
+                           sizeof(float2) * kF1Warps * kF1ScratchF2 + 16;
+
+__constant__ float2 c_w32[16];   // W32^m = exp(-2 pi i m / 32), m < 16
+
+__device__ __forceinline__ cplx fma2(cplx a, cplx b, cplx c) {
+  cplx r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// b * w, fused: (br wr - bi wi, bi wr + br wi)
+__device__ __forceinline__ cplx cmul_f(cplx b, const float wr, const float wi) {
+  return fma2(pk(hi(b), lo(b)), pk(-wi, wi), mul2(b, pk(wr, wr)));
+}
+// b * (-i) = (bi, -br)
+__device__ __forceinline__ cplx mul_mi(cplx b) { return pk(hi(b), -lo(b)); }
+
+__host__ __device__ constexpr int rev5c(int v) {
+  return ((v & 1) << 4) | ((v & 2) << 2) | (v & 4) | ((v & 8) >> 2) | ((v & 16) >> 4);
+}
+
+// 32-point forward transform in registers, decimation in frequency: natural order in, out[k] = v[rev5c(k)].
+__device__ __forceinline__ void fft32_dif(cplx (&v)[32]) {
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int L = 32 >> s, H = L >> 1;
+#pragma unroll
+    for (int base = 0; base < 32; base += L) {
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        const int m = k * (32 / L);   // W_L^k = W32^m
+        const cplx a = v[base + k], b = v[base + k + H];
+        v[base + k] = add2(a, b);
+        const cplx d = sub2(a, b);
+        if (m == 0) v[base + k + H] = d;
+        else if (m == 8) v[base + k + H] = mul_mi(d);
+        else v[base + k + H] = cmul_f(d, c_w32[m].x, c_w32[m].y);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kF1Threads, 1)
+    k1_fast_kernel(const TrackDev* __restrict__ tracks, const uint32_t* __restrict__ tile_prefix, uint32_t n_tracks,
+                   uint32_t n_tiles, const Tables* __restrict__ tab, const float2* __restrict__ tw_fast,
+                   const float* __restrict__ snorm, float* __restrict__ bins) {
+  extern __shared__ __align__(128) float smem[];
+  float* const tile0 = smem;                                        // 2 x kK1TileSamples (TMA destinations)
+  float* hann = smem + 2 * kK1TileSamples;                          // kFrame
+  float2* tw4 = reinterpret_cast<float2*>(hann + kFrame);           // [c][b]: W1024^(b c)
+  float2* twu = tw4 + 1024;                                         // [d - 3][c]: W2048^(c + 32 d)
+  float2* scratch_all = twu + kF1NumD * 32;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_all + kF1Warps * kF1ScratchF2);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float2* sc = scratch_all + warp * kF1ScratchF2;
+  float* pw = reinterpret_cast<float*>(sc);   // after the transposition: power terms of bins 96..767 (index k - 96)
+
+  for (int i = threadIdx.x; i < kFrame; i += kF1Threads) hann[i] = tab->hann[i];
+  for (int i = threadIdx.x; i < 1024 + kF1NumD * 32; i += kF1Threads) tw4[i] = tw_fast[i];
+  const int e_lo = (int)tab->edges[lane] - 96, e_hi = (int)tab->edges[lane + 1] - 96;
+  const float width = (float)(unsigned)(e_hi - e_lo);
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](uint32_t tix, int buf) {
+    const uint32_t t = find_segment<uint32_t>(tile_prefix, n_tracks, tix);
+    const uint32_t f0 = (tix - tile_prefix[t]) * kF1TileFrames;
+    const uint32_t nf = min((uint32_t)kF1TileFrames, tracks[t].n_frames - f0);
+    const uint32_t bytes = (kHop * (nf - 1) + kFrame) * (uint32_t)sizeof(float);
+    mbar_expect_tx(&bars[buf], bytes);
+    tma_load_1d(tile0 + buf * kK1TileSamples, snorm + tracks[t].s_off + (uint64_t)f0 * kHop, bytes, &bars[buf]);
+  };
+  if (threadIdx.x == 0 && blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+  uint32_t phase_bits = 0;
+  int cur = 0;
+  const int src_lane = (32 - lane) & 31;   // Z[1024 - k] lives in lane (32 - c) mod 32
+
+  for (uint32_t tix = blockIdx.x; tix < n_tiles; tix += gridDim.x, cur ^= 1) {
+    const uint32_t t = find_segment<uint32_t>(tile_prefix, n_tracks, tix);
+    const TrackDev tr = tracks[t];
+    const uint32_t f0 = (tix - tile_prefix[t]) * kF1TileFrames;
+    const uint32_t nf = min((uint32_t)kF1TileFrames, tr.n_frames - f0);
+    if (threadIdx.x == 0 && tix + gridDim.x < n_tiles) issue(tix + gridDim.x, cur ^ 1);
+    mbar_wait(&bars[cur], (phase_bits >> cur) & 1u);
+    phase_bits ^= 1u << cur;
+    const float* tile = tile0 + cur * kK1TileSamples;
+
+    for (uint32_t fl = warp; fl < nf; fl += kF1Warps) {
+      cplx v[32];
+      {  // z[32 a + b] = (x[2n] h[2n], x[2n+1] h[2n+1]), n = 32 a + b, b = lane
+        const cplx* fs = reinterpret_cast<const cplx*>(tile + fl * kHop) + lane;   // tile + 64 fl is 8-byte aligned
+        const cplx* hw = reinterpret_cast<const cplx*>(hann) + lane;
+#pragma unroll
+        for (int a = 0; a < 32; ++a) v[a] = mul2(fs[32 * a], hw[32 * a]);
+      }
+      fft32_dif(v);   // over a: Y_b[c] = v[rev5c(c)]
+      // twiddle by W1024^(b c) and transpose: scratch[c][b]
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        cplx y = v[rev5c(c)];
+        if (c) {
+          const float2 w = tw4[c * 32 + lane];
+          y = cmul_f(y, w.x, w.y);
+        }
+        reinterpret_cast<cplx*>(sc)[c * kF1TStride + lane] = y;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int b = 0; b < 32; ++b) v[b] = reinterpret_cast<const cplx*>(sc)[lane * kF1TStride + b];
+      __syncwarp();
+      fft32_dif(v);   // over b: Z[c + 32 d] = v[rev5c(d)], c = lane
+
+      // untangle bins k = c + 32 d, d = 3..23, and leave |X[k] / 1024|^2 in the scratch at k - 96
+#pragma unroll
+      for (int d = kF1FirstD; d <= kF1LastD; ++d) {
+        const cplx A = v[rev5c(d)];
+        // partner Z[1024 - k]: register 31 - d of lane 32 - c (register 32 - d of lane 0 for c == 0)
+        const cplx send = lane == 0 ? v[rev5c(32 - d)] : v[rev5c(31 - d)];
+        float pr, pi;
+        upk(send, pr, pi);
+        pr = __shfl_sync(0xffffffffu, pr, src_lane);
+        pi = __shfl_sync(0xffffffffu, pi, src_lane);
+        const cplx Bc = pk(pr, -pi);                       // conj Z[1024 - k]
+        const cplx S = add2(A, Bc), D = sub2(A, Bc);
+        const float2 w = twu[(d - kF1FirstD) * 32 + lane];
+        const cplx q = cmul_f(D, w.x, w.y);                // W2048^k (A - conj B)
+        const cplx X2 = add2(S, mul_mi(q));                // 2 X[k]
+        const cplx r = mul2(X2, pk(0.00048828125f, 0.00048828125f));   // X[k] / 1024
+        const cplx sq = mul2(r, r);
+        pw[32 * (d - kF1FirstD) + lane] = lo(sq) + hi(sq);
+      }
+      __syncwarp();
+      // band means (logbins.c:64-75), one band per lane, four partial sums
+      float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+      {
+        const float* __restrict__ pb = pw + e_lo;
+        const int w = e_hi - e_lo;
+#pragma unroll
+        for (int u = 0; u < kMaxBandWidth; u += 4) {
+          s0 += (u < w) ? pb[u] : 0.0f;
+          s1 += (u + 1 < w) ? pb[u + 1] : 0.0f;
+          s2 += (u + 2 < w) ? pb[u + 2] : 0.0f;
+          s3 += (u + 3 < w) ? pb[u + 3] : 0.0f;
+        }
+      }
+      bins[(tr.frame_off + f0 + fl) * kBands + lane] = __fdiv_rn((s0 + s1) + (s2 + s3), width);
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+}
+
+// host side of the tolerance mode: the twiddle tables, from double precision
+size_t k1_fast_table_float2() { return 1024 + (size_t)kF1NumD * 32; }
+void k1_fast_tables(float2* tw /* k1_fast_table_float2() entries */, float2 w32[16]) {
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int c = 0; c < 32; ++c)
+    for (int b = 0; b < 32; ++b) {
+      const double ang = -two_pi * (double)(b * c) / 1024.0;
+      tw[c * 32 + b] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+  for (int d = kF1FirstD; d <= kF1LastD; ++d)
+    for (int c = 0; c < 32; ++c) {
+      const double ang = -two_pi * (double)(c + 32 * d) / 2048.0;
+      tw[1024 + (d - kF1FirstD) * 32 + c] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+  for (int m = 0; m < 16; ++m) {
+    const double ang = -two_pi * (double)m / 32.0;
+    w32[m] = make_float2((float)cos(ang), (float)sin(ang));
+  }
+}
+void k1_fast_upload_constants(const float2 w32[16]) { cudaMemcpyToSymbol(c_w32, w32, sizeof(float2) * 16); }
+
+void launch_k1_fast(const TrackDev* tracks, const uint32_t* tile_prefix, uint32_t n_tracks, uint32_t n_tiles, const Tables* tab,
+                    const float2* tw_fast, const float* snorm, float* bins, int sm_count, cudaStream_t st) {
+  if (n_tiles == 0) return;
+  cudaFuncSetAttribute(k1_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF1Smem);
+  const unsigned grid = n_tiles < (uint32_t)sm_count ? n_tiles : (unsigned)sm_count;
+  k1_fast_kernel<<<grid, kF1Threads, kF1Smem, st>>>(tracks, tile_prefix, n_tracks, n_tiles, tab, tw_fast, snorm, bins);
 }
 
 void launch_normalize(const TrackDev* tracks, const uint32_t* chunk_track, uint64_t n_chunks, const float* s5512,

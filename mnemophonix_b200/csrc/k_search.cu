@@ -536,11 +536,46 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
       listed = 0;
       __syncthreads();
     };
-    for (uint32_t pass = 0; pass < n_pass; ++pass) {
+    // A range costs two barriers: [mark] | [clear the bitmap, flush if the short list is about to fill, stage the NEXT
+    // range] |.  The next range's ids are copied into shared memory (set + uniq, idle outside a flush) while the bitmap
+    // of this one is cleared: every warp issues 16-byte asynchronous copies for the pieces of its lists — the whole
+    // range in flight at once, no registers held.  A piece starts at any word, so its source is aligned down (up to 3
+    // ids of the neighbouring bucket in front, up to 3 behind) and those strangers are blanked once the copy has
+    // landed.  The marking loop then reads a flat array: no candidate -> (list, offset) walk, no global load.
+    uint32_t* const stage = set;
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+    auto next_pass = [&](uint32_t from) {   // first range at or after `from` in which something can repeat
+      while (from < n_pass && s_pref[from][kTables] < 2) ++from;
+      return from;
+    };
+    auto stage_pass = [&](uint32_t pass) {
+      if (s_so[pass][kTables] > kStageCap) return;   // a crowded range is marked straight from global memory
+      for (int k = warp; k < kTables; k += kSearchThreads / 32) {
+        const uint32_t b = s_bound[k][pass], n = s_bound[k][pass + 1] - b;
+        if (!n) continue;
+        const uint32_t first = pr.begin[k] + b, units = ((first & 3u) + n + 3u) >> 2;
+        const uint32_t dst = stage_s + (s_so[pass][k] << 2);
+        const uint32_t* src = p.ids + (first & ~3u);
+        for (uint32_t u = lane; u < units; u += 32)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (u << 4)), "l"(src + (u << 2)) : "memory");
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncwarp();
+      for (int k = warp; k < kTables; k += kSearchThreads / 32) {
+        const uint32_t b = s_bound[k][pass], n = s_bound[k][pass + 1] - b;
+        if (!n) continue;
+        const uint32_t lead = (pr.begin[k] + b) & 3u, words = ((lead + n + 3u) >> 2) << 2;
+        uint32_t* dst = stage + s_so[pass][k];
+        if ((uint32_t)lane < lead) dst[lane] = kEmpty;
+        if ((uint32_t)lane < words - lead - n) dst[lead + n + lane] = kEmpty;
+      }
+    };
+    uint32_t pass = next_pass(0);
+    if (pass < n_pass) stage_pass(pass);   // nothing is listed at the start of a group of ranges
+    __syncthreads();
+    while (pass < n_pass) {
       const uint32_t* __restrict__ pref = s_pref[pass];
       const uint32_t Lp = pref[kTables];
-      if (Lp < 2) continue;   // nothing can repeat in this id range; no barrier: the tables are read-only by now
-      if (listed && listed + Lp / 4 > kDupCap) flush();
       const uint32_t id_base = (c0 + pass) * range_ids;
       auto visit = [&](uint32_t g) {
         const uint32_t h = g - id_base;
@@ -552,33 +587,6 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
       };
       const uint32_t staged = s_so[pass][kTables];
       if (staged <= kStageCap) {
-        // The ids of this range go to shared memory first: every warp copies the pieces of its lists with 16-byte
-        // asynchronous copies (all of the range in flight at once, no registers held).  A piece starts at any word,
-        // so its source is aligned down — up to 3 ids of the neighbouring bucket in front, up to 3 behind — and
-        // those strangers are blanked once the copy has landed.  The marking loop then reads a flat array: no
-        // candidate -> (list, offset) walk, no global load in the loop.
-        uint32_t* const stage = set;   // set + uniq are idle between flushes
-        const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
-        for (int k = warp; k < kTables; k += kSearchThreads / 32) {
-          const uint32_t b = s_bound[k][pass], n = s_bound[k][pass + 1] - b;
-          if (!n) continue;
-          const uint32_t first = pr.begin[k] + b, units = ((first & 3u) + n + 3u) >> 2;
-          const uint32_t dst = stage_s + (s_so[pass][k] << 2);
-          const uint32_t* src = p.ids + (first & ~3u);
-          for (uint32_t u = lane; u < units; u += 32)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (u << 4)), "l"(src + (u << 2)) : "memory");
-        }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncwarp();
-        for (int k = warp; k < kTables; k += kSearchThreads / 32) {
-          const uint32_t b = s_bound[k][pass], n = s_bound[k][pass + 1] - b;
-          if (!n) continue;
-          const uint32_t lead = (pr.begin[k] + b) & 3u, words = ((lead + n + 3u) >> 2) << 2;
-          uint32_t* dst = stage + s_so[pass][k];
-          if ((uint32_t)lane < lead) dst[lane] = kEmpty;
-          if ((uint32_t)lane < words - lead - n) dst[lead + n + lane] = kEmpty;
-        }
-        __syncthreads();   // the whole range is staged
         uint32_t i = tid;
         for (; i + 3 * kSearchThreads < staged; i += 4 * kSearchThreads) {
           const uint32_t g0 = stage[i], g1 = stage[i + kSearchThreads], g2 = stage[i + 2 * kSearchThreads],
@@ -653,7 +661,13 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
           }
         }
       }
-      __syncthreads();   // bitmap clean, and nobody still reads s_ndup when the next pass appends
+      const uint32_t nxt = next_pass(pass + 1);
+      if (nxt < n_pass) {
+        if (listed && listed + s_pref[nxt][kTables] / 4 > kDupCap) flush();   // (uses the stage area: before staging)
+        stage_pass(nxt);
+      }
+      __syncthreads();   // bitmap clean, next range staged, and nobody still reads s_ndup when the next range appends
+      pass = nxt;
     }
     if (c0 + kMaxRangePasses < range_passes) {
       flush();
