@@ -48,15 +48,16 @@ def make_track(seconds: float, channels: int, seed: int) -> np.ndarray:
 
 
 def make_worst_content_track(seconds: float, channels: int, seed: int) -> np.ndarray:
-    """Content that defeats the sharing of group records (k15_groups.cu): a frequency-modulated tone under a level that
-    rises steadily for 14 s and drops back (the signal of tests/test_gpu_index.py::test_window_maximum_changes_every_image,
-    as a saw-tooth) gives nearly every spectral image its own window maximum, so an 8-frame group needs up to all 16
-    record slots instead of the ~5 a steady-level take needs (the slots in use are reported)."""
-    n = int(round(min(seconds, 630.0) * 44100))          # 45 saw-teeth, then tiled
+    """Content that defeats the sharing of group records (k15_groups.cu): a steady tone whose level doubles every second
+    for ten seconds and then drops back (a saw-tooth crescendo, 60 dB per tooth).  While the level rises, the loudest
+    frame of every spectral image is its newest one, so each image has its own window maximum and an 8-frame group
+    needs a record for nearly every one of the 16 images that contain it, instead of the ~5 a steady-level take needs
+    (the slots in use are reported)."""
+    n = int(round(min(seconds, 600.0) * 44100))          # 60 saw-teeth, then tiled
     t = np.arange(n, dtype=np.float64) / 44100.0
     rng = np.random.RandomState(seed)
-    env = 0.02 + 0.9 * ((t % 14.0) / 14.0) ** 2
-    x = env * (np.sin(2 * np.pi * (500 + 300 * np.sin(2 * np.pi * 0.7 * t)) * t) + 0.2 * rng.standard_normal(n))
+    env = 0.0009 * np.exp2(t % 10.0)                     # 0.0009 .. 0.92
+    x = env * (np.sin(2 * np.pi * 1000.0 * t) + 0.5 * np.sin(2 * np.pi * 640.0 * t) + 0.05 * rng.standard_normal(n))
     mono = np.clip(np.round(x * 20000), -32768, 32767).astype(np.int16)
     take = np.stack([mono] + [np.round(mono * 0.8).astype(np.int16)] * (channels - 1), axis=1) if channels > 1 else mono[:, None]
     reps = int(np.ceil(seconds * 44100 / n))
@@ -431,6 +432,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--search-c4-tracks", type=int, default=10000,
                     help="database size of the configs[3] search section, sharded over the N GPUs (0 = skip)")
+    ap.add_argument("--index-only", action="store_true",
+                    help="only the headline index measurement (value, e2e, roofline): for profiler launch lists")
     ap.add_argument("--search-c4-ref-queries", type=int, default=64,
                     help="queries of the configs[3] section also answered by the reference / oracle on rank 0")
     args = ap.parse_args()
@@ -652,7 +655,9 @@ def main():
             "gpu_launches_per_step": int(launches_per_run),
             "roofline": roofline, "signatures_per_track": int(n_sigs[0]), "group_record_slots_in_use": slots_in_use}
 
-    if world == 1 and rank == 0:
+    if args.index_only:
+        args.search_c4_tracks, args.no_cpu_baseline = 0, True
+    if world == 1 and rank == 0 and not args.index_only:
         # worst-case content for the group records: the same pass on a saw-tooth crescendo track
         try:
             wpcm = make_worst_content_track(args.seconds, args.channels, seed=1)
@@ -678,8 +683,8 @@ def main():
                                            "stage_ms": wstage, "slowdown_vs_value": wms / ms_per_step,
                                            "group_record_slots_in_use": batch.record_slots_in_use(0),
                                            "signatures": int(wn[0]),
-                                           "content": "frequency-modulated tone + noise under a 14 s saw-tooth crescendo: nearly "
-                                                      "every image has its own window maximum"}
+                                           "content": "two steady tones + noise under a 10 s saw-tooth crescendo (level doubling every "
+                                                      "second): nearly every image has its own window maximum"}
             del wpin
         except Exception as exc:
             line["value_worst_content"] = {"error": repr(exc)}

@@ -267,13 +267,16 @@ extern "C" int mnemo_create(int device, void* stream, mnemo_ctx** out) {
 
 extern "C" int mnemo_spectra_mode(const mnemo_ctx* ctx) { return ctx && ctx->fast_spectra ? 1 : 0; }
 
-static void live_release(mnemo_ctx* ctx) {
+static void live_release(mnemo_ctx* ctx, bool keep_context = false) {
   mnemo_ctx::Live& lv = ctx->live;
   if (lv.exec) cudaGraphExecDestroy(lv.exec);
   if (lv.batch) mnemo_batch_destroy(lv.batch);
   if (lv.pin_in) cudaFreeHost(lv.pin_in);
   if (lv.pin_out) cudaFreeHost(lv.pin_out);
+  mnemo_ctx* own = lv.own;
   lv = mnemo_ctx::Live();
+  if (keep_context) lv.own = own;
+  else if (own) mnemo_destroy(own);
 }
 
 extern "C" void mnemo_destroy(mnemo_ctx* ctx) {
@@ -804,18 +807,30 @@ extern "C" int mnemo_index_samples(mnemo_ctx* ctx, const float* samples, uint32_
   if (n < (uint32_t)kFrame || mnemo_frames(n) == 0) return -5;   // fingerprinting.c:82, spectralimages.c:128
   std::lock_guard<std::mutex> lock(ctx->live_mu);
   cudaSetDevice(ctx->device);
-  cudaStream_t st = ctx->stream;
   mnemo_ctx::Live& lv = ctx->live;
+  if (!lv.own) {   // the live path runs on a context (stream) of its own, under live_mu: a stream that is being captured
+                   // must not receive work from any other thread, and this context's stream is shared
+    int rc = mnemo_create_ex(ctx->device, nullptr, ctx->fast_spectra ? MNEMO_FAST_SPECTRA : 0u, &lv.own);
+    if (rc != 0) {
+      ctx->err = "mnemo_index_samples: cannot create the live path's context";
+      return rc;
+    }
+  }
+  mnemo_ctx* lc = lv.own;
+  cudaStream_t st = lc->stream;
   cudaError_t e = cudaSuccess;
   if (lv.n != n || !lv.batch) {
-    live_release(ctx);
+    live_release(ctx, /*keep_context=*/true);
     mnemo_track tr;
     tr.pcm = nullptr;
     tr.n_frames = n;
     tr.channels = 1;
     tr.reserved = 0;
-    int rc = batch_create_common(ctx, &tr, 1, true, &lv.batch, /*share_arena=*/false);
-    if (rc != 0) return rc;
+    int rc = batch_create_common(lc, &tr, 1, true, &lv.batch, /*share_arena=*/false);
+    if (rc != 0) {
+      ctx->err = lc->err;
+      return rc;
+    }
     mnemo_batch* b = lv.batch;
     const uint64_t out_bytes = b->n_images * kSigLen + 16;
     e = cudaHostAlloc((void**)&lv.pin_in, (uint64_t)n * sizeof(float), cudaHostAllocDefault);
@@ -835,7 +850,7 @@ extern "C" int mnemo_index_samples(mnemo_ctx* ctx, const float* samples, uint32_
     if (e == cudaSuccess) e = cudaGraphInstantiate(&lv.exec, graph, 0);
     if (graph) cudaGraphDestroy(graph);
     if (!lv.pin_in || !lv.pin_out) {
-      live_release(ctx);
+      live_release(ctx, true);
       return mnemo_fail(ctx, e, "mnemo_index_samples (pinned buffers)");
     }
     if (e != cudaSuccess) {   // not capturable here: the same operations are issued one by one on every call
@@ -857,13 +872,16 @@ extern "C" int mnemo_index_samples(mnemo_ctx* ctx, const float* samples, uint32_
     tr.reserved = 0;
     int rc = mnemo_batch_upload(b, &tr);
     if (rc == 0) rc = mnemo_batch_run(b);
-    if (rc != 0) return rc;
+    if (rc != 0) {
+      ctx->err = lc->err;
+      return rc;
+    }
     e = cudaMemcpyAsync(lv.pin_out, b->d_sig_out, b->n_images * kSigLen, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(lv.pin_out + b->n_images * kSigLen, b->d_n_sigs, 4, cudaMemcpyDeviceToHost, st);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {
-    live_release(ctx);
+    live_release(ctx, true);
     return mnemo_fail(ctx, e, "mnemo_index_samples");
   }
   uint32_t cnt = 0;

@@ -21,6 +21,7 @@ struct mnemo_ctx {
   // Live path (mnemo_index_samples, the ears loop's once-a-second call): the batch of the last sample count is kept,
   // with pinned in/out buffers and the whole call (copy in, kernels, copy out) captured as one CUDA graph.
   struct Live {
+    mnemo_ctx* own = nullptr;       // private context (own stream): nothing else can enqueue on a stream being captured
     struct mnemo_batch* batch = nullptr;
     uint32_t n = 0;
     float* pin_in = nullptr;

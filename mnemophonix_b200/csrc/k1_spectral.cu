@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(kK1Threads, 1)
 // The results differ from the reference's in the last bits of the band energies (measured gates: bench.py
 // "fast_spectra" and tools/fast_gates.py); everything downstream (group records, K2) is unchanged.
 
-constexpr int kF1Warps = 12;
+constexpr int kF1Warps = 16;
 constexpr int kF1Threads = kF1Warps * 32;
 constexpr int kF1TileFrames = kK1TileFrames;                     // same tiling as the exact kernel (launch code shared)
 constexpr int kF1TStride = 33;                                   // float2 per row of the transposition scratch

@@ -168,15 +168,23 @@ __global__ void __launch_bounds__(256) search_fixup_kernel(const mnemo_lastgroup
 // Top levels of the ranking tree, one thread per query: the lists of the n_nodes nodes (every shard's block of the
 // all-gathered buffer holds [nodes_per_shard][n_queries][kSelTop] records followed by [nodes_per_shard][n_queries]
 // counts; shard r owns nodes r * n_nodes / n_shards .. (r + 1) * n_nodes / n_shards - 1) are merged pairwise exactly as
-// glibc's merge sort merges the nodes' sorted ranges, truncated to the first ten, then search.c:173-185.
-__global__ void __launch_bounds__(128) select_merge_kernel(const uint8_t* __restrict__ gathered, uint32_t n_shards,
-                                                           uint32_t n_nodes, uint32_t nodes_per_shard, uint32_t n_queries,
-                                                           mnemo_match_dev* __restrict__ out) {
+// glibc's merge sort merges the nodes' sorted ranges, truncated to the first ten, then search.c:173-185.  The level
+// buffers live in shared memory, record e of thread t at [e][t] (consecutive threads, consecutive 16 bytes: no bank
+// conflicts); CTAs are one warp so that 10 000 queries spread over all SMs.
+constexpr int kMergeThreads = 32;
+size_t select_merge_smem(uint32_t n_nodes) { return sizeof(SelRec) * kSelTop * (n_nodes > 1 ? n_nodes / 2 : 1) * kMergeThreads; }
+
+__global__ void __launch_bounds__(kMergeThreads) select_merge_kernel(const uint8_t* __restrict__ gathered, uint32_t n_shards,
+                                                                     uint32_t n_nodes, uint32_t nodes_per_shard,
+                                                                     uint32_t n_queries, mnemo_match_dev* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  SelRec* const sm = reinterpret_cast<SelRec*>(sm_raw);
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_queries) return;
   const uint64_t shard_bytes = (uint64_t)nodes_per_shard * n_queries * (sizeof(SelRec) * kSelTop + 4);
   const uint64_t lists_bytes = (uint64_t)nodes_per_shard * n_queries * sizeof(SelRec) * kSelTop;
-  SelRec cur[kMergeMaxNodes / 2][kSelTop];   // level buffers: the leaves are read from the gathered buffer directly
+  // list i of the current level: records sm[(i * kSelTop + k) * kMergeThreads + threadIdx.x]
+  auto cur = [&](uint32_t i, uint32_t k) -> SelRec& { return sm[(i * kSelTop + k) * kMergeThreads + threadIdx.x]; };
   uint32_t ccnt[kMergeMaxNodes / 2];
   auto leaf = [&](uint32_t node, const SelRec** lst) -> uint32_t {
     uint32_t r = 0;
@@ -187,42 +195,59 @@ __global__ void __launch_bounds__(128) select_merge_kernel(const uint8_t* __rest
     const uint32_t c = reinterpret_cast<const uint32_t*>(blk + lists_bytes)[(uint64_t)slot * n_queries + q];
     return c < (uint32_t)kSelTop ? c : (uint32_t)kSelTop;
   };
-  auto merge = [&](const SelRec* A, uint32_t ca, const SelRec* B, uint32_t cb, SelRec* O) -> uint32_t {
-    SelRec tmp[kSelTop];
-    uint32_t ia = 0, ib = 0, w = 0;
-    while (w < (uint32_t)kSelTop && ia < ca && ib < cb)
-      tmp[w++] = cmp_entry_avg(A[ia].avg, A[ia].n, B[ib].avg, B[ib].n) <= 0 ? A[ia++] : B[ib++];
-    while (w < (uint32_t)kSelTop && ia < ca) tmp[w++] = A[ia++];
-    while (w < (uint32_t)kSelTop && ib < cb) tmp[w++] = B[ib++];
-    for (uint32_t k = 0; k < w; ++k) O[k] = tmp[k];   // O may alias A
-    return w;
-  };
-  uint32_t root_cnt;
-  const SelRec* root;
-  if (n_nodes == 1) {
-    root_cnt = leaf(0, &root);
-  } else {
-    for (uint32_t i = 0; i < n_nodes / 2; ++i) {
-      const SelRec *A, *B;
-      const uint32_t ca = leaf(2 * i, &A), cb = leaf(2 * i + 1, &B);
-      ccnt[i] = merge(A, ca, B, cb, cur[i]);
-    }
-    for (uint32_t m = n_nodes / 2; m > 1; m >>= 1)
-      for (uint32_t i = 0; i < m / 2; ++i) ccnt[i] = merge(cur[2 * i], ccnt[2 * i], cur[2 * i + 1], ccnt[2 * i + 1], cur[i]);
-    root = cur[0];
-    root_cnt = ccnt[0];
-  }
   mnemo_match_dev best = {-7, 0.0f, 0};
   float best_avg = 0.0f;
-  for (uint32_t k = 0; k < root_cnt; ++k) {
-    const SelRec r = root[k];
+  auto consider = [&](const SelRec r) {   // search.c:173-185
     if ((r.n >= 10 || (r.avg >= 35.0f && r.n >= 5)) && r.avg >= 30.0f && r.avg > best_avg) {
       best_avg = r.avg;
       best.entry = r.entry;
       best.score = r.score;
       best.n_matches = r.n;
     }
+  };
+  if (n_nodes == 1) {
+    const SelRec* root;
+    const uint32_t cnt = leaf(0, &root);
+    for (uint32_t k = 0; k < cnt; ++k) consider(root[k]);
+    out[q] = best;
+    return;
   }
+  // first level: pairs of gathered lists -> shared memory
+  for (uint32_t i = 0; i < n_nodes / 2; ++i) {
+    const SelRec *A, *B;
+    const uint32_t ca = leaf(2 * i, &A), cb = leaf(2 * i + 1, &B);
+    uint32_t ia = 0, ib = 0, w = 0;
+    while (w < (uint32_t)kSelTop && ia < ca && ib < cb) {
+      const SelRec a = A[ia], b = B[ib];
+      if (cmp_entry_avg(a.avg, a.n, b.avg, b.n) <= 0) {
+        cur(i, w++) = a;
+        ++ia;
+      } else {
+        cur(i, w++) = b;
+        ++ib;
+      }
+    }
+    while (w < (uint32_t)kSelTop && ia < ca) cur(i, w++) = A[ia++];
+    while (w < (uint32_t)kSelTop && ib < cb) cur(i, w++) = B[ib++];
+    ccnt[i] = w;
+  }
+  // further levels in place: list i <- merge(list 2i, list 2i+1); the left input is buffered because the output
+  // overwrites list i (i <= 2i: list 0 is its own left input, the others lie ahead of what is still to be read)
+  for (uint32_t m = n_nodes / 2; m > 1; m >>= 1)
+    for (uint32_t i = 0; i < m / 2; ++i) {
+      SelRec A[kSelTop];
+      const uint32_t ca = ccnt[2 * i], cb = ccnt[2 * i + 1];
+      for (uint32_t k = 0; k < ca; ++k) A[k] = cur(2 * i, k);
+      uint32_t ia = 0, ib = 0, w = 0;
+      SelRec B[kSelTop];
+      for (uint32_t k = 0; k < cb; ++k) B[k] = cur(2 * i + 1, k);
+      while (w < (uint32_t)kSelTop && ia < ca && ib < cb)
+        cur(i, w++) = cmp_entry_avg(A[ia].avg, A[ia].n, B[ib].avg, B[ib].n) <= 0 ? A[ia++] : B[ib++];
+      while (w < (uint32_t)kSelTop && ia < ca) cur(i, w++) = A[ia++];
+      while (w < (uint32_t)kSelTop && ib < cb) cur(i, w++) = B[ib++];
+      ccnt[i] = w;
+    }
+  for (uint32_t k = 0; k < ccnt[0]; ++k) consider(cur(0, k));
   out[q] = best;
 }
 
@@ -242,8 +267,8 @@ void launch_search_fixup(const mnemo_lastgroup_dev* last, const uint8_t* has_all
 void launch_select_merge(const void* gathered, uint32_t n_shards, uint32_t n_nodes, uint32_t nodes_per_shard,
                          uint32_t n_queries, mnemo_match_dev* out, cudaStream_t st) {
   if (n_queries)
-    select_merge_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(reinterpret_cast<const uint8_t*>(gathered), n_shards, n_nodes,
-                                                                 nodes_per_shard, n_queries, out);
+    select_merge_kernel<<<(n_queries + kMergeThreads - 1) / kMergeThreads, kMergeThreads, select_merge_smem(n_nodes), st>>>(
+        reinterpret_cast<const uint8_t*>(gathered), n_shards, n_nodes, nodes_per_shard, n_queries, out);
 }
 void launch_search_has(const mnemo_lastgroup_dev* last, uint32_t n_qsigs, uint8_t* has, cudaStream_t st) {
   if (n_qsigs) search_has_kernel<<<(n_qsigs + 255) / 256, 256, 0, st>>>(last, n_qsigs, has);
