@@ -686,10 +686,74 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
     }
     const uint32_t Lp = L;
     for (uint32_t i = tid; i < bm_words / 4; i += kSearchThreads) reinterpret_cast<uint4*>(bitmap)[i] = make_uint4(0, 0, 0, 0);
+    // stage offsets of the 25 lists padded to 16-byte units (as in the id-range mode; s_so[0] is free here)
+    if (warp == 0) {
+      uint32_t w = 0;
+      if (lane < kTables) {
+        const uint32_t n = pr.prefix[lane + 1] - pr.prefix[lane];
+        if (n) w = (((pr.begin[lane] & 3u) + n + 3u) >> 2) << 2;
+      }
+      uint32_t incl = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      if (lane <= kTables) s_so[0][lane] = incl - w;   // lane 25: the total
+    }
     __syncthreads();
     const uint32_t* const seg_prefix = pr.prefix;
     const uint32_t* const seg_begin = pr.begin;
-    {
+    auto visit = [&](uint32_t g) {
+      gmax = max(gmax, g);
+      const uint32_t h = (g * 2654435761u) >> bm_shift;
+      const uint32_t bit = 1u << (h & 31u);
+      const uint32_t old = atomicOr(&bitmap[h >> 5], bit);
+      if (old & bit) {
+        const uint32_t pos = atomicAdd(&s_ndup, 1u);
+        if (pos < kDupCap) dup[pos] = g;
+      }
+    };
+    const uint32_t staged = s_so[0][kTables];
+    if (staged <= kStageCap) {
+      // the whole candidate list goes through shared memory (set + uniq are idle until the de-duplication below):
+      // 16-byte asynchronous copies, strangers of the aligned-down pieces blanked, flat marking loop
+      uint32_t* const stage = set;
+      const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+      for (int k = warp; k < kTables; k += kSearchThreads / 32) {
+        const uint32_t n = seg_prefix[k + 1] - seg_prefix[k];
+        if (!n) continue;
+        const uint32_t first = seg_begin[k], units = ((first & 3u) + n + 3u) >> 2;
+        const uint32_t dst = stage_s + (s_so[0][k] << 2);
+        const uint32_t* src = p.ids + (first & ~3u);
+        for (uint32_t u = lane; u < units; u += 32)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (u << 4)), "l"(src + (u << 2)) : "memory");
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncwarp();
+      for (int k = warp; k < kTables; k += kSearchThreads / 32) {
+        const uint32_t n = seg_prefix[k + 1] - seg_prefix[k];
+        if (!n) continue;
+        const uint32_t lead = seg_begin[k] & 3u, words = ((lead + n + 3u) >> 2) << 2;
+        uint32_t* dst = stage + s_so[0][k];
+        if ((uint32_t)lane < lead) dst[lane] = kEmpty;
+        if ((uint32_t)lane < words - lead - n) dst[lead + n + lane] = kEmpty;
+      }
+      __syncthreads();
+      uint32_t i = tid;
+      for (; i + 3 * kSearchThreads < staged; i += 4 * kSearchThreads) {
+        const uint32_t g0 = stage[i], g1 = stage[i + kSearchThreads], g2 = stage[i + 2 * kSearchThreads],
+                       g3 = stage[i + 3 * kSearchThreads];
+        if (g0 != kEmpty) visit(g0);
+        if (g1 != kEmpty) visit(g1);
+        if (g2 != kEmpty) visit(g2);
+        if (g3 != kEmpty) visit(g3);
+      }
+      for (; i < staged; i += kSearchThreads) {
+        const uint32_t g = stage[i];
+        if (g != kEmpty) visit(g);
+      }
+    } else {
       // flat index over the candidates; the thread's position in the list table only moves forward, and four loads
       // are in flight before the first id is used
       uint32_t k = 0, seg_end = seg_prefix[1];
@@ -701,16 +765,6 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
           src = p.ids + seg_begin[k] - seg_prefix[k];
         }
         return src + i;
-      };
-      auto visit = [&](uint32_t g) {
-        gmax = max(gmax, g);
-        const uint32_t h = (g * 2654435761u) >> bm_shift;
-        const uint32_t bit = 1u << (h & 31u);
-        const uint32_t old = atomicOr(&bitmap[h >> 5], bit);
-        if (old & bit) {
-          const uint32_t pos = atomicAdd(&s_ndup, 1u);
-          if (pos < kDupCap) dup[pos] = g;
-        }
       };
       uint32_t i = tid;
       for (; i + 3 * kSearchThreads < Lp; i += 4 * kSearchThreads) {

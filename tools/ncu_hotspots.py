@@ -1,9 +1,10 @@
 """Per-source-line hot spots of one kernel from an .ncu-rep (source page, cuda,sass view).
-usage: python tools/ncu_hotspots.py report.ncu-rep [top_n] > profiles/<name>_source_hotspots.txt"""
+usage: python tools/ncu_hotspots.py report.ncu-rep [top_n] [kernel-name regex] > profiles/<name>_source_hotspots.txt"""
 import csv, io, subprocess, sys
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
+flt = ["-k", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+raw = subprocess.run(["ncu", "-i", rep, *flt, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 items, fpath, hdr = [], None, None
 for r in csv.reader(io.StringIO(raw)):
     if not r:

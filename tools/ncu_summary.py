@@ -1,6 +1,11 @@
 """Summarise an .ncu-rep (raw page) into a markdown table + traffic.json entries.
-usage: python tools/ncu_summary.py report.ncu-rep out.md [traffic.json]"""
+usage: python tools/ncu_summary.py report.ncu-rep out.md [traffic.json] [--title "workload and build the capture is of"]"""
 import csv, io, json, subprocess, sys
+title = None
+if "--title" in sys.argv:
+    i = sys.argv.index("--title")
+    title = sys.argv[i + 1]
+    del sys.argv[i:i + 2]
 rep, out_md = sys.argv[1], sys.argv[2]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -15,7 +20,12 @@ cols = [("gpu__time_duration.sum", "time"), ("smsp__inst_executed.sum", "warp in
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %"),
         ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
         ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
-        ("lts__t_sector_hit_rate.pct", "L2 hit %")]
+        ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+        ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long_sb"),
+        ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall short_sb"),
+        ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier"),
+        ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait"),
+        ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall math")]
 idx = {c: hdr.index(c) for c, _ in cols if c in hdr}
 ki = hdr.index("Kernel Name")
 lines = ["| kernel | " + " | ".join(n for c, n in cols if c in idx) + " |", "|---|" + "---|" * len(idx)]
@@ -39,6 +49,8 @@ for r in rows[2:]:
         traffic[key] = rd + wr
     except Exception:
         pass
+if title:
+    lines = [title, ""] + lines
 open(out_md, "w").write("\n".join(lines) + "\n")
 if len(sys.argv) > 3:
     json.dump(traffic, open(sys.argv[3], "w"), indent=1)
