@@ -96,6 +96,7 @@ def lib() -> C.CDLL:
             L.mnemo_db_destroy.argtypes = [vp]
             L.mnemo_db_table_size.argtypes = [vp]
             L.mnemo_db_table_size.restype = u32
+            L.mnemo_db_has_pair_index.argtypes = [vp]
             L.mnemo_db_get_matches.argtypes = [vp, vp, vp, u64]
             L.mnemo_db_get_matches.restype = C.c_int64
             L.mnemo_search_batch.argtypes = [vp, vp, vp, u32, vp, vp]
@@ -353,6 +354,10 @@ class Db:
     @property
     def table_size(self) -> int:
         return int(lib().mnemo_db_table_size(self.h))
+
+    @property
+    def has_pair_index(self) -> bool:
+        return bool(lib().mnemo_db_has_pair_index(self.h))
 
     def get_matches(self, sig: np.ndarray, cap: int = 1 << 20):
         sig = np.ascontiguousarray(sig, np.uint8)

@@ -23,6 +23,7 @@ struct mnemo_db {
   std::vector<uint32_t> h_entry_start;
   uint8_t* d_sigs = nullptr;
   uint32_t *d_entry_start = nullptr, *d_sig_entry = nullptr, *d_start = nullptr, *d_ids = nullptr;
+  unsigned long long* d_pairs = nullptr;   // pair index (k_search.cu: launch_pair_build), 300 * n_sigs entries, or nullptr
   // scratch kept between search calls (grown on demand): cudaMalloc/cudaFree cost more than the kernels
   struct Scratch {
     void* p = nullptr;
@@ -35,7 +36,7 @@ struct mnemo_db {
 
 enum {   // scratch slots
   kScrQ = 0, kScrQstart, kScrAccS, kScrAccN, kScrLast, kScrStats, kScrTotal, kScrQbase, kScrQcnt, kScrCands, kScrLeaf,
-  kScrSel, kScrSelCnt, kScrOut, kScrHas, kScrHasAll, kScrLists
+  kScrSel, kScrSelCnt, kScrOut, kScrHas, kScrHasAll, kScrLists, kScrBack
 };
 
 static cudaError_t scratch_get(mnemo_db* db, int slot, uint64_t bytes, void** out) {
@@ -118,6 +119,27 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
     TRY(cudaGetLastError());
   }
   TRY(cudaStreamSynchronize(st));
+  // Pair index (k_pairprobe.cu): worth its memory (2400 bytes per signature) and build time once the bucket lists a
+  // query signature probes are long, i.e. for databases beyond a few hundred thousand signatures; MNEMO_PAIR_INDEX=1 / 0
+  // forces it on (tests run the small cases through it) / off.
+  bool want_pairs = db->n_sigs >= 200000;
+  if (const char* env = getenv("MNEMO_PAIR_INDEX")) want_pairs = atoi(env) > 0;
+  if (e == cudaSuccess && want_pairs && db->n_sigs && pair_index_possible(db->size)) {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const uint64_t need = db->n_sigs * 300ull * 8ull + db->n_sigs * (25ull + 24ull) * 4ull;   // index + the scratch not held yet
+    if (need < free_b / 2) {
+      uint32_t *d_slots = nullptr, *d_vals_out = nullptr;
+      TRY(dalloc(&db->d_pairs, db->n_sigs * 300ull));
+      TRY(dalloc(&d_slots, db->n_sigs * kTables));
+      TRY(dalloc(&d_vals_out, db->n_sigs * kTables));
+      TRY(launch_pair_build(db->d_sigs, db->n_sigs, db->size, db->d_ids, d_slots, d_keys_in, d_vals_in, d_keys_out, d_vals_out,
+                            d_temp, db->d_pairs, st));
+      TRY(cudaStreamSynchronize(st));
+      cudaFree(d_slots);
+      cudaFree(d_vals_out);
+    }
+  }
   cudaFree(d_counts);
   cudaFree(d_cursor);
   cudaFree(d_block_sums);
@@ -134,11 +156,13 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
   return 0;
 }
 
+extern "C" int mnemo_db_has_pair_index(const mnemo_db* db) { return db && db->d_pairs ? 1 : 0; }
+
 extern "C" void mnemo_db_destroy(mnemo_db* db) {
   if (!db) return;
   cudaSetDevice(db->ctx->device);
   cudaStreamSynchronize(db->ctx->stream);
-  void* ptrs[] = {db->d_sigs, db->d_entry_start, db->d_sig_entry, db->d_start, db->d_ids};
+  void* ptrs[] = {db->d_sigs, db->d_entry_start, db->d_sig_entry, db->d_start, db->d_ids, db->d_pairs};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& sc : db->scratch)
@@ -161,6 +185,7 @@ static SearchParams base_params(const mnemo_db* db) {
   p.sig_entry = db->d_sig_entry;
   p.start = db->d_start;
   p.ids = db->d_ids;
+  p.pairs = db->d_pairs;
   p.size = db->size;
   p.size_magic = db->size ? 0xFFFFFFFFFFFFFFFFull / db->size + 1 : 0;
   if (db->size) {   // size = 2^shift * odd; inverse of the odd part modulo 2^32 by Newton's iteration
@@ -293,7 +318,25 @@ static cudaError_t probe_tile(mnemo_db* db, ProbeBatch& b, const uint32_t* query
   p.last = b.d_last + s0;
   p.stat_nodes = b.d_stats;
   p.stat_deep = b.d_stats + 1;
-  launch_search(p, ns, st);
+  if (db->d_pairs) {
+    static const bool trace = getenv("MNEMO_TRACE_PAIRS") != nullptr;   // diagnostics: pair-index entries visited
+    unsigned long long* d_vis = nullptr;
+    if (trace) {
+      TRY(scratch_get(db, kScrBack, 8, (void**)&d_vis));
+      TRY(cudaMemsetAsync(d_vis, 0, 8, st));
+      if (e != cudaSuccess) return e;
+    }
+    p.stat_pairs = d_vis;
+    launch_search_pairs(p, ns, st);
+    if (trace) {
+      unsigned long long visited = 0;
+      cudaMemcpyAsync(&visited, d_vis, 8, cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      fprintf(stderr, "[mnemo] pair index: %.0f entries visited per query signature\n", (double)visited / ns);
+    }
+  } else {
+    launch_search(p, ns, st);
+  }
   return cudaGetLastError();
 }
 

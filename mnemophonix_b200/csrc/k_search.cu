@@ -253,6 +253,9 @@ size_t lsh_sort_temp_bytes(uint64_t n_sigs, uint32_t size) {
   return sizeof(uint32_t) * (h + 1 + lsh_scan_blocks(h) + 1);
 }
 
+static void radix_sort_pairs(uint32_t*& ka, uint32_t*& va, uint32_t*& kb, uint32_t*& vb, uint64_t n, int bits, void* temp,
+                             cudaStream_t st);
+
 // keys_in / vals_in / keys_out: 25*n_sigs u32 each (the sort's two buffers); temp: lsh_sort_temp_bytes()
 cudaError_t launch_lsh_build(const uint8_t* sigs, uint64_t n_sigs, const uint32_t* entry_start, uint32_t n_entries,
                              uint32_t size, uint32_t* counts, uint32_t* start, uint32_t* scan_copy, uint32_t* block_sums,
@@ -273,26 +276,92 @@ cudaError_t launch_lsh_build(const uint8_t* sigs, uint64_t n_sigs, const uint32_
   cudaError_t e = cudaSuccess;
   {
     (void)temp_bytes;
-    const uint32_t n_tiles = sort_tiles(n_words);
-    const uint64_t h = 256ull * n_tiles;
-    uint32_t* hist = reinterpret_cast<uint32_t*>(temp);
-    uint32_t* hsums = hist + h + 1;
-    const uint32_t h_blocks = lsh_scan_blocks(h);
-    const int bits = key_bits(n_slots);
     uint32_t *ka = keys_in, *va = vals_in, *kb = keys_out, *vb = ids;
-    for (int shift = 0; shift < bits; shift += 8) {
-      radix_hist_kernel<<<n_tiles, kSortThreads, 0, st>>>(ka, n_words, shift, n_tiles, hist);
-      scan_reduce_kernel<<<h_blocks, kScanT, 0, st>>>(hist, h, hsums);
-      scan_sums_kernel<<<1, kScanT, 0, st>>>(hsums, h_blocks);
-      scan_apply_kernel<<<h_blocks, kScanT, 0, st>>>(hist, h, hsums, hist, hist);   // in place (each block reads its part first)
-      radix_scatter_kernel<<<n_tiles, kSortThreads, 0, st>>>(ka, va, n_words, shift, n_tiles, hist, kb, vb);
-      uint32_t* t = ka; ka = kb; kb = t;
-      t = va; va = vb; vb = t;
-    }
+    radix_sort_pairs(ka, va, kb, vb, n_words, key_bits(n_slots), temp, st);
     if (va != ids) e = cudaMemcpyAsync(ids, va, n_words * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
   }
   sig_entry_kernel<<<(unsigned)((n_sigs + 255) / 256), 256, 0, st>>>(entry_start, n_entries, n_sigs, sig_entry);
   return e;
+}
+
+// ---- pair index (probe side: k_pairprobe.cu) ----
+// search.c:147-165 deep-checks the signatures that share at least TWO buckets with the query signature.  For every pair of
+// tables i < j the pair index lists the database signatures ordered by (slot_i, slot_j, id) as 64-bit entries
+// (slot_j << 32 | id): the members of bucket (i, s_i) occupy the same positions as in table i's CSR, and inside that
+// slice the ones with slot_j == s_j are one contiguous run found by binary search.  A query signature's candidates with
+// two or more shared buckets are then the union of 300 short runs instead of whatever repeats among the ~42 k members
+// of its 25 buckets.  Built from what the CSR build leaves behind: table j's id list is sorted by (slot_j, id), so a
+// STABLE radix sort of it by slot_i gives the (slot_i, slot_j, id) order; all j > i of one i are sorted together with
+// the key (j - i - 1) << bits | slot_i.  300 * n entries of 8 bytes.
+
+// slots[k * n + id] = bucket of signature id in table k
+__global__ void __launch_bounds__(256) lsh_slot_table_kernel(const uint32_t* __restrict__ sig_words, uint64_t n_sigs,
+                                                             uint32_t size, uint32_t* __restrict__ slots) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_sigs * kTables) return;
+  slots[(i % kTables) * n_sigs + i / kTables] = bucket_key(sig_words[i]) % size;
+}
+
+__global__ void __launch_bounds__(256) pair_keys_kernel(const uint32_t* __restrict__ ids_tail, uint64_t n_elems, uint64_t n_sigs,
+                                                        const uint32_t* __restrict__ slots_i, int sbits,
+                                                        uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_elems) return;
+  const uint32_t id = ids_tail[t];
+  keys[t] = ((uint32_t)(t / n_sigs) << sbits) | slots_i[id];
+  vals[t] = id;
+}
+
+__global__ void __launch_bounds__(256) pair_finalize_kernel(const uint32_t* __restrict__ sorted_ids, uint64_t n_elems,
+                                                            uint64_t n_sigs, const uint32_t* __restrict__ slots, int i,
+                                                            unsigned long long* __restrict__ out) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_elems) return;
+  const uint32_t id = sorted_ids[t];
+  const uint32_t j = (uint32_t)i + 1u + (uint32_t)(t / n_sigs);
+  out[t] = ((unsigned long long)slots[(uint64_t)j * n_sigs + id] << 32) | id;
+}
+
+// stable LSD radix sort of n (key, value) pairs on the low `bits` bits of the key; the result is in (ka, va)
+static void radix_sort_pairs(uint32_t*& ka, uint32_t*& va, uint32_t*& kb, uint32_t*& vb, uint64_t n, int bits, void* temp,
+                             cudaStream_t st) {
+  const uint32_t n_tiles = sort_tiles(n);
+  const uint64_t h = 256ull * n_tiles;
+  uint32_t* hist = reinterpret_cast<uint32_t*>(temp);
+  uint32_t* hsums = hist + h + 1;
+  const uint32_t h_blocks = lsh_scan_blocks(h);
+  for (int shift = 0; shift < bits; shift += 8) {
+    radix_hist_kernel<<<n_tiles, kSortThreads, 0, st>>>(ka, n, shift, n_tiles, hist);
+    scan_reduce_kernel<<<h_blocks, kScanT, 0, st>>>(hist, h, hsums);
+    scan_sums_kernel<<<1, kScanT, 0, st>>>(hsums, h_blocks);
+    scan_apply_kernel<<<h_blocks, kScanT, 0, st>>>(hist, h, hsums, hist, hist);   // in place (each block reads its part first)
+    radix_scatter_kernel<<<n_tiles, kSortThreads, 0, st>>>(ka, va, n, shift, n_tiles, hist, kb, vb);
+    uint32_t* t = ka; ka = kb; kb = t;
+    t = va; va = vb; vb = t;
+  }
+}
+
+bool pair_index_possible(uint32_t size) { return size > 0 && key_bits(size) + 5 <= 32; }
+uint32_t pair_index_row_base(int i) { return (uint32_t)(i * (2 * (kTables - 1) - i + 1) / 2); }   // pairs (a, .) with a < i
+
+// ids: the CSR id lists (25 n); slots: 25 n scratch; ka / va / kb / vb: 24 n scratch each; temp: lsh_sort_temp_bytes();
+// pairs: 300 n entries
+cudaError_t launch_pair_build(const uint8_t* sigs, uint64_t n_sigs, uint32_t size, const uint32_t* ids, uint32_t* slots,
+                              uint32_t* ka, uint32_t* va, uint32_t* kb, uint32_t* vb, void* temp, unsigned long long* pairs,
+                              cudaStream_t st) {
+  if (n_sigs == 0 || size == 0) return cudaSuccess;
+  const uint64_t n_words = n_sigs * kTables;
+  lsh_slot_table_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(sigs), n_sigs, size, slots);
+  const int sbits = key_bits(size);
+  for (int i = 0; i + 1 < kTables; ++i) {
+    const uint64_t n_elems = (uint64_t)(kTables - 1 - i) * n_sigs;
+    const unsigned grid = (unsigned)((n_elems + 255) / 256);
+    uint32_t *a = ka, *b = va, *c = kb, *d = vb;
+    pair_keys_kernel<<<grid, 256, 0, st>>>(ids + (uint64_t)(i + 1) * n_sigs, n_elems, n_sigs, slots + (uint64_t)i * n_sigs, sbits, a, b);
+    radix_sort_pairs(a, b, c, d, n_elems, sbits + 5, temp, st);
+    pair_finalize_kernel<<<grid, 256, 0, st>>>(b, n_elems, n_sigs, slots, i, pairs + (uint64_t)pair_index_row_base(i) * n_sigs);
+  }
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ probe + score ----
@@ -351,8 +420,7 @@ __device__ __forceinline__ int table_of(const uint32_t* prefix, uint32_t i) {
 //     search; each pass streams just those through a bitmap with one bit per id (exact, no false repeats).  Every
 //     candidate id is read once however long the lists are, and passes without candidates cost nothing.
 //   Shards of any size: the ranges are walked kMaxRangePasses at a time.
-__global__ void __launch_bounds__(kSearchThreads, 3)
-    search_probe_kernel(SearchParams p) {
+__device__ __forceinline__ void probe_query_signature(const SearchParams& p, const uint32_t qs) {
   extern __shared__ __align__(16) uint32_t sm[];
   uint32_t* bitmap = sm;
   uint32_t* dup = bitmap + kBitmapMaxWords;
@@ -365,7 +433,6 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
   __shared__ uint32_t s_ndup, s_nuniq, s_gmax;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t qs = blockIdx.x;   // query-signature index
   const uint32_t* __restrict__ qwords = reinterpret_cast<const uint32_t*>(p.query_sigs) + (uint64_t)qs * kTables;
 
   if (tid < kTables) {
@@ -855,6 +922,9 @@ __global__ void __launch_bounds__(kSearchThreads, 3)
     if (warp == 0) atomicAdd(p.stat_nodes, (unsigned long long)L);
   }
 }
+
+// one CTA per query signature
+__global__ void __launch_bounds__(kSearchThreads, 3) search_probe_kernel(SearchParams p) { probe_query_signature(p, blockIdx.x); }
 
 // Per query: compact the non-zero per-entry accumulators into candidate records, ascending entry.
 __global__ void __launch_bounds__(256) search_compact_kernel(const uint32_t* __restrict__ acc_score,

@@ -56,6 +56,7 @@ struct SearchParams {
   const uint32_t* sig_entry;     // [n_sigs] shard-local entry index
   const uint32_t* start;         // [25*size + 1] CSR offsets into ids
   const uint32_t* ids;           // [25*n_sigs]
+  const unsigned long long* pairs;   // pair index [300*n_sigs] (slot_j << 32 | id), or nullptr (k_pairprobe.cu)
   uint32_t size;                 // lsh.c:61 (global)
   uint64_t size_magic;           // 0xFFFFFFFFFFFFFFFF / size + 1 (fastmod, k_search.cu)
   uint32_t div_inv, div_shift, div_thr;   // divisibility by size (same_slot, k_search.cu)
@@ -70,6 +71,7 @@ struct SearchParams {
   mnemo_lastgroup_dev* last;     // [n_query_sigs]
   unsigned long long* stat_nodes;
   unsigned long long* stat_deep;
+  unsigned long long* stat_pairs;   // optional: pair-index entries visited (diagnostics)
 };
 
 size_t lsh_sort_temp_bytes(uint64_t n_sigs, uint32_t size);
@@ -78,6 +80,12 @@ cudaError_t launch_lsh_build(const uint8_t* sigs, uint64_t n_sigs, const uint32_
                              uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, void* temp, size_t temp_bytes,
                              uint32_t* ids, uint32_t* sig_entry, cudaStream_t st);
 void launch_search(const SearchParams& p, uint32_t n_query_sigs, cudaStream_t st);
+// pair-index path (k_pairprobe.cu): candidates from the pair index instead of the probed buckets
+void launch_search_pairs(const SearchParams& p, uint32_t n_query_sigs, cudaStream_t st);
+bool pair_index_possible(uint32_t size);
+cudaError_t launch_pair_build(const uint8_t* sigs, uint64_t n_sigs, uint32_t size, const uint32_t* ids, uint32_t* slots,
+                              uint32_t* ka, uint32_t* va, uint32_t* kb, uint32_t* vb, void* temp, unsigned long long* pairs,
+                              cudaStream_t st);
 void launch_search_compact(const uint32_t* acc_score, const uint32_t* acc_n, uint32_t n_queries, uint32_t n_entries,
                            uint32_t entry_base, CandDev* cands, uint32_t cap, uint32_t* total, uint32_t* q_base,
                            uint32_t* q_cnt, cudaStream_t st);

@@ -11,6 +11,15 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+@pytest.fixture(autouse=True, params=["buckets", "pairs"])
+def probe_path(request, monkeypatch):
+    """Every test runs twice: candidates by streaming the probed buckets (k_search.cu) and through the pair index
+    (k_pairprobe.cu, forced on for these small databases; query signatures with too many candidates for it are handed
+    back to the streaming kernel on the device)."""
+    monkeypatch.setenv("MNEMO_PAIR_INDEX", "1" if request.param == "pairs" else "0")
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def corpus(ctx):
     pcms = [synth.synth_track(4000 + i, 20.0 + 3 * (i % 4), 1 + (i % 2)) for i in range(12)]
@@ -34,9 +43,10 @@ def test_golden_search_results(ctx):
     db.close()
 
 
-def test_scores_and_stats_equal_oracle(ctx, oracle, corpus):
+def test_scores_and_stats_equal_oracle(ctx, oracle, corpus, probe_path):
     sigs, qs = corpus
     db = capi.Db(ctx, sigs)
+    assert db.has_pair_index == (probe_path == "pairs")
     odb = oracle.make_db(sigs)
     assert db.table_size == sum(len(s) for s in sigs) // 2           # lsh.c:61
     res, (L, D) = db.search(qs)
