@@ -31,6 +31,14 @@ class Match(C.Structure):
     _fields_ = [("entry", C.c_int32), ("score", C.c_float), ("n_matches", C.c_int32)]
 
 
+MATCH_DTYPE = np.dtype([("entry", "<i4"), ("score", "<f4"), ("n_matches", "<i4")])
+
+
+def _matches(out, n: int):
+    """ctypes Match array -> [(entry, score, n_matches)] (through numpy: a field access per element costs more than the search)."""
+    return np.frombuffer(out, dtype=MATCH_DTYPE, count=n).tolist() if n else []
+
+
 class Cand(C.Structure):
     _fields_ = [("query", C.c_uint32), ("entry", C.c_int32), ("score", C.c_float), ("n_matches", C.c_int32)]
 
@@ -179,7 +187,7 @@ class Context:
         out = (Match * max(nq, 1))()
         self._check(lib().mnemo_selftest_select(self.h, score.ctypes.data, n_matches.ctypes.data, nq, ne, entry_base, out),
                     "mnemo_selftest_select")
-        return [(out[i].entry, out[i].score, out[i].n_matches) for i in range(nq)]
+        return _matches(out, nq)
 
     # -- indexing -------------------------------------------------------------------
     def index_pcm_batch(self, pcms):
@@ -382,7 +390,7 @@ class Db:
         buf = qs if qs.shape[0] else np.zeros((1, SIG_LEN), np.uint8)
         rc = lib().mnemo_search_batch(self.h, buf.ctypes.data, qstart.ctypes.data, nq, out, stats)
         self.ctx._check(rc, "mnemo_search_batch")
-        return [(out[i].entry, out[i].score, out[i].n_matches) for i in range(nq)], (stats[0], stats[1])
+        return _matches(out, nq), (stats[0], stats[1])
 
     def scores(self, queries):
         """Dense per-entry rows of search.c:55-59 for a (small) batch: (score[nq, n_entries], n_matches[nq, n_entries]) u32."""
@@ -498,7 +506,7 @@ def select_merge_dev(ctx: Context, d_gathered_ptr: int, n_shards: int, n_nodes: 
     out = (Match * max(n_queries, 1))()
     rc = lib().mnemo_select_merge_dev(ctx.h, C.c_void_p(d_gathered_ptr), n_shards, n_nodes, nodes_per_shard, n_queries, out)
     ctx._check(rc, "mnemo_select_merge_dev")
-    return [(out[i].entry, out[i].score, out[i].n_matches) for i in range(n_queries)]
+    return _matches(out, n_queries)
 
 
 def select_merge(lists: np.ndarray, counts: np.ndarray):
@@ -510,7 +518,7 @@ def select_merge(lists: np.ndarray, counts: np.ndarray):
     rc = lib().mnemo_select_merge(lists.ctypes.data, counts.ctypes.data, n_nodes, nq, out)
     if rc != 0:
         raise MnemoError(f"mnemo_select_merge: {ERRORS.get(rc, rc)}")
-    return [(out[i].entry, out[i].score, out[i].n_matches) for i in range(nq)]
+    return _matches(out, nq)
 
 
 CAND_DTYPE = np.dtype([("query", "<u4"), ("entry", "<i4"), ("score", "<f4"), ("n_matches", "<i4")])
@@ -532,4 +540,4 @@ def search_finish(cands: np.ndarray, last_all: np.ndarray | None, n_shards: int,
                                    qstart.ctypes.data, nq, n_entries_total, out)
     if rc != 0:
         raise MnemoError(f"mnemo_search_finish: {ERRORS.get(rc, rc)}")
-    return [(out[i].entry, out[i].score, out[i].n_matches) for i in range(nq)]
+    return _matches(out, nq)

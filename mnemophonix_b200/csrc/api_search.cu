@@ -36,7 +36,7 @@ struct mnemo_db {
 
 enum {   // scratch slots
   kScrQ = 0, kScrQstart, kScrAccS, kScrAccN, kScrLast, kScrStats, kScrTotal, kScrQbase, kScrQcnt, kScrCands, kScrLeaf,
-  kScrSel, kScrSelCnt, kScrOut, kScrHas, kScrHasAll, kScrLists, kScrBack
+  kScrSel, kScrSelCnt, kScrOut, kScrHas, kScrHasAll, kScrLists, kScrBack, kScrTodo
 };
 
 static cudaError_t scratch_get(mnemo_db* db, int slot, uint64_t bytes, void** out) {
@@ -382,6 +382,8 @@ static int search_batch_impl(mnemo_db* db, const uint8_t* query_sigs, const uint
   TRY(scratch_get(db, kScrSel, sizeof(SelRec) * (uint64_t)grid * n_total, (void**)&d_sel));
   TRY(scratch_get(db, kScrSelCnt, (uint64_t)grid << depth, (void**)&d_cnt));
   TRY(scratch_get(db, kScrOut, sizeof(mnemo_match_dev) * (uint64_t)n_queries, (void**)&d_out));
+  uint32_t* d_todo = nullptr;
+  TRY(scratch_get(db, kScrTodo, 4ull * (b.tile + 1), (void**)&d_todo));
   if (lists_out) {
     TRY(scratch_get(db, kScrLists, list_bytes + 4ull * n_queries, (void**)&d_lists));
     d_counts = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(d_lists) + list_bytes);
@@ -392,7 +394,7 @@ static int search_batch_impl(mnemo_db* db, const uint8_t* query_sigs, const uint
     TRY(probe_tile(db, b, query_start, q0, nq));
     if (e != cudaSuccess) break;
     launch_search_select(b.d_acc_s, b.d_acc_n, nq, db->n_entries, db->entry_base, n_total, 0, depth, d_leaf, d_sel, d_cnt,
-                         select_grid(nq, ctx->sm_count), lists_out ? nullptr : d_out + q0,
+                         select_grid(nq, ctx->sm_count), d_todo, lists_out ? nullptr : d_out + q0,
                          lists_out ? d_lists + (uint64_t)q0 * kSelTop : nullptr, lists_out ? d_counts + q0 : nullptr, st);
     TRY(cudaGetLastError());
   }
@@ -746,6 +748,8 @@ extern "C" int mnemo_search_dense_lists_dev(mnemo_db* db, const uint8_t* d_has_a
   TRY(scratch_get(db, kScrLeaf, 4ull * leaf_stride * n_nodes, (void**)&d_leaf));
   TRY(scratch_get(db, kScrSel, sizeof(SelRec) * (uint64_t)grid * (max_n ? max_n : 1), (void**)&d_sel));
   TRY(scratch_get(db, kScrSelCnt, (uint64_t)grid << max_depth, (void**)&d_cnt));
+  uint32_t* d_todo = nullptr;
+  TRY(scratch_get(db, kScrTodo, 4ull * (n_queries + 1), (void**)&d_todo));
   uint32_t* d_qstart = (uint32_t*)db->scratch[kScrQstart].p;
   uint32_t* d_acc_s = (uint32_t*)db->scratch[kScrAccS].p;
   uint32_t* d_acc_n = (uint32_t*)db->scratch[kScrAccN].p;
@@ -762,7 +766,7 @@ extern "C" int mnemo_search_dense_lists_dev(mnemo_db* db, const uint8_t* d_has_a
     launch_select_bounds(n, depth, leaf, st);
     // tree over the node's own entries: position p <-> accumulator column (lo - entry_base) + p, global entry lo + p
     launch_search_select(d_acc_s + (lo - db->entry_base), d_acc_n + (lo - db->entry_base), n_queries, db->n_entries, 0, n, lo,
-                         depth, leaf, d_sel, d_cnt, grid, nullptr,
+                         depth, leaf, d_sel, d_cnt, grid, d_todo, nullptr,
                          reinterpret_cast<SelRec*>(d_lists_out) + (uint64_t)i * n_queries * kSelTop,
                          d_counts_out + (uint64_t)i * n_queries, st);
     TRY(cudaGetLastError());
@@ -949,17 +953,19 @@ extern "C" int mnemo_selftest_select(mnemo_ctx* ctx, const uint32_t* score, cons
   TRY(dalloc(&d_sel, (uint64_t)grid * n_total));
   TRY(dalloc(&d_cnt, (uint64_t)grid << depth));
   TRY(dalloc(&d_out, (uint64_t)n_queries));
+  uint32_t* d_todo = nullptr;
+  TRY(dalloc(&d_todo, (uint64_t)n_queries + 1));
   TRY(cudaMemcpyAsync(d_s, score, cells * 4, cudaMemcpyHostToDevice, st));
   TRY(cudaMemcpyAsync(d_n, n_matches, cells * 4, cudaMemcpyHostToDevice, st));
   if (e == cudaSuccess) {
     launch_select_bounds(n_total, depth, d_leaf, st);
-    launch_search_select(d_s, d_n, n_queries, n_entries, entry_base, n_total, 0, depth, d_leaf, d_sel, d_cnt, grid, d_out,
-                         nullptr, nullptr, st);
+    launch_search_select(d_s, d_n, n_queries, n_entries, entry_base, n_total, 0, depth, d_leaf, d_sel, d_cnt, grid, d_todo,
+                         d_out, nullptr, nullptr, st);
     e = cudaGetLastError();
   }
   TRY(cudaMemcpyAsync(out, d_out, sizeof(mnemo_match) * (uint64_t)n_queries, cudaMemcpyDeviceToHost, st));
   TRY(cudaStreamSynchronize(st));
-  void* ptrs[] = {d_s, d_n, d_leaf, d_sel, d_cnt, d_out};
+  void* ptrs[] = {d_s, d_n, d_leaf, d_sel, d_cnt, d_out, d_todo};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_selftest_select");

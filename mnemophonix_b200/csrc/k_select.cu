@@ -14,6 +14,9 @@
 // list lives at the start of its own index range in a per-CTA scratch that stays in L2 — and thread 0 applies the
 // thresholds to the root's list.  With a database sharded on node boundaries of this tree each shard ranks its own
 // subtree the same way and emits the list of its root (kSelTop records per query) instead.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 #include "search_internal.h"
 
@@ -46,13 +49,16 @@ __global__ void __launch_bounds__(kSelThreads)
     search_select_kernel(const uint32_t* __restrict__ acc_score, const uint32_t* __restrict__ acc_n, uint32_t n_queries,
                          uint32_t n_local, uint32_t first_local, uint32_t n_total, uint32_t entry_offset, uint32_t depth,
                          const uint32_t* __restrict__ leaf_lo, SelRec* __restrict__ scratch, uint8_t* __restrict__ cnt_scratch,
-                         mnemo_match_dev* __restrict__ out, SelRec* __restrict__ out_lists, uint32_t* __restrict__ out_counts) {
+                         const uint32_t* __restrict__ todo, mnemo_match_dev* __restrict__ out, SelRec* __restrict__ out_lists,
+                         uint32_t* __restrict__ out_counts) {
   const uint32_t n_leaves = 1u << depth;
+  if (todo) n_queries = todo[0];   // only the queries the sparse pass left over: todo[1 + i]
   SelRec* __restrict__ S = scratch + (uint64_t)blockIdx.x * n_total;
   uint8_t* __restrict__ Cn = cnt_scratch + (uint64_t)blockIdx.x * n_leaves;
   const uint32_t tid = threadIdx.x;
 
-  for (uint32_t q = blockIdx.x; q < n_queries; q += gridDim.x) {
+  for (uint32_t qi = blockIdx.x; qi < n_queries; qi += gridDim.x) {
+    const uint32_t q = todo ? todo[1 + qi] : qi;
     const uint32_t* __restrict__ rs = acc_score + (uint64_t)q * n_local;
     const uint32_t* __restrict__ rn = acc_n + (uint64_t)q * n_local;
     // leaves: one or two entries each; position p of the tree is accumulator column p - first_local
@@ -139,6 +145,294 @@ __global__ void __launch_bounds__(kSelThreads)
       }
     }
     __syncthreads();   // S / Cn are rewritten by the next query's leaves
+  }
+}
+
+// The same tree with everything in shared memory, for index ranges of up to kSmemSelMax positions (10 bytes each: the
+// average, the match count and a 16-bit position per list slot): the merges are chains of dependent reads and writes,
+// which cost a shared-memory round trip here instead of an L2 one.  The row is loaded once, coalesced; a node's list is
+// a list of positions at the start of the node's own range; the score of the few records that leave the kernel is
+// read again from the accumulator row.
+constexpr int kSmemSelThreads = 512;
+constexpr uint32_t kSmemSelMax = 20000;
+size_t select_smem_bytes(uint32_t n_total, uint32_t depth) {
+  return (size_t)n_total * 10 + ((size_t)1 << depth) + 32;
+}
+
+__global__ void __launch_bounds__(kSmemSelThreads)
+    search_select_smem_kernel(const uint32_t* __restrict__ acc_score, const uint32_t* __restrict__ acc_n, uint32_t n_queries,
+                              uint32_t n_local, uint32_t first_local, uint32_t n_total, uint32_t entry_offset, uint32_t depth,
+                              const uint32_t* __restrict__ leaf_lo, const uint32_t* __restrict__ todo,
+                              mnemo_match_dev* __restrict__ out, SelRec* __restrict__ out_lists,
+                              uint32_t* __restrict__ out_counts) {
+  extern __shared__ __align__(16) uint8_t sel_smem[];
+  float* const avg = reinterpret_cast<float*>(sel_smem);                      // [n_total]
+  uint32_t* const nn = reinterpret_cast<uint32_t*>(avg + n_total);            // [n_total]
+  uint16_t* const L = reinterpret_cast<uint16_t*>(nn + n_total);              // [n_total] lists of positions
+  uint8_t* const Cn = reinterpret_cast<uint8_t*>(L + n_total + (n_total & 1));   // [2^depth] list lengths
+  const uint32_t n_leaves = 1u << depth;
+  const uint32_t tid = threadIdx.x;
+  if (todo) n_queries = todo[0];
+  auto before = [&](uint32_t x, uint32_t y) { return cmp_entry_avg(avg[x], (int32_t)nn[x], avg[y], (int32_t)nn[y]) <= 0; };
+
+  for (uint32_t qi = blockIdx.x; qi < n_queries; qi += gridDim.x) {
+    const uint32_t q = todo ? todo[1 + qi] : qi;
+    const uint32_t* __restrict__ rs = acc_score + (uint64_t)q * n_local;
+    const uint32_t* __restrict__ rn = acc_n + (uint64_t)q * n_local;
+    for (uint32_t p = tid; p < n_total; p += kSmemSelThreads) {
+      const uint32_t col = p - first_local;   // wraps for p < first_local: fails the range test
+      const uint32_t n = col < n_local ? __ldg(rn + col) : 0u;
+      nn[p] = n;
+      avg[p] = n ? __fdiv_rn((float)__ldg(rs + col), (float)n) : 0.0f;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n_leaves; i += kSmemSelThreads) {   // leaves: one or two positions each
+      const uint32_t lo = __ldg(leaf_lo + i), hi = __ldg(leaf_lo + i + 1);
+      uint32_t c = 0, r0 = 0, r1 = 0;
+      for (uint32_t p = lo; p < hi; ++p)
+        if (nn[p]) {
+          if (c == 0) r0 = p;
+          else r1 = p;
+          ++c;
+        }
+      if (c == 2 && !before(r0, r1)) {
+        const uint32_t t = r0;
+        r0 = r1;
+        r1 = t;
+      }
+      if (c > 0) L[lo] = (uint16_t)r0;
+      if (c > 1) L[lo + 1] = (uint16_t)r1;
+      Cn[i] = (uint8_t)c;
+    }
+    __syncthreads();
+    for (int d = (int)depth - 1; d >= 0; --d) {
+      const uint32_t nodes = 1u << d, sh = depth - d;
+      for (uint32_t i = tid; i < nodes; i += kSmemSelThreads) {
+        const uint32_t a = i << sh, b = a + (1u << (sh - 1));
+        const uint32_t ca = Cn[a], cb = Cn[b];
+        if (cb == 0) continue;   // the left list is the node's list and already sits at the node's start
+        const uint32_t lo_a = __ldg(leaf_lo + a), lo_b = __ldg(leaf_lo + b);
+        if (ca == 0) {           // forward copy (destination below source)
+          for (uint32_t k = 0; k < cb; ++k) L[lo_a + k] = L[lo_b + k];
+          Cn[a] = (uint8_t)cb;
+          continue;
+        }
+        uint32_t A[kSelTop];     // outputs overwrite the left list's slots: buffer it
+#pragma unroll
+        for (int k = 0; k < kSelTop; ++k) A[k] = (uint32_t)k < ca ? L[lo_a + k] : 0u;
+        auto left = [&](uint32_t ia) {
+          uint32_t x = A[0];
+#pragma unroll
+          for (int k = 1; k < kSelTop; ++k)
+            if ((uint32_t)k == ia) x = A[k];
+          return x;
+        };
+        uint32_t ia = 0, ib = 0, w = 0;
+        uint32_t hb = L[lo_b], ha = A[0];
+        while (w < (uint32_t)kSelTop && ia < ca && ib < cb) {
+          if (before(ha, hb)) {
+            L[lo_a + w++] = (uint16_t)ha;
+            if (++ia < ca) ha = left(ia);
+          } else {
+            L[lo_a + w++] = (uint16_t)hb;   // slot lo_a + w <= lo_b + ib: never ahead of the unread part of the right list
+            if (++ib < cb) hb = L[lo_b + ib];
+          }
+        }
+        while (w < (uint32_t)kSelTop && ia < ca) {
+          L[lo_a + w++] = (uint16_t)ha;
+          if (++ia < ca) ha = left(ia);
+        }
+        while (w < (uint32_t)kSelTop && ib < cb) {
+          L[lo_a + w++] = (uint16_t)hb;
+          if (++ib < cb) hb = L[lo_b + ib];
+        }
+        Cn[a] = (uint8_t)w;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const uint32_t cnt = Cn[0];
+      mnemo_match_dev best = {-7, 0.0f, 0};
+      float best_avg = 0.0f;
+      if (out_lists) out_counts[q] = cnt;
+      for (uint32_t k = 0; k < cnt; ++k) {
+        const uint32_t p = L[k];
+        SelRec r;
+        r.entry = (int32_t)(entry_offset + p);
+        r.score = (float)__ldg(rs + (p - first_local));
+        r.n = (int32_t)nn[p];
+        r.avg = avg[p];
+        if (out_lists) {
+          out_lists[(uint64_t)q * kSelTop + k] = r;
+        } else if ((r.n >= 10 || (r.avg >= 35.0f && r.n >= 5)) && r.avg >= 30.0f && r.avg > best_avg) {   // search.c:173-185
+          best_avg = r.avg;
+          best.entry = r.entry;
+          best.score = r.score;
+          best.n_matches = r.n;
+        }
+      }
+      if (!out_lists) out[q] = best;
+    }
+    __syncthreads();   // the arrays are rewritten by the next query's row
+  }
+}
+
+// The usual case — a query matches far fewer entries than the database holds — does not need the dense tree.  One
+// CTA per query scans the accumulator row and keeps the matched entries, in ascending position, in shared memory, each
+// with its path in the merge tree (one bit per level: msort's n/2 | n - n/2 split, followed until every node holds one
+// entry).  The paths are sorted, so the matched entries under any node are a contiguous run found by bisection; level
+// by level, the first thread of every run merges the lists of the node's two children exactly as above — the node's
+// list (at most ten records) sits at the start of its run, left first on cmp <= 0 — and nothing outside shared memory
+// is touched.  Queries with more than `cap` matched entries are appended to todo[] for the dense kernel above.
+constexpr int kCompactThreads = 256;
+constexpr int kCompactCap = 2048;
+constexpr int kCompactU = 8;   // columns per lane and chunk: a warp scans 256 consecutive columns, the CTA 2048
+
+__global__ void __launch_bounds__(kCompactThreads)
+    search_select_compact_kernel(const uint32_t* __restrict__ acc_score, const uint32_t* __restrict__ acc_n, uint32_t n_queries,
+                                 uint32_t n_local, uint32_t first_local, uint32_t n_total, uint32_t entry_offset,
+                                 uint32_t levels, uint32_t cap, uint32_t* __restrict__ todo, mnemo_match_dev* __restrict__ out,
+                                 SelRec* __restrict__ out_lists, uint32_t* __restrict__ out_counts) {
+  __shared__ SelRec R[kCompactCap];
+  __shared__ uint32_t key[kCompactCap];
+  __shared__ uint8_t cnt[kCompactCap];
+  __shared__ uint32_t s_wcnt[2][kCompactThreads / 32];
+  constexpr int kWarps = kCompactThreads / 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t q = blockIdx.x;
+  const uint32_t* __restrict__ rs = acc_score + (uint64_t)q * n_local;
+  const uint32_t* __restrict__ rn = acc_n + (uint64_t)q * n_local;
+  const uint32_t n_cols = first_local >= n_total ? 0u : min(n_local, n_total - first_local);
+  uint32_t K = 0;
+  int par = 0;
+  for (uint32_t c0 = 0; c0 < n_cols; c0 += kCompactThreads * kCompactU, par ^= 1) {
+    const uint32_t w0 = c0 + warp * (32 * kCompactU);
+    uint32_t v[kCompactU];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int u = 0; u < kCompactU; ++u) {
+      const uint32_t col = w0 + u * 32 + lane;
+      v[u] = col < n_cols ? __ldg(rn + col) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < kCompactU; ++u) mine += __popc(__ballot_sync(0xffffffffu, v[u] != 0u));
+    if (lane == 0) s_wcnt[par][warp] = mine;
+    __syncthreads();   // one barrier per chunk: the counts alternate between two rows
+    uint32_t pos = K, total = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const uint32_t c = s_wcnt[par][w];
+      pos += w < warp ? c : 0u;
+      total += c;
+    }
+    K += total;
+    if (mine == 0) continue;
+#pragma unroll
+    for (int u = 0; u < kCompactU; ++u) {
+      const uint32_t m = __ballot_sync(0xffffffffu, v[u] != 0u);
+      const uint32_t at = pos + __popc(m & ((1u << lane) - 1u));
+      if (v[u] && at < cap) {
+        const uint32_t col = w0 + u * 32 + lane, p = first_local + col;
+        const float sc = (float)__ldg(rs + col);
+        SelRec r;
+        r.entry = (int32_t)(entry_offset + p);
+        r.score = sc;
+        r.n = (int32_t)v[u];
+        r.avg = __fdiv_rn(sc, (float)v[u]);
+        R[at] = r;
+        uint32_t path = 0, lo = 0, n = n_total;
+        for (uint32_t l = 0; l < levels; ++l) {
+          const uint32_t n1 = n >> 1;
+          if (p >= lo + n1) {
+            path = (path << 1) | 1u;
+            lo += n1;
+            n -= n1;
+          } else {
+            path <<= 1;
+            n = n1;
+          }
+        }
+        key[at] = path;
+        cnt[at] = 1;
+      }
+      pos += __popc(m);
+    }
+  }
+  if (K > cap) {   // uniform: every thread has the same K
+    if (tid == 0) todo[1 + atomicAdd(&todo[0], 1u)] = q;
+    return;
+  }
+  __syncthreads();
+  for (uint32_t sh = 1; sh <= levels && K > 1; ++sh) {
+    for (uint32_t a = tid; a < K; a += kCompactThreads) {
+      const uint32_t ka = key[a], node = ka >> sh;
+      if (a > 0 && (key[a - 1] >> sh) == node) continue;   // not the first matched entry under this node
+      if ((ka >> (sh - 1)) & 1u) continue;                  // nothing under the left child: the list is in place
+      // first matched entry under the right child: the left child holds at most 2^(sh-1) entries
+      const uint32_t right = ((node << 1) | 1u) << (sh - 1);
+      uint32_t lo = a + 1, hi = min(K, a + (1u << (sh - 1)));
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (key[mid] < right) lo = mid + 1;
+        else hi = mid;
+      }
+      const uint32_t b = lo;
+      if (b >= K || (key[b] >> sh) != node) continue;       // nothing under the right child
+      const uint32_t ca = cnt[a], cb = cnt[b];
+      SelRec A[kSelTop];   // outputs overwrite the left list's slots: buffer it
+#pragma unroll
+      for (int k = 0; k < kSelTop; ++k)
+        if ((uint32_t)k < ca) A[k] = R[a + k];
+      uint32_t ia = 0, ib = 0, w = 0;
+      SelRec hb = R[b];
+      while (w < (uint32_t)kSelTop && ia < ca && ib < cb) {
+        SelRec x = A[0];
+#pragma unroll
+        for (int k = 1; k < kSelTop; ++k)
+          if ((uint32_t)k == ia) x = A[k];
+        if (cmp_entry_avg(x.avg, x.n, hb.avg, hb.n) <= 0) {
+          R[a + w++] = x;
+          ++ia;
+        } else {
+          R[a + w++] = hb;   // slot a + w <= b + ib: never ahead of the unread part of the right list
+          if (++ib < cb) hb = R[b + ib];
+        }
+      }
+      while (w < (uint32_t)kSelTop && ia < ca) {
+        SelRec x = A[0];
+#pragma unroll
+        for (int k = 1; k < kSelTop; ++k)
+          if ((uint32_t)k == ia) x = A[k];
+        R[a + w++] = x;
+        ++ia;
+      }
+      while (w < (uint32_t)kSelTop && ib < cb) {
+        R[a + w++] = hb;
+        if (++ib < cb) hb = R[b + ib];
+      }
+      cnt[a] = (uint8_t)w;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const uint32_t c = K ? min((uint32_t)cnt[0], (uint32_t)kSelTop) : 0u;
+    if (out_lists) {
+      out_counts[q] = c;
+      for (uint32_t k = 0; k < c; ++k) out_lists[(uint64_t)q * kSelTop + k] = R[k];
+    } else {
+      mnemo_match_dev best = {-7, 0.0f, 0};   // search.c:173-185
+      float best_avg = 0.0f;
+      for (uint32_t k = 0; k < c; ++k) {
+        const SelRec r = R[k];
+        if ((r.n >= 10 || (r.avg >= 35.0f && r.n >= 5)) && r.avg >= 30.0f && r.avg > best_avg) {
+          best_avg = r.avg;
+          best.entry = r.entry;
+          best.score = r.score;
+          best.n_matches = r.n;
+        }
+      }
+      out[q] = best;
+    }
   }
 }
 
@@ -286,14 +580,48 @@ void launch_select_bounds(uint32_t n_total, uint32_t depth, uint32_t* leaf_lo, c
   select_bounds_kernel<<<(n + 255) / 256, 256, 0, st>>>(n_total, depth, leaf_lo);
 }
 
+// todo: n_queries + 1 words of device scratch (count, then the queries left to the dense kernel)
 void launch_search_select(const uint32_t* acc_score, const uint32_t* acc_n, uint32_t n_queries, uint32_t n_local,
                           uint32_t first_local, uint32_t n_total, uint32_t entry_offset, uint32_t depth,
-                          const uint32_t* leaf_lo, SelRec* scratch, uint8_t* cnt_scratch, uint32_t grid,
+                          const uint32_t* leaf_lo, SelRec* scratch, uint8_t* cnt_scratch, uint32_t grid, uint32_t* todo,
                           mnemo_match_dev* out, SelRec* out_lists, uint32_t* out_counts, cudaStream_t st) {
   if (!n_queries || !n_total) return;
-  search_select_kernel<<<grid, kSelThreads, 0, st>>>(acc_score, acc_n, n_queries, n_local, first_local, n_total,
-                                                     entry_offset, depth, leaf_lo, scratch, cnt_scratch, out, out_lists,
-                                                     out_counts);
+  const uint32_t cap = [] {   // test hook (read per call): 0 sends every query with a match to the dense kernel
+    const char* v = getenv("MNEMO_SELECT_CAP");
+    const long c = v ? atol(v) : kCompactCap;
+    return (uint32_t)(c < 0 ? 0 : c > kCompactCap ? kCompactCap : c);
+  }();
+  cudaMemsetAsync(todo, 0, 4, st);
+  // levels: until every node of the tree holds one entry (one more than the dense kernel's leaves of one or two)
+  search_select_compact_kernel<<<n_queries, kCompactThreads, 0, st>>>(
+      acc_score, acc_n, n_queries, n_local, first_local, n_total, entry_offset, depth + 1, cap, todo, out, out_lists,
+      out_counts);
+  if (n_total <= kSmemSelMax && getenv("MNEMO_SELECT_GLOBAL") == nullptr) {   // (test hook: the kernel for larger ranges)
+    const size_t smem = select_smem_bytes(n_total, depth);
+    cudaFuncSetAttribute(search_select_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)select_smem_bytes(kSmemSelMax, 14));
+    // as many CTAs as stay resident: one wave, every CTA takes the same number of queries (+-1)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(2048 / kSmemSelThreads, (227 * 1024) / (smem + 1024)));
+    grid = std::min<uint32_t>(n_queries, per_sm * (uint32_t)sms);
+    search_select_smem_kernel<<<grid, kSmemSelThreads, smem, st>>>(acc_score, acc_n, n_queries, n_local, first_local, n_total,
+                                                                   entry_offset, depth, leaf_lo, todo, out, out_lists,
+                                                                   out_counts);
+  } else {
+    search_select_kernel<<<grid, kSelThreads, 0, st>>>(acc_score, acc_n, n_queries, n_local, first_local, n_total,
+                                                       entry_offset, depth, leaf_lo, scratch, cnt_scratch, todo, out, out_lists,
+                                                       out_counts);
+  }
+
+  if (getenv("MNEMO_TRACE_SELECT")) {   // diagnostic: how many queries the dense kernel had to rank
+    uint32_t left = 0;
+    cudaMemcpyAsync(&left, todo, 4, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[mnemo] select: %u of %u queries ranked by the dense kernel (more than %u matched entries)\n", left,
+            n_queries, cap);
+  }
 }
 
 }  // namespace mnemo

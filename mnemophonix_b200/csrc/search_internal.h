@@ -106,7 +106,7 @@ void launch_select_bounds(uint32_t n_total, uint32_t depth, uint32_t* leaf_lo, c
 // per query; out_lists != nullptr: the root's list (kSelTop records per query) and its length instead.
 void launch_search_select(const uint32_t* acc_score, const uint32_t* acc_n, uint32_t n_queries, uint32_t n_local,
                           uint32_t first_local, uint32_t n_total, uint32_t entry_offset, uint32_t depth,
-                          const uint32_t* leaf_lo, SelRec* scratch, uint8_t* cnt_scratch, uint32_t grid,
+                          const uint32_t* leaf_lo, SelRec* scratch, uint8_t* cnt_scratch, uint32_t grid, uint32_t* todo,
                           mnemo_match_dev* out, SelRec* out_lists, uint32_t* out_counts, cudaStream_t st);
 
 }  // namespace mnemo

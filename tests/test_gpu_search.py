@@ -235,9 +235,17 @@ def _select_cases(rng, n_cases, sizes, max_m, avgs=None):
 
 
 @pytest.mark.gpu
-def test_gpu_ranking_equals_libc_qsort_on_dense_rows(ctx, oracle):
-    """The truncated merge tree of k_select.cu against the oracle's qsort over the dense per-entry array, exactly as
-    the reference sorts it (search.c:170): sparse, dense, more than ten candidates, sizes around powers of two."""
+@pytest.mark.parametrize("select_cap,global_tree", [(None, False), ("0", False), ("3", False), ("0", True)])
+def test_gpu_ranking_equals_libc_qsort_on_dense_rows(ctx, oracle, monkeypatch, select_cap, global_tree):
+    """The merge tree of k_select.cu against the oracle's qsort over the dense per-entry array, exactly as the
+    reference sorts it (search.c:170): sparse, dense, more than ten candidates, sizes around powers of two.
+    select_cap: rows with at most that many matched entries are ranked by the compacting kernel (default 2048), the
+    others by the dense tree kernel — 0 sends everything to the dense kernel, 3 splits the small cases between the two;
+    global_tree: the dense kernel for index ranges that do not fit shared memory instead of the shared-memory one."""
+    if select_cap is not None:
+        monkeypatch.setenv("MNEMO_SELECT_CAP", select_cap)
+    if global_tree:
+        monkeypatch.setenv("MNEMO_SELECT_GLOBAL", "1")
     rng = np.random.RandomState(11)
     cases = _select_cases(rng, 1500, [1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 16, 17, 31, 33, 37, 100, 257, 1000, 1023, 1025, 4099], 25)
     cases += _select_cases(rng, 300, [300, 301, 511, 640], 40, avgs=(30, 42))
