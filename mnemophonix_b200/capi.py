@@ -501,11 +501,15 @@ def shard_record_bytes(nodes_per_shard: int, n_queries: int) -> int:
     return int(lib().mnemo_shard_record_bytes(nodes_per_shard, n_queries))
 
 
-def select_merge_dev(ctx: Context, d_gathered_ptr: int, n_shards: int, n_nodes: int, nodes_per_shard: int, n_queries: int):
-    """Top levels of the ranking tree on the GPU over the all-gathered shard blocks (device memory)."""
+def select_merge_dev(ctx: Context, d_gathered_ptr: int, n_shards: int, n_nodes: int, nodes_per_shard: int, n_queries: int,
+                     as_array: bool = False):
+    """Top levels of the ranking tree on the GPU over the all-gathered shard blocks (device memory).
+    as_array: the answers as one MATCH_DTYPE array (the bytes the library wrote) instead of a list of tuples."""
     out = (Match * max(n_queries, 1))()
     rc = lib().mnemo_select_merge_dev(ctx.h, C.c_void_p(d_gathered_ptr), n_shards, n_nodes, nodes_per_shard, n_queries, out)
     ctx._check(rc, "mnemo_select_merge_dev")
+    if as_array:
+        return np.frombuffer(out, dtype=MATCH_DTYPE, count=n_queries).copy() if n_queries else np.zeros(0, MATCH_DTYPE)
     return _matches(out, n_queries)
 
 

@@ -23,6 +23,7 @@ struct mnemo_db {
   std::vector<uint32_t> h_entry_start;
   uint8_t* d_sigs = nullptr;
   uint32_t *d_entry_start = nullptr, *d_sig_entry = nullptr, *d_start = nullptr, *d_ids = nullptr;
+  uint32_t* d_rows = nullptr;              // with the pair index: the signatures again, one 128-byte aligned row each
   unsigned long long* d_pairs = nullptr;   // pair index (k_search.cu: launch_pair_build), 300 * n_sigs entries, or nullptr
   // scratch kept between search calls (grown on demand): cudaMalloc/cudaFree cost more than the kernels
   struct Scratch {
@@ -127,7 +128,7 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
   if (e == cudaSuccess && want_pairs && db->n_sigs && pair_index_possible(db->size)) {
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    const uint64_t need = db->n_sigs * 300ull * 8ull + db->n_sigs * (25ull + 24ull) * 4ull;   // index + the scratch not held yet
+    const uint64_t need = db->n_sigs * 300ull * 8ull + db->n_sigs * (25ull + 24ull + 32ull) * 4ull;   // index + the scratch not held yet
     if (need < free_b / 2) {
       uint32_t *d_slots = nullptr, *d_vals_out = nullptr;
       TRY(dalloc(&db->d_pairs, db->n_sigs * 300ull));
@@ -135,6 +136,10 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
       TRY(dalloc(&d_vals_out, db->n_sigs * kTables));
       TRY(launch_pair_build(db->d_sigs, db->n_sigs, db->size, db->d_ids, d_slots, d_keys_in, d_vals_in, d_keys_out, d_vals_out,
                             d_temp, db->d_pairs, st));
+      // the deep check reads whole signatures at random: 100-byte rows straddle three 64-byte DRAM bursts 56 % of
+      // the time, 128-byte aligned rows always take two
+      TRY(dalloc(&db->d_rows, db->n_sigs * 32ull));
+      if (e == cudaSuccess) launch_pad_rows(db->d_sigs, db->n_sigs, db->d_rows, st);
       TRY(cudaStreamSynchronize(st));
       cudaFree(d_slots);
       cudaFree(d_vals_out);
@@ -162,7 +167,7 @@ extern "C" void mnemo_db_destroy(mnemo_db* db) {
   if (!db) return;
   cudaSetDevice(db->ctx->device);
   cudaStreamSynchronize(db->ctx->stream);
-  void* ptrs[] = {db->d_sigs, db->d_entry_start, db->d_sig_entry, db->d_start, db->d_ids, db->d_pairs};
+  void* ptrs[] = {db->d_sigs, db->d_entry_start, db->d_sig_entry, db->d_start, db->d_ids, db->d_pairs, db->d_rows};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& sc : db->scratch)
@@ -186,6 +191,7 @@ static SearchParams base_params(const mnemo_db* db) {
   p.start = db->d_start;
   p.ids = db->d_ids;
   p.pairs = db->d_pairs;
+  p.rows128 = db->d_rows;
   p.size = db->size;
   p.size_magic = db->size ? 0xFFFFFFFFFFFFFFFFull / db->size + 1 : 0;
   if (db->size) {   // size = 2^shift * odd; inverse of the odd part modulo 2^32 by Newton's iteration
@@ -322,17 +328,26 @@ static cudaError_t probe_tile(mnemo_db* db, ProbeBatch& b, const uint32_t* query
     static const bool trace = getenv("MNEMO_TRACE_PAIRS") != nullptr;   // diagnostics: pair-index entries visited
     unsigned long long* d_vis = nullptr;
     if (trace) {
-      TRY(scratch_get(db, kScrBack, 8, (void**)&d_vis));
-      TRY(cudaMemsetAsync(d_vis, 0, 8, st));
+      TRY(scratch_get(db, kScrBack, 128, (void**)&d_vis));
+      TRY(cudaMemsetAsync(d_vis, 0, 128, st));
       if (e != cudaSuccess) return e;
     }
     p.stat_pairs = d_vis;
     launch_search_pairs(p, ns, st);
     if (trace) {
-      unsigned long long visited = 0;
-      cudaMemcpyAsync(&visited, d_vis, 8, cudaMemcpyDeviceToHost, st);
+      unsigned long long v[16] = {0};
+      cudaMemcpyAsync(v, d_vis, 128, cudaMemcpyDeviceToHost, st);
       cudaStreamSynchronize(st);
-      fprintf(stderr, "[mnemo] pair index: %.0f entries visited per query signature\n", (double)visited / ns);
+      fprintf(stderr,
+              "[mnemo] pair index, per query signature: %.0f entries visited in %.1f runs (%.1f longer than the sectors read "
+              "inline), %.1f pairs searched, %.1f sector probes; %.3f of the query signatures took id ranges; CTA cycles: %.0f "
+              "per one-pass signature (thread 0: %.0f own search, %.0f waiting for the others, %.0f flat pass, %.0f deep checks), "
+              "%.0f per id-range signature\n",
+              (double)v[0] / ns, (double)v[1] / ns, (double)v[2] / ns, (double)v[3] / ns, (double)v[4] / ns, (double)v[5] / ns,
+              (double)v[6] / std::max<double>(1.0, (double)ns - (double)v[5]),
+              (double)v[8] / std::max<double>(1.0, (double)ns - (double)v[5]), (double)v[9] / std::max<double>(1.0, (double)ns - (double)v[5]),
+              (double)v[10] / std::max<double>(1.0, (double)ns - (double)v[5]), (double)v[11] / std::max<double>(1.0, (double)ns - (double)v[5]),
+              (double)v[7] / std::max<double>(1.0, (double)v[5]));
     }
   } else {
     launch_search(p, ns, st);
@@ -788,12 +803,13 @@ extern "C" int mnemo_select_merge_dev(mnemo_ctx* ctx, const void* d_gathered, ui
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
   mnemo_match_dev* d_out = nullptr;
-  cudaError_t e = cudaMalloc((void**)&d_out, sizeof(mnemo_match_dev) * (uint64_t)n_queries);
+  // stream-ordered allocation: no device-wide synchronisation per tile (cudaFree has one)
+  cudaError_t e = cudaMallocAsync((void**)&d_out, sizeof(mnemo_match_dev) * (uint64_t)n_queries, st);
   if (e == cudaSuccess) launch_select_merge(d_gathered, n_shards, n_nodes, nodes_per_shard, n_queries, d_out, st);
   TRY(cudaGetLastError());
   TRY(cudaMemcpyAsync(out, d_out, sizeof(mnemo_match) * (uint64_t)n_queries, cudaMemcpyDeviceToHost, st));
+  if (d_out) cudaFreeAsync(d_out, st);
   TRY(cudaStreamSynchronize(st));
-  if (d_out) cudaFree(d_out);
   if (e != cudaSuccess) return mnemo_fail(ctx, e, "mnemo_select_merge_dev");
   return 0;
 }

@@ -116,15 +116,17 @@ __global__ void __launch_bounds__(kPairThreads, 3)
   uint32_t* const uniq = pp_dyn + kPairSetCap;   // [kPairUniqCap]
   __shared__ uint32_t seg_pos[kPairs];          // first entry of the run, relative to the pair's array
   __shared__ uint32_t seg_pref[kPairs + 1];     // exclusive prefix of the run lengths
-  __shared__ uint32_t q_begin[kTables], q_len[kTables], q_slot[kTables], q_word[kTables];
+  __shared__ uint32_t q_begin[kTables], q_len[kTables], q_slot[kTables];
+  __shared__ __align__(16) uint32_t q_word[kTables + 3];
   __shared__ uint32_t s_warp_tot[kPairThreads / 32];
-  __shared__ uint32_t s_nuniq, s_gmax, s_L, s_over;
+  __shared__ uint32_t s_nuniq, s_gmax, s_L, s_over, s_T;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t qs = blockIdx.x;
   const uint32_t n = p.n_sigs;
+  const long long t_begin = p.stat_pairs ? clock64() : 0;   // diagnostics
   const uint32_t* __restrict__ qwords = reinterpret_cast<const uint32_t*>(p.query_sigs) + (uint64_t)qs * kTables;
-  const uint32_t* __restrict__ dbw = reinterpret_cast<const uint32_t*>(p.db_sigs);
+  const uint32_t* __restrict__ dbw = p.rows128;   // 32 words per signature, 25 used
 
   if (warp == 0) {
     uint32_t len = 0, last = 0;
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
       s_gmax = gmax;
       s_nuniq = 0;
       s_over = 0;
+      s_T = 0;
     }
   }
   for (uint32_t i = tid; i < kPairSetCap; i += kPairThreads) set[i] = kPairEmpty;
@@ -157,19 +160,138 @@ __global__ void __launch_bounds__(kPairThreads, 3)
   }
   const uint32_t gmax = s_gmax;
 
-  // 2. one search (lower bound + run length) per table pair: thread `tid` owns pair `tid`
-  const float inv_size = 1.0f / (float)p.size;
+  // 2. one search per table pair: thread `tid` owns pair `tid`.  Probes are whole 32-byte sectors (four entries,
+  // aligned), in coordinates x = position in the pair's array + r where r makes x = 0 a sector boundary.  A sector
+  // holds the lower bound itself whenever its entries are not all on one side, which ends the search early; the run
+  // is then read two sectors at a time and its first entries go straight into the hash set.
+  const float inv_n = 1.0f / (float)n;
   const unsigned long long* run = nullptr;   // this thread's run of entries with (slot_i, slot_j) equal to the query's
-  uint32_t run_len = 0;
+  uint32_t run_len = 0, run_pos = 0;         // run_pos: relative to the pair's array
+  uint32_t rest_pos = 0, rest_len = 0;       // what the inline insertion below left for the flat pass
+  uint32_t d_probes = 0;                     // diagnostics
+  auto insert = [&](uint32_t g) {
+    uint32_t h = (g * 2246822519u) & (kPairSetCap - 1);
+    while (true) {
+      const uint32_t prev = atomicCAS(&set[h], kPairEmpty, g);
+      if (prev == g) break;
+      if (prev == kPairEmpty) {
+        const uint32_t pos = atomicAdd(&s_nuniq, 1u);
+        if (pos < kPairUniqCap) uniq[pos] = g;
+        else s_over = 1;
+        break;
+      }
+      if (*(volatile uint32_t*)&s_over) break;   // the set may be full by now: the range is taken again anyway
+      h = (h + 1) & (kPairSetCap - 1);
+    }
+  };
   if (tid < kPairs) {
     const int i = c_pair_i[tid], j = c_pair_j[tid];
     const uint32_t len_i = q_len[i];
     if (len_i && q_len[j]) {
-      const unsigned long long* __restrict__ slice = p.pairs + (uint64_t)tid * n + q_begin[i];
-      const uint32_t sj = q_slot[j];
-      const uint32_t lo = pp_lower_bound(slice, len_i, sj, inv_size);
-      run_len = pp_run_length(slice, len_i, lo, sj);
-      run = slice + lo;
+      const uint64_t base = (uint64_t)tid * n;
+      const uint32_t r = (uint32_t)(base & 3u);
+      const unsigned long long* __restrict__ P4 = p.pairs + (base - r);   // sector-aligned origin of the x coordinates
+      const uint32_t Bx = q_begin[i] + r, Ex = Bx + len_i, sj = q_slot[j];
+      // number of entries of sector w that sort before the lower bound (entries of other buckets count as -inf / +inf)
+      auto less_in = [&](uint32_t w, const ulonglong2 u, const ulonglong2 v) -> uint32_t {
+        const uint32_t x = 4u * w;
+        uint32_t c = 0;
+        c += (x + 0 < Bx || (x + 0 < Ex && (uint32_t)(u.x >> 32) < sj)) ? 1u : 0u;
+        c += (x + 1 < Bx || (x + 1 < Ex && (uint32_t)(u.y >> 32) < sj)) ? 1u : 0u;
+        c += (x + 2 < Bx || (x + 2 < Ex && (uint32_t)(v.x >> 32) < sj)) ? 1u : 0u;
+        c += (x + 3 < Bx || (x + 3 < Ex && (uint32_t)(v.y >> 32) < sj)) ? 1u : 0u;
+        return c;
+      };
+      uint32_t lo = Bx >> 2, hi = (Ex - 1) >> 2;   // lower bound >= 4 lo, <= 4 (hi + 1)
+      // first guess: the rank of bucket (j, slot_j) among all signatures — table j's CSR offset, already at hand — is the
+      // empirical distribution of slot_j, a far better predictor than a uniform spread when popular slots hold thousands
+      uint32_t w = (Bx + min((uint32_t)((float)q_begin[j] * inv_n * (float)len_i), len_i - 1)) >> 2;
+      uint32_t step = 1, lbx = 0;
+      int dir = 0;   // 0 first probe, +-1 galloping, 2 bisecting
+      bool found = false;
+      uint32_t probes = 0;
+      while (lo <= hi) {
+        ++probes;
+        const ulonglong2* q2 = reinterpret_cast<const ulonglong2*>(P4) + 2ull * w;
+        const ulonglong2 u = __ldg(q2), v = __ldg(q2 + 1);
+        const uint32_t c = less_in(w, u, v);
+        if (c > 0 && c < 4) {
+          lbx = 4u * w + c;
+          found = true;
+          break;
+        }
+        if (c == 4) {
+          lo = w + 1;
+          dir = dir == 0 ? 1 : dir == -1 ? 2 : dir;
+        } else {
+          if (w == lo) {
+            lbx = 4u * w;
+            found = true;
+            break;
+          }
+          hi = w - 1;
+          dir = dir == 0 ? -1 : dir == 1 ? 2 : dir;
+        }
+        if (lo > hi) break;
+        if (dir == 1) w = min(hi, lo + step - 1);
+        else if (dir == -1) w = hi - lo >= step - 1 ? hi - (step - 1) : lo;
+        else w = lo + ((hi - lo) >> 1);
+        step <<= 1;
+      }
+      if (!found) lbx = 4u * lo;
+      lbx = max(lbx, Bx);
+      d_probes = probes;
+      if (lbx < Ex) {
+        // the run: entries from lbx on whose slot_j equals sj.  Its sector is the one the search ended on (an L1 hit);
+        // the next sector is read only when the run reaches the end of this one — most pairs have no entry at all.
+        const uint32_t w0 = lbx >> 2;
+        const ulonglong2* q2 = reinterpret_cast<const ulonglong2*>(P4) + 2ull * w0;
+        uint32_t m = 0, x_end = min(Ex, 4u * w0 + 4u);
+        bool open = true;   // every entry looked at so far belongs to the run
+        {
+          const ulonglong2 e0 = __ldg(q2), e1 = __ldg(q2 + 1);
+          const unsigned long long ent[4] = {e0.x, e0.y, e1.x, e1.y};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t x = 4u * w0 + k;
+            if (x >= lbx && x < x_end && open) {
+              if ((uint32_t)(ent[k] >> 32) == sj) {
+                insert((uint32_t)ent[k]);
+                ++m;
+              } else {
+                open = false;
+              }
+            }
+          }
+        }
+        if (open && x_end < Ex) {
+          const ulonglong2 e0 = __ldg(q2 + 2), e1 = __ldg(q2 + 3);
+          const unsigned long long ent[4] = {e0.x, e0.y, e1.x, e1.y};
+          const uint32_t x0 = x_end;
+          x_end = min(Ex, x0 + 4u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t x = x0 + k;
+            if (x < x_end && open) {
+              if ((uint32_t)(ent[k] >> 32) == sj) {
+                insert((uint32_t)ent[k]);
+                ++m;
+              } else {
+                open = false;
+              }
+            }
+          }
+        }
+        run = P4 + lbx;
+        run_pos = lbx - r;
+        run_len = m;
+        if (open && x_end < Ex) {   // longer than the sectors read: the remainder goes through the flat pass
+          rest_len = pp_run_length(P4 + x_end, Ex - x_end, 0, sj);
+          rest_pos = x_end - r;
+          run_len += rest_len;
+        }
+
+      }
     }
   }
   // block-wide exclusive scan of this round's piece lengths -> flat index over the entries (seg_pos: where the piece
@@ -197,26 +319,80 @@ __global__ void __launch_bounds__(kPairThreads, 3)
     __syncthreads();
     return total;
   };
-  const uint32_t run_pos = run ? (uint32_t)(run - (p.pairs + (uint64_t)tid * n)) : 0u;
-  const uint32_t T = publish(run_pos, run_len);
-  if (tid == 0 && p.stat_pairs) atomicAdd(p.stat_pairs, (unsigned long long)T);
+  // flat pass: every thread takes entries of the published pieces, four loads in flight, and inserts their ids
+  auto insert_published = [&](uint32_t Tr) {
+    for (uint32_t t0 = tid; t0 < Tr; t0 += kPairThreads * 4) {
+      uint32_t g[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t t = t0 + u * kPairThreads;
+        g[u] = kPairEmpty;
+        if (t < Tr) {
+          uint32_t lo = 0, hi = kPairs;   // piece that holds flat index t: last pid with seg_pref[pid] <= t
+          while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (seg_pref[mid] <= t) lo = mid;
+            else hi = mid;
+          }
+          g[u] = (uint32_t)__ldg(p.pairs + (uint64_t)lo * n + seg_pos[lo] + (t - seg_pref[lo]));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (g[u] != kPairEmpty) insert(g[u]);
+    }
+  };
+  {
+    const uint32_t t_warp = __reduce_add_sync(0xffffffffu, run_len);
+    if (lane == 0 && t_warp) atomicAdd(&s_T, t_warp);
+  }
+  if (p.stat_pairs) {   // diagnostics: one atomic per warp and counter
+    const uint32_t a = __reduce_add_sync(0xffffffffu, run_len ? 1u : 0u), b = __reduce_add_sync(0xffffffffu, rest_len ? 1u : 0u);
+    const uint32_t c = __reduce_add_sync(0xffffffffu, d_probes ? 1u : 0u), d = __reduce_add_sync(0xffffffffu, d_probes);
+    if (lane == 0) {
+      atomicAdd(p.stat_pairs + 1, (unsigned long long)a);
+      atomicAdd(p.stat_pairs + 2, (unsigned long long)b);
+      atomicAdd(p.stat_pairs + 3, (unsigned long long)c);
+      atomicAdd(p.stat_pairs + 4, (unsigned long long)d);
+    }
+  }
+  const long long t_searched = p.stat_pairs ? clock64() : 0;
+  const uint32_t T_rest = publish(rest_pos, rest_len);   // (its barriers also order the inline insertions and s_T)
+  const long long t_published = p.stat_pairs ? clock64() : 0;
+  const uint32_t T = s_T;
+  // more entries than the list holds distinct ids: go straight to the id ranges below instead of filling the set in vain
+  const bool one_pass = T <= kPairUniqCap;   // (measured: trying up to 2x and falling back on overflow costs more than it saves)
+  if (one_pass) insert_published(T_rest);
+  __syncthreads();
+  const long long t_inserted = p.stat_pairs ? clock64() : 0;
+  if (tid == 0 && p.stat_pairs) {
+    atomicAdd(p.stat_pairs, (unsigned long long)T);
+    if (!one_pass) atomicAdd(p.stat_pairs + 5, 1ull);
+  }
   const uint32_t query = find_segment<uint32_t>(p.query_start, p.n_queries, qs);
   const uint32_t my_slot = lane < kTables ? q_slot[lane] : 0u, my_word = lane < kTables ? q_word[lane] : 0u;
   uint32_t deep = 0;
 
-  // 3.-4. The entries are de-duplicated and deep-checked one id range at a time.  T bounds the number of distinct
-  // candidates, so T <= kPairUniqCap (the usual case: T ~ 2000) is one round over all ids.  Otherwise the id space is cut
-  // into ranges: a run is sorted by id, so its piece inside a range is found by two short binary searches and a round
-  // only visits the entries of its range; a range whose distinct ids still do not fit the list is halved and taken
-  // again — nothing of it has been scored at that point — so there is no limit on the number of candidates.
+  // 3.-4. Usually that was all: the distinct candidates (T ~ 2000 entries, ~1500 ids) fit the list and are deep-checked
+  // in one go.  When they did not, the id space is cut into ranges: a run is sorted by id, so its piece inside a range
+  // is found by two short binary searches and a round only visits the entries of its range; a range whose distinct ids
+  // still do not fit the list is halved and taken again — nothing of it has been scored at that point — so there is
+  // no limit on the number of candidates.
   uint32_t span = n;
-  while (span > 1 && (uint64_t)T * span > (uint64_t)kPairUniqCap * n) span = (span + 1) >> 1;   // first guess: even spread
+  bool filled = one_pass && !s_over;   // the set and the list hold the whole id range
+  if (!filled)
+    while (span > 1 && (uint64_t)T * span > (uint64_t)kPairUniqCap * n) span = (span + 1) >> 1;   // first guess: even spread
+  if (!filled && span == n) span = (n + 1) >> 1;
+  __syncthreads();   // everyone has read s_over before a round clears it
   uint32_t id_lo = 0;
-  bool first = true;
   while (id_lo < n && T) {
     const uint32_t id_hi = (n - id_lo > span) ? id_lo + span : n;
-    uint32_t Tr = T;
-    if (!(id_lo == 0 && id_hi == n)) {
+    if (!filled) {
+      for (uint32_t i = tid; i < kPairSetCap; i += kPairThreads) set[i] = kPairEmpty;
+      if (tid == 0) {
+        s_nuniq = 0;
+        s_over = 0;
+      }
       // this round's piece of every run: ids in [id_lo, id_hi)
       uint32_t a = 0, b = 0;
       if (run_len) {
@@ -235,46 +411,16 @@ __global__ void __launch_bounds__(kPairThreads, 3)
         }
         b = lo;
       }
-      Tr = publish(run_pos + a, b - a);
-    }
-    if (!first) {   // the set was filled by the previous round
-      for (uint32_t i = tid; i < kPairSetCap; i += kPairThreads) set[i] = kPairEmpty;
-      if (tid == 0) {
-        s_nuniq = 0;
-        s_over = 0;
-      }
+      const uint32_t Tr = publish(run_pos + a, b - a);   // (barriers: the set is clear before anyone inserts)
+      insert_published(Tr);
       __syncthreads();
-    }
-    first = false;
-    for (uint32_t t = tid; t < Tr; t += kPairThreads) {
-      // run that holds flat index t: last pid with seg_pref[pid] <= t
-      uint32_t lo = 0, hi = kPairs;
-      while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (seg_pref[mid] <= t) lo = mid;
-        else hi = mid;
-      }
-      const uint32_t g = (uint32_t)__ldg(p.pairs + (uint64_t)lo * n + seg_pos[lo] + (t - seg_pref[lo]));
-      uint32_t h = (g * 2246822519u) & (kPairSetCap - 1);
-      while (true) {
-        const uint32_t prev = atomicCAS(&set[h], kPairEmpty, g);
-        if (prev == g) break;
-        if (prev == kPairEmpty) {
-          const uint32_t pos = atomicAdd(&s_nuniq, 1u);
-          if (pos < kPairUniqCap) uniq[pos] = g;
-          else s_over = 1;
-          break;
-        }
-        if (*(volatile uint32_t*)&s_over) break;   // the set may be full by now: the round is taken again anyway
-        h = (h + 1) & (kPairSetCap - 1);
+      if (s_over) {   // more distinct ids in this range than the list holds: halve it (a single id cannot overflow)
+        span = (span + 1) >> 1;
+        __syncthreads();   // everyone has read s_over before the next round clears it
+        continue;
       }
     }
-    __syncthreads();
-    if (s_over) {   // more distinct ids in this range than the list holds: halve it (a single id cannot overflow)
-      span = (span + 1) >> 1;
-      __syncthreads();   // everyone has read s_over before the next round clears it
-      continue;
-    }
+    filled = false;
     const uint32_t nuniq = s_nuniq;
     // deep checks, 32 signatures per warp at a time (see check_list in k_search.cu)
     for (uint32_t base = (uint32_t)warp * 32u; base < nuniq; base += kPairThreads) {
@@ -284,7 +430,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
         const uint32_t g = __shfl_sync(0xffffffffu, my_g, r);
-        w[r] = lane < kTables ? __ldg(dbw + (uint64_t)g * kTables + lane) : 0u;   // lanes >= 25 hold "equal" words
+        w[r] = lane < kTables ? __ldg(dbw + (uint64_t)g * 32u + lane) : 0u;   // lanes >= 25 hold "equal" words
       }
       uint32_t mine = 0;
 #pragma unroll
@@ -302,7 +448,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
         const uint32_t g = __shfl_sync(0xffffffffu, my_g, r);
         uint32_t hh = 0;
         if (lane < kTables)
-          hh = pp_same_slot(pp_bucket_key(__ldg(dbw + (uint64_t)g * kTables + lane)), my_slot, p.div_inv, p.div_shift, p.div_thr);
+          hh = pp_same_slot(pp_bucket_key(__ldg(dbw + (uint64_t)g * 32u + lane)), my_slot, p.div_inv, p.div_shift, p.div_thr);
         const uint32_t exact = __popc(__ballot_sync(0xffffffffu, hh));
         if (lane == r) hits = exact;
       }
@@ -323,7 +469,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
   if (warp == 0) {
     uint32_t h = 0, eq = 0;
     if (lane < kTables) {
-      const uint32_t w = __ldg(dbw + (uint64_t)gmax * kTables + lane);
+      const uint32_t w = __ldg(dbw + (uint64_t)gmax * 32u + lane);
       h = pp_same_slot(pp_bucket_key(w), q_slot[lane], p.div_inv, p.div_shift, p.div_thr);
       eq = 4u - pp_differing_bytes(w, q_word[lane]);
     }
@@ -331,11 +477,31 @@ __global__ void __launch_bounds__(kPairThreads, 3)
     const uint32_t score = __reduce_add_sync(0xffffffffu, eq);
     if (lane == 0) p.last[qs] = mnemo_lastgroup_dev{1u, gmax, hits, score};
   }
+  if (p.stat_pairs && tid == 0) {
+    const long long t_end = clock64();
+    atomicAdd(p.stat_pairs + (one_pass ? 6 : 7), (unsigned long long)(t_end - t_begin));
+    if (one_pass) {
+      atomicAdd(p.stat_pairs + 8, (unsigned long long)(t_searched - t_begin));      // thread 0: setup + its own search
+      atomicAdd(p.stat_pairs + 9, (unsigned long long)(t_published - t_searched));  // waiting for the slowest search
+      atomicAdd(p.stat_pairs + 10, (unsigned long long)(t_inserted - t_published));
+      atomicAdd(p.stat_pairs + 11, (unsigned long long)(t_end - t_inserted));
+    }
+  }
   deep = __reduce_add_sync(0xffffffffu, deep);
   if (lane == 0) {
     if (deep) atomicAdd(p.stat_deep, (unsigned long long)deep);
     if (warp == 0) atomicAdd(p.stat_nodes, (unsigned long long)L);
   }
+}
+
+__global__ void __launch_bounds__(256) pad_rows_kernel(const uint32_t* __restrict__ words, uint64_t n_sigs, uint32_t* __restrict__ rows) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_sigs * 32u) return;
+  const uint32_t k = (uint32_t)(t & 31u);
+  rows[t] = k < (uint32_t)kTables ? words[(t >> 5) * kTables + k] : 0u;
+}
+void launch_pad_rows(const uint8_t* sigs, uint64_t n_sigs, uint32_t* rows, cudaStream_t st) {
+  if (n_sigs) pad_rows_kernel<<<(unsigned)((n_sigs * 32u + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(sigs), n_sigs, rows);
 }
 
 static void pair_upload_constants() {

@@ -173,17 +173,29 @@ __global__ void __launch_bounds__(kSmemSelThreads)
   const uint32_t n_leaves = 1u << depth;
   const uint32_t tid = threadIdx.x;
   if (todo) n_queries = todo[0];
-  auto before = [&](uint32_t x, uint32_t y) { return cmp_entry_avg(avg[x], (int32_t)nn[x], avg[y], (int32_t)nn[y]) <= 0; };
+  auto before = [&](uint32_t x, uint32_t y) { return entry_before(avg[x], (int32_t)nn[x], avg[y], (int32_t)nn[y]); };
 
   for (uint32_t qi = blockIdx.x; qi < n_queries; qi += gridDim.x) {
     const uint32_t q = todo ? todo[1 + qi] : qi;
     const uint32_t* __restrict__ rs = acc_score + (uint64_t)q * n_local;
     const uint32_t* __restrict__ rn = acc_n + (uint64_t)q * n_local;
-    for (uint32_t p = tid; p < n_total; p += kSmemSelThreads) {
-      const uint32_t col = p - first_local;   // wraps for p < first_local: fails the range test
-      const uint32_t n = col < n_local ? __ldg(rn + col) : 0u;
-      nn[p] = n;
-      avg[p] = n ? __fdiv_rn((float)__ldg(rs + col), (float)n) : 0.0f;
+    for (uint32_t p0 = 0; p0 < n_total; p0 += kSmemSelThreads * 4) {   // eight independent loads per thread in flight
+      uint32_t n[4], sc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t col = p0 + u * kSmemSelThreads + tid - first_local;   // wraps below first_local: fails the range test
+        const bool in = p0 + u * kSmemSelThreads + tid < n_total && col < n_local;
+        n[u] = in ? __ldg(rn + col) : 0u;
+        sc[u] = in ? __ldg(rs + col) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t p = p0 + u * kSmemSelThreads + tid;
+        if (p < n_total) {
+          nn[p] = n[u];
+          avg[p] = n[u] ? __fdiv_rn((float)sc[u], (float)n[u]) : 0.0f;
+        }
+      }
     }
     __syncthreads();
     for (uint32_t i = tid; i < n_leaves; i += kSmemSelThreads) {   // leaves: one or two positions each
@@ -212,40 +224,35 @@ __global__ void __launch_bounds__(kSmemSelThreads)
         const uint32_t ca = Cn[a], cb = Cn[b];
         if (cb == 0) continue;   // the left list is the node's list and already sits at the node's start
         const uint32_t lo_a = __ldg(leaf_lo + a), lo_b = __ldg(leaf_lo + b);
-        if (ca == 0) {           // forward copy (destination below source)
-          for (uint32_t k = 0; k < cb; ++k) L[lo_a + k] = L[lo_b + k];
-          Cn[a] = (uint8_t)cb;
-          continue;
-        }
-        uint32_t A[kSelTop];     // outputs overwrite the left list's slots: buffer it
+        // The outputs stay in registers until the merge is over, so the left list is read in place although the
+        // node's list overwrites it.  The heads' averages and counts are kept in registers: a step reloads one head.
+        const uint32_t w = min((uint32_t)kSelTop, ca + cb);
+        uint32_t O[kSelTop];
+        uint32_t ia = 0, ib = 0;
+        uint32_t ha = ca ? L[lo_a] : 0u, hb = L[lo_b];
+        float ha_avg = avg[ha], hb_avg = avg[hb];
+        int32_t ha_n = (int32_t)nn[ha], hb_n = (int32_t)nn[hb];
 #pragma unroll
-        for (int k = 0; k < kSelTop; ++k) A[k] = (uint32_t)k < ca ? L[lo_a + k] : 0u;
-        auto left = [&](uint32_t ia) {
-          uint32_t x = A[0];
-#pragma unroll
-          for (int k = 1; k < kSelTop; ++k)
-            if ((uint32_t)k == ia) x = A[k];
-          return x;
-        };
-        uint32_t ia = 0, ib = 0, w = 0;
-        uint32_t hb = L[lo_b], ha = A[0];
-        while (w < (uint32_t)kSelTop && ia < ca && ib < cb) {
-          if (before(ha, hb)) {
-            L[lo_a + w++] = (uint16_t)ha;
-            if (++ia < ca) ha = left(ia);
-          } else {
-            L[lo_a + w++] = (uint16_t)hb;   // slot lo_a + w <= lo_b + ib: never ahead of the unread part of the right list
-            if (++ib < cb) hb = L[lo_b + ib];
+        for (int k = 0; k < kSelTop; ++k) {
+          if ((uint32_t)k < w) {
+            const bool take_a = ib >= cb || (ia < ca && entry_before(ha_avg, ha_n, hb_avg, hb_n));
+            O[k] = take_a ? ha : hb;
+            if (take_a) {
+              if (++ia < ca) {
+                ha = L[lo_a + ia];
+                ha_avg = avg[ha];
+                ha_n = (int32_t)nn[ha];
+              }
+            } else if (++ib < cb) {
+              hb = L[lo_b + ib];
+              hb_avg = avg[hb];
+              hb_n = (int32_t)nn[hb];
+            }
           }
         }
-        while (w < (uint32_t)kSelTop && ia < ca) {
-          L[lo_a + w++] = (uint16_t)ha;
-          if (++ia < ca) ha = left(ia);
-        }
-        while (w < (uint32_t)kSelTop && ib < cb) {
-          L[lo_a + w++] = (uint16_t)hb;
-          if (++ib < cb) hb = L[lo_b + ib];
-        }
+#pragma unroll
+        for (int k = 0; k < kSelTop; ++k)
+          if ((uint32_t)k < w) L[lo_a + k] = (uint16_t)O[k];
         Cn[a] = (uint8_t)w;
       }
       __syncthreads();

@@ -51,12 +51,26 @@ __host__ __device__ inline int cmp_entry_avg(float avg_a, int32_t n_a, float avg
   return 0;
 }
 
+// cmp_entry_avg(a, b) <= 0 ("a is emitted before b by a merge") in integer form: delta is the float of an integer, so
+// delta <= 3 is di <= 3 (delta <= 5 then holds) and (double)delta < 0.5 is di == 0.
+__host__ __device__ inline bool entry_before(float avg_a, int32_t n_a, float avg_b, int32_t n_b) {
+  int di = (int)(avg_a - avg_b);
+  if (di < 0) di = -di;
+  if (di <= 3) {
+    if (n_a >= n_b + 5) return true;
+    if (n_b >= n_a + 5) return false;
+    if (di == 0 && n_a != n_b) return n_a > n_b;
+  }
+  return !(avg_b > avg_a);
+}
+
 struct SearchParams {
   const uint8_t* db_sigs;        // [n_sigs][100]
   const uint32_t* sig_entry;     // [n_sigs] shard-local entry index
   const uint32_t* start;         // [25*size + 1] CSR offsets into ids
   const uint32_t* ids;           // [25*n_sigs]
   const unsigned long long* pairs;   // pair index [300*n_sigs] (slot_j << 32 | id), or nullptr (k_pairprobe.cu)
+  const uint32_t* rows128;           // with the pair index: signature g at words [32 g, 32 g + 25)
   uint32_t size;                 // lsh.c:61 (global)
   uint64_t size_magic;           // 0xFFFFFFFFFFFFFFFF / size + 1 (fastmod, k_search.cu)
   uint32_t div_inv, div_shift, div_thr;   // divisibility by size (same_slot, k_search.cu)
@@ -81,6 +95,7 @@ cudaError_t launch_lsh_build(const uint8_t* sigs, uint64_t n_sigs, const uint32_
                              uint32_t* ids, uint32_t* sig_entry, cudaStream_t st);
 void launch_search(const SearchParams& p, uint32_t n_query_sigs, cudaStream_t st);
 // pair-index path (k_pairprobe.cu): candidates from the pair index instead of the probed buckets
+void launch_pad_rows(const uint8_t* sigs, uint64_t n_sigs, uint32_t* rows, cudaStream_t st);
 void launch_search_pairs(const SearchParams& p, uint32_t n_query_sigs, cudaStream_t st);
 bool pair_index_possible(uint32_t size);
 cudaError_t launch_pair_build(const uint8_t* sigs, uint64_t n_sigs, uint32_t size, const uint32_t* ids, uint32_t* slots,

