@@ -62,6 +62,9 @@ def lib() -> C.CDLL:
         L.mnemo_create_ex.argtypes = [i32, vp, u32, C.POINTER(vp)]
         L.mnemo_spectra_mode.argtypes = [vp]
         L.mnemo_destroy.argtypes = [vp]
+        L.mnemo_host_alloc.argtypes = [vp, C.POINTER(vp), u64]
+        L.mnemo_host_free.argtypes = [vp, vp]
+        L.mnemo_host_free.restype = None
         L.mnemo_last_error.argtypes = [vp]
         L.mnemo_last_error.restype = C.c_char_p
         L.mnemo_logf_variant.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
@@ -167,6 +170,22 @@ class Context:
     def _check(self, rc, what):
         if rc != 0:
             raise MnemoError(f"{what}: {ERRORS.get(rc, rc)}: {lib().mnemo_last_error(self.h).decode()}")
+
+    def pinned(self, nbytes: int) -> np.ndarray:
+        """A page-locked host buffer (mnemo_host_alloc) as a uint8 array; freed when the array and its views are gone
+        (while this context is still open).  Copies from it run at the full host -> device rate, a pageable source is
+        staged by the driver at a third of that."""
+        import weakref
+        ptr = C.c_void_p()
+        self._check(lib().mnemo_host_alloc(self.h, C.byref(ptr), max(int(nbytes), 1)), "mnemo_host_alloc")
+        raw = (C.c_uint8 * max(int(nbytes), 1)).from_address(ptr.value)
+        ctx, addr = self, ptr.value
+
+        def release():
+            if ctx.h:
+                lib().mnemo_host_free(ctx.h, C.c_void_p(addr))
+        weakref.finalize(raw, release)
+        return np.ctypeslib.as_array(raw)[:nbytes]
 
     def logf_variant(self):
         p, m = C.c_uint32(), C.c_uint32()
@@ -376,9 +395,15 @@ class Db:
         return [tuple(x) for x in out[:min(n, cap)].tolist()]
 
     @staticmethod
-    def prepare(queries):
-        """Concatenate a list of [n,100] u8 arrays once; the result can be passed to search/search_shard."""
-        return _concat(queries)
+    def prepare(queries, ctx: "Context | None" = None):
+        """Concatenate a list of [n,100] u8 arrays once; the result can be passed to search/search_shard.
+        ctx: put the concatenated signatures into page-locked memory of that context (Context.pinned)."""
+        sigs, start = _concat(queries)
+        if ctx is not None and sigs.shape[0]:
+            buf = ctx.pinned(sigs.size).reshape(sigs.shape)
+            buf[...] = sigs
+            sigs = buf
+        return sigs, start
 
     def search(self, queries):
         """queries: list of [n,100] u8 arrays (or Db.prepare(list)).  Returns (results list of

@@ -77,7 +77,7 @@ def c4_search(ctx, stream, dev, rank: int, world: int, dist, n_tracks: int = 100
     order = [r * per + i for r in range(world) for i in range(own[r])]
     n_q = n_queries or n_tracks
     queries = [qdat[s, :qcnt[s]] for s in order][:n_q]
-    prepared = capi.Db.prepare(queries)
+    prepared = capi.Db.prepare(queries, ctx)          # page-locked: the upload runs at the H2D rate
     n_qsig = int(prepared[1][-1])
     n_local = torch.tensor([sum(len(s) for s in my_sigs)], dtype=torch.int64, device=dev)
     if dist is not None:

@@ -374,3 +374,16 @@ def test_device_resident_ranked_protocol_equals_single_database(ctx, corpus, mon
     assert set(one.phase_ms) == set(one.PHASES) and one.phase_ms["probe"] > 0
     one.close()
     ctx2.close()
+
+
+@pytest.mark.gpu
+def test_page_locked_query_buffer_gives_the_same_answers(ctx, corpus):
+    """Db.prepare(queries, ctx) puts the concatenated query signatures into page-locked memory (mnemo_host_alloc)."""
+    sigs, qs = corpus
+    db = capi.Db(ctx, sigs)
+    want, stats = db.search(qs)
+    pinned = capi.Db.prepare(qs, ctx)
+    got, stats2 = db.search(pinned)
+    assert got == want and stats2 == stats
+    del pinned
+    db.close()
