@@ -23,6 +23,7 @@ struct mnemo_db {
   std::vector<uint32_t> h_entry_start;
   uint8_t* d_sigs = nullptr;
   uint32_t *d_entry_start = nullptr, *d_sig_entry = nullptr, *d_start = nullptr, *d_ids = nullptr;
+  double expected_list_ids = 0;            // sum over buckets of len^2 / n_sigs (see mnemo_db_create)
   uint32_t* d_rows = nullptr;              // with the pair index: the signatures again, one 128-byte aligned row each
   unsigned long long* d_pairs = nullptr;   // pair index (k_search.cu: launch_pair_build), 300 * n_sigs entries, or nullptr
   // scratch kept between search calls (grown on demand): cudaMalloc/cudaFree cost more than the kernels
@@ -121,9 +122,20 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
   }
   TRY(cudaStreamSynchronize(st));
   // Pair index (k_pairprobe.cu): worth its memory (2400 bytes per signature) and build time once the bucket lists a
-  // query signature probes are long, i.e. for databases beyond a few hundred thousand signatures; MNEMO_PAIR_INDEX=1 / 0
-  // forces it on (tests run the small cases through it) / off.
-  bool want_pairs = db->n_sigs >= 200000;
+  // query signature probes are long.  What a query that resembles the database meets is sum(len^2) / n_sigs ids per
+  // table; measured on config #4's corpus cut to 380 k / 760 k / 1.52 M / 3.04 M signatures (L = 5.3 k / 10.6 k / 21 k /
+  // 42 k ids over the 25 tables) the streaming kernel is 1.4x faster / equal / 1.5x slower / 1.7x slower than the pair
+  // kernel, so the index is built from L = 12 k on.  MNEMO_PAIR_INDEX=1 / 0 forces it on (tests run the small cases
+  // through it) / off.
+  bool want_pairs = false;
+  if (e == cudaSuccess && db->size && db->n_sigs) {
+    unsigned long long sum_sq = 0, *d_sum = reinterpret_cast<unsigned long long*>(d_block_sums);   // (idle by now)
+    launch_bucket_load(db->d_start, n_slots, d_sum, st);
+    TRY(cudaMemcpyAsync(&sum_sq, d_sum, 8, cudaMemcpyDeviceToHost, st));
+    TRY(cudaStreamSynchronize(st));
+    db->expected_list_ids = (double)sum_sq / (double)db->n_sigs;
+    want_pairs = db->expected_list_ids >= 12000.0;
+  }
   if (const char* env = getenv("MNEMO_PAIR_INDEX")) want_pairs = atoi(env) > 0;
   if (e == cudaSuccess && want_pairs && db->n_sigs && pair_index_possible(db->size)) {
     size_t free_b = 0, total_b = 0;

@@ -341,6 +341,23 @@ static void radix_sort_pairs(uint32_t*& ka, uint32_t*& va, uint32_t*& kb, uint32
   }
 }
 
+// sum over all buckets of len^2: divided by the number of signatures it is the list length a query signature that
+// resembles the database meets in ONE table (a bucket is hit in proportion to its size)
+__global__ void __launch_bounds__(256) lsh_bucket_load_kernel(const uint32_t* __restrict__ start, uint64_t n_slots,
+                                                              unsigned long long* __restrict__ sum_sq) {
+  unsigned long long acc = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long len = start[i + 1] - start[i];
+    acc += len * len;
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(sum_sq, acc);
+}
+void launch_bucket_load(const uint32_t* start, uint64_t n_slots, unsigned long long* sum_sq, cudaStream_t st) {
+  cudaMemsetAsync(sum_sq, 0, 8, st);
+  if (n_slots) lsh_bucket_load_kernel<<<592, 256, 0, st>>>(start, n_slots, sum_sq);
+}
+
 bool pair_index_possible(uint32_t size) { return size > 0 && key_bits(size) + 5 <= 32; }
 uint32_t pair_index_row_base(int i) { return (uint32_t)(i * (2 * (kTables - 1) - i + 1) / 2); }   // pairs (a, .) with a < i
 

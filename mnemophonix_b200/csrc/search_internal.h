@@ -95,6 +95,7 @@ cudaError_t launch_lsh_build(const uint8_t* sigs, uint64_t n_sigs, const uint32_
                              uint32_t* ids, uint32_t* sig_entry, cudaStream_t st);
 void launch_search(const SearchParams& p, uint32_t n_query_sigs, cudaStream_t st);
 // pair-index path (k_pairprobe.cu): candidates from the pair index instead of the probed buckets
+void launch_bucket_load(const uint32_t* start, uint64_t n_slots, unsigned long long* sum_sq, cudaStream_t st);
 void launch_pad_rows(const uint8_t* sigs, uint64_t n_sigs, uint32_t* rows, cudaStream_t st);
 void launch_search_pairs(const SearchParams& p, uint32_t n_query_sigs, cudaStream_t st);
 bool pair_index_possible(uint32_t size);
