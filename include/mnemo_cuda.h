@@ -130,9 +130,10 @@ int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32_t* entry_s
 void mnemo_db_destroy(mnemo_db* db);
 uint32_t mnemo_db_table_size(const mnemo_db* db);
 /* 1 if the database carries the pair index (signatures ordered by the buckets of every pair of tables: candidates that share
- * two buckets with a query signature are looked up instead of found by streaming the 25 probed buckets).  Built for
- * databases of 200 000 signatures and more when device memory allows (2400 bytes per signature); the environment variable
- * MNEMO_PAIR_INDEX=1 / 0 forces it on / off.  Results are identical either way. */
+ * two buckets with a query signature are looked up instead of found by streaming the 25 probed buckets).  Built when
+ * the bucket load calls for it — sum over all buckets of len^2 / signatures, the number of ids a query signature that
+ * resembles the database meets in its 25 buckets, is 12 000 or more — and device memory allows (2400 + 128 bytes per
+ * signature); the environment variable MNEMO_PAIR_INDEX=1 / 0 forces it on / off.  Results are identical either way. */
 int mnemo_db_has_pair_index(const mnemo_db* db);
 
 typedef struct mnemo_match {
