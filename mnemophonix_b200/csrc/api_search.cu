@@ -31,6 +31,7 @@ struct mnemo_db {
     void* p = nullptr;
     uint64_t bytes = 0;
   } scratch[20];
+  uint32_t pair_cap = 4096;           // distinct candidates per round of the pair kernel; MNEMO_PAIR_CAP shrinks it (tests)
   uint32_t range_ids = 1u << 18;      // ids per pass of the probe's id-range mode; MNEMO_RANGE_IDS shrinks it (tests)
   uint64_t acc_budget = 1ull << 30;   // bytes of dense accumulators per query tile; MNEMO_ACC_BYTES shrinks it (tests)
   uint32_t dense_nq = 0, dense_nqs = 0;   // query batch held on the device between mnemo_search_dense_begin / _lists
@@ -83,6 +84,10 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
   if (const char* env = getenv("MNEMO_RANGE_IDS")) {   // test hook: many small id ranges on a small database
     const long v = atol(env);
     if (v > 0) db->range_ids = (uint32_t)std::min<long>(1L << 18, (v + 127) / 128 * 128);
+  }
+  if (const char* env = getenv("MNEMO_PAIR_CAP")) {   // test hook: id ranges, halving and widening in the pair kernel
+    const long v = atol(env);
+    if (v > 0) db->pair_cap = (uint32_t)std::min<long>(4096, v);
   }
   if (const char* env = getenv("MNEMO_ACC_BYTES")) {   // test hook: several query tiles on a small batch
     const long long v = atoll(env);
@@ -204,6 +209,7 @@ static SearchParams base_params(const mnemo_db* db) {
   p.ids = db->d_ids;
   p.pairs = db->d_pairs;
   p.rows128 = db->d_rows;
+  p.pair_cap = db->pair_cap;
   p.size = db->size;
   p.size_magic = db->size ? 0xFFFFFFFFFFFFFFFFull / db->size + 1 : 0;
   if (db->size) {   // size = 2^shift * odd; inverse of the odd part modulo 2^32 by Newton's iteration

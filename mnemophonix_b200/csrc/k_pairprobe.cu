@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
   // holds the lower bound itself whenever its entries are not all on one side, which ends the search early; the run
   // is then read two sectors at a time and its first entries go straight into the hash set.
   const float inv_n = 1.0f / (float)n;
+  const uint32_t cap = p.pair_cap;   // kPairUniqCap unless a test shrinks it
   const unsigned long long* run = nullptr;   // this thread's run of entries with (slot_i, slot_j) equal to the query's
   uint32_t run_len = 0, run_pos = 0;         // run_pos: relative to the pair's array
   uint32_t rest_pos = 0, rest_len = 0;       // what the inline insertion below left for the flat pass
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
       if (prev == g) break;
       if (prev == kPairEmpty) {
         const uint32_t pos = atomicAdd(&s_nuniq, 1u);
-        if (pos < kPairUniqCap) uniq[pos] = g;
+        if (pos < cap) uniq[pos] = g;
         else s_over = 1;
         break;
       }
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
   const long long t_published = p.stat_pairs ? clock64() : 0;
   const uint32_t T = s_T;
   // more entries than the list holds distinct ids: go straight to the id ranges below instead of filling the set in vain
-  const bool one_pass = T <= kPairUniqCap;   // (measured: trying up to 2x and falling back on overflow costs more than it saves)
+  const bool one_pass = T <= cap;   // (measured: trying up to 2x and falling back on overflow costs more than it saves)
   if (one_pass) insert_published(T_rest);
   __syncthreads();
   const long long t_inserted = p.stat_pairs ? clock64() : 0;
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
   uint32_t span = n;
   bool filled = one_pass && !s_over;   // the set and the list hold the whole id range
   if (!filled)
-    while (span > 1 && (uint64_t)T * span > (uint64_t)kPairUniqCap * n) span = (span + 1) >> 1;   // first guess: even spread
+    while (span > 1 && (uint64_t)T * span > (uint64_t)cap * n) span = (span + 1) >> 1;   // first guess: even spread
   if (!filled && span == n) span = (n + 1) >> 1;
   __syncthreads();   // everyone has read s_over before a round clears it
   uint32_t id_lo = 0;
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
       }
     }
     id_lo = id_hi;
-    if (nuniq < kPairUniqCap / 4 && span < n) span <<= 1;   // a sparse range: widen the next one again
+    if (nuniq < cap / 4 && span < n) span <<= 1;   // a sparse range: widen the next one again
     __syncthreads();   // uniq and the set are rewritten by the next round
   }
   // this shard's last group: bucket hits and score of the greatest candidate

@@ -71,6 +71,7 @@ struct SearchParams {
   const uint32_t* ids;           // [25*n_sigs]
   const unsigned long long* pairs;   // pair index [300*n_sigs] (slot_j << 32 | id), or nullptr (k_pairprobe.cu)
   const uint32_t* rows128;           // with the pair index: signature g at words [32 g, 32 g + 25)
+  uint32_t pair_cap;                 // distinct candidates the pair kernel lists per round (4096; MNEMO_PAIR_CAP shrinks it: tests)
   uint32_t size;                 // lsh.c:61 (global)
   uint64_t size_magic;           // 0xFFFFFFFFFFFFFFFF / size + 1 (fastmod, k_search.cu)
   uint32_t div_inv, div_shift, div_thr;   // divisibility by size (same_slot, k_search.cu)

@@ -11,12 +11,15 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.fixture(autouse=True, params=["buckets", "pairs"])
+@pytest.fixture(autouse=True, params=["buckets", "pairs", "pairs-cap5"])
 def probe_path(request, monkeypatch):
-    """Every test runs twice: candidates by streaming the probed buckets (k_search.cu) and through the pair index
-    (k_pairprobe.cu, forced on for these small databases; query signatures with too many candidates for it are handed
-    back to the streaming kernel on the device)."""
-    monkeypatch.setenv("MNEMO_PAIR_INDEX", "1" if request.param == "pairs" else "0")
+    """Every test runs three times: candidates by streaming the probed buckets (k_search.cu), through the pair index
+    (k_pairprobe.cu, forced on for these small databases), and through the pair index with room for five distinct
+    candidates per round, so that nearly every query signature goes through the id ranges (narrowing of the runs,
+    halving on overflow, widening after a sparse range) that only the heaviest ones need at full capacity."""
+    monkeypatch.setenv("MNEMO_PAIR_INDEX", "0" if request.param == "buckets" else "1")
+    if request.param == "pairs-cap5":
+        monkeypatch.setenv("MNEMO_PAIR_CAP", "5")
     return request.param
 
 
@@ -46,7 +49,7 @@ def test_golden_search_results(ctx):
 def test_scores_and_stats_equal_oracle(ctx, oracle, corpus, probe_path):
     sigs, qs = corpus
     db = capi.Db(ctx, sigs)
-    assert db.has_pair_index == (probe_path == "pairs")
+    assert db.has_pair_index == probe_path.startswith("pairs")
     odb = oracle.make_db(sigs)
     assert db.table_size == sum(len(s) for s in sigs) // 2           # lsh.c:61
     res, (L, D) = db.search(qs)
