@@ -151,7 +151,7 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
       TRY(dalloc(&db->d_pairs, db->n_sigs * 300ull));
       TRY(dalloc(&d_slots, db->n_sigs * kTables));
       TRY(dalloc(&d_vals_out, db->n_sigs * kTables));
-      TRY(launch_pair_build(db->d_sigs, db->n_sigs, db->size, db->d_ids, d_slots, d_keys_in, d_vals_in, d_keys_out, d_vals_out,
+      TRY(launch_pair_build(db->d_sigs, db->n_sigs, db->size, db->d_start, db->d_ids, d_slots, d_keys_in, d_vals_in, d_keys_out, d_vals_out,
                             d_temp, db->d_pairs, st));
       // the deep check reads whole signatures at random: 100-byte rows straddle three 64-byte DRAM bursts 56 % of
       // the time, 128-byte aligned rows always take two
@@ -208,6 +208,7 @@ static SearchParams base_params(const mnemo_db* db) {
   p.start = db->d_start;
   p.ids = db->d_ids;
   p.pairs = db->d_pairs;
+  p.pair_fbits = (uint32_t)pair_index_fbits(db->size);
   p.rows128 = db->d_rows;
   p.pair_cap = db->pair_cap;
   p.size = db->size;

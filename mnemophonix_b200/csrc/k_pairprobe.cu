@@ -42,73 +42,6 @@ __device__ __forceinline__ uint32_t pp_differing_bytes(uint32_t a, uint32_t b) {
   return __popc((((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u);
 }
 
-__device__ __forceinline__ uint32_t pp_key(const unsigned long long* __restrict__ slice, uint32_t i) {
-  return (uint32_t)(__ldg(slice + i) >> 32);
-}
-// First index in [0, len) whose slot_j is >= sj (len if none).  Slots are key % size of scrambled keys, close to uniform
-// over [0, size), so the search starts at the interpolated position and gallops outwards before it bisects: ~5 probes of
-// a slice that lives in DRAM instead of log2(len) ~ 13.
-__device__ __forceinline__ uint32_t pp_lower_bound(const unsigned long long* __restrict__ slice, uint32_t len, uint32_t sj,
-                                                   float inv_size) {
-  uint32_t pos = (uint32_t)((float)sj * inv_size * (float)len);
-  pos = min(pos, len - 1);
-  uint32_t lo, hi;   // invariant: key(lo - 1) < sj (or lo == 0), key(hi) >= sj (or hi == len)
-  if (pp_key(slice, pos) >= sj) {
-    hi = pos;
-    lo = 0;
-    uint32_t step = 1;
-    while (hi > 0) {
-      const uint32_t probe = hi > step ? hi - step : 0;
-      if (pp_key(slice, probe) < sj) {
-        lo = probe + 1;
-        break;
-      }
-      hi = probe;
-      step <<= 1;
-    }
-  } else {
-    lo = pos + 1;
-    hi = len;
-    uint32_t step = 1;
-    while (lo < len) {
-      const uint32_t probe = min(lo + step - 1, len - 1);
-      if (pp_key(slice, probe) >= sj) {
-        hi = probe;
-        break;
-      }
-      lo = probe + 1;
-      step <<= 1;
-    }
-  }
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (pp_key(slice, mid) < sj) lo = mid + 1;
-    else hi = mid;
-  }
-  return lo;
-}
-// length of the run of entries with slot_j == sj that starts at lb: gallop, then bisect (runs are short)
-__device__ __forceinline__ uint32_t pp_run_length(const unsigned long long* __restrict__ slice, uint32_t len, uint32_t lb,
-                                                  uint32_t sj) {
-  if (lb >= len || pp_key(slice, lb) != sj) return 0;
-  uint32_t lo = lb + 1, hi = len, step = 1;   // key(lo - 1) == sj; key(hi) > sj (or hi == len)
-  while (lo < len) {
-    const uint32_t probe = min(lo + step - 1, len - 1);
-    if (pp_key(slice, probe) > sj) {
-      hi = probe;
-      break;
-    }
-    lo = probe + 1;
-    step <<= 1;
-  }
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (pp_key(slice, mid) <= sj) lo = mid + 1;
-    else hi = mid;
-  }
-  return lo - lb;
-}
-
 __global__ void __launch_bounds__(kPairThreads, 3)
     search_pair_kernel(SearchParams p) {
   extern __shared__ __align__(16) uint32_t pp_dyn[];
@@ -166,6 +99,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
   // is then read two sectors at a time and its first entries go straight into the hash set.
   const float inv_n = 1.0f / (float)n;
   const uint32_t cap = p.pair_cap;   // kPairUniqCap unless a test shrinks it
+  const uint32_t fb = p.pair_fbits, rem_mask = (1u << fb) - 1u;
   const unsigned long long* run = nullptr;   // this thread's run of entries with (slot_i, slot_j) equal to the query's
   uint32_t run_len = 0, run_pos = 0;         // run_pos: relative to the pair's array
   uint32_t rest_pos = 0, rest_len = 0;       // what the inline insertion below left for the flat pass
@@ -197,10 +131,10 @@ __global__ void __launch_bounds__(kPairThreads, 3)
       auto less_in = [&](uint32_t w, const ulonglong2 u, const ulonglong2 v) -> uint32_t {
         const uint32_t x = 4u * w;
         uint32_t c = 0;
-        c += (x + 0 < Bx || (x + 0 < Ex && (uint32_t)(u.x >> 32) < sj)) ? 1u : 0u;
-        c += (x + 1 < Bx || (x + 1 < Ex && (uint32_t)(u.y >> 32) < sj)) ? 1u : 0u;
-        c += (x + 2 < Bx || (x + 2 < Ex && (uint32_t)(v.x >> 32) < sj)) ? 1u : 0u;
-        c += (x + 3 < Bx || (x + 3 < Ex && (uint32_t)(v.y >> 32) < sj)) ? 1u : 0u;
+        c += (x + 0 < Bx || (x + 0 < Ex && ((uint32_t)(u.x >> 32) >> fb) < sj)) ? 1u : 0u;
+        c += (x + 1 < Bx || (x + 1 < Ex && ((uint32_t)(u.y >> 32) >> fb) < sj)) ? 1u : 0u;
+        c += (x + 2 < Bx || (x + 2 < Ex && ((uint32_t)(v.x >> 32) >> fb) < sj)) ? 1u : 0u;
+        c += (x + 3 < Bx || (x + 3 < Ex && ((uint32_t)(v.y >> 32) >> fb) < sj)) ? 1u : 0u;
         return c;
       };
       uint32_t lo = Bx >> 2, hi = (Ex - 1) >> 2;   // lower bound >= 4 lo, <= 4 (hi + 1)
@@ -243,55 +177,48 @@ __global__ void __launch_bounds__(kPairThreads, 3)
       lbx = max(lbx, Bx);
       d_probes = probes;
       if (lbx < Ex) {
-        // the run: entries from lbx on whose slot_j equals sj.  Its sector is the one the search ended on (an L1 hit);
-        // the next sector is read only when the run reaches the end of this one — most pairs have no entry at all.
+        // the run: entries from lbx on whose slot_j equals sj.  Its first sector is the one the search ended on (an L1
+        // hit), and its first entry says how many follow (saturating field: a longer run is walked in hops of rem_mask
+        // entries), so the length costs no second search.  The next sector is read only when the run reaches into it.
         const uint32_t w0 = lbx >> 2;
         const ulonglong2* q2 = reinterpret_cast<const ulonglong2*>(P4) + 2ull * w0;
-        uint32_t m = 0, x_end = min(Ex, 4u * w0 + 4u);
-        bool open = true;   // every entry looked at so far belongs to the run
-        {
-          const ulonglong2 e0 = __ldg(q2), e1 = __ldg(q2 + 1);
-          const unsigned long long ent[4] = {e0.x, e0.y, e1.x, e1.y};
+        const ulonglong2 e0 = __ldg(q2), e1 = __ldg(q2 + 1);
+        const unsigned long long ent[4] = {e0.x, e0.y, e1.x, e1.y};
+        const uint32_t k0 = lbx & 3u;
+        const unsigned long long first = k0 == 0 ? ent[0] : k0 == 1 ? ent[1] : k0 == 2 ? ent[2] : ent[3];
+        if (((uint32_t)(first >> 32) >> fb) == sj) {
+          uint32_t pos = lbx, rem = (uint32_t)(first >> 32) & rem_mask;
+          while (rem == rem_mask) {
+            pos += rem_mask;
+            rem = (uint32_t)(__ldg(P4 + pos) >> 32) & rem_mask;
+          }
+          const uint32_t total = pos - lbx + rem + 1u, x_run = lbx + total;   // the run is [lbx, x_run)
+          uint32_t m = 0;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t x = 4u * w0 + k;
-            if (x >= lbx && x < x_end && open) {
-              if ((uint32_t)(ent[k] >> 32) == sj) {
-                insert((uint32_t)ent[k]);
-                ++m;
-              } else {
-                open = false;
-              }
+            if (x >= lbx && x < x_run) {
+              insert((uint32_t)ent[k]);
+              ++m;
             }
           }
-        }
-        if (open && x_end < Ex) {
-          const ulonglong2 e0 = __ldg(q2 + 2), e1 = __ldg(q2 + 3);
-          const unsigned long long ent[4] = {e0.x, e0.y, e1.x, e1.y};
-          const uint32_t x0 = x_end;
-          x_end = min(Ex, x0 + 4u);
+          if (x_run > 4u * w0 + 4u) {
+            const ulonglong2 f0 = __ldg(q2 + 2), f1 = __ldg(q2 + 3);
+            const unsigned long long nxt[4] = {f0.x, f0.y, f1.x, f1.y};
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t x = x0 + k;
-            if (x < x_end && open) {
-              if ((uint32_t)(ent[k] >> 32) == sj) {
-                insert((uint32_t)ent[k]);
+            for (int k = 0; k < 4; ++k) {
+              if (4u * w0 + 4u + k < x_run) {
+                insert((uint32_t)nxt[k]);
                 ++m;
-              } else {
-                open = false;
               }
             }
           }
+          run = P4 + lbx;
+          run_pos = lbx - r;
+          run_len = total;
+          rest_len = total - m;   // longer than the sectors read: the remainder goes through the flat pass
+          rest_pos = lbx + m - r;
         }
-        run = P4 + lbx;
-        run_pos = lbx - r;
-        run_len = m;
-        if (open && x_end < Ex) {   // longer than the sectors read: the remainder goes through the flat pass
-          rest_len = pp_run_length(P4 + x_end, Ex - x_end, 0, sj);
-          rest_pos = x_end - r;
-          run_len += rest_len;
-        }
-
       }
     }
   }

@@ -25,6 +25,7 @@
 //      buckets and >= 30 equal bytes add (score, 1) to the query's per-entry accumulators.
 // Traffic per query signature = 100 + 25*8 + 4*L + 100*D' bytes, D' = deep checks
 // plus the few bitmap false positives.
+#include <algorithm>
 #include "common.cuh"
 #include "search_internal.h"
 
@@ -312,14 +313,52 @@ __global__ void __launch_bounds__(256) pair_keys_kernel(const uint32_t* __restri
   vals[t] = id;
 }
 
+// entry = ((slot_j << fbits) | remaining) << 32 | id; `remaining` (entries that follow in the same run, saturated) is
+// filled in by pair_remaining_kernel
 __global__ void __launch_bounds__(256) pair_finalize_kernel(const uint32_t* __restrict__ sorted_ids, uint64_t n_elems,
-                                                            uint64_t n_sigs, const uint32_t* __restrict__ slots, int i,
+                                                            uint64_t n_sigs, const uint32_t* __restrict__ slots, int i, int fbits,
                                                             unsigned long long* __restrict__ out) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_elems) return;
   const uint32_t id = sorted_ids[t];
   const uint32_t j = (uint32_t)i + 1u + (uint32_t)(t / n_sigs);
-  out[t] = ((unsigned long long)slots[(uint64_t)j * n_sigs + id] << 32) | id;
+  out[t] = ((unsigned long long)(slots[(uint64_t)j * n_sigs + id] << fbits) << 32) | id;
+}
+
+// Runs: maximal stretches of entries with the same (pair, slot_i, slot_j).  A run starts where bucket (i, slot_i) starts
+// in the slice — table i's CSR offsets, the same in each of the row's slices — or where slot_j changes.
+__global__ void __launch_bounds__(256) pair_bucket_marks_kernel(const uint32_t* __restrict__ start_i, uint32_t size,
+                                                                uint64_t n_sigs, uint32_t base_i, uint32_t n_slices,
+                                                                uint32_t* __restrict__ flags) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)size * n_slices) return;
+  const uint32_t s = (uint32_t)(t % size), slice = (uint32_t)(t / size);
+  const uint32_t b = start_i[s], e = start_i[s + 1];
+  if (e > b) flags[(uint64_t)slice * n_sigs + (b - base_i)] = 1u;   // non-empty bucket: its first position
+}
+__global__ void __launch_bounds__(256) pair_flags_kernel(const unsigned long long* __restrict__ entries, uint64_t n_elems,
+                                                         int fbits, uint32_t* __restrict__ flags) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_elems) return;
+  if (t == 0 || ((uint32_t)(entries[t] >> 32) >> fbits) != ((uint32_t)(entries[t - 1] >> 32) >> fbits)) flags[t] = 1u;
+}
+// starts[r] = position of the first entry of run r; starts[n_runs] = n_elems
+__global__ void __launch_bounds__(256) pair_run_starts_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ excl,
+                                                              uint64_t n_elems, uint32_t* __restrict__ starts) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n_elems) return;
+  if (t == n_elems) starts[excl[n_elems]] = (uint32_t)n_elems;
+  else if (flags[t]) starts[excl[t]] = (uint32_t)t;
+}
+__global__ void __launch_bounds__(256) pair_remaining_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ excl,
+                                                             const uint32_t* __restrict__ starts, uint64_t n_elems, int fbits,
+                                                             unsigned long long* __restrict__ entries) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_elems) return;
+  const uint32_t run = excl[t] + flags[t] - 1u;
+  const uint32_t remaining = starts[run + 1] - (uint32_t)t - 1u;
+  const uint32_t cap = (1u << fbits) - 1u;
+  entries[t] |= (unsigned long long)(remaining < cap ? remaining : cap) << 32;
 }
 
 // stable LSD radix sort of n (key, value) pairs on the low `bits` bits of the key; the result is in (ka, va)
@@ -359,24 +398,41 @@ void launch_bucket_load(const uint32_t* start, uint64_t n_slots, unsigned long l
 }
 
 bool pair_index_possible(uint32_t size) { return size > 0 && key_bits(size) + 5 <= 32; }
+// bits of an entry's high word left of slot_j for the saturated remaining-run-length field (5 .. 12)
+int pair_index_fbits(uint32_t size) { return std::min(12, 32 - key_bits(size)); }
 uint32_t pair_index_row_base(int i) { return (uint32_t)(i * (2 * (kTables - 1) - i + 1) / 2); }   // pairs (a, .) with a < i
 
-// ids: the CSR id lists (25 n); slots: 25 n scratch; ka / va / kb / vb: 24 n scratch each; temp: lsh_sort_temp_bytes();
-// pairs: 300 n entries
-cudaError_t launch_pair_build(const uint8_t* sigs, uint64_t n_sigs, uint32_t size, const uint32_t* ids, uint32_t* slots,
-                              uint32_t* ka, uint32_t* va, uint32_t* kb, uint32_t* vb, void* temp, unsigned long long* pairs,
-                              cudaStream_t st) {
+// start: the CSR offsets (25 size + 1); ids: the CSR id lists (25 n); slots: 25 n scratch; ka / va / kb / vb: 25 n scratch
+// each; temp: lsh_sort_temp_bytes(); pairs: 300 n entries
+cudaError_t launch_pair_build(const uint8_t* sigs, uint64_t n_sigs, uint32_t size, const uint32_t* start, const uint32_t* ids,
+                              uint32_t* slots, uint32_t* ka, uint32_t* va, uint32_t* kb, uint32_t* vb, void* temp,
+                              unsigned long long* pairs, cudaStream_t st) {
   if (n_sigs == 0 || size == 0) return cudaSuccess;
   const uint64_t n_words = n_sigs * kTables;
   lsh_slot_table_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(sigs), n_sigs, size, slots);
-  const int sbits = key_bits(size);
+  const int sbits = key_bits(size), fbits = pair_index_fbits(size);
+  uint32_t* block_sums = reinterpret_cast<uint32_t*>(temp);
   for (int i = 0; i + 1 < kTables; ++i) {
-    const uint64_t n_elems = (uint64_t)(kTables - 1 - i) * n_sigs;
+    const uint32_t n_slices = (uint32_t)(kTables - 1 - i);
+    const uint64_t n_elems = (uint64_t)n_slices * n_sigs;
     const unsigned grid = (unsigned)((n_elems + 255) / 256);
     uint32_t *a = ka, *b = va, *c = kb, *d = vb;
+    unsigned long long* row = pairs + (uint64_t)pair_index_row_base(i) * n_sigs;
     pair_keys_kernel<<<grid, 256, 0, st>>>(ids + (uint64_t)(i + 1) * n_sigs, n_elems, n_sigs, slots + (uint64_t)i * n_sigs, sbits, a, b);
     radix_sort_pairs(a, b, c, d, n_elems, sbits + 5, temp, st);
-    pair_finalize_kernel<<<grid, 256, 0, st>>>(b, n_elems, n_sigs, slots, i, pairs + (uint64_t)pair_index_row_base(i) * n_sigs);
+    pair_finalize_kernel<<<grid, 256, 0, st>>>(b, n_elems, n_sigs, slots, i, fbits, row);
+    // remaining run lengths: flags (a) -> exclusive scan (c) -> run starts (d) -> field
+    cudaMemsetAsync(a, 0, n_elems * 4, st);
+    const uint64_t n_marks = (uint64_t)size * n_slices;
+    pair_bucket_marks_kernel<<<(unsigned)((n_marks + 255) / 256), 256, 0, st>>>(start + (uint64_t)i * size, size, n_sigs,
+                                                                               (uint32_t)((uint64_t)i * n_sigs), n_slices, a);
+    pair_flags_kernel<<<grid, 256, 0, st>>>(row, n_elems, fbits, a);
+    const uint32_t n_blocks = lsh_scan_blocks(n_elems);
+    scan_reduce_kernel<<<n_blocks, kScanT, 0, st>>>(a, n_elems, block_sums);
+    scan_sums_kernel<<<1, kScanT, 0, st>>>(block_sums, n_blocks);
+    scan_apply_kernel<<<n_blocks, kScanT, 0, st>>>(a, n_elems, block_sums, c, c);
+    pair_run_starts_kernel<<<(unsigned)((n_elems + 256) / 256), 256, 0, st>>>(a, c, n_elems, d);
+    pair_remaining_kernel<<<grid, 256, 0, st>>>(a, c, d, n_elems, fbits, row);
   }
   return cudaGetLastError();
 }

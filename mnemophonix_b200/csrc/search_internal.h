@@ -69,7 +69,8 @@ struct SearchParams {
   const uint32_t* sig_entry;     // [n_sigs] shard-local entry index
   const uint32_t* start;         // [25*size + 1] CSR offsets into ids
   const uint32_t* ids;           // [25*n_sigs]
-  const unsigned long long* pairs;   // pair index [300*n_sigs] (slot_j << 32 | id), or nullptr (k_pairprobe.cu)
+  const unsigned long long* pairs;   // pair index [300*n_sigs]: ((slot_j << pair_fbits) | remaining) << 32 | id, or nullptr
+  uint32_t pair_fbits;               // width of the saturated remaining-run-length field (k_search.cu: pair_remaining_kernel)
   const uint32_t* rows128;           // with the pair index: signature g at words [32 g, 32 g + 25)
   uint32_t pair_cap;                 // distinct candidates the pair kernel lists per round (4096; MNEMO_PAIR_CAP shrinks it: tests)
   uint32_t size;                 // lsh.c:61 (global)
@@ -100,9 +101,10 @@ void launch_bucket_load(const uint32_t* start, uint64_t n_slots, unsigned long l
 void launch_pad_rows(const uint8_t* sigs, uint64_t n_sigs, uint32_t* rows, cudaStream_t st);
 void launch_search_pairs(const SearchParams& p, uint32_t n_query_sigs, cudaStream_t st);
 bool pair_index_possible(uint32_t size);
-cudaError_t launch_pair_build(const uint8_t* sigs, uint64_t n_sigs, uint32_t size, const uint32_t* ids, uint32_t* slots,
-                              uint32_t* ka, uint32_t* va, uint32_t* kb, uint32_t* vb, void* temp, unsigned long long* pairs,
-                              cudaStream_t st);
+int pair_index_fbits(uint32_t size);
+cudaError_t launch_pair_build(const uint8_t* sigs, uint64_t n_sigs, uint32_t size, const uint32_t* start, const uint32_t* ids,
+                              uint32_t* slots, uint32_t* ka, uint32_t* va, uint32_t* kb, uint32_t* vb, void* temp,
+                              unsigned long long* pairs, cudaStream_t st);
 void launch_search_compact(const uint32_t* acc_score, const uint32_t* acc_n, uint32_t n_queries, uint32_t n_entries,
                            uint32_t entry_base, CandDev* cands, uint32_t cap, uint32_t* total, uint32_t* q_base,
                            uint32_t* q_cnt, cudaStream_t st);
