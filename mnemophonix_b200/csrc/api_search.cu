@@ -148,7 +148,7 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
     const uint64_t need = db->n_sigs * 300ull * 8ull + db->n_sigs * (25ull + 24ull + 32ull) * 4ull;   // index + the scratch not held yet
     if (need < free_b / 2) {
       uint32_t *d_slots = nullptr, *d_vals_out = nullptr;
-      TRY(dalloc(&db->d_pairs, db->n_sigs * 300ull));
+      TRY(dalloc(&db->d_pairs, db->n_sigs * 300ull + 8));   // + 8: the last probe window may reach past the last entry
       TRY(dalloc(&d_slots, db->n_sigs * kTables));
       TRY(dalloc(&d_vals_out, db->n_sigs * kTables));
       TRY(launch_pair_build(db->d_sigs, db->n_sigs, db->size, db->d_start, db->d_ids, d_slots, d_keys_in, d_vals_in, d_keys_out, d_vals_out,
