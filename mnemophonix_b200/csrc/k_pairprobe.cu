@@ -62,8 +62,9 @@ __global__ void __launch_bounds__(kPairThreads, 3)
   const uint32_t* __restrict__ qwords = reinterpret_cast<const uint32_t*>(p.query_sigs) + (uint64_t)qs * kTables;
   const uint32_t* __restrict__ dbw = p.rows128;   // 32 words per signature, 25 used
 
+  uint32_t last = 0;   // warp 0: greatest member of the lane's bucket; the load stays in flight until after the searches
   if (warp == 0) {
-    uint32_t len = 0, last = 0;
+    uint32_t len = 0;
     if (lane < kTables) {
       const uint32_t w = qwords[lane];
       const uint32_t slot = pp_fastmod(pp_bucket_key(w), p.size_magic, p.size);
@@ -76,10 +77,8 @@ __global__ void __launch_bounds__(kPairThreads, 3)
       if (len) last = __ldg(p.ids + e - 1);   // lists are sorted by id: the greatest member is the last one
     }
     const uint32_t L = __reduce_add_sync(0xffffffffu, len);
-    const uint32_t gmax = __reduce_max_sync(0xffffffffu, last);
     if (lane == 0) {
       s_L = L;
-      s_gmax = gmax;
       s_nuniq = 0;
       s_over = 0;
       s_T = 0;
@@ -92,7 +91,6 @@ __global__ void __launch_bounds__(kPairThreads, 3)
     if (tid == 0) p.last[qs] = mnemo_lastgroup_dev{0, 0, 0, 0};
     return;
   }
-  const uint32_t gmax = s_gmax;
 
   // 2. one search per table pair: thread `tid` owns pair `tid`.  Probes are whole 32-byte sectors (four entries,
   // aligned), in coordinates x = position in the pair's array + r where r makes x = 0 a sector boundary.  A sector
@@ -294,10 +292,15 @@ __global__ void __launch_bounds__(kPairThreads, 3)
       atomicAdd(p.stat_pairs + 4, (unsigned long long)d);
     }
   }
+  if (warp == 0) {   // the greatest candidate id: the group search.c:147-165 never scores
+    const uint32_t g = __reduce_max_sync(0xffffffffu, last);
+    if (lane == 0) s_gmax = g;
+  }
   const long long t_searched = p.stat_pairs ? clock64() : 0;
   const uint32_t T_rest = publish(rest_pos, rest_len);   // (its barriers also order the inline insertions and s_T)
   const long long t_published = p.stat_pairs ? clock64() : 0;
   const uint32_t T = s_T;
+  const uint32_t gmax = s_gmax;
   // more entries than the list holds distinct ids: go straight to the id ranges below instead of filling the set in vain
   const bool one_pass = T <= cap;   // (measured: trying up to 2x and falling back on overflow costs more than it saves)
   if (one_pass) insert_published(T_rest);
