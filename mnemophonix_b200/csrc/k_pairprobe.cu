@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
     while (span > 1 && (uint64_t)T * span > (uint64_t)cap * n) span = (span + 1) >> 1;   // first guess: even spread
   if (!filled && span == n) span = (n + 1) >> 1;
   __syncthreads();   // everyone has read s_over before a round clears it
-  uint32_t id_lo = 0;
+  uint32_t id_lo = 0, cur = 0, next_cur = 0;   // cur: this thread's first run entry with id >= id_lo
   while (id_lo < n && T) {
     const uint32_t id_hi = (n - id_lo > span) ? id_lo + span : n;
     if (!filled) {
@@ -334,24 +334,32 @@ __global__ void __launch_bounds__(kPairThreads, 3)
         s_nuniq = 0;
         s_over = 0;
       }
-      // this round's piece of every run: ids in [id_lo, id_hi)
-      uint32_t a = 0, b = 0;
-      if (run_len) {
-        uint32_t lo = 0, hi = run_len;
-        while (lo < hi) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if ((uint32_t)__ldg(run + mid) < id_lo) lo = mid + 1;
-          else hi = mid;
+      // this round's piece of every run: ids in [id_lo, id_hi).  The rounds walk the id space upwards, so the piece
+      // starts where the previous one ended (cur) and its end is found by galloping from there
+      uint32_t a = cur, b = cur;
+      if (cur < run_len) {
+        if (id_hi >= n) {
+          b = run_len;
+        } else {
+          uint32_t lo = cur, hi = run_len, step = 1;   // id(lo - 1) < id_hi (or lo == cur), id(hi) >= id_hi (or hi == run_len)
+          while (lo < run_len) {
+            const uint32_t probe = min(lo + step - 1, run_len - 1);
+            if ((uint32_t)__ldg(run + probe) >= id_hi) {
+              hi = probe;
+              break;
+            }
+            lo = probe + 1;
+            step <<= 1;
+          }
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((uint32_t)__ldg(run + mid) < id_hi) lo = mid + 1;
+            else hi = mid;
+          }
+          b = lo;
         }
-        a = lo;
-        hi = run_len;
-        while (lo < hi) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if ((uint32_t)__ldg(run + mid) < id_hi) lo = mid + 1;
-          else hi = mid;
-        }
-        b = lo;
       }
+      next_cur = b;
       const uint32_t Tr = publish(run_pos + a, b - a);   // (barriers: the set is clear before anyone inserts)
       insert_published(Tr);
       __syncthreads();
@@ -403,6 +411,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
       }
     }
     id_lo = id_hi;
+    cur = next_cur;
     if (nuniq < cap / 4 && span < n) span <<= 1;   // a sparse range: widen the next one again
     __syncthreads();   // uniq and the set are rewritten by the next round
   }
