@@ -24,6 +24,7 @@ struct mnemo_db {
   uint8_t* d_sigs = nullptr;
   uint32_t *d_entry_start = nullptr, *d_sig_entry = nullptr, *d_start = nullptr, *d_ids = nullptr;
   double expected_list_ids = 0;            // sum over buckets of len^2 / n_sigs (see mnemo_db_create)
+  uint32_t* d_dir = nullptr;               // with the pair index, memory allowing: run directory, 600 * n_sigs slots
   uint32_t* d_rows = nullptr;              // with the pair index: the signatures again, one 128-byte aligned row each
   unsigned long long* d_pairs = nullptr;   // pair index (k_search.cu: launch_pair_build), 300 * n_sigs entries, or nullptr
   // scratch kept between search calls (grown on demand): cudaMalloc/cudaFree cost more than the kernels
@@ -151,8 +152,12 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
       TRY(dalloc(&db->d_pairs, db->n_sigs * 300ull + 8));   // + 8: the last probe window may reach past the last entry
       TRY(dalloc(&d_slots, db->n_sigs * kTables));
       TRY(dalloc(&d_vals_out, db->n_sigs * kTables));
+      // run directory (one probe instead of a search per pair): as much memory again as the index; MNEMO_PAIR_DIR=0 / 1
+      bool want_dir = need + db->n_sigs * 2400ull < free_b / 2;
+      if (const char* env = getenv("MNEMO_PAIR_DIR")) want_dir = atoi(env) > 0;
+      if (want_dir) TRY(dalloc(&db->d_dir, db->n_sigs * 600ull));
       TRY(launch_pair_build(db->d_sigs, db->n_sigs, db->size, db->d_start, db->d_ids, d_slots, d_keys_in, d_vals_in, d_keys_out, d_vals_out,
-                            d_temp, db->d_pairs, st));
+                            d_temp, db->d_pairs, db->d_dir, st));
       // the deep check reads whole signatures at random: 100-byte rows straddle three 64-byte DRAM bursts 56 % of
       // the time, 128-byte aligned rows always take two
       TRY(dalloc(&db->d_rows, db->n_sigs * 32ull));
@@ -184,7 +189,7 @@ extern "C" void mnemo_db_destroy(mnemo_db* db) {
   if (!db) return;
   cudaSetDevice(db->ctx->device);
   cudaStreamSynchronize(db->ctx->stream);
-  void* ptrs[] = {db->d_sigs, db->d_entry_start, db->d_sig_entry, db->d_start, db->d_ids, db->d_pairs, db->d_rows};
+  void* ptrs[] = {db->d_sigs, db->d_entry_start, db->d_sig_entry, db->d_start, db->d_ids, db->d_pairs, db->d_rows, db->d_dir};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& sc : db->scratch)
@@ -209,6 +214,7 @@ static SearchParams base_params(const mnemo_db* db) {
   p.ids = db->d_ids;
   p.pairs = db->d_pairs;
   p.pair_fbits = (uint32_t)pair_index_fbits(db->size);
+  p.pair_dir = db->d_dir;
   p.rows128 = db->d_rows;
   p.pair_cap = db->pair_cap;
   p.size = db->size;

@@ -144,44 +144,77 @@ __global__ void __launch_bounds__(kPairThreads, 3)
         for (int k = 0; k < kWin; ++k) c += (x + k < Bx || (x + k < Ex && ((uint32_t)(e[k] >> 32) >> fb) < sj)) ? 1u : 0u;
         return c;
       };
-      uint32_t lo = Bx / kWin, hi = (Ex - 1) / kWin;   // lower bound >= kWin lo, <= kWin (hi + 1)
-      // first guess: the rank of bucket (j, slot_j) among all signatures — table j's CSR offset, already at hand — is the
-      // empirical distribution of slot_j, a far better predictor than a uniform spread when popular slots hold thousands
-      uint32_t w = (Bx + min((uint32_t)((float)q_begin[j] * inv_n * (float)len_i), len_i - 1)) / kWin;
-      uint32_t step = 1, lbx = 0;
-      int dir = 0;   // 0 first probe, +-1 galloping, 2 bisecting
+      uint32_t w = 0, lbx = Ex, probes = 0;   // lbx: x of the first entry >= sj (sorted search) / of the run (directory); Ex: none
       bool found = false;
-      uint32_t probes = 0;
       unsigned long long ent[kWin];
-      while (lo <= hi) {
-        ++probes;
-        load_win(w, ent);
-        const uint32_t c = less_in(w, ent);
-        if (c > 0 && c < kWin) {
-          lbx = kWin * w + c;
-          found = true;
-          break;
+      if (p.pair_dir) {
+        // Run directory: the slot for (slice, slot_i, slot_j) holds the position of the run's first entry in row i's
+        // array, if the run exists.  Linear probing; a stranger in the chain is told by its position (outside this
+        // bucket of this slice) or, inside the bucket, by the slot_j of the entry it points to.
+        const uint32_t slice = (uint32_t)(j - i - 1), n_slices = (uint32_t)(kTables - 1 - i);
+        const uint32_t* __restrict__ dir_i = p.pair_dir + 2ull * (uint64_t)(tid - slice) * n;   // tid - slice = pairs before row i
+        const uint32_t capacity = 2u * n_slices * n;
+        const uint32_t t_lo = slice * n + q_begin[i];   // bucket (i, slot_i) of this slice in the row's array
+        uint32_t idx = pair_dir_slot(pair_dir_hash(slice, q_slot[i], sj), capacity);
+        while (true) {
+          ++probes;
+          const uint32_t v = __ldg(dir_i + idx);
+          if (v == 0xFFFFFFFFu) break;
+          if (v - t_lo < len_i) {
+            const uint32_t x = v - slice * n + r;
+            ++probes;
+            load_win(x / kWin, ent);
+            unsigned long long e = ent[0];
+#pragma unroll
+            for (int k = 1; k < (int)kWin; ++k)
+              if ((uint32_t)k == (x & (kWin - 1))) e = ent[k];
+            if (((uint32_t)(e >> 32) >> fb) == sj) {
+              lbx = x;
+              w = x / kWin;
+              found = true;
+              break;
+            }
+          }
+          idx = idx + 1 == capacity ? 0 : idx + 1;
         }
-        if (c == kWin) {
-          lo = w + 1;
-          dir = dir == 0 ? 1 : dir == -1 ? 2 : dir;
-        } else {
-          if (w == lo) {
-            lbx = kWin * w;
+      } else {
+        uint32_t lo = Bx / kWin, hi = (Ex - 1) / kWin;   // lower bound >= kWin lo, <= kWin (hi + 1)
+        // first guess: the rank of bucket (j, slot_j) among all signatures — table j's CSR offset, already at hand — is the
+        // empirical distribution of slot_j, a far better predictor than a uniform spread when popular slots hold thousands
+        w = (Bx + min((uint32_t)((float)q_begin[j] * inv_n * (float)len_i), len_i - 1)) / kWin;
+        uint32_t step = 1;
+        lbx = 0;
+        int dir = 0;   // 0 first probe, +-1 galloping, 2 bisecting
+        while (lo <= hi) {
+          ++probes;
+          load_win(w, ent);
+          const uint32_t c = less_in(w, ent);
+          if (c > 0 && c < kWin) {
+            lbx = kWin * w + c;
             found = true;
             break;
           }
-          hi = w - 1;
-          dir = dir == 0 ? -1 : dir == 1 ? 2 : dir;
+          if (c == kWin) {
+            lo = w + 1;
+            dir = dir == 0 ? 1 : dir == -1 ? 2 : dir;
+          } else {
+            if (w == lo) {
+              lbx = kWin * w;
+              found = true;
+              break;
+            }
+            hi = w - 1;
+            dir = dir == 0 ? -1 : dir == 1 ? 2 : dir;
+          }
+          if (lo > hi) break;
+          if (dir == 1) w = min(hi, lo + step - 1);
+          else if (dir == -1) w = hi - lo >= step - 1 ? hi - (step - 1) : lo;
+          else w = lo + ((hi - lo) >> 1);
+          step <<= 1;
         }
-        if (lo > hi) break;
-        if (dir == 1) w = min(hi, lo + step - 1);
-        else if (dir == -1) w = hi - lo >= step - 1 ? hi - (step - 1) : lo;
-        else w = lo + ((hi - lo) >> 1);
-        step <<= 1;
+        if (!found) lbx = kWin * lo;
+        lbx = max(lbx, Bx);
       }
-      if (!found) lbx = kWin * lo;
-      lbx = max(lbx, Bx);
       d_probes = probes;
       if (lbx < Ex) {
         // the run: entries from lbx on whose slot_j equals sj.  Its first window is usually the one the search ended on

@@ -397,6 +397,22 @@ void launch_bucket_load(const uint32_t* start, uint64_t n_slots, unsigned long l
   if (n_slots) lsh_bucket_load_kernel<<<592, 256, 0, st>>>(start, n_slots, sum_sq);
 }
 
+// Run directory: one open-addressing table per row i (all slices j > i together), two slots per index entry, mapping
+// (slice, slot_i, slot_j) -> position of the run's first entry in the row's array.  A slot holds only that position:
+// the probe kernel recognises its run by the position lying inside bucket (i, slot_i) of its slice and by the slot_j
+// of the entry found there (search_internal.h: pair_dir_hash).  Built from the run starts of the remaining-length pass.
+__global__ void __launch_bounds__(256) pair_dir_insert_kernel(const unsigned long long* __restrict__ entries,
+                                                              const uint32_t* __restrict__ flags, uint64_t n_elems,
+                                                              uint64_t n_sigs, const uint32_t* __restrict__ slots_i, int fbits,
+                                                              uint32_t* __restrict__ dir, uint32_t capacity) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_elems || !flags[t]) return;
+  const unsigned long long e = entries[t];
+  const uint32_t slice = (uint32_t)(t / n_sigs);
+  uint32_t idx = pair_dir_slot(pair_dir_hash(slice, slots_i[(uint32_t)e], (uint32_t)(e >> 32) >> fbits), capacity);
+  while (atomicCAS(&dir[idx], 0xFFFFFFFFu, (uint32_t)t) != 0xFFFFFFFFu) idx = idx + 1 == capacity ? 0 : idx + 1;
+}
+
 bool pair_index_possible(uint32_t size) { return size > 0 && key_bits(size) + 5 <= 32; }
 // bits of an entry's high word left of slot_j for the saturated remaining-run-length field (5 .. 12)
 int pair_index_fbits(uint32_t size) { return std::min(12, 32 - key_bits(size)); }
@@ -404,9 +420,10 @@ uint32_t pair_index_row_base(int i) { return (uint32_t)(i * (2 * (kTables - 1) -
 
 // start: the CSR offsets (25 size + 1); ids: the CSR id lists (25 n); slots: 25 n scratch; ka / va / kb / vb: 25 n scratch
 // each; temp: lsh_sort_temp_bytes(); pairs: 300 n entries
+// dir: 600 n slots (or nullptr: no directory, the probe kernel searches the sorted slices)
 cudaError_t launch_pair_build(const uint8_t* sigs, uint64_t n_sigs, uint32_t size, const uint32_t* start, const uint32_t* ids,
                               uint32_t* slots, uint32_t* ka, uint32_t* va, uint32_t* kb, uint32_t* vb, void* temp,
-                              unsigned long long* pairs, cudaStream_t st) {
+                              unsigned long long* pairs, uint32_t* dir, cudaStream_t st) {
   if (n_sigs == 0 || size == 0) return cudaSuccess;
   const uint64_t n_words = n_sigs * kTables;
   lsh_slot_table_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(sigs), n_sigs, size, slots);
@@ -433,6 +450,12 @@ cudaError_t launch_pair_build(const uint8_t* sigs, uint64_t n_sigs, uint32_t siz
     scan_apply_kernel<<<n_blocks, kScanT, 0, st>>>(a, n_elems, block_sums, c, c);
     pair_run_starts_kernel<<<(unsigned)((n_elems + 256) / 256), 256, 0, st>>>(a, c, n_elems, d);
     pair_remaining_kernel<<<grid, 256, 0, st>>>(a, c, d, n_elems, fbits, row);
+    if (dir) {
+      uint32_t* dir_i = dir + 2ull * pair_index_row_base(i) * n_sigs;
+      cudaMemsetAsync(dir_i, 0xFF, 8ull * n_elems, st);
+      pair_dir_insert_kernel<<<grid, 256, 0, st>>>(row, a, n_elems, n_sigs, slots + (uint64_t)i * n_sigs, fbits, dir_i,
+                                                   (uint32_t)(2 * n_elems));
+    }
   }
   return cudaGetLastError();
 }

@@ -64,6 +64,18 @@ __host__ __device__ inline bool entry_before(float avg_a, int32_t n_a, float avg
   return !(avg_b > avg_a);
 }
 
+// run directory of the pair index: hash of (slice, slot_i, slot_j) and its reduction to a slot of a table of any capacity
+__host__ __device__ inline uint32_t pair_dir_hash(uint32_t slice, uint32_t slot_i, uint32_t slot_j) {
+  unsigned long long x = ((unsigned long long)slot_i << 32 | slot_j) * 0x9E3779B97F4A7C15ull;
+  x ^= (unsigned long long)(slice + 1u) * 0xC2B2AE3D27D4EB4Full;
+  x ^= x >> 29;
+  x *= 0xBF58476D1CE4E5B9ull;
+  return (uint32_t)(x >> 32);
+}
+__host__ __device__ inline uint32_t pair_dir_slot(uint32_t hash, uint32_t capacity) {
+  return (uint32_t)(((unsigned long long)hash * capacity) >> 32);
+}
+
 struct SearchParams {
   const uint8_t* db_sigs;        // [n_sigs][100]
   const uint32_t* sig_entry;     // [n_sigs] shard-local entry index
@@ -71,6 +83,7 @@ struct SearchParams {
   const uint32_t* ids;           // [25*n_sigs]
   const unsigned long long* pairs;   // pair index [300*n_sigs]: ((slot_j << pair_fbits) | remaining) << 32 | id, or nullptr
   uint32_t pair_fbits;               // width of the saturated remaining-run-length field (k_search.cu: pair_remaining_kernel)
+  const uint32_t* pair_dir;          // run directory [600*n_sigs] (k_search.cu: pair_dir_insert_kernel), or nullptr
   const uint32_t* rows128;           // with the pair index: signature g at words [32 g, 32 g + 25)
   uint32_t pair_cap;                 // distinct candidates the pair kernel lists per round (4096; MNEMO_PAIR_CAP shrinks it: tests)
   uint32_t size;                 // lsh.c:61 (global)
@@ -104,7 +117,7 @@ bool pair_index_possible(uint32_t size);
 int pair_index_fbits(uint32_t size);
 cudaError_t launch_pair_build(const uint8_t* sigs, uint64_t n_sigs, uint32_t size, const uint32_t* start, const uint32_t* ids,
                               uint32_t* slots, uint32_t* ka, uint32_t* va, uint32_t* kb, uint32_t* vb, void* temp,
-                              unsigned long long* pairs, cudaStream_t st);
+                              unsigned long long* pairs, uint32_t* dir, cudaStream_t st);
 void launch_search_compact(const uint32_t* acc_score, const uint32_t* acc_n, uint32_t n_queries, uint32_t n_entries,
                            uint32_t entry_base, CandDev* cands, uint32_t cap, uint32_t* total, uint32_t* q_base,
                            uint32_t* q_cnt, cudaStream_t st);
