@@ -358,6 +358,18 @@ def c4_checker(entries, queries, pick, got, single_score, single_n, sharded_rows
     return out
 
 
+def corpus_checker(pcm, sigs):
+    """Checker leg of the corpus sections (rank 0): one ring track through the unmodified reference (oracle/_ref) when it
+    is built on this box, else through the oracle port; the GPU's signatures of that track must be identical."""
+    from oracle import ref as refmod
+    if refmod.available():
+        rc, want = refmod.Ref().fingerprint_pcm(pcm)
+    else:
+        from oracle.oracle import Oracle
+        rc, want = Oracle().fingerprint_pcm(pcm)
+    return rc == 0 and want.shape == sigs.shape and bool(np.array_equal(want, sigs))
+
+
 # ----------------------------------------------------------------------- reference arm ----
 def reference_throughput(seconds_sample: float, channels: int, steps: int, warmup: int, variant: str = "O2"):
     """Times the unmodified reference (oracle/_ref -O2, generate_fingerprint on a WAV file) on the host
@@ -432,6 +444,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--search-c4-tracks", type=int, default=10000,
                     help="database size of the configs[3] search section, sharded over the N GPUs (0 = skip)")
+    ap.add_argument("--corpus-hours", type=float, default=1000.0,
+                    help="length of the configs[4] streaming corpus, dealt to the N GPUs (0 = skip configs[2] and [4])")
     ap.add_argument("--index-only", action="store_true",
                     help="only the headline index measurement (value, e2e, roofline): for profiler launch lists")
     ap.add_argument("--search-c4-ref-queries", type=int, default=64,
@@ -656,7 +670,7 @@ def main():
             "roofline": roofline, "signatures_per_track": int(n_sigs[0]), "group_record_slots_in_use": slots_in_use}
 
     if args.index_only:
-        args.search_c4_tracks, args.no_cpu_baseline = 0, True
+        args.search_c4_tracks, args.no_cpu_baseline, args.corpus_hours = 0, True, 0.0
     if world == 1 and rank == 0 and not args.index_only:
         # worst-case content for the group records: the same pass on a saw-tooth crescendo track
         try:
@@ -747,6 +761,20 @@ def main():
             c4 = {"error": repr(exc)}
         if rank == 0:
             line["search_c4"] = c4
+    if args.corpus_hours > 0:
+        # BASELINE.json configs[2] (130 four-minute tracks, the DEFCON-scale batch) and configs[4] (1000 h streamed with
+        # overlapped uploads) at every N: tracks dealt to the ranks, no collective on the data path
+        from mnemophonix_b200 import workloads
+        dev = torch.device("cuda", local_rank)
+        for key, kw in (("batch_c3", dict(n_tracks=130, per_batch=max(1, -(-130 // (2 * world))), label="configs[2]: ",
+                                          passes=8, checker=corpus_checker)),
+                        ("stream_c5", dict(n_tracks=int(round(args.corpus_hours * 15)), per_batch=64, label="configs[4]: "))):
+            try:
+                sec = workloads.stream_index(local_rank, dev, rank, world, dist, seconds=240.0, **kw)
+            except Exception as exc:
+                sec = {"error": repr(exc)}
+            if rank == 0:
+                line[key] = sec
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         r = reference_throughput(args.cpu_sample_seconds, args.channels, 1, 0)
         if r is not None:

@@ -6,8 +6,11 @@ Search: RankedShardedSearcher — the database is split on node boundaries of th
 tree, one contiguous entry range per rank; every rank probes its shard with the GLOBAL table size
 (lsh.c:61), ranks its own nodes on its GPU, and two small all-gathers per query tile (NCCL on device
 tensors, no host bounce) carry one byte per query signature and ten records per query and node; the
-top levels of the tree are merged on the GPU.  search_sharded / merge_shards are the older record form
-(arbitrary cuts, host merge), kept as a diagnostic.
+top levels of the tree are merged on the GPU.  GridShardedSearcher lays the ranks out as database shards x query
+groups (shard for capacity, replicate for throughput): each group of S ranks is one RankedShardedSearcher over an
+S-way split database and answers its own slice of the query batch; one more all-gather of 12 bytes per query
+returns every answer to every rank.  search_sharded / merge_shards are the older record form (arbitrary cuts, host
+merge), kept as a diagnostic.
 """
 from __future__ import annotations
 
@@ -275,3 +278,95 @@ class RankedShardedSearcher:
 
     def close(self):
         self.db.close()
+
+
+def grid_layout(world: int, db_shards: int):
+    """rank -> (shard index, query group) for a world laid out as db_shards x query groups: the ranks of one group are
+    consecutive (rank = group * db_shards + shard), so a group sits on neighbouring GPUs."""
+    assert db_shards >= 1 and world % db_shards == 0, "the world must be a whole number of database replicas"
+    return [(r % db_shards, r // db_shards) for r in range(world)]
+
+
+def query_slices(qstart, n_groups: int):
+    """Contiguous slices of the query batch with roughly equal numbers of query SIGNATURES (the unit of probe work):
+    n_groups + 1 cut points into the queries."""
+    qstart = np.asarray(qstart, np.int64)
+    nq, total = len(qstart) - 1, int(qstart[-1])
+    cuts = [0]
+    for g in range(1, n_groups):
+        cuts.append(max(cuts[-1], min(nq, int(np.searchsorted(qstart, total * g / n_groups, side="left")))))
+    cuts.append(nq)
+    return cuts
+
+
+class GridShardedSearcher:
+    """world = db_shards x query groups.  The database is split db_shards ways (as few as its size needs: every
+    shard costs each query signature a bucket lookup, its list walks and a share of two all-gathers, so a batch
+    strong-scales poorly over shards) and each replica of that split — one group of db_shards ranks
+    running the RankedShardedSearcher protocol among themselves over NCCL — answers 1 / groups of the query batch.  A
+    last all-gather (12 bytes per query) hands every rank every answer.
+
+        shard, group = dist.grid_layout(world, db_shards)[rank]
+        cuts, _ = capi.tree_cuts(n_entries_total, db_shards)          # this rank holds entries cuts[shard] .. cuts[shard+1]-1
+        g = GridShardedSearcher(ctx, sigs_of_those_entries, table_size, n_entries_total, rank, world, db_shards, device, stream=st)
+        answers = g.search(prepared_queries)                          # capi.MATCH_DTYPE array, the same on every rank
+    """
+
+    def __init__(self, ctx, shard_sigs, table_size: int, n_entries_total: int, rank: int, world: int, db_shards: int,
+                 device="cpu", db_factory=None, stream=None, tile_queries: int | None = None):
+        import torch.distributed as dist
+        self.rank, self.world, self.db_shards, self.device, self.stream = rank, world, db_shards, device, stream
+        self.n_groups = world // db_shards
+        self.shard, self.group_index = grid_layout(world, db_shards)[rank]
+        sub = None
+        if world > 1 and db_shards < world:
+            # every rank creates every group, in the same order (torch.distributed.new_group is collective)
+            for g in range(self.n_groups):
+                grp = dist.new_group(list(range(g * db_shards, (g + 1) * db_shards))) if db_shards > 1 else None
+                if g == self.group_index:
+                    sub = grp
+        self.inner = RankedShardedSearcher(ctx, shard_sigs, table_size, n_entries_total, self.shard, db_shards, device=device,
+                                           group=sub, db_factory=db_factory, stream=stream, tile_queries=tile_queries)
+        self.message_bytes = 0
+
+    @property
+    def db(self):
+        return self.inner.db
+
+    def search(self, queries):
+        import torch
+        import torch.distributed as dist
+        qs, qstart = queries if isinstance(queries, tuple) else capi.Db.prepare(queries)
+        nq = len(qstart) - 1
+        cuts = query_slices(qstart, self.n_groups)
+        q0, q1 = cuts[self.group_index], cuts[self.group_index + 1]
+        s0, s1 = int(qstart[q0]), int(qstart[q1])
+        sub = (qs[s0:s1], np.ascontiguousarray(np.asarray(qstart[q0:q1 + 1], np.int64) - int(qstart[q0])).astype(np.uint32))
+        if self.inner.on_gpu:
+            mine = self.inner.search(sub, as_array=True)
+        else:
+            mine = np.array([tuple(r) for r in self.inner.search(sub)], capi.MATCH_DTYPE).reshape(-1)
+        self.message_bytes = self.inner.message_bytes
+        if self.n_groups == 1:
+            return mine
+        per = max(b - a for a, b in zip(cuts, cuts[1:]))
+        item = capi.MATCH_DTYPE.itemsize
+        send = np.zeros(max(per, 1) * item, np.uint8)
+        send[:len(mine) * item] = mine.view(np.uint8).reshape(-1)
+        t = torch.from_numpy(send).to(self.device)
+        out = torch.empty(self.world * t.numel(), dtype=torch.uint8, device=t.device)
+        scope = torch.cuda.stream(self.stream) if (self.stream is not None and self.inner.on_gpu) else None
+        if scope is not None:
+            with scope:
+                dist.all_gather_into_tensor(out, t)
+        else:
+            dist.all_gather_into_tensor(out, t)
+        self.message_bytes += t.numel()
+        if self.stream is not None and self.inner.on_gpu:
+            self.stream.synchronize()
+        allb = out.cpu().numpy().reshape(self.world, -1)
+        parts = [allb[g * self.db_shards][: (cuts[g + 1] - cuts[g]) * item].view(capi.MATCH_DTYPE) for g in range(self.n_groups)]
+        return np.concatenate(parts) if nq else np.zeros(0, capi.MATCH_DTYPE)
+
+    def close(self):
+        self.inner.close()

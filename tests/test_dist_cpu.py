@@ -177,6 +177,71 @@ def test_ranked_shards_over_gloo_equal_single_database(world, tile):
     assert res == want
 
 
+def _grid_worker(rank, world, port, out, db_shards):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mnemophonix_b200 import capi, dist as mdist
+    from oracle.oracle import Oracle
+    o = Oracle()
+    entries, queries = _make_corpus()
+    total = sum(len(s) for s in entries)
+    shard, _group = mdist.grid_layout(world, db_shards)[rank]
+    cuts, _ = capi.tree_cuts(len(entries), db_shards)
+    mine = entries[int(cuts[shard]):int(cuts[shard + 1])]
+    s = mdist.GridShardedSearcher(None, mine, total // 2, len(entries), rank, world, db_shards, device="cpu",
+                                  db_factory=lambda sigs, ts, base: _OracleShard(o, sigs, ts, base))
+    res = s.search(capi.Db.prepare(queries))
+    s.close()
+    out.put((rank, res.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,db_shards", [(4, 2), (2, 1), (3, 3)])
+def test_grid_of_shards_and_query_groups_over_gloo(world, db_shards):
+    """dist.GridShardedSearcher: world = database shards x query groups.  4 ranks as two replicas of a two-way split
+    (each pair runs the ranked-shard protocol in its own subgroup on its slice of the queries), 2 ranks as two whole
+    replicas (no database collective at all), 3 ranks as one three-way split (the plain protocol); every rank ends up
+    with every answer, equal to the oracle's search of the single database."""
+    from oracle.oracle import Oracle
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grid_worker, args=(r, world, port, out, db_shards)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    o = Oracle()
+    entries, queries = _make_corpus()
+    db = o.make_db(entries)
+    want = []
+    for q in queries:
+        best, sc, _, _ = o.search(db, q)
+        want.append((best, float(sc[best, 0]) if best >= 0 else 0.0, int(sc[best, 1]) if best >= 0 else 0))
+    for r in range(world):
+        assert got[r] == want, r
+
+
+def test_query_slices_balance_query_signatures():
+    from mnemophonix_b200 import dist as mdist
+    rng = np.random.RandomState(3)
+    for n_groups in (1, 2, 4, 8):
+        lens = rng.randint(0, 60, 37)
+        qstart = np.concatenate([[0], np.cumsum(lens)])
+        cuts = mdist.query_slices(qstart, n_groups)
+        assert len(cuts) == n_groups + 1 and cuts[0] == 0 and cuts[-1] == 37
+        assert all(a <= b for a, b in zip(cuts, cuts[1:]))
+        per = [int(qstart[b] - qstart[a]) for a, b in zip(cuts, cuts[1:])]
+        assert max(per) <= qstart[-1] / n_groups + lens.max()
+    assert mdist.query_slices(np.zeros(1, np.uint32), 4) == [0, 0, 0, 0, 0]
+    assert mdist.grid_layout(8, 2)[5] == (1, 2)
+
+
 def test_two_rank_search_merge_equals_single_database():
     from oracle.oracle import Oracle
     ctx = mp.get_context("spawn")

@@ -50,8 +50,17 @@ def _worker(rank, world, port, out):
     res_ranked = ranked.search(qs + [sigs[7]])
     assert ranked.message_bytes > 0
     ranked.close()
-    ctx_s.close()
     assert res_ranked == [tuple(r) for r in res] or res_ranked == res, (res_ranked, res)
+    # database shards x query groups (dist.GridShardedSearcher): 2 x 2 on four GPUs, 1 x N (whole replicas) otherwise
+    db_shards = 2 if world % 2 == 0 and world > 2 else 1
+    shard, _ = mdist.grid_layout(world, db_shards)[rank]
+    gcuts, _ = capi.tree_cuts(len(sigs), db_shards)
+    grid = mdist.GridShardedSearcher(ctx_s, sigs[int(gcuts[shard]):int(gcuts[shard + 1])], total // 2, len(sigs), rank, world,
+                                     db_shards, device=torch.device("cuda", rank), stream=stream)
+    res_grid = grid.search(qs + [sigs[7]])
+    grid.close()
+    ctx_s.close()
+    assert [tuple(r) for r in res_grid.tolist()] == [tuple(r) for r in res], (res_grid, res)
     if rank == 0:
         out.put(([len(s) for s in sigs], res, [np.asarray(s).tobytes() for s in sigs], [np.asarray(q).tobytes() for q in qs]))
     dist.barrier()
