@@ -12,8 +12,8 @@
 //   3. a block-wide scan turns the 300 run lengths into a flat index; every thread takes entries of that flat index,
 //      inserts their ids into a shared-memory hash set (a signature sharing h buckets shows up h(h-1)/2 times) and
 //      lists the new ones;
-//   4. warps deep-check the listed ids in groups of 32 (equal words, differing bytes; k_search.cu has the same code)
-//      and add (score, 1) to the per-(query, entry) accumulators.
+//   4. warps deep-check the listed ids in groups of 32, four 128-byte rows per load instruction, and add (score, 1) to
+//      the per-(query, entry) accumulators (the two shared buckets search.c:153 asks for hold by construction here).
 // The runs are de-duplicated one id range at a time: usually one range (all ids), narrower ones when a query signature
 // has more distinct candidates than the shared-memory list holds (step 3 below), so there is no upper limit.
 #include "common.cuh"
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
   __shared__ uint32_t seg_pos[kPairs];          // first entry of the run, relative to the pair's array
   __shared__ uint32_t seg_pref[kPairs + 1];     // exclusive prefix of the run lengths
   __shared__ uint32_t q_begin[kTables], q_len[kTables], q_slot[kTables];
-  __shared__ __align__(16) uint32_t q_word[kTables + 3];
+  __shared__ __align__(16) uint32_t q_word[32];   // the query's 25 words, then zeros like the padding of a 128-byte row
   __shared__ uint32_t s_warp_tot[kPairThreads / 32];
   __shared__ uint32_t s_nuniq, s_gmax, s_L, s_over, s_T;
 
@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(kPairThreads, 3)
       q_begin[lane] = b - lane * n;   // position inside table `lane`: the CSR gives every table n consecutive ids
       q_len[lane] = len;
       if (len) last = __ldg(p.ids + e - 1);   // lists are sorted by id: the greatest member is the last one
+    } else {
+      q_word[lane] = 0u;
     }
     const uint32_t L = __reduce_add_sync(0xffffffffu, len);
     if (lane == 0) {
@@ -288,21 +290,23 @@ __global__ void __launch_bounds__(kPairThreads, 3)
     __syncthreads();
     return total;
   };
-  // flat pass: every thread takes entries of the published pieces, four loads in flight, and inserts their ids
+  // flat pass: every thread takes four CONSECUTIVE entries of the published pieces (one 32-byte sector when they lie in
+  // one run, as they usually do): one bisection of the prefix table per four entries, four loads in flight
   auto insert_published = [&](uint32_t Tr) {
-    for (uint32_t t0 = tid; t0 < Tr; t0 += kPairThreads * 4) {
+    for (uint32_t t0 = 4u * tid; t0 < Tr; t0 += kPairThreads * 4) {
+      uint32_t lo = 0, hi = kPairs;   // piece that holds flat index t0: last pid with seg_pref[pid] <= t0
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (seg_pref[mid] <= t0) lo = mid;
+        else hi = mid;
+      }
       uint32_t g[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const uint32_t t = t0 + u * kPairThreads;
+        const uint32_t t = t0 + u;
         g[u] = kPairEmpty;
         if (t < Tr) {
-          uint32_t lo = 0, hi = kPairs;   // piece that holds flat index t: last pid with seg_pref[pid] <= t
-          while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (seg_pref[mid] <= t) lo = mid;
-            else hi = mid;
-          }
+          while (seg_pref[lo + 1] <= t) ++lo;   // (empty pieces are skipped; seg_pref[kPairs] = Tr > t ends the walk)
           g[u] = (uint32_t)__ldg(p.pairs + (uint64_t)lo * n + seg_pos[lo] + (t - seg_pref[lo]));
         }
       }
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
     if (!one_pass) atomicAdd(p.stat_pairs + 5, 1ull);
   }
   const uint32_t query = find_segment<uint32_t>(p.query_start, p.n_queries, qs);
-  const uint32_t my_slot = lane < kTables ? q_slot[lane] : 0u, my_word = lane < kTables ? q_word[lane] : 0u;
+  const uint4 my_q = *reinterpret_cast<const uint4*>(&q_word[4 * (lane & 7)]);   // this lane's 16 bytes of the query's row
   uint32_t deep = 0;
 
   // 3.-4. Usually that was all: the distinct candidates (T ~ 2000 entries, ~1500 ids) fit the list and are deep-checked
@@ -404,40 +408,34 @@ __global__ void __launch_bounds__(kPairThreads, 3)
     }
     filled = false;
     const uint32_t nuniq = s_nuniq;
-    // deep checks, 32 signatures per warp at a time (see check_list in k_search.cu)
+    // deep checks, 32 signatures per warp at a time, four per load instruction: eight lanes read the 128-byte row of one
+    // signature as 16-byte pieces and compare them with the query's piece; the four byte counts travel through one warp
+    // reduction in four 8-bit fields (at most 100 differing bytes).  Every candidate of the pair index shares the two
+    // buckets of its pair with the query, so MIN_BUCKET_MATCH_FOR_DEEP_CHECK (search.c:153) holds by construction and
+    // only the score (search.c:35-43) is computed.
     for (uint32_t base = (uint32_t)warp * 32u; base < nuniq; base += kPairThreads) {
       const uint32_t cnt = min(32u, nuniq - base);
       const uint32_t my_g = uniq[base + ((uint32_t)lane < cnt ? lane : 0)];
-      uint32_t w[32];
+      const uint32_t my_entry = __ldg(p.sig_entry + my_g);   // in flight with the rows, not after them
+      uint4 w[8];
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        const uint32_t g = __shfl_sync(0xffffffffu, my_g, r);
-        w[r] = lane < kTables ? __ldg(dbw + (uint64_t)g * 32u + lane) : 0u;   // lanes >= 25 hold "equal" words
+      for (int r = 0; r < 8; ++r) {
+        const uint32_t g = __shfl_sync(0xffffffffu, my_g, 4 * r + (lane >> 3));
+        w[r] = __ldg(reinterpret_cast<const uint4*>(dbw + (uint64_t)g * 32u) + (lane & 7));
       }
       uint32_t mine = 0;
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        uint32_t v = pp_differing_bytes(w[r], my_word) | (w[r] == my_word ? 0x10000u : 0u);
-        v = __reduce_add_sync(0xffffffffu, v);
-        if (lane == r) mine = v;
+      for (int r = 0; r < 8; ++r) {
+        const uint32_t d = pp_differing_bytes(w[r].x, my_q.x) + pp_differing_bytes(w[r].y, my_q.y) +
+                           pp_differing_bytes(w[r].z, my_q.z) + pp_differing_bytes(w[r].w, my_q.w);
+        const uint32_t v = __reduce_add_sync(0xffffffffu, d << (8 * (lane >> 3)));
+        if ((lane >> 2) == r) mine = v;   // lane = candidate 4 r + (lane & 3)
       }
-      const uint32_t score = 100u - (mine & 0xFFFFu);   // search.c:35-43
-      uint32_t hits = (mine >> 16) - (32u - kTables);
-      uint32_t slow = __ballot_sync(0xffffffffu, (uint32_t)lane < cnt && hits < 2u);
-      while (slow) {   // fewer than two equal words: the shared buckets come from key % size collisions, recount
-        const int r = __ffs(slow) - 1;
-        slow &= slow - 1u;
-        const uint32_t g = __shfl_sync(0xffffffffu, my_g, r);
-        uint32_t hh = 0;
-        if (lane < kTables)
-          hh = pp_same_slot(pp_bucket_key(__ldg(dbw + (uint64_t)g * 32u + lane)), my_slot, p.div_inv, p.div_shift, p.div_thr);
-        const uint32_t exact = __popc(__ballot_sync(0xffffffffu, hh));
-        if (lane == r) hits = exact;
-      }
-      if ((uint32_t)lane < cnt && my_g != gmax && hits >= 2u) {   // last group never flushed; MIN_BUCKET_MATCH_FOR_DEEP_CHECK
+      const uint32_t score = 100u - ((mine >> (8 * (lane & 3))) & 0xFFu);   // search.c:35-43
+      if ((uint32_t)lane < cnt && my_g != gmax) {   // the last group is never flushed (search.c:147-165)
         ++deep;
-        if (score >= 30u) {                                       // MIN_SCORE (search.c:16)
-          const uint64_t a = (uint64_t)query * p.n_entries + p.sig_entry[my_g];
+        if (score >= 30u) {                          // MIN_SCORE (search.c:16)
+          const uint64_t a = (uint64_t)query * p.n_entries + my_entry;
           atomicAdd(&p.acc_score[a], score);
           atomicAdd(&p.acc_n[a], 1u);
         }
