@@ -583,14 +583,19 @@ def main():
         return collect(steps - 1)
 
     e2e_loop(3)
-    barrier()
-    t_wall = time.perf_counter()
-    _, n_sigs, status = e2e_loop(args.steps)
-    barrier()
-    wall_ms = (time.perf_counter() - t_wall) * 1e3
-    clocks_e2e = sampler.summary(t_wall, time.perf_counter())
+    # K steps, timed three times over (barrier + synchronize on both sides of each); the median is reported and all three
+    # are listed: the loop is bound by the host -> device copies, which share the host with whatever else runs on the box
+    e2e_each = []
+    t_e2e0 = time.perf_counter()
+    for _ in range(3):
+        barrier()
+        t_wall = time.perf_counter()
+        _, n_sigs, status = e2e_loop(args.steps)
+        barrier()
+        e2e_each.append(max_over_ranks((time.perf_counter() - t_wall) * 1e3) / args.steps)
+    clocks_e2e = sampler.summary(t_e2e0, time.perf_counter())
     sampler.stop()
-    e2e_ms = max_over_ranks(wall_ms) / args.steps
+    e2e_ms = float(np.median(e2e_each))
     e2e_value = world * hours_per_step / (e2e_ms / 1e3)
     h2d = int(pcm.nbytes)
     d2h = int(batch.cap * 100 + 4)
@@ -655,17 +660,17 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks, "clocks_e2e": clocks_e2e,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "isolated_step_ms": e2e_single_ms,
+                    "ms_per_step": e2e_ms, "ms_per_step_each_repeat": e2e_each, "isolated_step_ms": e2e_single_ms,
                     "h2d_GBps_aggregate": world * h2d / (e2e_ms / 1e3) / 1e9,
                     "h2d_ceiling_GBps_aggregate": world * h2d / copy_s / 1e9,
                     "frac_of_h2d_ceiling": copy_s / (e2e_ms / 1e3),
                     "host_placement": placement,
                     "note": "two batches in flight on two streams; each step copies its PCM from pinned host "
-                            "memory and its signatures back; timed on the host clock around all K steps; "
+                            "memory and its signatures back; timed on the host clock around all K steps, three times over, median reported; "
                             "h2d_ceiling = the same ranks sending the same pinned buffers with no kernels, same run"},
-            # kernels of the timed regions and their warm-ups: `value` (warm-up + K runs) and `e2e` (3 + K + 1 steps), each run
+            # kernels of the timed regions and their warm-ups: `value` (warm-up + K runs) and `e2e` (3 + 3 K + 1 steps), each run
             # launching launches_per_run kernels (counted by the library); the supplementary sections are not included
-            "gpu_launches": int(launches_per_run * (max(args.warmup, 3) + args.steps + 3 + args.steps + 1)),
+            "gpu_launches": int(launches_per_run * (max(args.warmup, 3) + args.steps + 3 + 3 * args.steps + 1)),
             "gpu_launches_per_step": int(launches_per_run),
             "roofline": roofline, "signatures_per_track": int(n_sigs[0]), "group_record_slots_in_use": slots_in_use}
 

@@ -329,9 +329,11 @@ __global__ void __launch_bounds__(kPairThreads, 3)
       atomicAdd(p.stat_pairs + 4, (unsigned long long)d);
     }
   }
+  uint32_t gmax_word = 0;   // warp 0: the greatest candidate's row, in flight until the last-group record at the end
   if (warp == 0) {   // the greatest candidate id: the group search.c:147-165 never scores
     const uint32_t g = __reduce_max_sync(0xffffffffu, last);
     if (lane == 0) s_gmax = g;
+    if (lane < kTables) gmax_word = __ldg(dbw + (uint64_t)g * 32u + lane);
   }
   const long long t_searched = p.stat_pairs ? clock64() : 0;
   const uint32_t T_rest = publish(rest_pos, rest_len);   // (its barriers also order the inline insertions and s_T)
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
   if (warp == 0) {
     uint32_t h = 0, eq = 0;
     if (lane < kTables) {
-      const uint32_t w = __ldg(dbw + (uint64_t)gmax * 32u + lane);
+      const uint32_t w = gmax_word;
       h = pp_same_slot(pp_bucket_key(w), q_slot[lane], p.div_inv, p.div_shift, p.div_thr);
       eq = 4u - pp_differing_bytes(w, q_word[lane]);
     }
