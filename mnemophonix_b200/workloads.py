@@ -314,14 +314,15 @@ def stream_index(local_rank: int, dev, rank: int, world: int, dist, n_tracks: in
     b.sync()
     copy_s = time.perf_counter() - t1
     copy_bytes = reps * b.n * n_frames * 2
-    t = torch.tensor([dt, float(tot["sigs"]), float(tot["checked"]), float(tot["bad"]), float(len(mine)), copy_bytes / copy_s],
+    t = torch.tensor([dt, float(tot["sigs"]), float(tot["checked"]), float(tot["bad"]), float(len(mine)), float(copy_bytes), copy_s],
                      dtype=torch.float64, device=dev)
     if dist is not None:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        t[0] = tmax[0]
-    dt, sigs, checked, bad, n_done, ceil = float(t[0]), int(t[1]), int(t[2]), int(t[3]), int(t[4]), float(t[5])
+        t[0], t[6] = tmax[0], tmax[6]
+    dt, sigs, checked, bad, n_done = float(t[0]), int(t[1]), int(t[2]), int(t[3]), int(t[4])
+    ceil = float(t[5]) / float(t[6])          # all ranks' bytes over the slowest rank's time: the copies ran at once
     out = None
     if rank == 0:
         hours = n_done * seconds / 3600.0
