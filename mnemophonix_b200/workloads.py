@@ -109,7 +109,7 @@ def c4_search(ctx, stream, dev, rank: int, world: int, dist, n_tracks: int = 100
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
         times.append(dt)
-    dt = float(np.mean(times))
+    dt = float(np.median(times))          # every batch is listed (s_per_batch_each)
     batch_times = [float(x) for x in times]
     res = res.tolist()
     searcher.profile = True                              # one more batch with CUDA events between the phases
@@ -172,7 +172,7 @@ def c4_search(ctx, stream, dev, rank: int, world: int, dist, n_tracks: int = 100
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             gtimes.append(float(tt.item()))
         grid = {"layout": f"{grid_db_shards} database shards x {world // grid_db_shards} query groups",
-                "queries_per_s": n_q / float(np.mean(gtimes)), "s_per_batch": float(np.mean(gtimes)), "s_per_batch_each": gtimes,
+                "queries_per_s": n_q / float(np.median(gtimes)), "s_per_batch": float(np.median(gtimes)), "s_per_batch_each": gtimes,
                 "lsh_build_s_per_shard": g_build, "nccl_message_bytes_per_batch_per_rank": int(gs.message_bytes)}
         gs.close()
     out = None
