@@ -130,9 +130,9 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
   // Pair index (k_pairprobe.cu): worth its memory (2400 bytes per signature) and build time once the bucket lists a
   // query signature probes are long.  What a query that resembles the database meets is sum(len^2) / n_sigs ids per
   // table; measured on config #4's corpus cut to 380 k / 760 k / 1.52 M / 3.04 M signatures (L = 5.3 k / 10.6 k / 21 k /
-  // 42 k ids over the 25 tables) the streaming kernel is 1.4x faster / equal / 1.5x slower / 1.7x slower than the pair
-  // kernel, so the index is built from L = 12 k on.  MNEMO_PAIR_INDEX=1 / 0 forces it on (tests run the small cases
-  // through it) / off.
+  // 42 k ids over the 25 tables; tools/crossover_run.sh, whole search of 10 k queries) the streaming kernel takes 15.2 /
+  // 25.9 / 45.3 / 95 ms and the pair kernel with its run directory 16.2 / 19.4 / 25.2 / 38.3 ms, so the index is built from
+  // L = 7.5 k on.  MNEMO_PAIR_INDEX=1 / 0 forces it on (tests run the small cases through it) / off.
   bool want_pairs = false;
   if (e == cudaSuccess && db->size && db->n_sigs) {
     unsigned long long sum_sq = 0, *d_sum = reinterpret_cast<unsigned long long*>(d_block_sums);   // (idle by now)
@@ -140,7 +140,7 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
     TRY(cudaMemcpyAsync(&sum_sq, d_sum, 8, cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(st));
     db->expected_list_ids = (double)sum_sq / (double)db->n_sigs;
-    want_pairs = db->expected_list_ids >= 12000.0;
+    want_pairs = db->expected_list_ids >= 7500.0;
   }
   if (const char* env = getenv("MNEMO_PAIR_INDEX")) want_pairs = atoi(env) > 0;
   if (e == cudaSuccess && want_pairs && db->n_sigs && pair_index_possible(db->size)) {

@@ -2,7 +2,7 @@
 whatever libmnemo_cuda.so is in place; the corpus is cached in /tmp so that several library variants can be timed in
 one gpurun call (tools/build_variants.sh).  Prints one JSON line: ms per batch, answers CRC (must not change).
 
-    python tools/pair_ab.py [label]"""
+    python tools/pair_ab.py [label] [tracks]      # tracks < 10000: a shard (first tracks, the whole database's table size)"""
 import json, os, sys, time, zlib
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,6 +10,7 @@ import torch
 from mnemophonix_b200 import capi, synth
 
 label = sys.argv[1] if len(sys.argv) > 1 else ""
+n_shard = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 cache = "/tmp/c4_corpus.npz"
 torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
@@ -38,7 +39,10 @@ else:
     np.savez(cache, sig_all=sig_all, sig_cnt=sig_cnt, q_all=q_all, q_cnt=q_cnt)
 entries = np.split(sig_all, np.cumsum(sig_cnt)[:-1])
 queries = np.split(q_all, np.cumsum(q_cnt)[:-1])
-db = capi.Db(ctx, entries)
+if n_shard:
+    db = capi.Db(ctx, entries[:n_shard], table_size=len(sig_all) // 2)
+else:
+    db = capi.Db(ctx, entries)
 prepared = capi.Db.prepare(queries, ctx)
 db.search(prepared)
 db.search(prepared)
@@ -49,7 +53,7 @@ for _ in range(5):
     res, (L, D) = db.search(prepared)
     times.append((time.perf_counter() - t0) * 1e3)
 crc = zlib.crc32(np.array(res, dtype=np.float64).tobytes())
-print(json.dumps({"label": label, "ms_per_batch": float(np.median(times)), "ms_each": times, "queries_per_s": len(queries) / (np.median(times) / 1e3),
+print(json.dumps({"label": label, "tracks": n_shard or len(entries), "pair_index": db.has_pair_index, "ms_per_batch": float(np.median(times)), "ms_each": times, "queries_per_s": len(queries) / (np.median(times) / 1e3),
                   "answers_crc": crc, "L": L, "D": D, "identified": int(sum(int(r[0] == i) for i, r in enumerate(res)))}))
 db.close()
 ctx.close()
