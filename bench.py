@@ -765,6 +765,19 @@ def main():
         except Exception as exc:   # a supplementary section must never cost the bench line
             c4 = {"error": repr(exc)}
         if rank == 0:
+            if isinstance(c4, dict) and "phase_ms" in c4 and c4["phase_ms"].get("probe"):
+                # roofline of the search path's dominant kernel (the probe: search_pair_kernel with the pair index, else
+                # search_probe_kernel), same definition as `roofline` above: SURVEY.md §8d's algorithmic bytes of the batch
+                # (300 + 4 L + 100 D per query signature; every rank meets every query signature of its shard) over the
+                # probe phase, CUDA events on the context's stream, slowest layout-independent figure: rank 0's shard
+                alg = (c4["query_signatures"] * 300 + 4 * c4["probed_nodes_per_query_signature"] * c4["query_signatures"]
+                       + 100 * c4["deep_checks_per_query_signature"] * c4["query_signatures"])
+                ach = alg / (c4["phase_ms"]["probe"] / 1e3) / 1e9
+                c4["roofline"] = {"bound": "hbm", "kernel": "search probe (k_pairprobe.cu / k_search.cu)", "achieved": ach,
+                                  "peak": peak * world, "unit": "GB/s", "frac": ach / (peak * world),
+                                  "algorithmic_bytes_per_batch": alg, "kernel_ms": c4["phase_ms"]["probe"],
+                                  "traffic": None, "note": "probe phase includes the query upload and the accumulator "
+                                  "memsets; ncu per-launch DRAM bytes: profiles/r02_ncu_search_pairs_summary.md"}
             line["search_c4"] = c4
     if args.corpus_hours > 0:
         # BASELINE.json configs[2] (130 four-minute tracks, the DEFCON-scale batch) and configs[4] (1000 h streamed with

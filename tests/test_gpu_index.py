@@ -324,3 +324,21 @@ def test_staged_api_reuse_and_error_paths(ctx, oracle):
     with pytest.raises(capi.MnemoError):
         b.read(6, 0)
     b.close()
+
+
+def test_corpus_streaming_workload_is_batch_independent_and_equals_the_oracle(oracle):
+    """workloads.stream_index (BASELINE configs[2] / [4] on the bench line) on a small corpus: 14 tracks cycled from a ring
+    of 3, ragged batches of 4 in flight on two streams, two passes; every track's signatures equal the ones its ring track
+    produced alone (count + CRC-32), and that single-track run equals the oracle."""
+    import torch
+    from mnemophonix_b200 import workloads
+
+    def checker(pcm, sigs):
+        rc, want = oracle.fingerprint_pcm(pcm)
+        return rc == 0 and np.array_equal(want, sigs)
+
+    out = workloads.stream_index(0, torch.device("cuda", 0), 0, 1, None, n_tracks=14, seconds=12.0, per_batch=4, distinct=3,
+                                 passes=2, checker=checker)
+    assert out["tracks_crc_checked"] == 28 and out["tracks_differing_from_single_track_run"] == 0
+    assert out["ring_track_equals_oracle"] is True
+    assert out["signatures"] > 0 and out["audio_hours_per_s"] > 0
