@@ -32,6 +32,9 @@ struct mnemo_db {
     void* p = nullptr;
     uint64_t bytes = 0;
   } scratch[20];
+  bool pair_wanted = false;           // the pair index pays for this database (decided at create) but is not built yet
+  uint64_t pair_after = 4096;         // ... until this many query signatures have been searched; MNEMO_PAIR_LAZY_AFTER
+  uint64_t served_qsigs = 0;
   uint32_t pair_cap = 4096;           // distinct candidates per round of the pair kernel; MNEMO_PAIR_CAP shrinks it (tests)
   uint32_t range_ids = 1u << 18;      // ids per pass of the probe's id-range mode; MNEMO_RANGE_IDS shrinks it (tests)
   uint64_t acc_budget = 1ull << 30;   // bytes of dense accumulators per query tile; MNEMO_ACC_BYTES shrinks it (tests)
@@ -68,6 +71,51 @@ static cudaError_t dalloc(T** p, uint64_t count) {
   do {                              \
     if (e == cudaSuccess) e = (x);  \
   } while (0)
+
+// Pair index + run directory + 128-byte rows of a database whose CSR stands (k_search.cu: launch_pair_build).  Skipped,
+// for good, when less than half of the free device memory would remain.
+static cudaError_t build_pair_index(mnemo_db* db) {
+  db->pair_wanted = false;
+  if (db->d_pairs || !db->n_sigs || !pair_index_possible(db->size)) return cudaSuccess;
+  cudaStream_t st = db->ctx->stream;
+  cudaError_t e = cudaSuccess;
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  const size_t temp_bytes = lsh_sort_temp_bytes(db->n_sigs, db->size);
+  const uint64_t need = db->n_sigs * 300ull * 8ull + db->n_sigs * (5ull * 25ull + 32ull) * 4ull + temp_bytes;   // index + rows + scratch
+  if (need >= free_b / 2) return cudaSuccess;
+  uint32_t *d_slots = nullptr, *d_vals_out = nullptr, *d_keys_in = nullptr, *d_vals_in = nullptr, *d_keys_out = nullptr;
+  void* d_temp = nullptr;
+  TRY(dalloc(&db->d_pairs, db->n_sigs * 300ull + 8));   // + 8: the last probe window may reach past the last entry
+  TRY(dalloc(&d_slots, db->n_sigs * kTables));
+  TRY(dalloc(&d_vals_out, db->n_sigs * kTables));
+  TRY(dalloc(&d_keys_in, db->n_sigs * kTables));
+  TRY(dalloc(&d_vals_in, db->n_sigs * kTables));
+  TRY(dalloc(&d_keys_out, db->n_sigs * kTables));
+  TRY(cudaMalloc(&d_temp, temp_bytes ? temp_bytes : 1));
+  // run directory (one probe instead of a search per pair): as much memory again as the index; MNEMO_PAIR_DIR=0 / 1
+  bool want_dir = need + db->n_sigs * 2400ull < free_b / 2;
+  if (const char* env = getenv("MNEMO_PAIR_DIR")) want_dir = atoi(env) > 0;
+  if (want_dir) TRY(dalloc(&db->d_dir, db->n_sigs * 600ull));
+  TRY(launch_pair_build(db->d_sigs, db->n_sigs, db->size, db->d_start, db->d_ids, d_slots, d_keys_in, d_vals_in, d_keys_out, d_vals_out,
+                        d_temp, db->d_pairs, db->d_dir, st));
+  // the deep check reads whole signatures at random: 100-byte rows straddle three 64-byte DRAM bursts 56 % of
+  // the time, 128-byte aligned rows always take two
+  TRY(dalloc(&db->d_rows, db->n_sigs * 32ull));
+  if (e == cudaSuccess) launch_pad_rows(db->d_sigs, db->n_sigs, db->d_rows, st);
+  TRY(cudaStreamSynchronize(st));
+  void* tmp[] = {d_slots, d_vals_out, d_keys_in, d_vals_in, d_keys_out, d_temp};
+  for (void* q : tmp)
+    if (q) cudaFree(q);
+  if (e != cudaSuccess) {   // the streaming kernel goes on answering
+    void** mine[] = {(void**)&db->d_pairs, (void**)&db->d_dir, (void**)&db->d_rows};
+    for (void** q : mine) {
+      if (*q) cudaFree(*q);
+      *q = nullptr;
+    }
+  }
+  return e;
+}
 
 extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32_t* entry_start, uint32_t n_entries,
                                uint32_t table_size, uint32_t entry_base, mnemo_db** out) {
@@ -133,7 +181,7 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
   // 42 k ids over the 25 tables; tools/crossover_run.sh, whole search of 10 k queries) the streaming kernel takes 15.2 /
   // 25.9 / 45.3 / 95 ms and the pair kernel with its run directory 16.2 / 19.4 / 25.2 / 38.3 ms, so the index is built from
   // L = 7.5 k on.  MNEMO_PAIR_INDEX=1 / 0 forces it on (tests run the small cases through it) / off.
-  bool want_pairs = false;
+  bool want_pairs = false, build_now = false;
   if (e == cudaSuccess && db->size && db->n_sigs) {
     unsigned long long sum_sq = 0, *d_sum = reinterpret_cast<unsigned long long*>(d_block_sums);   // (idle by now)
     launch_bucket_load(db->d_start, n_slots, d_sum, st);
@@ -142,31 +190,16 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
     db->expected_list_ids = (double)sum_sq / (double)db->n_sigs;
     want_pairs = db->expected_list_ids >= 7500.0;
   }
-  if (const char* env = getenv("MNEMO_PAIR_INDEX")) want_pairs = atoi(env) > 0;
-  if (e == cudaSuccess && want_pairs && db->n_sigs && pair_index_possible(db->size)) {
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    const uint64_t need = db->n_sigs * 300ull * 8ull + db->n_sigs * (25ull + 24ull + 32ull) * 4ull;   // index + the scratch not held yet
-    if (need < free_b / 2) {
-      uint32_t *d_slots = nullptr, *d_vals_out = nullptr;
-      TRY(dalloc(&db->d_pairs, db->n_sigs * 300ull + 8));   // + 8: the last probe window may reach past the last entry
-      TRY(dalloc(&d_slots, db->n_sigs * kTables));
-      TRY(dalloc(&d_vals_out, db->n_sigs * kTables));
-      // run directory (one probe instead of a search per pair): as much memory again as the index; MNEMO_PAIR_DIR=0 / 1
-      bool want_dir = need + db->n_sigs * 2400ull < free_b / 2;
-      if (const char* env = getenv("MNEMO_PAIR_DIR")) want_dir = atoi(env) > 0;
-      if (want_dir) TRY(dalloc(&db->d_dir, db->n_sigs * 600ull));
-      TRY(launch_pair_build(db->d_sigs, db->n_sigs, db->size, db->d_start, db->d_ids, d_slots, d_keys_in, d_vals_in, d_keys_out, d_vals_out,
-                            d_temp, db->d_pairs, db->d_dir, st));
-      // the deep check reads whole signatures at random: 100-byte rows straddle three 64-byte DRAM bursts 56 % of
-      // the time, 128-byte aligned rows always take two
-      TRY(dalloc(&db->d_rows, db->n_sigs * 32ull));
-      if (e == cudaSuccess) launch_pad_rows(db->d_sigs, db->n_sigs, db->d_rows, st);
-      TRY(cudaStreamSynchronize(st));
-      cudaFree(d_slots);
-      cudaFree(d_vals_out);
-    }
+  // The index is built when the database has answered pair_after query signatures, not at create: 0.2-1.3 s and 4.8 KB
+  // per signature are wasted on a process that loads a database for one query (`mnemophonix search`); the streaming
+  // kernel answers the first few in the meantime (same results).  MNEMO_PAIR_INDEX=1 builds it here and now.
+  if (const char* env = getenv("MNEMO_PAIR_INDEX")) {
+    const int v = atoi(env);
+    want_pairs = v > 0;
+    build_now = v == 1;
   }
+  if (const char* env = getenv("MNEMO_PAIR_LAZY_AFTER")) db->pair_after = (uint64_t)std::max<long long>(0, atoll(env));
+  db->pair_wanted = want_pairs && db->n_sigs && pair_index_possible(db->size);
   cudaFree(d_counts);
   cudaFree(d_cursor);
   cudaFree(d_block_sums);
@@ -174,6 +207,7 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
   cudaFree(d_vals_in);
   cudaFree(d_keys_out);
   cudaFree(d_temp);
+  if (e == cudaSuccess && db->pair_wanted && (build_now || db->pair_after == 0)) e = build_pair_index(db);
   if (e != cudaSuccess) {
     int rc = mnemo_fail(ctx, e, "mnemo_db_create");
     mnemo_db_destroy(db);
@@ -311,6 +345,10 @@ static cudaError_t probe_batch(mnemo_db* db, const uint8_t* query_sigs, const ui
   cudaStream_t st = db->ctx->stream;
   b.n_queries = n_queries;
   b.n_qsigs = query_start[n_queries];
+  // the pair index is due once the database has seen enough query signatures to pay for it (mnemo_db_create)
+  db->served_qsigs += b.n_qsigs;
+  if (db->pair_wanted && !db->d_pairs && db->served_qsigs >= db->pair_after && build_pair_index(db) != cudaSuccess)
+    cudaGetLastError();   // no memory for it after all: the streaming kernel goes on answering
   b.tile = std::max<uint32_t>(1, std::min(n_queries, tile ? tile : mnemo_db_tile_queries(db)));
   const uint64_t cells = (uint64_t)b.tile * db->n_entries;
   cudaError_t e = cudaSuccess;

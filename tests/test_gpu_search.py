@@ -390,3 +390,30 @@ def test_page_locked_query_buffer_gives_the_same_answers(ctx, corpus):
     assert got == want and stats2 == stats
     del pinned
     db.close()
+
+
+def test_pair_index_is_built_lazily_and_changes_no_answer(ctx, corpus, monkeypatch):
+    """mnemo_db_create only decides that the pair index pays (MNEMO_PAIR_INDEX=2: wanted, not forced); it is built when
+    the database has answered MNEMO_PAIR_LAZY_AFTER query signatures — the streaming kernel answers until then — and the
+    answers before, across and after the switch are the ones of a database that never has the index."""
+    sigs, qs = corpus
+    monkeypatch.setenv("MNEMO_PAIR_INDEX", "0")
+    plain = capi.Db(ctx, sigs)
+    want, stats = plain.search(qs)
+    plain.close()
+    n_first = sum(len(q) for q in qs[:2])
+    monkeypatch.setenv("MNEMO_PAIR_INDEX", "2")
+    monkeypatch.setenv("MNEMO_PAIR_LAZY_AFTER", str(n_first + 1))
+    db = capi.Db(ctx, sigs)
+    assert not db.has_pair_index
+    got_a, _ = db.search(qs[:2])
+    assert not db.has_pair_index                       # n_first query signatures so far: one short of the threshold
+    got_b, _ = db.search(qs[2:])
+    assert db.has_pair_index                           # built at the start of the batch that crosses it
+    got_c, stats_c = db.search(qs)
+    db.close()
+    assert got_a + got_b == want and got_c == want and tuple(stats_c) == tuple(stats)
+    monkeypatch.setenv("MNEMO_PAIR_LAZY_AFTER", "0")   # nothing to wait for: built at create
+    db = capi.Db(ctx, sigs)
+    assert db.has_pair_index
+    db.close()
