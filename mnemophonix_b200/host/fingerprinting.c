@@ -29,7 +29,7 @@ static int trace_on(void) {
 }
 #define TRACE(what, t0) do { if (trace_on()) fprintf(stderr, "[mnemo] %-28s %8.1f ms\n", what, now_ms() - (t0)); } while (0)
 
-/* MNEMO_READERS=n caps the reader threads of the streaming ingest (default: up to 8) */
+/* MNEMO_READERS=n caps the reader threads of the streaming ingest (default: one per core, at most 32) */
 static int const_env_readers(void) {
     static int n = -1;
     if (n < 0) {
@@ -86,8 +86,8 @@ static struct signatures* new_signatures(uint64_t capacity) {
 
 /* Pinned staging for the streaming ingest: a ring of buffers per process, reused for every file. */
 #define PIECE_BYTES (4u << 20)
-#define RING 32                      /* 128 MB of pinned memory */
-#define MAX_READERS 16
+#define RING 64                      /* 256 MB of pinned memory: half in flight to the GPU, half being refilled */
+#define MAX_READERS 32              /* one per core at most (24-core boxes: 16 readers left PCIe a third idle) */
 static void* g_ring[RING];
 static pthread_mutex_t g_stage_lock = PTHREAD_MUTEX_INITIALIZER;   /* one file at a time through the ring */
 
