@@ -8,6 +8,25 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Checked build (-DMNEMO_CHECKED, tools/checked_build.sh): bounds assertions on the data-dependent indices of the search
+// kernels; a violation prints its condition and traps, which fails whatever GPU test was running.  compute-sanitizer is
+// closed on the development pool, so this is the memory-safety evidence beside bit-exact parity.  Without the flag
+// the macros vanish (identical SASS).
+#ifdef MNEMO_CHECKED
+#include <cstdio>
+#define MN_CHECK(cond)                                                                                              \
+  do {                                                                                                              \
+    if (!(cond)) {                                                                                                  \
+      printf("MN_CHECK failed: %s at %s:%d (block %u thread %u)\n", #cond, __FILE__, __LINE__, blockIdx.x, threadIdx.x); \
+      __trap();                                                                                                     \
+    }                                                                                                               \
+  } while (0)
+#else
+#define MN_CHECK(cond) \
+  do {                 \
+  } while (0)
+#endif
+
 namespace mnemo {
 
 constexpr int kFrame = 2048;        // spectralimages.h:12

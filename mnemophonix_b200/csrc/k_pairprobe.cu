@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(kPairThreads, 3)
     if (lane < kTables) {
       const uint32_t w = qwords[lane];
       const uint32_t slot = pp_fastmod(pp_bucket_key(w), p.size_magic, p.size);
+      MN_CHECK(slot < p.size);
       const uint32_t b = p.start[(uint64_t)lane * p.size + slot], e = p.start[(uint64_t)lane * p.size + slot + 1];
+      MN_CHECK(b <= e && e <= (uint32_t)(lane + 1) * n && b >= (uint32_t)lane * n);
       len = e - b;
       q_word[lane] = w;
       q_slot[lane] = slot;
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
       if (prev == g) break;
       if (prev == kPairEmpty) {
         const uint32_t pos = atomicAdd(&s_nuniq, 1u);
+        MN_CHECK(g < n && cap <= kPairUniqCap);
         if (pos < cap) uniq[pos] = g;
         else s_over = 1;
         break;
@@ -130,6 +133,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
       const uint32_t Bx = q_begin[i] + r, Ex = Bx + len_i, sj = q_slot[j];
       // probe = one aligned window of kWin entries
       auto load_win = [&](uint32_t w, unsigned long long (&e)[kWin]) {
+        MN_CHECK((base - r) + (uint64_t)kWin * (w + 1) <= 300ull * n + 8);   // the index is allocated with 8 entries to spare
         const ulonglong2* q2 = reinterpret_cast<const ulonglong2*>(P4) + (uint64_t)(kWin / 2) * w;
 #pragma unroll
         for (int k = 0; k < kWin / 2; ++k) {
@@ -160,6 +164,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
         uint32_t idx = pair_dir_slot(pair_dir_hash(slice, q_slot[i], sj), capacity);
         while (true) {
           ++probes;
+          MN_CHECK(idx < capacity && probes <= capacity);
           const uint32_t v = __ldg(dir_i + idx);
           if (v == 0xFFFFFFFFu) break;
           if (v - t_lo < len_i) {
@@ -234,9 +239,11 @@ __global__ void __launch_bounds__(kPairThreads, 3)
           uint32_t pos = lbx, rem = (uint32_t)(first >> 32) & rem_mask;
           while (rem == rem_mask) {
             pos += rem_mask;
+            MN_CHECK(pos < Ex);
             rem = (uint32_t)(__ldg(P4 + pos) >> 32) & rem_mask;
           }
           const uint32_t total = pos - lbx + rem + 1u, x_run = lbx + total;   // the run is [lbx, x_run)
+          MN_CHECK(lbx >= Bx && x_run <= Ex);
           uint32_t m = 0;
 #pragma unroll
           for (int k = 0; k < kWin; ++k) {
@@ -307,6 +314,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
         g[u] = kPairEmpty;
         if (t < Tr) {
           while (seg_pref[lo + 1] <= t) ++lo;   // (empty pieces are skipped; seg_pref[kPairs] = Tr > t ends the walk)
+          MN_CHECK(lo < (uint32_t)kPairs && seg_pos[lo] + (t - seg_pref[lo]) < n);
           g[u] = (uint32_t)__ldg(p.pairs + (uint64_t)lo * n + seg_pos[lo] + (t - seg_pref[lo]));
         }
       }
@@ -333,6 +341,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
   if (warp == 0) {   // the greatest candidate id: the group search.c:147-165 never scores
     const uint32_t g = __reduce_max_sync(0xffffffffu, last);
     if (lane == 0) s_gmax = g;
+    MN_CHECK(g < n);
     if (lane < kTables) gmax_word = __ldg(dbw + (uint64_t)g * 32u + lane);
   }
   const long long t_searched = p.stat_pairs ? clock64() : 0;
@@ -383,6 +392,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
           uint32_t lo = cur, hi = run_len, step = 1;   // id(lo - 1) < id_hi (or lo == cur), id(hi) >= id_hi (or hi == run_len)
           while (lo < run_len) {
             const uint32_t probe = min(lo + step - 1, run_len - 1);
+            MN_CHECK(probe < run_len);
             if ((uint32_t)__ldg(run + probe) >= id_hi) {
               hi = probe;
               break;
@@ -392,6 +402,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
           }
           while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
+            MN_CHECK(mid < run_len);
             if ((uint32_t)__ldg(run + mid) < id_hi) lo = mid + 1;
             else hi = mid;
           }
@@ -418,7 +429,9 @@ __global__ void __launch_bounds__(kPairThreads, 3)
     for (uint32_t base = (uint32_t)warp * 32u; base < nuniq; base += kPairThreads) {
       const uint32_t cnt = min(32u, nuniq - base);
       const uint32_t my_g = uniq[base + ((uint32_t)lane < cnt ? lane : 0)];
+      MN_CHECK(my_g < n && base + ((uint32_t)lane < cnt ? lane : 0) < cap);
       const uint32_t my_entry = __ldg(p.sig_entry + my_g);   // in flight with the rows, not after them
+      MN_CHECK(my_entry < p.n_entries);
       uint4 w[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
@@ -438,6 +451,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
         ++deep;
         if (score >= 30u) {                          // MIN_SCORE (search.c:16)
           const uint64_t a = (uint64_t)query * p.n_entries + my_entry;
+          MN_CHECK(a < (uint64_t)p.n_queries * p.n_entries);
           atomicAdd(&p.acc_score[a], score);
           atomicAdd(&p.acc_n[a], 1u);
         }
@@ -458,6 +472,7 @@ __global__ void __launch_bounds__(kPairThreads, 3)
     }
     const uint32_t hits = __popc(__ballot_sync(0xffffffffu, h));
     const uint32_t score = __reduce_add_sync(0xffffffffu, eq);
+    MN_CHECK(qs < gridDim.x && query < p.n_queries);
     if (lane == 0) p.last[qs] = mnemo_lastgroup_dev{1u, gmax, hits, score};
   }
   if (p.stat_pairs && tid == 0) {

@@ -536,7 +536,9 @@ __device__ __forceinline__ void probe_query_signature(const SearchParams& p, con
     const uint32_t slot = fastmod(bucket_key(w), p.size_magic, p.size);
     pr.qword[tid] = w;
     pr.qslot[tid] = slot;
+    MN_CHECK(slot < p.size);
     const uint32_t b = p.start[(uint64_t)tid * p.size + slot], e = p.start[(uint64_t)tid * p.size + slot + 1];
+    MN_CHECK(b <= e && (uint64_t)e <= (uint64_t)kTables * p.n_sigs);
     pr.begin[tid] = b;
     pr.prefix[tid + 1] = e - b;
   }
@@ -581,6 +583,7 @@ __device__ __forceinline__ void probe_query_signature(const SearchParams& p, con
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
         const uint32_t g = __shfl_sync(0xffffffffu, my_g, r);
+        MN_CHECK(g < p.n_sigs);
         w[r] = lane < kTables ? __ldg(dbw + (uint64_t)g * kTables + lane) : 0u;   // lanes >= 25 hold "equal" words
       }
       uint32_t mine = 0;
@@ -607,6 +610,7 @@ __device__ __forceinline__ void probe_query_signature(const SearchParams& p, con
         ++deep_t;
         if (score >= 30u) {                                         // MIN_SCORE (search.c:16)
           const uint64_t a = (uint64_t)query * p.n_entries + p.sig_entry[my_g];
+          MN_CHECK(a < (uint64_t)p.n_queries * p.n_entries);
           atomicAdd(&p.acc_score[a], score);
           atomicAdd(&p.acc_n[a], 1u);
         }
@@ -719,6 +723,7 @@ __device__ __forceinline__ void probe_query_signature(const SearchParams& p, con
         const uint32_t first = pr.begin[k] + b, units = ((first & 3u) + n + 3u) >> 2;
         const uint32_t dst = stage_s + (s_so[pass][k] << 2);
         const uint32_t* src = p.ids + (first & ~3u);
+        MN_CHECK(s_so[pass][k] + 4 * units <= kStageCap && (uint64_t)(first & ~3u) + 4ull * units <= (uint64_t)kTables * p.n_sigs + 4);
         for (uint32_t u = lane; u < units; u += 32)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (u << 4)), "l"(src + (u << 2)) : "memory");
       }
@@ -743,6 +748,7 @@ __device__ __forceinline__ void probe_query_signature(const SearchParams& p, con
       auto visit = [&](uint32_t g) {
         const uint32_t h = g - id_base;
         const uint32_t bit = 1u << (h & 31u);
+        MN_CHECK(g >= id_base && (h >> 5) < kBitmapMaxWords && g < p.n_sigs);
         if (atomicOr(&bitmap[h >> 5], bit) & bit) {
           const uint32_t pos = atomicAdd(&s_ndup, 1u);
           if (pos < kDupCap) dup[pos] = g;
@@ -817,7 +823,8 @@ __device__ __forceinline__ void probe_query_signature(const SearchParams& p, con
               ++deep;
               if (score >= 30 && lane == 0) {
                 const uint64_t a = (uint64_t)query * p.n_entries + p.sig_entry[g];
-                atomicAdd(&p.acc_score[a], score);
+                MN_CHECK(a < (uint64_t)p.n_queries * p.n_entries);
+          atomicAdd(&p.acc_score[a], score);
                 atomicAdd(&p.acc_n[a], 1u);
               }
             }
@@ -871,6 +878,7 @@ __device__ __forceinline__ void probe_query_signature(const SearchParams& p, con
       gmax = max(gmax, g);
       const uint32_t h = (g * 2654435761u) >> bm_shift;
       const uint32_t bit = 1u << (h & 31u);
+      MN_CHECK((h >> 5) < bm_words && g < p.n_sigs);
       const uint32_t old = atomicOr(&bitmap[h >> 5], bit);
       if (old & bit) {
         const uint32_t pos = atomicAdd(&s_ndup, 1u);
@@ -889,6 +897,7 @@ __device__ __forceinline__ void probe_query_signature(const SearchParams& p, con
         const uint32_t first = seg_begin[k], units = ((first & 3u) + n + 3u) >> 2;
         const uint32_t dst = stage_s + (s_so[0][k] << 2);
         const uint32_t* src = p.ids + (first & ~3u);
+        MN_CHECK(s_so[0][k] + 4 * units <= kStageCap && (uint64_t)(first & ~3u) + 4ull * units <= (uint64_t)kTables * p.n_sigs + 4);
         for (uint32_t u = lane; u < units; u += 32)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (u << 4)), "l"(src + (u << 2)) : "memory");
       }
@@ -992,7 +1001,8 @@ __device__ __forceinline__ void probe_query_signature(const SearchParams& p, con
           ++deep;
           if (score >= 30 && lane == 0) {
             const uint64_t a = (uint64_t)query * p.n_entries + p.sig_entry[g];
-            atomicAdd(&p.acc_score[a], score);
+            MN_CHECK(a < (uint64_t)p.n_queries * p.n_entries);
+          atomicAdd(&p.acc_score[a], score);
             atomicAdd(&p.acc_n[a], 1u);
           }
         }
@@ -1068,7 +1078,9 @@ __global__ void __launch_bounds__(256) search_gather_kernel(SearchParams p, uint
   const uint32_t* __restrict__ qwords = reinterpret_cast<const uint32_t*>(p.query_sigs);
   if (tid < kTables) {
     const uint32_t slot = bucket_key(qwords[tid]) % p.size;
+    MN_CHECK(slot < p.size);
     const uint32_t b = p.start[(uint64_t)tid * p.size + slot], e = p.start[(uint64_t)tid * p.size + slot + 1];
+    MN_CHECK(b <= e && (uint64_t)e <= (uint64_t)kTables * p.n_sigs);
     pr.begin[tid] = b;
     pr.prefix[tid + 1] = e - b;
     table_counts[tid] = e - b;
