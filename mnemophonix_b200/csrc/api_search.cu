@@ -31,7 +31,7 @@ struct mnemo_db {
   struct Scratch {
     void* p = nullptr;
     uint64_t bytes = 0;
-  } scratch[20];
+  } scratch[24];
   bool pair_wanted = false;           // the pair index pays for this database (decided at create) but is not built yet
   uint64_t pair_after = 4096;         // ... until this many query signatures have been searched; MNEMO_PAIR_LAZY_AFTER
   uint64_t served_qsigs = 0;
@@ -43,7 +43,7 @@ struct mnemo_db {
 
 enum {   // scratch slots
   kScrQ = 0, kScrQstart, kScrAccS, kScrAccN, kScrLast, kScrStats, kScrTotal, kScrQbase, kScrQcnt, kScrCands, kScrLeaf,
-  kScrSel, kScrSelCnt, kScrOut, kScrHas, kScrHasAll, kScrLists, kScrBack, kScrTodo
+  kScrSel, kScrSelCnt, kScrOut, kScrHas, kScrHasAll, kScrLists, kScrBack, kScrTodo, kScrQsQuery
 };
 
 static cudaError_t scratch_get(mnemo_db* db, int slot, uint64_t bytes, void** out) {
@@ -381,6 +381,11 @@ static cudaError_t probe_tile(mnemo_db* db, ProbeBatch& b, const uint32_t* query
   SearchParams p = base_params(db);
   p.query_sigs = b.d_q + (uint64_t)s0 * kSigLen;
   p.query_start = b.d_qstart;
+  uint32_t* d_qs_query = nullptr;
+  TRY(scratch_get(db, kScrQsQuery, 4ull * ((uint64_t)ns + 1), (void**)&d_qs_query));
+  if (e != cudaSuccess) return e;
+  launch_qs_query(b.d_qstart, nq, ns, d_qs_query, st);
+  p.qs_query = d_qs_query;
   p.n_queries = nq;
   p.acc_score = b.d_acc_s;
   p.acc_n = b.d_acc_n;

@@ -551,7 +551,7 @@ __device__ __forceinline__ void probe_query_signature(const SearchParams& p, con
     for (int k = 0; k < kTables; ++k) pr.prefix[k + 1] += pr.prefix[k];
   __syncthreads();
   const uint32_t L = pr.prefix[kTables];
-  const uint32_t query = find_segment<uint32_t>(p.query_start, p.n_queries, qs);
+  const uint32_t query = __ldg(p.qs_query + qs);   // (a bisection of query_start here was 14 dependent loads per CTA)
   mnemo_lastgroup_dev lg = {0, 0, 0, 0};
   if (L == 0) {
     if (tid == 0) p.last[qs] = lg;
@@ -1096,6 +1096,16 @@ __global__ void __launch_bounds__(256) search_gather_kernel(SearchParams p, uint
     while (k < kTables - 1 && pr.prefix[k + 1] <= i) ++k;
     out[i] = p.ids[pr.begin[k] + (i - pr.prefix[k])];
   }
+}
+
+// query of every query signature, once per batch: the probe kernels read one word instead of bisecting query_start
+__global__ void __launch_bounds__(256) qs_query_kernel(const uint32_t* __restrict__ query_start, uint32_t n_queries,
+                                                       uint32_t n_query_sigs, uint32_t* __restrict__ qs_query) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_query_sigs) qs_query[i] = find_segment<uint32_t>(query_start, n_queries, i);
+}
+void launch_qs_query(const uint32_t* query_start, uint32_t n_queries, uint32_t n_query_sigs, uint32_t* qs_query, cudaStream_t st) {
+  if (n_query_sigs) qs_query_kernel<<<(n_query_sigs + 255) / 256, 256, 0, st>>>(query_start, n_queries, n_query_sigs, qs_query);
 }
 
 void launch_search(const SearchParams& p, uint32_t n_query_sigs, cudaStream_t st) {
