@@ -579,6 +579,8 @@ __device__ __forceinline__ void probe_query_signature(const SearchParams& p, con
     for (uint32_t base = (uint32_t)warp * 32u; base < n; base += kSearchThreads) {
       const uint32_t cnt = min(32u, n - base);
       const uint32_t my_g = lst[base + ((uint32_t)lane < cnt ? lane : 0)];
+      MN_CHECK(my_g < p.n_sigs);
+      const uint32_t my_entry = __ldg(p.sig_entry + my_g);   // in flight with the rows, not after them
       uint32_t w[32];
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
@@ -609,7 +611,7 @@ __device__ __forceinline__ void probe_query_signature(const SearchParams& p, con
       if ((uint32_t)lane < cnt && my_g != g_skip && hits >= 2u) {   // search.c:147-165 (last group never flushed), MIN_BUCKET_MATCH_FOR_DEEP_CHECK
         ++deep_t;
         if (score >= 30u) {                                         // MIN_SCORE (search.c:16)
-          const uint64_t a = (uint64_t)query * p.n_entries + p.sig_entry[my_g];
+          const uint64_t a = (uint64_t)query * p.n_entries + my_entry;
           MN_CHECK(a < (uint64_t)p.n_queries * p.n_entries);
           atomicAdd(&p.acc_score[a], score);
           atomicAdd(&p.acc_n[a], 1u);
