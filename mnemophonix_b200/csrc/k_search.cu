@@ -531,24 +531,31 @@ __device__ __forceinline__ void probe_query_signature(const SearchParams& p, con
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t* __restrict__ qwords = reinterpret_cast<const uint32_t*>(p.query_sigs) + (uint64_t)qs * kTables;
 
-  if (tid < kTables) {
-    const uint32_t w = qwords[tid];
-    const uint32_t slot = fastmod(bucket_key(w), p.size_magic, p.size);
-    pr.qword[tid] = w;
-    pr.qslot[tid] = slot;
-    MN_CHECK(slot < p.size);
-    const uint32_t b = p.start[(uint64_t)tid * p.size + slot], e = p.start[(uint64_t)tid * p.size + slot + 1];
-    MN_CHECK(b <= e && (uint64_t)e <= (uint64_t)kTables * p.n_sigs);
-    pr.begin[tid] = b;
-    pr.prefix[tid + 1] = e - b;
+  if (warp == 0) {   // the 25 probed buckets and the prefix of their lengths (warp scan: one barrier, no serial loop)
+    uint32_t len = 0;
+    if (lane < kTables) {
+      const uint32_t w = qwords[lane];
+      const uint32_t slot = fastmod(bucket_key(w), p.size_magic, p.size);
+      pr.qword[lane] = w;
+      pr.qslot[lane] = slot;
+      MN_CHECK(slot < p.size);
+      const uint32_t b = p.start[(uint64_t)lane * p.size + slot], e = p.start[(uint64_t)lane * p.size + slot + 1];
+      MN_CHECK(b <= e && (uint64_t)e <= (uint64_t)kTables * p.n_sigs);
+      pr.begin[lane] = b;
+      len = e - b;
+    }
+    uint32_t incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane < kTables) pr.prefix[lane + 1] = incl;
+    if (lane == 0) {
+      pr.prefix[0] = 0;
+      s_gmax = 0;
+    }
   }
-  if (tid == 0) {
-    pr.prefix[0] = 0;
-    s_gmax = 0;
-  }
-  __syncthreads();
-  if (tid == 0)
-    for (int k = 0; k < kTables; ++k) pr.prefix[k + 1] += pr.prefix[k];
   __syncthreads();
   const uint32_t L = pr.prefix[kTables];
   const uint32_t query = __ldg(p.qs_query + qs);   // (a bisection of query_start here was 14 dependent loads per CTA)
