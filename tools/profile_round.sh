@@ -18,6 +18,6 @@ ncu --set full --clock-control none --import-source on -k regex:k1_fast -s 1 -c 
     -o $OUT/${TAG}_prof_k1_fast python tools/profile_index.py --runs 2 --fast > $OUT/${TAG}_ncu_k1_fast.log 2>&1
 # 4. the probe and ranking kernels on configs[3] (first 2000 of the 10 000 queries, the whole 10 000-track database)
 python tools/bench_c4_pcm.py --ref-queries 0 --queries 2000 > $OUT/${TAG}_c4_q2000.json 2> $OUT/${TAG}_c4_q2000.err &&
-ncu --set full --clock-control none --import-source on -k 'regex:search_pair|search_probe|search_select|select_merge' -s 3 -c 3 \
+ncu --set full --clock-control none --import-source on -k 'regex:search_pair|search_probe|search_select|select_merge' -s 4 -c 4 \
     -o $OUT/${TAG}_prof_search python tools/bench_c4_pcm.py --ref-queries 0 --queries 2000 > $OUT/${TAG}_ncu_search.log 2>&1
 ls -la $OUT/${TAG}_prof_*.ncu-rep
