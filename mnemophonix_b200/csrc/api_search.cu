@@ -36,7 +36,7 @@ struct mnemo_db {
   uint64_t pair_after = 4096;         // ... until this many query signatures have been searched; MNEMO_PAIR_LAZY_AFTER
   uint64_t served_qsigs = 0;
   uint32_t pair_cap = 4096;           // distinct candidates per round of the pair kernel; MNEMO_PAIR_CAP shrinks it (tests)
-  uint32_t range_ids = 1u << 18;      // ids per pass of the probe's id-range mode; MNEMO_RANGE_IDS shrinks it (tests)
+  uint32_t range_ids = search_range_bits();   // ids per pass of the probe's id-range mode; MNEMO_RANGE_IDS shrinks it (tests)
   uint64_t acc_budget = 1ull << 30;   // bytes of dense accumulators per query tile; MNEMO_ACC_BYTES shrinks it (tests)
   uint32_t dense_nq = 0, dense_nqs = 0;   // query batch held on the device between mnemo_search_dense_begin / _lists
 };
@@ -132,7 +132,7 @@ extern "C" int mnemo_db_create(mnemo_ctx* ctx, const uint8_t* sigs, const uint32
   db->size = table_size ? table_size : (uint32_t)(db->n_sigs / 2);   // lsh.c:61
   if (const char* env = getenv("MNEMO_RANGE_IDS")) {   // test hook: many small id ranges on a small database
     const long v = atol(env);
-    if (v > 0) db->range_ids = (uint32_t)std::min<long>(1L << 18, (v + 127) / 128 * 128);
+    if (v > 0) db->range_ids = (uint32_t)std::min<long>(search_range_bits(), (v + 127) / 128 * 128);
   }
   if (const char* env = getenv("MNEMO_PAIR_CAP")) {   // test hook: id ranges, halving and widening in the pair kernel
     const long v = atol(env);

@@ -465,13 +465,23 @@ cudaError_t launch_pair_build(const uint8_t* sigs, uint64_t n_sigs, uint32_t siz
 constexpr int kSearchThreads = 256;
 constexpr uint32_t kDupCap = 2048;        // short list capacity (ids seen "again")
 constexpr uint32_t kSetCap = 4096;        // hash set slots for de-duplication (power of two, >= 2 * kDupCap)
-constexpr uint32_t kBitmapMaxWords = 8192;    // 32 KB: 64 KB of shared memory per CTA in all, 3 CTAs per SM
+// 16 KB bitmap, 48 KB of dynamic shared memory per CTA, 64 registers: FOUR CTAs per SM.  (8192 words at three CTAs per SM
+// was the round-1 shape; with the big databases on the pair index this kernel serves shards and small databases, where
+// the extra CTA buys 4-9 %: 10.1 -> 9.2 / 14.2 -> 13.4 / 24.9 -> 23.8 ms per 10 k-query batch at 180 k / 380 k / 760 k signatures.)
+#ifndef PROBE_BITMAP_WORDS
+#define PROBE_BITMAP_WORDS 4096
+#endif
+#ifndef PROBE_MIN_BLOCKS
+#define PROBE_MIN_BLOCKS 4
+#endif
+constexpr uint32_t kBitmapMaxWords = PROBE_BITMAP_WORDS;
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kPassCap = 8192;          // candidates per id-space partition (>= 32 bitmap bits each)
 constexpr uint32_t kRangeBits = kBitmapMaxWords * 32;   // ids per pass in range mode: one bitmap bit per id, exact
-constexpr uint32_t kMaxRangePasses = 16;                // id ranges whose tables are held at a time (4.2 M signatures)
+constexpr uint32_t kMaxRangePasses = 16;                // id ranges whose tables are held at a time (2.1 M signatures)
 constexpr uint32_t kStageCap = kSetCap + kDupCap;       // ids of one id range staged in shared memory (the flush's set + uniq areas)
 
+uint32_t search_range_bits() { return kRangeBits; }
 size_t search_smem_bytes() { return sizeof(uint32_t) * (kBitmapMaxWords + kDupCap + kSetCap + kDupCap); }
 
 struct Probe {
@@ -1039,7 +1049,7 @@ __device__ __forceinline__ void probe_query_signature(const SearchParams& p, con
 }
 
 // one CTA per query signature
-__global__ void __launch_bounds__(kSearchThreads, 3) search_probe_kernel(SearchParams p) { probe_query_signature(p, blockIdx.x); }
+__global__ void __launch_bounds__(kSearchThreads, PROBE_MIN_BLOCKS) search_probe_kernel(SearchParams p) { probe_query_signature(p, blockIdx.x); }
 
 // Per query: compact the non-zero per-entry accumulators into candidate records, ascending entry.
 __global__ void __launch_bounds__(256) search_compact_kernel(const uint32_t* __restrict__ acc_score,

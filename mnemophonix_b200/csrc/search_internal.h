@@ -91,7 +91,7 @@ struct SearchParams {
   uint32_t div_inv, div_shift, div_thr;   // divisibility by size (same_slot, k_search.cu)
   uint32_t n_entries;            // entries in this shard
   uint32_t n_sigs;               // signatures in this shard
-  uint32_t range_ids;            // ids per pass of the probe's id-range mode (multiple of 128, <= 2^18)
+  uint32_t range_ids;            // ids per pass of the probe's id-range mode (multiple of 128, <= search_range_bits())
   const uint8_t* query_sigs;     // [n_query_sigs][100]
   const uint32_t* query_start;   // [n_queries + 1]
   const uint32_t* qs_query;      // [n_query_sigs] query of every query signature (k_search.cu: launch_qs_query)
@@ -109,6 +109,7 @@ cudaError_t launch_lsh_build(const uint8_t* sigs, uint64_t n_sigs, const uint32_
                              uint32_t size, uint32_t* counts, uint32_t* start, uint32_t* scan_copy, uint32_t* block_sums,
                              uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, void* temp, size_t temp_bytes,
                              uint32_t* ids, uint32_t* sig_entry, cudaStream_t st);
+uint32_t search_range_bits();   // ids per pass of the streaming kernel's id-range mode (one bitmap bit per id)
 void launch_search(const SearchParams& p, uint32_t n_query_sigs, cudaStream_t st);
 void launch_qs_query(const uint32_t* query_start, uint32_t n_queries, uint32_t n_query_sigs, uint32_t* qs_query, cudaStream_t st);
 // pair-index path (k_pairprobe.cu): candidates from the pair index instead of the probed buckets
